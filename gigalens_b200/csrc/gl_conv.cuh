@@ -1,0 +1,234 @@
+// gl_conv.cuh -- PSF convolution fused with ss x ss mean pooling, the pixel likelihood, and the
+// adjoint of all three (reference: src/gigalens/tf/simulator.py:142-156, tf/model.py:91-101).
+//
+// conv2d(SAME, stride 1, K x K) followed by avg_pool(ss) is ONE stride-ss correlation with the
+// folded kernel Keff = box_ss * K of side E = K + ss - 1 (3.7x fewer MACs at K=25, ss=2).  Written
+// in polyphase form that is ss^2 stride-1 correlations with A x A taps, A = ceil(E/ss):
+//
+//   out[oy][ox] = sum_{py,px} sum_{a,b<A} W[py][px][a][b] * I_{py,px}[oy+a][ox+b],
+//   I_{py,px}[r][c] = S[ss*r + py - pad][ss*c + px - pad]   (zero outside the image),
+//
+// and the adjoint is, per phase, the same stride-1 correlation of the zero-padded dL/d(out) with
+// the flipped taps.  Both directions share corr_rows(): each thread owns an RY x RX register tile
+// of outputs, walks the RY+A-1 input rows of its strip once (RX+A-1 floats per row, LDS.128) and
+// applies each row to every output row it reaches; tap weights are broadcast LDS.128.  In the
+// steady state ~90% of issued instructions are FFMA (FP32-FMA bound; north_star forbids tensor
+// cores here), and HBM sees each ss pixel once per direction.
+#pragma once
+#include <cuda_runtime.h>
+
+#define GLC_RX 4
+#define GLC_RY 5
+
+struct GlConvGeom {
+  int n;        // image side (pooled)
+  int hs;       // n * ss
+  int ss;
+  int A;        // taps per phase (template value actually used; weights zero-padded up to it)
+  int pad;      // SAME padding of the K x K kernel: (K-1)/2
+  int ntx, nty; // thread tiles per CTA tile in x / y
+  int tw, th;   // CTA tile size in outputs: ntx*RX, nty*RY
+  int tiles_x, tiles_y;
+  int in_rows, in_pitch;   // smem input tile: rows = th + A - 1, pitch = roundup4(tw + A - 1)
+  int wpitch;   // roundup4(A)
+  int rc0;      // adjoint only: first padded-phase row/column (pad / ss)
+};
+
+// acc[r][c] += sum_{a,b} w[a][b] * in[(r+a)*pitch + c + b]   for the thread's strip origin `in`.
+template <int A>
+__device__ __forceinline__ void corr_rows(const float* __restrict__ in, int pitch, const float* __restrict__ w, int wpitch,
+                                          float (&acc)[GLC_RY][GLC_RX]) {
+  constexpr int SL = (GLC_RX + A - 1 + 3) & ~3;   // strip length rounded up to float4
+  constexpr int WL = (A + 3) & ~3;
+#pragma unroll 1
+  for (int row = 0; row < GLC_RY + A - 1; ++row) {
+    float strip[SL];
+    const float4* src = reinterpret_cast<const float4*>(in + row * pitch);
+#pragma unroll
+    for (int v = 0; v < SL / 4; ++v) {
+      float4 t = src[v];
+      strip[4 * v] = t.x; strip[4 * v + 1] = t.y; strip[4 * v + 2] = t.z; strip[4 * v + 3] = t.w;
+    }
+#pragma unroll
+    for (int r = 0; r < GLC_RY; ++r) {
+      const int a = row - r;
+      if (a >= 0 && a < A) {
+        float wt[WL];
+        const float4* wsrc = reinterpret_cast<const float4*>(w + a * wpitch);
+#pragma unroll
+        for (int v = 0; v < WL / 4; ++v) {
+          float4 t = wsrc[v];
+          wt[4 * v] = t.x; wt[4 * v + 1] = t.y; wt[4 * v + 2] = t.z; wt[4 * v + 3] = t.w;
+        }
+#pragma unroll
+        for (int b = 0; b < A; ++b)
+#pragma unroll
+          for (int c = 0; c < GLC_RX; ++c) acc[r][c] = fmaf(wt[b], strip[c + b], acc[r][c]);
+      }
+    }
+  }
+}
+
+struct GlLikeArgs {
+  const float* observed;    // [n*n]
+  const float* error_map;   // [n*n] or null
+  const unsigned char* mask;  // [n*n] or null
+  float bg2;                // background_rms^2
+  float inv_exp;            // 1 / exp_time
+  int enabled;
+};
+
+// Forward: ss image -> pooled image (x scale), optional likelihood partial sums and dL/d(image).
+//   grid = (tiles_x * tiles_y, bs), block = ntx*nty threads (rounded up to a warp multiple)
+//   part [bs][tiles][2] = (chi2, normalization) partial sums of this tile
+template <int A>
+__global__ void __launch_bounds__(256) k_conv_fwd(GlConvGeom g, const float* __restrict__ ss_img, const float* __restrict__ wts,
+                                                  float scale, float* __restrict__ img, GlLikeArgs like,
+                                                  float* __restrict__ part, float* __restrict__ gimg) {
+  extern __shared__ __align__(16) float smem[];
+  const int nph = g.ss * g.ss;
+  const int phase_size = g.in_rows * g.in_pitch;
+  float* s_in = smem;                              // [nph][in_rows][in_pitch]
+  float* s_w = smem + nph * phase_size;            // [nph][A][wpitch]
+  __shared__ float s_red[2][8];
+
+  const int tile = blockIdx.x, b = blockIdx.y;
+  const int oy0 = (tile / g.tiles_x) * g.th, ox0 = (tile % g.tiles_x) * g.tw;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+
+  for (int i = tid; i < nph * A * g.wpitch; i += nthr) s_w[i] = wts[i];
+  // input tile: global rows ss*oy0 - pad .. , de-interleaved by phase on the way in
+  {
+    const int grows = g.ss * g.in_rows, gcols = g.ss * g.in_pitch;
+    const int gi0 = g.ss * oy0 - g.pad, gj0 = g.ss * ox0 - g.pad;
+    const float* src = ss_img + (size_t)b * g.hs * g.hs;
+    for (int e = tid; e < grows * gcols; e += nthr) {
+      const int li = e / gcols, lj = e - li * gcols;
+      const int gi = gi0 + li, gj = gj0 + lj;
+      float v = 0.f;
+      if (gi >= 0 && gi < g.hs && gj >= 0 && gj < g.hs) v = __ldg(src + (size_t)gi * g.hs + gj);
+      const int r = li / g.ss, py = li - r * g.ss, c = lj / g.ss, px = lj - c * g.ss;
+      s_in[(py * g.ss + px) * phase_size + r * g.in_pitch + c] = v;
+    }
+  }
+  __syncthreads();
+
+  const int ty = tid / g.ntx, tx = tid - ty * g.ntx;
+  const bool active = ty < g.nty;
+  float acc[GLC_RY][GLC_RX];
+#pragma unroll
+  for (int r = 0; r < GLC_RY; ++r)
+#pragma unroll
+    for (int c = 0; c < GLC_RX; ++c) acc[r][c] = 0.f;
+  if (active) {
+    const int origin = ty * GLC_RY * g.in_pitch + tx * GLC_RX;
+    for (int ph = 0; ph < nph; ++ph)
+      corr_rows<A>(s_in + ph * phase_size + origin, g.in_pitch, s_w + ph * A * g.wpitch, g.wpitch, acc);
+  }
+
+  float chi2 = 0.f, norm = 0.f;
+  if (active) {
+#pragma unroll
+    for (int r = 0; r < GLC_RY; ++r) {
+      const int oy = oy0 + ty * GLC_RY + r;
+#pragma unroll
+      for (int c = 0; c < GLC_RX; ++c) {
+        const int ox = ox0 + tx * GLC_RX + c;
+        if (oy < g.n && ox < g.n) {
+          const float v = acc[r][c] * scale;
+          const size_t o = (size_t)oy * g.n + ox;
+          if (img) img[(size_t)b * g.n * g.n + o] = v;
+          if (like.enabled) {
+            const float m = like.mask ? (like.mask[o] ? 1.f : 0.f) : 1.f;
+            const float res = v - like.observed[o];
+            float var, dvar;
+            if (like.error_map) { const float e = like.error_map[o]; var = e * e; dvar = 0.f; }
+            else {
+              // err = sqrt(bg^2 + I/t), var = err^2 (tf/model.py:95-98); negative => NaN like the reference
+              const float e = sqrtf(like.bg2 + v * like.inv_exp); var = e * e; dvar = like.inv_exp;
+            }
+            const float q = res / sqrtf(var);
+            chi2 += q * q * m;
+            norm += logf(6.283185307179586f * var) * m;
+            if (gimg) {
+              // d(-0.5*(chi2+norm))/dI
+              const float gi = -0.5f * m * (2.f * res / var - (res * res) / (var * var) * dvar + dvar / var);
+              gimg[(size_t)b * g.n * g.n + o] = gi;
+            }
+          }
+        }
+      }
+    }
+  }
+  if (like.enabled && part) {
+    for (int off = 16; off > 0; off >>= 1) {
+      chi2 += __shfl_xor_sync(0xffffffffu, chi2, off);
+      norm += __shfl_xor_sync(0xffffffffu, norm, off);
+    }
+    const int warp = tid >> 5, lane = tid & 31, nw = (nthr + 31) >> 5;
+    if (lane == 0) { s_red[0][warp] = chi2; s_red[1][warp] = norm; }
+    __syncthreads();
+    if (tid == 0) {
+      float c2 = 0.f, nm = 0.f;
+      for (int w2 = 0; w2 < nw; ++w2) { c2 += s_red[0][w2]; nm += s_red[1][w2]; }
+      float* p = part + ((size_t)b * gridDim.x + tile) * 2;
+      p[0] = c2; p[1] = nm;
+    }
+  }
+}
+
+// Adjoint: dL/d(image) [bs][n][n] -> dL/d(ss image) [bs][hs][hs]  (x scale).
+//   Work space is the padded-phase grid (r, c): ss pixel (i, j) = (ss*r + py - pad, ss*c + px - pad).
+//   grid = (tiles_x * tiles_y, bs) over r,c in [0, nr) with nr = ceil((hs + pad) / ss).
+//   wts here are the flipped taps: wflip[ph][a'][b'] = W[ph][A-1-a'][A-1-b'].
+template <int A>
+__global__ void __launch_bounds__(256) k_conv_bwd(GlConvGeom g, const float* __restrict__ gimg, const float* __restrict__ wts,
+                                                  float scale, const unsigned char* __restrict__ ss_mask,
+                                                  float* __restrict__ gss) {
+  extern __shared__ __align__(16) float smem[];
+  const int nph = g.ss * g.ss;
+  float* s_in = smem;                                   // [in_rows][in_pitch]  zero-padded dL/d(image)
+  float* s_w = smem + g.in_rows * g.in_pitch;           // [nph][A][wpitch]
+  const int tile = blockIdx.x, b = blockIdx.y;
+  const int r0 = g.rc0 + (tile / g.tiles_x) * g.th, c0 = g.rc0 + (tile % g.tiles_x) * g.tw;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+
+  for (int i = tid; i < nph * A * g.wpitch; i += nthr) s_w[i] = wts[i];
+  {
+    const float* src = gimg + (size_t)b * g.n * g.n;
+    for (int e = tid; e < g.in_rows * g.in_pitch; e += nthr) {
+      const int li = e / g.in_pitch, lj = e - li * g.in_pitch;
+      const int oy = r0 + li - (A - 1), ox = c0 + lj - (A - 1);
+      float v = 0.f;
+      if (oy >= 0 && oy < g.n && ox >= 0 && ox < g.n) v = __ldg(src + (size_t)oy * g.n + ox);
+      s_in[e] = v;
+    }
+  }
+  __syncthreads();
+  const int ty = tid / g.ntx, tx = tid - ty * g.ntx;
+  if (ty >= g.nty) return;
+  const int origin = ty * GLC_RY * g.in_pitch + tx * GLC_RX;
+  float* dst = gss + (size_t)b * g.hs * g.hs;
+  for (int ph = 0; ph < nph; ++ph) {
+    const int py = ph / g.ss, px = ph - py * g.ss;
+    float acc[GLC_RY][GLC_RX];
+#pragma unroll
+    for (int r = 0; r < GLC_RY; ++r)
+#pragma unroll
+      for (int c = 0; c < GLC_RX; ++c) acc[r][c] = 0.f;
+    corr_rows<A>(s_in + origin, g.in_pitch, s_w + ph * A * g.wpitch, g.wpitch, acc);
+#pragma unroll
+    for (int r = 0; r < GLC_RY; ++r) {
+      const int i = g.ss * (r0 + ty * GLC_RY + r) + py - g.pad;
+#pragma unroll
+      for (int c = 0; c < GLC_RX; ++c) {
+        const int j = g.ss * (c0 + tx * GLC_RX + c) + px - g.pad;
+        if (i >= 0 && i < g.hs && j >= 0 && j < g.hs) {
+          float v = acc[r][c] * scale;
+          if (ss_mask && !ss_mask[(size_t)i * g.hs + j]) v = 0.f;
+          dst[(size_t)i * g.hs + j] = v;
+        }
+      }
+    }
+  }
+}

@@ -1,0 +1,783 @@
+// gl_kernels.cu -- sm_100a kernels and the C ABI of libgigalens_b200.so (include/gigalens_b200.h).
+//
+// Data flow of one log-prob + gradient evaluation of a batch (all fp32, one stream):
+//
+//   z[bs][d] --k_sample_fwd--> params[P][bs], derived[bs][ND], logprior[bs]
+//   derived  --k_raytrace_fwd--> ss[bs][hs][hs]                  (ray-shoot + light, NaN scrub)
+//   ss       --k_conv_fwd-----> image[bs][n][n], like partials, dL/dimage
+//   dL/dimage--k_conv_bwd-----> dL/dss[bs][hs][hs]
+//   dL/dss   --k_raytrace_bwd-> gpart[bs][chunks][NG]             (recompute + hand adjoint)
+//   gpart    --k_sample_bwd---> dparams[P][bs] / dz[bs][d], loglike, red_chi2, logp
+//
+// No framework autodiff graph and no CPU fallback anywhere: every entry point needs the GPU.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "gl_build.h"
+#include "gl_conv.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// error handling / bookkeeping
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static int64_t g_launch_count = 0;
+
+static int gl_fail(const std::string& msg) { g_last_error = msg; return 1; }
+#define GL_CUDA(call)                                                                              \
+  do {                                                                                             \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess) return gl_fail(std::string(#call) + ": " + cudaGetErrorString(_e));     \
+  } while (0)
+#define GL_LAUNCH_CHECK(name)                                                                      \
+  do {                                                                                             \
+    ++g_launch_count;                                                                              \
+    cudaError_t _e = cudaGetLastError();                                                           \
+    if (_e != cudaSuccess) return gl_fail(std::string("launch ") + name + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// prior / bijector leaves
+// ---------------------------------------------------------------------------------------------
+struct GlLeaf { int dist; int slot; float a, b, low, high, log_norm; };
+
+__device__ __forceinline__ float gl_softplus(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }
+__device__ __forceinline__ float gl_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
+
+// x = bijector(z); lp = log p(x) + log|dx/dz|; also d x/d z and d lp/d z.
+__device__ __forceinline__ void gl_leaf_eval(const GlLeaf& L, float z, float& x, float& lp, float& dxdz, float& dlpdz) {
+  const float LOG_2PI = 1.8378770664093453f;
+  switch (L.dist) {
+    case GL_DIST_NORMAL: {
+      x = z; dxdz = 1.f;
+      const float u = (x - L.a) / L.b;
+      lp = -0.5f * u * u - 0.5f * LOG_2PI - logf(L.b);
+      dlpdz = -u / L.b;
+    } break;
+    case GL_DIST_LOGNORMAL: {
+      x = expf(z); dxdz = x;
+      // log x = z exactly: -log x - log s - .5 log 2pi - .5 ((log x - m)/s)^2 + fldj(z) = z
+      const float lx = logf(x);
+      const float u = (lx - L.a) / L.b;
+      lp = -lx - logf(L.b) - 0.5f * LOG_2PI - 0.5f * u * u + z;
+      dlpdz = -u / L.b;   // (-1 + 1) from -log x + fldj cancel
+    } break;
+    default: {  // Uniform / TruncatedNormal: Sigmoid(low, high)
+      const float lo = (L.dist == GL_DIST_UNIFORM) ? L.a : L.low;
+      const float hi = (L.dist == GL_DIST_UNIFORM) ? L.b : L.high;
+      const float diff = hi - lo;
+      const float sg = gl_sigmoid(z), sgm = gl_sigmoid(-z);
+      x = (z < 0.f) ? lo + diff * sg : hi - diff * sgm;
+      dxdz = diff * sg * sgm;
+      const float fldj = logf(diff) - gl_softplus(-z) - gl_softplus(z);
+      const float dfldj = sgm - sg;
+      if (L.dist == GL_DIST_UNIFORM) {
+        lp = -logf(diff) + fldj;
+        dlpdz = dfldj;
+      } else {
+        const float u = (x - L.a) / L.b;
+        lp = -0.5f * u * u - 0.5f * LOG_2PI - logf(L.b) - L.log_norm + fldj;
+        dlpdz = -u / L.b * dxdz + dfldj;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-sample kernels
+// ---------------------------------------------------------------------------------------------
+// z -> params (+ logprior); one thread per sample.
+__global__ void k_unconstrain(int bs, int d, const GlLeaf* __restrict__ leaves, const float* __restrict__ z,
+                              float* __restrict__ params, float* __restrict__ logprior) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= bs) return;
+  float lp = 0.f;
+  for (int k = 0; k < d; ++k) {
+    const GlLeaf L = leaves[k];
+    float x, l, dx, dl;
+    gl_leaf_eval(L, z[(size_t)b * d + k], x, l, dx, dl);
+    lp += l;
+    if (params && L.slot >= 0) params[(size_t)L.slot * bs + b] = x;
+  }
+  if (logprior) logprior[b] = lp;
+}
+
+// batch maximum of the EPL series ratio f (epl.py:33,37) for the reference-exact trip count
+__global__ void k_epl_fmax(GlProgram P, int bs, const float* __restrict__ params, const float* __restrict__ member_factor,
+                           int* __restrict__ fmax_bits) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= bs) return;
+  for (int i = 0; i < P.n_lens; ++i) {
+    if (P.prof[i].type != GLT_EPL) continue;
+    float raw[GL_MAX_RAW];
+    gl_gather_raw<float, float>(P.prof[i], params, bs, b, member_factor, 0, raw);
+    float phi, q, c;
+    ellip_fwd(raw[2], raw[3], 1.f, phi, q, c);
+    const float f = (1.f - q) / (1.f + q);
+    if (f > 0.f) atomicMax(fmax_bits + i, __float_as_int(f));   // f >= 0: int order == float order
+  }
+}
+
+// params -> derived vector; one thread per sample.
+__global__ void k_prep(GlProgram P, int bs, const float* __restrict__ params, const float* __restrict__ member_factor,
+                       const float* __restrict__ epl_fmax, float* __restrict__ derived) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= bs) return;
+  gl_sample_prep<float, float>(P, params, bs, b, member_factor, epl_fmax, derived + (size_t)b * P.der_total);
+}
+
+// partial sums -> loglike, red_chi2, dparams / dz, logp; one thread per sample.
+__global__ void k_sample_bwd(GlProgram P, int bs, const float* __restrict__ params, const float* __restrict__ member_factor,
+                             const float* __restrict__ derived, const float* __restrict__ gpart, int nchunk,
+                             float* __restrict__ gsum /*[bs][g_total] scratch*/, const float* __restrict__ like_part,
+                             int ntile, float n_pix_used, float* __restrict__ loglike, float* __restrict__ red_chi2,
+                             float* __restrict__ dparams, int d, const GlLeaf* __restrict__ leaves,
+                             const float* __restrict__ z, const float* __restrict__ logprior, float* __restrict__ logp,
+                             float* __restrict__ dz) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= bs) return;
+  float chi2 = 0.f, norm = 0.f;
+  for (int t = 0; t < ntile; ++t) {
+    chi2 += like_part[((size_t)b * ntile + t) * 2];
+    norm += like_part[((size_t)b * ntile + t) * 2 + 1];
+  }
+  const float ll = -0.5f * (chi2 + norm);
+  if (loglike) loglike[b] = ll;
+  if (red_chi2) red_chi2[b] = chi2 / n_pix_used;
+  if (logp) logp[b] = ll + (logprior ? logprior[b] : 0.f);
+  if (!dparams) return;
+  float* g = gsum + (size_t)b * P.g_total;
+  for (int k = 0; k < P.g_total; ++k) {
+    float s = 0.f;
+    for (int c = 0; c < nchunk; ++c) s += gpart[((size_t)b * nchunk + c) * P.g_total + k];
+    g[k] = s;
+  }
+  gl_sample_prep_bwd<float, float>(P, params, bs, b, member_factor, derived + (size_t)b * P.der_total, g, dparams);
+  if (dz) {
+    for (int k = 0; k < d; ++k) {
+      const GlLeaf L = leaves[k];
+      float x, l, dx, dl;
+      gl_leaf_eval(L, z[(size_t)b * d + k], x, l, dx, dl);
+      const float gp = (L.slot >= 0) ? dparams[(size_t)L.slot * bs + b] : 0.f;
+      dz[(size_t)b * d + k] = gp * dx + dl;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ray-shooting + light: forward and adjoint.  One thread per (sample, ss pixel), PPT pixels per
+// thread per batch for ILP, per-sample derived constants staged in shared memory.
+//   grid = (chunks, bs); a CTA walks pixel batches  chunk, chunk + chunks, ...
+// ---------------------------------------------------------------------------------------------
+#define GLK_THREADS 256
+
+template <int PPT>
+__global__ void __launch_bounds__(GLK_THREADS) k_raytrace_fwd(GlProgram P, int npix, const float* __restrict__ grid_x,
+                                                              const float* __restrict__ grid_y,
+                                                              const unsigned char* __restrict__ ss_mask,
+                                                              const float* __restrict__ derived, int no_deflection,
+                                                              float* __restrict__ ss_img) {
+  extern __shared__ __align__(16) float s_der[];
+  const int b = blockIdx.y;
+  const float* dsrc = derived + (size_t)b * P.der_total;
+  for (int i = threadIdx.x; i < P.der_total; i += blockDim.x) s_der[i] = dsrc[i];
+  __syncthreads();
+  const int per_batch = GLK_THREADS * PPT;
+  const int nbatch = (npix + per_batch - 1) / per_batch;
+  float* dst = ss_img + (size_t)b * npix;
+  for (int batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
+    float x[PPT], y[PPT], v[PPT];
+    int pix[PPT];
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+      pix[j] = batch * per_batch + j * GLK_THREADS + threadIdx.x;
+      const int p = pix[j] < npix ? pix[j] : 0;
+      x[j] = __ldg(grid_x + p); y[j] = __ldg(grid_y + p);
+    }
+    gl_pix_image<float, PPT>(P, s_der, x, y, no_deflection != 0, v);
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+      if (pix[j] < npix) {
+        float o = v[j];
+        if (o != o) o = 0.f;                                   // tf.where(is_nan(img), 0, img)  (tf/simulator.py:140)
+        if (ss_mask && !ss_mask[pix[j]]) o = 0.f;              // pixels outside pix_region are never evaluated (:34-44)
+        dst[pix[j]] = o;
+      }
+    }
+  }
+}
+
+struct DevFlush {
+  float* s_acc;   // this warp's accumulator row in shared memory
+  int lane;
+  __device__ __forceinline__ void operator()(const float* acc, int n, int off) {
+#pragma unroll
+    for (int k = 0; k < GL_MAX_DVARS; ++k) {
+      if (k < n) {
+        float v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) s_acc[off + k] += v;
+      }
+    }
+  }
+};
+
+template <int PPT>
+__global__ void __launch_bounds__(GLK_THREADS) k_raytrace_bwd(GlProgram P, int npix, const float* __restrict__ grid_x,
+                                                              const float* __restrict__ grid_y,
+                                                              const unsigned char* __restrict__ ss_mask,
+                                                              const float* __restrict__ derived, int no_deflection,
+                                                              const float* __restrict__ gss, float* __restrict__ gpart) {
+  extern __shared__ __align__(16) float smem[];
+  float* s_der = smem;                               // [der_total]
+  float* s_acc = smem + P.der_total;                 // [nwarps][g_total]
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = GLK_THREADS / 32;
+  const float* dsrc = derived + (size_t)b * P.der_total;
+  for (int i = threadIdx.x; i < P.der_total; i += blockDim.x) s_der[i] = dsrc[i];
+  for (int i = threadIdx.x; i < nw * P.g_total; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  DevFlush flush{s_acc + warp * P.g_total, lane};
+  const int per_batch = GLK_THREADS * PPT;
+  const int nbatch = (npix + per_batch - 1) / per_batch;
+  const float* gsrc = gss + (size_t)b * npix;
+  for (int batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
+    float x[PPT], y[PPT], gs[PPT];
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+      const int pix = batch * per_batch + j * GLK_THREADS + threadIdx.x;
+      const bool ok = pix < npix && (!ss_mask || ss_mask[pix]);
+      const int p = pix < npix ? pix : 0;
+      x[j] = __ldg(grid_x + p); y[j] = __ldg(grid_y + p);
+      gs[j] = ok ? __ldg(gsrc + p) : 0.f;
+    }
+    gl_pix_image_bwd<float, PPT>(P, s_der, x, y, gs, no_deflection != 0, flush);
+  }
+  __syncthreads();
+  float* out = gpart + ((size_t)b * gridDim.x + blockIdx.x) * P.g_total;
+  for (int k = threadIdx.x; k < P.g_total; k += blockDim.x) {
+    float s = 0.f;
+    for (int w = 0; w < nw; ++w) s += s_acc[w * P.g_total + k];
+    out[k] = s;
+  }
+}
+
+// deflection / beta / surface brightness at arbitrary points shared by all samples
+// mode 0: beta (x - alpha), 1: alpha, 2: surface brightness (lens light at theta + source at beta)
+__global__ void k_points(GlProgram P, int npts, const float* __restrict__ px, const float* __restrict__ py,
+                         const float* __restrict__ derived, int mode, float* __restrict__ out0, float* __restrict__ out1) {
+  extern __shared__ __align__(16) float s_der[];
+  const int b = blockIdx.y;
+  const float* dsrc = derived + (size_t)b * P.der_total;
+  for (int i = threadIdx.x; i < P.der_total; i += blockDim.x) s_der[i] = dsrc[i];
+  __syncthreads();
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < npts; p += gridDim.x * blockDim.x) {
+    float x[1] = {px[p]}, y[1] = {py[p]};
+    if (mode == 2) {
+      float v[1];
+      gl_pix_image<float, 1>(P, s_der, x, y, false, v);
+      out0[(size_t)b * npts + p] = v[0];
+    } else {
+      float bx[1], by[1];
+      gl_pix_beta<float, 1>(P, s_der, x, y, bx, by);
+      if (mode == 1) { bx[0] = x[0] - bx[0]; by[0] = y[0] - by[0]; }
+      out0[(size_t)b * npts + p] = bx[0];
+      out1[(size_t)b * npts + p] = by[0];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------------------------
+struct gl_plan {
+  int device = 0;
+  int bs = 0;
+  GlProgram prog;
+  int n = 0, ss = 1, hs = 0, npix = 0;
+  float conversion_factor = 1.f;
+  bool has_epl = false;
+  int epl_batch_max = 0;
+  // static inputs
+  float* d_grid_x = nullptr; float* d_grid_y = nullptr;
+  unsigned char* d_ss_mask = nullptr; unsigned char* d_mask = nullptr;
+  float* d_member_factor = nullptr;
+  float* d_wf = nullptr; float* d_wb = nullptr;     // forward / flipped taps [nph][A][wpitch]
+  int A = 1, pad = 0;
+  GlConvGeom gf, gb;
+  int bwd_rc_start = 0;
+  size_t smem_cf = 0, smem_cb = 0;
+  int conv_threads_f = 0, conv_threads_b = 0;
+  // likelihood
+  bool has_like = false;
+  float* d_obs = nullptr; float* d_err = nullptr;
+  float bg2 = 0.f, inv_exp = 0.f, n_pix_used = 0.f;
+  // prior
+  int d = 0;
+  GlLeaf* d_leaves = nullptr;
+  // workspace
+  float* d_params = nullptr;     // [P][bs] (for the z entry points)
+  float* d_dparams = nullptr;    // [P][bs]
+  float* d_derived = nullptr;    // [bs][der_total]
+  float* d_ss = nullptr;         // [bs][npix]  ss image, reused for dL/dss
+  float* d_img = nullptr;        // [bs][n*n]
+  float* d_gimg = nullptr;       // [bs][n*n]
+  float* d_like_part = nullptr;  // [bs][tiles][2]
+  float* d_gpart = nullptr;      // [bs][chunks][g_total]
+  float* d_gsum = nullptr;       // [bs][g_total]
+  float* d_logprior = nullptr;   // [bs]
+  float* d_fmax = nullptr;       // [GL_MAX_PROF]
+  float* d_z = nullptr; float* d_logp = nullptr; float* d_chi = nullptr; float* d_dz = nullptr;  // *_host staging
+  int chunks = 1;
+  int sm_count = 148;
+};
+
+static void gl_free_plan(gl_plan* p) {
+  if (!p) return;
+  cudaSetDevice(p->device);
+  float* fl[] = {p->d_grid_x, p->d_grid_y, p->d_member_factor, p->d_wf, p->d_wb, p->d_obs, p->d_err, p->d_params,
+                 p->d_dparams, p->d_derived, p->d_ss, p->d_img, p->d_gimg, p->d_like_part, p->d_gpart, p->d_gsum,
+                 p->d_logprior, p->d_fmax, p->d_z, p->d_logp, p->d_chi, p->d_dz};
+  for (float* q : fl) if (q) cudaFree(q);
+  if (p->d_ss_mask) cudaFree(p->d_ss_mask);
+  if (p->d_mask) cudaFree(p->d_mask);
+  if (p->d_leaves) cudaFree(p->d_leaves);
+  delete p;
+}
+
+template <class T>
+static cudaError_t gl_upload(T** dst, const T* src, size_t count) {
+  cudaError_t e = cudaMalloc((void**)dst, count * sizeof(T));
+  if (e != cudaSuccess) return e;
+  return cudaMemcpy(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+static const int kConvA[] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 11, 13, 16, 20, 25, 32};
+
+// choose the CTA tile of the conv kernels: cover `extent` outputs with ntx*RX (nty*RY) per tile,
+// at most 256 threads and a bounded smem footprint
+static void gl_pick_tiles(int extent, int A, int nph_in, GlConvGeom& g) {
+  auto ceil_div = [](int a, int b) { return (a + b - 1) / b; };
+  int best_ntx = 1, best_nty = 1; double best_cost = 1e30;
+  for (int tiles_x = 1; tiles_x <= 64; ++tiles_x) {
+    const int ntx = ceil_div(ceil_div(extent, tiles_x), GLC_RX);
+    for (int tiles_y = 1; tiles_y <= 64; ++tiles_y) {
+      const int nty = ceil_div(ceil_div(extent, tiles_y), GLC_RY);
+      const int threads = ntx * nty;
+      if (threads > 256) continue;
+      const int in_rows = nty * GLC_RY + A - 1, in_pitch = (ntx * GLC_RX + A - 1 + 3) & ~3;
+      const size_t smem = (size_t)(nph_in * in_rows * in_pitch + 16 * A * ((A + 3) & ~3)) * 4;
+      if (smem > 100 * 1024) continue;
+      const int warps = ceil_div(threads, 32);
+      // cost: issued warp-work (incl. idle lanes / edge waste) + halo traffic
+      const double work = (double)tiles_x * tiles_y * warps * 32;
+      const double halo = (double)tiles_x * tiles_y * in_rows * in_pitch * nph_in / 169.0;
+      const double small = threads < 96 ? 1.15 : 1.0;
+      const double cost = (work + halo) * small;
+      if (cost < best_cost) { best_cost = cost; best_ntx = ntx; best_nty = nty; g.tiles_x = tiles_x; g.tiles_y = tiles_y; }
+    }
+  }
+  g.ntx = best_ntx; g.nty = best_nty;
+  g.tw = g.ntx * GLC_RX; g.th = g.nty * GLC_RY;
+  g.tiles_x = ceil_div(extent, g.tw); g.tiles_y = ceil_div(extent, g.th);
+  g.in_rows = g.th + A - 1; g.in_pitch = (g.tw + A - 1 + 3) & ~3;
+}
+
+extern "C" {
+
+const char* gl_last_error(void) { return g_last_error.c_str(); }
+int32_t gl_abi_version(void) { return GL_ABI_VERSION; }
+int64_t gl_launch_count(void) { return g_launch_count; }
+int32_t gl_plan_depth(const gl_plan* plan) { return plan ? plan->prog.depth : 0; }
+
+void gl_plan_destroy(gl_plan* plan) { gl_free_plan(plan); }
+
+int gl_plan_create(const gl_model_desc* model, const gl_sim_config* sim, int32_t bs, int32_t device, gl_plan** out) {
+  if (!out) return gl_fail("gl_plan_create: out is NULL");
+  *out = nullptr;
+  if (!model || !sim) return gl_fail("gl_plan_create: NULL descriptor");
+  if (bs <= 0) return gl_fail("gl_plan_create: bs must be positive");
+  if (sim->num_pix <= 0 || sim->supersample <= 0) return gl_fail("gl_plan_create: bad num_pix / supersample");
+  if (!sim->grid_x || !sim->grid_y) return gl_fail("gl_plan_create: grid_x / grid_y are required");
+  if (sim->psf && (sim->psf_n <= 0 || sim->psf_n > 255)) return gl_fail("gl_plan_create: bad psf_n");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return gl_fail("gl_plan_create: no CUDA device available (this library has no CPU path)");
+  if (device < 0 || device >= ndev) return gl_fail("gl_plan_create: device index out of range");
+  GL_CUDA(cudaSetDevice(device));
+
+  GlBuilt built;
+  std::string err = gl_build_program(model, built);
+  if (!err.empty()) return gl_fail("gl_plan_create: " + err);
+  for (int i = 0; i < built.prog.n_prof; ++i)
+    if (built.prog.prof[i].type == GLT_SHAPELETS) return gl_fail("gl_plan_create: Shapelets are not implemented yet");
+
+  gl_plan* p = new gl_plan();
+  p->device = device; p->bs = bs; p->prog = built.prog;
+  p->n = sim->num_pix; p->ss = sim->supersample; p->hs = p->n * p->ss; p->npix = p->hs * p->hs;
+  p->conversion_factor = sim->conversion_factor;
+  for (int i = 0; i < p->prog.n_lens; ++i) if (p->prog.prof[i].type == GLT_EPL) p->has_epl = true;
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  p->sm_count = prop.multiProcessorCount;
+
+#define GL_TRY(call)                                                                               \
+  do {                                                                                             \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess) { gl_free_plan(p); return gl_fail(std::string(#call) + ": " + cudaGetErrorString(_e)); } \
+  } while (0)
+
+  GL_TRY(gl_upload(&p->d_grid_x, sim->grid_x, (size_t)p->npix));
+  GL_TRY(gl_upload(&p->d_grid_y, sim->grid_y, (size_t)p->npix));
+  if (sim->mask) {
+    std::vector<unsigned char> m((size_t)p->n * p->n), ms((size_t)p->npix);
+    for (int i = 0; i < p->n * p->n; ++i) m[i] = sim->mask[i] ? 1 : 0;
+    for (int i = 0; i < p->hs; ++i)
+      for (int j = 0; j < p->hs; ++j) ms[(size_t)i * p->hs + j] = m[(size_t)(i / p->ss) * p->n + j / p->ss];
+    GL_TRY(gl_upload(&p->d_mask, m.data(), m.size()));
+    GL_TRY(gl_upload(&p->d_ss_mask, ms.data(), ms.size()));
+  }
+  if (!built.member_factor.empty()) GL_TRY(gl_upload(&p->d_member_factor, built.member_factor.data(), built.member_factor.size()));
+
+  // folded kernel Keff = box_ss (*) K, polyphase taps W[py][px][a][b] = Keff[ss a + py][ss b + px] / ss^2
+  {
+    const int K = sim->psf ? sim->psf_n : 1, ss = p->ss;
+    const int E = K + ss - 1;
+    std::vector<double> keff((size_t)E * E, 0.0);
+    for (int i = 0; i < K; ++i)
+      for (int j = 0; j < K; ++j) {
+        const double kv = sim->psf ? (double)sim->psf[(size_t)i * K + j] : 1.0;
+        for (int sy = 0; sy < ss; ++sy)
+          for (int sx = 0; sx < ss; ++sx) keff[(size_t)(i + sy) * E + (j + sx)] += kv / (double)(ss * ss);
+      }
+    const int Aexact = (E + ss - 1) / ss;
+    int A = -1;
+    for (int a : kConvA) if (a >= Aexact) { A = a; break; }
+    if (A < 0) { gl_free_plan(p); return gl_fail("gl_plan_create: PSF too large for the conv kernels (taps per phase > 32)"); }
+    p->A = A; p->pad = (K - 1) / 2;
+    const int wpitch = (A + 3) & ~3, nph = ss * ss;
+    std::vector<float> wf((size_t)nph * A * wpitch, 0.f), wb((size_t)nph * A * wpitch, 0.f);
+    for (int py = 0; py < ss; ++py)
+      for (int px = 0; px < ss; ++px)
+        for (int a = 0; a < A; ++a)
+          for (int b2 = 0; b2 < A; ++b2) {
+            const int u = ss * a + py, v = ss * b2 + px;
+            const float w = (u < E && v < E) ? (float)keff[(size_t)u * E + v] : 0.f;
+            const int ph = py * ss + px;
+            wf[((size_t)ph * A + a) * wpitch + b2] = w;
+            wb[((size_t)ph * A + (A - 1 - a)) * wpitch + (A - 1 - b2)] = w;
+          }
+    GL_TRY(gl_upload(&p->d_wf, wf.data(), wf.size()));
+    GL_TRY(gl_upload(&p->d_wb, wb.data(), wb.size()));
+    GlConvGeom g{};
+    g.n = p->n; g.hs = p->hs; g.ss = ss; g.A = A; g.pad = p->pad; g.wpitch = wpitch;
+    p->gf = g; p->gb = g;
+    gl_pick_tiles(p->n, A, nph, p->gf);
+    // adjoint runs over padded-phase coordinates r in [pad/ss, (hs-1+pad)/ss]
+    p->bwd_rc_start = p->pad / ss;
+    const int nr = (p->hs - 1 + p->pad) / ss - p->bwd_rc_start + 1;
+    gl_pick_tiles(nr, A, 1, p->gb);
+    p->gb.rc0 = p->bwd_rc_start;
+    p->conv_threads_f = ((p->gf.ntx * p->gf.nty + 31) / 32) * 32;
+    p->conv_threads_b = ((p->gb.ntx * p->gb.nty + 31) / 32) * 32;
+    p->smem_cf = (size_t)(nph * p->gf.in_rows * p->gf.in_pitch + nph * A * wpitch) * sizeof(float);
+    p->smem_cb = (size_t)(p->gb.in_rows * p->gb.in_pitch + nph * A * wpitch) * sizeof(float);
+  }
+
+  // chunks per sample for the ray-tracing kernels: enough CTAs for ~4 waves, at most one per pixel batch
+  {
+    const int per_batch = GLK_THREADS * 4;
+    const int nbatch = (p->npix + per_batch - 1) / per_batch;
+    int chunks = (p->sm_count * 8 * 4 + bs - 1) / bs;
+    if (chunks > nbatch) chunks = nbatch;
+    if (chunks < 1) chunks = 1;
+    p->chunks = chunks;
+  }
+  const size_t P_ = (size_t)(p->prog.n_params > 0 ? p->prog.n_params : 1);
+  const int ntile = p->gf.tiles_x * p->gf.tiles_y;
+  GL_TRY(cudaMalloc((void**)&p->d_params, P_ * bs * sizeof(float)));
+  GL_TRY(cudaMalloc((void**)&p->d_dparams, P_ * bs * sizeof(float)));
+  GL_TRY(cudaMalloc((void**)&p->d_derived, (size_t)bs * p->prog.der_total * sizeof(float)));
+  GL_TRY(cudaMalloc((void**)&p->d_ss, (size_t)bs * p->npix * sizeof(float)));
+  GL_TRY(cudaMalloc((void**)&p->d_img, (size_t)bs * p->n * p->n * sizeof(float)));
+  GL_TRY(cudaMalloc((void**)&p->d_gimg, (size_t)bs * p->n * p->n * sizeof(float)));
+  GL_TRY(cudaMalloc((void**)&p->d_like_part, (size_t)bs * ntile * 2 * sizeof(float)));
+  GL_TRY(cudaMalloc((void**)&p->d_gpart, (size_t)bs * p->chunks * (p->prog.g_total + 1) * sizeof(float)));
+  GL_TRY(cudaMalloc((void**)&p->d_gsum, (size_t)bs * (p->prog.g_total + 1) * sizeof(float)));
+  GL_TRY(cudaMalloc((void**)&p->d_logprior, (size_t)bs * sizeof(float)));
+  GL_TRY(cudaMalloc((void**)&p->d_fmax, GL_MAX_PROF * sizeof(float)));
+  GL_TRY(cudaMemset(p->d_logprior, 0, (size_t)bs * sizeof(float)));
+#undef GL_TRY
+  *out = p;
+  return 0;
+}
+
+int gl_plan_set_option(gl_plan* p, const char* name, int32_t value) {
+  if (!p || !name) return gl_fail("gl_plan_set_option: NULL argument");
+  if (!strcmp(name, "epl_batch_max")) { p->epl_batch_max = value; return 0; }
+  return gl_fail(std::string("gl_plan_set_option: unknown option ") + name);
+}
+
+int gl_plan_set_likelihood(gl_plan* p, const gl_like_config* like) {
+  if (!p || !like || !like->observed) return gl_fail("gl_plan_set_likelihood: NULL argument");
+  GL_CUDA(cudaSetDevice(p->device));
+  const size_t nn = (size_t)p->n * p->n;
+  if (p->d_obs) { cudaFree(p->d_obs); p->d_obs = nullptr; }
+  if (p->d_err) { cudaFree(p->d_err); p->d_err = nullptr; }
+  GL_CUDA(gl_upload(&p->d_obs, like->observed, nn));
+  if (like->error_map) GL_CUDA(gl_upload(&p->d_err, like->error_map, nn));
+  else if (!(like->exp_time != 0.f)) return gl_fail("gl_plan_set_likelihood: exp_time must be non-zero without an error map");
+  p->bg2 = like->background_rms * like->background_rms;
+  p->inv_exp = like->error_map ? 0.f : 1.f / like->exp_time;
+  // count_nonzero(img_region)  (tf/model.py:100)
+  p->n_pix_used = (float)nn;
+  if (p->d_mask) {
+    std::vector<unsigned char> m(nn);
+    GL_CUDA(cudaMemcpy(m.data(), p->d_mask, nn, cudaMemcpyDeviceToHost));
+    size_t c = 0; for (unsigned char v : m) c += v ? 1 : 0;
+    p->n_pix_used = (float)c;
+  }
+  p->has_like = true;
+  return 0;
+}
+
+int gl_plan_set_prior(gl_plan* p, const gl_prior_leaf* leaves, int32_t n_leaves) {
+  if (!p || !leaves || n_leaves <= 0) return gl_fail("gl_plan_set_prior: bad arguments");
+  GL_CUDA(cudaSetDevice(p->device));
+  std::vector<GlLeaf> L(n_leaves);
+  for (int k = 0; k < n_leaves; ++k) {
+    const gl_prior_leaf& s = leaves[k];
+    if (s.slot >= p->prog.n_params) return gl_fail("gl_plan_set_prior: leaf slot out of range");
+    if (s.dist < GL_DIST_NORMAL || s.dist > GL_DIST_TRUNCNORMAL) return gl_fail("gl_plan_set_prior: unknown distribution");
+    L[k].dist = s.dist; L[k].slot = s.slot; L[k].a = s.a; L[k].b = s.b; L[k].low = s.low; L[k].high = s.high;
+    L[k].log_norm = 0.f;
+    if (s.dist == GL_DIST_TRUNCNORMAL) {
+      const double al = ((double)s.low - s.a) / s.b, be = ((double)s.high - s.a) / s.b;
+      const double Z = 0.5 * (std::erf(be / std::sqrt(2.0)) - std::erf(al / std::sqrt(2.0)));
+      L[k].log_norm = (float)std::log(Z);
+    }
+  }
+  if (p->d_leaves) { cudaFree(p->d_leaves); p->d_leaves = nullptr; }
+  GL_CUDA(gl_upload(&p->d_leaves, L.data(), L.size()));
+  p->d = n_leaves;
+  for (float** q : {&p->d_z, &p->d_logp, &p->d_chi, &p->d_dz}) if (*q) { cudaFree(*q); *q = nullptr; }
+  GL_CUDA(cudaMalloc((void**)&p->d_z, (size_t)p->bs * p->d * sizeof(float)));
+  GL_CUDA(cudaMalloc((void**)&p->d_dz, (size_t)p->bs * p->d * sizeof(float)));
+  GL_CUDA(cudaMalloc((void**)&p->d_logp, (size_t)p->bs * sizeof(float)));
+  GL_CUDA(cudaMalloc((void**)&p->d_chi, (size_t)p->bs * sizeof(float)));
+  return 0;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------------------------
+static int gl_run_prep(gl_plan* p, const float* params, cudaStream_t st) {
+  const int tb = 128, gb = (p->bs + tb - 1) / tb;
+  const float* fmax = nullptr;
+  if (p->has_epl && p->epl_batch_max) {
+    GL_CUDA(cudaMemsetAsync(p->d_fmax, 0, GL_MAX_PROF * sizeof(float), st));
+    k_epl_fmax<<<gb, tb, 0, st>>>(p->prog, p->bs, params, p->d_member_factor, (int*)p->d_fmax);
+    GL_LAUNCH_CHECK("k_epl_fmax");
+    fmax = p->d_fmax;
+  }
+  k_prep<<<gb, tb, 0, st>>>(p->prog, p->bs, params, p->d_member_factor, fmax, p->d_derived);
+  GL_LAUNCH_CHECK("k_prep");
+  return 0;
+}
+
+static int gl_run_raytrace_fwd(gl_plan* p, float* ss_out, int no_deflection, cudaStream_t st) {
+  dim3 grid(p->chunks, p->bs);
+  const size_t smem = (size_t)p->prog.der_total * sizeof(float);
+  if (smem > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_fwd<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_raytrace_fwd<4><<<grid, GLK_THREADS, smem, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask, p->d_derived,
+                                                     no_deflection, ss_out);
+  GL_LAUNCH_CHECK("k_raytrace_fwd");
+  return 0;
+}
+
+static int gl_run_raytrace_bwd(gl_plan* p, const float* gss, int no_deflection, cudaStream_t st) {
+  dim3 grid(p->chunks, p->bs);
+  const size_t smem = (size_t)(p->prog.der_total + (GLK_THREADS / 32) * p->prog.g_total) * sizeof(float);
+  if (smem > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_bwd<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_raytrace_bwd<4><<<grid, GLK_THREADS, smem, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask, p->d_derived,
+                                                     no_deflection, gss, p->d_gpart);
+  GL_LAUNCH_CHECK("k_raytrace_bwd");
+  return 0;
+}
+
+template <int A>
+static int gl_launch_conv_fwd_A(gl_plan* p, const float* ss, float scale, float* img, bool like, float* gimg, cudaStream_t st) {
+  if (p->smem_cf > 48 * 1024)
+    GL_CUDA(cudaFuncSetAttribute(k_conv_fwd<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cf));
+  GlLikeArgs la{};
+  la.enabled = like ? 1 : 0;
+  if (like) { la.observed = p->d_obs; la.error_map = p->d_err; la.mask = p->d_mask; la.bg2 = p->bg2; la.inv_exp = p->inv_exp; }
+  dim3 grid(p->gf.tiles_x * p->gf.tiles_y, p->bs);
+  k_conv_fwd<A><<<grid, p->conv_threads_f, p->smem_cf, st>>>(p->gf, ss, p->d_wf, scale, img, la, like ? p->d_like_part : nullptr, gimg);
+  GL_LAUNCH_CHECK("k_conv_fwd");
+  return 0;
+}
+template <int A>
+static int gl_launch_conv_bwd_A(gl_plan* p, const float* gimg, float scale, float* gss, cudaStream_t st) {
+  if (p->smem_cb > 48 * 1024)
+    GL_CUDA(cudaFuncSetAttribute(k_conv_bwd<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cb));
+  dim3 grid(p->gb.tiles_x * p->gb.tiles_y, p->bs);
+  k_conv_bwd<A><<<grid, p->conv_threads_b, p->smem_cb, st>>>(p->gb, gimg, p->d_wb, scale, nullptr, gss);
+  GL_LAUNCH_CHECK("k_conv_bwd");
+  return 0;
+}
+#define GL_CONV_DISPATCH(fn, ...)                                                                  \
+  switch (p->A) {                                                                                  \
+    case 1: return fn<1>(__VA_ARGS__); case 2: return fn<2>(__VA_ARGS__); case 3: return fn<3>(__VA_ARGS__);   \
+    case 4: return fn<4>(__VA_ARGS__); case 5: return fn<5>(__VA_ARGS__); case 6: return fn<6>(__VA_ARGS__);   \
+    case 7: return fn<7>(__VA_ARGS__); case 8: return fn<8>(__VA_ARGS__); case 9: return fn<9>(__VA_ARGS__);   \
+    case 11: return fn<11>(__VA_ARGS__); case 13: return fn<13>(__VA_ARGS__); case 16: return fn<16>(__VA_ARGS__); \
+    case 20: return fn<20>(__VA_ARGS__); case 25: return fn<25>(__VA_ARGS__); case 32: return fn<32>(__VA_ARGS__); \
+  }                                                                                                \
+  return gl_fail("conv dispatch: unsupported tap count")
+static int gl_run_conv_fwd(gl_plan* p, const float* ss, float scale, float* img, bool like, float* gimg, cudaStream_t st) {
+  GL_CONV_DISPATCH(gl_launch_conv_fwd_A, p, ss, scale, img, like, gimg, st);
+}
+static int gl_run_conv_bwd(gl_plan* p, const float* gimg, float scale, float* gss, cudaStream_t st) {
+  // the adjoint tiles start at r = pad/ss: shift the geometry by moving the base pointers' origin
+  GL_CONV_DISPATCH(gl_launch_conv_bwd_A, p, gimg, scale, gss, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// data-path entry points
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int gl_simulate_ss(gl_plan* p, const float* params_dev, float* ss_dev, void* stream) {
+  if (!p || !params_dev || !ss_dev) return gl_fail("gl_simulate_ss: NULL argument");
+  GL_CUDA(cudaSetDevice(p->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (gl_run_prep(p, params_dev, st)) return 1;
+  return gl_run_raytrace_fwd(p, ss_dev, 0, st);
+}
+
+int gl_simulate(gl_plan* p, const float* params_dev, float* image_dev, void* stream) {
+  if (!p || !params_dev || !image_dev) return gl_fail("gl_simulate: NULL argument");
+  GL_CUDA(cudaSetDevice(p->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (gl_run_prep(p, params_dev, st)) return 1;
+  if (gl_run_raytrace_fwd(p, p->d_ss, 0, st)) return 1;
+  return gl_run_conv_fwd(p, p->d_ss, p->conversion_factor, image_dev, false, nullptr, st);
+}
+
+int gl_beta(gl_plan* p, const float* params_dev, int32_t npts, const float* x_dev, const float* y_dev, float* bx, float* by,
+            void* stream) {
+  if (!p || !params_dev || !x_dev || !y_dev || !bx || !by || npts <= 0) return gl_fail("gl_beta: bad argument");
+  GL_CUDA(cudaSetDevice(p->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (gl_run_prep(p, params_dev, st)) return 1;
+  dim3 grid((npts + 127) / 128 > 1024 ? 1024 : (npts + 127) / 128, p->bs);
+  k_points<<<grid, 128, (size_t)p->prog.der_total * sizeof(float), st>>>(p->prog, npts, x_dev, y_dev, p->d_derived, 0, bx, by);
+  GL_LAUNCH_CHECK("k_points");
+  return 0;
+}
+
+/* mode 1: total deflection (alpha_x, alpha_y); mode 2: surface brightness (out1 unused) */
+int gl_eval_points(gl_plan* p, const float* params_dev, int32_t npts, const float* x_dev, const float* y_dev, int32_t mode,
+                   float* out0, float* out1, void* stream) {
+  if (!p || !params_dev || !x_dev || !y_dev || !out0 || npts <= 0) return gl_fail("gl_eval_points: bad argument");
+  if (mode < 0 || mode > 2 || (mode != 2 && !out1)) return gl_fail("gl_eval_points: bad mode");
+  GL_CUDA(cudaSetDevice(p->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (gl_run_prep(p, params_dev, st)) return 1;
+  dim3 grid((npts + 127) / 128 > 1024 ? 1024 : (npts + 127) / 128, p->bs);
+  k_points<<<grid, 128, (size_t)p->prog.der_total * sizeof(float), st>>>(p->prog, npts, x_dev, y_dev, p->d_derived, mode, out0, out1);
+  GL_LAUNCH_CHECK("k_points");
+  return 0;
+}
+
+static int gl_loglike_core(gl_plan* p, const float* params, float* loglike, float* red_chi2, float* dparams,
+                           const float* z, float* logp, float* dz, cudaStream_t st) {
+  if (!p->has_like) return gl_fail("log-likelihood requested but gl_plan_set_likelihood was never called");
+  const bool grad = dparams != nullptr;
+  if (gl_run_prep(p, params, st)) return 1;
+  if (gl_run_raytrace_fwd(p, p->d_ss, 0, st)) return 1;
+  if (gl_run_conv_fwd(p, p->d_ss, p->conversion_factor, p->d_img, true, grad ? p->d_gimg : nullptr, st)) return 1;
+  if (grad) {
+    if (gl_run_conv_bwd(p, p->d_gimg, p->conversion_factor, p->d_ss, st)) return 1;
+    if (gl_run_raytrace_bwd(p, p->d_ss, 0, st)) return 1;
+  }
+  const int tb = 128, gb = (p->bs + tb - 1) / tb;
+  k_sample_bwd<<<gb, tb, 0, st>>>(p->prog, p->bs, params, p->d_member_factor, p->d_derived, p->d_gpart, p->chunks, p->d_gsum,
+                                  p->d_like_part, p->gf.tiles_x * p->gf.tiles_y, p->n_pix_used, loglike, red_chi2, dparams,
+                                  p->d, p->d_leaves, z, z ? p->d_logprior : nullptr, logp, dz);
+  GL_LAUNCH_CHECK("k_sample_bwd");
+  return 0;
+}
+
+int gl_loglike_grad(gl_plan* p, const float* params_dev, float* loglike_dev, float* red_chi2_dev, float* dparams_dev,
+                    void* stream) {
+  if (!p || !params_dev) return gl_fail("gl_loglike_grad: NULL argument");
+  GL_CUDA(cudaSetDevice(p->device));
+  return gl_loglike_core(p, params_dev, loglike_dev, red_chi2_dev, dparams_dev, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int gl_unconstrain(gl_plan* p, const float* z_dev, float* params_dev, float* logprior_dev, void* stream) {
+  if (!p || !z_dev) return gl_fail("gl_unconstrain: NULL argument");
+  if (!p->d_leaves) return gl_fail("gl_unconstrain: gl_plan_set_prior was never called");
+  GL_CUDA(cudaSetDevice(p->device));
+  const int tb = 128, gb = (p->bs + tb - 1) / tb;
+  k_unconstrain<<<gb, tb, 0, (cudaStream_t)stream>>>(p->bs, p->d, p->d_leaves, z_dev, params_dev, logprior_dev);
+  GL_LAUNCH_CHECK("k_unconstrain");
+  return 0;
+}
+
+int gl_logprob_grad(gl_plan* p, const float* z_dev, float* logp_dev, float* red_chi2_dev, float* dz_dev, void* stream) {
+  if (!p || !z_dev) return gl_fail("gl_logprob_grad: NULL argument");
+  if (!p->d_leaves) return gl_fail("gl_logprob_grad: gl_plan_set_prior was never called");
+  GL_CUDA(cudaSetDevice(p->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int tb = 128, gb = (p->bs + tb - 1) / tb;
+  k_unconstrain<<<gb, tb, 0, st>>>(p->bs, p->d, p->d_leaves, z_dev, p->d_params, p->d_logprior);
+  GL_LAUNCH_CHECK("k_unconstrain");
+  return gl_loglike_core(p, p->d_params, nullptr, red_chi2_dev, dz_dev ? p->d_dparams : nullptr, z_dev, logp_dev, dz_dev, st);
+}
+
+int gl_logprob_grad_host(gl_plan* p, const float* z_host, float* logp_host, float* red_chi2_host, float* dz_host) {
+  if (!p || !z_host) return gl_fail("gl_logprob_grad_host: NULL argument");
+  if (!p->d_leaves) return gl_fail("gl_logprob_grad_host: gl_plan_set_prior was never called");
+  GL_CUDA(cudaSetDevice(p->device));
+  const size_t nz = (size_t)p->bs * p->d * sizeof(float), nb = (size_t)p->bs * sizeof(float);
+  GL_CUDA(cudaMemcpyAsync(p->d_z, z_host, nz, cudaMemcpyHostToDevice, 0));
+  if (gl_logprob_grad(p, p->d_z, p->d_logp, p->d_chi, dz_host ? p->d_dz : nullptr, nullptr)) return 1;
+  if (logp_host) GL_CUDA(cudaMemcpyAsync(logp_host, p->d_logp, nb, cudaMemcpyDeviceToHost, 0));
+  if (red_chi2_host) GL_CUDA(cudaMemcpyAsync(red_chi2_host, p->d_chi, nb, cudaMemcpyDeviceToHost, 0));
+  if (dz_host) GL_CUDA(cudaMemcpyAsync(dz_host, p->d_dz, nz, cudaMemcpyDeviceToHost, 0));
+  GL_CUDA(cudaStreamSynchronize(0));
+  return 0;
+}
+
+int gl_simulate_host(gl_plan* p, const float* params_host, float* image_host) {
+  if (!p || !params_host || !image_host) return gl_fail("gl_simulate_host: NULL argument");
+  GL_CUDA(cudaSetDevice(p->device));
+  const size_t np = (size_t)p->prog.n_params * p->bs * sizeof(float);
+  GL_CUDA(cudaMemcpyAsync(p->d_params, params_host, np, cudaMemcpyHostToDevice, 0));
+  if (gl_simulate(p, p->d_params, p->d_img, nullptr)) return 1;
+  GL_CUDA(cudaMemcpyAsync(image_host, p->d_img, (size_t)p->bs * p->n * p->n * sizeof(float), cudaMemcpyDeviceToHost, 0));
+  GL_CUDA(cudaStreamSynchronize(0));
+  return 0;
+}
+
+int gl_lstsq_simulate(gl_plan* p, const float*, float*, float*, void*) {
+  (void)p;
+  return gl_fail("gl_lstsq_simulate: not implemented yet");
+}
+int gl_lstsq_loglike_grad(gl_plan* p, const float*, float*, float*, float*, void*) {
+  (void)p;
+  return gl_fail("gl_lstsq_loglike_grad: not implemented yet");
+}
+
+}  // extern "C"

@@ -1,0 +1,957 @@
+// gl_math.cuh -- per-sample and per-pixel arithmetic of the forward model and its hand adjoint.
+//
+// Everything here is a template over the scalar type and is `__host__ __device__`, so the very
+// same source is (a) instantiated in fp32 inside the sm_100a kernels and (b) compiled by g++ in
+// fp32/fp64 into the test-only host harness (tests/hostcheck) that checks every formula and every
+// adjoint against the oracle's autograd without a GPU.  The product never calls the host build.
+//
+// Structure of one profile type X:
+//   X_prep     raw params (one sample)            -> derived block d[] (constants + tables)
+//   X_fwd      d[], NP pixel coordinates           -> deflection / surface brightness
+//   X_bwd      d[], coordinates, output cotangent  -> += g[] (cotangent of the "dvars" of d[])
+//                                                     (+ coordinate cotangent for source light)
+//   X_prep_bwd raw, d[], g[]                       -> graw[] (cotangent of the raw params)
+// The per-pixel kernels never see raw parameters: clamps, `where`s and trigonometry of the
+// parameter conversion run once per sample in X_prep and their gradient conventions
+//  are applied once per sample in X_prep_bwd.
+#pragma once
+
+#include <math.h>
+
+#ifdef __CUDACC__
+#define GL_HD __host__ __device__ __forceinline__
+#else
+#define GL_HD inline
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// scalar math wrappers (fp32 uses the accurate CUDA libm: results must hold 1e-5 vs the oracle)
+// ---------------------------------------------------------------------------------------------
+GL_HD float gl_sqrt(float x) { return sqrtf(x); }
+GL_HD double gl_sqrt(double x) { return sqrt(x); }
+GL_HD float gl_exp(float x) { return expf(x); }
+GL_HD double gl_exp(double x) { return exp(x); }
+GL_HD float gl_log(float x) { return logf(x); }
+GL_HD double gl_log(double x) { return log(x); }
+GL_HD float gl_pow(float x, float y) { return powf(x, y); }
+GL_HD double gl_pow(double x, double y) { return pow(x, y); }
+GL_HD float gl_atan2(float y, float x) { return atan2f(y, x); }
+GL_HD double gl_atan2(double y, double x) { return atan2(y, x); }
+GL_HD float gl_atan(float x) { return atanf(x); }
+GL_HD double gl_atan(double x) { return atan(x); }
+GL_HD float gl_atanh(float x) { return atanhf(x); }
+GL_HD double gl_atanh(double x) { return atanh(x); }
+GL_HD float gl_acosh(float x) { return acoshf(x); }
+GL_HD double gl_acosh(double x) { return acosh(x); }
+GL_HD float gl_acos(float x) { return acosf(x); }
+GL_HD double gl_acos(double x) { return acos(x); }
+GL_HD float gl_cos(float x) { return cosf(x); }
+GL_HD double gl_cos(double x) { return cos(x); }
+GL_HD float gl_sin(float x) { return sinf(x); }
+GL_HD double gl_sin(double x) { return sin(x); }
+GL_HD float gl_abs(float x) { return fabsf(x); }
+GL_HD double gl_abs(double x) { return fabs(x); }
+GL_HD float gl_ceil(float x) { return ceilf(x); }
+GL_HD double gl_ceil(double x) { return ceil(x); }
+GL_HD float gl_min(float a, float b) { return fminf(a, b); }
+GL_HD double gl_min(double a, double b) { return fmin(a, b); }
+GL_HD float gl_max(float a, float b) { return fmaxf(a, b); }
+GL_HD double gl_max(double a, double b) { return fmax(a, b); }
+GL_HD bool gl_isnan(float x) { return x != x; }
+GL_HD bool gl_isnan(double x) { return x != x; }
+
+// Profile type ids (same values as include/gigalens_b200.h).
+enum {
+  GLT_EPL = 1, GLT_SHEAR = 2, GLT_SIE = 3, GLT_SIS = 4, GLT_NFW = 5, GLT_NFW_ELLIPSE = 6, GLT_DPIS = 7, GLT_DPIE = 8,
+  GLT_SERSIC = 32, GLT_SERSIC_ELLIPSE = 33, GLT_SHAPELETS = 34
+};
+
+#define GL_MAX_DVARS 8      // accumulators per profile in the pixel adjoint
+#define GL_MAX_RAW 8
+
+// ---------------------------------------------------------------------------------------------
+// ellipticity (e1, e2) -> (phi, q) and its adjoint  
+//   phi = atan2(e2, e1)/2,  c = min(|e|, cmax)  [EPL: clip(|e|, 0, 1)],  q = (1-c)/(1+c)
+// ---------------------------------------------------------------------------------------------
+template <class T>
+GL_HD void ellip_fwd(T e1, T e2, T cmax, T& phi, T& q, T& c) {
+  phi = gl_atan2(e2, e1) / T(2);
+  T craw = gl_sqrt(e1 * e1 + e2 * e2);
+  c = gl_min(craw, cmax);
+  q = (T(1) - c) / (T(1) + c);
+}
+// tf.minimum / clip_by_value pass the gradient on the un-clamped side (ties included).
+// At e = (0,0) TF yields NaN (0/0); measure zero under every prior, we return 0.
+template <class T>
+GL_HD void ellip_bwd(T e1, T e2, T cmax, T gphi, T gq, T& ge1, T& ge2) {
+  T r2 = e1 * e1 + e2 * e2;
+  if (!(r2 > T(0))) { ge1 = T(0); ge2 = T(0); return; }
+  T craw = gl_sqrt(r2);
+  T c = gl_min(craw, cmax);
+  T gc = gq * (-T(2) / ((T(1) + c) * (T(1) + c)));
+  T gcraw = (craw <= cmax) ? gc : T(0);
+  ge1 = gcraw * e1 / craw - gphi * e2 / (T(2) * r2);
+  ge2 = gcraw * e2 / craw + gphi * e1 / (T(2) * r2);
+}
+
+// =============================================================================================
+// EPL  (src/gigalens/tf/profiles/mass/epl.py:19-57)
+//   raw  : theta_E, gamma, e1, e2, center_x, center_y
+//   d[]  : cx, cy, cos(phi), sin(phi), q, b, t, pref0 = 2b/(1+q), f, N (trip count),
+//          then three tables of stride ts:  A_n, dA_n/df, dA_n/dt   (n = 0..N)
+//   dvars: cx, cy, phi, q, b, t, f, pref0
+// The reference iterates Omega_n = c_n Rot(2 ang) Omega_{n-1}, c_n = -f (2n-(2-t))/(2n+(2-t)), and
+// sums Omega_0..Omega_N.  With u = e^{i ang}, w = u^2 and A_n = prod_{k<=n} c_k (per-sample
+// constants) that sum is u * P(w), P(w) = sum_n A_n w^n, which we evaluate by complex Horner:
+// 4 FMA per trip instead of the recurrence's 8, and no per-pixel state beyond (P_re, P_im).
+// =============================================================================================
+enum { EPL_CX = 0, EPL_CY, EPL_C, EPL_S, EPL_Q, EPL_B, EPL_T, EPL_PREF0, EPL_F, EPL_N, EPL_TAB = 12 };
+enum { EPLG_CX = 0, EPLG_CY, EPLG_PHI, EPLG_Q, EPLG_B, EPLG_T, EPLG_F, EPLG_PREF0 };
+
+GL_HD int epl_table_stride(int niter_cap) { return ((niter_cap + 1) + 3) & ~3; }
+GL_HD int epl_der_size(int niter_cap) { return EPL_TAB + 3 * epl_table_stride(niter_cap); }
+
+// Trip count of `tf.while_loop(i < niter, i0 = 1.0, maximum_iterations=cap)` (epl.py:37,47-54).
+template <class T>
+GL_HD int epl_trip_count(T fmax, int cap) {
+  T niter = gl_log(T(1e-12)) / gl_log(fmax) + T(2);
+  if (!(niter > T(1))) return 0;  // also catches NaN / -inf
+  T n = gl_ceil(niter) - T(1);
+  if (n > T(cap)) return cap;
+  return (int)n;
+}
+
+// fmax_batch < 0  => use this sample's own f (default; differs from the reference's batch-global
+// count only by series terms below 1e-12, SURVEY.md §7 "Iteration count semantics").
+template <class T>
+GL_HD void epl_prep(const T* raw, T* d, int niter_cap, T fmax_batch) {
+  T theta_E = raw[0], gamma = raw[1], e1 = raw[2], e2 = raw[3];
+  T phi, q, c;
+  ellip_fwd(e1, e2, T(1), phi, q, c);
+  T theta_E_conv = theta_E / gl_sqrt((T(1) + q * q) / (T(2) * q));
+  T b = theta_E_conv * gl_sqrt((T(1) + q * q) / T(2));
+  T t = gamma - T(1);
+  T f = (T(1) - q) / (T(1) + q);
+  d[EPL_CX] = raw[4]; d[EPL_CY] = raw[5];
+  d[EPL_C] = gl_cos(phi); d[EPL_S] = gl_sin(phi);
+  d[EPL_Q] = q; d[EPL_B] = b; d[EPL_T] = t;
+  d[EPL_PREF0] = (T(2) * b) / (T(1) + q);
+  d[EPL_F] = f;
+  int N = epl_trip_count(fmax_batch < T(0) ? f : fmax_batch, niter_cap);
+  d[EPL_N] = T(N);
+  d[10] = T(0); d[11] = T(0);
+  const int ts = epl_table_stride(niter_cap);
+  T* A = d + EPL_TAB; T* Af = A + ts; T* At = Af + ts;
+  T s = T(2) - t;
+  T a = T(1), af = T(0), at = T(0);
+  A[0] = a; Af[0] = af; At[0] = at;
+  for (int n = 1; n < ts; ++n) {
+    if (n <= N) {
+      T tn = T(2 * n);
+      T kap = -(tn - s) / (tn + s);           // c_n = f * kap
+      T cn = f * kap;
+      T dcdt = -f * T(4 * n) / ((tn + s) * (tn + s));
+      T a1 = a * cn;
+      T af1 = af * cn + a * kap;
+      T at1 = at * cn + a * dcdt;
+      a = a1; af = af1; at = at1;
+      A[n] = a; Af[n] = af; At[n] = at;
+    } else {
+      A[n] = T(0); Af[n] = T(0); At[n] = T(0);
+    }
+  }
+}
+
+template <class T>
+GL_HD void epl_prep_bwd(const T* raw, const T* d, const T* g, T* graw) {
+  T e1 = raw[2], e2 = raw[3];
+  T q = d[EPL_Q], b = d[EPL_B];
+  T gq = g[EPLG_Q], gb = g[EPLG_B];
+  T opq = T(1) + q;
+  gb += g[EPLG_PREF0] * T(2) / opq;
+  gq -= g[EPLG_PREF0] * T(2) * b / (opq * opq);
+  gq -= g[EPLG_F] * T(2) / (opq * opq);
+  // b = theta_E * sqrt(q) (algebraically; epl.py:24-25)
+  T sq = gl_sqrt(q);
+  graw[0] = gb * sq;
+  gq += (q > T(0)) ? gb * b / (T(2) * q) : T(0);
+  graw[1] = g[EPLG_T];
+  ellip_bwd(e1, e2, T(1), g[EPLG_PHI], gq, graw[2], graw[3]);
+  graw[4] = g[EPLG_CX];
+  graw[5] = g[EPLG_CY];
+}
+
+// Shared per-pixel geometry of the EPL forward / adjoint.
+template <class T>
+struct EplGeom {
+  T xr, yr, qx, R0, R, Cs, Ss, wr, wi;
+};
+template <class T>
+GL_HD void epl_geom(const T* d, T x, T y, EplGeom<T>& G) {
+  T dx = x - d[EPL_CX], dy = y - d[EPL_CY];
+  T c = d[EPL_C], s = d[EPL_S];
+  G.xr = dx * c + dy * s;
+  G.yr = -dx * s + dy * c;
+  G.qx = d[EPL_Q] * G.xr;
+  G.R0 = gl_sqrt(G.qx * G.qx + G.yr * G.yr);
+  G.R = gl_min(gl_max(G.R0, T(1e-10)), T(1e10));
+  if (G.R0 > T(0)) {
+    T inv = T(1) / G.R0;
+    G.Cs = G.qx * inv; G.Ss = G.yr * inv;   // cos/sin of atan2(yr, q xr)
+  } else {
+    G.Cs = T(1); G.Ss = T(0);               // atan2(0, 0) = 0
+  }
+  G.wr = G.Cs * G.Cs - G.Ss * G.Ss;
+  G.wi = T(2) * G.Cs * G.Ss;
+}
+
+template <class T, int NP>
+GL_HD void epl_fwd(const T* d, int ts, const T* x, const T* y, T* ax, T* ay) {
+  EplGeom<T> G[NP];
+  T Pr[NP], Pi[NP];
+  const int N = (int)d[EPL_N];
+  const T* A = d + EPL_TAB;
+  (void)ts;
+#pragma unroll
+  for (int j = 0; j < NP; ++j) { epl_geom(d, x[j], y[j], G[j]); Pr[j] = A[N]; Pi[j] = T(0); }
+  for (int n = N - 1; n >= 0; --n) {
+    T a = A[n];
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      T pr = Pr[j] * G[j].wr - Pi[j] * G[j].wi + a;
+      T pi = Pr[j] * G[j].wi + Pi[j] * G[j].wr;
+      Pr[j] = pr; Pi[j] = pi;
+    }
+  }
+  T c = d[EPL_C], s = d[EPL_S], b = d[EPL_B], tm1 = d[EPL_T] - T(1), pref0 = d[EPL_PREF0];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    T fx = G[j].Cs * Pr[j] - G[j].Ss * Pi[j];
+    T fy = G[j].Cs * Pi[j] + G[j].Ss * Pr[j];
+    T pref = pref0 * gl_pow(b / G[j].R, tm1);
+    fx *= pref; fy *= pref;
+    ax[j] = fx * c - fy * s;
+    ay[j] = fx * s + fy * c;
+  }
+}
+
+// Adjoint: (gax, gay) is the cotangent of the deflection; accumulates into g[EPLG_*].
+template <class T, int NP>
+GL_HD void epl_bwd(const T* d, int ts, const T* x, const T* y, const T* gax, const T* gay, T* g) {
+  EplGeom<T> G[NP];
+  T Pr[NP], Pi[NP], Fr[NP], Fi[NP], Tr[NP], Ti[NP];
+  const int N = (int)d[EPL_N];
+  const T* A = d + EPL_TAB; const T* Af = A + ts; const T* At = Af + ts;
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    epl_geom(d, x[j], y[j], G[j]);
+    Pr[j] = A[N]; Pi[j] = T(0); Fr[j] = Af[N]; Fi[j] = T(0); Tr[j] = At[N]; Ti[j] = T(0);
+  }
+  for (int n = N - 1; n >= 0; --n) {
+    T a = A[n], af = Af[n], at = At[n];
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      T wr = G[j].wr, wi = G[j].wi;
+      T pr = Pr[j] * wr - Pi[j] * wi + a, pi = Pr[j] * wi + Pi[j] * wr;
+      T fr = Fr[j] * wr - Fi[j] * wi + af, fi = Fr[j] * wi + Fi[j] * wr;
+      T tr = Tr[j] * wr - Ti[j] * wi + at, ti = Tr[j] * wi + Ti[j] * wr;
+      Pr[j] = pr; Pi[j] = pi; Fr[j] = fr; Fi[j] = fi; Tr[j] = tr; Ti[j] = ti;
+    }
+  }
+  T c = d[EPL_C], s = d[EPL_S], q = d[EPL_Q], b = d[EPL_B], tm1 = d[EPL_T] - T(1), pref0 = d[EPL_PREF0], f = d[EPL_F];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    const EplGeom<T>& E = G[j];
+    // forward values
+    T fx = E.Cs * Pr[j] - E.Ss * Pi[j], fy = E.Cs * Pi[j] + E.Ss * Pr[j];      // u P
+    T pw = gl_pow(b / E.R, tm1);
+    T pref = pref0 * pw;
+    T Fx = fx * pref, Fy = fy * pref;
+    T ax = Fx * c - Fy * s, ay = Fx * s + Fy * c;
+    // back-rotation by -phi
+    g[EPLG_PHI] += -gax[j] * ay + gay[j] * ax;
+    T gFx = gax[j] * c + gay[j] * s, gFy = -gax[j] * s + gay[j] * c;
+    // prefactor
+    T gpref = gFx * fx + gFy * fy;
+    T gr = gFx * pref, gi = gFy * pref;              // cotangent of u P (complex pair)
+    g[EPLG_PREF0] += gpref * pw;
+    T gpw = gpref * pref0;
+    T lnbr = gl_log(b / E.R);
+    g[EPLG_T] += gpw * pw * lnbr;
+    g[EPLG_B] += gpw * pw * tm1 / b;
+    bool r_free = (E.R0 >= T(1e-10)) && (E.R0 <= T(1e10));
+    T gR = r_free ? -gpw * pw * tm1 / E.R : T(0);
+    // series: F = u P(w; f, t).  <g, u X> = Re(conj(g) u X) for X = dP/df, dP/dt
+    T hr = gr * E.Cs + gi * E.Ss, hi = gi * E.Cs - gr * E.Ss;   // conj(u) g  (so <g,uX> = hr Xr + hi Xi)
+    g[EPLG_F] += hr * Fr[j] + hi * Fi[j];
+    g[EPLG_T] += hr * Tr[j] + hi * Ti[j];
+    // d/d(ang): dF = i u (P + 2 w P_w) d(ang), with w P_w = f dP/df
+    T Zr = Pr[j] + T(2) * f * Fr[j], Zi = Pi[j] + T(2) * f * Fi[j];
+    T gang = -hr * Zi + hi * Zr;                      // Re(conj(g) i u Z)
+    // ang = atan2(yr, qx), R0 = hypot(qx, yr)
+    T gqx = T(0), gyr = T(0);
+    if (E.R0 > T(0)) {
+      T inv2 = T(1) / (E.R0 * E.R0);
+      gqx = -gang * E.yr * inv2 + gR * E.Cs;
+      gyr = gang * E.qx * inv2 + gR * E.Ss;
+    }
+    g[EPLG_Q] += gqx * E.xr;
+    T gxr = gqx * q;
+    g[EPLG_PHI] += gxr * E.yr - gyr * E.xr;
+    T gdx = gxr * c - gyr * s, gdy = gxr * s + gyr * c;
+    g[EPLG_CX] -= gdx;
+    g[EPLG_CY] -= gdy;
+  }
+}
+
+// =============================================================================================
+// SHEAR  (tf/profiles/mass/shear.py:14-16)   raw = d = dvars = (gamma1, gamma2)
+// =============================================================================================
+template <class T, int NP>
+GL_HD void shear_fwd(const T* d, const T* x, const T* y, T* ax, T* ay) {
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    ax[j] = d[0] * x[j] + d[1] * y[j];
+    ay[j] = d[1] * x[j] - d[0] * y[j];
+  }
+}
+template <class T, int NP>
+GL_HD void shear_bwd(const T* d, const T* x, const T* y, const T* gax, const T* gay, T* g) {
+  (void)d;
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    g[0] += gax[j] * x[j] - gay[j] * y[j];
+    g[1] += gax[j] * y[j] + gay[j] * x[j];
+  }
+}
+
+// =============================================================================================
+// SIS  (tf/profiles/mass/sis.py:12-17)   raw = d = dvars = (theta_E, cx, cy)
+// =============================================================================================
+template <class T, int NP>
+GL_HD void sis_fwd(const T* d, const T* x, const T* y, T* ax, T* ay) {
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    T dx = x[j] - d[1], dy = y[j] - d[2];
+    T R = gl_sqrt(dx * dx + dy * dy);
+    T a = (R == T(0)) ? T(0) : d[0] / R;
+    ax[j] = a * dx; ay[j] = a * dy;
+  }
+}
+template <class T, int NP>
+GL_HD void sis_bwd(const T* d, const T* x, const T* y, const T* gax, const T* gay, T* g) {
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    T dx = x[j] - d[1], dy = y[j] - d[2];
+    T R2 = dx * dx + dy * dy;
+    if (R2 > T(0)) {
+      T R = gl_sqrt(R2);
+      T a = d[0] / R;
+      T ga = gax[j] * dx + gay[j] * dy;
+      g[0] += ga / R;
+      T gR = -ga * a / R;
+      T gdx = gax[j] * a + gR * dx / R, gdy = gay[j] * a + gR * dy / R;
+      g[1] -= gdx; g[2] -= gdy;
+    }
+  }
+}
+
+// =============================================================================================
+// SIE  (tf/profiles/mass/sie.py:13-42, core s = 0)
+//   raw  : theta_E, e1, e2, cx, cy
+//   d[]  : cx, cy, cos, sin, q, b, w = sqrt(1-q^2)
+//   dvars: cx, cy, phi, q, b, w
+// =============================================================================================
+enum { SIE_CX = 0, SIE_CY, SIE_C, SIE_S, SIE_Q, SIE_B, SIE_W, SIE_SIZE = 8 };
+enum { SIEG_CX = 0, SIEG_CY, SIEG_PHI, SIEG_Q, SIEG_B, SIEG_W };
+template <class T>
+GL_HD void sie_prep(const T* raw, T* d) {
+  T phi, q, c;
+  ellip_fwd(raw[1], raw[2], T(0.9999), phi, q, c);
+  T theta_E_conv = raw[0] / gl_sqrt((T(1) + q * q) / (T(2) * q));
+  d[SIE_CX] = raw[3]; d[SIE_CY] = raw[4];
+  d[SIE_C] = gl_cos(phi); d[SIE_S] = gl_sin(phi);
+  d[SIE_Q] = q;
+  d[SIE_B] = theta_E_conv * gl_sqrt((T(1) + q * q) / T(2));
+  d[SIE_W] = gl_sqrt(T(1) - q * q);
+  d[7] = T(0);
+}
+template <class T>
+GL_HD void sie_prep_bwd(const T* raw, const T* d, const T* g, T* graw) {
+  T q = d[SIE_Q], b = d[SIE_B], w = d[SIE_W];
+  T gq = g[SIEG_Q] - g[SIEG_W] * q / w;
+  graw[0] = g[SIEG_B] * gl_sqrt(q);
+  gq += g[SIEG_B] * b / (T(2) * q);
+  ellip_bwd(raw[1], raw[2], T(0.9999), g[SIEG_PHI], gq, graw[1], graw[2]);
+  graw[3] = g[SIEG_CX]; graw[4] = g[SIEG_CY];
+}
+template <class T, int NP>
+GL_HD void sie_fwd(const T* d, const T* x, const T* y, T* ax, T* ay) {
+  T c = d[SIE_C], s = d[SIE_S], q = d[SIE_Q], w = d[SIE_W], bw = d[SIE_B] / d[SIE_W];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    T dx = x[j] - d[SIE_CX], dy = y[j] - d[SIE_CY];
+    T xr = dx * c + dy * s, yr = -dx * s + dy * c;
+    T psi = gl_sqrt(q * q * (xr * xr) + yr * yr);
+    T fx = bw * gl_atan(w * xr / psi);
+    T fy = bw * gl_atanh(w * yr / psi);
+    ax[j] = fx * c - fy * s; ay[j] = fx * s + fy * c;
+  }
+}
+template <class T, int NP>
+GL_HD void sie_bwd(const T* d, const T* x, const T* y, const T* gax, const T* gay, T* g) {
+  T c = d[SIE_C], s = d[SIE_S], q = d[SIE_Q], w = d[SIE_W], b = d[SIE_B];
+  T bw = b / w;
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    T dx = x[j] - d[SIE_CX], dy = y[j] - d[SIE_CY];
+    T xr = dx * c + dy * s, yr = -dx * s + dy * c;
+    T psi2 = q * q * (xr * xr) + yr * yr;
+    T psi = gl_sqrt(psi2);
+    T ux = w * xr / psi, uy = w * yr / psi;
+    T atx = gl_atan(ux), aty = gl_atanh(uy);
+    T fx = bw * atx, fy = bw * aty;
+    T ax = fx * c - fy * s, ay = fx * s + fy * c;
+    g[SIEG_PHI] += -gax[j] * ay + gay[j] * ax;
+    T gfx = gax[j] * c + gay[j] * s, gfy = -gax[j] * s + gay[j] * c;
+    T gbw = gfx * atx + gfy * aty;
+    g[SIEG_B] += gbw / w;
+    T gw = -gbw * bw / w;
+    T gux = gfx * bw / (T(1) + ux * ux);
+    T guy = gfy * bw / (T(1) - uy * uy);
+    // u = w * r / psi
+    gw += (gux * xr + guy * yr) / psi;
+    T gxr = gux * w / psi, gyr = guy * w / psi;
+    T gpsi = -(gux * ux + guy * uy) / psi;
+    // psi = sqrt(q^2 xr^2 + yr^2)
+    T gpsi2 = gpsi / (T(2) * psi);
+    g[SIEG_Q] += gpsi2 * T(2) * q * xr * xr;
+    gxr += gpsi2 * T(2) * q * q * xr;
+    gyr += gpsi2 * T(2) * yr;
+    g[SIEG_W] += gw;
+    g[SIEG_PHI] += gxr * yr - gyr * xr;
+    T gdx = gxr * c - gyr * s, gdy = gxr * s + gyr * c;
+    g[SIEG_CX] -= gdx; g[SIEG_CY] -= gdy;
+  }
+}
+
+// =============================================================================================
+// NFW / NFW_ELLIPSE  (tf/profiles/mass/nfw.py:15-52, 106-134)
+//   raw  : Rs, alpha_Rs, [e1, e2,] cx, cy
+//   d[]  : cx, cy, cos, sin, s1 = sqrt(1-e), s2 = sqrt(1+e), Rs_c = max(Rs, 1e-7), pref = 4 rho0 Rs_c
+//   dvars: cx, cy, phi, s1, s2, Rs_c, pref
+//   (spherical NFW: cos = 1, sin = 0, s1 = s2 = 1 and their cotangents are dropped)
+// =============================================================================================
+enum { NFW_CX = 0, NFW_CY, NFW_C, NFW_S, NFW_S1, NFW_S2, NFW_RS, NFW_PREF, NFW_SIZE = 8 };
+enum { NFWG_CX = 0, NFWG_CY, NFWG_PHI, NFWG_S1, NFWG_S2, NFWG_RS, NFWG_PREF };
+#define GL_NFW_RMIN 0.0000001
+#define GL_NFW_C 0.000001
+#define GL_ONE_MINUS_LN2 0.30685281944005469
+template <class T>
+GL_HD void nfw_prep(const T* raw, T* d, bool ellipse) {
+  T Rs = raw[0], alpha_Rs = raw[1];
+  T rho0 = alpha_Rs / (T(4) * Rs * Rs * T(GL_ONE_MINUS_LN2));
+  T Rs_c = gl_max(T(GL_NFW_RMIN), Rs);
+  d[NFW_RS] = Rs_c;
+  d[NFW_PREF] = T(4) * rho0 * Rs_c;
+  if (ellipse) {
+    T phi, q, c;
+    ellip_fwd(raw[2], raw[3], T(0.9999), phi, q, c);
+    T e = gl_abs(T(1) - q * q) / (T(1) + q * q);
+    d[NFW_C] = gl_cos(phi); d[NFW_S] = gl_sin(phi);
+    d[NFW_S1] = gl_sqrt(T(1) - e); d[NFW_S2] = gl_sqrt(T(1) + e);
+    d[NFW_CX] = raw[4]; d[NFW_CY] = raw[5];
+  } else {
+    d[NFW_C] = T(1); d[NFW_S] = T(0); d[NFW_S1] = T(1); d[NFW_S2] = T(1);
+    d[NFW_CX] = raw[2]; d[NFW_CY] = raw[3];
+  }
+}
+template <class T>
+GL_HD void nfw_prep_bwd(const T* raw, const T* d, const T* g, T* graw, bool ellipse) {
+  T Rs = raw[0], alpha_Rs = raw[1];
+  T k = T(4) * T(GL_ONE_MINUS_LN2);
+  T Rs_c = d[NFW_RS];
+  // pref = 4 rho0 Rs_c, rho0 = alpha_Rs / (k Rs^2)
+  T rho0 = alpha_Rs / (k * Rs * Rs);
+  T gRs_c = g[NFWG_RS] + g[NFWG_PREF] * T(4) * rho0;
+  T grho0 = g[NFWG_PREF] * T(4) * Rs_c;
+  graw[1] = grho0 / (k * Rs * Rs);
+  graw[0] = -grho0 * T(2) * rho0 / Rs + ((Rs >= T(GL_NFW_RMIN)) ? gRs_c : T(0));
+  if (ellipse) {
+    T phi, q, c;
+    ellip_fwd(raw[2], raw[3], T(0.9999), phi, q, c);
+    T e = gl_abs(T(1) - q * q) / (T(1) + q * q);
+    T ge = -g[NFWG_S1] / (T(2) * d[NFW_S1]) + g[NFWG_S2] / (T(2) * d[NFW_S2]);
+    // e = (1-q^2)/(1+q^2) for q <= 1 (always, since c >= 0): de/dq = -4q/(1+q^2)^2
+    T opq2 = T(1) + q * q;
+    T gq = ge * (-T(4) * q / (opq2 * opq2));
+    (void)e;
+    ellip_bwd(raw[2], raw[3], T(0.9999), g[NFWG_PHI], gq, graw[2], graw[3]);
+    graw[4] = g[NFWG_CX]; graw[5] = g[NFWG_CY];
+  } else {
+    graw[2] = g[NFWG_CX]; graw[3] = g[NFWG_CY];
+  }
+}
+// g(X) of nfw.py:34-52 and its derivative; X == 1 keeps the reference's 1.0.
+template <class T>
+GL_HD T nfw_g(T X, T& dg) {
+  if (X < T(1)) {
+    T om = T(1) - X * X;
+    T r = gl_sqrt(om);
+    T ach = gl_acosh(T(1) / X);
+    dg = T(1) / X + X * ach / (om * r) - T(1) / (X * om);
+    return gl_log(X / T(2)) + ach / r;
+  } else if (X > T(1)) {
+    T om = X * X - T(1);
+    T r = gl_sqrt(om);
+    T ac = gl_acos(T(1) / X);
+    dg = T(1) / X - X * ac / (om * r) + T(1) / (X * om);
+    return gl_log(X / T(2)) + ac / r;
+  }
+  dg = T(0);
+  return T(1);
+}
+template <class T, int NP>
+GL_HD void nfw_fwd(const T* d, const T* x, const T* y, T* ax, T* ay) {
+  T c = d[NFW_C], s = d[NFW_S], s1 = d[NFW_S1], s2 = d[NFW_S2];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    T dx = x[j] - d[NFW_CX], dy = y[j] - d[NFW_CY];
+    T xr = (dx * c + dy * s) * s1, yr = (-dx * s + dy * c) * s2;
+    T R = gl_max(T(GL_NFW_RMIN), gl_sqrt(xr * xr + yr * yr));
+    T X = gl_max(T(GL_NFW_C), R / d[NFW_RS]);
+    T dg;
+    T a = d[NFW_PREF] * nfw_g(X, dg) / ((R / d[NFW_RS]) * (R / d[NFW_RS]));
+    T fx = a * xr * s1, fy = a * yr * s2;
+    ax[j] = fx * c - fy * s; ay[j] = fx * s + fy * c;
+  }
+}
+template <class T, int NP>
+GL_HD void nfw_bwd(const T* d, const T* x, const T* y, const T* gax, const T* gay, T* g) {
+  T c = d[NFW_C], s = d[NFW_S], s1 = d[NFW_S1], s2 = d[NFW_S2], Rs = d[NFW_RS], pref = d[NFW_PREF];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    T dx = x[j] - d[NFW_CX], dy = y[j] - d[NFW_CY];
+    T xr0 = dx * c + dy * s, yr0 = -dx * s + dy * c;
+    T xr = xr0 * s1, yr = yr0 * s2;
+    T R0 = gl_sqrt(xr * xr + yr * yr);
+    T R = gl_max(T(GL_NFW_RMIN), R0);
+    T X0 = R / Rs;
+    T X = gl_max(T(GL_NFW_C), X0);
+    T dg;
+    T gx = nfw_g(X, dg);
+    T a = pref * gx / (X0 * X0);
+    T fx = a * xr * s1, fy = a * yr * s2;
+    T ax = fx * c - fy * s, ay = fx * s + fy * c;
+    g[NFWG_PHI] += -gax[j] * ay + gay[j] * ax;
+    T gfx = gax[j] * c + gay[j] * s, gfy = -gax[j] * s + gay[j] * c;
+    // fx = a xr s1, fy = a yr s2
+    T ga = gfx * xr * s1 + gfy * yr * s2;
+    T gxr = gfx * a * s1, gyr = gfy * a * s2;
+    g[NFWG_S1] += gfx * a * xr;
+    g[NFWG_S2] += gfy * a * yr;
+    // a = pref g(X) / X0^2
+    g[NFWG_PREF] += ga * gx / (X0 * X0);
+    T gX0 = -T(2) * ga * a / X0 + ((X0 >= T(GL_NFW_C)) ? ga * pref * dg / (X0 * X0) : T(0));
+    // X0 = R / Rs
+    g[NFWG_RS] += -gX0 * X0 / Rs;
+    T gR = gX0 / Rs;
+    if (R0 >= T(GL_NFW_RMIN) && R0 > T(0)) {
+      gxr += gR * xr / R0; gyr += gR * yr / R0;
+    }
+    g[NFWG_S1] += gxr * xr0;
+    g[NFWG_S2] += gyr * yr0;
+    T gxr0 = gxr * s1, gyr0 = gyr * s2;
+    g[NFWG_PHI] += gxr0 * yr0 - gyr0 * xr0;
+    T gdx = gxr0 * c - gyr0 * s, gdy = gxr0 * s + gyr0 * c;
+    g[NFWG_CX] -= gdx; g[NFWG_CY] -= gdy;
+  }
+}
+
+// =============================================================================================
+// dPIS / dPIE  (tf/profiles/mass/piemd.py:33-60, 105-119, 183-255)
+//   raw  : theta_E, r_core, r_cut, [e1, e2,] cx, cy
+//   d[]  : cx, cy, cos, sin, scale = theta_E r_cut/(r_cut - r_core), rc, rt (sorted, floored),
+//          e, (dPIE only; the pixel code derives sqrt(e), q, ... from e)
+//   dvars: cx, cy, phi, scale, rc, rt, e
+// =============================================================================================
+enum { DP_CX = 0, DP_CY, DP_C, DP_S, DP_SCALE, DP_RC, DP_RT, DP_E, DP_SIZE = 8 };
+enum { DPG_CX = 0, DPG_CY, DPG_PHI, DPG_SCALE, DPG_RC, DPG_RT, DPG_E };
+#define GL_DPIE_RMIN 0.0001
+// _sort_ra_rs (piemd.py:51-60): returns the sorted/floored radii and the selection pattern needed
+// by the adjoint.  sel bit0: r_core < r_cut (kept), bit1: r_core floored, bit2: r_cut bumped.
+template <class T>
+GL_HD void dpie_sort(T r_core, T r_cut, T& rc, T& rt) {
+  T a = (r_core < r_cut) ? r_core : r_cut;
+  T b = (a > r_cut) ? a : r_cut;
+  a = gl_max(T(GL_DPIE_RMIN), a);
+  b = (b > a + T(GL_DPIE_RMIN)) ? b : b + T(GL_DPIE_RMIN);
+  rc = a; rt = b;
+}
+template <class T>
+GL_HD void dpie_sort_bwd(T r_core, T r_cut, T grc, T grt, T& g_core, T& g_cut) {
+  // a0 = where(r_core < r_cut, r_core, r_cut); b0 = where(a0 > r_cut, a0, r_cut) == r_cut always
+  // (a0 <= r_cut), a1 = max(rmin, a0), b1 = b0 or b0 + rmin (derivative 1 either way).
+  T a0 = (r_core < r_cut) ? r_core : r_cut;
+  T ga0 = (a0 >= T(GL_DPIE_RMIN)) ? grc : T(0);
+  g_core = T(0); g_cut = grt;
+  if (r_core < r_cut) g_core += ga0; else g_cut += ga0;
+}
+template <class T>
+GL_HD void dpie_prep(const T* raw, T* d, bool ellipse) {
+  T rc, rt;
+  dpie_sort(raw[1], raw[2], rc, rt);
+  d[DP_SCALE] = raw[0] * rt / (rt - rc);
+  d[DP_RC] = rc; d[DP_RT] = rt;
+  if (ellipse) {
+    T phi, q, e;
+    ellip_fwd(raw[3], raw[4], T(0.9999), phi, q, e);
+    d[DP_C] = gl_cos(phi); d[DP_S] = gl_sin(phi); d[DP_E] = e;
+    d[DP_CX] = raw[5]; d[DP_CY] = raw[6];
+  } else {
+    d[DP_C] = T(1); d[DP_S] = T(0); d[DP_E] = T(0);
+    d[DP_CX] = raw[3]; d[DP_CY] = raw[4];
+  }
+}
+template <class T>
+GL_HD void dpie_prep_bwd(const T* raw, const T* d, const T* g, T* graw, bool ellipse) {
+  T rc = d[DP_RC], rt = d[DP_RT], theta_E = raw[0];
+  T dif = rt - rc;
+  graw[0] = g[DPG_SCALE] * rt / dif;
+  T grt = g[DPG_RT] + g[DPG_SCALE] * theta_E * (-rc) / (dif * dif);
+  T grc = g[DPG_RC] + g[DPG_SCALE] * theta_E * rt / (dif * dif);
+  dpie_sort_bwd(raw[1], raw[2], grc, grt, graw[1], graw[2]);
+  if (ellipse) {
+    // e = min(|e|, 0.9999) is ellip_fwd's `c`; q = (1-c)/(1+c) => feed gq = 0 and add gc by hand.
+    T e1 = raw[3], e2 = raw[4];
+    T r2 = e1 * e1 + e2 * e2;
+    if (r2 > T(0)) {
+      T craw = gl_sqrt(r2);
+      T gcraw = (craw <= T(0.9999)) ? g[DPG_E] : T(0);
+      graw[3] = gcraw * e1 / craw - g[DPG_PHI] * e2 / (T(2) * r2);
+      graw[4] = gcraw * e2 / craw + g[DPG_PHI] * e1 / (T(2) * r2);
+    } else { graw[3] = T(0); graw[4] = T(0); }
+    graw[5] = g[DPG_CX]; graw[6] = g[DPG_CY];
+  } else {
+    graw[3] = g[DPG_CX]; graw[4] = g[DPG_CY];
+  }
+}
+template <class T, int NP>
+GL_HD void dpis_fwd(const T* d, const T* x, const T* y, T* ax, T* ay) {
+  T rc = d[DP_RC], rt = d[DP_RT], scale = d[DP_SCALE];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    T dx = x[j] - d[DP_CX], dy = y[j] - d[DP_CY];
+    T r2 = dx * dx + dy * dy;
+    T fa = gl_sqrt(r2 + rc * rc) - rc - gl_sqrt(r2 + rt * rt) + rt;
+    T ar = scale / r2 * fa;
+    ax[j] = ar * dx; ay[j] = ar * dy;
+  }
+}
+template <class T, int NP>
+GL_HD void dpis_bwd(const T* d, const T* x, const T* y, const T* gax, const T* gay, T* g) {
+  T rc = d[DP_RC], rt = d[DP_RT], scale = d[DP_SCALE];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    T dx = x[j] - d[DP_CX], dy = y[j] - d[DP_CY];
+    T r2 = dx * dx + dy * dy;
+    T sc = gl_sqrt(r2 + rc * rc), st = gl_sqrt(r2 + rt * rt);
+    T fa = sc - rc - st + rt;
+    T ar = scale / r2 * fa;
+    T gar = gax[j] * dx + gay[j] * dy;
+    T gdx = gax[j] * ar, gdy = gay[j] * ar;
+    g[DPG_SCALE] += gar * fa / r2;
+    T gfa = gar * scale / r2;
+    T gr2 = -gar * ar / r2 + gfa * (T(0.5) / sc - T(0.5) / st);
+    g[DPG_RC] += gfa * (rc / sc - T(1));
+    g[DPG_RT] += gfa * (T(1) - rt / st);
+    gdx += gr2 * T(2) * dx; gdy += gr2 * T(2) * dy;
+    g[DPG_CX] -= gdx; g[DPG_CY] -= gdy;
+  }
+}
+
+// complex_deriv_dual (piemd.py:201-255) on rotated coordinates; returns the unscaled (re, im).
+template <class T>
+struct DpieFw {
+  T sqe, q, ope2, ome2, zci, rem2, sc, st, a, b_, c_, d_, e_, f_, aa, bb, cc, dd, norm, aaa, bbb, norm2, zr_re, zr_im;
+};
+template <class T>
+GL_HD void dpie_core_fwd(T x, T y, T rc, T rt, T e, DpieFw<T>& W, T& re, T& im) {
+  W.sqe = gl_sqrt(e);
+  W.q = (T(1) - e) / (T(1) + e);
+  W.ope2 = (T(1) + e) * (T(1) + e);
+  W.ome2 = (T(1) - e) * (T(1) - e);
+  W.rem2 = x * x / W.ope2 + y * y / W.ome2;
+  W.zci = -T(0.5) * (T(1) - e * e) / W.sqe;
+  W.sc = gl_sqrt(rc * rc + W.rem2);
+  W.st = gl_sqrt(rt * rt + W.rem2);
+  W.a = W.q * x;                                 // znum_rc_re
+  W.b_ = T(2) * W.sqe * W.sc - y / W.q;          // znum_rc_im
+  W.c_ = x;                                      // zden_rc_re
+  W.d_ = T(2) * rc * W.sqe - y;                  // zden_rc_im
+  W.e_ = T(2) * W.sqe * W.st - y / W.q;          // znum_rcut_im
+  W.f_ = T(2) * rt * W.sqe - y;                  // zden_rcut_im
+  W.aa = W.a * W.c_ - W.b_ * W.f_;
+  W.bb = W.a * W.f_ + W.b_ * W.c_;
+  W.cc = W.a * W.c_ - W.d_ * W.e_;
+  W.dd = W.a * W.d_ + W.c_ * W.e_;
+  W.norm = W.cc * W.cc + W.dd * W.dd;
+  W.aaa = (W.aa * W.cc + W.bb * W.dd) / W.norm;
+  W.bbb = (W.bb * W.cc - W.aa * W.dd) / W.norm;
+  W.norm2 = W.aaa * W.aaa + W.bbb * W.bbb;
+  W.zr_re = gl_log(gl_sqrt(W.norm2));
+  W.zr_im = gl_atan2(W.bbb, W.aaa);
+  re = -W.zci * W.zr_im;
+  im = W.zci * W.zr_re;
+}
+template <class T, int NP>
+GL_HD void dpie_fwd(const T* d, const T* x, const T* y, T* ax, T* ay) {
+  T c = d[DP_C], s = d[DP_S], scale = d[DP_SCALE];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    T dx = x[j] - d[DP_CX], dy = y[j] - d[DP_CY];
+    T xr = dx * c + dy * s, yr = -dx * s + dy * c;
+    DpieFw<T> W; T re, im;
+    dpie_core_fwd(xr, yr, d[DP_RC], d[DP_RT], d[DP_E], W, re, im);
+    ax[j] = scale * (re * c - im * s);
+    ay[j] = scale * (re * s + im * c);
+  }
+}
+template <class T, int NP>
+GL_HD void dpie_bwd(const T* d, const T* x, const T* y, const T* gax, const T* gay, T* g) {
+  T c = d[DP_C], s = d[DP_S], scale = d[DP_SCALE], rc = d[DP_RC], rt = d[DP_RT], e = d[DP_E];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    T dx = x[j] - d[DP_CX], dy = y[j] - d[DP_CY];
+    T xr = dx * c + dy * s, yr = -dx * s + dy * c;
+    DpieFw<T> W; T re, im;
+    dpie_core_fwd(xr, yr, rc, rt, e, W, re, im);
+    T ux = re * c - im * s, uy = re * s + im * c;     // rotated back, unscaled
+    g[DPG_SCALE] += gax[j] * ux + gay[j] * uy;
+    T gux = gax[j] * scale, guy = gay[j] * scale;
+    g[DPG_PHI] += -gux * uy + guy * ux;
+    T gre = gux * c + guy * s, gim = -gux * s + guy * c;
+    // re = -zci zr_im ; im = zci zr_re
+    T gzci = -gre * W.zr_im + gim * W.zr_re;
+    T gzr_im = -gre * W.zci, gzr_re = gim * W.zci;
+    // zr_re = 0.5 log(norm2), zr_im = atan2(bbb, aaa)
+    T gaaa = (gzr_re * W.aaa - gzr_im * W.bbb) / W.norm2;
+    T gbbb = (gzr_re * W.bbb + gzr_im * W.aaa) / W.norm2;
+    // aaa = (aa cc + bb dd)/norm, bbb = (bb cc - aa dd)/norm
+    T gaa = (gaaa * W.cc - gbbb * W.dd) / W.norm;
+    T gbb = (gaaa * W.dd + gbbb * W.cc) / W.norm;
+    T gnorm = -(gaaa * W.aaa + gbbb * W.bbb) / W.norm;
+    T gcc = (gaaa * W.aa + gbbb * W.bb) / W.norm + gnorm * T(2) * W.cc;
+    T gdd = (gaaa * W.bb - gbbb * W.aa) / W.norm + gnorm * T(2) * W.dd;
+    // aa = a c - b f ; bb = a f + b c ; cc = a c - d e ; dd = a d + c e
+    T ga = gaa * W.c_ + gbb * W.f_ + gcc * W.c_ + gdd * W.d_;
+    T gb = -gaa * W.f_ + gbb * W.c_;
+    T gc = gaa * W.a + gbb * W.b_ + gcc * W.a + gdd * W.e_;
+    T gd = -gcc * W.e_ + gdd * W.a;
+    T ge_ = -gcc * W.d_ + gdd * W.c_;
+    T gf = -gaa * W.b_ + gbb * W.a;
+    // a = q x ; b = 2 sqe sc - y/q ; c = x ; d = 2 rc sqe - y ; e = 2 sqe st - y/q ; f = 2 rt sqe - y
+    T gq = ga * xr + (gb + ge_) * yr / (W.q * W.q);
+    T gx = ga * W.q + gc;
+    T gy = -(gb + ge_) / W.q - gd - gf;
+    T gsqe = T(2) * (gb * W.sc + ge_ * W.st + gd * rc + gf * rt);
+    T gsc = gb * T(2) * W.sqe, gst = ge_ * T(2) * W.sqe;
+    g[DPG_RC] += gd * T(2) * W.sqe + gsc * rc / W.sc;
+    g[DPG_RT] += gf * T(2) * W.sqe + gst * rt / W.st;
+    T grem2 = gsc * T(0.5) / W.sc + gst * T(0.5) / W.st;
+    // rem2 = x^2/(1+e)^2 + y^2/(1-e)^2
+    gx += grem2 * T(2) * xr / W.ope2;
+    gy += grem2 * T(2) * yr / W.ome2;
+    T ge = grem2 * (-T(2) * xr * xr / (W.ope2 * (T(1) + e)) + T(2) * yr * yr / (W.ome2 * (T(1) - e)));
+    // zci = -0.5 (1 - e^2)/sqe ; sqe = sqrt(e) ; q = (1-e)/(1+e)
+    gsqe += gzci * T(0.5) * (T(1) - e * e) / (W.sqe * W.sqe);
+    ge += gzci * e / W.sqe;
+    ge += gsqe * T(0.5) / W.sqe;
+    ge += gq * (-T(2) / ((T(1) + e) * (T(1) + e)));
+    g[DPG_E] += ge;
+    g[DPG_PHI] += gx * yr - gy * xr;
+    T gdx = gx * c - gy * s, gdy = gx * s + gy * c;
+    g[DPG_CX] -= gdx; g[DPG_CY] -= gdy;
+  }
+}
+
+// =============================================================================================
+// SERSIC / SERSIC_ELLIPSE  (tf/profiles/light/sersic.py:29-80)
+//   raw  : R_sersic, n_sersic, [e1, e2,] cx, cy, Ie      (Ie == 1 under use_lstsq, sersic.py:31,76)
+//   d[]  : cx, cy, cos, sin, sq = sqrt(q), isq = 1/sq, 1/R_sersic, 1/n, bn, Ie
+//   dvars: cx, cy, phi, sq, invRs, invn, bn, Ie
+// =============================================================================================
+enum { SER_CX = 0, SER_CY, SER_C, SER_S, SER_SQ, SER_ISQ, SER_IRS, SER_IN, SER_BN, SER_IE, SER_SIZE = 12 };
+enum { SERG_CX = 0, SERG_CY, SERG_PHI, SERG_SQ, SERG_IRS, SERG_IN, SERG_BN, SERG_IE };
+template <class T>
+GL_HD void sersic_prep(const T* raw, T* d, bool ellipse, bool use_lstsq) {
+  T Rs = raw[0], n = raw[1];
+  d[SER_IRS] = T(1) / Rs;
+  d[SER_IN] = T(1) / n;
+  d[SER_BN] = T(1.9992) * n - T(0.3271);
+  if (ellipse) {
+    T phi, q, c;
+    ellip_fwd(raw[2], raw[3], T(0.9999), phi, q, c);
+    d[SER_C] = gl_cos(phi); d[SER_S] = gl_sin(phi);
+    d[SER_SQ] = gl_sqrt(q); d[SER_ISQ] = T(1) / gl_sqrt(q);
+    d[SER_CX] = raw[4]; d[SER_CY] = raw[5];
+    d[SER_IE] = use_lstsq ? T(1) : raw[6];
+  } else {
+    d[SER_C] = T(1); d[SER_S] = T(0); d[SER_SQ] = T(1); d[SER_ISQ] = T(1);
+    d[SER_CX] = raw[2]; d[SER_CY] = raw[3];
+    d[SER_IE] = use_lstsq ? T(1) : raw[4];
+  }
+  d[10] = T(0); d[11] = T(0);
+}
+template <class T>
+GL_HD void sersic_prep_bwd(const T* raw, const T* d, const T* g, T* graw, bool ellipse, bool use_lstsq) {
+  T Rs = raw[0], n = raw[1];
+  graw[0] = -g[SERG_IRS] / (Rs * Rs);
+  graw[1] = -g[SERG_IN] / (n * n) + T(1.9992) * g[SERG_BN];
+  if (ellipse) {
+    T gq = g[SERG_SQ] / (T(2) * d[SER_SQ]);
+    ellip_bwd(raw[2], raw[3], T(0.9999), g[SERG_PHI], gq, graw[2], graw[3]);
+    graw[4] = g[SERG_CX]; graw[5] = g[SERG_CY];
+    graw[6] = use_lstsq ? T(0) : g[SERG_IE];
+  } else {
+    graw[2] = g[SERG_CX]; graw[3] = g[SERG_CY];
+    graw[4] = use_lstsq ? T(0) : g[SERG_IE];
+  }
+}
+template <class T, int NP>
+GL_HD void sersic_fwd(const T* d, const T* x, const T* y, T* out) {
+  T c = d[SER_C], s = d[SER_S];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    T dx = x[j] - d[SER_CX], dy = y[j] - d[SER_CY];
+    T xt1 = (c * dx + s * dy) * d[SER_SQ];
+    T xt2 = (-s * dx + c * dy) * d[SER_ISQ];
+    T R = gl_sqrt(xt1 * xt1 + xt2 * xt2);
+    T p = gl_pow(R * d[SER_IRS], d[SER_IN]);
+    out[j] += d[SER_IE] * gl_exp(-d[SER_BN] * (p - T(1)));
+  }
+}
+// gI: cotangent of the surface brightness.  gx/gy (may be null): += cotangent of the coordinates.
+template <class T, int NP>
+GL_HD void sersic_bwd(const T* d, const T* x, const T* y, const T* gI, T* g, T* gx, T* gy) {
+  T c = d[SER_C], s = d[SER_S], sq = d[SER_SQ], isq = d[SER_ISQ], irs = d[SER_IRS], in_ = d[SER_IN], bn = d[SER_BN];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    T dx = x[j] - d[SER_CX], dy = y[j] - d[SER_CY];
+    T xr = c * dx + s * dy, yr = -s * dx + c * dy;
+    T xt1 = xr * sq, xt2 = yr * isq;
+    T R = gl_sqrt(xt1 * xt1 + xt2 * xt2);
+    T u = R * irs;
+    T p = gl_pow(u, in_);
+    T E = gl_exp(-bn * (p - T(1)));
+    g[SERG_IE] += gI[j] * E;
+    T garg = gI[j] * d[SER_IE] * E;
+    g[SERG_BN] += -garg * (p - T(1));
+    T gp = -garg * bn;
+    if (u > T(0)) {
+      g[SERG_IN] += gp * p * gl_log(u);
+      T gu = gp * p * in_ / u;
+      g[SERG_IRS] += gu * R;
+      T gR = gu * irs;
+      T gxt1 = gR * xt1 / R, gxt2 = gR * xt2 / R;
+      g[SERG_SQ] += gxt1 * xr - gxt2 * yr * isq * isq;
+      T gxr = gxt1 * sq, gyr = gxt2 * isq;
+      g[SERG_PHI] += gxr * yr - gyr * xr;
+      T gdx = gxr * c - gyr * s, gdy = gxr * s + gyr * c;
+      g[SERG_CX] -= gdx; g[SERG_CY] -= gdy;
+      if (gx) { gx[j] += gdx; gy[j] += gdy; }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic per-type tables
+// ---------------------------------------------------------------------------------------------
+GL_HD int gl_n_raw(int type) {
+  switch (type) {
+    case GLT_EPL: return 6; case GLT_SHEAR: return 2; case GLT_SIE: return 5; case GLT_SIS: return 3;
+    case GLT_NFW: return 4; case GLT_NFW_ELLIPSE: return 6; case GLT_DPIS: return 5; case GLT_DPIE: return 7;
+    case GLT_SERSIC: return 5; case GLT_SERSIC_ELLIPSE: return 7; case GLT_SHAPELETS: return 3;
+  }
+  return 0;
+}
+GL_HD int gl_n_dvars(int type) {
+  switch (type) {
+    case GLT_EPL: return 8; case GLT_SHEAR: return 2; case GLT_SIE: return 6; case GLT_SIS: return 3;
+    case GLT_NFW: case GLT_NFW_ELLIPSE: return 7; case GLT_DPIS: case GLT_DPIE: return 7;
+    case GLT_SERSIC: case GLT_SERSIC_ELLIPSE: return 8; case GLT_SHAPELETS: return 3;
+  }
+  return 0;
+}
+GL_HD int gl_der_size(int type, int niter) {
+  switch (type) {
+    case GLT_EPL: return epl_der_size(niter); case GLT_SHEAR: return 4; case GLT_SIE: return SIE_SIZE; case GLT_SIS: return 4;
+    case GLT_NFW: case GLT_NFW_ELLIPSE: return NFW_SIZE; case GLT_DPIS: case GLT_DPIE: return DP_SIZE;
+    case GLT_SERSIC: case GLT_SERSIC_ELLIPSE: return SER_SIZE; case GLT_SHAPELETS: return 4;
+  }
+  return 0;
+}
+
+// raw -> derived for the simple (non-scaled, non-shapelets) types
+template <class T>
+GL_HD void gl_prep(int type, unsigned flags, int niter, const T* raw, T* d, T epl_fmax) {
+  switch (type) {
+    case GLT_EPL: epl_prep(raw, d, niter, epl_fmax); break;
+    case GLT_SHEAR: d[0] = raw[0]; d[1] = raw[1]; d[2] = T(0); d[3] = T(0); break;
+    case GLT_SIE: sie_prep(raw, d); break;
+    case GLT_SIS: d[0] = raw[0]; d[1] = raw[1]; d[2] = raw[2]; d[3] = T(0); break;
+    case GLT_NFW: nfw_prep(raw, d, false); break;
+    case GLT_NFW_ELLIPSE: nfw_prep(raw, d, true); break;
+    case GLT_DPIS: dpie_prep(raw, d, false); break;
+    case GLT_DPIE: dpie_prep(raw, d, true); break;
+    case GLT_SERSIC: sersic_prep(raw, d, false, (flags & 1u) != 0); break;
+    case GLT_SERSIC_ELLIPSE: sersic_prep(raw, d, true, (flags & 1u) != 0); break;
+    default: break;
+  }
+}
+template <class T>
+GL_HD void gl_prep_bwd(int type, unsigned flags, const T* raw, const T* d, const T* g, T* graw) {
+  switch (type) {
+    case GLT_EPL: epl_prep_bwd(raw, d, g, graw); break;
+    case GLT_SHEAR: graw[0] = g[0]; graw[1] = g[1]; break;
+    case GLT_SIE: sie_prep_bwd(raw, d, g, graw); break;
+    case GLT_SIS: graw[0] = g[0]; graw[1] = g[1]; graw[2] = g[2]; break;
+    case GLT_NFW: nfw_prep_bwd(raw, d, g, graw, false); break;
+    case GLT_NFW_ELLIPSE: nfw_prep_bwd(raw, d, g, graw, true); break;
+    case GLT_DPIS: dpie_prep_bwd(raw, d, g, graw, false); break;
+    case GLT_DPIE: dpie_prep_bwd(raw, d, g, graw, true); break;
+    case GLT_SERSIC: sersic_prep_bwd(raw, d, g, graw, false, (flags & 1u) != 0); break;
+    case GLT_SERSIC_ELLIPSE: sersic_prep_bwd(raw, d, g, graw, true, (flags & 1u) != 0); break;
+    default: break;
+  }
+}
+
+// deflection of one lens entry at NP points (d = derived block of the entry)
+template <class T, int NP>
+GL_HD void gl_lens_fwd(int type, int ts, const T* d, const T* x, const T* y, T* ax, T* ay) {
+  switch (type) {
+    case GLT_EPL: epl_fwd<T, NP>(d, ts, x, y, ax, ay); break;
+    case GLT_SHEAR: shear_fwd<T, NP>(d, x, y, ax, ay); break;
+    case GLT_SIE: sie_fwd<T, NP>(d, x, y, ax, ay); break;
+    case GLT_SIS: sis_fwd<T, NP>(d, x, y, ax, ay); break;
+    case GLT_NFW: case GLT_NFW_ELLIPSE: nfw_fwd<T, NP>(d, x, y, ax, ay); break;
+    case GLT_DPIS: dpis_fwd<T, NP>(d, x, y, ax, ay); break;
+    case GLT_DPIE: dpie_fwd<T, NP>(d, x, y, ax, ay); break;
+    default:
+#pragma unroll
+      for (int j = 0; j < NP; ++j) { ax[j] = T(0); ay[j] = T(0); }
+  }
+}
+template <class T, int NP>
+GL_HD void gl_lens_bwd(int type, int ts, const T* d, const T* x, const T* y, const T* gax, const T* gay, T* g) {
+  switch (type) {
+    case GLT_EPL: epl_bwd<T, NP>(d, ts, x, y, gax, gay, g); break;
+    case GLT_SHEAR: shear_bwd<T, NP>(d, x, y, gax, gay, g); break;
+    case GLT_SIE: sie_bwd<T, NP>(d, x, y, gax, gay, g); break;
+    case GLT_SIS: sis_bwd<T, NP>(d, x, y, gax, gay, g); break;
+    case GLT_NFW: case GLT_NFW_ELLIPSE: nfw_bwd<T, NP>(d, x, y, gax, gay, g); break;
+    case GLT_DPIS: dpis_bwd<T, NP>(d, x, y, gax, gay, g); break;
+    case GLT_DPIE: dpie_bwd<T, NP>(d, x, y, gax, gay, g); break;
+    default: break;
+  }
+}

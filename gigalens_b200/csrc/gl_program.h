@@ -1,0 +1,210 @@
+// gl_program.h -- the flat "program" a physical model compiles to, and the per-sample /
+// per-pixel drivers that interpret it.  Shared by the CUDA library (device, fp32) and by the
+// test-only host harness (g++, fp32/fp64).
+//
+// A program is the reference's PhysicalModel (src/gigalens/tf/model.py:290-306) flattened:
+// entries [0, n_lens) are deflectors, then lens-light, then source-light profiles.  Each entry
+// owns a slice of the per-sample derived vector (der_off) and of the per-sample dvar-cotangent
+// vector (g_off).  An entry with n_members > 0 is a scaling-relation sum over a galaxy catalogue
+// (src/gigalens/tf/profiles/mass/scaling_relation.py:61-70): it owns n_members consecutive
+// derived blocks and n_members consecutive dvar blocks.
+#pragma once
+#include "gl_math.cuh"
+
+#define GL_MAX_PROF 24
+
+struct GlProf {
+  int type;
+  unsigned flags;
+  int der_off;     // offset of the (first) derived block
+  int der_size;    // size of one derived block (per member)
+  int g_off;       // offset of the (first) dvar block
+  int n_dvars;     // dvars per member
+  int ts;          // EPL table stride
+  int niter;       // EPL iteration cap
+  int n_max;       // Shapelets order
+  int n_members;   // 0 = plain profile
+  int member_off;  // offset into the member-factor array ([n_raw][n_members] per entry)
+  int amp_off;     // Shapelets: offset into the amp-slot array
+  int slot[GL_MAX_RAW];
+  float constant[GL_MAX_RAW];
+};
+
+struct GlProgram {
+  int n_lens, n_ll, n_sl;
+  int n_prof;
+  int der_total;   // floats per sample in the derived vector
+  int g_total;     // floats per sample in the dvar-cotangent vector
+  int n_params;    // P
+  int depth;       // number of linear light components (lstsq)
+  GlProf prof[GL_MAX_PROF];
+};
+
+// ---------------------------------------------------------------------------------------------
+// per-sample: raw gather, prep, prep adjoint
+// ---------------------------------------------------------------------------------------------
+// Gather the raw parameters of entry `pr`, member m, sample b from params[P][bs].
+template <class T, class TP>
+GL_HD void gl_gather_raw(const GlProf& pr, const TP* params, int bs, int b, const float* member_factor, int m, T* raw) {
+  const int nraw = gl_n_raw(pr.type);
+#pragma unroll
+  for (int k = 0; k < GL_MAX_RAW; ++k) {
+    if (k < nraw) {
+      T v = (pr.slot[k] >= 0) ? T(params[(size_t)pr.slot[k] * bs + b]) : T(pr.constant[k]);
+      if (pr.n_members > 0) v *= T(member_factor[pr.member_off + k * pr.n_members + m]);
+      raw[k] = v;
+    } else {
+      raw[k] = T(0);
+    }
+  }
+}
+
+// params -> derived vector of one sample.  epl_fmax: per-entry batch maximum of f, or null for
+// per-sample trip counts.
+template <class T, class TP>
+GL_HD void gl_sample_prep(const GlProgram& P, const TP* params, int bs, int b, const float* member_factor,
+                          const float* epl_fmax, T* der) {
+  for (int i = 0; i < P.n_prof; ++i) {
+    const GlProf& pr = P.prof[i];
+    if (pr.type == GLT_SHAPELETS) {
+      T raw[GL_MAX_RAW];
+      gl_gather_raw<T, TP>(pr, params, bs, b, member_factor, 0, raw);
+      T* d = der + pr.der_off;
+      d[0] = raw[1]; d[1] = raw[2]; d[2] = T(1) / raw[0]; d[3] = T(0);
+      continue;
+    }
+    const int nm = pr.n_members > 0 ? pr.n_members : 1;
+    for (int m = 0; m < nm; ++m) {
+      T raw[GL_MAX_RAW];
+      gl_gather_raw<T, TP>(pr, params, bs, b, member_factor, m, raw);
+      gl_prep<T>(pr.type, pr.flags, pr.niter, raw, der + pr.der_off + m * pr.der_size,
+                 epl_fmax ? T(epl_fmax[i]) : T(-1));
+    }
+  }
+}
+
+// dvar cotangents g[] of one sample -> gparams[P][bs] column b (overwritten).
+template <class T, class TP>
+GL_HD void gl_sample_prep_bwd(const GlProgram& P, const TP* params, int bs, int b, const float* member_factor,
+                              const T* der, const T* g, TP* gparams) {
+  for (int k = 0; k < P.n_params; ++k) gparams[(size_t)k * bs + b] = TP(0);
+  for (int i = 0; i < P.n_prof; ++i) {
+    const GlProf& pr = P.prof[i];
+    const int nraw = gl_n_raw(pr.type);
+    if (pr.type == GLT_SHAPELETS) {
+      T raw[GL_MAX_RAW];
+      gl_gather_raw<T, TP>(pr, params, bs, b, member_factor, 0, raw);
+      const T* gg = g + pr.g_off;   // cx, cy, invbeta
+      T graw[3] = {-gg[2] / (raw[0] * raw[0]), gg[0], gg[1]};
+      for (int k = 0; k < 3; ++k)
+        if (pr.slot[k] >= 0) gparams[(size_t)pr.slot[k] * bs + b] += TP(graw[k]);
+      continue;
+    }
+    const int nm = pr.n_members > 0 ? pr.n_members : 1;
+    T gbase[GL_MAX_RAW];
+    for (int k = 0; k < GL_MAX_RAW; ++k) gbase[k] = T(0);
+    for (int m = 0; m < nm; ++m) {
+      T raw[GL_MAX_RAW], graw[GL_MAX_RAW];
+      gl_gather_raw<T, TP>(pr, params, bs, b, member_factor, m, raw);
+      for (int k = 0; k < GL_MAX_RAW; ++k) graw[k] = T(0);
+      gl_prep_bwd<T>(pr.type, pr.flags, raw, der + pr.der_off + m * pr.der_size, g + pr.g_off + m * pr.n_dvars, graw);
+      for (int k = 0; k < nraw; ++k) {
+        T fac = pr.n_members > 0 ? T(member_factor[pr.member_off + k * pr.n_members + m]) : T(1);
+        gbase[k] += graw[k] * fac;
+      }
+    }
+    for (int k = 0; k < nraw; ++k)
+      if (pr.slot[k] >= 0) gparams[(size_t)pr.slot[k] * bs + b] += TP(gbase[k]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-pixel drivers (NP pixels of one sample at a time; der = derived vector of the sample)
+// ---------------------------------------------------------------------------------------------
+// beta = theta - sum_i alpha_i(theta)   (src/gigalens/tf/simulator.py:72-78)
+template <class T, int NP>
+GL_HD void gl_pix_beta(const GlProgram& P, const T* der, const T* x, const T* y, T* bx, T* by) {
+#pragma unroll
+  for (int j = 0; j < NP; ++j) { bx[j] = x[j]; by[j] = y[j]; }
+  for (int i = 0; i < P.n_lens; ++i) {
+    const GlProf& pr = P.prof[i];
+    const int nm = pr.n_members > 0 ? pr.n_members : 1;
+    for (int m = 0; m < nm; ++m) {
+      T ax[NP], ay[NP];
+      gl_lens_fwd<T, NP>(pr.type, pr.ts, der + pr.der_off + m * pr.der_size, x, y, ax, ay);
+#pragma unroll
+      for (int j = 0; j < NP; ++j) { bx[j] -= ax[j]; by[j] -= ay[j]; }
+    }
+  }
+}
+
+// Supersampled surface brightness before the NaN scrub (tf/simulator.py:124-138), non-lstsq mode.
+template <class T, int NP>
+GL_HD void gl_pix_image(const GlProgram& P, const T* der, const T* x, const T* y, bool no_deflection, T* out) {
+  T bx[NP], by[NP];
+  if (no_deflection) {
+#pragma unroll
+    for (int j = 0; j < NP; ++j) { bx[j] = x[j]; by[j] = y[j]; }
+  } else {
+    gl_pix_beta<T, NP>(P, der, x, y, bx, by);
+  }
+#pragma unroll
+  for (int j = 0; j < NP; ++j) out[j] = T(0);
+  for (int i = P.n_lens; i < P.n_prof; ++i) {
+    const GlProf& pr = P.prof[i];
+    const bool src = i >= P.n_lens + P.n_ll;
+    const T* px = src ? bx : x;
+    const T* py = src ? by : y;
+    switch (pr.type) {
+      case GLT_SERSIC: case GLT_SERSIC_ELLIPSE: sersic_fwd<T, NP>(der + pr.der_off, px, py, out); break;
+      default: break;
+    }
+  }
+}
+
+// Adjoint of gl_pix_image: gS is the cotangent of the (scrubbed) surface brightness at the NP
+// pixels.  `flush(acc, n, off)` receives the NP-pixel partial cotangent of dvars [off, off+n) --
+// the host harness adds it into a vector, the CUDA kernel warp-reduces it into shared memory.
+template <class T, int NP, class Flush>
+GL_HD void gl_pix_image_bwd(const GlProgram& P, const T* der, const T* x, const T* y, const T* gS,
+                            bool no_deflection, Flush& flush) {
+  T bx[NP], by[NP], Gx[NP], Gy[NP];
+  if (no_deflection) {
+#pragma unroll
+    for (int j = 0; j < NP; ++j) { bx[j] = x[j]; by[j] = y[j]; }
+  } else {
+    gl_pix_beta<T, NP>(P, der, x, y, bx, by);
+  }
+#pragma unroll
+  for (int j = 0; j < NP; ++j) { Gx[j] = T(0); Gy[j] = T(0); }
+  for (int i = P.n_lens; i < P.n_prof; ++i) {
+    const GlProf& pr = P.prof[i];
+    const bool src = i >= P.n_lens + P.n_ll;
+    T acc[GL_MAX_DVARS];
+#pragma unroll
+    for (int k = 0; k < GL_MAX_DVARS; ++k) acc[k] = T(0);
+    switch (pr.type) {
+      case GLT_SERSIC: case GLT_SERSIC_ELLIPSE:
+        if (src) sersic_bwd<T, NP>(der + pr.der_off, bx, by, gS, acc, Gx, Gy);
+        else sersic_bwd<T, NP>(der + pr.der_off, x, y, gS, acc, (T*)nullptr, (T*)nullptr);
+        break;
+      default: break;
+    }
+    flush(acc, pr.n_dvars, pr.g_off);
+  }
+  if (no_deflection) return;
+  // d(beta)/d(lens) = -d(alpha): cotangent of each deflection is (-Gx, -Gy)
+#pragma unroll
+  for (int j = 0; j < NP; ++j) { Gx[j] = -Gx[j]; Gy[j] = -Gy[j]; }
+  for (int i = 0; i < P.n_lens; ++i) {
+    const GlProf& pr = P.prof[i];
+    const int nm = pr.n_members > 0 ? pr.n_members : 1;
+    for (int m = 0; m < nm; ++m) {
+      T acc[GL_MAX_DVARS];
+#pragma unroll
+      for (int k = 0; k < GL_MAX_DVARS; ++k) acc[k] = T(0);
+      gl_lens_bwd<T, NP>(pr.type, pr.ts, der + pr.der_off + m * pr.der_size, x, y, Gx, Gy, acc);
+      flush(acc, pr.n_dvars, pr.g_off + m * pr.n_dvars);
+    }
+  }
+}

@@ -1,0 +1,171 @@
+/*
+ * gigalens_b200 -- C ABI of the B200-native forward model (libgigalens_b200.so).
+ *
+ * The reference (furcelay/gigalens) is pure Python on TensorFlow/JAX and has no FFI of its
+ * own; the entry points below are what a binding for its hot path would bind.  Each one
+ * cites the reference interface it replaces (paths relative to /root/reference).
+ * INTEGRATION.md shows the reference-side ctypes stub.
+ *
+ * Conventions
+ *   - Plain C: opaque plan handle, plain pointers and sizes, `int` status (0 = ok), message via
+ *     gl_last_error() (thread-local).  No exceptions cross the ABI, no torch types.
+ *   - "dev" pointers are CUDA device pointers owned by the caller; "host" pointers are ordinary
+ *     host memory.  The plan owns only its workspace and its copies of the static inputs
+ *     (grid, mask, PSF, observation, catalogue).  No allocation happens per call.
+ *   - Kernels are launched asynchronously on the caller's `stream` (a cudaStream_t passed as
+ *     void*; NULL = legacy default stream).  No entry point synchronises except the *_host ones.
+ *   - A plan is bound to one device and one batch size and is not thread-safe.
+ *   - Parameters cross as SoA fp32 `params[P][bs]` (row = one free parameter, the natural layout
+ *     after the reference's tfb.Split, src/gigalens/tf/model.py:78-85).  All arithmetic is fp32
+ *     like the reference (tf.float32 throughout, e.g. src/gigalens/tf/simulator.py:27-32).
+ */
+#ifndef GIGALENS_B200_H
+#define GIGALENS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GL_ABI_VERSION 1
+#define GL_MAX_PROFILE_PARAMS 8
+
+/* Profile type ids.  The raw-parameter order of each type is fixed here and mirrors the
+ * keyword names of the reference's `deriv` / `light`. */
+typedef enum {
+  GL_EPL = 1,          /* theta_E, gamma, e1, e2, center_x, center_y      tf/profiles/mass/epl.py:12-57 */
+  GL_SHEAR = 2,        /* gamma1, gamma2                                  tf/profiles/mass/shear.py:8-16 */
+  GL_SIE = 3,          /* theta_E, e1, e2, center_x, center_y             tf/profiles/mass/sie.py:6-42 */
+  GL_SIS = 4,          /* theta_E, center_x, center_y                     tf/profiles/mass/sis.py:6-17 */
+  GL_NFW = 5,          /* Rs, alpha_Rs, center_x, center_y                tf/profiles/mass/nfw.py:7-52 */
+  GL_NFW_ELLIPSE = 6,  /* Rs, alpha_Rs, e1, e2, center_x, center_y        tf/profiles/mass/nfw.py:99-134 */
+  GL_DPIS = 7,         /* theta_E, r_core, r_cut, center_x, center_y      tf/profiles/mass/piemd.py:26-60 */
+  GL_DPIE = 8,         /* theta_E, r_core, r_cut, e1, e2, center_x, center_y  tf/profiles/mass/piemd.py:98-119,183-255 */
+  GL_SERSIC = 32,          /* R_sersic, n_sersic, center_x, center_y, Ie          tf/profiles/light/sersic.py:22-35 */
+  GL_SERSIC_ELLIPSE = 33,  /* R_sersic, n_sersic, e1, e2, center_x, center_y, Ie  tf/profiles/light/sersic.py:67-80 */
+  GL_SHAPELETS = 34        /* beta, center_x, center_y (+ amplitudes)              tf/profiles/light/shapelets.py:17-75 */
+} gl_profile_type;
+
+#define GL_FLAG_USE_LSTSQ 1u   /* LightProfile.use_lstsq  (src/gigalens/profile.py:36-41) */
+#define GL_FLAG_INTERPOLATE 2u /* Shapelets(interpolate=True)  (shapelets.py:20,54-66) */
+
+/* One profile of the physical model.
+ *
+ * Raw parameter k of sample b is  base_k(b) * member_factor[k*n_members + g]  where
+ * base_k(b) = params[slot[k]][b] if slot[k] >= 0 else constant[k], and the factor is 1 when
+ * n_members == 0.  n_members > 0 makes this entry a scaling-relation sum over a galaxy
+ * catalogue (tf/profiles/mass/scaling_relation.py:57-70): scaled parameters carry
+ * (L_g/L*)^power_k in member_factor, catalogue columns carry constant[k]=1 and the catalogue
+ * value in member_factor, and the deflection is summed over the n_members members. */
+typedef struct {
+  int32_t type;                           /* gl_profile_type */
+  uint32_t flags;                         /* GL_FLAG_* */
+  int32_t slot[GL_MAX_PROFILE_PARAMS];    /* row of params[P][bs], or -1 = constant */
+  float constant[GL_MAX_PROFILE_PARAMS];  /* used when slot[k] < 0 */
+  int32_t niter;                          /* GL_EPL: iteration cap (EPL(niter=50), epl.py:15) */
+  int32_t n_max;                          /* GL_SHAPELETS: maximum order */
+  const int32_t* amp_slot;                /* GL_SHAPELETS without use_lstsq: [n_layers] rows of params, host */
+  int32_t n_members;                      /* 0, or G for a scaling-relation sum */
+  const float* member_factor;             /* host, [n_raw_params(type)][n_members], NULL if n_members == 0 */
+} gl_profile_desc;
+
+/* PhysicalModel(lenses, lens_light, source_light, *_constants): src/gigalens/tf/model.py:290-306 */
+typedef struct {
+  int32_t n_lens, n_lens_light, n_source_light;
+  const gl_profile_desc* lens;
+  const gl_profile_desc* lens_light;
+  const gl_profile_desc* source_light;
+  int32_t n_params;                       /* P: rows of params[P][bs] */
+} gl_model_desc;
+
+/* SimulatorConfig + the host-side setup of LensSimulator.__init__:
+ * src/gigalens/simulator.py:11-29, src/gigalens/tf/simulator.py:14-70 */
+typedef struct {
+  int32_t num_pix;          /* n: the image is n x n */
+  int32_t supersample;      /* ss: ray-shooting grid is (n*ss) x (n*ss) */
+  const float* grid_x;      /* host [(n*ss)^2] row-major: LensWCS.pix2angle x of every ss pixel (tf/simulator.py:45) */
+  const float* grid_y;      /* host [(n*ss)^2] */
+  const float* psf;         /* host [psf_n*psf_n]: the kernel exactly as handed to tf.nn.conv2d, i.e.
+                               subgrid_kernel(kernel, ss, odd=True)[::-1, ::-1] (tf/simulator.py:62-70); NULL = no PSF */
+  int32_t psf_n;
+  const uint8_t* mask;      /* host [n*n] pix_region (non-zero = used), NULL = all pixels (tf/simulator.py:34-44) */
+  float conversion_factor;  /* det(transform_pix2angle), tf/simulator.py:27-29 */
+} gl_sim_config;
+
+/* Pixel likelihood of ForwardProbModel.stats_pixels (src/gigalens/tf/model.py:89-101) or, with
+ * fixed_error_map, the Independent(Normal(obs, err)) of BackwardProbModel (:221-226,266-267). */
+typedef struct {
+  const float* observed;    /* host [n*n] */
+  const float* error_map;   /* host [n*n] or NULL => sqrt(background_rms^2 + im_sim/exp_time) */
+  float background_rms;
+  float exp_time;
+} gl_like_config;
+
+/* Prior + default event-space bijector of one flattened leaf (the reference
+ * delegates these to TFP: tf/model.py:76-87,148,164-166). */
+typedef enum { GL_DIST_NORMAL = 0, GL_DIST_LOGNORMAL = 1, GL_DIST_UNIFORM = 2, GL_DIST_TRUNCNORMAL = 3 } gl_dist_type;
+typedef struct {
+  int32_t dist;        /* gl_dist_type */
+  int32_t slot;        /* row of params[P][bs] this leaf feeds (simulator slot order) */
+  float a, b;          /* Normal/LogNormal/TruncNormal: loc, scale.  Uniform: low, high */
+  float low, high;     /* TruncNormal bounds */
+} gl_prior_leaf;
+
+typedef struct gl_plan gl_plan;
+
+/* --- lifecycle ------------------------------------------------------------------------- */
+/* LensSimulator(phys_model, sim_config, bs): tf/simulator.py:14-70 */
+int gl_plan_create(const gl_model_desc* model, const gl_sim_config* sim, int32_t bs, int32_t device, gl_plan** out);
+/* ForwardProbModel(prior, observed_image, background_rms, exp_time, error_map): tf/model.py:32-66 */
+int gl_plan_set_likelihood(gl_plan* plan, const gl_like_config* like);
+/* prior / bijector leaves in z-column order (tf/model.py:76-87); d = n_leaves */
+int gl_plan_set_prior(gl_plan* plan, const gl_prior_leaf* leaves, int32_t n_leaves);
+void gl_plan_destroy(gl_plan* plan);
+const char* gl_last_error(void);
+int32_t gl_abi_version(void);
+/* number of kernels the library has launched in this process (bench.py's gpu_launches) */
+int64_t gl_launch_count(void);
+
+/* --- simulate -------------------------------------------------------------------------- */
+/* LensSimulator.simulate(params): tf/simulator.py:109-156.  image_dev [bs][n][n]. */
+int gl_simulate(gl_plan* plan, const float* params_dev, float* image_dev, void* stream);
+/* The supersampled pre-convolution image after the NaN scrub (tf/simulator.py:124-140),
+ * ss_dev [bs][n*ss][n*ss].  Diagnostic / parity entry point. */
+int gl_simulate_ss(gl_plan* plan, const float* params_dev, float* ss_dev, void* stream);
+/* LensSimulator.beta(x, y, lens_params) at arbitrary points: tf/simulator.py:72-78.
+ * x,y [npts] shared by all samples; beta_* [bs][npts]. */
+int gl_beta(gl_plan* plan, const float* params_dev, int32_t npts, const float* x_dev, const float* y_dev,
+            float* beta_x_dev, float* beta_y_dev, void* stream);
+
+/* --- likelihood and gradient ----------------------------------------------------------- */
+/* ForwardProbModel.stats_pixels + d(log_like)/d(params): tf/model.py:89-101 with the gradient
+ * tf.GradientTape would give (tf/inference.py:34-37).  loglike/red_chi2 [bs]; dparams [P][bs] or
+ * NULL for forward only. */
+int gl_loglike_grad(gl_plan* plan, const float* params_dev, float* loglike_dev, float* red_chi2_dev,
+                    float* dparams_dev, void* stream);
+/* ForwardProbModel.log_prob(simulator, z) and its gradient: tf/model.py:126-167.
+ * z [bs][d] row-major (unconstrained); logp/red_chi2 [bs]; dz [bs][d] or NULL. */
+int gl_logprob_grad(gl_plan* plan, const float* z_dev, float* logp_dev, float* red_chi2_dev, float* dz_dev,
+                    void* stream);
+/* bij.forward(z) -> params[P][bs] and log_prior(z) [bs] (either output may be NULL): tf/model.py:148,164-166,183-185 */
+int gl_unconstrain(gl_plan* plan, const float* z_dev, float* params_dev, float* logprior_dev, void* stream);
+
+/* Host-buffer convenience wrappers (pinned or pageable host memory): copy in, run, copy out,
+ * synchronise.  These are the calls a reference-side binding would make per optimiser step. */
+int gl_logprob_grad_host(gl_plan* plan, const float* z_host, float* logp_host, float* red_chi2_host, float* dz_host);
+int gl_simulate_host(gl_plan* plan, const float* params_host, float* image_host);
+
+/* --- linear light-amplitude solve ------------------------------------------------------ */
+/* LensSimulator.lstsq_simulate(params, observed_image, err_map, return_coeffs): tf/simulator.py:158-240
+ * (layout jax/simulator.py:171-195).  image_dev [bs][n][n] or NULL; coeffs_dev [bs][D] or NULL. */
+int gl_lstsq_simulate(gl_plan* plan, const float* params_dev, float* image_dev, float* coeffs_dev, void* stream);
+/* BackwardProbModel.log_prob likelihood part + gradient w.r.t. the non-linear params: tf/model.py:242-273 */
+int gl_lstsq_loglike_grad(gl_plan* plan, const float* params_dev, float* loglike_dev, float* red_chi2_dev,
+                          float* dparams_dev, void* stream);
+int32_t gl_plan_depth(const gl_plan* plan); /* D: number of linear light components */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GIGALENS_B200_H */

@@ -1,0 +1,83 @@
+// hostcheck.cpp -- TEST-ONLY host build of the device arithmetic (gl_math.cuh / gl_program.h).
+//
+// Compiled by g++ (no CUDA) from tests/test_hostcheck.py into tests/hostcheck/_build/.  It runs
+// the exact template code the sm_100a kernels instantiate -- prep, per-pixel forward, per-pixel
+// adjoint, prep adjoint -- in fp32 and fp64 with plain loops, so every formula and every hand
+// adjoint can be checked against the oracle's autograd on a machine without a GPU.  Nothing
+// under gigalens_b200/ loads this library; it is not a CPU fallback.
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../gigalens_b200/csrc/gl_build.h"
+
+static thread_local std::string g_err;
+
+template <class T>
+struct HostFlush {
+  T* g;
+  void operator()(const T* acc, int n, int off) { for (int k = 0; k < n; ++k) g[off + k] += acc[k]; }
+};
+
+template <class T>
+static int run(const gl_model_desc* m, int bs, const T* params, int npix, const T* gx, const T* gy, int no_deflection,
+               int epl_batch_max, T* ss_out, const T* g_ss, T* gparams, T* beta_out) {
+  GlBuilt B;
+  std::string e = gl_build_program(m, B);
+  if (!e.empty()) { g_err = e; return 1; }
+  const GlProgram& P = B.prog;
+  const float* mf = B.member_factor.empty() ? nullptr : B.member_factor.data();
+  std::vector<float> fmax(P.n_prof, -1.f);
+  if (epl_batch_max) {
+    for (int i = 0; i < P.n_lens; ++i) {
+      if (P.prof[i].type != GLT_EPL) continue;
+      T best = T(0);
+      for (int b = 0; b < bs; ++b) {
+        T raw[GL_MAX_RAW];
+        gl_gather_raw<T, T>(P.prof[i], params, bs, b, mf, 0, raw);
+        T phi, q, c;
+        ellip_fwd(raw[2], raw[3], T(1), phi, q, c);
+        T f = (T(1) - q) / (T(1) + q);
+        if (f > best) best = f;
+      }
+      fmax[i] = (float)best;
+    }
+  }
+  std::vector<T> der(P.der_total), g(P.g_total > 0 ? P.g_total : 1);
+  for (int b = 0; b < bs; ++b) {
+    gl_sample_prep<T, T>(P, params, bs, b, mf, epl_batch_max ? fmax.data() : nullptr, der.data());
+    std::fill(g.begin(), g.end(), T(0));
+    HostFlush<T> fl{g.data()};
+    for (int p = 0; p < npix; ++p) {
+      T x[1] = {gx[p]}, y[1] = {gy[p]}, v[1];
+      if (ss_out) {
+        gl_pix_image<T, 1>(P, der.data(), x, y, no_deflection != 0, v);
+        ss_out[(size_t)b * npix + p] = gl_isnan(v[0]) ? T(0) : v[0];
+      }
+      if (beta_out) {
+        T bx[1], by[1];
+        gl_pix_beta<T, 1>(P, der.data(), x, y, bx, by);
+        beta_out[((size_t)b * 2 + 0) * npix + p] = bx[0];
+        beta_out[((size_t)b * 2 + 1) * npix + p] = by[0];
+      }
+      if (g_ss && gparams) {
+        T gs[1] = {g_ss[(size_t)b * npix + p]};
+        gl_pix_image_bwd<T, 1>(P, der.data(), x, y, gs, no_deflection != 0, fl);
+      }
+    }
+    if (g_ss && gparams) gl_sample_prep_bwd<T, T>(P, params, bs, b, mf, der.data(), g.data(), gparams);
+  }
+  return 0;
+}
+
+extern "C" {
+const char* glh_last_error() { return g_err.c_str(); }
+int glh_run_f64(const gl_model_desc* m, int bs, const double* params, int npix, const double* gx, const double* gy,
+                int no_deflection, int epl_batch_max, double* ss_out, const double* g_ss, double* gparams, double* beta_out) {
+  return run<double>(m, bs, params, npix, gx, gy, no_deflection, epl_batch_max, ss_out, g_ss, gparams, beta_out);
+}
+int glh_run_f32(const gl_model_desc* m, int bs, const float* params, int npix, const float* gx, const float* gy,
+                int no_deflection, int epl_batch_max, float* ss_out, const float* g_ss, float* gparams, float* beta_out) {
+  return run<float>(m, bs, params, npix, gx, gy, no_deflection, epl_batch_max, ss_out, g_ss, gparams, beta_out);
+}
+}
