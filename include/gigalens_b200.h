@@ -121,6 +121,9 @@ int gl_plan_create(const gl_model_desc* model, const gl_sim_config* sim, int32_t
 int gl_plan_set_likelihood(gl_plan* plan, const gl_like_config* like);
 /* prior / bijector leaves in z-column order (tf/model.py:76-87); d = n_leaves */
 int gl_plan_set_prior(gl_plan* plan, const gl_prior_leaf* leaves, int32_t n_leaves);
+/* Options.  "epl_batch_max" = 1: EPL series length from the batch maximum of f exactly like
+ * tf/profiles/mass/epl.py:37 (default 0: per-sample length, identical to fp32 rounding). */
+int gl_plan_set_option(gl_plan* plan, const char* name, int32_t value);
 void gl_plan_destroy(gl_plan* plan);
 const char* gl_last_error(void);
 int32_t gl_abi_version(void);
@@ -137,6 +140,12 @@ int gl_simulate_ss(gl_plan* plan, const float* params_dev, float* ss_dev, void* 
  * x,y [npts] shared by all samples; beta_* [bs][npts]. */
 int gl_beta(gl_plan* plan, const float* params_dev, int32_t npts, const float* x_dev, const float* y_dev,
             float* beta_x_dev, float* beta_y_dev, void* stream);
+
+/* Total deflection (mode 1: out0 = alpha_x, out1 = alpha_y), beta (mode 0) or surface brightness
+ * (mode 2: out0 only) at arbitrary points: MassProfile.deriv / LightProfile.light as the reference's
+ * profile tests call them (tests/test_profiles.py:14-111).  out* [bs][npts]. */
+int gl_eval_points(gl_plan* plan, const float* params_dev, int32_t npts, const float* x_dev, const float* y_dev,
+                   int32_t mode, float* out0_dev, float* out1_dev, void* stream);
 
 /* --- likelihood and gradient ----------------------------------------------------------- */
 /* ForwardProbModel.stats_pixels + d(log_like)/d(params): tf/model.py:89-101 with the gradient

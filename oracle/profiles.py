@@ -298,8 +298,11 @@ class ScalingRelation:
             self._galaxy_constants.append(
                 {k: torch.as_tensor(np.asarray(galaxy_catalogue[k], dtype=np.float32)[chunk]).to(dtype)
                  for k in self.not_scaling_params})
+            # fp32 constants in the reference (:52-54); computed in fp32 then promoted so that the fp64
+            # arbiter run sees the same catalogue-derived inputs as the fp32 run.
+            lum32 = np.asarray(galaxy_catalogue["lum"], dtype=np.float32)[chunk]
             self._unscaled_params.append(
-                {k: (lum[chunk] / torch.as_tensor(lum_star, dtype=dtype)) ** self.power[k]
+                {k: torch.as_tensor((lum32 / np.float32(lum_star)) ** np.float32(self.power[k])).to(dtype)
                  for k in self.scaling_params})
 
     def deriv(self, x, y, **scales):

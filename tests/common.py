@@ -114,3 +114,35 @@ def host_run(cm: CompiledModel, mat, gx, gy, g_ss=None, dtype=np.float64, no_def
     if rc != 0:
         raise RuntimeError(lib.glh_last_error().decode())
     return dict(ss=ss, gparams=gparams, beta=beta)
+
+
+# ---------------------------------------------------------------- parity rule
+def ulp_perturb(mat, seed=99):
+    """The same fp32 inputs moved by +-1/2 ulp(fp32) relative: an input error no fp32 computation can
+    distinguish from its own first rounding.  Used to probe the conditioning of a test case."""
+    rng = np.random.default_rng(seed)
+    return np.asarray(mat, dtype=np.float64) * (1.0 + rng.choice([-1.0, 1.0], size=np.shape(mat)) * 2.0 ** -24)
+
+
+def assert_parity(cuda, o32, o64, tol, what, o64_perturbed=None, factor=4.0, axis=None):
+    """The parity rule (DESIGN.md "Parity metric").
+
+    error(a) = max|a - o64| / max|o64| over `axis` (None = the whole array); the worst slice decides.
+    The CUDA (or float-instantiated) result must satisfy  error <= tol  -- BASELINE.json's 1e-5 for
+    images / log-likelihoods, 1e-4 for gradients -- except where fp32 arithmetic itself cannot hold
+    `tol` for that input (cuspy Sersic cores under the lens mapping, NFW at X ~ 1, the dPIE log
+    ratio): there the bound is `factor` x the fp32 noise floor of the case, measured as the larger of
+    (i) the fp32 oracle's own error against the fp64 oracle and (ii) the change of the fp64 oracle
+    when its inputs move by half an fp32 ulp.  The median slice must hold `tol` outright."""
+    cuda, o32, o64 = (np.asarray(v, dtype=np.float64) for v in (cuda, o32, o64))
+    red = (lambda v: np.max(v)) if axis is None else (lambda v: np.max(v, axis=axis))
+    scale = red(np.abs(o64))
+    e_c = red(np.abs(cuda - o64)) / scale
+    floor = red(np.abs(o32 - o64)) / scale
+    if o64_perturbed is not None:
+        floor = np.maximum(floor, red(np.abs(np.asarray(o64_perturbed, dtype=np.float64) - o64)) / scale)
+    bad = np.atleast_1d(e_c > np.maximum(tol, factor * floor))
+    assert not bad.any(), (what, np.nonzero(bad)[0][:8], np.atleast_1d(e_c)[bad][:8], np.atleast_1d(floor)[bad][:8])
+    if axis is not None and np.size(e_c) >= 4:
+        assert np.median(e_c) <= tol, (what, "median", float(np.median(e_c)))
+    return float(np.max(e_c))

@@ -1,0 +1,94 @@
+"""CPU tests of the device arithmetic: gl_math.cuh / gl_program.h compiled by g++ into the
+test-only host harness (tests/hostcheck) and compared with the oracle's autograd.  fp64 pins
+every formula and hand adjoint to ~1e-12; fp32 shows the float instantiation the kernels use
+stays within the fp32 oracle's own rounding.  (This harness is not a product path.)"""
+import numpy as np
+import pytest
+import torch
+
+import common
+from common import CompiledModel, PhysicalModel, draw_matrix, host_run, matrix_to_pytree, to_oracle_model
+from gigalens_b200.profiles.light import sersic
+from gigalens_b200.profiles.mass import dpie_subhalo, epl, nfw, piemd, shear, sie, sis
+from oracle.simulator import OracleSimulator
+
+SRC = lambda: [sersic.SersicEllipse()]
+
+
+def _catalogue(G=5, seed=7):
+    rng = np.random.default_rng(seed)
+    e = rng.normal(0, 0.1, size=(2, G))
+    return dict(lum=rng.lognormal(0, 0.5, G).tolist(), center_x=rng.uniform(-1, 1, G).tolist(),
+                center_y=rng.uniform(-1, 1, G).tolist(), e1=(e[0] + 0.05).tolist(), e2=(e[1] - 0.04).tolist())
+
+
+MODELS = {
+    "c2": lambda: PhysicalModel([epl.EPL(50), shear.Shear()], [sersic.SersicEllipse()], SRC()),
+    "sis": lambda: PhysicalModel([sis.SIS()], [sersic.Sersic()], SRC()),
+    "sie": lambda: PhysicalModel([sie.SIE()], [], SRC()),
+    "nfw": lambda: PhysicalModel([nfw.NFW()], [], SRC()),
+    "nfw_ellipse": lambda: PhysicalModel([nfw.NFW_ELLIPSE()], [], SRC()),
+    "dpis": lambda: PhysicalModel([piemd.DPIS()], [], SRC()),
+    "dpie": lambda: PhysicalModel([piemd.DPIE()], [], SRC()),
+    "constants": lambda: PhysicalModel([epl.EPL(20), shear.Shear()], [], [sersic.Sersic()],
+                                       lenses_constants=[{"gamma": 2.1, "center_x": 0.05}, {}],
+                                       source_light_constants=[{"n_sersic": 1.5}]),
+    "cluster": lambda: PhysicalModel([nfw.NFW(), dpie_subhalo.DPIESubhalo(1.0, _catalogue()), shear.Shear()], [], SRC()),
+}
+
+
+def _reference(pm, mat, dtype, seed, num_pix=12, delta=0.25):
+    bs = mat.shape[1]
+    cm = CompiledModel(pm)
+    sim = OracleSimulator(to_oracle_model(pm, dtype), delta, num_pix, 1, bs=bs, dtype=dtype)
+    params, leaf = matrix_to_pytree(cm, mat, dtype, True)
+    S = sim.simulate_ss(params).reshape(-1, bs).T
+    G = np.random.default_rng(seed + 1).normal(size=tuple(S.shape))
+    (S * torch.as_tensor(G, dtype=dtype)).sum().backward()
+    return cm, sim.img_X[:, 0].numpy(), sim.img_Y[:, 0].numpy(), S.detach().numpy(), G, leaf.grad.numpy()
+
+
+@pytest.mark.parametrize("name", sorted(MODELS))
+def test_formulas_and_adjoints_fp64(name):
+    pm = MODELS[name]()
+    mat = draw_matrix(CompiledModel(pm), 3, seed=1)
+    cm, gx, gy, S, G, gref = _reference(pm, mat, torch.float64, 1)
+    out = host_run(cm, mat, gx, gy, g_ss=G, dtype=np.float64)
+    assert np.max(np.abs(out["ss"] - S)) / np.max(np.abs(S)) < 1e-11
+    for k in range(cm.n_params):
+        assert np.max(np.abs(out["gparams"][k] - gref[k])) / np.max(np.abs(gref[k])) < 1e-9, cm.slot_keys[k]
+
+
+@pytest.mark.parametrize("name", sorted(MODELS))
+def test_float_instantiation_tracks_fp32_oracle(name):
+    pm = MODELS[name]()
+    mat = draw_matrix(CompiledModel(pm), 3, seed=2).astype(np.float32)
+    cm, gx, gy, S64, G, g64 = _reference(pm, mat.astype(np.float64), torch.float64, 2)
+    _, _, _, S32, _, g32 = _reference(pm, mat.astype(np.float64), torch.float32, 2)
+    _, _, _, S64p, _, g64p = _reference(pm, common.ulp_perturb(mat), torch.float64, 2)
+    out = host_run(cm, mat, gx, gy, g_ss=G, dtype=np.float32)
+    common.assert_parity(out["ss"], S32, S64, 1e-5, "ss image", S64p, axis=1)
+    for k in range(cm.n_params):
+        common.assert_parity(out["gparams"][k], g32[k], g64[k], 1e-4, f"grad {cm.slot_keys[k]}", g64p[k])
+
+
+def test_epl_per_sample_trip_count_equals_batch_max():
+    """Per-sample series length (the CUDA default) vs the reference's batch-global length."""
+    pm = MODELS["c2"]()
+    mat = draw_matrix(CompiledModel(pm), 6, seed=3)
+    cm, gx, gy, S, G, gref = _reference(pm, mat, torch.float64, 3)
+    a = host_run(cm, mat, gx, gy, g_ss=G, dtype=np.float64, epl_batch_max=True)
+    b = host_run(cm, mat, gx, gy, g_ss=G, dtype=np.float64, epl_batch_max=False)
+    assert np.max(np.abs(a["ss"] - b["ss"])) / np.max(np.abs(S)) < 1e-10
+    assert np.max(np.abs(a["gparams"] - b["gparams"]) / np.max(np.abs(gref), axis=1, keepdims=True)) < 1e-9
+
+
+def test_beta_matches_oracle():
+    pm = MODELS["c2"]()
+    cm = CompiledModel(pm)
+    mat = draw_matrix(cm, 2, seed=4)
+    sim = OracleSimulator(to_oracle_model(pm, torch.float64), 0.25, 12, 1, bs=2, dtype=torch.float64)
+    params, _ = matrix_to_pytree(cm, mat, torch.float64)
+    bx, by = sim.beta(sim.img_X, sim.img_Y, params["lens_mass"])
+    out = host_run(cm, mat, sim.img_X[:, 0].numpy(), sim.img_Y[:, 0].numpy(), dtype=np.float64, want_beta=True)
+    assert np.allclose(out["beta"][:, 0], bx.numpy().T, atol=1e-12) and np.allclose(out["beta"][:, 1], by.numpy().T, atol=1e-12)

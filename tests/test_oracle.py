@@ -1,0 +1,186 @@
+"""CPU tests pinning the oracle (no GPU): the framework-free known-answer tests recoverable from
+the reference's own tests (tests/test_profiles.py, tests/tf/test_model.py), cross-profile
+identities, the demo.npy image-level pin, golden vectors, and fp64 finite differences."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import common
+import oracle_bridge
+from gigalens_b200 import workloads
+from oracle import model as OM
+from oracle import profiles as OP
+from oracle.simulator import OracleSimulator, subgrid_kernel
+
+D = torch.float64
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def pts(n=2000, seed=0, dtype=D):
+    rng = np.random.default_rng(seed)
+    return torch.as_tensor(rng.normal(size=n), dtype=dtype), torch.as_tensor(rng.normal(size=n), dtype=dtype)
+
+
+def test_sersic_half_light_identity():
+    # reference tests/test_profiles.py:17-26
+    se = OP.SersicEllipse()
+    a = se.light(torch.tensor(0.0, dtype=D), torch.tensor(1.0, dtype=D), R_sersic=1.0, n_sersic=2.0, e1=0.0, e2=0.0,
+                 center_x=0.0, center_y=0.0, Ie=5.0)
+    assert math.isclose(float(a), 5.0)
+
+
+def test_epl_isothermal_round_is_sis():
+    # tests/test_profiles.py:55-58 with :71-74 : EPL(theta_E=1, gamma=2, e=0) == SIS == (x/r, y/r)
+    x, y = pts()
+    ax, ay = OP.EPL(100).deriv(x, y, theta_E=1.0, gamma=2.0, e1=0.0, e2=0.0, center_x=0.0, center_y=0.0)
+    sx, sy = OP.SIS().deriv(x, y, theta_E=1.0, center_x=0.0, center_y=0.0)
+    r = torch.sqrt(x ** 2 + y ** 2)
+    assert torch.allclose(ax, sx, rtol=1e-5, atol=1e-4) and torch.allclose(ay, sy, rtol=1e-5, atol=1e-4)
+    assert torch.allclose(sx, x / r) and torch.allclose(sy, y / r)
+
+
+def test_epl_gamma2_equals_sie():
+    # both use b = theta_E sqrt(q): the framework-free test of the EPL series with e != 0
+    x, y = pts()
+    kw = dict(theta_E=1.2, e1=0.1, e2=-0.1, center_x=0.0, center_y=0.0)
+    ax, ay = OP.EPL(100).deriv(x, y, gamma=2.0, **kw)
+    sx, sy = OP.SIE().deriv(x, y, **kw)
+    assert torch.allclose(ax, sx, rtol=0, atol=1e-12) and torch.allclose(ay, sy, rtol=0, atol=1e-12)
+
+
+def test_sie_small_e_is_sis():
+    # tests/test_profiles.py:87-90
+    x, y = pts()
+    ax, ay = OP.SIE().deriv(x, y, theta_E=1.0, e1=1e-3, e2=1e-3, center_x=0.0, center_y=0.0)
+    sx, sy = OP.SIS().deriv(x, y, theta_E=1.0, center_x=0.0, center_y=0.0)
+    assert torch.allclose(ax, sx, rtol=1e-2, atol=1e-2) and torch.allclose(ay, sy, rtol=1e-2, atol=1e-2)
+
+
+def test_shear_closed_form():
+    # tests/test_profiles.py:103-111
+    x, y = pts()
+    ax, ay = OP.Shear().deriv(x, y, gamma1=0.1, gamma2=0.1)
+    assert torch.allclose(ax, 0.1 * x + 0.1 * y) and torch.allclose(ay, 0.1 * x - 0.1 * y)
+    ax, ay = OP.Shear().deriv(x, y, gamma1=0.0, gamma2=0.0)
+    assert float(ax.abs().max()) == 0 and float(ay.abs().max()) == 0
+
+
+def test_shapelets_interpolate_matches_recurrence():
+    # tests/test_profiles.py:36-47: both modes are compared with the same external answer
+    rng = np.random.default_rng(1)
+    x = torch.as_tensor(rng.normal(size=(5, 5, 1)), dtype=torch.float32)
+    y = torch.as_tensor(rng.normal(size=(5, 5, 1)), dtype=torch.float32)
+    a, b = OP.Shapelets(5, interpolate=True), OP.Shapelets(5, interpolate=False)
+    amps = {n: torch.as_tensor(rng.normal(size=1), dtype=torch.float32) for n in a.amp_names}
+    va = a.light(x, y, center_x=0.0, center_y=0.0, beta=1.0, **amps)
+    vb = b.light(x, y, center_x=0.0, center_y=0.0, beta=1.0, **amps)
+    assert np.allclose(va.numpy(), vb.numpy(), rtol=1e-5, atol=1e-4)
+    # orthonormality of the basis: integral phi_n phi_m = delta_nm
+    g = np.linspace(-12, 12, 48001)
+    for n in range(6):
+        for m in range(6):
+            v = np.trapezoid(OP.shapelet_phi_n_np(n, g) * OP.shapelet_phi_n_np(m, g), g)
+            assert abs(v - (n == m)) < 1e-9
+
+
+def test_nfw_ellipse_round_is_nfw():
+    x, y = pts()
+    kw = dict(Rs=1.3, alpha_Rs=0.9, center_x=0.05, center_y=-0.02)
+    ax, ay = OP.NFW_ELLIPSE().deriv(x, y, e1=1e-9, e2=0.0, **kw)
+    sx, sy = OP.NFW().deriv(x, y, **kw)
+    assert torch.allclose(ax, sx, atol=1e-7) and torch.allclose(ay, sy, atol=1e-7)
+
+
+def test_dpie_small_e_tends_to_dpis():
+    x, y = pts()
+    kw = dict(theta_E=1.0, r_core=0.05, r_cut=3.0, center_x=0.0, center_y=0.0)
+    sx, sy = OP.DPIS().deriv(x, y, **kw)
+    for e in (1e-3, 1e-4):
+        ax, ay = OP.DPIE().deriv(x, y, e1=e, e2=0.0, **kw)
+        assert float((ax - sx).abs().max()) < e and float((ay - sy).abs().max()) < e
+
+
+def test_scaling_relation_single_member_is_dpie():
+    x, y = pts(500)
+    x, y = x[:, None].repeat(1, 2), y[:, None].repeat(1, 2)
+    cat = dict(lum=[1.0], center_x=[0.3], center_y=[-0.2], e1=[0.1], e2=[0.05])
+    sr = OP.DPIESubhalo(1.0, cat, dtype=D)
+    th, rc, rt = (torch.tensor(v, dtype=D) for v in ([0.8, 0.9], [0.05, 0.06], [5.0, 4.0]))
+    ax, ay = sr.deriv(x, y, theta_E=th, r_core=rc, r_cut=rt)
+    f = lambda v: torch.tensor(np.float32(v), dtype=D)
+    bx, by = OP.DPIE().deriv(x, y, theta_E=th, r_core=rc, r_cut=rt, e1=f(0.1), e2=f(0.05), center_x=f(0.3), center_y=f(-0.2))
+    assert torch.allclose(ax, bx, atol=1e-12) and torch.allclose(ay, by, atol=1e-12)
+
+
+def test_subgrid_kernel_checkpoint():
+    k = subgrid_kernel(workloads.load_psf(), 2, odd=True)
+    assert k.shape == (25, 25) and abs(k.sum() - 1) < 1e-12 and abs(k.max() - 0.18792085) < 1e-7
+
+
+def test_demo_image_level_pin():
+    # tf-demo.ipynb cells 5-9: chi^2 of simulate(truth) against the reference asset demo.npy must be ~1;
+    # wrong conventions are rejected (un-flipped PSF 1.08, no PSF 1.49, transposed grid 21.9 -- SURVEY §8c)
+    wl = workloads.c2_workload()
+    sim, _ = oracle_bridge.build_oracle(wl, 1, torch.float32)
+    t = {k: [{kk: torch.tensor([vv], dtype=torch.float32) for kk, vv in d.items()} for d in v]
+         for k, v in workloads.DEMO_TRUTH.items()}
+    im = sim.simulate(t).numpy()
+    err = np.sqrt(0.2 ** 2 + im / 100)
+    chi2 = np.mean(((im - wl["observed"]) / err) ** 2)
+    assert 0.93 < chi2 < 1.03
+    assert abs(im.max() - 44.0347) < 5e-3
+
+
+def test_bijector_round_trip_and_fldj_shape():
+    # tests/tf/test_model.py:10-26
+    prior = oracle_bridge.to_oracle_prior(workloads.demo_prior())
+    x = torch.as_tensor(prior.sample(5, seed=0), dtype=D)
+    z = prior.inverse(x)
+    _, leaves = prior.forward(z)
+    assert torch.allclose(torch.stack(leaves, 1), x, rtol=1e-10)
+    assert prior.log_prior(z).shape == (5,)
+    # flatten order: dict keys sorted (lens_light < lens_mass < source_light; inner names sorted)
+    assert [p for p, _ in prior.leaves][:3] == [("lens_light", 0, "Ie"), ("lens_light", 0, "R_sersic"), ("lens_light", 0, "center_x")]
+
+
+def test_prior_densities_integrate_to_one():
+    for d, lo, hi in [(OM.Normal(0.3, 0.2), -3, 3), (OM.LogNormal(0.1, 0.3), 1e-6, 8), (OM.Uniform(2, 6), 2, 6),
+                      (OM.TruncatedNormal(2, 0.25, 1, 3), 1, 3)]:
+        g = torch.linspace(lo, hi, 200001, dtype=D)
+        assert abs(float(torch.trapz(torch.exp(d.log_prob(g)), g)) - 1) < 1e-5
+        # change of variables: density of z integrates to one too
+        z = torch.linspace(-12, 12, 200001, dtype=D)
+        lp = d.log_prob(d.forward(z)) + d.fldj(z)
+        assert abs(float(torch.trapz(torch.exp(lp), z)) - 1) < 2e-4
+
+
+def test_logprob_autograd_matches_finite_differences():
+    wl = workloads.c2_workload()
+    prior = workloads.demo_prior()
+    from gigalens_b200.model import ProbabilisticModel
+
+    z = ProbabilisticModel(prior).bij_inverse(prior.sample(2, seed=2)).astype(np.float64)
+    lp, _, g = oracle_bridge.logprob_and_grad(wl, z, torch.float64)
+    sim, pm = oracle_bridge.build_oracle(wl, 2, torch.float64)
+    for k in (0, 5, 9, 12, 17, 21):
+        h = 1e-6
+        zp, zm = z.copy(), z.copy()
+        zp[:, k] += h
+        zm[:, k] -= h
+        fp = pm.log_prob(sim, torch.as_tensor(zp))[0].numpy()
+        fm = pm.log_prob(sim, torch.as_tensor(zm))[0].numpy()
+        fd = (fp - fm) / (2 * h)
+        assert np.allclose(fd, g[:, k], rtol=2e-5, atol=1e-4 * np.abs(g[:, k]).max()), k
+
+
+def test_golden_vectors_reproduce():
+    """tests/golden/c2_golden.npz was written by tests/golden/make_golden.py from this oracle; it pins
+    the oracle against accidental edits and is what the GPU tests compare with on the box."""
+    gold = np.load(os.path.join(GOLDEN, "c2_golden.npz"))
+    wl = workloads.c2_workload()
+    lp, chi, dz = oracle_bridge.logprob_and_grad(wl, gold["z"].astype(np.float64), torch.float64)
+    assert np.allclose(lp, gold["logp"], rtol=1e-12) and np.allclose(dz, gold["dz"], rtol=1e-9, atol=1e-9)
+    assert np.allclose(chi, gold["red_chi2"], rtol=1e-12)
