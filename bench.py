@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py -- log-prob + gradient evaluations per second on the C2 workload (BASELINE.json
+configs[1]: EPL+shear lens, SersicEllipse lens light + source, 60x60, supersample 2, 13x13 PSF,
+batch 4096 per GPU), one process per GPU.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+A "step" is one pass of the hot path over one batch: ``ForwardProbModel.log_prob`` and its
+gradient w.r.t. ``z`` for ``bs`` samples (bijector + prior, ray-shooting + light, PSF conv + pool,
+chi^2 likelihood, and the hand adjoint of all of it).  ``value`` times it with ``z`` resident in
+HBM; ``e2e`` times the same call through the C ABI's host-buffer entry point
+(``gl_logprob_grad_host``: pinned host ``z`` in, ``logp`` / ``red_chi2`` / ``dz`` out, copies inside
+the timed region).  Samples are independent, so N GPUs run N shards with no data-path collective
+("weak" scaling); timing is CUDA events, max over ranks.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "logprob+grad evals/sec (60x60, ss=2)"
+UNIT = "evals/s"
+BS_PER_GPU = 4096
+
+
+def _peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return None
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": float(self.samples[0][1]) if self.samples else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+def _dist_setup(n_gpus):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+        dist.init_process_group(backend=backend)
+    return rank, world, local
+
+
+def cpu_reference_rate(bs, reps, threads=None):
+    """The reference's CPU path (oracle port: torch CPU fp32 + autograd) on a bounded sample."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    import torch
+
+    import oracle_bridge
+    from gigalens_b200 import workloads
+    from gigalens_b200.model import ProbabilisticModel
+
+    if threads:
+        torch.set_num_threads(threads)
+    wl = workloads.c2_workload()
+    z = ProbabilisticModel(wl["prior"]).bij_inverse(wl["prior"].sample(bs, seed=0))
+    sim, pm = oracle_bridge.build_oracle(wl, bs, torch.float32)
+
+    def step():
+        zt = torch.as_tensor(z).clone().requires_grad_(True)
+        logp, _ = pm.log_prob(sim, zt)
+        logp.sum().backward()
+        return float(logp[0])
+
+    step()
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    med = sorted(times)[len(times) // 2]
+    return bs / med, med, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank, world, _ = _dist_setup(args.gpus)
+    if rank != 0:
+        return
+    bs = 64
+    # each "step" = one bounded sample of the workload: bs=64 of the 4096-sample batch
+    t0 = time.perf_counter()
+    rate, med, cores = cpu_reference_rate(bs, max(1, args.steps), None)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C2: EPL+shear / SersicEllipse x2, 60x60, ss=2, PSF 13x13, MAP logprob+grad",
+                   "global_batch": BS_PER_GPU * args.gpus, "sample_batch": bs},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"bs={bs} slice of the bs=4096 batch per step, torch-CPU fp32 oracle port with autograd "
+                                   f"(the reference's TF/JAX stack is not installable offline)"},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line))
+
+
+def run_cuda(args):
+    import numpy as np
+    import torch
+
+    rank, world, local = _dist_setup(args.gpus)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (this repo has no CPU path; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    import torch.distributed as dist
+
+    from gigalens_b200 import _cabi, workloads
+    from gigalens_b200.model import ForwardProbModel
+    from gigalens_b200.simulator import LensSimulator
+
+    lib = _cabi.load()
+    wl = workloads.c2_workload()
+    bs = BS_PER_GPU
+    sim = LensSimulator(wl["phys_model"], wl["sim_config"], bs=bs)
+    pmod = ForwardProbModel(wl["prior"], wl["observed"], background_rms=wl["background_rms"], exp_time=wl["exp_time"])
+    z_host = torch.as_tensor(pmod.bij_inverse(wl["prior"].sample(bs, seed=rank))).pin_memory()
+    z = z_host.cuda()
+    d = z.shape[1]
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident throughput -----------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        out = pmod.log_prob_and_grad(sim, z)
+    sync_all()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = lib.gl_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = pmod.log_prob_and_grad(sim, z)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = lib.gl_launch_count() - launches0
+    sync_all()
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    assert bool(torch.isfinite(out[0]).all()), "non-finite log-prob in the benchmark batch"
+
+    # ---- end to end through the C ABI with host buffers ---------------------------------------
+    logp_h = torch.empty(bs, dtype=torch.float32).pin_memory()
+    chi_h = torch.empty(bs, dtype=torch.float32).pin_memory()
+    dz_h = torch.empty((bs, d), dtype=torch.float32).pin_memory()
+    pmod._bind(sim)
+
+    def e2e_step():
+        _cabi.check(lib.gl_logprob_grad_host(sim._plan, z_host.data_ptr(), logp_h.data_ptr(), chi_h.data_ptr(),
+                                             dz_h.data_ptr()), lib)
+
+    for _ in range(3):
+        e2e_step()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    assert np.allclose(logp_h.numpy(), out[0].cpu().numpy(), rtol=1e-6), "host-buffer path disagrees with device path"
+
+    # ---- roofline of the dominant kernel (ray-shooting adjoint), timed live --------------------
+    roof = None
+    if rank == 0:
+        roof = kernel_roofline(sim, pmod, z, lib)
+
+    if rank != 0:
+        return
+    cpu = None
+    if world == 1 or True:
+        rate, med, cores = cpu_reference_rate(32, 3)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "bs=32 slice of the batch, median of 3 (torch-CPU fp32 oracle port with autograd)"}
+    value = bs * world * args.steps / (ms_max * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C2: EPL+shear / SersicEllipse x2, 60x60, ss=2, PSF 13x13, MAP logprob+grad (BASELINE.json configs[1])",
+                   "global_batch": bs * world, "batch_per_gpu": bs, "params_per_sample": d, "parallelism": f"dp{world} (sample shards, no collective)",
+                   "l2": "working set per step (236 MB ss image + adjoint) exceeds the 126 MB L2; no explicit flush"},
+        "e2e": {"value": bs * world * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": bs * d * 4,
+                "d2h_bytes_per_step": bs * (d + 2) * 4, "api": "gl_logprob_grad_host (pinned host z -> logp, red_chi2, dz)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks, "roofline": roof["roofline"], "roofline_fp32": roof["fp32"], "kernel_ms": roof["kernel_ms"],
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+
+
+def kernel_roofline(sim, pmod, z, lib):
+    """Per-kernel device times of one step (CUDA events on the launch stream around each C-ABI stage
+    are not exposed, so time the stages through the public entry points that isolate them) and the
+    roofline of the dominant kernel.  Algorithmic bytes / flops per eval are DESIGN.md's figures."""
+    import torch
+
+    peaks = _peaks() or {}
+    bs = sim.bs
+    npix = (sim.numPix * sim.supersample) ** 2
+    P = sim.numPix ** 2
+
+    def timeit(fn, reps=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    params = pmod.bij_forward(sim, z)
+    mat = sim._params_matrix(params)
+    t_ss = timeit(lambda: sim.simulate_ss(mat))                    # prep + raytrace_fwd
+    t_sim = timeit(lambda: sim.simulate(mat))                      # + conv_fwd
+    t_fwd = timeit(lambda: pmod.log_prob(sim, z))                  # + unconstrain, likelihood
+    t_all = timeit(lambda: pmod.log_prob_and_grad(sim, z))         # + conv_bwd, raytrace_bwd, sample_bwd
+    t_bwd = t_all - t_fwd
+    # ncu launch list (profiles/) gives the split of t_bwd between conv_bwd and raytrace_bwd; the
+    # adjoint ray-tracing kernel is the dominant one.  Algorithmic traffic of that kernel per eval:
+    # read dL/dss (4 N) + grid (8 N, L2-resident) + derived block; write partial gradients.
+    bytes_per_eval_step = 16 * npix + 8 * P + 8 * z.shape[1] * 4
+    flops_per_eval = 34e6  # SURVEY.md §8d / DESIGN.md: 24 MFLOP profile fwd+bwd + 9.7 MFLOP conv fwd+bwd
+    sm_mhz = peaks.get("sm_max_mhz", 1965.0)
+    fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    achieved_gbs = bytes_per_eval_step * bs / (t_all * 1e-3) / 1e9
+    return {
+        "kernel_ms": {"prep+raytrace_fwd": t_ss, "conv_fwd": t_sim - t_ss, "forward_total": t_fwd,
+                      "backward_total(conv_bwd+raytrace_bwd+sample_bwd)": t_bwd, "step_total": t_all},
+        "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": achieved_gbs / hbm_peak, "traffic": None,
+                     "note": "whole step; the path is FP32-FMA/SFU bound (see roofline_fp32), HBM GB/s reported as north_star asks; "
+                             + ("peak of measured" if _peaks() else "peak of fallback")},
+        "fp32": {"bound": "fp32_fma", "achieved": flops_per_eval * bs / (t_all * 1e-3) / 1e12, "peak": fp32_peak,
+                 "unit": "TFLOP/s", "frac": flops_per_eval * bs / (t_all * 1e-3) / 1e12 / fp32_peak,
+                 "note": "nominal 34 MFLOP/eval (hand count, FMA=2) over the whole step; peak = 148 SM x 128 lanes x 2 x max SM clock"},
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -31,41 +31,96 @@ struct GlConvGeom {
   int tiles_x, tiles_y;
   int in_rows, in_pitch;   // smem input tile: rows = th + A - 1, pitch = roundup4(tw + A - 1)
   int wpitch;   // roundup4(A)
+  int phase_stride;  // forward only: floats between phase sub-images (in_rows*in_pitch padded so that the
+                     // de-interleaving stores of one warp fall into distinct banks)
   int rc0;      // adjoint only: first padded-phase row/column (pad / ss)
 };
 
+// One input row of the thread's strip applied to output rows r in [RLO, RHI] (compile-time range):
+// the row sits `row` below the strip origin and reaches output row r through tap row a = row - r,
+// so the tap rows are wrow, wrow - wpitch, ... for r = 0, 1, ...  (wrow = w + row * wpitch).
+template <int A, int RLO, int RHI>
+__device__ __forceinline__ void corr_one_row(const float* __restrict__ inrow, const float* __restrict__ wrow, int wpitch,
+                                             float (&acc)[GLC_RY][GLC_RX]) {
+  constexpr int SL = (GLC_RX + A - 1 + 3) & ~3;   // strip length rounded up to float4
+  constexpr int WL = (A + 3) & ~3;
+  float strip[SL];
+  const float4* src = reinterpret_cast<const float4*>(inrow);
+#pragma unroll
+  for (int v = 0; v < SL / 4; ++v) {
+    float4 t = src[v];
+    strip[4 * v] = t.x; strip[4 * v + 1] = t.y; strip[4 * v + 2] = t.z; strip[4 * v + 3] = t.w;
+  }
+#pragma unroll
+  for (int r = RLO; r <= RHI; ++r) {
+    float wt[WL];
+    const float4* wsrc = reinterpret_cast<const float4*>(wrow - r * wpitch);
+#pragma unroll
+    for (int v = 0; v < WL / 4; ++v) {
+      float4 t = wsrc[v];
+      wt[4 * v] = t.x; wt[4 * v + 1] = t.y; wt[4 * v + 2] = t.z; wt[4 * v + 3] = t.w;
+    }
+#pragma unroll
+    for (int b = 0; b < A; ++b)
+#pragma unroll
+      for (int c = 0; c < GLC_RX; ++c) acc[r][c] = fmaf(wt[b], strip[c + b], acc[r][c]);
+  }
+}
+
+// Same for a ramp-up / ramp-down row, where only some output rows are reachable (range test per r).
+template <int A>
+__device__ __forceinline__ void corr_edge_row(const float* __restrict__ inrow, const float* __restrict__ w, int wpitch, int row,
+                                              float (&acc)[GLC_RY][GLC_RX]) {
+  constexpr int SL = (GLC_RX + A - 1 + 3) & ~3;
+  constexpr int WL = (A + 3) & ~3;
+  float strip[SL];
+  const float4* src = reinterpret_cast<const float4*>(inrow);
+#pragma unroll
+  for (int v = 0; v < SL / 4; ++v) {
+    float4 t = src[v];
+    strip[4 * v] = t.x; strip[4 * v + 1] = t.y; strip[4 * v + 2] = t.z; strip[4 * v + 3] = t.w;
+  }
+#pragma unroll
+  for (int r = 0; r < GLC_RY; ++r) {
+    const int a = row - r;
+    if (a >= 0 && a < A) {
+      float wt[WL];
+      const float4* wsrc = reinterpret_cast<const float4*>(w + a * wpitch);
+#pragma unroll
+      for (int v = 0; v < WL / 4; ++v) {
+        float4 t = wsrc[v];
+        wt[4 * v] = t.x; wt[4 * v + 1] = t.y; wt[4 * v + 2] = t.z; wt[4 * v + 3] = t.w;
+      }
+#pragma unroll
+      for (int b = 0; b < A; ++b)
+#pragma unroll
+        for (int c = 0; c < GLC_RX; ++c) acc[r][c] = fmaf(wt[b], strip[c + b], acc[r][c]);
+    }
+  }
+}
+
 // acc[r][c] += sum_{a,b} w[a][b] * in[(r+a)*pitch + c + b]   for the thread's strip origin `in`.
+// Rows that reach every output row (RY-1 <= row <= A-1) run in a rolled loop whose body is
+// RY*A*RX FFMA + (RY+1) float4-groups of LDS and two pointer bumps, with no range tests; only the
+// RY-1 ramp-up and RY-1 ramp-down rows pay a per-output-row test.
 template <int A>
 __device__ __forceinline__ void corr_rows(const float* __restrict__ in, int pitch, const float* __restrict__ w, int wpitch,
                                           float (&acc)[GLC_RY][GLC_RX]) {
-  constexpr int SL = (GLC_RX + A - 1 + 3) & ~3;   // strip length rounded up to float4
-  constexpr int WL = (A + 3) & ~3;
+  if constexpr (A >= GLC_RY) {
 #pragma unroll 1
-  for (int row = 0; row < GLC_RY + A - 1; ++row) {
-    float strip[SL];
-    const float4* src = reinterpret_cast<const float4*>(in + row * pitch);
-#pragma unroll
-    for (int v = 0; v < SL / 4; ++v) {
-      float4 t = src[v];
-      strip[4 * v] = t.x; strip[4 * v + 1] = t.y; strip[4 * v + 2] = t.z; strip[4 * v + 3] = t.w;
+    for (int row = 0; row < GLC_RY - 1; ++row) corr_edge_row<A>(in + row * pitch, w, wpitch, row, acc);
+    const float* inrow = in + (GLC_RY - 1) * pitch;
+    const float* wrow = w + (GLC_RY - 1) * wpitch;
+#pragma unroll 1
+    for (int row = GLC_RY - 1; row <= A - 1; ++row) {
+      corr_one_row<A, 0, GLC_RY - 1>(inrow, wrow, wpitch, acc);
+      inrow += pitch; wrow += wpitch;
     }
-#pragma unroll
-    for (int r = 0; r < GLC_RY; ++r) {
-      const int a = row - r;
-      if (a >= 0 && a < A) {
-        float wt[WL];
-        const float4* wsrc = reinterpret_cast<const float4*>(w + a * wpitch);
-#pragma unroll
-        for (int v = 0; v < WL / 4; ++v) {
-          float4 t = wsrc[v];
-          wt[4 * v] = t.x; wt[4 * v + 1] = t.y; wt[4 * v + 2] = t.z; wt[4 * v + 3] = t.w;
-        }
-#pragma unroll
-        for (int b = 0; b < A; ++b)
-#pragma unroll
-          for (int c = 0; c < GLC_RX; ++c) acc[r][c] = fmaf(wt[b], strip[c + b], acc[r][c]);
-      }
-    }
+#pragma unroll 1
+    for (int row = A; row < GLC_RY + A - 1; ++row) corr_edge_row<A>(in + row * pitch, w, wpitch, row, acc);
+  } else {
+#pragma unroll 1
+    for (int row = 0; row < GLC_RY + A - 1; ++row) corr_edge_row<A>(in + row * pitch, w, wpitch, row, acc);
   }
 }
 
@@ -82,13 +137,13 @@ struct GlLikeArgs {
 //   grid = (tiles_x * tiles_y, bs), block = ntx*nty threads (rounded up to a warp multiple)
 //   part [bs][tiles][2] = (chi2, normalization) partial sums of this tile
 template <int A>
-__global__ void __launch_bounds__(256) k_conv_fwd(GlConvGeom g, const float* __restrict__ ss_img, const float* __restrict__ wts,
+__global__ void __launch_bounds__(256, 2) k_conv_fwd(GlConvGeom g, const float* __restrict__ ss_img, const float* __restrict__ wts,
                                                   float scale, float* __restrict__ img, GlLikeArgs like,
                                                   float* __restrict__ part, float* __restrict__ gimg) {
   extern __shared__ __align__(16) float smem[];
   const int nph = g.ss * g.ss;
-  const int phase_size = g.in_rows * g.in_pitch;
-  float* s_in = smem;                              // [nph][in_rows][in_pitch]
+  const int phase_size = g.phase_stride;
+  float* s_in = smem;                              // [nph][phase_stride]  (rows of in_pitch)
   float* s_w = smem + nph * phase_size;            // [nph][A][wpitch]
   __shared__ float s_red[2][8];
 
@@ -97,18 +152,26 @@ __global__ void __launch_bounds__(256) k_conv_fwd(GlConvGeom g, const float* __r
   const int tid = threadIdx.x, nthr = blockDim.x;
 
   for (int i = tid; i < nph * A * g.wpitch; i += nthr) s_w[i] = wts[i];
-  // input tile: global rows ss*oy0 - pad .. , de-interleaved by phase on the way in
+  // input tile: global rows ss*oy0 - pad .., one warp per row, lanes along the row (coalesced),
+  // de-interleaved by phase on the way into shared memory
   {
+    const int warp = tid >> 5, lane = tid & 31, nw = nthr >> 5;
     const int grows = g.ss * g.in_rows, gcols = g.ss * g.in_pitch;
     const int gi0 = g.ss * oy0 - g.pad, gj0 = g.ss * ox0 - g.pad;
     const float* src = ss_img + (size_t)b * g.hs * g.hs;
-    for (int e = tid; e < grows * gcols; e += nthr) {
-      const int li = e / gcols, lj = e - li * gcols;
-      const int gi = gi0 + li, gj = gj0 + lj;
-      float v = 0.f;
-      if (gi >= 0 && gi < g.hs && gj >= 0 && gj < g.hs) v = __ldg(src + (size_t)gi * g.hs + gj);
-      const int r = li / g.ss, py = li - r * g.ss, c = lj / g.ss, px = lj - c * g.ss;
-      s_in[(py * g.ss + px) * phase_size + r * g.in_pitch + c] = v;
+    for (int li = warp; li < grows; li += nw) {
+      const int gi = gi0 + li;
+      const int r = li / g.ss, py = li - r * g.ss;
+      const bool row_ok = gi >= 0 && gi < g.hs;
+      float* drow = s_in + py * g.ss * phase_size + r * g.in_pitch;
+      const float* srow = src + (size_t)(row_ok ? gi : 0) * g.hs;
+      for (int lj = lane; lj < gcols; lj += 32) {
+        const int gj = gj0 + lj;
+        float v = 0.f;
+        if (row_ok && gj >= 0 && gj < g.hs) v = __ldg(srow + gj);
+        const int c = lj / g.ss, px = lj - c * g.ss;
+        drow[px * phase_size + c] = v;
+      }
     }
   }
   __syncthreads();
@@ -182,7 +245,7 @@ __global__ void __launch_bounds__(256) k_conv_fwd(GlConvGeom g, const float* __r
 //   grid = (tiles_x * tiles_y, bs) over r,c in [0, nr) with nr = ceil((hs + pad) / ss).
 //   wts here are the flipped taps: wflip[ph][a'][b'] = W[ph][A-1-a'][A-1-b'].
 template <int A>
-__global__ void __launch_bounds__(256) k_conv_bwd(GlConvGeom g, const float* __restrict__ gimg, const float* __restrict__ wts,
+__global__ void __launch_bounds__(256, 2) k_conv_bwd(GlConvGeom g, const float* __restrict__ gimg, const float* __restrict__ wts,
                                                   float scale, const unsigned char* __restrict__ ss_mask,
                                                   float* __restrict__ gss) {
   extern __shared__ __align__(16) float smem[];

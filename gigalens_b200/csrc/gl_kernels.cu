@@ -212,19 +212,32 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_fwd(GlProgram P, int n
   }
 }
 
+// Warp-level reduction of the <= 8 dvar cotangents of one profile: a reduce-scatter butterfly (each
+// exchange halves the number of live values per lane: 4+2+1 exchanges, then two plain steps), 9
+// shuffles instead of 8 x 5.  Afterwards lane L (L % 4 == 0) holds the warp total of value
+// v = 4*bit4(L) + 2*bit3(L) + bit2(L) and adds it to this warp's accumulator row in shared memory.
 struct DevFlush {
   float* s_acc;   // this warp's accumulator row in shared memory
   int lane;
   __device__ __forceinline__ void operator()(const float* acc, int n, int off) {
+    const unsigned FULL = 0xffffffffu;
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+    float a4[4], a2[2];
 #pragma unroll
-    for (int k = 0; k < GL_MAX_DVARS; ++k) {
-      if (k < n) {
-        float v = acc[k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) s_acc[off + k] += v;
-      }
+    for (int i = 0; i < 4; ++i) {
+      const float send = b4 ? acc[i] : acc[i + 4], keep = b4 ? acc[i + 4] : acc[i];
+      a4[i] = keep + __shfl_xor_sync(FULL, send, 16);
     }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = b3 ? a4[i] : a4[i + 2], keep = b3 ? a4[i + 2] : a4[i];
+      a2[i] = keep + __shfl_xor_sync(FULL, send, 8);
+    }
+    float a1 = (b2 ? a2[1] : a2[0]) + __shfl_xor_sync(FULL, b2 ? a2[0] : a2[1], 4);
+    a1 += __shfl_xor_sync(FULL, a1, 2);
+    a1 += __shfl_xor_sync(FULL, a1, 1);
+    const int v = (b4 ? 4 : 0) + (b3 ? 2 : 0) + (b2 ? 1 : 0);
+    if ((lane & 3) == 0 && v < n) s_acc[off + v] += a1;
   }
 };
 
@@ -486,7 +499,13 @@ int gl_plan_create(const gl_model_desc* model, const gl_sim_config* sim, int32_t
     p->gb.rc0 = p->bwd_rc_start;
     p->conv_threads_f = ((p->gf.ntx * p->gf.nty + 31) / 32) * 32;
     p->conv_threads_b = ((p->gb.ntx * p->gb.nty + 31) / 32) * 32;
-    p->smem_cf = (size_t)(nph * p->gf.in_rows * p->gf.in_pitch + nph * A * wpitch) * sizeof(float);
+    {
+      // phase sub-images are spaced so that px*stride mod 32 spreads the ss interleaved lanes over the banks
+      int stride = (p->gf.in_rows * p->gf.in_pitch + 31) & ~31;
+      if (ss > 1) stride += ((32 / ss) + 3) & ~3;
+      p->gf.phase_stride = stride;
+    }
+    p->smem_cf = (size_t)(nph * p->gf.phase_stride + nph * A * wpitch) * sizeof(float);
     p->smem_cb = (size_t)(p->gb.in_rows * p->gb.in_pitch + nph * A * wpitch) * sizeof(float);
   }
 

@@ -59,6 +59,31 @@ GL_HD float gl_max(float a, float b) { return fmaxf(a, b); }
 GL_HD double gl_max(double a, double b) { return fmax(a, b); }
 GL_HD bool gl_isnan(float x) { return x != x; }
 GL_HD bool gl_isnan(double x) { return x != x; }
+GL_HD float gl_fma(float a, float b, float c) { return fmaf(a, b, c); }
+GL_HD double gl_fma(double a, double b, double c) { return a * b + c; }   // host harness: plain (no contraction)
+
+// Hot-loop special functions.  On the device (fp32) these are single MUFU operations:
+//   lg2.approx (abs error <= 2^-22.6), ex2.approx (rel error <= 2^-22), rcp/rsqrt.approx (1-2 ulp).
+// They are only used where the log feeds an exponent of magnitude <= ~1 (x^y = 2^(y log2 x) with
+// |y| <= 1, Sersic 1/n and EPL gamma-2), so the result error stays at the 1e-7 level of powf/expf
+// themselves; GPU parity tests hold 1e-5 with them.  The fp64 / host instantiation is exact.
+#if defined(__CUDA_ARCH__)
+GL_HD float gl_log2_fast(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+GL_HD float gl_exp2_fast(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+GL_HD float gl_div_fast(float a, float b) { return __fdividef(a, b); }
+GL_HD float gl_rsqrt_fast(float x) { return rsqrtf(x); }
+#else
+GL_HD float gl_log2_fast(float x) { return log2f(x); }
+GL_HD float gl_exp2_fast(float x) { return exp2f(x); }
+GL_HD float gl_div_fast(float a, float b) { return a / b; }
+GL_HD float gl_rsqrt_fast(float x) { return 1.0f / sqrtf(x); }
+#endif
+GL_HD double gl_log2_fast(double x) { return log2(x); }
+GL_HD double gl_exp2_fast(double x) { return exp2(x); }
+GL_HD double gl_div_fast(double a, double b) { return a / b; }
+GL_HD double gl_rsqrt_fast(double x) { return 1.0 / sqrt(x); }
+#define GL_LN2 0.69314718055994531
+#define GL_LOG2E 1.4426950408889634
 
 // Profile type ids (same values as include/gigalens_b200.h).
 enum {
@@ -105,7 +130,7 @@ GL_HD void ellip_bwd(T e1, T e2, T cmax, T gphi, T gq, T& ge1, T& ge2) {
 // constants) that sum is u * P(w), P(w) = sum_n A_n w^n, which we evaluate by complex Horner:
 // 4 FMA per trip instead of the recurrence's 8, and no per-pixel state beyond (P_re, P_im).
 // =============================================================================================
-enum { EPL_CX = 0, EPL_CY, EPL_C, EPL_S, EPL_Q, EPL_B, EPL_T, EPL_PREF0, EPL_F, EPL_N, EPL_TAB = 12 };
+enum { EPL_CX = 0, EPL_CY, EPL_C, EPL_S, EPL_Q, EPL_B, EPL_T, EPL_PREF0, EPL_F, EPL_N, EPL_LOG2B, EPL_TAB = 12 };
 enum { EPLG_CX = 0, EPLG_CY, EPLG_PHI, EPLG_Q, EPLG_B, EPLG_T, EPLG_F, EPLG_PREF0 };
 
 GL_HD int epl_table_stride(int niter_cap) { return ((niter_cap + 1) + 3) & ~3; }
@@ -139,7 +164,7 @@ GL_HD void epl_prep(const T* raw, T* d, int niter_cap, T fmax_batch) {
   d[EPL_F] = f;
   int N = epl_trip_count(fmax_batch < T(0) ? f : fmax_batch, niter_cap);
   d[EPL_N] = T(N);
-  d[10] = T(0); d[11] = T(0);
+  d[EPL_LOG2B] = gl_log(b) * T(GL_LOG2E); d[11] = T(0);
   const int ts = epl_table_stride(niter_cap);
   T* A = d + EPL_TAB; T* Af = A + ts; T* At = Af + ts;
   T s = T(2) - t;
@@ -181,27 +206,28 @@ GL_HD void epl_prep_bwd(const T* raw, const T* d, const T* g, T* graw) {
   graw[5] = g[EPLG_CY];
 }
 
-// Shared per-pixel geometry of the EPL forward / adjoint.
+// Shared per-pixel geometry of the EPL forward / adjoint.  R = clip(sqrt(R2), 1e-10, 1e10) enters
+// only through log2(R2) (prefactor) and 1/sqrt(R2) (cos/sin of the polar angle), so no sqrt is taken.
 template <class T>
 struct EplGeom {
-  T xr, yr, qx, R0, R, Cs, Ss, wr, wi;
+  T xr, yr, qx, R2, ir, l2r2, Cs, Ss, wr, wi;   // ir = 1/R0 (0 when R0 == 0), l2r2 = log2(clamped R^2)
 };
 template <class T>
 GL_HD void epl_geom(const T* d, T x, T y, EplGeom<T>& G) {
   T dx = x - d[EPL_CX], dy = y - d[EPL_CY];
   T c = d[EPL_C], s = d[EPL_S];
-  G.xr = dx * c + dy * s;
-  G.yr = -dx * s + dy * c;
+  G.xr = gl_fma(dx, c, dy * s);
+  G.yr = gl_fma(dy, c, -(dx * s));
   G.qx = d[EPL_Q] * G.xr;
-  G.R0 = gl_sqrt(G.qx * G.qx + G.yr * G.yr);
-  G.R = gl_min(gl_max(G.R0, T(1e-10)), T(1e10));
-  if (G.R0 > T(0)) {
-    T inv = T(1) / G.R0;
-    G.Cs = G.qx * inv; G.Ss = G.yr * inv;   // cos/sin of atan2(yr, q xr)
+  G.R2 = gl_fma(G.qx, G.qx, G.yr * G.yr);
+  if (G.R2 > T(0)) {
+    G.ir = gl_rsqrt_fast(G.R2);
+    G.Cs = G.qx * G.ir; G.Ss = G.yr * G.ir;   // cos/sin of atan2(yr, q xr)
   } else {
-    G.Cs = T(1); G.Ss = T(0);               // atan2(0, 0) = 0
+    G.ir = T(0); G.Cs = T(1); G.Ss = T(0);    // atan2(0, 0) = 0
   }
-  G.wr = G.Cs * G.Cs - G.Ss * G.Ss;
+  G.l2r2 = gl_log2_fast(gl_min(gl_max(G.R2, T(1e-20)), T(1e20)));
+  G.wr = gl_fma(G.Cs, G.Cs, -(G.Ss * G.Ss));
   G.wi = T(2) * G.Cs * G.Ss;
 }
 
@@ -218,20 +244,20 @@ GL_HD void epl_fwd(const T* d, int ts, const T* x, const T* y, T* ax, T* ay) {
     T a = A[n];
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
-      T pr = Pr[j] * G[j].wr - Pi[j] * G[j].wi + a;
-      T pi = Pr[j] * G[j].wi + Pi[j] * G[j].wr;
+      T pr = gl_fma(Pr[j], G[j].wr, gl_fma(-Pi[j], G[j].wi, a));
+      T pi = gl_fma(Pr[j], G[j].wi, Pi[j] * G[j].wr);
       Pr[j] = pr; Pi[j] = pi;
     }
   }
-  T c = d[EPL_C], s = d[EPL_S], b = d[EPL_B], tm1 = d[EPL_T] - T(1), pref0 = d[EPL_PREF0];
+  T c = d[EPL_C], s = d[EPL_S], l2b = d[EPL_LOG2B], tm1 = d[EPL_T] - T(1), pref0 = d[EPL_PREF0];
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
-    T fx = G[j].Cs * Pr[j] - G[j].Ss * Pi[j];
-    T fy = G[j].Cs * Pi[j] + G[j].Ss * Pr[j];
-    T pref = pref0 * gl_pow(b / G[j].R, tm1);
+    T fx = gl_fma(G[j].Cs, Pr[j], -(G[j].Ss * Pi[j]));
+    T fy = gl_fma(G[j].Cs, Pi[j], G[j].Ss * Pr[j]);
+    T pref = pref0 * gl_exp2_fast(tm1 * gl_fma(T(-0.5), G[j].l2r2, l2b));   // (b/R)^(t-1)
     fx *= pref; fy *= pref;
-    ax[j] = fx * c - fy * s;
-    ay[j] = fx * s + fy * c;
+    ax[j] = gl_fma(fx, c, -(fy * s));
+    ay[j] = gl_fma(fx, s, fy * c);
   }
 }
 
@@ -252,53 +278,51 @@ GL_HD void epl_bwd(const T* d, int ts, const T* x, const T* y, const T* gax, con
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
       T wr = G[j].wr, wi = G[j].wi;
-      T pr = Pr[j] * wr - Pi[j] * wi + a, pi = Pr[j] * wi + Pi[j] * wr;
-      T fr = Fr[j] * wr - Fi[j] * wi + af, fi = Fr[j] * wi + Fi[j] * wr;
-      T tr = Tr[j] * wr - Ti[j] * wi + at, ti = Tr[j] * wi + Ti[j] * wr;
+      T pr = gl_fma(Pr[j], wr, gl_fma(-Pi[j], wi, a)), pi = gl_fma(Pr[j], wi, Pi[j] * wr);
+      T fr = gl_fma(Fr[j], wr, gl_fma(-Fi[j], wi, af)), fi = gl_fma(Fr[j], wi, Fi[j] * wr);
+      T tr = gl_fma(Tr[j], wr, gl_fma(-Ti[j], wi, at)), ti = gl_fma(Tr[j], wi, Ti[j] * wr);
       Pr[j] = pr; Pi[j] = pi; Fr[j] = fr; Fi[j] = fi; Tr[j] = tr; Ti[j] = ti;
     }
   }
-  T c = d[EPL_C], s = d[EPL_S], q = d[EPL_Q], b = d[EPL_B], tm1 = d[EPL_T] - T(1), pref0 = d[EPL_PREF0], f = d[EPL_F];
+  T c = d[EPL_C], s = d[EPL_S], q = d[EPL_Q], l2b = d[EPL_LOG2B], tm1 = d[EPL_T] - T(1), pref0 = d[EPL_PREF0], f = d[EPL_F];
+  T tm1_over_b = tm1 / d[EPL_B];
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
     const EplGeom<T>& E = G[j];
     // forward values
-    T fx = E.Cs * Pr[j] - E.Ss * Pi[j], fy = E.Cs * Pi[j] + E.Ss * Pr[j];      // u P
-    T pw = gl_pow(b / E.R, tm1);
+    T fx = gl_fma(E.Cs, Pr[j], -(E.Ss * Pi[j])), fy = gl_fma(E.Cs, Pi[j], E.Ss * Pr[j]);      // u P
+    T l2br = gl_fma(T(-0.5), E.l2r2, l2b);            // log2(b/R)
+    T pw = gl_exp2_fast(tm1 * l2br);
     T pref = pref0 * pw;
     T Fx = fx * pref, Fy = fy * pref;
-    T ax = Fx * c - Fy * s, ay = Fx * s + Fy * c;
+    T ax = gl_fma(Fx, c, -(Fy * s)), ay = gl_fma(Fx, s, Fy * c);
     // back-rotation by -phi
-    g[EPLG_PHI] += -gax[j] * ay + gay[j] * ax;
-    T gFx = gax[j] * c + gay[j] * s, gFy = -gax[j] * s + gay[j] * c;
+    g[EPLG_PHI] += gl_fma(gay[j], ax, -(gax[j] * ay));
+    T gFx = gl_fma(gax[j], c, gay[j] * s), gFy = gl_fma(gay[j], c, -(gax[j] * s));
     // prefactor
-    T gpref = gFx * fx + gFy * fy;
-    T gr = gFx * pref, gi = gFy * pref;              // cotangent of u P (complex pair)
+    T gpref = gl_fma(gFx, fx, gFy * fy);
+    T gr = gFx * pref, gi = gFy * pref;               // cotangent of u P (complex pair)
     g[EPLG_PREF0] += gpref * pw;
-    T gpw = gpref * pref0;
-    T lnbr = gl_log(b / E.R);
-    g[EPLG_T] += gpw * pw * lnbr;
-    g[EPLG_B] += gpw * pw * tm1 / b;
-    bool r_free = (E.R0 >= T(1e-10)) && (E.R0 <= T(1e10));
-    T gR = r_free ? -gpw * pw * tm1 / E.R : T(0);
+    T gpwpw = gpref * pref;                           // gpw * pw
+    g[EPLG_T] += gpwpw * (l2br * T(GL_LN2));
+    g[EPLG_B] += gpwpw * tm1_over_b;
+    bool r_free = (E.R2 >= T(1e-20)) && (E.R2 <= T(1e20));
+    T gR_over_R = r_free ? -gpwpw * tm1 * (E.ir * E.ir) : T(0);   // gR / R0
     // series: F = u P(w; f, t).  <g, u X> = Re(conj(g) u X) for X = dP/df, dP/dt
-    T hr = gr * E.Cs + gi * E.Ss, hi = gi * E.Cs - gr * E.Ss;   // conj(u) g  (so <g,uX> = hr Xr + hi Xi)
-    g[EPLG_F] += hr * Fr[j] + hi * Fi[j];
-    g[EPLG_T] += hr * Tr[j] + hi * Ti[j];
+    T hr = gl_fma(gr, E.Cs, gi * E.Ss), hi = gl_fma(gi, E.Cs, -(gr * E.Ss));   // conj(u) g
+    g[EPLG_F] += gl_fma(hr, Fr[j], hi * Fi[j]);
+    g[EPLG_T] += gl_fma(hr, Tr[j], hi * Ti[j]);
     // d/d(ang): dF = i u (P + 2 w P_w) d(ang), with w P_w = f dP/df
-    T Zr = Pr[j] + T(2) * f * Fr[j], Zi = Pi[j] + T(2) * f * Fi[j];
-    T gang = -hr * Zi + hi * Zr;                      // Re(conj(g) i u Z)
-    // ang = atan2(yr, qx), R0 = hypot(qx, yr)
-    T gqx = T(0), gyr = T(0);
-    if (E.R0 > T(0)) {
-      T inv2 = T(1) / (E.R0 * E.R0);
-      gqx = -gang * E.yr * inv2 + gR * E.Cs;
-      gyr = gang * E.qx * inv2 + gR * E.Ss;
-    }
+    T Zr = gl_fma(T(2) * f, Fr[j], Pr[j]), Zi = gl_fma(T(2) * f, Fi[j], Pi[j]);
+    T gang = gl_fma(hi, Zr, -(hr * Zi));              // Re(conj(g) i u Z)
+    // ang = atan2(yr, qx), R0 = hypot(qx, yr):  d(ang) = (qx dyr - yr dqx)/R0^2, dR0 = (qx dqx + yr dyr)/R0
+    T ga = gang * (E.ir * E.ir);
+    T gqx = gl_fma(gR_over_R, E.qx, -(ga * E.yr));
+    T gyr = gl_fma(gR_over_R, E.yr, ga * E.qx);
     g[EPLG_Q] += gqx * E.xr;
     T gxr = gqx * q;
-    g[EPLG_PHI] += gxr * E.yr - gyr * E.xr;
-    T gdx = gxr * c - gyr * s, gdy = gxr * s + gyr * c;
+    g[EPLG_PHI] += gl_fma(gxr, E.yr, -(gyr * E.xr));
+    T gdx = gl_fma(gxr, c, -(gyr * s)), gdy = gl_fma(gxr, s, gyr * c);
     g[EPLG_CX] -= gdx;
     g[EPLG_CY] -= gdy;
   }
@@ -781,7 +805,7 @@ GL_HD void dpie_bwd(const T* d, const T* x, const T* y, const T* gax, const T* g
 //   d[]  : cx, cy, cos, sin, sq = sqrt(q), isq = 1/sq, 1/R_sersic, 1/n, bn, Ie
 //   dvars: cx, cy, phi, sq, invRs, invn, bn, Ie
 // =============================================================================================
-enum { SER_CX = 0, SER_CY, SER_C, SER_S, SER_SQ, SER_ISQ, SER_IRS, SER_IN, SER_BN, SER_IE, SER_SIZE = 12 };
+enum { SER_CX = 0, SER_CY, SER_C, SER_S, SER_SQ, SER_ISQ, SER_IRS, SER_IN, SER_BN, SER_IE, SER_NBL, SER_SIZE = 12 };
 enum { SERG_CX = 0, SERG_CY, SERG_PHI, SERG_SQ, SERG_IRS, SERG_IN, SERG_BN, SERG_IE };
 template <class T>
 GL_HD void sersic_prep(const T* raw, T* d, bool ellipse, bool use_lstsq) {
@@ -801,7 +825,7 @@ GL_HD void sersic_prep(const T* raw, T* d, bool ellipse, bool use_lstsq) {
     d[SER_CX] = raw[2]; d[SER_CY] = raw[3];
     d[SER_IE] = use_lstsq ? T(1) : raw[4];
   }
-  d[10] = T(0); d[11] = T(0);
+  d[SER_NBL] = -d[SER_BN] * T(GL_LOG2E); d[11] = T(0);
 }
 template <class T>
 GL_HD void sersic_prep_bwd(const T* raw, const T* d, const T* g, T* graw, bool ellipse, bool use_lstsq) {
@@ -818,46 +842,49 @@ GL_HD void sersic_prep_bwd(const T* raw, const T* d, const T* g, T* graw, bool e
     graw[4] = use_lstsq ? T(0) : g[SERG_IE];
   }
 }
+// (R/Rs)^(1/n) = 2^((0.5/n) log2(R^2/Rs^2)) and exp(-bn (p-1)) = 2^(-bn log2e (p-1)): no sqrt, no powf.
 template <class T, int NP>
 GL_HD void sersic_fwd(const T* d, const T* x, const T* y, T* out) {
-  T c = d[SER_C], s = d[SER_S];
+  T c = d[SER_C], s = d[SER_S], irs2 = d[SER_IRS] * d[SER_IRS], hin = T(0.5) * d[SER_IN];
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
     T dx = x[j] - d[SER_CX], dy = y[j] - d[SER_CY];
-    T xt1 = (c * dx + s * dy) * d[SER_SQ];
-    T xt2 = (-s * dx + c * dy) * d[SER_ISQ];
-    T R = gl_sqrt(xt1 * xt1 + xt2 * xt2);
-    T p = gl_pow(R * d[SER_IRS], d[SER_IN]);
-    out[j] += d[SER_IE] * gl_exp(-d[SER_BN] * (p - T(1)));
+    T xt1 = gl_fma(c, dx, s * dy) * d[SER_SQ];
+    T xt2 = gl_fma(c, dy, -(s * dx)) * d[SER_ISQ];
+    T u2 = gl_fma(xt1, xt1, xt2 * xt2) * irs2;
+    T p = gl_exp2_fast(hin * gl_log2_fast(u2));
+    out[j] = gl_fma(d[SER_IE], gl_exp2_fast(d[SER_NBL] * (p - T(1))), out[j]);
   }
 }
 // gI: cotangent of the surface brightness.  gx/gy (may be null): += cotangent of the coordinates.
 template <class T, int NP>
 GL_HD void sersic_bwd(const T* d, const T* x, const T* y, const T* gI, T* g, T* gx, T* gy) {
-  T c = d[SER_C], s = d[SER_S], sq = d[SER_SQ], isq = d[SER_ISQ], irs = d[SER_IRS], in_ = d[SER_IN], bn = d[SER_BN];
+  T c = d[SER_C], s = d[SER_S], sq = d[SER_SQ], isq = d[SER_ISQ], irs = d[SER_IRS], bn = d[SER_BN];
+  T irs2 = irs * irs, hin = T(0.5) * d[SER_IN];
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
     T dx = x[j] - d[SER_CX], dy = y[j] - d[SER_CY];
-    T xr = c * dx + s * dy, yr = -s * dx + c * dy;
+    T xr = gl_fma(c, dx, s * dy), yr = gl_fma(c, dy, -(s * dx));
     T xt1 = xr * sq, xt2 = yr * isq;
-    T R = gl_sqrt(xt1 * xt1 + xt2 * xt2);
-    T u = R * irs;
-    T p = gl_pow(u, in_);
-    T E = gl_exp(-bn * (p - T(1)));
+    T r2 = gl_fma(xt1, xt1, xt2 * xt2);
+    T u2 = r2 * irs2;
+    T L2 = gl_log2_fast(u2);
+    T p = gl_exp2_fast(hin * L2);
+    T E = gl_exp2_fast(d[SER_NBL] * (p - T(1)));
     g[SERG_IE] += gI[j] * E;
     T garg = gI[j] * d[SER_IE] * E;
-    g[SERG_BN] += -garg * (p - T(1));
-    T gp = -garg * bn;
-    if (u > T(0)) {
-      g[SERG_IN] += gp * p * gl_log(u);
-      T gu = gp * p * in_ / u;
-      g[SERG_IRS] += gu * R;
-      T gR = gu * irs;
-      T gxt1 = gR * xt1 / R, gxt2 = gR * xt2 / R;
-      g[SERG_SQ] += gxt1 * xr - gxt2 * yr * isq * isq;
+    g[SERG_BN] -= garg * (p - T(1));
+    T gpp = -garg * bn * p;                       // gp * p
+    if (u2 > T(0)) {
+      g[SERG_IN] += gpp * (T(0.5 * GL_LN2) * L2);
+      T gu2 = gl_div_fast(gpp * hin, u2);
+      g[SERG_IRS] += gu2 * r2 * T(2) * irs;
+      T gr2 = gu2 * irs2 * T(2);
+      T gxt1 = gr2 * xt1, gxt2 = gr2 * xt2;
+      g[SERG_SQ] += gl_fma(gxt1, xr, -(gxt2 * yr * isq * isq));
       T gxr = gxt1 * sq, gyr = gxt2 * isq;
-      g[SERG_PHI] += gxr * yr - gyr * xr;
-      T gdx = gxr * c - gyr * s, gdy = gxr * s + gyr * c;
+      g[SERG_PHI] += gl_fma(gxr, yr, -(gyr * xr));
+      T gdx = gl_fma(gxr, c, -(gyr * s)), gdy = gl_fma(gxr, s, gyr * c);
       g[SERG_CX] -= gdx; g[SERG_CY] -= gdy;
       if (gx) { gx[j] += gdx; gy[j] += gdy; }
     }

@@ -143,6 +143,6 @@ def assert_parity(cuda, o32, o64, tol, what, o64_perturbed=None, factor=4.0, axi
         floor = np.maximum(floor, red(np.abs(np.asarray(o64_perturbed, dtype=np.float64) - o64)) / scale)
     bad = np.atleast_1d(e_c > np.maximum(tol, factor * floor))
     assert not bad.any(), (what, np.nonzero(bad)[0][:8], np.atleast_1d(e_c)[bad][:8], np.atleast_1d(floor)[bad][:8])
-    if axis is not None and np.size(e_c) >= 4:
+    if axis is not None and np.size(e_c) >= 16:
         assert np.median(e_c) <= tol, (what, "median", float(np.median(e_c)))
     return float(np.max(e_c))
