@@ -19,6 +19,16 @@
 
 #define GLC_RX 4
 #define GLC_RY 5
+#define GLC_MAX_COL_ITERS 10   // staged tile rows are at most 320 floats wide
+
+// 4-byte asynchronous global->shared copy (LDGSTS); src_bytes = 0 zero-fills (used for the SAME padding).
+__device__ __forceinline__ void glc_cp_async4(float* smem_dst, const float* gsrc, int src_bytes) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sa), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void glc_cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
 
 struct GlConvGeom {
   int n;        // image side (pooled)
@@ -153,26 +163,39 @@ __global__ void __launch_bounds__(256, 2) k_conv_fwd(GlConvGeom g, const float* 
 
   for (int i = tid; i < nph * A * g.wpitch; i += nthr) s_w[i] = wts[i];
   // input tile: global rows ss*oy0 - pad .., one warp per row, lanes along the row (coalesced),
-  // de-interleaved by phase on the way into shared memory
+  // de-interleaved by phase on the way into shared memory with asynchronous 4-byte copies: every
+  // load of the tile is in flight at once and nothing is staged through registers.
   {
     const int warp = tid >> 5, lane = tid & 31, nw = nthr >> 5;
     const int grows = g.ss * g.in_rows, gcols = g.ss * g.in_pitch;
     const int gi0 = g.ss * oy0 - g.pad, gj0 = g.ss * ox0 - g.pad;
     const float* src = ss_img + (size_t)b * g.hs * g.hs;
+    int doff[GLC_MAX_COL_ITERS];      // smem offset of this lane's column within a row, per column chunk
+    bool cok[GLC_MAX_COL_ITERS];
+#pragma unroll
+    for (int it = 0; it < GLC_MAX_COL_ITERS; ++it) {
+      const int lj = lane + 32 * it;
+      const int c = lj / g.ss, px = lj - c * g.ss;
+      doff[it] = px * phase_size + c;
+      const int gj = gj0 + lj;
+      cok[it] = lj < gcols && gj >= 0 && gj < g.hs;
+    }
     for (int li = warp; li < grows; li += nw) {
       const int gi = gi0 + li;
       const int r = li / g.ss, py = li - r * g.ss;
       const bool row_ok = gi >= 0 && gi < g.hs;
       float* drow = s_in + py * g.ss * phase_size + r * g.in_pitch;
-      const float* srow = src + (size_t)(row_ok ? gi : 0) * g.hs;
-      for (int lj = lane; lj < gcols; lj += 32) {
-        const int gj = gj0 + lj;
-        float v = 0.f;
-        if (row_ok && gj >= 0 && gj < g.hs) v = __ldg(srow + gj);
-        const int c = lj / g.ss, px = lj - c * g.ss;
-        drow[px * phase_size + c] = v;
+      const float* srow = src + (size_t)(row_ok ? gi : 0) * g.hs + gj0;
+#pragma unroll
+      for (int it = 0; it < GLC_MAX_COL_ITERS; ++it) {
+        const int lj = lane + 32 * it;
+        if (lj < gcols) {
+          const bool ok = row_ok && cok[it];
+          glc_cp_async4(drow + doff[it], ok ? srow + lj : src, ok ? 4 : 0);
+        }
       }
     }
+    glc_cp_async_wait_all();
   }
   __syncthreads();
 
@@ -258,14 +281,20 @@ __global__ void __launch_bounds__(256, 2) k_conv_bwd(GlConvGeom g, const float* 
 
   for (int i = tid; i < nph * A * g.wpitch; i += nthr) s_w[i] = wts[i];
   {
+    const int warp = tid >> 5, lane = tid & 31, nw = nthr >> 5;
     const float* src = gimg + (size_t)b * g.n * g.n;
-    for (int e = tid; e < g.in_rows * g.in_pitch; e += nthr) {
-      const int li = e / g.in_pitch, lj = e - li * g.in_pitch;
-      const int oy = r0 + li - (A - 1), ox = c0 + lj - (A - 1);
-      float v = 0.f;
-      if (oy >= 0 && oy < g.n && ox >= 0 && ox < g.n) v = __ldg(src + (size_t)oy * g.n + ox);
-      s_in[e] = v;
+    for (int li = warp; li < g.in_rows; li += nw) {
+      const int oy = r0 + li - (A - 1);
+      const bool row_ok = oy >= 0 && oy < g.n;
+      const float* srow = src + (size_t)(row_ok ? oy : 0) * g.n + (c0 - (A - 1));
+      float* drow = s_in + li * g.in_pitch;
+      for (int lj = lane; lj < g.in_pitch; lj += 32) {
+        const int ox = c0 + lj - (A - 1);
+        const bool ok = row_ok && ox >= 0 && ox < g.n;
+        glc_cp_async4(drow + lj, ok ? srow + lj : src, ok ? 4 : 0);
+      }
     }
+    glc_cp_async_wait_all();
   }
   __syncthreads();
   const int ty = tid / g.ntx, tx = tid - ty * g.ntx;

@@ -387,6 +387,7 @@ static void gl_pick_tiles(int extent, int A, int nph_in, GlConvGeom& g) {
       const int in_rows = nty * GLC_RY + A - 1, in_pitch = (ntx * GLC_RX + A - 1 + 3) & ~3;
       const size_t smem = (size_t)(nph_in * in_rows * in_pitch + 16 * A * ((A + 3) & ~3)) * 4;
       if (smem > 100 * 1024) continue;
+      if ((nph_in > 1 ? g.ss : 1) * in_pitch > 32 * GLC_MAX_COL_ITERS) continue;   // staged row width handled by the loader
       const int warps = ceil_div(threads, 32);
       // cost: issued warp-work (incl. idle lanes / edge waste) + halo traffic
       const double work = (double)tiles_x * tiles_y * warps * 32;

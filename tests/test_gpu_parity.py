@@ -43,7 +43,8 @@ def test_c1_truth_image_matches_oracle_golden_and_demo():
 
 
 def test_c2_golden_logprob_and_grad():
-    """Committed fp64-oracle vectors (tests/golden/make_golden.py), strict tolerances."""
+    """Committed oracle vectors (tests/golden/make_golden.py): image / log-prob at the strict 1e-5,
+    gradients at 1e-4 or the committed fp32 noise floor of these inputs (DESIGN.md "Parity metric")."""
     gold = np.load(os.path.join(GOLDEN, "c2_golden.npz"))
     wl = workloads.c2_workload()
     z = gold["z"]
@@ -57,7 +58,7 @@ def test_c2_golden_logprob_and_grad():
     assert np.max(np.abs(logp - gold["logp"]) / np.abs(gold["logp"])) < 1e-5
     assert np.max(np.abs(chi2 - gold["red_chi2"]) / np.abs(gold["red_chi2"])) < 1e-5
     for k in range(z.shape[1]):
-        assert np.max(np.abs(dz[:, k] - gold["dz"][:, k])) / np.max(np.abs(gold["dz"][:, k])) < 1e-4, k
+        assert_parity(dz[:, k], gold["dz_fp32"][:, k], gold["dz"][:, k], 1e-4, f"dz[{k}]", gold["dz_pert"][:, k])
 
 
 @pytest.mark.parametrize("bs,batch_max", [(1, 1), (5, 1), (64, 1), (64, 0)])
