@@ -1,6 +1,7 @@
 // gl_build.h -- host-only: validate a gl_model_desc and flatten it into a GlProgram.
 // Used by the CUDA library (gl_plan_create) and by the test-only host harness.
 #pragma once
+#include <cmath>
 #include <string>
 #include <vector>
 
@@ -11,7 +12,27 @@ struct GlBuilt {
   GlProgram prog;
   std::vector<float> member_factor;  // concatenated [n_raw][n_members] blocks
   std::vector<int> amp_slot;         // concatenated Shapelets amplitude slots
+  std::vector<float> tables;         // concatenated Shapelets interpolation tables
+  std::vector<int> table_off;        // per profile: offset into tables, or -1
 };
+
+// lenstronomy Shapelets.phi_n on linspace(-5, 5, 6000), cast to fp32 (shapelets.py:39-40,50-51)
+inline void gl_shapelets_table(int n_max, std::vector<float>& out) {
+  const int N = GL_SHP_TABLE_N;
+  const size_t base = out.size();
+  out.resize(base + (size_t)(n_max + 1) * N);
+  for (int i = 0; i < N; ++i) {
+    const double x = -5.0 + 10.0 * (double)i / (double)(N - 1);
+    double hm2 = 0.0, hm1 = 0.75112554446494248;   // pi^(-1/4)
+    const double gauss = std::exp(-x * x / 2.0);
+    out[base + i] = (float)(hm1 * gauss);
+    for (int n = 1; n <= n_max; ++n) {
+      const double hn = std::sqrt(2.0 / n) * x * hm1 - std::sqrt((n - 1.0) / n) * hm2;
+      out[base + (size_t)n * N + i] = (float)(hn * gauss);
+      hm2 = hm1; hm1 = hn;
+    }
+  }
+}
 
 inline int gl_shapelets_layers(int n_max) { return (n_max + 1) * (n_max + 2) / 2; }
 
@@ -63,8 +84,12 @@ inline std::string gl_build_program(const gl_model_desc* m, GlBuilt& out) {
       out.member_factor.insert(out.member_factor.end(), src->member_factor, src->member_factor + (size_t)nraw * pr.n_members);
     }
     pr.amp_off = (int)out.amp_slot.size();
+    out.table_off.push_back(-1);
+    pr.table = nullptr;
+    pr.comp_off = depth;
     if (pr.type == GLT_SHAPELETS) {
-      if (pr.n_max < 0 || pr.n_max > 30) return "Shapelets n_max out of range [0, 30]";
+      if (pr.n_max < 0 || pr.n_max > GL_SHP_MAXN) return "Shapelets n_max out of range [0, " + std::to_string(GL_SHP_MAXN) + "]";
+      if (pr.flags & GL_FLAG_INTERPOLATE) { out.table_off.back() = (int)out.tables.size(); gl_shapelets_table(pr.n_max, out.tables); }
       const int nl = gl_shapelets_layers(pr.n_max);
       if (!(pr.flags & GL_FLAG_USE_LSTSQ)) {
         if (!src->amp_slot) return "Shapelets without use_lstsq needs amp_slot";
@@ -77,8 +102,9 @@ inline std::string gl_build_program(const gl_model_desc* m, GlBuilt& out) {
     } else if (!is_lens) {
       depth += 1;
     }
-    pr.der_size = gl_der_size(pr.type, pr.niter);
+    pr.der_size = gl_der_size(pr.type, pr.niter, pr.n_max);
     pr.n_dvars = gl_n_dvars(pr.type);
+    if (pr.type == GLT_SHAPELETS && !(pr.flags & GL_FLAG_USE_LSTSQ)) pr.n_dvars += gl_shapelets_layers(pr.n_max);
     pr.der_off = der;
     pr.g_off = g;
     const int nm = pr.n_members > 0 ? pr.n_members : 1;

@@ -144,7 +144,7 @@ struct GlLikeArgs {
 };
 
 // Forward: ss image -> pooled image (x scale), optional likelihood partial sums and dL/d(image).
-//   grid = (tiles_x * tiles_y, bs), block = ntx*nty threads (rounded up to a warp multiple)
+//   grid = tiles_x * tiles_y * n_images (tile fastest), block = ntx*nty threads (rounded up to a warp multiple)
 //   part [bs][tiles][2] = (chi2, normalization) partial sums of this tile
 template <int A>
 __global__ void __launch_bounds__(256, 2) k_conv_fwd(GlConvGeom g, const float* __restrict__ ss_img, const float* __restrict__ wts,
@@ -157,41 +157,48 @@ __global__ void __launch_bounds__(256, 2) k_conv_fwd(GlConvGeom g, const float* 
   float* s_w = smem + nph * phase_size;            // [nph][A][wpitch]
   __shared__ float s_red[2][8];
 
-  const int tile = blockIdx.x, b = blockIdx.y;
+  const int ntiles = g.tiles_x * g.tiles_y;
+  const int b = blockIdx.x / ntiles, tile = blockIdx.x - b * ntiles;
   const int oy0 = (tile / g.tiles_x) * g.th, ox0 = (tile % g.tiles_x) * g.tw;
   const int tid = threadIdx.x, nthr = blockDim.x;
 
   for (int i = tid; i < nph * A * g.wpitch; i += nthr) s_w[i] = wts[i];
   // input tile: global rows ss*oy0 - pad .., one warp per row, lanes along the row (coalesced),
   // de-interleaved by phase on the way into shared memory with asynchronous 4-byte copies: every
-  // load of the tile is in flight at once and nothing is staged through registers.
+  // load of the tile is in flight at once and nothing is staged through registers.  Per-lane column
+  // bookkeeping (clamped global column, shared-memory byte offset, validity) is hoisted out of the
+  // row loop; out-of-image elements are zero-filled (src-size 0) from a clamped, always valid address.
   {
     const int warp = tid >> 5, lane = tid & 31, nw = nthr >> 5;
     const int grows = g.ss * g.in_rows, gcols = g.ss * g.in_pitch;
     const int gi0 = g.ss * oy0 - g.pad, gj0 = g.ss * ox0 - g.pad;
     const float* src = ss_img + (size_t)b * g.hs * g.hs;
-    int doff[GLC_MAX_COL_ITERS];      // smem offset of this lane's column within a row, per column chunk
-    bool cok[GLC_MAX_COL_ITERS];
+    const unsigned s_in_u32 = (unsigned)__cvta_generic_to_shared(s_in);
+    const int niters = (gcols + 31) >> 5;
+    unsigned doff[GLC_MAX_COL_ITERS];   // byte offset of this lane's element within a staged row
+    int gjc[GLC_MAX_COL_ITERS];         // clamped global column
+    unsigned csz[GLC_MAX_COL_ITERS];    // 4 if the column is inside the image and the tile, else 0
 #pragma unroll
     for (int it = 0; it < GLC_MAX_COL_ITERS; ++it) {
       const int lj = lane + 32 * it;
       const int c = lj / g.ss, px = lj - c * g.ss;
-      doff[it] = px * phase_size + c;
+      doff[it] = (unsigned)(px * phase_size + c) * 4u;
       const int gj = gj0 + lj;
-      cok[it] = lj < gcols && gj >= 0 && gj < g.hs;
+      gjc[it] = min(max(gj, 0), g.hs - 1);
+      csz[it] = (lj < gcols && gj >= 0 && gj < g.hs) ? 4u : 0u;
+      if (lj >= gcols) doff[it] = 0xffffffffu;
     }
     for (int li = warp; li < grows; li += nw) {
       const int gi = gi0 + li;
       const int r = li / g.ss, py = li - r * g.ss;
       const bool row_ok = gi >= 0 && gi < g.hs;
-      float* drow = s_in + py * g.ss * phase_size + r * g.in_pitch;
-      const float* srow = src + (size_t)(row_ok ? gi : 0) * g.hs + gj0;
+      const unsigned drow = s_in_u32 + (unsigned)(py * g.ss * phase_size + r * g.in_pitch) * 4u;
+      const float* srow = src + (size_t)min(max(gi, 0), g.hs - 1) * g.hs;
 #pragma unroll
       for (int it = 0; it < GLC_MAX_COL_ITERS; ++it) {
-        const int lj = lane + 32 * it;
-        if (lj < gcols) {
-          const bool ok = row_ok && cok[it];
-          glc_cp_async4(drow + doff[it], ok ? srow + lj : src, ok ? 4 : 0);
+        if (it < niters && doff[it] != 0xffffffffu) {
+          const unsigned sz = row_ok ? csz[it] : 0u;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(drow + doff[it]), "l"(srow + gjc[it]), "r"(sz) : "memory");
         }
       }
     }
@@ -257,7 +264,7 @@ __global__ void __launch_bounds__(256, 2) k_conv_fwd(GlConvGeom g, const float* 
     if (tid == 0) {
       float c2 = 0.f, nm = 0.f;
       for (int w2 = 0; w2 < nw; ++w2) { c2 += s_red[0][w2]; nm += s_red[1][w2]; }
-      float* p = part + ((size_t)b * gridDim.x + tile) * 2;
+      float* p = part + ((size_t)b * ntiles + tile) * 2;
       p[0] = c2; p[1] = nm;
     }
   }
@@ -265,7 +272,7 @@ __global__ void __launch_bounds__(256, 2) k_conv_fwd(GlConvGeom g, const float* 
 
 // Adjoint: dL/d(image) [bs][n][n] -> dL/d(ss image) [bs][hs][hs]  (x scale).
 //   Work space is the padded-phase grid (r, c): ss pixel (i, j) = (ss*r + py - pad, ss*c + px - pad).
-//   grid = (tiles_x * tiles_y, bs) over r,c in [0, nr) with nr = ceil((hs + pad) / ss).
+//   grid = tiles * n_images over r,c in [rc0, rc0 + nr), nr = number of padded-phase rows touching the image.
 //   wts here are the flipped taps: wflip[ph][a'][b'] = W[ph][A-1-a'][A-1-b'].
 template <int A>
 __global__ void __launch_bounds__(256, 2) k_conv_bwd(GlConvGeom g, const float* __restrict__ gimg, const float* __restrict__ wts,
@@ -275,7 +282,8 @@ __global__ void __launch_bounds__(256, 2) k_conv_bwd(GlConvGeom g, const float* 
   const int nph = g.ss * g.ss;
   float* s_in = smem;                                   // [in_rows][in_pitch]  zero-padded dL/d(image)
   float* s_w = smem + g.in_rows * g.in_pitch;           // [nph][A][wpitch]
-  const int tile = blockIdx.x, b = blockIdx.y;
+  const int ntiles = g.tiles_x * g.tiles_y;
+  const int b = blockIdx.x / ntiles, tile = blockIdx.x - b * ntiles;
   const int r0 = g.rc0 + (tile / g.tiles_x) * g.th, c0 = g.rc0 + (tile % g.tiles_x) * g.tw;
   const int tid = threadIdx.x, nthr = blockDim.x;
 

@@ -21,6 +21,7 @@
 
 #include "gl_build.h"
 #include "gl_conv.cuh"
+#include "gl_lstsq.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // error handling / bookkeeping
@@ -125,15 +126,15 @@ __global__ void k_epl_fmax(GlProgram P, int bs, const float* __restrict__ params
 
 // params -> derived vector; one thread per sample.
 __global__ void k_prep(GlProgram P, int bs, const float* __restrict__ params, const float* __restrict__ member_factor,
-                       const float* __restrict__ epl_fmax, float* __restrict__ derived) {
+                       const int* __restrict__ amp_slot, const float* __restrict__ epl_fmax, float* __restrict__ derived) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= bs) return;
-  gl_sample_prep<float, float>(P, params, bs, b, member_factor, epl_fmax, derived + (size_t)b * P.der_total);
+  gl_sample_prep<float, float>(P, params, bs, b, member_factor, amp_slot, epl_fmax, derived + (size_t)b * P.der_total);
 }
 
 // partial sums -> loglike, red_chi2, dparams / dz, logp; one thread per sample.
 __global__ void k_sample_bwd(GlProgram P, int bs, const float* __restrict__ params, const float* __restrict__ member_factor,
-                             const float* __restrict__ derived, const float* __restrict__ gpart, int nchunk,
+                             const int* __restrict__ amp_slot, const float* __restrict__ derived, const float* __restrict__ gpart, int nchunk,
                              float* __restrict__ gsum /*[bs][g_total] scratch*/, const float* __restrict__ like_part,
                              int ntile, float n_pix_used, float* __restrict__ loglike, float* __restrict__ red_chi2,
                              float* __restrict__ dparams, int d, const GlLeaf* __restrict__ leaves,
@@ -141,14 +142,19 @@ __global__ void k_sample_bwd(GlProgram P, int bs, const float* __restrict__ para
                              float* __restrict__ dz) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= bs) return;
-  float chi2 = 0.f, norm = 0.f;
-  for (int t = 0; t < ntile; ++t) {
-    chi2 += like_part[((size_t)b * ntile + t) * 2];
-    norm += like_part[((size_t)b * ntile + t) * 2 + 1];
+  float ll;
+  if (like_part) {
+    float chi2 = 0.f, norm = 0.f;
+    for (int t = 0; t < ntile; ++t) {
+      chi2 += like_part[((size_t)b * ntile + t) * 2];
+      norm += like_part[((size_t)b * ntile + t) * 2 + 1];
+    }
+    ll = -0.5f * (chi2 + norm);
+    if (loglike) loglike[b] = ll;
+    if (red_chi2) red_chi2[b] = chi2 / n_pix_used;
+  } else {
+    ll = loglike[b];   // lstsq path: k_lstsq_image already wrote log-like and red chi^2
   }
-  const float ll = -0.5f * (chi2 + norm);
-  if (loglike) loglike[b] = ll;
-  if (red_chi2) red_chi2[b] = chi2 / n_pix_used;
   if (logp) logp[b] = ll + (logprior ? logprior[b] : 0.f);
   if (!dparams) return;
   float* g = gsum + (size_t)b * P.g_total;
@@ -157,7 +163,7 @@ __global__ void k_sample_bwd(GlProgram P, int bs, const float* __restrict__ para
     for (int c = 0; c < nchunk; ++c) s += gpart[((size_t)b * nchunk + c) * P.g_total + k];
     g[k] = s;
   }
-  gl_sample_prep_bwd<float, float>(P, params, bs, b, member_factor, derived + (size_t)b * P.der_total, g, dparams);
+  gl_sample_prep_bwd<float, float>(P, params, bs, b, member_factor, amp_slot, derived + (size_t)b * P.der_total, g, dparams);
   if (dz) {
     for (int k = 0; k < d; ++k) {
       const GlLeaf L = leaves[k];
@@ -321,6 +327,8 @@ struct gl_plan {
   float* d_grid_x = nullptr; float* d_grid_y = nullptr;
   unsigned char* d_ss_mask = nullptr; unsigned char* d_mask = nullptr;
   float* d_member_factor = nullptr;
+  int* d_amp_slot = nullptr;
+  float* d_tables = nullptr;
   float* d_wf = nullptr; float* d_wb = nullptr;     // forward / flipped taps [nph][A][wpitch]
   int A = 1, pad = 0;
   GlConvGeom gf, gb;
@@ -349,6 +357,11 @@ struct gl_plan {
   float* d_z = nullptr; float* d_logp = nullptr; float* d_chi = nullptr; float* d_dz = nullptr;  // *_host staging
   int chunks = 1;
   int sm_count = 148;
+  // lstsq workspace (allocated on first use)
+  int lstsq = 0;
+  int lq_chunk = 0;
+  float* d_comps = nullptr; float* d_R = nullptr; float* d_gram = nullptr; float* d_coef = nullptr; float* d_w = nullptr;
+  float* d_ll = nullptr;
 };
 
 static void gl_free_plan(gl_plan* p) {
@@ -356,11 +369,13 @@ static void gl_free_plan(gl_plan* p) {
   cudaSetDevice(p->device);
   float* fl[] = {p->d_grid_x, p->d_grid_y, p->d_member_factor, p->d_wf, p->d_wb, p->d_obs, p->d_err, p->d_params,
                  p->d_dparams, p->d_derived, p->d_ss, p->d_img, p->d_gimg, p->d_like_part, p->d_gpart, p->d_gsum,
-                 p->d_logprior, p->d_fmax, p->d_z, p->d_logp, p->d_chi, p->d_dz};
+                 p->d_logprior, p->d_fmax, p->d_z, p->d_logp, p->d_chi, p->d_dz, p->d_comps, p->d_R, p->d_gram, p->d_coef, p->d_w, p->d_ll};
   for (float* q : fl) if (q) cudaFree(q);
   if (p->d_ss_mask) cudaFree(p->d_ss_mask);
   if (p->d_mask) cudaFree(p->d_mask);
   if (p->d_leaves) cudaFree(p->d_leaves);
+  if (p->d_amp_slot) cudaFree(p->d_amp_slot);
+  if (p->d_tables) cudaFree(p->d_tables);
   delete p;
 }
 
@@ -401,6 +416,14 @@ static void gl_pick_tiles(int extent, int A, int nph_in, GlConvGeom& g) {
   g.tw = g.ntx * GLC_RX; g.th = g.nty * GLC_RY;
   g.tiles_x = ceil_div(extent, g.tw); g.tiles_y = ceil_div(extent, g.th);
   g.in_rows = g.th + A - 1; g.in_pitch = (g.tw + A - 1 + 3) & ~3;
+  // Strip loads are LDS.128 by consecutive threads (tx fastest).  When ntx is not a multiple of 8 a
+  // quarter-warp wraps into the next thread row; pad the pitch so that the wrap continues the bank
+  // sequence ((RY * pitch) mod 32 == (RX * ntx) mod 32), which keeps those wavefronts conflict-free.
+  if (g.ntx % 8 != 0 && g.nty > 1) {
+    for (int extra = 0; extra < 32; extra += 4) {
+      if (((GLC_RY * (g.in_pitch + extra)) & 31) == ((GLC_RX * g.ntx) & 31)) { g.in_pitch += extra; break; }
+    }
+  }
 }
 
 extern "C" {
@@ -429,8 +452,6 @@ int gl_plan_create(const gl_model_desc* model, const gl_sim_config* sim, int32_t
   GlBuilt built;
   std::string err = gl_build_program(model, built);
   if (!err.empty()) return gl_fail("gl_plan_create: " + err);
-  for (int i = 0; i < built.prog.n_prof; ++i)
-    if (built.prog.prof[i].type == GLT_SHAPELETS) return gl_fail("gl_plan_create: Shapelets are not implemented yet");
 
   gl_plan* p = new gl_plan();
   p->device = device; p->bs = bs; p->prog = built.prog;
@@ -458,6 +479,12 @@ int gl_plan_create(const gl_model_desc* model, const gl_sim_config* sim, int32_t
     GL_TRY(gl_upload(&p->d_ss_mask, ms.data(), ms.size()));
   }
   if (!built.member_factor.empty()) GL_TRY(gl_upload(&p->d_member_factor, built.member_factor.data(), built.member_factor.size()));
+  if (!built.amp_slot.empty()) GL_TRY(gl_upload(&p->d_amp_slot, built.amp_slot.data(), built.amp_slot.size()));
+  if (!built.tables.empty()) {
+    GL_TRY(gl_upload(&p->d_tables, built.tables.data(), built.tables.size()));
+    for (int i = 0; i < p->prog.n_prof; ++i)
+      if (built.table_off[i] >= 0) p->prog.prof[i].table = p->d_tables + built.table_off[i];
+  }
 
   // folded kernel Keff = box_ss (*) K, polyphase taps W[py][px][a][b] = Keff[ss a + py][ss b + px] / ss^2
   {
@@ -541,6 +568,7 @@ int gl_plan_create(const gl_model_desc* model, const gl_sim_config* sim, int32_t
 int gl_plan_set_option(gl_plan* p, const char* name, int32_t value) {
   if (!p || !name) return gl_fail("gl_plan_set_option: NULL argument");
   if (!strcmp(name, "epl_batch_max")) { p->epl_batch_max = value; return 0; }
+  if (!strcmp(name, "lstsq")) { p->lstsq = value; return 0; }
   return gl_fail(std::string("gl_plan_set_option: unknown option ") + name);
 }
 
@@ -562,6 +590,12 @@ int gl_plan_set_likelihood(gl_plan* p, const gl_like_config* like) {
     GL_CUDA(cudaMemcpy(m.data(), p->d_mask, nn, cudaMemcpyDeviceToHost));
     size_t c = 0; for (unsigned char v : m) c += v ? 1 : 0;
     p->n_pix_used = (float)c;
+  }
+  if (p->d_w) { cudaFree(p->d_w); p->d_w = nullptr; }
+  if (like->error_map) {
+    std::vector<float> w(nn);
+    for (size_t i = 0; i < nn; ++i) w[i] = 1.f / like->error_map[i];   // W = 1 / err_map (tf/simulator.py:232)
+    GL_CUDA(gl_upload(&p->d_w, w.data(), nn));
   }
   p->has_like = true;
   return 0;
@@ -608,7 +642,7 @@ static int gl_run_prep(gl_plan* p, const float* params, cudaStream_t st) {
     GL_LAUNCH_CHECK("k_epl_fmax");
     fmax = p->d_fmax;
   }
-  k_prep<<<gb, tb, 0, st>>>(p->prog, p->bs, params, p->d_member_factor, fmax, p->d_derived);
+  k_prep<<<gb, tb, 0, st>>>(p->prog, p->bs, params, p->d_member_factor, p->d_amp_slot, fmax, p->d_derived);
   GL_LAUNCH_CHECK("k_prep");
   return 0;
 }
@@ -634,22 +668,22 @@ static int gl_run_raytrace_bwd(gl_plan* p, const float* gss, int no_deflection, 
 }
 
 template <int A>
-static int gl_launch_conv_fwd_A(gl_plan* p, const float* ss, float scale, float* img, bool like, float* gimg, cudaStream_t st) {
+static int gl_launch_conv_fwd_A(gl_plan* p, const float* ss, float scale, float* img, bool like, float* gimg, cudaStream_t st, int nimg) {
   if (p->smem_cf > 48 * 1024)
     GL_CUDA(cudaFuncSetAttribute(k_conv_fwd<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cf));
   GlLikeArgs la{};
   la.enabled = like ? 1 : 0;
   if (like) { la.observed = p->d_obs; la.error_map = p->d_err; la.mask = p->d_mask; la.bg2 = p->bg2; la.inv_exp = p->inv_exp; }
-  dim3 grid(p->gf.tiles_x * p->gf.tiles_y, p->bs);
+  dim3 grid((unsigned)(p->gf.tiles_x * p->gf.tiles_y) * (unsigned)nimg);
   k_conv_fwd<A><<<grid, p->conv_threads_f, p->smem_cf, st>>>(p->gf, ss, p->d_wf, scale, img, la, like ? p->d_like_part : nullptr, gimg);
   GL_LAUNCH_CHECK("k_conv_fwd");
   return 0;
 }
 template <int A>
-static int gl_launch_conv_bwd_A(gl_plan* p, const float* gimg, float scale, float* gss, cudaStream_t st) {
+static int gl_launch_conv_bwd_A(gl_plan* p, const float* gimg, float scale, float* gss, cudaStream_t st, int nimg) {
   if (p->smem_cb > 48 * 1024)
     GL_CUDA(cudaFuncSetAttribute(k_conv_bwd<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cb));
-  dim3 grid(p->gb.tiles_x * p->gb.tiles_y, p->bs);
+  dim3 grid((unsigned)(p->gb.tiles_x * p->gb.tiles_y) * (unsigned)nimg);
   k_conv_bwd<A><<<grid, p->conv_threads_b, p->smem_cb, st>>>(p->gb, gimg, p->d_wb, scale, nullptr, gss);
   GL_LAUNCH_CHECK("k_conv_bwd");
   return 0;
@@ -663,12 +697,14 @@ static int gl_launch_conv_bwd_A(gl_plan* p, const float* gimg, float scale, floa
     case 20: return fn<20>(__VA_ARGS__); case 25: return fn<25>(__VA_ARGS__); case 32: return fn<32>(__VA_ARGS__); \
   }                                                                                                \
   return gl_fail("conv dispatch: unsupported tap count")
-static int gl_run_conv_fwd(gl_plan* p, const float* ss, float scale, float* img, bool like, float* gimg, cudaStream_t st) {
-  GL_CONV_DISPATCH(gl_launch_conv_fwd_A, p, ss, scale, img, like, gimg, st);
+static int gl_run_conv_fwd(gl_plan* p, const float* ss, float scale, float* img, bool like, float* gimg, cudaStream_t st,
+                           int nimg = -1) {
+  if (nimg < 0) nimg = p->bs;
+  GL_CONV_DISPATCH(gl_launch_conv_fwd_A, p, ss, scale, img, like, gimg, st, nimg);
 }
-static int gl_run_conv_bwd(gl_plan* p, const float* gimg, float scale, float* gss, cudaStream_t st) {
-  // the adjoint tiles start at r = pad/ss: shift the geometry by moving the base pointers' origin
-  GL_CONV_DISPATCH(gl_launch_conv_bwd_A, p, gimg, scale, gss, st);
+static int gl_run_conv_bwd(gl_plan* p, const float* gimg, float scale, float* gss, cudaStream_t st, int nimg = -1) {
+  if (nimg < 0) nimg = p->bs;
+  GL_CONV_DISPATCH(gl_launch_conv_bwd_A, p, gimg, scale, gss, st, nimg);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -719,9 +755,12 @@ int gl_eval_points(gl_plan* p, const float* params_dev, int32_t npts, const floa
   return 0;
 }
 
+static int gl_lstsq_loglike_core(gl_plan* p, const float* params, float* loglike, float* red_chi2, float* dparams,
+                                 const float* z, float* logp, float* dz, cudaStream_t st);
 static int gl_loglike_core(gl_plan* p, const float* params, float* loglike, float* red_chi2, float* dparams,
                            const float* z, float* logp, float* dz, cudaStream_t st) {
   if (!p->has_like) return gl_fail("log-likelihood requested but gl_plan_set_likelihood was never called");
+  if (p->lstsq) return gl_lstsq_loglike_core(p, params, loglike, red_chi2, dparams, z, logp, dz, st);
   const bool grad = dparams != nullptr;
   if (gl_run_prep(p, params, st)) return 1;
   if (gl_run_raytrace_fwd(p, p->d_ss, 0, st)) return 1;
@@ -731,7 +770,7 @@ static int gl_loglike_core(gl_plan* p, const float* params, float* loglike, floa
     if (gl_run_raytrace_bwd(p, p->d_ss, 0, st)) return 1;
   }
   const int tb = 128, gb = (p->bs + tb - 1) / tb;
-  k_sample_bwd<<<gb, tb, 0, st>>>(p->prog, p->bs, params, p->d_member_factor, p->d_derived, p->d_gpart, p->chunks, p->d_gsum,
+  k_sample_bwd<<<gb, tb, 0, st>>>(p->prog, p->bs, params, p->d_member_factor, p->d_amp_slot, p->d_derived, p->d_gpart, p->chunks, p->d_gsum,
                                   p->d_like_part, p->gf.tiles_x * p->gf.tiles_y, p->n_pix_used, loglike, red_chi2, dparams,
                                   p->d, p->d_leaves, z, z ? p->d_logprior : nullptr, logp, dz);
   GL_LAUNCH_CHECK("k_sample_bwd");
@@ -791,13 +830,84 @@ int gl_simulate_host(gl_plan* p, const float* params_host, float* image_host) {
   return 0;
 }
 
-int gl_lstsq_simulate(gl_plan* p, const float*, float*, float*, void*) {
-  (void)p;
-  return gl_fail("gl_lstsq_simulate: not implemented yet");
+static int gl_lstsq_forward(gl_plan* p, const float* params, float* image, float* coeffs_out, float* loglike,
+                            float* red_chi2, bool want_gimg, cudaStream_t st) {
+  if (!p->has_like || !p->d_err) return gl_fail("lstsq: needs gl_plan_set_likelihood with observed image and error_map");
+  const int D = p->prog.depth, npx = p->n * p->n;
+  if (D <= 0) return gl_fail("lstsq: the model has no linear light component");
+  if (D + 1 > 128 || D > 104) return gl_fail("lstsq: more than 104 linear components are not supported yet");
+  if (!p->d_comps) {
+    const size_t per_sample = (size_t)D * p->npix * sizeof(float);
+    size_t cb = (size_t)6 << 30;
+    cb = cb / per_sample;
+    if (cb < 1) cb = 1;
+    if (cb > (size_t)p->bs) cb = p->bs;
+    p->lq_chunk = (int)cb;
+    GL_CUDA(cudaMalloc((void**)&p->d_comps, cb * per_sample));
+    GL_CUDA(cudaMalloc((void**)&p->d_R, cb * (size_t)D * npx * sizeof(float)));
+    GL_CUDA(cudaMalloc((void**)&p->d_gram, cb * (size_t)(D + 1) * (D + 1) * sizeof(float)));
+    GL_CUDA(cudaMalloc((void**)&p->d_coef, (size_t)p->bs * D * sizeof(float)));
+    GL_CUDA(cudaMalloc((void**)&p->d_ll, (size_t)p->bs * 2 * sizeof(float)));
+  }
+  if (gl_run_prep(p, params, st)) return 1;
+  const size_t smem_der = (size_t)p->prog.der_total * sizeof(float);
+  if (smem_der > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_comps<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_der));
+  const int nt = (D + 1 + 3) / 4;
+  const size_t smem_gram = (size_t)GLL_PT * nt * 4 * sizeof(float);
+  const int npair = ((D + 1) & ~1) / 2;
+  const size_t smem_solve = (size_t)(2 * D * D + 2 * (npair + 1)) * sizeof(double) + (size_t)(2 * (npair + 1) + 2) * sizeof(int) + 4 * sizeof(double);
+  if (smem_solve > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_pinv_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve));
+  for (int b0 = 0; b0 < p->bs; b0 += p->lq_chunk) {
+    const int nb = (p->bs - b0 < p->lq_chunk) ? p->bs - b0 : p->lq_chunk;
+    dim3 grid(p->chunks, nb);
+    k_raytrace_comps<4><<<grid, GLL_THREADS, smem_der, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,
+                                                            p->d_derived + (size_t)b0 * p->prog.der_total, 0, p->d_comps);
+    GL_LAUNCH_CHECK("k_raytrace_comps");
+    if (gl_run_conv_fwd(p, p->d_comps, 1.f, p->d_R, false, nullptr, st, nb * D)) return 1;
+    k_gram<<<nb, GLL_THREADS, smem_gram, st>>>(D, npx, p->d_R, p->d_w, p->d_obs, p->d_gram);
+    GL_LAUNCH_CHECK("k_gram");
+    k_pinv_solve<<<nb, 128, smem_solve, st>>>(D, p->d_gram, 1e-6, 30, p->d_coef + (size_t)b0 * D);
+    GL_LAUNCH_CHECK("k_pinv_solve");
+    k_lstsq_image<<<nb, GLL_THREADS, (size_t)D * sizeof(float), st>>>(
+        D, npx, p->d_R, p->d_coef + (size_t)b0 * D, p->d_obs, p->d_err, image ? image + (size_t)b0 * npx : nullptr,
+        loglike ? loglike + b0 : nullptr, red_chi2 ? red_chi2 + b0 : nullptr, want_gimg ? p->d_gimg + (size_t)b0 * npx : nullptr);
+    GL_LAUNCH_CHECK("k_lstsq_image");
+  }
+  if (coeffs_out) GL_CUDA(cudaMemcpyAsync(coeffs_out, p->d_coef, (size_t)p->bs * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
 }
-int gl_lstsq_loglike_grad(gl_plan* p, const float*, float*, float*, float*, void*) {
-  (void)p;
-  return gl_fail("gl_lstsq_loglike_grad: not implemented yet");
+
+// log-like (+ gradient) of BackwardProbModel; shares the tail (k_sample_bwd) with the forward model.
+static int gl_lstsq_loglike_core(gl_plan* p, const float* params, float* loglike, float* red_chi2, float* dparams,
+                                 const float* z, float* logp, float* dz, cudaStream_t st) {
+  float* ll = loglike ? loglike : p->d_ll;
+  float* chi = red_chi2 ? red_chi2 : p->d_ll + p->bs;
+  const bool grad = dparams != nullptr;
+  if (gl_lstsq_forward(p, params, nullptr, nullptr, ll, chi, grad, st)) return 1;
+  const int tb = 128, gb = (p->bs + tb - 1) / tb;
+  if (grad) {
+    k_patch_amps<<<gb, tb, 0, st>>>(p->prog, p->bs, p->d_coef, p->d_derived);
+    GL_LAUNCH_CHECK("k_patch_amps");
+    if (gl_run_conv_bwd(p, p->d_gimg, 1.f, p->d_ss, st)) return 1;
+    if (gl_run_raytrace_bwd(p, p->d_ss, 0, st)) return 1;
+  }
+  k_sample_bwd<<<gb, tb, 0, st>>>(p->prog, p->bs, params, p->d_member_factor, p->d_amp_slot, p->d_derived, p->d_gpart, p->chunks,
+                                  p->d_gsum, nullptr, 0, 1.f, ll, chi, dparams, p->d, p->d_leaves, z,
+                                  z ? p->d_logprior : nullptr, logp, dz);
+  GL_LAUNCH_CHECK("k_sample_bwd");
+  return 0;
+}
+
+int gl_lstsq_simulate(gl_plan* p, const float* params_dev, float* image_dev, float* coeffs_dev, void* stream) {
+  if (!p || !params_dev) return gl_fail("gl_lstsq_simulate: NULL argument");
+  GL_CUDA(cudaSetDevice(p->device));
+  return gl_lstsq_forward(p, params_dev, image_dev, coeffs_dev, nullptr, nullptr, false, (cudaStream_t)stream);
+}
+int gl_lstsq_loglike_grad(gl_plan* p, const float* params_dev, float* loglike_dev, float* red_chi2_dev, float* dparams_dev,
+                          void* stream) {
+  if (!p || !params_dev) return gl_fail("gl_lstsq_loglike_grad: NULL argument");
+  GL_CUDA(cudaSetDevice(p->device));
+  return gl_lstsq_loglike_core(p, params_dev, loglike_dev, red_chi2_dev, dparams_dev, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,289 @@
+// gl_lstsq.cuh -- linear light-amplitude solve of LensSimulator.lstsq_simulate
+// (src/gigalens/tf/simulator.py:158-240; coherent tensor layout src/gigalens/jax/simulator.py:171-195).
+//
+//   comps[b][c][ss pixel]   unit-amplitude light components on the ray-shooting grid (k_raytrace_comps)
+//   R[b][c][pixel]          after PSF conv + pooling (k_conv_fwd with bs' = bs*D, scale 1), NaN scrubbed
+//   X = R * W, Y = obs * W,  W = 1/err_map        (:232-234)
+//   gram[b] = [X Y]^T [X Y]                         (k_gram: (D+1)^2 matrix, last column = X^T Y)
+//   coeffs  = pinv(X^T X, rcond=1e-6) X^T Y         (k_pinv_solve: symmetric Jacobi eigen-solve in fp64)
+//   image   = sum_c R_c coeffs_c                    (k_lstsq_image, + Gaussian log-likelihood and dL/dimage)
+//
+// Gradient w.r.t. the non-linear parameters: coeffs minimise the same chi^2 the likelihood measures,
+// so (envelope theorem) dL/dtheta = <dL/dimage, sum_c coeffs_c dR_c/dtheta>: the adjoint is the
+// ordinary simulate-adjoint with the amplitudes frozen at `coeffs` (k_patch_amps writes them into the
+// derived blocks).  Exact while no singular value is truncated; with an active rcond cut TF
+// differentiates through the SVD with the mask fixed and the two differ at first order in the cut
+// directions (documented in DESIGN.md).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "gl_program.h"
+
+#define GLL_THREADS 256
+
+template <int PPT>
+__global__ void __launch_bounds__(GLL_THREADS) k_raytrace_comps(GlProgram P, int npix, const float* __restrict__ grid_x,
+                                                                const float* __restrict__ grid_y,
+                                                                const unsigned char* __restrict__ ss_mask,
+                                                                const float* __restrict__ derived, int no_deflection,
+                                                                float* __restrict__ comps) {
+  extern __shared__ __align__(16) float s_der[];
+  const int b = blockIdx.y;
+  const float* dsrc = derived + (size_t)b * P.der_total;
+  for (int i = threadIdx.x; i < P.der_total; i += blockDim.x) s_der[i] = dsrc[i];
+  __syncthreads();
+  const int per_batch = GLL_THREADS * PPT;
+  const int nbatch = (npix + per_batch - 1) / per_batch;
+  float* dst = comps + (size_t)b * P.depth * npix;
+  for (int batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
+    float x[PPT], y[PPT], bx[PPT], by[PPT];
+    int pix[PPT];
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+      pix[j] = batch * per_batch + j * GLL_THREADS + threadIdx.x;
+      const int p = pix[j] < npix ? pix[j] : 0;
+      x[j] = __ldg(grid_x + p); y[j] = __ldg(grid_y + p);
+    }
+    if (no_deflection) {
+#pragma unroll
+      for (int j = 0; j < PPT; ++j) { bx[j] = x[j]; by[j] = y[j]; }
+    } else {
+      gl_pix_beta<float, PPT>(P, s_der, x, y, bx, by);
+    }
+    for (int j = 0; j < PPT; ++j) {
+      if (pix[j] >= npix) continue;
+      const bool keep = !ss_mask || ss_mask[pix[j]];
+      gl_point_components<float>(P, s_der, x[j], y[j], bx[j], by[j], dst + pix[j], npix, keep);
+    }
+  }
+}
+
+// gram[b] = [X Y]^T [X Y] with X[p][c] = R[b][c][p] * w[p], Y[p] = obs[p] * w[p].
+//   grid = bs, block = 256; 4x4 register tiles over the (D+1)^2 outputs (D + 1 <= 128).
+#define GLL_PT 32
+__global__ void __launch_bounds__(GLL_THREADS) k_gram(int D, int npx, const float* __restrict__ R, const float* __restrict__ w,
+                                                      const float* __restrict__ obs, float* __restrict__ gram) {
+  extern __shared__ __align__(16) float s_x[];   // [GLL_PT][Dp]
+  const int Dx = D + 1, nt = (Dx + 3) >> 2, Dp = nt * 4;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* Rb = R + (size_t)b * D * npx;
+  const int ntile = nt * nt;
+  float acc[4][4][4];   // up to 4 tiles per thread
+#pragma unroll
+  for (int t = 0; t < 4; ++t)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[t][i][j] = 0.f;
+  for (int p0 = 0; p0 < npx; p0 += GLL_PT) {
+    for (int e = tid; e < Dp * GLL_PT; e += GLL_THREADS) {
+      const int c = e / GLL_PT, pp = e - c * GLL_PT, p = p0 + pp;
+      float v = 0.f;
+      if (p < npx) {
+        if (c < D) { v = __ldg(Rb + (size_t)c * npx + p); if (v != v) v = 0.f; v *= w[p]; }   // NaN scrub (:228)
+        else if (c == D) v = obs[p] * w[p];
+      }
+      s_x[pp * Dp + c] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int tile = tid + t * GLL_THREADS;
+      if (tile < ntile) {
+        const int ti = tile / nt, tj = tile - ti * nt;
+#pragma unroll 4
+        for (int pp = 0; pp < GLL_PT; ++pp) {
+          const float4 a = *reinterpret_cast<const float4*>(s_x + pp * Dp + ti * 4);
+          const float4 c4 = *reinterpret_cast<const float4*>(s_x + pp * Dp + tj * 4);
+          const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[t][i][j] = fmaf(av[i], bv[j], acc[t][i][j]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  float* out = gram + (size_t)b * Dx * Dx;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int tile = tid + t * GLL_THREADS;
+    if (tile < ntile) {
+      const int ti = tile / nt, tj = tile - ti * nt;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r = ti * 4 + i, c = tj * 4 + j;
+          if (r < Dx && c < Dx) out[(size_t)r * Dx + c] = acc[t][i][j];
+        }
+    }
+  }
+}
+
+// coeffs = pinv(G, rcond) h for the symmetric PSD G = X^T X: cyclic parallel Jacobi (round-robin
+// pairing, two-sided rotations) in fp64 in shared memory, then V diag(1/lambda_i > cut) V^T h.
+// tf.linalg.pinv keeps singular values > rcond * max (src/gigalens/tf/simulator.py:235).
+//   grid = bs, block = 128, smem = 2*D*D doubles + small
+__global__ void __launch_bounds__(128) k_pinv_solve(int D, const float* __restrict__ gram, double rcond, int max_sweeps,
+                                                    float* __restrict__ coeffs) {
+  extern __shared__ __align__(16) double s_d[];
+  double* A = s_d;                 // [D][D]
+  double* V = A + D * D;           // [D][D]
+  double* cs = V + D * D;          // [m/2][2] rotation (c, s) per pair
+  int* pq = reinterpret_cast<int*>(cs + 2 * ((D + 1) / 2 + 1));   // [m/2][2]
+  double* red = reinterpret_cast<double*>(pq + 2 * ((D + 1) / 2 + 1) + 2);   // [4]
+  const int b = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+  const int Dx = D + 1;
+  const float* G = gram + (size_t)b * Dx * Dx;
+  for (int e = tid; e < D * D; e += nthr) {
+    const int i = e / D, j = e - i * D;
+    // symmetrise (the two triangles of the fp32 Gram matrix can differ by rounding)
+    A[e] = 0.5 * ((double)G[(size_t)i * Dx + j] + (double)G[(size_t)j * Dx + i]);
+    V[e] = (i == j) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  const int m = (D + 1) & ~1, npair = m / 2;
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    // convergence: off-diagonal mass relative to the diagonal
+    if (tid < 32) {
+      double off = 0.0, dg = 0.0;
+      for (int e = tid; e < D * D; e += 32) {
+        const int i = e / D, j = e - i * D;
+        const double v = A[e] * A[e];
+        if (i == j) dg += v; else off += v;
+      }
+      for (int o = 16; o > 0; o >>= 1) { off += __shfl_xor_sync(0xffffffffu, off, o); dg += __shfl_xor_sync(0xffffffffu, dg, o); }
+      if (tid == 0) { red[0] = off; red[1] = dg; }
+    }
+    __syncthreads();
+    if (red[0] <= 1e-30 * red[1]) break;
+    for (int round = 0; round < m - 1; ++round) {
+      if (tid < npair) {
+        int p, q;
+        if (tid == 0) { p = m - 1; q = round; }
+        else { p = (round + tid) % (m - 1); q = (round - tid + (m - 1)) % (m - 1); }
+        if (p > q) { const int t = p; p = q; q = t; }
+        double c = 1.0, s = 0.0;
+        if (q < D) {
+          const double apq = A[p * D + q];
+          if (fabs(apq) > 1e-300) {
+            const double tau = (A[q * D + q] - A[p * D + p]) / (2.0 * apq);
+            const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+            c = 1.0 / sqrt(1.0 + t * t);
+            s = t * c;
+          }
+        }
+        cs[2 * tid] = c; cs[2 * tid + 1] = s;
+        pq[2 * tid] = p; pq[2 * tid + 1] = q;
+      }
+      __syncthreads();
+      // columns: A <- A J, V <- V J
+      for (int e = tid; e < npair * D; e += nthr) {
+        const int pr = e / D, k = e - pr * D;
+        const int p = pq[2 * pr], q = pq[2 * pr + 1];
+        if (q >= D) continue;
+        const double c = cs[2 * pr], s = cs[2 * pr + 1];
+        const double akp = A[k * D + p], akq = A[k * D + q];
+        A[k * D + p] = c * akp - s * akq; A[k * D + q] = s * akp + c * akq;
+        const double vkp = V[k * D + p], vkq = V[k * D + q];
+        V[k * D + p] = c * vkp - s * vkq; V[k * D + q] = s * vkp + c * vkq;
+      }
+      __syncthreads();
+      // rows: A <- J^T A
+      for (int e = tid; e < npair * D; e += nthr) {
+        const int pr = e / D, k = e - pr * D;
+        const int p = pq[2 * pr], q = pq[2 * pr + 1];
+        if (q >= D) continue;
+        const double c = cs[2 * pr], s = cs[2 * pr + 1];
+        const double apk = A[p * D + k], aqk = A[q * D + k];
+        A[p * D + k] = c * apk - s * aqk; A[q * D + k] = s * apk + c * aqk;
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  // lambda_i = A_ii; y = V^T h; coeffs = V (y / lambda) over kept eigenvalues
+  double* y = cs;   // reuse: needs D doubles -> cs has only ~D+2; use red-adjacent space carefully
+  // (cs holds 2*(npair+1) >= D + 2 doubles, enough for D)
+  if (tid == 0) {
+    double lmax = 0.0;
+    for (int i = 0; i < D; ++i) lmax = fmax(lmax, fabs(A[i * D + i]));
+    red[2] = lmax;
+  }
+  __syncthreads();
+  const double cut = rcond * red[2];
+  for (int i = tid; i < D; i += nthr) {
+    double acc = 0.0;
+    for (int k = 0; k < D; ++k) acc += V[k * D + i] * (double)G[(size_t)k * Dx + D];
+    const double lam = A[i * D + i];
+    y[i] = (fabs(lam) > cut) ? acc / lam : 0.0;
+  }
+  __syncthreads();
+  for (int k = tid; k < D; k += nthr) {
+    double acc = 0.0;
+    for (int i = 0; i < D; ++i) acc += V[k * D + i] * y[i];
+    coeffs[(size_t)b * D + k] = (float)acc;
+  }
+}
+
+// image = sum_c R_c coeffs_c; Independent(Normal(obs, err)).log_prob(image) (tf/model.py:221-226,266-273)
+// and dL/dimage.  grid = bs, block = 256.
+__global__ void __launch_bounds__(GLL_THREADS) k_lstsq_image(int D, int npx, const float* __restrict__ R,
+                                                             const float* __restrict__ coeffs, const float* __restrict__ obs,
+                                                             const float* __restrict__ err, float* __restrict__ image,
+                                                             float* __restrict__ loglike, float* __restrict__ red_chi2,
+                                                             float* __restrict__ gimg) {
+  extern __shared__ float s_c[];   // [D]
+  __shared__ float s_red[2][GLL_THREADS / 32];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  for (int c = tid; c < D; c += blockDim.x) s_c[c] = coeffs[(size_t)b * D + c];
+  __syncthreads();
+  const float* Rb = R + (size_t)b * D * npx;
+  float ll = 0.f, chi = 0.f;
+  for (int p = tid; p < npx; p += blockDim.x) {
+    float v = 0.f;
+    for (int c = 0; c < D; ++c) {
+      float r = __ldg(Rb + (size_t)c * npx + p);
+      if (r != r) r = 0.f;
+      v = fmaf(r, s_c[c], v);
+    }
+    if (image) image[(size_t)b * npx + p] = v;
+    if (obs) {
+      const float e = err[p];
+      const float q = (v - obs[p]) / e;
+      chi += q * q;
+      ll += -0.5f * q * q - 0.9189385332046727f - logf(e);
+      if (gimg) gimg[(size_t)b * npx + p] = -q / e;
+    }
+  }
+  if (obs && (loglike || red_chi2)) {
+    for (int o = 16; o > 0; o >>= 1) { ll += __shfl_xor_sync(0xffffffffu, ll, o); chi += __shfl_xor_sync(0xffffffffu, chi, o); }
+    if ((tid & 31) == 0) { s_red[0][tid >> 5] = ll; s_red[1][tid >> 5] = chi; }
+    __syncthreads();
+    if (tid == 0) {
+      float a = 0.f, c2 = 0.f;
+      for (int w2 = 0; w2 < (int)(blockDim.x >> 5); ++w2) { a += s_red[0][w2]; c2 += s_red[1][w2]; }
+      if (loglike) loglike[b] = a;
+      if (red_chi2) red_chi2[b] = c2 / (float)npx;
+    }
+  }
+}
+
+// write the solved amplitudes into the derived blocks (Sersic Ie, Shapelets amplitudes) so that the
+// ordinary adjoint kernels differentiate the combined image with the amplitudes frozen.
+__global__ void k_patch_amps(GlProgram P, int bs, const float* __restrict__ coeffs, float* __restrict__ derived) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= bs) return;
+  float* der = derived + (size_t)b * P.der_total;
+  const float* c = coeffs + (size_t)b * P.depth;
+  for (int i = P.n_lens; i < P.n_prof; ++i) {
+    const GlProf& pr = P.prof[i];
+    if (pr.type == GLT_SERSIC || pr.type == GLT_SERSIC_ELLIPSE) der[pr.der_off + SER_IE] = c[pr.comp_off];
+    else if (pr.type == GLT_SHAPELETS) {
+      const int L = shp_layers(pr.n_max);
+      for (int k = 0; k < L; ++k) der[pr.der_off + shp_amp_off(pr.n_max) + k] = c[pr.comp_off + k];
+    }
+  }
+}

@@ -891,6 +891,124 @@ GL_HD void sersic_bwd(const T* d, const T* x, const T* y, const T* gI, T* g, T* 
   }
 }
 
+// =============================================================================================
+// SHAPELETS  (tf/profiles/light/shapelets.py:20-85)
+//   raw  : beta, center_x, center_y  (+ n_layers amplitudes, staged separately)
+//   d[]  : cx, cy, 1/beta, n_max, then tables c1[n], c2[n], c3[n] (n = 0..n_max) of the normalised
+//          Hermite recurrence, then the n_layers amplitudes in component order
+//   dvars: cx, cy, 1/beta, amp_0 .. amp_{L-1}
+// Basis (interpolate=False, :67-85): psi_n(u) = H_n(u) / sqrt(2^n sqrt(pi) n!) via the normalised
+// recurrence psi_n = sqrt(2/n) u psi_{n-1} - sqrt((n-1)/n) psi_{n-2} (same polynomials as the
+// reference's H_n recurrence times its prefactor; psi_n' = sqrt(2n) psi_{n-1}); component k of
+// order o = n1 + n2 is exp(-(u^2+v^2)/2) psi_{n1}(u) psi_{n2}(v), k = o(o+1)/2 + n2  (:26-46).
+// interpolate=True (:54-66): psi_n(u) exp(-u^2/2) is read by linear interpolation from a 6000-point
+// table on [-5, 5] (tfp.math.interp_regular_1d_grid semantics, 0 outside).
+// =============================================================================================
+#define GL_SHP_MAXN 20
+#define GL_SHP_TABLE_N 6000
+enum { SHP_CX = 0, SHP_CY, SHP_IB, SHP_NMAX, SHP_TAB = 4 };
+enum { SHPG_CX = 0, SHPG_CY, SHPG_IB, SHPG_AMP = 3 };
+GL_HD int shp_layers(int nmax) { return (nmax + 1) * (nmax + 2) / 2; }
+GL_HD int shp_amp_off(int nmax) { return SHP_TAB + 3 * (nmax + 1); }
+GL_HD int shp_der_size(int nmax) { return (shp_amp_off(nmax) + shp_layers(nmax) + 3) & ~3; }
+
+template <class T>
+GL_HD void shp_prep(const T* raw, T* d, int nmax) {
+  d[SHP_CX] = raw[1]; d[SHP_CY] = raw[2]; d[SHP_IB] = T(1) / raw[0]; d[SHP_NMAX] = T(nmax);
+  T* c1 = d + SHP_TAB; T* c2 = c1 + (nmax + 1); T* c3 = c2 + (nmax + 1);
+  c1[0] = T(0.75112554446494248);   // pi^(-1/4) = psi_0
+  c2[0] = T(0); c3[0] = T(0);
+  for (int n = 1; n <= nmax; ++n) {
+    c1[n] = gl_sqrt(T(2) / T(n));
+    c2[n] = gl_sqrt(T(n - 1) / T(n));
+    c3[n] = gl_sqrt(T(2 * n));
+  }
+}
+
+// h[n] = basis function n at u, dh[n] = its derivative (dh may be null).  Returns false when the
+// point is outside the interpolation table (all components are 0 there).
+template <class T>
+GL_HD void shp_basis_rec(const T* d, int nmax, T u, T* h, T* dh) {
+  const T* c1 = d + SHP_TAB; const T* c2 = c1 + (nmax + 1); const T* c3 = c2 + (nmax + 1);
+  h[0] = c1[0];
+  if (dh) dh[0] = T(0);
+  T hm2 = T(0), hm1 = c1[0];
+  for (int n = 1; n <= nmax; ++n) {
+    T hn = c1[n] * u * hm1 - c2[n] * hm2;
+    h[n] = hn;
+    if (dh) dh[n] = c3[n] * hm1;
+    hm2 = hm1; hm1 = hn;
+  }
+}
+template <class T>
+GL_HD void shp_basis_interp(const float* table, int nmax, T u, T* h, T* dh) {
+  const T nm1 = T(GL_SHP_TABLE_N - 1);
+  T xi_un = (u - T(-5)) / (T(5) - T(-5)) * nm1;
+  bool outside = (xi_un < T(0)) || (xi_un > nm1) || gl_isnan(xi_un);
+  T xi = gl_min(gl_max(xi_un, T(0)), nm1);
+  T fl = T((int)xi);                                  // floor (xi >= 0)
+  T above = gl_min(fl + T(1), nm1);
+  T below = gl_max(above - T(1), T(0));
+  int ib = (int)below, ia = (int)above;
+  T t = xi - below;
+  T slope_scale = nm1 / T(10);
+  for (int n = 0; n <= nmax; ++n) {
+    T yb = T(table[n * GL_SHP_TABLE_N + ib]), ya = T(table[n * GL_SHP_TABLE_N + ia]);
+    h[n] = outside ? T(0) : t * ya + (T(1) - t) * yb;
+    if (dh) dh[n] = outside ? T(0) : (ya - yb) * slope_scale;
+  }
+}
+
+// Surface brightness sum_k amp_k B_k at one point.  If comps != null, instead writes the L unit-
+// amplitude components B_k to comps[k * stride] (lstsq stack).  If gI != null, runs the adjoint:
+// g[SHPG_*] += cotangents (amplitude cotangents only when gamp != null), *gx/*gy += coordinate cotangents.
+template <class T>
+GL_HD T shp_point(const T* d, const float* table, bool interp, int nmax, T x, T y, T* comps, int stride,
+                  const T* gI, T* g, T* gamp, T* gx, T* gy) {
+  T hu[GL_SHP_MAXN + 1], hv[GL_SHP_MAXN + 1], dhu[GL_SHP_MAXN + 1], dhv[GL_SHP_MAXN + 1];
+  const T ib = d[SHP_IB];
+  const T dx = x - d[SHP_CX], dy = y - d[SHP_CY];
+  const T u = dx * ib, v = dy * ib;
+  T fac;
+  if (interp) {
+    shp_basis_interp(table, nmax, u, hu, gI ? dhu : (T*)nullptr);
+    shp_basis_interp(table, nmax, v, hv, gI ? dhv : (T*)nullptr);
+    fac = T(1);
+  } else {
+    shp_basis_rec(d, nmax, u, hu, gI ? dhu : (T*)nullptr);
+    shp_basis_rec(d, nmax, v, hv, gI ? dhv : (T*)nullptr);
+    fac = gl_exp(-(u * u + v * v) / T(2));
+  }
+  const T* amp = d + shp_amp_off(nmax);
+  T I = T(0), Iu = T(0), Iv = T(0);
+  int k = 0;
+  for (int o = 0; o <= nmax; ++o) {
+    for (int n2 = 0; n2 <= o; ++n2, ++k) {
+      const int n1 = o - n2;
+      const T B = hu[n1] * hv[n2];
+      if (comps) { comps[k * stride] = fac * B; continue; }
+      I += amp[k] * B;
+      if (gI) {
+        Iu += amp[k] * dhu[n1] * hv[n2];
+        Iv += amp[k] * hu[n1] * dhv[n2];
+        if (gamp) gamp[k] += gI[0] * fac * B;
+      }
+    }
+  }
+  if (comps) return T(0);
+  I *= fac;
+  if (gI) {
+    T dIdu = fac * Iu, dIdv = fac * Iv;
+    if (!interp) { dIdu -= u * I; dIdv -= v * I; }
+    const T gu = gI[0] * dIdu, gv = gI[0] * dIdv;
+    g[SHPG_IB] += gu * dx + gv * dy;
+    const T gdx = gu * ib, gdy = gv * ib;
+    g[SHPG_CX] -= gdx; g[SHPG_CY] -= gdy;
+    if (gx) { *gx += gdx; *gy += gdy; }
+  }
+  return I;
+}
+
 // ---------------------------------------------------------------------------------------------
 // generic per-type tables
 // ---------------------------------------------------------------------------------------------
@@ -906,15 +1024,15 @@ GL_HD int gl_n_dvars(int type) {
   switch (type) {
     case GLT_EPL: return 8; case GLT_SHEAR: return 2; case GLT_SIE: return 6; case GLT_SIS: return 3;
     case GLT_NFW: case GLT_NFW_ELLIPSE: return 7; case GLT_DPIS: case GLT_DPIE: return 7;
-    case GLT_SERSIC: case GLT_SERSIC_ELLIPSE: return 8; case GLT_SHAPELETS: return 3;
+    case GLT_SERSIC: case GLT_SERSIC_ELLIPSE: return 8; case GLT_SHAPELETS: return 3;   // + n_layers amplitudes without use_lstsq
   }
   return 0;
 }
-GL_HD int gl_der_size(int type, int niter) {
+GL_HD int gl_der_size(int type, int niter, int nmax) {
   switch (type) {
     case GLT_EPL: return epl_der_size(niter); case GLT_SHEAR: return 4; case GLT_SIE: return SIE_SIZE; case GLT_SIS: return 4;
     case GLT_NFW: case GLT_NFW_ELLIPSE: return NFW_SIZE; case GLT_DPIS: case GLT_DPIE: return DP_SIZE;
-    case GLT_SERSIC: case GLT_SERSIC_ELLIPSE: return SER_SIZE; case GLT_SHAPELETS: return 4;
+    case GLT_SERSIC: case GLT_SERSIC_ELLIPSE: return SER_SIZE; case GLT_SHAPELETS: return shp_der_size(nmax);
   }
   return 0;
 }

@@ -26,6 +26,8 @@ struct GlProf {
   int n_members;   // 0 = plain profile
   int member_off;  // offset into the member-factor array ([n_raw][n_members] per entry)
   int amp_off;     // Shapelets: offset into the amp-slot array
+  int comp_off;    // light profiles: index of the first linear component (lstsq stack channel)
+  const float* table;  // Shapelets(interpolate=True): [n_max+1][6000] basis table (device / host pointer)
   int slot[GL_MAX_RAW];
   float constant[GL_MAX_RAW];
 };
@@ -63,14 +65,18 @@ GL_HD void gl_gather_raw(const GlProf& pr, const TP* params, int bs, int b, cons
 // per-sample trip counts.
 template <class T, class TP>
 GL_HD void gl_sample_prep(const GlProgram& P, const TP* params, int bs, int b, const float* member_factor,
-                          const float* epl_fmax, T* der) {
+                          const int* amp_slot, const float* epl_fmax, T* der) {
   for (int i = 0; i < P.n_prof; ++i) {
     const GlProf& pr = P.prof[i];
     if (pr.type == GLT_SHAPELETS) {
       T raw[GL_MAX_RAW];
       gl_gather_raw<T, TP>(pr, params, bs, b, member_factor, 0, raw);
       T* d = der + pr.der_off;
-      d[0] = raw[1]; d[1] = raw[2]; d[2] = T(1) / raw[0]; d[3] = T(0);
+      shp_prep<T>(raw, d, pr.n_max);
+      T* amp = d + shp_amp_off(pr.n_max);
+      const int L = shp_layers(pr.n_max);
+      const bool lstsq = (pr.flags & 1u) != 0;   // amplitudes are solved for; filled in after the solve
+      for (int k = 0; k < L; ++k) amp[k] = lstsq ? T(0) : T(params[(size_t)amp_slot[pr.amp_off + k] * bs + b]);
       continue;
     }
     const int nm = pr.n_members > 0 ? pr.n_members : 1;
@@ -86,7 +92,7 @@ GL_HD void gl_sample_prep(const GlProgram& P, const TP* params, int bs, int b, c
 // dvar cotangents g[] of one sample -> gparams[P][bs] column b (overwritten).
 template <class T, class TP>
 GL_HD void gl_sample_prep_bwd(const GlProgram& P, const TP* params, int bs, int b, const float* member_factor,
-                              const T* der, const T* g, TP* gparams) {
+                              const int* amp_slot, const T* der, const T* g, TP* gparams) {
   for (int k = 0; k < P.n_params; ++k) gparams[(size_t)k * bs + b] = TP(0);
   for (int i = 0; i < P.n_prof; ++i) {
     const GlProf& pr = P.prof[i];
@@ -94,10 +100,14 @@ GL_HD void gl_sample_prep_bwd(const GlProgram& P, const TP* params, int bs, int 
     if (pr.type == GLT_SHAPELETS) {
       T raw[GL_MAX_RAW];
       gl_gather_raw<T, TP>(pr, params, bs, b, member_factor, 0, raw);
-      const T* gg = g + pr.g_off;   // cx, cy, invbeta
-      T graw[3] = {-gg[2] / (raw[0] * raw[0]), gg[0], gg[1]};
+      const T* gg = g + pr.g_off;   // cx, cy, invbeta, amplitudes
+      T graw[3] = {-gg[SHPG_IB] / (raw[0] * raw[0]), gg[SHPG_CX], gg[SHPG_CY]};
       for (int k = 0; k < 3; ++k)
         if (pr.slot[k] >= 0) gparams[(size_t)pr.slot[k] * bs + b] += TP(graw[k]);
+      if (!(pr.flags & 1u)) {
+        const int L = shp_layers(pr.n_max);
+        for (int k = 0; k < L; ++k) gparams[(size_t)amp_slot[pr.amp_off + k] * bs + b] += TP(gg[SHPG_AMP + k]);
+      }
       continue;
     }
     const int nm = pr.n_members > 0 ? pr.n_members : 1;
@@ -157,6 +167,41 @@ GL_HD void gl_pix_image(const GlProgram& P, const T* der, const T* x, const T* y
     const T* py = src ? by : y;
     switch (pr.type) {
       case GLT_SERSIC: case GLT_SERSIC_ELLIPSE: sersic_fwd<T, NP>(der + pr.der_off, px, py, out); break;
+      case GLT_SHAPELETS:
+        for (int j = 0; j < NP; ++j)
+          out[j] += shp_point<T>(der + pr.der_off, pr.table, (pr.flags & 2u) != 0, pr.n_max, px[j], py[j], (T*)nullptr, 0,
+                                 (const T*)nullptr, (T*)nullptr, (T*)nullptr, (T*)nullptr, (T*)nullptr);
+        break;
+      default: break;
+    }
+  }
+}
+
+// The D unit-amplitude linear light components at one pixel (lstsq stack before the convolution,
+// tf/simulator.py:183-200 with the layout of jax/simulator.py:171-175): out[c * stride], NaN scrubbed
+// (:200); `keep` = false (pixel outside pix_region) writes zeros.
+template <class T>
+GL_HD void gl_point_components(const GlProgram& P, const T* der, T x, T y, T bx, T by, T* out, int stride, bool keep) {
+  for (int i = P.n_lens; i < P.n_prof; ++i) {
+    const GlProf& pr = P.prof[i];
+    const bool src = i >= P.n_lens + P.n_ll;
+    const T px = src ? bx : x, py = src ? by : y;
+    switch (pr.type) {
+      case GLT_SERSIC: case GLT_SERSIC_ELLIPSE: {
+        T v[1] = {T(0)}, xx[1] = {px}, yy[1] = {py};
+        sersic_fwd<T, 1>(der + pr.der_off, xx, yy, v);
+        out[pr.comp_off * stride] = (keep && !gl_isnan(v[0])) ? v[0] : T(0);
+      } break;
+      case GLT_SHAPELETS: {
+        const int L = shp_layers(pr.n_max);
+        T* o = out + pr.comp_off * stride;
+        shp_point<T>(der + pr.der_off, pr.table, (pr.flags & 2u) != 0, pr.n_max, px, py, o, stride, (const T*)nullptr,
+                     (T*)nullptr, (T*)nullptr, (T*)nullptr, (T*)nullptr);
+        for (int k = 0; k < L; ++k) {
+          const T v = o[k * stride];
+          if (!keep || gl_isnan(v)) o[k * stride] = T(0);
+        }
+      } break;
       default: break;
     }
   }
@@ -188,9 +233,27 @@ GL_HD void gl_pix_image_bwd(const GlProgram& P, const T* der, const T* x, const 
         if (src) sersic_bwd<T, NP>(der + pr.der_off, bx, by, gS, acc, Gx, Gy);
         else sersic_bwd<T, NP>(der + pr.der_off, x, y, gS, acc, (T*)nullptr, (T*)nullptr);
         break;
+      case GLT_SHAPELETS: {
+        const bool want_amp = !(pr.flags & 1u);
+        const int L = shp_layers(pr.n_max);
+        T gamp[(GL_SHP_MAXN + 1) * (GL_SHP_MAXN + 2) / 2];
+        if (want_amp) for (int k = 0; k < L; ++k) gamp[k] = T(0);
+        for (int j = 0; j < NP; ++j)
+          shp_point<T>(der + pr.der_off, pr.table, (pr.flags & 2u) != 0, pr.n_max, src ? bx[j] : x[j], src ? by[j] : y[j],
+                       (T*)nullptr, 0, gS + j, acc, want_amp ? gamp : (T*)nullptr, src ? Gx + j : (T*)nullptr,
+                       src ? Gy + j : (T*)nullptr);
+        if (want_amp) {
+          for (int k0 = 0; k0 < L; k0 += GL_MAX_DVARS) {
+            T a8[GL_MAX_DVARS];
+#pragma unroll
+            for (int k = 0; k < GL_MAX_DVARS; ++k) a8[k] = (k0 + k < L) ? gamp[k0 + k] : T(0);
+            flush(a8, (L - k0) < GL_MAX_DVARS ? (L - k0) : GL_MAX_DVARS, pr.g_off + SHPG_AMP + k0);
+          }
+        }
+      } break;
       default: break;
     }
-    flush(acc, pr.n_dvars, pr.g_off);
+    flush(acc, pr.type == GLT_SHAPELETS ? 3 : pr.n_dvars, pr.g_off);
   }
   if (no_deflection) return;
   // d(beta)/d(lens) = -d(alpha): cotangent of each deflection is (-Gx, -Gy)

@@ -110,6 +110,35 @@ class ProbabilisticModel:
                                                   simulator._stream()), simulator._lib)
         return simulator.compiled.unflatten(mat)
 
+    def _eval(self, simulator, z, want_grad):
+        torch = simulator._torch
+        self._bind(simulator)
+        z = z.to(device=simulator.device, dtype=torch.float32).contiguous()
+        if z.shape != (simulator.bs, self.size):
+            raise ValueError(f"z must have shape ({simulator.bs}, {self.size}), got {tuple(z.shape)}")
+        logp = torch.empty((simulator.bs,), dtype=torch.float32, device=simulator.device)
+        chi = torch.empty_like(logp)
+        dz = torch.empty_like(z) if want_grad else None
+        _cabi.check(simulator._lib.gl_logprob_grad(simulator._plan, z.data_ptr(), logp.data_ptr(), chi.data_ptr(),
+                                                   dz.data_ptr() if want_grad else None, simulator._stream()),
+                    simulator._lib)
+        return logp, chi, dz
+
+    def log_prob_and_grad(self, simulator, z):
+        """``(log_prob, red_chi2, d log_prob / d z)``: one fused forward + hand-adjoint pass."""
+        torch = simulator._torch
+        return self._eval(simulator, torch.as_tensor(z), True)
+
+    def log_prob(self, simulator, z):
+        """Reference ``log_prob(simulator, z) -> (log_like + log_prior, red_chi2)`` (``tf/model.py:126-167``,
+        ``:242-273``); differentiable through torch.autograd via the hand-written adjoint."""
+        torch = simulator._torch
+        z = torch.as_tensor(z)
+        if torch.is_grad_enabled() and z.requires_grad:
+            return _autograd_wrap(torch, lambda zz, g: self._eval(simulator, zz, g), z)
+        logp, chi, _ = self._eval(simulator, z, False)
+        return logp, chi
+
     def log_prior(self, simulator, z):
         """``tf/model.py:183-185``: prior.log_prob(bij.forward(z)) + forward_log_det_jacobian."""
         torch = simulator._torch
@@ -176,6 +205,7 @@ class ForwardProbModel(ProbabilisticModel):
         if self.observed_image.shape != (n, n):
             raise ValueError(f"observed_image must be ({n}, {n})")
         _cabi.check(simulator._lib.gl_plan_set_likelihood(simulator._plan, C.byref(lc)), simulator._lib)
+        simulator.set_option("lstsq", 0)
 
     def stats_pixels(self, simulator, params):
         """``tf/model.py:89-101`` -> ``(log_like, red_chi2)``, both ``(bs,)``."""
@@ -204,35 +234,6 @@ class ForwardProbModel(ProbabilisticModel):
                                                    g.data_ptr(), simulator._stream()), simulator._lib)
         return ll, chi, g
 
-    def _eval(self, simulator, z, want_grad):
-        torch = simulator._torch
-        self._bind(simulator)
-        z = z.to(device=simulator.device, dtype=torch.float32).contiguous()
-        if z.shape != (simulator.bs, self.size):
-            raise ValueError(f"z must have shape ({simulator.bs}, {self.size}), got {tuple(z.shape)}")
-        logp = torch.empty((simulator.bs,), dtype=torch.float32, device=simulator.device)
-        chi = torch.empty_like(logp)
-        dz = torch.empty_like(z) if want_grad else None
-        _cabi.check(simulator._lib.gl_logprob_grad(simulator._plan, z.data_ptr(), logp.data_ptr(), chi.data_ptr(),
-                                                   dz.data_ptr() if want_grad else None, simulator._stream()),
-                    simulator._lib)
-        return logp, chi, dz
-
-    def log_prob_and_grad(self, simulator, z):
-        """``(log_prob, red_chi2, d log_prob / d z)``: one fused forward + hand-adjoint pass."""
-        torch = simulator._torch
-        z = torch.as_tensor(z)
-        return self._eval(simulator, z, True)
-
-    def log_prob(self, simulator, z):
-        """``tf/model.py:126-167``: returns ``(log_like + log_prior, red_chi2)``."""
-        torch = simulator._torch
-        z = torch.as_tensor(z)
-        if torch.is_grad_enabled() and z.requires_grad:
-            return _autograd_wrap(torch, lambda zz, g: self._eval(simulator, zz, g), z)
-        logp, chi, _ = self._eval(simulator, z, False)
-        return logp, chi
-
     def log_like(self, simulator, z):
         """``tf/model.py:169-180``."""
         return self.stats_pixels(simulator, self.bij_forward(simulator, z))[0]
@@ -248,5 +249,27 @@ class BackwardProbModel(ProbabilisticModel):
         self.observed_image = obs
         self.err_map = np.sqrt(np.float32(background_rms) ** 2 + np.clip(obs, 0, np.inf) / np.float32(exp_time)).astype(np.float32)
 
-    def log_prob(self, simulator, z):
-        raise NotImplementedError("BackwardProbModel.log_prob: lstsq CUDA path not built yet")
+    def _install_likelihood(self, simulator):
+        lc = _cabi.LikeConfig()
+        lc.observed = self.observed_image.ctypes.data_as(C.POINTER(C.c_float))
+        lc.error_map = self.err_map.ctypes.data_as(C.POINTER(C.c_float))
+        lc.background_rms, lc.exp_time = 0.0, 1.0
+        n = simulator.numPix
+        if self.observed_image.shape != (n, n):
+            raise ValueError(f"observed_image must be ({n}, {n})")
+        _cabi.check(simulator._lib.gl_plan_set_likelihood(simulator._plan, C.byref(lc)), simulator._lib)
+        simulator.set_option("lstsq", 1)   # log-prob entry points use the linear-amplitude solve
+
+    def loglike_and_grad(self, simulator, params):
+        """log-likelihood, red_chi2 and d(log_like)/d(non-linear params) ``[P][bs]``."""
+        torch = simulator._torch
+        if simulator._like_owner is not self:
+            self._install_likelihood(simulator)
+            simulator._like_owner = self
+        mat = simulator._params_matrix(params)
+        ll = torch.empty((simulator.bs,), dtype=torch.float32, device=simulator.device)
+        chi = torch.empty_like(ll)
+        g = torch.empty_like(mat)
+        _cabi.check(simulator._lib.gl_lstsq_loglike_grad(simulator._plan, mat.data_ptr(), ll.data_ptr(), chi.data_ptr(),
+                                                         g.data_ptr(), simulator._stream()), simulator._lib)
+        return ll, chi, g

@@ -322,7 +322,33 @@ class LensSimulator(LensSimulatorInterface):
         """``tf/simulator.py:72-78`` at points ``(x, y)`` shared by all samples -> ``(bs, npts)`` each."""
         return self.eval_points({"lens_mass": lens_params}, x, y, mode=0, missing_ok=("lens_light", "source_light"))
 
+    def _install_lstsq_data(self, observed_image, err_map):
+        """(observed, err_map) of lstsq_simulate live in the plan's likelihood slot."""
+        obs = np.ascontiguousarray(np.asarray(observed_image.cpu() if hasattr(observed_image, "cpu") else observed_image),
+                                   dtype=np.float32)
+        err = np.ascontiguousarray(np.asarray(err_map.cpu() if hasattr(err_map, "cpu") else err_map), dtype=np.float32)
+        key = (obs.tobytes(), err.tobytes())
+        if self._like_owner != key:
+            lc = _cabi.LikeConfig()
+            lc.observed = obs.ctypes.data_as(C.POINTER(C.c_float))
+            lc.error_map = err.ctypes.data_as(C.POINTER(C.c_float))
+            lc.background_rms, lc.exp_time = 0.0, 1.0
+            _cabi.check(self._lib.gl_plan_set_likelihood(self._plan, C.byref(lc)), self._lib)
+            self._like_owner = key
+
     def lstsq_simulate(self, params, observed_image, err_map, return_stacked=False, return_coeffs=False,
                        no_deflection=False):
-        """``tf/simulator.py:158-240``."""
-        raise NotImplementedError("lstsq_simulate: CUDA path not built yet")
+        """``tf/simulator.py:158-240``: solve the linear light amplitudes against ``observed_image``
+        with weights ``1/err_map`` and return the best-fitting image ``(bs, n, n)`` (squeezed), or the
+        amplitudes ``(bs, D)`` with ``return_coeffs``."""
+        if return_stacked or no_deflection:
+            raise NotImplementedError("return_stacked / no_deflection are not wired through the C ABI yet")
+        torch = self._torch
+        self._install_lstsq_data(observed_image, err_map)
+        mat = self._params_matrix(params)
+        n = self.numPix
+        img = torch.empty((self.bs, n, n), dtype=torch.float32, device=self.device)
+        coef = torch.empty((self.bs, self.depth), dtype=torch.float32, device=self.device)
+        _cabi.check(self._lib.gl_lstsq_simulate(self._plan, mat.data_ptr(), img.data_ptr(), coef.data_ptr(), self._stream()),
+                    self._lib)
+        return coef if return_coeffs else img.squeeze()

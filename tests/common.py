@@ -94,7 +94,7 @@ def hostcheck_lib():
 
 
 def host_run(cm: CompiledModel, mat, gx, gy, g_ss=None, dtype=np.float64, no_deflection=False, epl_batch_max=True,
-             want_beta=False):
+             want_beta=False, want_comps=False):
     """Run prep -> pixel forward (-> pixel adjoint -> prep adjoint) on the host harness.
     Returns dict(ss=[bs][npix], gparams=[P][bs] or None, beta=[bs][2][npix] or None)."""
     lib = hostcheck_lib()
@@ -107,13 +107,17 @@ def host_run(cm: CompiledModel, mat, gx, gy, g_ss=None, dtype=np.float64, no_def
     ss = np.zeros((bs, npix), dtype=dtype)
     gparams = np.zeros((P, bs), dtype=dtype) if g_ss is not None else None
     beta = np.zeros((bs, 2, npix), dtype=dtype) if want_beta else None
+    comps = None
+    if want_comps:
+        depth = lib.glh_depth(C.byref(cm.desc))
+        comps = np.zeros((bs, depth, npix), dtype=dtype)
     g_ss_c = np.ascontiguousarray(g_ss, dtype=dtype) if g_ss is not None else None
     vp = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
     rc = fn(C.byref(cm.desc), C.c_int(bs), vp(mat), C.c_int(npix), vp(gx), vp(gy), C.c_int(int(no_deflection)),
-            C.c_int(int(epl_batch_max)), vp(ss), vp(g_ss_c), vp(gparams), vp(beta))
+            C.c_int(int(epl_batch_max)), vp(ss), vp(g_ss_c), vp(gparams), vp(beta), vp(comps))
     if rc != 0:
         raise RuntimeError(lib.glh_last_error().decode())
-    return dict(ss=ss, gparams=gparams, beta=beta)
+    return dict(ss=ss, gparams=gparams, beta=beta, comps=comps)
 
 
 # ---------------------------------------------------------------- parity rule

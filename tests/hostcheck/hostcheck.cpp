@@ -21,12 +21,15 @@ struct HostFlush {
 
 template <class T>
 static int run(const gl_model_desc* m, int bs, const T* params, int npix, const T* gx, const T* gy, int no_deflection,
-               int epl_batch_max, T* ss_out, const T* g_ss, T* gparams, T* beta_out) {
+               int epl_batch_max, T* ss_out, const T* g_ss, T* gparams, T* beta_out, T* comps_out) {
   GlBuilt B;
   std::string e = gl_build_program(m, B);
   if (!e.empty()) { g_err = e; return 1; }
-  const GlProgram& P = B.prog;
+  GlProgram& P = B.prog;
+  for (int i = 0; i < P.n_prof; ++i)
+    if (B.table_off[i] >= 0) P.prof[i].table = B.tables.data() + B.table_off[i];
   const float* mf = B.member_factor.empty() ? nullptr : B.member_factor.data();
+  const int* as = B.amp_slot.empty() ? nullptr : B.amp_slot.data();
   std::vector<float> fmax(P.n_prof, -1.f);
   if (epl_batch_max) {
     for (int i = 0; i < P.n_lens; ++i) {
@@ -45,7 +48,7 @@ static int run(const gl_model_desc* m, int bs, const T* params, int npix, const 
   }
   std::vector<T> der(P.der_total), g(P.g_total > 0 ? P.g_total : 1);
   for (int b = 0; b < bs; ++b) {
-    gl_sample_prep<T, T>(P, params, bs, b, mf, epl_batch_max ? fmax.data() : nullptr, der.data());
+    gl_sample_prep<T, T>(P, params, bs, b, mf, as, epl_batch_max ? fmax.data() : nullptr, der.data());
     std::fill(g.begin(), g.end(), T(0));
     HostFlush<T> fl{g.data()};
     for (int p = 0; p < npix; ++p) {
@@ -53,6 +56,11 @@ static int run(const gl_model_desc* m, int bs, const T* params, int npix, const 
       if (ss_out) {
         gl_pix_image<T, 1>(P, der.data(), x, y, no_deflection != 0, v);
         ss_out[(size_t)b * npix + p] = gl_isnan(v[0]) ? T(0) : v[0];
+      }
+      if (comps_out) {   // [bs][depth][npix]
+        T bx[1], by[1];
+        if (no_deflection) { bx[0] = x[0]; by[0] = y[0]; } else gl_pix_beta<T, 1>(P, der.data(), x, y, bx, by);
+        gl_point_components<T>(P, der.data(), x[0], y[0], bx[0], by[0], comps_out + (size_t)b * P.depth * npix + p, npix, true);
       }
       if (beta_out) {
         T bx[1], by[1];
@@ -65,19 +73,22 @@ static int run(const gl_model_desc* m, int bs, const T* params, int npix, const 
         gl_pix_image_bwd<T, 1>(P, der.data(), x, y, gs, no_deflection != 0, fl);
       }
     }
-    if (g_ss && gparams) gl_sample_prep_bwd<T, T>(P, params, bs, b, mf, der.data(), g.data(), gparams);
+    if (g_ss && gparams) gl_sample_prep_bwd<T, T>(P, params, bs, b, mf, as, der.data(), g.data(), gparams);
   }
   return 0;
 }
 
 extern "C" {
 const char* glh_last_error() { return g_err.c_str(); }
+int glh_depth(const gl_model_desc* m) { GlBuilt B; std::string e = gl_build_program(m, B); if (!e.empty()) { g_err = e; return -1; } return B.prog.depth; }
 int glh_run_f64(const gl_model_desc* m, int bs, const double* params, int npix, const double* gx, const double* gy,
-                int no_deflection, int epl_batch_max, double* ss_out, const double* g_ss, double* gparams, double* beta_out) {
-  return run<double>(m, bs, params, npix, gx, gy, no_deflection, epl_batch_max, ss_out, g_ss, gparams, beta_out);
+                int no_deflection, int epl_batch_max, double* ss_out, const double* g_ss, double* gparams, double* beta_out,
+                double* comps_out) {
+  return run<double>(m, bs, params, npix, gx, gy, no_deflection, epl_batch_max, ss_out, g_ss, gparams, beta_out, comps_out);
 }
 int glh_run_f32(const gl_model_desc* m, int bs, const float* params, int npix, const float* gx, const float* gy,
-                int no_deflection, int epl_batch_max, float* ss_out, const float* g_ss, float* gparams, float* beta_out) {
-  return run<float>(m, bs, params, npix, gx, gy, no_deflection, epl_batch_max, ss_out, g_ss, gparams, beta_out);
+                int no_deflection, int epl_batch_max, float* ss_out, const float* g_ss, float* gparams, float* beta_out,
+                float* comps_out) {
+  return run<float>(m, bs, params, npix, gx, gy, no_deflection, epl_batch_max, ss_out, g_ss, gparams, beta_out, comps_out);
 }
 }

@@ -65,3 +65,22 @@ def loglike_and_grad_matrix(wl, cm, mat, dtype=torch.float32):
     ll, chi2 = pm.stats_pixels_from_image(im, sim.img_region)
     ll.sum().backward()
     return ll.detach().numpy(), chi2.detach().numpy(), im.detach().numpy(), leaf.grad.numpy()
+
+
+def build_oracle_backward(wl, bs, dtype=torch.float32):
+    sc = wl["sim_config"]
+    om = common.to_oracle_model(wl["phys_model"], dtype)
+    sim = OracleSimulator(om, sc.delta_pix, sc.num_pix, sc.supersample, kernel=sc.kernel,
+                          transform_pix2angle=sc.transform_pix2angle, pix_region=sc.pix_region, bs=bs, dtype=dtype)
+    pm = OM.BackwardProbModel(to_oracle_prior(wl["prior"]), wl["observed"], wl["background_rms"], wl["exp_time"], dtype=dtype)
+    return sim, pm
+
+
+def backward_logprob_and_grad(wl, z, dtype=torch.float32):
+    """BackwardProbModel.log_prob (lstsq path) and its autograd gradient through torch.linalg.pinv."""
+    z = np.asarray(z)
+    sim, pm = build_oracle_backward(wl, z.shape[0], dtype)
+    zt = torch.as_tensor(z, dtype=dtype).clone().requires_grad_(True)
+    logp, chi2 = pm.log_prob(sim, zt)
+    logp.sum().backward()
+    return logp.detach().numpy(), chi2.detach().numpy(), zt.grad.numpy()

@@ -15,7 +15,8 @@ import oracle_bridge
 from common import assert_parity
 from gigalens_b200 import workloads
 from gigalens_b200.model import ForwardProbModel, PhysicalModel
-from gigalens_b200.profiles.light import sersic
+from gigalens_b200.model import BackwardProbModel
+from gigalens_b200.profiles.light import sersic, shapelets
 from gigalens_b200.profiles.mass import dpie_subhalo, epl, nfw, piemd, shear, sie, sis
 from gigalens_b200.simulator import LensSimulator, SimulatorConfig
 from oracle import model as OM
@@ -193,3 +194,79 @@ def test_profile_point_evaluation_mirrors_reference_profile_tests():
     half = sersic.SersicEllipse().light(x=np.float32(0.0), y=np.float32(1.0), R_sersic=1.0, n_sersic=2.0, e1=0.0, e2=0.0,
                                         center_x=0.0, center_y=0.0, Ie=5.0)
     assert abs(float(half) - 5.0) < 1e-5
+
+
+@pytest.mark.parametrize("interpolate", [False, True])
+def test_shapelets_source_with_free_amplitudes(interpolate):
+    """Shapelets (non-lstsq: amplitudes are free parameters) through the full pipeline and adjoint."""
+    n, bs, ss = 24, 3, 2
+    pm = PhysicalModel([epl.EPL(30), shear.Shear()], [sersic.Sersic()], [shapelets.Shapelets(4, interpolate=interpolate)])
+    rng = np.random.default_rng(5)
+    sc = SimulatorConfig(delta_pix=0.04, num_pix=n, supersample=ss, kernel=workloads.load_psf()[4:9, 4:9])
+    obs = rng.normal(0, 1, size=(n, n)).astype(np.float32) + 5
+    emap = rng.uniform(0.5, 1.5, size=(n, n)).astype(np.float32)
+    sim = LensSimulator(pm, sc, bs=bs)
+    cm = sim.compiled
+    mat = common.draw_matrix(cm, bs, seed=9).astype(np.float32)
+    pmod = ForwardProbModel({"lens_mass": []}, obs, error_map=emap)
+    dev = torch.as_tensor(mat, device="cuda")
+    ll, chi2, g = (t.cpu().numpy() for t in pmod.loglike_and_grad(sim, dev))
+    img = sim.simulate(dev).cpu().numpy()
+
+    def oracle(m, dt):
+        osim = OracleSimulator(common.to_oracle_model(pm, dt), sc.delta_pix, n, ss, kernel=sc.kernel, bs=bs, dtype=dt)
+        opm = OM.ForwardProbModel(OM.JointPrior({}), obs, error_map=emap, dtype=dt)
+        params, leaf = common.matrix_to_pytree(cm, m, dt, requires_grad=True)
+        im = osim.simulate(params)
+        rll, _ = opm.stats_pixels_from_image(im, osim.img_region)
+        rll.sum().backward()
+        return im.detach().numpy(), rll.detach().numpy(), leaf.grad.numpy()
+
+    im32, ll32, g32 = oracle(mat.astype(np.float64), torch.float32)
+    im64, ll64, g64 = oracle(mat.astype(np.float64), torch.float64)
+    im64p, ll64p, g64p = oracle(common.ulp_perturb(mat), torch.float64)
+    assert_parity(img, im32, im64, 1e-5, "image", im64p, axis=(1, 2))
+    assert_parity(ll[:, None], ll32[:, None], ll64[:, None], 1e-5, "log-like", ll64p[:, None], axis=1)
+    for k in range(cm.n_params):
+        assert_parity(g[k], g32[k], g64[k], 1e-4, f"grad {cm.slot_keys[k]}", g64p[k])
+
+
+@pytest.mark.parametrize("n_max,interpolate,with_lens_light", [(10, False, False), (6, True, True)])
+def test_lstsq_simulate_and_backward_model(n_max, interpolate, with_lens_light):
+    """lstsq_simulate (component stack -> depthwise conv -> normal equations -> pinv -> image) and
+    BackwardProbModel.log_prob with its gradient, vs the oracle (torch.linalg.pinv + autograd)."""
+    bs = 4
+    wl = workloads.c3_workload(n_max=n_max, interpolate=interpolate)
+    if with_lens_light:
+        wl["phys_model"] = PhysicalModel(wl["phys_model"].lenses, [sersic.SersicEllipse(use_lstsq=True)], wl["phys_model"].source_light)
+        prior = dict(wl["prior"].model)
+        from gigalens_b200 import distributions as tfd
+        prior["lens_light"] = [dict(R_sersic=tfd.LogNormal(0.0, 0.15), n_sersic=tfd.Uniform(2, 6), e1=tfd.Normal(0, 0.1),
+                                    e2=tfd.Normal(0, 0.1), center_x=tfd.Normal(0, 0.05), center_y=tfd.Normal(0, 0.05))]
+        wl["prior"] = tfd.JointDistributionNamed(prior)
+    sim = LensSimulator(wl["phys_model"], wl["sim_config"], bs=bs)
+    pmod = BackwardProbModel(wl["prior"], wl["observed"], wl["background_rms"], wl["exp_time"])
+    z = pmod.bij_inverse(wl["prior"].sample(bs, seed=2))
+    zdev = torch.as_tensor(z, device="cuda")
+    params = pmod.bij_forward(sim, zdev)
+    coef = sim.lstsq_simulate(params, wl["observed"], pmod.err_map, return_coeffs=True).cpu().numpy()
+    img = sim.lstsq_simulate(params, wl["observed"], pmod.err_map).cpu().numpy()
+    logp, chi2, dz = (t.cpu().numpy() for t in pmod.log_prob_and_grad(sim, zdev))
+
+    ref = {}
+    for dt, zz in ((torch.float32, z), (torch.float64, z.astype(np.float64)), ("pert", common.ulp_perturb(z))):
+        tdt = torch.float64 if dt == "pert" else dt
+        osim, opm = oracle_bridge.build_oracle_backward(wl, bs, tdt)
+        p, _ = opm.prior.forward(torch.as_tensor(zz, dtype=tdt))
+        c = osim.lstsq_simulate(p, opm.observed_image, opm.err_map, return_coeffs=True).numpy()
+        im = osim.lstsq_simulate(p, opm.observed_image, opm.err_map).numpy()
+        ref[dt] = (c, im) + oracle_bridge.backward_logprob_and_grad(wl, zz, tdt)
+    c32, im32, lp32, chi32, dz32 = ref[torch.float32]
+    c64, im64, lp64, chi64, dz64 = ref[torch.float64]
+    c64p, im64p, lp64p, chi64p, dz64p = ref["pert"]
+    assert_parity(coef, c32, c64, 1e-5, "coeffs", c64p, axis=1)
+    assert_parity(img, im32, im64, 1e-5, "image", im64p, axis=(1, 2))
+    assert_parity(logp[:, None], lp32[:, None], lp64[:, None], 1e-5, "logp", lp64p[:, None], axis=1)
+    assert_parity(chi2[:, None], chi32[:, None], chi64[:, None], 1e-5, "red chi2", chi64p[:, None], axis=1)
+    for k in range(z.shape[1]):
+        assert_parity(dz[:, k], dz32[:, k], dz64[:, k], 1e-4, f"dz[{k}]", dz64p[:, k])
