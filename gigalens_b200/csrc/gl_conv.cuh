@@ -18,7 +18,7 @@
 #include <cuda_runtime.h>
 
 #define GLC_RX 4
-#define GLC_RY 5
+#define GLC_RY 6
 #define GLC_MAX_COL_ITERS 10   // staged tile rows are at most 320 floats wide
 
 // 4-byte asynchronous global->shared copy (LDGSTS); src_bytes = 0 zero-fills (used for the SAME padding).
@@ -37,6 +37,7 @@ struct GlConvGeom {
   int A;        // taps per phase (template value actually used; weights zero-padded up to it)
   int pad;      // SAME padding of the K x K kernel: (K-1)/2
   int ntx, nty; // thread tiles per CTA tile in x / y
+  int tpr;      // threads per thread-row (ntx rounded up so that LDS.128 quarter-warps do not straddle rows)
   int tw, th;   // CTA tile size in outputs: ntx*RX, nty*RY
   int tiles_x, tiles_y;
   int in_rows, in_pitch;   // smem input tile: rows = th + A - 1, pitch = roundup4(tw + A - 1)
@@ -46,43 +47,26 @@ struct GlConvGeom {
   int rc0;      // adjoint only: first padded-phase row/column (pad / ss)
 };
 
-// One input row of the thread's strip applied to output rows r in [RLO, RHI] (compile-time range):
-// the row sits `row` below the strip origin and reaches output row r through tap row a = row - r,
-// so the tap rows are wrow, wrow - wpitch, ... for r = 0, 1, ...  (wrow = w + row * wpitch).
-template <int A, int RLO, int RHI>
-__device__ __forceinline__ void corr_one_row(const float* __restrict__ inrow, const float* __restrict__ wrow, int wpitch,
-                                             float (&acc)[GLC_RY][GLC_RX]) {
-  constexpr int SL = (GLC_RX + A - 1 + 3) & ~3;   // strip length rounded up to float4
-  constexpr int WL = (A + 3) & ~3;
-  float strip[SL];
-  const float4* src = reinterpret_cast<const float4*>(inrow);
-#pragma unroll
-  for (int v = 0; v < SL / 4; ++v) {
-    float4 t = src[v];
-    strip[4 * v] = t.x; strip[4 * v + 1] = t.y; strip[4 * v + 2] = t.z; strip[4 * v + 3] = t.w;
-  }
-#pragma unroll
-  for (int r = RLO; r <= RHI; ++r) {
-    float wt[WL];
-    const float4* wsrc = reinterpret_cast<const float4*>(wrow - r * wpitch);
-#pragma unroll
-    for (int v = 0; v < WL / 4; ++v) {
-      float4 t = wsrc[v];
-      wt[4 * v] = t.x; wt[4 * v + 1] = t.y; wt[4 * v + 2] = t.z; wt[4 * v + 3] = t.w;
-    }
-#pragma unroll
-    for (int b = 0; b < A; ++b)
-#pragma unroll
-      for (int c = 0; c < GLC_RX; ++c) acc[r][c] = fmaf(wt[b], strip[c + b], acc[r][c]);
-  }
-}
+// ---- register-tile correlation with packed fp32 FMA (FFMA2, sm_100+) ---------------------------
+// acc2[rp][c] holds the output pair (row 2rp, row 2rp+1) of column c.  One input row of the thread's
+// strip (RX+A-1 floats, LDS.128) sits `row` below the strip origin and reaches output row r through
+// tap row a = row - r.  For tap column b the two taps of a pair are (w[row-2rp][b], w[row-2rp-1][b]):
+// consecutive entries of the per-column REVERSED, zero-padded tap array
+//     U[b][j] = w[A-1-(j-(RY-1))][b]   (0 outside),   j0(row) = A + RY - 2 - row,
+// so the pair for rp is (U[b][j0+2rp], U[b][j0+2rp+1]) -- one broadcast LDS.64.  Two copies of U
+// (shifted by one float) keep that load 8-byte aligned for both parities of j0.  The FMA is
+//     FFMA2 acc2, strip[c+b].F32 (scalar broadcast), taps.F32x2, acc2
+// i.e. two FMAs per issue slot; out-of-range taps are zeros, and whole pairs that a ramp-up /
+// ramp-down row cannot reach are skipped with a compile-time mask.
+#define GLC_RP (GLC_RY / 2)
+__host__ __device__ constexpr int glc_ulen(int A) { return (A + 2 * GLC_RY - 2 + 3) & ~3; }   // floats per U copy
+// taps table: [phase][b][copy(2)][ulen]
 
-// Same for a ramp-up / ramp-down row, where only some output rows are reachable (range test per r).
-template <int A>
-__device__ __forceinline__ void corr_edge_row(const float* __restrict__ inrow, const float* __restrict__ w, int wpitch, int row,
-                                              float (&acc)[GLC_RY][GLC_RX]) {
+template <int A, int MASK>
+__device__ __forceinline__ void corr_row2(const float* __restrict__ inrow, const float* __restrict__ urow /* &U[0][copy][j0e] */,
+                                          float2 (&acc2)[GLC_RP][GLC_RX]) {
   constexpr int SL = (GLC_RX + A - 1 + 3) & ~3;
-  constexpr int WL = (A + 3) & ~3;
+  constexpr int UL = glc_ulen(A);
   float strip[SL];
   const float4* src = reinterpret_cast<const float4*>(inrow);
 #pragma unroll
@@ -91,46 +75,50 @@ __device__ __forceinline__ void corr_edge_row(const float* __restrict__ inrow, c
     strip[4 * v] = t.x; strip[4 * v + 1] = t.y; strip[4 * v + 2] = t.z; strip[4 * v + 3] = t.w;
   }
 #pragma unroll
-  for (int r = 0; r < GLC_RY; ++r) {
-    const int a = row - r;
-    if (a >= 0 && a < A) {
-      float wt[WL];
-      const float4* wsrc = reinterpret_cast<const float4*>(w + a * wpitch);
+  for (int b = 0; b < A; ++b) {
+    const float2* u2 = reinterpret_cast<const float2*>(urow + b * 2 * UL);
 #pragma unroll
-      for (int v = 0; v < WL / 4; ++v) {
-        float4 t = wsrc[v];
-        wt[4 * v] = t.x; wt[4 * v + 1] = t.y; wt[4 * v + 2] = t.z; wt[4 * v + 3] = t.w;
+    for (int rp = 0; rp < GLC_RP; ++rp) {
+      if ((MASK >> rp) & 1) {
+        const float2 w2 = u2[rp];
+#pragma unroll
+        for (int c = 0; c < GLC_RX; ++c) {
+          const float sv = strip[c + b];
+          acc2[rp][c] = __ffma2_rn(make_float2(sv, sv), w2, acc2[rp][c]);
+        }
       }
-#pragma unroll
-      for (int b = 0; b < A; ++b)
-#pragma unroll
-        for (int c = 0; c < GLC_RX; ++c) acc[r][c] = fmaf(wt[b], strip[c + b], acc[r][c]);
     }
   }
 }
 
-// acc[r][c] += sum_{a,b} w[a][b] * in[(r+a)*pitch + c + b]   for the thread's strip origin `in`.
-// Rows that reach every output row (RY-1 <= row <= A-1) run in a rolled loop whose body is
-// RY*A*RX FFMA + (RY+1) float4-groups of LDS and two pointer bumps, with no range tests; only the
-// RY-1 ramp-up and RY-1 ramp-down rows pay a per-output-row test.
+// acc2 += correlation of the thread's strip (origin `in`) with the taps of one phase (table `u`).
 template <int A>
-__device__ __forceinline__ void corr_rows(const float* __restrict__ in, int pitch, const float* __restrict__ w, int wpitch,
-                                          float (&acc)[GLC_RY][GLC_RX]) {
-  if constexpr (A >= GLC_RY) {
+__device__ __forceinline__ void corr_rows2(const float* __restrict__ in, int pitch, const float* __restrict__ u,
+                                           float2 (&acc2)[GLC_RP][GLC_RX]) {
+  constexpr int UL = glc_ulen(A);
+  constexpr int ROWS = GLC_RY + A - 1;
 #pragma unroll 1
-    for (int row = 0; row < GLC_RY - 1; ++row) corr_edge_row<A>(in + row * pitch, w, wpitch, row, acc);
-    const float* inrow = in + (GLC_RY - 1) * pitch;
-    const float* wrow = w + (GLC_RY - 1) * wpitch;
-#pragma unroll 1
-    for (int row = GLC_RY - 1; row <= A - 1; ++row) {
-      corr_one_row<A, 0, GLC_RY - 1>(inrow, wrow, wpitch, acc);
-      inrow += pitch; wrow += wpitch;
+  for (int row = 0; row < ROWS; ++row) {
+    const int j0 = A + GLC_RY - 2 - row;
+    // copy 1 holds U shifted left by one float, so an odd j0 reads copy 1 at index j0 - 1 (even)
+    const float* up = (j0 & 1) ? (u + UL + (j0 - 1)) : (u + j0);
+    const int lo_r = row - (A - 1) > 0 ? row - (A - 1) : 0;
+    const int hi_r = row < GLC_RY - 1 ? row : GLC_RY - 1;
+    const int lo_p = lo_r >> 1, hi_p = hi_r >> 1;
+    const float* inrow = in + row * pitch;
+    if (lo_p == 0 && hi_p == GLC_RP - 1) corr_row2<A, (1 << GLC_RP) - 1>(inrow, up, acc2);
+    else {
+      int mask = 0;
+      for (int q = lo_p; q <= hi_p; ++q) mask |= 1 << q;
+      switch (mask) {
+        case 1: corr_row2<A, 1>(inrow, up, acc2); break;
+        case 2: corr_row2<A, 2>(inrow, up, acc2); break;
+        case 3: corr_row2<A, 3>(inrow, up, acc2); break;
+        case 4: corr_row2<A, 4>(inrow, up, acc2); break;
+        case 6: corr_row2<A, 6>(inrow, up, acc2); break;
+        default: corr_row2<A, 7>(inrow, up, acc2); break;
+      }
     }
-#pragma unroll 1
-    for (int row = A; row < GLC_RY + A - 1; ++row) corr_edge_row<A>(in + row * pitch, w, wpitch, row, acc);
-  } else {
-#pragma unroll 1
-    for (int row = 0; row < GLC_RY + A - 1; ++row) corr_edge_row<A>(in + row * pitch, w, wpitch, row, acc);
   }
 }
 
@@ -154,7 +142,7 @@ __global__ void __launch_bounds__(256, 2) k_conv_fwd(GlConvGeom g, const float* 
   const int nph = g.ss * g.ss;
   const int phase_size = g.phase_stride;
   float* s_in = smem;                              // [nph][phase_stride]  (rows of in_pitch)
-  float* s_w = smem + nph * phase_size;            // [nph][A][wpitch]
+  float* s_w = smem + nph * phase_size;            // [nph][A][2][ulen] packed tap table
   __shared__ float s_red[2][8];
 
   const int ntiles = g.tiles_x * g.tiles_y;
@@ -162,7 +150,8 @@ __global__ void __launch_bounds__(256, 2) k_conv_fwd(GlConvGeom g, const float* 
   const int oy0 = (tile / g.tiles_x) * g.th, ox0 = (tile % g.tiles_x) * g.tw;
   const int tid = threadIdx.x, nthr = blockDim.x;
 
-  for (int i = tid; i < nph * A * g.wpitch; i += nthr) s_w[i] = wts[i];
+  constexpr int UTAB = A * 2 * glc_ulen(A);         // floats per phase
+  for (int i = tid; i < nph * UTAB; i += nthr) s_w[i] = wts[i];
   // input tile: global rows ss*oy0 - pad .., one warp per row, lanes along the row (coalesced),
   // de-interleaved by phase on the way into shared memory with asynchronous 4-byte copies: every
   // load of the tile is in flight at once and nothing is staged through registers.  Per-lane column
@@ -206,17 +195,17 @@ __global__ void __launch_bounds__(256, 2) k_conv_fwd(GlConvGeom g, const float* 
   }
   __syncthreads();
 
-  const int ty = tid / g.ntx, tx = tid - ty * g.ntx;
-  const bool active = ty < g.nty;
-  float acc[GLC_RY][GLC_RX];
+  const int ty = tid / g.tpr, tx = tid - ty * g.tpr;
+  const bool active = ty < g.nty && tx < g.ntx;
+  float2 acc2[GLC_RP][GLC_RX];
 #pragma unroll
-  for (int r = 0; r < GLC_RY; ++r)
+  for (int r = 0; r < GLC_RP; ++r)
 #pragma unroll
-    for (int c = 0; c < GLC_RX; ++c) acc[r][c] = 0.f;
+    for (int c = 0; c < GLC_RX; ++c) acc2[r][c] = make_float2(0.f, 0.f);
   if (active) {
     const int origin = ty * GLC_RY * g.in_pitch + tx * GLC_RX;
     for (int ph = 0; ph < nph; ++ph)
-      corr_rows<A>(s_in + ph * phase_size + origin, g.in_pitch, s_w + ph * A * g.wpitch, g.wpitch, acc);
+      corr_rows2<A>(s_in + ph * phase_size + origin, g.in_pitch, s_w + ph * UTAB, acc2);
   }
 
   float chi2 = 0.f, norm = 0.f;
@@ -228,7 +217,7 @@ __global__ void __launch_bounds__(256, 2) k_conv_fwd(GlConvGeom g, const float* 
       for (int c = 0; c < GLC_RX; ++c) {
         const int ox = ox0 + tx * GLC_RX + c;
         if (oy < g.n && ox < g.n) {
-          const float v = acc[r][c] * scale;
+          const float v = ((r & 1) ? acc2[r >> 1][c].y : acc2[r >> 1][c].x) * scale;
           const size_t o = (size_t)oy * g.n + ox;
           if (img) img[(size_t)b * g.n * g.n + o] = v;
           if (like.enabled) {
@@ -281,13 +270,14 @@ __global__ void __launch_bounds__(256, 2) k_conv_bwd(GlConvGeom g, const float* 
   extern __shared__ __align__(16) float smem[];
   const int nph = g.ss * g.ss;
   float* s_in = smem;                                   // [in_rows][in_pitch]  zero-padded dL/d(image)
-  float* s_w = smem + g.in_rows * g.in_pitch;           // [nph][A][wpitch]
+  float* s_w = smem + g.in_rows * g.in_pitch;           // [nph][A][2][ulen] packed (flipped) tap table
   const int ntiles = g.tiles_x * g.tiles_y;
   const int b = blockIdx.x / ntiles, tile = blockIdx.x - b * ntiles;
   const int r0 = g.rc0 + (tile / g.tiles_x) * g.th, c0 = g.rc0 + (tile % g.tiles_x) * g.tw;
   const int tid = threadIdx.x, nthr = blockDim.x;
 
-  for (int i = tid; i < nph * A * g.wpitch; i += nthr) s_w[i] = wts[i];
+  constexpr int UTAB = A * 2 * glc_ulen(A);
+  for (int i = tid; i < nph * UTAB; i += nthr) s_w[i] = wts[i];
   {
     const int warp = tid >> 5, lane = tid & 31, nw = nthr >> 5;
     const float* src = gimg + (size_t)b * g.n * g.n;
@@ -305,18 +295,18 @@ __global__ void __launch_bounds__(256, 2) k_conv_bwd(GlConvGeom g, const float* 
     glc_cp_async_wait_all();
   }
   __syncthreads();
-  const int ty = tid / g.ntx, tx = tid - ty * g.ntx;
-  if (ty >= g.nty) return;
+  const int ty = tid / g.tpr, tx = tid - ty * g.tpr;
+  if (ty >= g.nty || tx >= g.ntx) return;
   const int origin = ty * GLC_RY * g.in_pitch + tx * GLC_RX;
   float* dst = gss + (size_t)b * g.hs * g.hs;
   for (int ph = 0; ph < nph; ++ph) {
     const int py = ph / g.ss, px = ph - py * g.ss;
-    float acc[GLC_RY][GLC_RX];
+    float2 acc2[GLC_RP][GLC_RX];
 #pragma unroll
-    for (int r = 0; r < GLC_RY; ++r)
+    for (int r = 0; r < GLC_RP; ++r)
 #pragma unroll
-      for (int c = 0; c < GLC_RX; ++c) acc[r][c] = 0.f;
-    corr_rows<A>(s_in + origin, g.in_pitch, s_w + ph * A * g.wpitch, g.wpitch, acc);
+      for (int c = 0; c < GLC_RX; ++c) acc2[r][c] = make_float2(0.f, 0.f);
+    corr_rows2<A>(s_in + origin, g.in_pitch, s_w + ph * UTAB, acc2);
 #pragma unroll
     for (int r = 0; r < GLC_RY; ++r) {
       const int i = g.ss * (r0 + ty * GLC_RY + r) + py - g.pad;
@@ -324,7 +314,7 @@ __global__ void __launch_bounds__(256, 2) k_conv_bwd(GlConvGeom g, const float* 
       for (int c = 0; c < GLC_RX; ++c) {
         const int j = g.ss * (c0 + tx * GLC_RX + c) + px - g.pad;
         if (i >= 0 && i < g.hs && j >= 0 && j < g.hs) {
-          float v = acc[r][c] * scale;
+          float v = ((r & 1) ? acc2[r >> 1][c].y : acc2[r >> 1][c].x) * scale;
           if (ss_mask && !ss_mask[(size_t)i * g.hs + j]) v = 0.f;
           dst[(size_t)i * g.hs + j] = v;
         }

@@ -182,7 +182,7 @@ __global__ void k_sample_bwd(GlProgram P, int bs, const float* __restrict__ para
 // ---------------------------------------------------------------------------------------------
 #define GLK_THREADS 256
 
-template <int PPT>
+template <int PPT, unsigned F>
 __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_fwd(GlProgram P, int npix, const float* __restrict__ grid_x,
                                                               const float* __restrict__ grid_y,
                                                               const unsigned char* __restrict__ ss_mask,
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_fwd(GlProgram P, int n
       const int p = pix[j] < npix ? pix[j] : 0;
       x[j] = __ldg(grid_x + p); y[j] = __ldg(grid_y + p);
     }
-    gl_pix_image<float, PPT>(P, s_der, x, y, no_deflection != 0, v);
+    gl_pix_image<float, PPT, F>(P, s_der, x, y, no_deflection != 0, v);
 #pragma unroll
     for (int j = 0; j < PPT; ++j) {
       if (pix[j] < npix) {
@@ -247,7 +247,7 @@ struct DevFlush {
   }
 };
 
-template <int PPT>
+template <int PPT, unsigned F>
 __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_bwd(GlProgram P, int npix, const float* __restrict__ grid_x,
                                                               const float* __restrict__ grid_y,
                                                               const unsigned char* __restrict__ ss_mask,
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_bwd(GlProgram P, int n
       x[j] = __ldg(grid_x + p); y[j] = __ldg(grid_y + p);
       gs[j] = ok ? __ldg(gsrc + p) : 0.f;
     }
-    gl_pix_image_bwd<float, PPT>(P, s_der, x, y, gs, no_deflection != 0, flush);
+    gl_pix_image_bwd<float, PPT, F>(P, s_der, x, y, gs, no_deflection != 0, flush);
   }
   __syncthreads();
   float* out = gpart + ((size_t)b * gridDim.x + blockIdx.x) * P.g_total;
@@ -289,6 +289,7 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_bwd(GlProgram P, int n
 
 // deflection / beta / surface brightness at arbitrary points shared by all samples
 // mode 0: beta (x - alpha), 1: alpha, 2: surface brightness (lens light at theta + source at beta)
+template <unsigned F>
 __global__ void k_points(GlProgram P, int npts, const float* __restrict__ px, const float* __restrict__ py,
                          const float* __restrict__ derived, int mode, float* __restrict__ out0, float* __restrict__ out1) {
   extern __shared__ __align__(16) float s_der[];
@@ -300,11 +301,11 @@ __global__ void k_points(GlProgram P, int npts, const float* __restrict__ px, co
     float x[1] = {px[p]}, y[1] = {py[p]};
     if (mode == 2) {
       float v[1];
-      gl_pix_image<float, 1>(P, s_der, x, y, false, v);
+      gl_pix_image<float, 1, F>(P, s_der, x, y, false, v);
       out0[(size_t)b * npts + p] = v[0];
     } else {
       float bx[1], by[1];
-      gl_pix_beta<float, 1>(P, s_der, x, y, bx, by);
+      gl_pix_beta<float, 1, F>(P, s_der, x, y, bx, by);
       if (mode == 1) { bx[0] = x[0] - bx[0]; by[0] = y[0] - by[0]; }
       out0[(size_t)b * npts + p] = bx[0];
       out1[(size_t)b * npts + p] = by[0];
@@ -322,6 +323,7 @@ struct gl_plan {
   int n = 0, ss = 1, hs = 0, npix = 0;
   float conversion_factor = 1.f;
   bool has_epl = false;
+  int feat_idx = 3;
   int epl_batch_max = 0;
   // static inputs
   float* d_grid_x = nullptr; float* d_grid_y = nullptr;
@@ -386,6 +388,20 @@ static cudaError_t gl_upload(T** dst, const T* src, size_t count) {
   return cudaMemcpy(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice);
 }
 
+// Kernel instantiations by feature set (gl_math.cuh GLF_*): the first set covering the program is used.
+#define GL_FS0 (GLF_EPL | GLF_SHEAR | GLF_SERSIC)
+#define GL_FS1 (GLF_EPL | GLF_SHEAR | GLF_SERSIC | GLF_SHAPELETS)
+#define GL_FS2 (GLF_NFW | GLF_DPIE | GLF_SHEAR | GLF_SERSIC)
+#define GL_FS3 (GLF_ALL)
+static const unsigned kFeatSets[] = {GL_FS0, GL_FS1, GL_FS2, GL_FS3};
+#define GL_FEAT_DISPATCH(idx, ...)                              \
+  switch (idx) {                                                \
+    case 0: { constexpr unsigned F = GL_FS0; __VA_ARGS__; } break; \
+    case 1: { constexpr unsigned F = GL_FS1; __VA_ARGS__; } break; \
+    case 2: { constexpr unsigned F = GL_FS2; __VA_ARGS__; } break; \
+    default: { constexpr unsigned F = GL_FS3; __VA_ARGS__; } break; \
+  }
+
 static const int kConvA[] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 11, 13, 16, 20, 25, 32};
 
 // choose the CTA tile of the conv kernels: cover `extent` outputs with ntx*RX (nty*RY) per tile,
@@ -400,7 +416,7 @@ static void gl_pick_tiles(int extent, int A, int nph_in, GlConvGeom& g) {
       const int threads = ntx * nty;
       if (threads > 256) continue;
       const int in_rows = nty * GLC_RY + A - 1, in_pitch = (ntx * GLC_RX + A - 1 + 3) & ~3;
-      const size_t smem = (size_t)(nph_in * in_rows * in_pitch + 16 * A * ((A + 3) & ~3)) * 4;
+      const size_t smem = (size_t)(nph_in * in_rows * in_pitch + (nph_in > 1 ? nph_in : g.ss * g.ss) * A * 2 * glc_ulen(A)) * 4;
       if (smem > 100 * 1024) continue;
       if ((nph_in > 1 ? g.ss : 1) * in_pitch > 32 * GLC_MAX_COL_ITERS) continue;   // staged row width handled by the loader
       const int warps = ceil_div(threads, 32);
@@ -416,13 +432,13 @@ static void gl_pick_tiles(int extent, int A, int nph_in, GlConvGeom& g) {
   g.tw = g.ntx * GLC_RX; g.th = g.nty * GLC_RY;
   g.tiles_x = ceil_div(extent, g.tw); g.tiles_y = ceil_div(extent, g.th);
   g.in_rows = g.th + A - 1; g.in_pitch = (g.tw + A - 1 + 3) & ~3;
-  // Strip loads are LDS.128 by consecutive threads (tx fastest).  When ntx is not a multiple of 8 a
-  // quarter-warp wraps into the next thread row; pad the pitch so that the wrap continues the bank
-  // sequence ((RY * pitch) mod 32 == (RX * ntx) mod 32), which keeps those wavefronts conflict-free.
-  if (g.ntx % 8 != 0 && g.nty > 1) {
-    for (int extra = 0; extra < 32; extra += 4) {
-      if (((GLC_RY * (g.in_pitch + extra)) & 31) == ((GLC_RX * g.ntx) & 31)) { g.in_pitch += extra; break; }
-    }
+  // Strip loads are LDS.128 by consecutive threads (tx fastest): rows of threads are padded to a
+  // multiple of 8 (one quarter-warp = one 128-byte wavefront) when that costs no extra warp, so a
+  // quarter-warp never straddles two strip rows and the loads stay conflict-free.
+  g.tpr = g.ntx;
+  {
+    const int padded = (g.ntx + 7) & ~7;
+    if (padded * g.nty <= 256 && ceil_div(padded * g.nty, 32) <= ceil_div(g.ntx * g.nty, 32) + 1) g.tpr = padded;
   }
 }
 
@@ -458,6 +474,11 @@ int gl_plan_create(const gl_model_desc* model, const gl_sim_config* sim, int32_t
   p->n = sim->num_pix; p->ss = sim->supersample; p->hs = p->n * p->ss; p->npix = p->hs * p->hs;
   p->conversion_factor = sim->conversion_factor;
   for (int i = 0; i < p->prog.n_lens; ++i) if (p->prog.prof[i].type == GLT_EPL) p->has_epl = true;
+  {
+    unsigned need = 0;
+    for (int i = 0; i < p->prog.n_prof; ++i) need |= gl_feature_of(p->prog.prof[i].type);
+    for (int k = 3; k >= 0; --k) if ((kFeatSets[k] & need) == need) p->feat_idx = k;
+  }
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, device);
   p->sm_count = prop.multiProcessorCount;
@@ -503,7 +524,16 @@ int gl_plan_create(const gl_model_desc* model, const gl_sim_config* sim, int32_t
     if (A < 0) { gl_free_plan(p); return gl_fail("gl_plan_create: PSF too large for the conv kernels (taps per phase > 32)"); }
     p->A = A; p->pad = (K - 1) / 2;
     const int wpitch = (A + 3) & ~3, nph = ss * ss;
-    std::vector<float> wf((size_t)nph * A * wpitch, 0.f), wb((size_t)nph * A * wpitch, 0.f);
+    // packed tap tables for corr_rows2 (gl_conv.cuh): per phase and tap column b two copies of the
+    // reversed, zero-padded column  U[j] = w[A-1-(j-(RY-1))][b]
+    const int UL = glc_ulen(A), UTAB = A * 2 * UL;
+    std::vector<float> wf((size_t)nph * UTAB, 0.f), wb((size_t)nph * UTAB, 0.f);
+    auto put = [&](std::vector<float>& tab, int ph, int a, int b2, float w) {
+      const int j = (A - 1 - a) + (GLC_RY - 1);
+      float* base = tab.data() + (size_t)ph * UTAB + (size_t)b2 * 2 * UL;
+      base[j] = w;                       // copy 0: U[j]
+      if (j >= 1) base[UL + j - 1] = w;  // copy 1: U shifted left by one
+    };
     for (int py = 0; py < ss; ++py)
       for (int px = 0; px < ss; ++px)
         for (int a = 0; a < A; ++a)
@@ -511,8 +541,8 @@ int gl_plan_create(const gl_model_desc* model, const gl_sim_config* sim, int32_t
             const int u = ss * a + py, v = ss * b2 + px;
             const float w = (u < E && v < E) ? (float)keff[(size_t)u * E + v] : 0.f;
             const int ph = py * ss + px;
-            wf[((size_t)ph * A + a) * wpitch + b2] = w;
-            wb[((size_t)ph * A + (A - 1 - a)) * wpitch + (A - 1 - b2)] = w;
+            put(wf, ph, a, b2, w);
+            put(wb, ph, A - 1 - a, A - 1 - b2, w);   // adjoint: flipped taps
           }
     GL_TRY(gl_upload(&p->d_wf, wf.data(), wf.size()));
     GL_TRY(gl_upload(&p->d_wb, wb.data(), wb.size()));
@@ -525,16 +555,16 @@ int gl_plan_create(const gl_model_desc* model, const gl_sim_config* sim, int32_t
     const int nr = (p->hs - 1 + p->pad) / ss - p->bwd_rc_start + 1;
     gl_pick_tiles(nr, A, 1, p->gb);
     p->gb.rc0 = p->bwd_rc_start;
-    p->conv_threads_f = ((p->gf.ntx * p->gf.nty + 31) / 32) * 32;
-    p->conv_threads_b = ((p->gb.ntx * p->gb.nty + 31) / 32) * 32;
+    p->conv_threads_f = ((p->gf.tpr * p->gf.nty + 31) / 32) * 32;
+    p->conv_threads_b = ((p->gb.tpr * p->gb.nty + 31) / 32) * 32;
     {
       // phase sub-images are spaced so that px*stride mod 32 spreads the ss interleaved lanes over the banks
       int stride = (p->gf.in_rows * p->gf.in_pitch + 31) & ~31;
       if (ss > 1) stride += ((32 / ss) + 3) & ~3;
       p->gf.phase_stride = stride;
     }
-    p->smem_cf = (size_t)(nph * p->gf.phase_stride + nph * A * wpitch) * sizeof(float);
-    p->smem_cb = (size_t)(p->gb.in_rows * p->gb.in_pitch + nph * A * wpitch) * sizeof(float);
+    p->smem_cf = (size_t)(nph * p->gf.phase_stride + nph * UTAB) * sizeof(float);
+    p->smem_cb = (size_t)(p->gb.in_rows * p->gb.in_pitch + nph * UTAB) * sizeof(float);
   }
 
   // chunks per sample for the ray-tracing kernels: enough CTAs for ~4 waves, at most one per pixel batch
@@ -650,9 +680,11 @@ static int gl_run_prep(gl_plan* p, const float* params, cudaStream_t st) {
 static int gl_run_raytrace_fwd(gl_plan* p, float* ss_out, int no_deflection, cudaStream_t st) {
   dim3 grid(p->chunks, p->bs);
   const size_t smem = (size_t)p->prog.der_total * sizeof(float);
-  if (smem > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_fwd<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_raytrace_fwd<4><<<grid, GLK_THREADS, smem, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask, p->d_derived,
-                                                     no_deflection, ss_out);
+  GL_FEAT_DISPATCH(p->feat_idx, {
+    if (smem > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_fwd<4, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_raytrace_fwd<4, F><<<grid, GLK_THREADS, smem, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask, p->d_derived,
+                                                          no_deflection, ss_out);
+  })
   GL_LAUNCH_CHECK("k_raytrace_fwd");
   return 0;
 }
@@ -660,9 +692,11 @@ static int gl_run_raytrace_fwd(gl_plan* p, float* ss_out, int no_deflection, cud
 static int gl_run_raytrace_bwd(gl_plan* p, const float* gss, int no_deflection, cudaStream_t st) {
   dim3 grid(p->chunks, p->bs);
   const size_t smem = (size_t)(p->prog.der_total + (GLK_THREADS / 32) * p->prog.g_total) * sizeof(float);
-  if (smem > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_bwd<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_raytrace_bwd<4><<<grid, GLK_THREADS, smem, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask, p->d_derived,
-                                                     no_deflection, gss, p->d_gpart);
+  GL_FEAT_DISPATCH(p->feat_idx, {
+    if (smem > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_bwd<4, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_raytrace_bwd<4, F><<<grid, GLK_THREADS, smem, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask, p->d_derived,
+                                                          no_deflection, gss, p->d_gpart);
+  })
   GL_LAUNCH_CHECK("k_raytrace_bwd");
   return 0;
 }
@@ -736,7 +770,7 @@ int gl_beta(gl_plan* p, const float* params_dev, int32_t npts, const float* x_de
   cudaStream_t st = (cudaStream_t)stream;
   if (gl_run_prep(p, params_dev, st)) return 1;
   dim3 grid((npts + 127) / 128 > 1024 ? 1024 : (npts + 127) / 128, p->bs);
-  k_points<<<grid, 128, (size_t)p->prog.der_total * sizeof(float), st>>>(p->prog, npts, x_dev, y_dev, p->d_derived, 0, bx, by);
+  GL_FEAT_DISPATCH(p->feat_idx, { k_points<F><<<grid, 128, (size_t)p->prog.der_total * sizeof(float), st>>>(p->prog, npts, x_dev, y_dev, p->d_derived, 0, bx, by); })
   GL_LAUNCH_CHECK("k_points");
   return 0;
 }
@@ -750,7 +784,7 @@ int gl_eval_points(gl_plan* p, const float* params_dev, int32_t npts, const floa
   cudaStream_t st = (cudaStream_t)stream;
   if (gl_run_prep(p, params_dev, st)) return 1;
   dim3 grid((npts + 127) / 128 > 1024 ? 1024 : (npts + 127) / 128, p->bs);
-  k_points<<<grid, 128, (size_t)p->prog.der_total * sizeof(float), st>>>(p->prog, npts, x_dev, y_dev, p->d_derived, mode, out0, out1);
+  GL_FEAT_DISPATCH(p->feat_idx, { k_points<F><<<grid, 128, (size_t)p->prog.der_total * sizeof(float), st>>>(p->prog, npts, x_dev, y_dev, p->d_derived, mode, out0, out1); })
   GL_LAUNCH_CHECK("k_points");
   return 0;
 }
@@ -851,7 +885,9 @@ static int gl_lstsq_forward(gl_plan* p, const float* params, float* image, float
   }
   if (gl_run_prep(p, params, st)) return 1;
   const size_t smem_der = (size_t)p->prog.der_total * sizeof(float);
-  if (smem_der > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_comps<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_der));
+  GL_FEAT_DISPATCH(p->feat_idx, {
+    if (smem_der > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_comps<4, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_der));
+  })
   const int nt = (D + 1 + 3) / 4;
   const size_t smem_gram = (size_t)GLL_PT * nt * 4 * sizeof(float);
   const int npair = ((D + 1) & ~1) / 2;
@@ -860,8 +896,10 @@ static int gl_lstsq_forward(gl_plan* p, const float* params, float* image, float
   for (int b0 = 0; b0 < p->bs; b0 += p->lq_chunk) {
     const int nb = (p->bs - b0 < p->lq_chunk) ? p->bs - b0 : p->lq_chunk;
     dim3 grid(p->chunks, nb);
-    k_raytrace_comps<4><<<grid, GLL_THREADS, smem_der, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,
-                                                            p->d_derived + (size_t)b0 * p->prog.der_total, 0, p->d_comps);
+    GL_FEAT_DISPATCH(p->feat_idx, {
+      k_raytrace_comps<4, F><<<grid, GLL_THREADS, smem_der, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,
+                                                                 p->d_derived + (size_t)b0 * p->prog.der_total, 0, p->d_comps);
+    })
     GL_LAUNCH_CHECK("k_raytrace_comps");
     if (gl_run_conv_fwd(p, p->d_comps, 1.f, p->d_R, false, nullptr, st, nb * D)) return 1;
     k_gram<<<nb, GLL_THREADS, smem_gram, st>>>(D, npx, p->d_R, p->d_w, p->d_obs, p->d_gram);

@@ -21,7 +21,7 @@
 
 #define GLL_THREADS 256
 
-template <int PPT>
+template <int PPT, unsigned F>
 __global__ void __launch_bounds__(GLL_THREADS) k_raytrace_comps(GlProgram P, int npix, const float* __restrict__ grid_x,
                                                                 const float* __restrict__ grid_y,
                                                                 const unsigned char* __restrict__ ss_mask,
@@ -48,12 +48,12 @@ __global__ void __launch_bounds__(GLL_THREADS) k_raytrace_comps(GlProgram P, int
 #pragma unroll
       for (int j = 0; j < PPT; ++j) { bx[j] = x[j]; by[j] = y[j]; }
     } else {
-      gl_pix_beta<float, PPT>(P, s_der, x, y, bx, by);
+      gl_pix_beta<float, PPT, F>(P, s_der, x, y, bx, by);
     }
     for (int j = 0; j < PPT; ++j) {
       if (pix[j] >= npix) continue;
       const bool keep = !ss_mask || ss_mask[pix[j]];
-      gl_point_components<float>(P, s_der, x[j], y[j], bx[j], by[j], dst + pix[j], npix, keep);
+      gl_point_components<float, F>(P, s_der, x[j], y[j], bx[j], by[j], dst + pix[j], npix, keep);
     }
   }
 }

@@ -91,6 +91,23 @@ enum {
   GLT_SERSIC = 32, GLT_SERSIC_ELLIPSE = 33, GLT_SHAPELETS = 34
 };
 
+// Feature bits: which profile families a kernel instantiation contains code for.  The per-pixel
+// drivers are templates over a feature mask F; cases outside F are compiled out, so a program that
+// uses only {EPL, SHEAR, SERSIC} runs a kernel whose register allocation is not inflated by the dPIE
+// adjoint or the Shapelets scratch arrays.  GLF_ALL is the generic interpreter.
+enum {
+  GLF_EPL = 1, GLF_SHEAR = 2, GLF_SIE = 4, GLF_SIS = 8, GLF_NFW = 16, GLF_DPIS = 32, GLF_DPIE = 64, GLF_SERSIC = 128,
+  GLF_SHAPELETS = 256, GLF_ALL = 511
+};
+GL_HD unsigned gl_feature_of(int type) {
+  switch (type) {
+    case GLT_EPL: return GLF_EPL; case GLT_SHEAR: return GLF_SHEAR; case GLT_SIE: return GLF_SIE; case GLT_SIS: return GLF_SIS;
+    case GLT_NFW: case GLT_NFW_ELLIPSE: return GLF_NFW; case GLT_DPIS: return GLF_DPIS; case GLT_DPIE: return GLF_DPIE;
+    case GLT_SERSIC: case GLT_SERSIC_ELLIPSE: return GLF_SERSIC; case GLT_SHAPELETS: return GLF_SHAPELETS;
+  }
+  return 0;
+}
+
 #define GL_MAX_DVARS 8      // accumulators per profile in the pixel adjoint
 #define GL_MAX_RAW 8
 
@@ -132,6 +149,20 @@ GL_HD void ellip_bwd(T e1, T e2, T cmax, T gphi, T gq, T& ge1, T& ge2) {
 // =============================================================================================
 enum { EPL_CX = 0, EPL_CY, EPL_C, EPL_S, EPL_Q, EPL_B, EPL_T, EPL_PREF0, EPL_F, EPL_N, EPL_LOG2B, EPL_TAB = 12 };
 enum { EPLG_CX = 0, EPLG_CY, EPLG_PHI, EPLG_Q, EPLG_B, EPLG_T, EPLG_F, EPLG_PREF0 };
+
+// Complex Horner step P <- P w + a for TWO pixels at once with Blackwell's packed fp32 FMA (FFMA2,
+// sm_100+): the series loops are issue-bound, and one FFMA2 retires two FMAs per issue slot.
+#if defined(__CUDA_ARCH__)
+#define GL_HAVE_F32X2 1
+struct GlC2 { float2 r, i; };   // (re, im) of two pixels
+__device__ __forceinline__ void gl_horner2(GlC2& P, const float2 wr, const float2 wi, const float a) {
+  const float2 a2 = make_float2(a, a);
+  const float2 nPi = make_float2(-P.i.x, -P.i.y);
+  const float2 pr = __ffma2_rn(P.r, wr, __ffma2_rn(nPi, wi, a2));
+  const float2 pi = __ffma2_rn(P.r, wi, __fmul2_rn(P.i, wr));
+  P.r = pr; P.i = pi;
+}
+#endif
 
 GL_HD int epl_table_stride(int niter_cap) { return ((niter_cap + 1) + 3) & ~3; }
 GL_HD int epl_der_size(int niter_cap) { return EPL_TAB + 3 * epl_table_stride(niter_cap); }
@@ -240,6 +271,28 @@ GL_HD void epl_fwd(const T* d, int ts, const T* x, const T* y, T* ax, T* ay) {
   (void)ts;
 #pragma unroll
   for (int j = 0; j < NP; ++j) { epl_geom(d, x[j], y[j], G[j]); Pr[j] = A[N]; Pi[j] = T(0); }
+  bool done = false;
+#ifdef GL_HAVE_F32X2
+  if constexpr (sizeof(T) == 4 && (NP % 2) == 0) {
+    GlC2 P2[NP / 2]; float2 wr2[NP / 2], wi2[NP / 2];
+#pragma unroll
+    for (int h = 0; h < NP / 2; ++h) {
+      P2[h].r = make_float2(Pr[2 * h], Pr[2 * h + 1]); P2[h].i = make_float2(0.f, 0.f);
+      wr2[h] = make_float2(G[2 * h].wr, G[2 * h + 1].wr); wi2[h] = make_float2(G[2 * h].wi, G[2 * h + 1].wi);
+    }
+    for (int n = N - 1; n >= 0; --n) {
+      const float a = A[n];
+#pragma unroll
+      for (int h = 0; h < NP / 2; ++h) gl_horner2(P2[h], wr2[h], wi2[h], a);
+    }
+#pragma unroll
+    for (int h = 0; h < NP / 2; ++h) {
+      Pr[2 * h] = P2[h].r.x; Pr[2 * h + 1] = P2[h].r.y; Pi[2 * h] = P2[h].i.x; Pi[2 * h + 1] = P2[h].i.y;
+    }
+    done = true;
+  }
+#endif
+  if (!done)
   for (int n = N - 1; n >= 0; --n) {
     T a = A[n];
 #pragma unroll
@@ -273,6 +326,36 @@ GL_HD void epl_bwd(const T* d, int ts, const T* x, const T* y, const T* gax, con
     epl_geom(d, x[j], y[j], G[j]);
     Pr[j] = A[N]; Pi[j] = T(0); Fr[j] = Af[N]; Fi[j] = T(0); Tr[j] = At[N]; Ti[j] = T(0);
   }
+  bool done = false;
+#ifdef GL_HAVE_F32X2
+  if constexpr (sizeof(T) == 4 && (NP % 2) == 0) {
+    GlC2 P2[NP / 2], F2[NP / 2], T2[NP / 2]; float2 wr2[NP / 2], wi2[NP / 2];
+#pragma unroll
+    for (int h = 0; h < NP / 2; ++h) {
+      P2[h].r = make_float2(Pr[2 * h], Pr[2 * h + 1]); P2[h].i = make_float2(0.f, 0.f);
+      F2[h].r = make_float2(Fr[2 * h], Fr[2 * h + 1]); F2[h].i = make_float2(0.f, 0.f);
+      T2[h].r = make_float2(Tr[2 * h], Tr[2 * h + 1]); T2[h].i = make_float2(0.f, 0.f);
+      wr2[h] = make_float2(G[2 * h].wr, G[2 * h + 1].wr); wi2[h] = make_float2(G[2 * h].wi, G[2 * h + 1].wi);
+    }
+    for (int n = N - 1; n >= 0; --n) {
+      const float a = A[n], af = Af[n], at = At[n];
+#pragma unroll
+      for (int h = 0; h < NP / 2; ++h) {
+        gl_horner2(P2[h], wr2[h], wi2[h], a);
+        gl_horner2(F2[h], wr2[h], wi2[h], af);
+        gl_horner2(T2[h], wr2[h], wi2[h], at);
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < NP / 2; ++h) {
+      Pr[2 * h] = P2[h].r.x; Pr[2 * h + 1] = P2[h].r.y; Pi[2 * h] = P2[h].i.x; Pi[2 * h + 1] = P2[h].i.y;
+      Fr[2 * h] = F2[h].r.x; Fr[2 * h + 1] = F2[h].r.y; Fi[2 * h] = F2[h].i.x; Fi[2 * h + 1] = F2[h].i.y;
+      Tr[2 * h] = T2[h].r.x; Tr[2 * h + 1] = T2[h].r.y; Ti[2 * h] = T2[h].i.x; Ti[2 * h + 1] = T2[h].i.y;
+    }
+    done = true;
+  }
+#endif
+  if (!done)
   for (int n = N - 1; n >= 0; --n) {
     T a = A[n], af = Af[n], at = At[n];
 #pragma unroll
@@ -1072,31 +1155,31 @@ GL_HD void gl_prep_bwd(int type, unsigned flags, const T* raw, const T* d, const
 }
 
 // deflection of one lens entry at NP points (d = derived block of the entry)
-template <class T, int NP>
+template <class T, int NP, unsigned F>
 GL_HD void gl_lens_fwd(int type, int ts, const T* d, const T* x, const T* y, T* ax, T* ay) {
-  switch (type) {
-    case GLT_EPL: epl_fwd<T, NP>(d, ts, x, y, ax, ay); break;
-    case GLT_SHEAR: shear_fwd<T, NP>(d, x, y, ax, ay); break;
-    case GLT_SIE: sie_fwd<T, NP>(d, x, y, ax, ay); break;
-    case GLT_SIS: sis_fwd<T, NP>(d, x, y, ax, ay); break;
-    case GLT_NFW: case GLT_NFW_ELLIPSE: nfw_fwd<T, NP>(d, x, y, ax, ay); break;
-    case GLT_DPIS: dpis_fwd<T, NP>(d, x, y, ax, ay); break;
-    case GLT_DPIE: dpie_fwd<T, NP>(d, x, y, ax, ay); break;
-    default:
 #pragma unroll
-      for (int j = 0; j < NP; ++j) { ax[j] = T(0); ay[j] = T(0); }
+  for (int j = 0; j < NP; ++j) { ax[j] = T(0); ay[j] = T(0); }
+  switch (type) {
+    case GLT_EPL: if constexpr ((F & GLF_EPL) != 0) epl_fwd<T, NP>(d, ts, x, y, ax, ay); break;
+    case GLT_SHEAR: if constexpr ((F & GLF_SHEAR) != 0) shear_fwd<T, NP>(d, x, y, ax, ay); break;
+    case GLT_SIE: if constexpr ((F & GLF_SIE) != 0) sie_fwd<T, NP>(d, x, y, ax, ay); break;
+    case GLT_SIS: if constexpr ((F & GLF_SIS) != 0) sis_fwd<T, NP>(d, x, y, ax, ay); break;
+    case GLT_NFW: case GLT_NFW_ELLIPSE: if constexpr ((F & GLF_NFW) != 0) nfw_fwd<T, NP>(d, x, y, ax, ay); break;
+    case GLT_DPIS: if constexpr ((F & GLF_DPIS) != 0) dpis_fwd<T, NP>(d, x, y, ax, ay); break;
+    case GLT_DPIE: if constexpr ((F & GLF_DPIE) != 0) dpie_fwd<T, NP>(d, x, y, ax, ay); break;
+    default: break;
   }
 }
-template <class T, int NP>
+template <class T, int NP, unsigned F>
 GL_HD void gl_lens_bwd(int type, int ts, const T* d, const T* x, const T* y, const T* gax, const T* gay, T* g) {
   switch (type) {
-    case GLT_EPL: epl_bwd<T, NP>(d, ts, x, y, gax, gay, g); break;
-    case GLT_SHEAR: shear_bwd<T, NP>(d, x, y, gax, gay, g); break;
-    case GLT_SIE: sie_bwd<T, NP>(d, x, y, gax, gay, g); break;
-    case GLT_SIS: sis_bwd<T, NP>(d, x, y, gax, gay, g); break;
-    case GLT_NFW: case GLT_NFW_ELLIPSE: nfw_bwd<T, NP>(d, x, y, gax, gay, g); break;
-    case GLT_DPIS: dpis_bwd<T, NP>(d, x, y, gax, gay, g); break;
-    case GLT_DPIE: dpie_bwd<T, NP>(d, x, y, gax, gay, g); break;
+    case GLT_EPL: if constexpr ((F & GLF_EPL) != 0) epl_bwd<T, NP>(d, ts, x, y, gax, gay, g); break;
+    case GLT_SHEAR: if constexpr ((F & GLF_SHEAR) != 0) shear_bwd<T, NP>(d, x, y, gax, gay, g); break;
+    case GLT_SIE: if constexpr ((F & GLF_SIE) != 0) sie_bwd<T, NP>(d, x, y, gax, gay, g); break;
+    case GLT_SIS: if constexpr ((F & GLF_SIS) != 0) sis_bwd<T, NP>(d, x, y, gax, gay, g); break;
+    case GLT_NFW: case GLT_NFW_ELLIPSE: if constexpr ((F & GLF_NFW) != 0) nfw_bwd<T, NP>(d, x, y, gax, gay, g); break;
+    case GLT_DPIS: if constexpr ((F & GLF_DPIS) != 0) dpis_bwd<T, NP>(d, x, y, gax, gay, g); break;
+    case GLT_DPIE: if constexpr ((F & GLF_DPIE) != 0) dpie_bwd<T, NP>(d, x, y, gax, gay, g); break;
     default: break;
   }
 }

@@ -132,7 +132,7 @@ GL_HD void gl_sample_prep_bwd(const GlProgram& P, const TP* params, int bs, int 
 // per-pixel drivers (NP pixels of one sample at a time; der = derived vector of the sample)
 // ---------------------------------------------------------------------------------------------
 // beta = theta - sum_i alpha_i(theta)   (src/gigalens/tf/simulator.py:72-78)
-template <class T, int NP>
+template <class T, int NP, unsigned F>
 GL_HD void gl_pix_beta(const GlProgram& P, const T* der, const T* x, const T* y, T* bx, T* by) {
 #pragma unroll
   for (int j = 0; j < NP; ++j) { bx[j] = x[j]; by[j] = y[j]; }
@@ -141,7 +141,7 @@ GL_HD void gl_pix_beta(const GlProgram& P, const T* der, const T* x, const T* y,
     const int nm = pr.n_members > 0 ? pr.n_members : 1;
     for (int m = 0; m < nm; ++m) {
       T ax[NP], ay[NP];
-      gl_lens_fwd<T, NP>(pr.type, pr.ts, der + pr.der_off + m * pr.der_size, x, y, ax, ay);
+      gl_lens_fwd<T, NP, F>(pr.type, pr.ts, der + pr.der_off + m * pr.der_size, x, y, ax, ay);
 #pragma unroll
       for (int j = 0; j < NP; ++j) { bx[j] -= ax[j]; by[j] -= ay[j]; }
     }
@@ -149,14 +149,14 @@ GL_HD void gl_pix_beta(const GlProgram& P, const T* der, const T* x, const T* y,
 }
 
 // Supersampled surface brightness before the NaN scrub (tf/simulator.py:124-138), non-lstsq mode.
-template <class T, int NP>
+template <class T, int NP, unsigned F>
 GL_HD void gl_pix_image(const GlProgram& P, const T* der, const T* x, const T* y, bool no_deflection, T* out) {
   T bx[NP], by[NP];
   if (no_deflection) {
 #pragma unroll
     for (int j = 0; j < NP; ++j) { bx[j] = x[j]; by[j] = y[j]; }
   } else {
-    gl_pix_beta<T, NP>(P, der, x, y, bx, by);
+    gl_pix_beta<T, NP, F>(P, der, x, y, bx, by);
   }
 #pragma unroll
   for (int j = 0; j < NP; ++j) out[j] = T(0);
@@ -166,8 +166,11 @@ GL_HD void gl_pix_image(const GlProgram& P, const T* der, const T* x, const T* y
     const T* px = src ? bx : x;
     const T* py = src ? by : y;
     switch (pr.type) {
-      case GLT_SERSIC: case GLT_SERSIC_ELLIPSE: sersic_fwd<T, NP>(der + pr.der_off, px, py, out); break;
+      case GLT_SERSIC: case GLT_SERSIC_ELLIPSE:
+        if constexpr ((F & GLF_SERSIC) != 0) sersic_fwd<T, NP>(der + pr.der_off, px, py, out);
+        break;
       case GLT_SHAPELETS:
+        if constexpr ((F & GLF_SHAPELETS) != 0)
         for (int j = 0; j < NP; ++j)
           out[j] += shp_point<T>(der + pr.der_off, pr.table, (pr.flags & 2u) != 0, pr.n_max, px[j], py[j], (T*)nullptr, 0,
                                  (const T*)nullptr, (T*)nullptr, (T*)nullptr, (T*)nullptr, (T*)nullptr);
@@ -180,19 +183,19 @@ GL_HD void gl_pix_image(const GlProgram& P, const T* der, const T* x, const T* y
 // The D unit-amplitude linear light components at one pixel (lstsq stack before the convolution,
 // tf/simulator.py:183-200 with the layout of jax/simulator.py:171-175): out[c * stride], NaN scrubbed
 // (:200); `keep` = false (pixel outside pix_region) writes zeros.
-template <class T>
+template <class T, unsigned F>
 GL_HD void gl_point_components(const GlProgram& P, const T* der, T x, T y, T bx, T by, T* out, int stride, bool keep) {
   for (int i = P.n_lens; i < P.n_prof; ++i) {
     const GlProf& pr = P.prof[i];
     const bool src = i >= P.n_lens + P.n_ll;
     const T px = src ? bx : x, py = src ? by : y;
     switch (pr.type) {
-      case GLT_SERSIC: case GLT_SERSIC_ELLIPSE: {
+      case GLT_SERSIC: case GLT_SERSIC_ELLIPSE: if constexpr ((F & GLF_SERSIC) != 0) {
         T v[1] = {T(0)}, xx[1] = {px}, yy[1] = {py};
         sersic_fwd<T, 1>(der + pr.der_off, xx, yy, v);
         out[pr.comp_off * stride] = (keep && !gl_isnan(v[0])) ? v[0] : T(0);
       } break;
-      case GLT_SHAPELETS: {
+      case GLT_SHAPELETS: if constexpr ((F & GLF_SHAPELETS) != 0) {
         const int L = shp_layers(pr.n_max);
         T* o = out + pr.comp_off * stride;
         shp_point<T>(der + pr.der_off, pr.table, (pr.flags & 2u) != 0, pr.n_max, px, py, o, stride, (const T*)nullptr,
@@ -210,7 +213,7 @@ GL_HD void gl_point_components(const GlProgram& P, const T* der, T x, T y, T bx,
 // Adjoint of gl_pix_image: gS is the cotangent of the (scrubbed) surface brightness at the NP
 // pixels.  `flush(acc, n, off)` receives the NP-pixel partial cotangent of dvars [off, off+n) --
 // the host harness adds it into a vector, the CUDA kernel warp-reduces it into shared memory.
-template <class T, int NP, class Flush>
+template <class T, int NP, unsigned F, class Flush>
 GL_HD void gl_pix_image_bwd(const GlProgram& P, const T* der, const T* x, const T* y, const T* gS,
                             bool no_deflection, Flush& flush) {
   T bx[NP], by[NP], Gx[NP], Gy[NP];
@@ -218,7 +221,7 @@ GL_HD void gl_pix_image_bwd(const GlProgram& P, const T* der, const T* x, const 
 #pragma unroll
     for (int j = 0; j < NP; ++j) { bx[j] = x[j]; by[j] = y[j]; }
   } else {
-    gl_pix_beta<T, NP>(P, der, x, y, bx, by);
+    gl_pix_beta<T, NP, F>(P, der, x, y, bx, by);
   }
 #pragma unroll
   for (int j = 0; j < NP; ++j) { Gx[j] = T(0); Gy[j] = T(0); }
@@ -230,10 +233,12 @@ GL_HD void gl_pix_image_bwd(const GlProgram& P, const T* der, const T* x, const 
     for (int k = 0; k < GL_MAX_DVARS; ++k) acc[k] = T(0);
     switch (pr.type) {
       case GLT_SERSIC: case GLT_SERSIC_ELLIPSE:
-        if (src) sersic_bwd<T, NP>(der + pr.der_off, bx, by, gS, acc, Gx, Gy);
-        else sersic_bwd<T, NP>(der + pr.der_off, x, y, gS, acc, (T*)nullptr, (T*)nullptr);
+        if constexpr ((F & GLF_SERSIC) != 0) {
+          if (src) sersic_bwd<T, NP>(der + pr.der_off, bx, by, gS, acc, Gx, Gy);
+          else sersic_bwd<T, NP>(der + pr.der_off, x, y, gS, acc, (T*)nullptr, (T*)nullptr);
+        }
         break;
-      case GLT_SHAPELETS: {
+      case GLT_SHAPELETS: if constexpr ((F & GLF_SHAPELETS) != 0) {
         const bool want_amp = !(pr.flags & 1u);
         const int L = shp_layers(pr.n_max);
         T gamp[(GL_SHP_MAXN + 1) * (GL_SHP_MAXN + 2) / 2];
@@ -266,7 +271,7 @@ GL_HD void gl_pix_image_bwd(const GlProgram& P, const T* der, const T* x, const 
       T acc[GL_MAX_DVARS];
 #pragma unroll
       for (int k = 0; k < GL_MAX_DVARS; ++k) acc[k] = T(0);
-      gl_lens_bwd<T, NP>(pr.type, pr.ts, der + pr.der_off + m * pr.der_size, x, y, Gx, Gy, acc);
+      gl_lens_bwd<T, NP, F>(pr.type, pr.ts, der + pr.der_off + m * pr.der_size, x, y, Gx, Gy, acc);
       flush(acc, pr.n_dvars, pr.g_off + m * pr.n_dvars);
     }
   }

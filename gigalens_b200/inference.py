@@ -1,0 +1,293 @@
+"""``ModellingSequence``: MAP / SVI / HMC drivers with the reference's signatures
+(``src/gigalens/inference.py:10-139``, ``src/gigalens/tf/inference.py:17-182``), re-hosted on torch.
+
+Every driver is a thin caller of the hot path ``prob_model.log_prob_and_grad(simulator, z)`` (one
+fused CUDA forward + hand-adjoint pass); the optimiser / sampler state is a handful of small
+``(bs, d)`` tensors.  Multi-GPU: one process per GPU (torchrun), each rank owns a contiguous shard of
+the samples / chains; NCCL carries only the small reductions the algorithms need:
+
+* MAP  - none (per-sample Adam); ``gather=True`` all-gathers the final ``z`` and log-probs.
+* SVI  - one all-reduce(sum) per step of ``[ELBO, grad_mu (d), grad_L (d(d+1)/2)]``
+         (``src/gigalens/jax/inference.py:126-128``).
+* HMC  - per step all-reduce of the acceptance statistic (dual averaging) and the ChEES moments,
+         so that adaptation equals the single-device run.
+SMC (``tf/inference.py:184-302``) is out of scope.
+"""
+import math
+
+import numpy as np
+
+from .simulator import LensSimulator
+
+
+class PolynomialDecay:
+    """``tf.keras.optimizers.schedules.PolynomialDecay`` (used by the reference notebooks)."""
+
+    def __init__(self, initial_learning_rate, decay_steps, end_learning_rate=0.0001, power=1.0):
+        self.lr0, self.steps, self.lr1, self.power = initial_learning_rate, decay_steps, end_learning_rate, power
+
+    def __call__(self, step):
+        s = min(step, self.steps)
+        return (self.lr0 - self.lr1) * (1 - s / self.steps) ** self.power + self.lr1
+
+
+class Adam:
+    """Minimal Adam on one tensor (Keras defaults: beta1 0.9, beta2 0.999, eps 1e-7); ``lr`` may be a
+    float or a schedule ``step -> lr``.  Element-wise, so sharding the batch changes nothing."""
+
+    def __init__(self, learning_rate=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7):
+        self.lr, self.b1, self.b2, self.eps = learning_rate, beta_1, beta_2, epsilon
+        self.t, self.m, self.v = 0, None, None
+
+    def step(self, x, grad):
+        import torch
+
+        if self.m is None:
+            self.m, self.v = torch.zeros_like(x), torch.zeros_like(x)
+        lr = self.lr(self.t) if callable(self.lr) else self.lr
+        self.t += 1
+        self.m.mul_(self.b1).add_(grad, alpha=1 - self.b1)
+        self.v.mul_(self.b2).addcmul_(grad, grad, value=1 - self.b2)
+        alpha = lr * math.sqrt(1 - self.b2 ** self.t) / (1 - self.b1 ** self.t)
+        x.addcdiv_(self.m, self.v.sqrt().add_(self.eps), value=-alpha)
+        return x
+
+
+def _dist():
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized():
+        return dist, dist.get_rank(), dist.get_world_size()
+    return None, 0, 1
+
+
+def _shard(n, rank, world):
+    """Contiguous shard of n items for this rank."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class SurrogateMVN:
+    """``tfd.MultivariateNormalTriL(loc, FillScaleTriL(diag_bijector=Exp, diag_shift=1e-6))``
+    (``tf/inference.py:65-74``) or the diagonal variant (``:76-83``)."""
+
+    def __init__(self, loc, scale_tril):
+        self.loc, self.scale_tril = loc, scale_tril
+
+    def mean(self):
+        return self.loc
+
+    def covariance(self):
+        return self.scale_tril @ self.scale_tril.T
+
+    def sample(self, n, generator=None):
+        import torch
+
+        eps = torch.randn((n, self.loc.shape[0]), device=self.loc.device, dtype=self.loc.dtype, generator=generator)
+        return self.loc + eps @ self.scale_tril.T
+
+
+class ModellingSequence:
+    """``src/gigalens/tf/inference.py:17`` on the CUDA hot path."""
+
+    def __init__(self, phys_model, prob_model, sim_config, simulator_cls=LensSimulator):
+        self.phys_model = phys_model
+        self.prob_model = prob_model
+        self.sim_config = sim_config
+        self._simulator_cls = simulator_cls   # injectable so the sharding / collective logic is testable on CPU
+
+    # ------------------------------------------------------------------ MAP
+    def MAP(self, optimizer=None, start=None, n_samples=500, num_steps=350, seed=0, gather=True, callback=None):
+        """``tf/inference.py:18-45``: per-sample Adam ascent of ``log_prob / event_size``.
+
+        ``optimizer``: an :class:`Adam` (or anything with ``step(z, grad)``); default ``Adam(1e-2)``.
+        ``start``: physical-parameter pytree with ``n_samples`` leaves, default: prior draws.
+        Returns the final unconstrained ``z`` ``(n_samples, d)`` (all samples when ``gather``)."""
+        import torch
+
+        dist, rank, world = _dist()
+        pm = self.prob_model
+        optimizer = optimizer or Adam(1e-2)
+        start = pm.prior.sample(n_samples, seed=seed) if start is None else start
+        z_all = pm.bij_inverse(start)
+        lo, hi = _shard(n_samples, rank, world)
+        sim = self._simulator_cls(self.phys_model, self.sim_config, bs=hi - lo)
+        z = torch.as_tensor(z_all[lo:hi], device=sim.device).clone()
+        event_size = float(torch.count_nonzero(sim.img_region))
+        self.last_red_chi2 = None
+        for step in range(num_steps):
+            logp, red_chi2, dz = pm.log_prob_and_grad(sim, z)
+            grad = dz.mul_(-1.0 / (event_size * n_samples))   # d mean(-logp / event_size) / dz
+            grad = torch.nan_to_num_(grad, nan=0.0, posinf=0.0, neginf=0.0)
+            optimizer.step(z, grad)
+            if callback is not None:
+                callback(step, red_chi2)
+        self.last_red_chi2 = red_chi2
+        if gather and world > 1:
+            sizes = [_shard(n_samples, r, world)[1] - _shard(n_samples, r, world)[0] for r in range(world)]
+            pad = torch.zeros((max(sizes), z.shape[1]), device=z.device)
+            pad[: z.shape[0]] = z
+            parts = [torch.empty_like(pad) for _ in range(world)]
+            dist.all_gather(parts, pad)     # equal-sized blocks; trim the padding of the short shards
+            z = torch.cat([q[:n] for q, n in zip(parts, sizes)], 0)
+        return z
+
+    # ------------------------------------------------------------------ SVI
+    def SVI(self, optimizer=None, start_mean=None, n_vi=250, init_scales=1e-3, num_steps=500, seed=2, full_rank=True):
+        """``tf/inference.py:47-93``: fit a (full-rank) Gaussian surrogate by maximising the ELBO with
+        reparameterised samples; returns ``(q_z, losses)``."""
+        import torch
+
+        dist, rank, world = _dist()
+        pm = self.prob_model
+        optimizer = optimizer or Adam(1e-3)
+        lo, hi = _shard(n_vi, rank, world)
+        sim = self._simulator_cls(self.phys_model, self.sim_config, bs=hi - lo)
+        dev = sim.device
+        mu = torch.as_tensor(np.asarray(start_mean.detach().cpu() if torch.is_tensor(start_mean) else start_mean),
+                             dtype=torch.float32, device=dev).reshape(-1).clone()
+        d = mu.numel()
+        scale = torch.eye(d, device=dev) * init_scales if np.size(init_scales) == 1 \
+            else torch.as_tensor(np.asarray(init_scales), dtype=torch.float32, device=dev)
+        tril_idx = torch.tril_indices(d, d, device=dev)
+        diag_mask = tril_idx[0] == tril_idx[1]
+        # unconstrained parameters of FillScaleTriL(Exp, shift 1e-6): log(diag - 1e-6), off-diagonals as is
+        if full_rank:
+            raw = scale[tril_idx[0], tril_idx[1]].clone()
+            raw[diag_mask] = torch.log(raw[diag_mask] - 1e-6)
+        else:
+            raw = torch.log(torch.diagonal(scale).clone())
+        theta = torch.cat([mu, raw]).requires_grad_(True)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(seed * 1000003 + rank)
+        losses = []
+
+        def build(th):
+            m, r = th[:d], th[d:]
+            if full_rank:
+                L = torch.zeros((d, d), device=dev)
+                vals = torch.where(diag_mask, torch.exp(r) + 1e-6, r)
+                L = L.index_put((tril_idx[0], tril_idx[1]), vals)
+            else:
+                L = torch.diag(torch.exp(r))
+            return m, L
+
+        for step in range(num_steps):
+            m, L = build(theta)
+            eps = torch.randn((hi - lo, d), device=dev, generator=gen)
+            z = m + eps @ L.T
+            logp, _, dz = pm.log_prob_and_grad(sim, z.detach())
+            # loss = mean_i[log q(z_i) - log p(z_i)] over all n_vi samples (tfp.vi.fit_surrogate_posterior);
+            # log q(z(eps)) = -|eps|^2/2 - sum log L_ii - d/2 log 2pi.  The hot-path gradient enters
+            # through the surrogate term <stop_grad(dlogp/dz), z>.
+            logq = -0.5 * (eps ** 2).sum(1) - torch.log(torch.diagonal(L)).sum() - 0.5 * d * math.log(2 * math.pi)
+            good = torch.isfinite(logp)
+            dz = torch.where(good[:, None], dz, torch.zeros_like(dz))
+            surrogate = (logq.sum() - (dz * z).sum()) / n_vi
+            (g,) = torch.autograd.grad(surrogate, theta)
+            loss = (logq - torch.where(good, logp, torch.zeros_like(logp))).sum() / n_vi
+            packed = torch.cat([loss.detach().reshape(1), g])
+            if world > 1:
+                dist.all_reduce(packed)   # the one collective of SVI: [ELBO, grad_mu, grad_L]
+            losses.append(float(packed[0]))
+            with torch.no_grad():
+                optimizer.step(theta, packed[1:])
+        m, L = build(theta.detach())
+        return SurrogateMVN(m, L), losses
+
+    # ------------------------------------------------------------------ HMC
+    def HMC(self, q_z, init_eps=0.3, init_l=3, n_hmc=50, num_burnin_steps=250, num_results=750, max_leapfrog_steps=30,
+            adapt_rate=0.05, adapt_mode="dual", seed=3, target_accept=0.75):
+        """``tf/inference.py:95-182``: HMC preconditioned with the SVI covariance (momentum precision =
+        Sigma, ``:131-138``), dual-averaging (or simple) step-size adaptation and ChEES trajectory-length
+        adaptation during the first 80% of burn-in (``:140-158``).  Returns ``(samples, stats)`` with
+        samples ``(num_results, n_hmc, d)`` (this rank's chains)."""
+        import torch
+
+        if adapt_mode not in ("dual", "simple"):
+            raise ValueError(f"Invalid adaptation mode {adapt_mode}, the options are 'simple' and 'dual'")
+        dist, rank, world = _dist()
+        pm = self.prob_model
+        lo, hi = _shard(n_hmc, rank, world)
+        nloc = hi - lo
+        sim = self._simulator_cls(self.phys_model, self.sim_config, bs=nloc)
+        dev = sim.device
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(seed * 1000003 + rank)
+        cov = q_z.covariance().to(dev)
+        Lc = torch.linalg.cholesky(cov)
+        d = cov.shape[0]
+        z = q_z.sample(nloc, generator=gen).to(dev)
+        logp, _, grad = pm.log_prob_and_grad(sim, z)
+        logp, grad = logp.clone(), grad.clone()
+
+        def allsum(t):
+            if world > 1:
+                dist.all_reduce(t)
+            return t
+
+        n_adapt = int(num_burnin_steps * 0.8)
+        log_eps, log_eps_bar, h_bar, mu_da = math.log(init_eps), 0.0, 0.0, math.log(10 * init_eps)
+        gamma_da, t0_da, kappa_da = 0.05, 10.0, 0.75     # tfp.mcmc.DualAveragingStepSizeAdaptation defaults
+        traj = init_eps * init_l                          # trajectory length T (ChEES adapts log T with Adam)
+        chees_opt = Adam(0.025)
+        log_T = torch.tensor([math.log(traj)], device=dev)
+        samples = torch.empty((num_results, nloc, d), device=dev)
+        stats = {"accept_prob": [], "step_size": [], "num_leapfrog": []}
+        n_evals = 0
+        for it in range(num_burnin_steps + num_results):
+            eps = math.exp(log_eps)
+            # jittered trajectory (Halton-like, shared by all chains / ranks)
+            u = ((it * 0.6180339887498949) % 1.0) if it < n_adapt else 0.5
+            n_leap = int(max(1, min(max_leapfrog_steps, math.ceil(2.0 * u * float(torch.exp(log_T)) / eps))))
+            xi = torch.randn((nloc, d), device=dev, generator=gen)
+            p0 = torch.linalg.solve_triangular(Lc.T, xi.T, upper=True).T          # p ~ N(0, Sigma^-1)
+            zc, pc, gc, lpc = z.clone(), p0.clone(), grad, logp
+            pc = pc + 0.5 * eps * gc
+            for leap in range(n_leap):
+                zc = zc + eps * (pc @ cov)                                           # dz/dt = Sigma p
+                lpc, _, gc = pm.log_prob_and_grad(sim, zc)
+                n_evals += nloc
+                pc = pc + (eps if leap < n_leap - 1 else 0.5 * eps) * gc
+            k0 = 0.5 * ((p0 @ cov) * p0).sum(1)
+            k1 = 0.5 * ((pc @ cov) * pc).sum(1)
+            log_acc = (lpc - k1) - (logp - k0)
+            log_acc = torch.where(torch.isfinite(log_acc), log_acc, torch.full_like(log_acc, -float("inf")))
+            acc_prob = torch.exp(torch.clamp(log_acc, max=0.0))
+            accept = torch.log(torch.rand(nloc, device=dev, generator=gen)) < log_acc
+            if it < n_adapt:
+                # ChEES (tfp GradientBasedTrajectoryLengthAdaptation): moments over ALL chains
+                tot = allsum(torch.cat([zc.sum(0), z.sum(0), torch.tensor([float(nloc)], device=dev)]))
+                mean_prop, mean_prev = tot[:d] / tot[-1], tot[d:2 * d] / tot[-1]
+                xc, yc = zc - mean_prop, z - mean_prev
+                v = pc @ cov
+                dsq = (xc ** 2).sum(1) - (yc ** 2).sum(1)
+                gi = 2.0 * u * dsq * (xc * v).sum(1)
+                gi = torch.where(torch.isfinite(gi), gi, torch.zeros_like(gi))
+                num_den = allsum(torch.stack([(acc_prob * gi).sum(), acc_prob.sum(), acc_prob.sum() * 0 + float(nloc)]))
+                g_T = num_den[0] / torch.clamp(num_den[1], min=1e-20)
+                # ascent on log T (d crit / d log T = T * d crit / dT), normalised like TFP by T^2
+                chees_opt.step(log_T, -(g_T / torch.exp(log_T)).reshape(1))
+                log_T.clamp_(max=math.log(max_leapfrog_steps * eps))
+                mean_acc = float(num_den[1] / num_den[2])
+                if adapt_mode == "dual":
+                    t_da = it + 1
+                    h_bar = (1 - 1 / (t_da + t0_da)) * h_bar + (target_accept - mean_acc) / (t_da + t0_da)
+                    log_eps = mu_da - math.sqrt(t_da) / gamma_da * h_bar
+                    eta = t_da ** (-kappa_da)
+                    log_eps_bar = eta * log_eps + (1 - eta) * log_eps_bar
+                else:
+                    log_eps += math.log1p(adapt_rate) if mean_acc > target_accept else -math.log1p(adapt_rate)
+                if it == n_adapt - 1 and adapt_mode == "dual":
+                    log_eps = log_eps_bar
+            z = torch.where(accept[:, None], zc, z)
+            logp = torch.where(accept, lpc, logp)
+            grad = torch.where(accept[:, None], gc, grad)
+            stats["accept_prob"].append(float(acc_prob.mean()))
+            stats["step_size"].append(eps)
+            stats["num_leapfrog"].append(n_leap)
+            if it >= num_burnin_steps:
+                samples[it - num_burnin_steps] = z
+        stats["n_evals"] = n_evals
+        return samples, stats

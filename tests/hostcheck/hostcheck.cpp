@@ -54,23 +54,23 @@ static int run(const gl_model_desc* m, int bs, const T* params, int npix, const 
     for (int p = 0; p < npix; ++p) {
       T x[1] = {gx[p]}, y[1] = {gy[p]}, v[1];
       if (ss_out) {
-        gl_pix_image<T, 1>(P, der.data(), x, y, no_deflection != 0, v);
+        gl_pix_image<T, 1, GLF_ALL>(P, der.data(), x, y, no_deflection != 0, v);
         ss_out[(size_t)b * npix + p] = gl_isnan(v[0]) ? T(0) : v[0];
       }
       if (comps_out) {   // [bs][depth][npix]
         T bx[1], by[1];
-        if (no_deflection) { bx[0] = x[0]; by[0] = y[0]; } else gl_pix_beta<T, 1>(P, der.data(), x, y, bx, by);
-        gl_point_components<T>(P, der.data(), x[0], y[0], bx[0], by[0], comps_out + (size_t)b * P.depth * npix + p, npix, true);
+        if (no_deflection) { bx[0] = x[0]; by[0] = y[0]; } else gl_pix_beta<T, 1, GLF_ALL>(P, der.data(), x, y, bx, by);
+        gl_point_components<T, GLF_ALL>(P, der.data(), x[0], y[0], bx[0], by[0], comps_out + (size_t)b * P.depth * npix + p, npix, true);
       }
       if (beta_out) {
         T bx[1], by[1];
-        gl_pix_beta<T, 1>(P, der.data(), x, y, bx, by);
+        gl_pix_beta<T, 1, GLF_ALL>(P, der.data(), x, y, bx, by);
         beta_out[((size_t)b * 2 + 0) * npix + p] = bx[0];
         beta_out[((size_t)b * 2 + 1) * npix + p] = by[0];
       }
       if (g_ss && gparams) {
         T gs[1] = {g_ss[(size_t)b * npix + p]};
-        gl_pix_image_bwd<T, 1>(P, der.data(), x, y, gs, no_deflection != 0, fl);
+        gl_pix_image_bwd<T, 1, GLF_ALL>(P, der.data(), x, y, gs, no_deflection != 0, fl);
       }
     }
     if (g_ss && gparams) gl_sample_prep_bwd<T, T>(P, params, bs, b, mf, as, der.data(), g.data(), gparams);
