@@ -9,7 +9,14 @@
 //   I_{py,px}[r][c] = S[ss*r + py - pad][ss*c + px - pad]   (zero outside the image),
 //
 // and the adjoint is, per phase, the same stride-1 correlation of the zero-padded dL/d(out) with
-// the flipped taps.  Both directions share corr_rows(): each thread owns an RY x RX register tile
+// the flipped taps.
+//
+// HBM layout of the supersampled image: PHASE-MAJOR, ss[b][py'][px'][n][n] with
+// S[ss*ri + py'][ss*cj + px'] at ((py'*ss + px')*n + ri)*n + cj.  The ray-tracing kernels are
+// oblivious (their coordinate tables are permuted once at plan creation), and both conv kernels move
+// contiguous rows: the forward kernel streams one phase sub-image at a time through a two-stage
+// cp.async pipeline (load of phase k+1 overlaps the FMAs of phase k; 2 x one phase tile of shared
+// memory instead of ss^2 tiles => 4 CTAs/SM instead of 2), the adjoint writes each phase contiguously.  Both directions share corr_rows(): each thread owns an RY x RX register tile
 // of outputs, walks the RY+A-1 input rows of its strip once (RX+A-1 floats per row, LDS.128) and
 // applies each row to every output row it reaches; tap weights are broadcast LDS.128.  In the
 // steady state ~90% of issued instructions are FFMA (FP32-FMA bound; north_star forbids tensor
@@ -140,60 +147,42 @@ __global__ void __launch_bounds__(256, 2) k_conv_fwd(GlConvGeom g, const float* 
                                                   float* __restrict__ part, float* __restrict__ gimg) {
   extern __shared__ __align__(16) float smem[];
   const int nph = g.ss * g.ss;
-  const int phase_size = g.phase_stride;
-  float* s_in = smem;                              // [nph][phase_stride]  (rows of in_pitch)
-  float* s_w = smem + nph * phase_size;            // [nph][A][2][ulen] packed tap table
+  const int tile_size = g.in_rows * g.in_pitch;
+  float* s_in = smem;                              // [2][in_rows][in_pitch]  double-buffered phase tile
+  float* s_w = smem + 2 * tile_size;               // [nph][A][2][ulen] packed tap table
   __shared__ float s_red[2][8];
 
   const int ntiles = g.tiles_x * g.tiles_y;
   const int b = blockIdx.x / ntiles, tile = blockIdx.x - b * ntiles;
   const int oy0 = (tile / g.tiles_x) * g.th, ox0 = (tile % g.tiles_x) * g.tw;
   const int tid = threadIdx.x, nthr = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31, nw = nthr >> 5;
 
   constexpr int UTAB = A * 2 * glc_ulen(A);         // floats per phase
   for (int i = tid; i < nph * UTAB; i += nthr) s_w[i] = wts[i];
-  // input tile: global rows ss*oy0 - pad .., one warp per row, lanes along the row (coalesced),
-  // de-interleaved by phase on the way into shared memory with asynchronous 4-byte copies: every
-  // load of the tile is in flight at once and nothing is staged through registers.  Per-lane column
-  // bookkeeping (clamped global column, shared-memory byte offset, validity) is hoisted out of the
-  // row loop; out-of-image elements are zero-filled (src-size 0) from a clamped, always valid address.
-  {
-    const int warp = tid >> 5, lane = tid & 31, nw = nthr >> 5;
-    const int grows = g.ss * g.in_rows, gcols = g.ss * g.in_pitch;
-    const int gi0 = g.ss * oy0 - g.pad, gj0 = g.ss * ox0 - g.pad;
-    const float* src = ss_img + (size_t)b * g.hs * g.hs;
-    const unsigned s_in_u32 = (unsigned)__cvta_generic_to_shared(s_in);
-    const int niters = (gcols + 31) >> 5;
-    unsigned doff[GLC_MAX_COL_ITERS];   // byte offset of this lane's element within a staged row
-    int gjc[GLC_MAX_COL_ITERS];         // clamped global column
-    unsigned csz[GLC_MAX_COL_ITERS];    // 4 if the column is inside the image and the tile, else 0
-#pragma unroll
-    for (int it = 0; it < GLC_MAX_COL_ITERS; ++it) {
-      const int lj = lane + 32 * it;
-      const int c = lj / g.ss, px = lj - c * g.ss;
-      doff[it] = (unsigned)(px * phase_size + c) * 4u;
-      const int gj = gj0 + lj;
-      gjc[it] = min(max(gj, 0), g.hs - 1);
-      csz[it] = (lj < gcols && gj >= 0 && gj < g.hs) ? 4u : 0u;
-      if (lj >= gcols) doff[it] = 0xffffffffu;
-    }
-    for (int li = warp; li < grows; li += nw) {
-      const int gi = gi0 + li;
-      const int r = li / g.ss, py = li - r * g.ss;
-      const bool row_ok = gi >= 0 && gi < g.hs;
-      const unsigned drow = s_in_u32 + (unsigned)(py * g.ss * phase_size + r * g.in_pitch) * 4u;
-      const float* srow = src + (size_t)min(max(gi, 0), g.hs - 1) * g.hs;
-#pragma unroll
-      for (int it = 0; it < GLC_MAX_COL_ITERS; ++it) {
-        if (it < niters && doff[it] != 0xffffffffu) {
-          const unsigned sz = row_ok ? csz[it] : 0u;
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(drow + doff[it]), "l"(srow + gjc[it]), "r"(sz) : "memory");
-        }
+
+  const float* src_b = ss_img + (size_t)b * nph * g.n * g.n;
+  // Stage the tile of image-phase (py', px') = (q / ss, q % ss): padded-phase row r of the conv holds
+  // image row ri = r - sy of that phase (sy = (py' + pad) / ss), zero outside the image.
+  auto issue_phase = [&](int q, float* buf) {
+    const int pyi = q / g.ss, pxi = q - pyi * g.ss;
+    const int sy = (pyi + g.pad) / g.ss, sx = (pxi + g.pad) / g.ss;
+    const float* src = src_b + (size_t)q * g.n * g.n;
+    const unsigned buf_u32 = (unsigned)__cvta_generic_to_shared(buf);
+    for (int li = warp; li < g.in_rows; li += nw) {
+      const int ri = oy0 + li - sy;
+      const bool row_ok = ri >= 0 && ri < g.n;
+      const float* srow = src + (size_t)min(max(ri, 0), g.n - 1) * g.n;
+      const unsigned drow = buf_u32 + (unsigned)(li * g.in_pitch) * 4u;
+      for (int lj = lane; lj < g.in_pitch; lj += 32) {
+        const int cj = ox0 + lj - sx;
+        const bool ok = row_ok && cj >= 0 && cj < g.n;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(drow + 4u * lj), "l"(srow + min(max(cj, 0), g.n - 1)),
+                     "r"(ok ? 4u : 0u) : "memory");
       }
     }
-    glc_cp_async_wait_all();
-  }
-  __syncthreads();
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
 
   const int ty = tid / g.tpr, tx = tid - ty * g.tpr;
   const bool active = ty < g.nty && tx < g.ntx;
@@ -202,10 +191,24 @@ __global__ void __launch_bounds__(256, 2) k_conv_fwd(GlConvGeom g, const float* 
   for (int r = 0; r < GLC_RP; ++r)
 #pragma unroll
     for (int c = 0; c < GLC_RX; ++c) acc2[r][c] = make_float2(0.f, 0.f);
-  if (active) {
-    const int origin = ty * GLC_RY * g.in_pitch + tx * GLC_RX;
-    for (int ph = 0; ph < nph; ++ph)
-      corr_rows2<A>(s_in + ph * phase_size + origin, g.in_pitch, s_w + ph * UTAB, acc2);
+  const int origin = ty * GLC_RY * g.in_pitch + tx * GLC_RX;
+
+  issue_phase(0, s_in);
+  for (int q = 0; q < nph; ++q) {
+    if (q + 1 < nph) {
+      issue_phase(q + 1, s_in + ((q + 1) & 1) * tile_size);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    if (active) {
+      // conv phase of this image phase: (py, px) = ((py' + pad) % ss, (px' + pad) % ss)
+      const int pyi = q / g.ss, pxi = q - pyi * g.ss;
+      const int ph = ((pyi + g.pad) % g.ss) * g.ss + (pxi + g.pad) % g.ss;
+      corr_rows2<A>(s_in + (q & 1) * tile_size + origin, g.in_pitch, s_w + ph * UTAB, acc2);
+    }
+    __syncthreads();
   }
 
   float chi2 = 0.f, norm = 0.f;
@@ -267,6 +270,7 @@ template <int A>
 __global__ void __launch_bounds__(256, 2) k_conv_bwd(GlConvGeom g, const float* __restrict__ gimg, const float* __restrict__ wts,
                                                   float scale, const unsigned char* __restrict__ ss_mask,
                                                   float* __restrict__ gss) {
+  (void)ss_mask;
   extern __shared__ __align__(16) float smem[];
   const int nph = g.ss * g.ss;
   float* s_in = smem;                                   // [in_rows][in_pitch]  zero-padded dL/d(image)
@@ -314,9 +318,12 @@ __global__ void __launch_bounds__(256, 2) k_conv_bwd(GlConvGeom g, const float* 
       for (int c = 0; c < GLC_RX; ++c) {
         const int j = g.ss * (c0 + tx * GLC_RX + c) + px - g.pad;
         if (i >= 0 && i < g.hs && j >= 0 && j < g.hs) {
-          float v = ((r & 1) ? acc2[r >> 1][c].y : acc2[r >> 1][c].x) * scale;
-          if (ss_mask && !ss_mask[(size_t)i * g.hs + j]) v = 0.f;
-          dst[(size_t)i * g.hs + j] = v;
+          const float v = ((r & 1) ? acc2[r >> 1][c].y : acc2[r >> 1][c].x) * scale;
+          // phase-major destination: image phase (i % ss, j % ss), sub-image pixel (i / ss, j / ss);
+          // for fixed conv phase consecutive c are consecutive addresses
+          const int ri = i / g.ss, cj = j / g.ss;
+          const int q = (i - ri * g.ss) * g.ss + (j - cj * g.ss);
+          dst[((size_t)q * g.n + ri) * g.n + cj] = v;
         }
       }
     }

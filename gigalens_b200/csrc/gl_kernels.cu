@@ -287,6 +287,13 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_bwd(GlProgram P, int n
   }
 }
 
+// phase-major -> natural row-major (diagnostic output of gl_simulate_ss only)
+__global__ void k_unpermute(int npix, int bs, const int* __restrict__ perm, const float* __restrict__ src, float* __restrict__ dst) {
+  const int b = blockIdx.y;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < npix; k += gridDim.x * blockDim.x)
+    dst[(size_t)b * npix + perm[k]] = src[(size_t)b * npix + k];
+}
+
 // deflection / beta / surface brightness at arbitrary points shared by all samples
 // mode 0: beta (x - alpha), 1: alpha, 2: surface brightness (lens light at theta + source at beta)
 template <unsigned F>
@@ -330,6 +337,7 @@ struct gl_plan {
   unsigned char* d_ss_mask = nullptr; unsigned char* d_mask = nullptr;
   float* d_member_factor = nullptr;
   int* d_amp_slot = nullptr;
+  int* d_perm = nullptr;
   float* d_tables = nullptr;
   float* d_wf = nullptr; float* d_wb = nullptr;     // forward / flipped taps [nph][A][wpitch]
   int A = 1, pad = 0;
@@ -377,6 +385,7 @@ static void gl_free_plan(gl_plan* p) {
   if (p->d_mask) cudaFree(p->d_mask);
   if (p->d_leaves) cudaFree(p->d_leaves);
   if (p->d_amp_slot) cudaFree(p->d_amp_slot);
+  if (p->d_perm) cudaFree(p->d_perm);
   if (p->d_tables) cudaFree(p->d_tables);
   delete p;
 }
@@ -416,9 +425,8 @@ static void gl_pick_tiles(int extent, int A, int nph_in, GlConvGeom& g) {
       const int threads = ntx * nty;
       if (threads > 256) continue;
       const int in_rows = nty * GLC_RY + A - 1, in_pitch = (ntx * GLC_RX + A - 1 + 3) & ~3;
-      const size_t smem = (size_t)(nph_in * in_rows * in_pitch + (nph_in > 1 ? nph_in : g.ss * g.ss) * A * 2 * glc_ulen(A)) * 4;
+      const size_t smem = (size_t)(nph_in * in_rows * in_pitch + g.ss * g.ss * A * 2 * glc_ulen(A)) * 4;
       if (smem > 100 * 1024) continue;
-      if ((nph_in > 1 ? g.ss : 1) * in_pitch > 32 * GLC_MAX_COL_ITERS) continue;   // staged row width handled by the loader
       const int warps = ceil_div(threads, 32);
       // cost: issued warp-work (incl. idle lanes / edge waste) + halo traffic
       const double work = (double)tiles_x * tiles_y * warps * 32;
@@ -489,13 +497,30 @@ int gl_plan_create(const gl_model_desc* model, const gl_sim_config* sim, int32_t
     if (_e != cudaSuccess) { gl_free_plan(p); return gl_fail(std::string(#call) + ": " + cudaGetErrorString(_e)); } \
   } while (0)
 
-  GL_TRY(gl_upload(&p->d_grid_x, sim->grid_x, (size_t)p->npix));
-  GL_TRY(gl_upload(&p->d_grid_y, sim->grid_y, (size_t)p->npix));
+  // The supersampled buffers are PHASE-MAJOR (gl_conv.cuh): element ((py*ss+px)*n + ri)*n + cj holds
+  // ss pixel (ss*ri + py, ss*cj + px).  The ray-tracing kernels just walk that index space with
+  // permuted coordinate tables, so the permutation costs nothing at run time.
+  std::vector<int> perm((size_t)p->npix);   // phase-major index -> natural row-major index
+  {
+    const int ss = p->ss, n = p->n, hs = p->hs;
+    for (int py = 0; py < ss; ++py)
+      for (int px = 0; px < ss; ++px)
+        for (int ri = 0; ri < n; ++ri)
+          for (int cj = 0; cj < n; ++cj)
+            perm[(((size_t)py * ss + px) * n + ri) * n + cj] = (ss * ri + py) * hs + (ss * cj + px);
+    std::vector<float> gx((size_t)p->npix), gy((size_t)p->npix);
+    for (size_t k = 0; k < perm.size(); ++k) { gx[k] = sim->grid_x[perm[k]]; gy[k] = sim->grid_y[perm[k]]; }
+    GL_TRY(gl_upload(&p->d_grid_x, gx.data(), gx.size()));
+    GL_TRY(gl_upload(&p->d_grid_y, gy.data(), gy.size()));
+    GL_TRY(gl_upload(&p->d_perm, perm.data(), perm.size()));
+  }
   if (sim->mask) {
     std::vector<unsigned char> m((size_t)p->n * p->n), ms((size_t)p->npix);
     for (int i = 0; i < p->n * p->n; ++i) m[i] = sim->mask[i] ? 1 : 0;
-    for (int i = 0; i < p->hs; ++i)
-      for (int j = 0; j < p->hs; ++j) ms[(size_t)i * p->hs + j] = m[(size_t)(i / p->ss) * p->n + j / p->ss];
+    for (size_t k = 0; k < perm.size(); ++k) {
+      const int i = perm[k] / p->hs, j = perm[k] % p->hs;
+      ms[k] = m[(size_t)(i / p->ss) * p->n + j / p->ss];
+    }
     GL_TRY(gl_upload(&p->d_mask, m.data(), m.size()));
     GL_TRY(gl_upload(&p->d_ss_mask, ms.data(), ms.size()));
   }
@@ -549,7 +574,7 @@ int gl_plan_create(const gl_model_desc* model, const gl_sim_config* sim, int32_t
     GlConvGeom g{};
     g.n = p->n; g.hs = p->hs; g.ss = ss; g.A = A; g.pad = p->pad; g.wpitch = wpitch;
     p->gf = g; p->gb = g;
-    gl_pick_tiles(p->n, A, nph, p->gf);
+    gl_pick_tiles(p->n, A, 2, p->gf);   // two staged phase tiles (double buffer)
     // adjoint runs over padded-phase coordinates r in [pad/ss, (hs-1+pad)/ss]
     p->bwd_rc_start = p->pad / ss;
     const int nr = (p->hs - 1 + p->pad) / ss - p->bwd_rc_start + 1;
@@ -557,13 +582,8 @@ int gl_plan_create(const gl_model_desc* model, const gl_sim_config* sim, int32_t
     p->gb.rc0 = p->bwd_rc_start;
     p->conv_threads_f = ((p->gf.tpr * p->gf.nty + 31) / 32) * 32;
     p->conv_threads_b = ((p->gb.tpr * p->gb.nty + 31) / 32) * 32;
-    {
-      // phase sub-images are spaced so that px*stride mod 32 spreads the ss interleaved lanes over the banks
-      int stride = (p->gf.in_rows * p->gf.in_pitch + 31) & ~31;
-      if (ss > 1) stride += ((32 / ss) + 3) & ~3;
-      p->gf.phase_stride = stride;
-    }
-    p->smem_cf = (size_t)(nph * p->gf.phase_stride + nph * UTAB) * sizeof(float);
+    p->gf.phase_stride = p->gf.in_rows * p->gf.in_pitch;
+    p->smem_cf = (size_t)(2 * p->gf.in_rows * p->gf.in_pitch + nph * UTAB) * sizeof(float);
     p->smem_cb = (size_t)(p->gb.in_rows * p->gb.in_pitch + nph * UTAB) * sizeof(float);
   }
 
@@ -751,7 +771,11 @@ int gl_simulate_ss(gl_plan* p, const float* params_dev, float* ss_dev, void* str
   GL_CUDA(cudaSetDevice(p->device));
   cudaStream_t st = (cudaStream_t)stream;
   if (gl_run_prep(p, params_dev, st)) return 1;
-  return gl_run_raytrace_fwd(p, ss_dev, 0, st);
+  if (gl_run_raytrace_fwd(p, p->d_ss, 0, st)) return 1;
+  dim3 grid((p->npix + 255) / 256 > 256 ? 256 : (p->npix + 255) / 256, p->bs);
+  k_unpermute<<<grid, 256, 0, st>>>(p->npix, p->bs, p->d_perm, p->d_ss, ss_dev);
+  GL_LAUNCH_CHECK("k_unpermute");
+  return 0;
 }
 
 int gl_simulate(gl_plan* p, const float* params_dev, float* image_dev, void* stream) {

@@ -1,0 +1,69 @@
+"""GPU smoke tests of the inference drivers, mirroring the reference's ``tests/tf/test_model.py``:
+bijector round trip, fldj shape, MAP / SVI with learning rate 0 leave the parameters unchanged and
+a positive rate changes them, HMC returns ``num_results`` samples.  Data fixture as in the
+reference's ``tests/conftest.py:83-85``: a 20x20 all-zeros image, bg 0.1, exp 100, delta_pix 0.05."""
+import numpy as np
+import pytest
+import torch
+
+from gigalens_b200 import workloads
+from gigalens_b200.inference import Adam, ModellingSequence, PolynomialDecay
+from gigalens_b200.model import ForwardProbModel
+from gigalens_b200.simulator import LensSimulator, SimulatorConfig
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture
+def setup():
+    prior = workloads.demo_prior()
+    phys = workloads.demo_phys_model()
+    prob = ForwardProbModel(prior, np.zeros((20, 20)), background_rms=0.1, exp_time=100)
+    cfg = SimulatorConfig(delta_pix=0.05, num_pix=20)
+    return prior, phys, prob, cfg
+
+
+def test_bij_round_trip_and_fldj_shape(setup):
+    prior, phys, prob, cfg = setup           # tests/tf/test_model.py:10-26
+    sample = prior.sample(5, seed=0)
+    sim = LensSimulator(phys, cfg, bs=5)
+    z = prob.bij_inverse(sample)
+    back = prob.bij_forward(sim, torch.as_tensor(z, device="cuda"))
+    flat_a = sim.compiled.flatten(back, 5, torch, sim.device).cpu().numpy()
+    flat_b = sim.compiled.flatten(sample, 5, torch, "cpu").numpy()
+    assert np.allclose(flat_a, flat_b, rtol=1e-5, atol=1e-6)
+    assert prob.log_prior(sim, torch.as_tensor(z, device="cuda")).numel() == 5
+
+
+def test_map_lr_zero_and_positive(setup):
+    prior, phys, prob, cfg = setup           # tests/tf/test_model.py:29-43
+    seq = ModellingSequence(phys, prob, cfg)
+    start = prior.sample(2, seed=1)
+    z0 = prob.bij_inverse(start)
+    ret = seq.MAP(Adam(0.0), start, n_samples=2, num_steps=5, seed=0)
+    assert np.allclose(ret.cpu().numpy(), z0)
+    ret = seq.MAP(Adam(1e-3), start, n_samples=2, num_steps=5, seed=0)
+    assert not np.allclose(ret.cpu().numpy(), z0)
+
+
+def test_vi_lr_zero_and_positive_then_hmc(setup):
+    prior, phys, prob, cfg = setup           # tests/tf/test_model.py:46-72
+    seq = ModellingSequence(phys, prob, cfg)
+    start = prob.bij_inverse(prior.sample(2, seed=2))[0]
+    q_z, losses = seq.SVI(optimizer=Adam(0.0), start_mean=start, n_vi=5, num_steps=5)
+    assert np.allclose(q_z.mean().cpu().numpy(), start)
+    q_z2, losses = seq.SVI(optimizer=Adam(1e-3), start_mean=start, n_vi=5, num_steps=5)
+    assert not np.allclose(q_z2.mean().cpu().numpy(), start) and len(losses) == 5
+    samples, stats = seq.HMC(q_z, n_hmc=3, init_eps=0.3, init_l=3, max_leapfrog_steps=5, num_burnin_steps=3, num_results=5)
+    assert len(samples) == 5 and samples.shape == (5, 3, 22)
+
+
+def test_map_improves_fit_on_demo_image():
+    """tf-demo.ipynb cell 12 in miniature: MAP from prior draws lowers the best reduced chi^2."""
+    wl = workloads.c2_workload()
+    prob = ForwardProbModel(wl["prior"], wl["observed"], background_rms=0.2, exp_time=100.0)
+    seq = ModellingSequence(wl["phys_model"], prob, wl["sim_config"])
+    hist = []
+    seq.MAP(Adam(PolynomialDecay(1e-2, 150, 2e-3)), n_samples=64, num_steps=150, seed=0,
+            callback=lambda i, chi: hist.append(float(torch.nan_to_num(chi, nan=1e30).min())))
+    assert hist[-1] < 0.2 * hist[0] and hist[-1] < 10.0
