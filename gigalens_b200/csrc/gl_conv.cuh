@@ -311,20 +311,22 @@ __global__ void __launch_bounds__(256, 2) k_conv_bwd(GlConvGeom g, const float* 
 #pragma unroll
       for (int c = 0; c < GLC_RX; ++c) acc2[r][c] = make_float2(0.f, 0.f);
     corr_rows2<A>(s_in + origin, g.in_pitch, s_w + ph * UTAB, acc2);
+    // ss pixel (i, j) = (ss*r + py - pad, ss*c + px - pad) lives in image phase (i mod ss, j mod ss) at
+    // sub-image pixel (i div ss, j div ss): both are constant offsets per conv phase, so the phase-major
+    // destination is contiguous in c and needs no per-element division.
+    const int fy = py - g.pad, fx = px - g.pad;
+    const int dy = (fy >= 0) ? fy / g.ss : -((-fy + g.ss - 1) / g.ss);   // floor division
+    const int dx = (fx >= 0) ? fx / g.ss : -((-fx + g.ss - 1) / g.ss);
+    const int q = (fy - dy * g.ss) * g.ss + (fx - dx * g.ss);
+    float* dq = dst + (size_t)q * g.n * g.n;
 #pragma unroll
     for (int r = 0; r < GLC_RY; ++r) {
-      const int i = g.ss * (r0 + ty * GLC_RY + r) + py - g.pad;
+      const int ri = r0 + ty * GLC_RY + r + dy;
+      if (ri < 0 || ri >= g.n) continue;
 #pragma unroll
       for (int c = 0; c < GLC_RX; ++c) {
-        const int j = g.ss * (c0 + tx * GLC_RX + c) + px - g.pad;
-        if (i >= 0 && i < g.hs && j >= 0 && j < g.hs) {
-          const float v = ((r & 1) ? acc2[r >> 1][c].y : acc2[r >> 1][c].x) * scale;
-          // phase-major destination: image phase (i % ss, j % ss), sub-image pixel (i / ss, j / ss);
-          // for fixed conv phase consecutive c are consecutive addresses
-          const int ri = i / g.ss, cj = j / g.ss;
-          const int q = (i - ri * g.ss) * g.ss + (j - cj * g.ss);
-          dst[((size_t)q * g.n + ri) * g.n + cj] = v;
-        }
+        const int cj = c0 + tx * GLC_RX + c + dx;
+        if (cj >= 0 && cj < g.n) dq[(size_t)ri * g.n + cj] = ((r & 1) ? acc2[r >> 1][c].y : acc2[r >> 1][c].x) * scale;
       }
     }
   }

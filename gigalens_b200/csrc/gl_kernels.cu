@@ -369,7 +369,9 @@ struct gl_plan {
   int sm_count = 148;
   // lstsq workspace (allocated on first use)
   int lstsq = 0;
+  int no_deflection = 0;
   int lq_chunk = 0;
+  int lq_chunk_req = 0;
   float* d_comps = nullptr; float* d_R = nullptr; float* d_gram = nullptr; float* d_coef = nullptr; float* d_w = nullptr;
   float* d_ll = nullptr;
 };
@@ -619,6 +621,11 @@ int gl_plan_set_option(gl_plan* p, const char* name, int32_t value) {
   if (!p || !name) return gl_fail("gl_plan_set_option: NULL argument");
   if (!strcmp(name, "epl_batch_max")) { p->epl_batch_max = value; return 0; }
   if (!strcmp(name, "lstsq")) { p->lstsq = value; return 0; }
+  if (!strcmp(name, "no_deflection")) { p->no_deflection = value; return 0; }
+  if (!strcmp(name, "lstsq_chunk")) {   // samples per pass of the lstsq component stack (0 = size by memory budget)
+    if (p->d_comps) return gl_fail("gl_plan_set_option: lstsq_chunk must be set before the first lstsq call");
+    p->lq_chunk_req = value; return 0;
+  }
   return gl_fail(std::string("gl_plan_set_option: unknown option ") + name);
 }
 
@@ -771,7 +778,7 @@ int gl_simulate_ss(gl_plan* p, const float* params_dev, float* ss_dev, void* str
   GL_CUDA(cudaSetDevice(p->device));
   cudaStream_t st = (cudaStream_t)stream;
   if (gl_run_prep(p, params_dev, st)) return 1;
-  if (gl_run_raytrace_fwd(p, p->d_ss, 0, st)) return 1;
+  if (gl_run_raytrace_fwd(p, p->d_ss, p->no_deflection, st)) return 1;
   dim3 grid((p->npix + 255) / 256 > 256 ? 256 : (p->npix + 255) / 256, p->bs);
   k_unpermute<<<grid, 256, 0, st>>>(p->npix, p->bs, p->d_perm, p->d_ss, ss_dev);
   GL_LAUNCH_CHECK("k_unpermute");
@@ -783,7 +790,7 @@ int gl_simulate(gl_plan* p, const float* params_dev, float* image_dev, void* str
   GL_CUDA(cudaSetDevice(p->device));
   cudaStream_t st = (cudaStream_t)stream;
   if (gl_run_prep(p, params_dev, st)) return 1;
-  if (gl_run_raytrace_fwd(p, p->d_ss, 0, st)) return 1;
+  if (gl_run_raytrace_fwd(p, p->d_ss, p->no_deflection, st)) return 1;
   return gl_run_conv_fwd(p, p->d_ss, p->conversion_factor, image_dev, false, nullptr, st);
 }
 
@@ -821,11 +828,11 @@ static int gl_loglike_core(gl_plan* p, const float* params, float* loglike, floa
   if (p->lstsq) return gl_lstsq_loglike_core(p, params, loglike, red_chi2, dparams, z, logp, dz, st);
   const bool grad = dparams != nullptr;
   if (gl_run_prep(p, params, st)) return 1;
-  if (gl_run_raytrace_fwd(p, p->d_ss, 0, st)) return 1;
+  if (gl_run_raytrace_fwd(p, p->d_ss, p->no_deflection, st)) return 1;
   if (gl_run_conv_fwd(p, p->d_ss, p->conversion_factor, p->d_img, true, grad ? p->d_gimg : nullptr, st)) return 1;
   if (grad) {
     if (gl_run_conv_bwd(p, p->d_gimg, p->conversion_factor, p->d_ss, st)) return 1;
-    if (gl_run_raytrace_bwd(p, p->d_ss, 0, st)) return 1;
+    if (gl_run_raytrace_bwd(p, p->d_ss, p->no_deflection, st)) return 1;
   }
   const int tb = 128, gb = (p->bs + tb - 1) / tb;
   k_sample_bwd<<<gb, tb, 0, st>>>(p->prog, p->bs, params, p->d_member_factor, p->d_amp_slot, p->d_derived, p->d_gpart, p->chunks, p->d_gsum,
@@ -899,6 +906,7 @@ static int gl_lstsq_forward(gl_plan* p, const float* params, float* image, float
     size_t cb = (size_t)6 << 30;
     cb = cb / per_sample;
     if (cb < 1) cb = 1;
+    if (p->lq_chunk_req > 0) cb = (size_t)p->lq_chunk_req;
     if (cb > (size_t)p->bs) cb = p->bs;
     p->lq_chunk = (int)cb;
     GL_CUDA(cudaMalloc((void**)&p->d_comps, cb * per_sample));
@@ -922,7 +930,7 @@ static int gl_lstsq_forward(gl_plan* p, const float* params, float* image, float
     dim3 grid(p->chunks, nb);
     GL_FEAT_DISPATCH(p->feat_idx, {
       k_raytrace_comps<4, F><<<grid, GLL_THREADS, smem_der, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,
-                                                                 p->d_derived + (size_t)b0 * p->prog.der_total, 0, p->d_comps);
+                                                                 p->d_derived + (size_t)b0 * p->prog.der_total, p->no_deflection, p->d_comps);
     })
     GL_LAUNCH_CHECK("k_raytrace_comps");
     if (gl_run_conv_fwd(p, p->d_comps, 1.f, p->d_R, false, nullptr, st, nb * D)) return 1;
@@ -951,7 +959,7 @@ static int gl_lstsq_loglike_core(gl_plan* p, const float* params, float* loglike
     k_patch_amps<<<gb, tb, 0, st>>>(p->prog, p->bs, p->d_coef, p->d_derived);
     GL_LAUNCH_CHECK("k_patch_amps");
     if (gl_run_conv_bwd(p, p->d_gimg, 1.f, p->d_ss, st)) return 1;
-    if (gl_run_raytrace_bwd(p, p->d_ss, 0, st)) return 1;
+    if (gl_run_raytrace_bwd(p, p->d_ss, p->no_deflection, st)) return 1;
   }
   k_sample_bwd<<<gb, tb, 0, st>>>(p->prog, p->bs, params, p->d_member_factor, p->d_amp_slot, p->d_derived, p->d_gpart, p->chunks,
                                   p->d_gsum, nullptr, 0, 1.f, ll, chi, dparams, p->d, p->d_leaves, z,

@@ -682,7 +682,8 @@ GL_HD void nfw_bwd(const T* d, const T* x, const T* y, const T* gax, const T* ga
 //          e, (dPIE only; the pixel code derives sqrt(e), q, ... from e)
 //   dvars: cx, cy, phi, scale, rc, rt, e
 // =============================================================================================
-enum { DP_CX = 0, DP_CY, DP_C, DP_S, DP_SCALE, DP_RC, DP_RT, DP_E, DP_SIZE = 8 };
+enum { DP_CX = 0, DP_CY, DP_C, DP_S, DP_SCALE, DP_RC, DP_RT, DP_E,
+       DP_SQE, DP_Q, DP_IQ, DP_IOPE2, DP_IOME2, DP_ZCI, DP_RC2, DP_RT2, DP_SIZE = 16 };   // second row: per-member constants of e, rc, rt
 enum { DPG_CX = 0, DPG_CY, DPG_PHI, DPG_SCALE, DPG_RC, DPG_RT, DPG_E };
 #define GL_DPIE_RMIN 0.0001
 // _sort_ra_rs (piemd.py:51-60): returns the sorted/floored radii and the selection pattern needed
@@ -715,10 +716,18 @@ GL_HD void dpie_prep(const T* raw, T* d, bool ellipse) {
     ellip_fwd(raw[3], raw[4], T(0.9999), phi, q, e);
     d[DP_C] = gl_cos(phi); d[DP_S] = gl_sin(phi); d[DP_E] = e;
     d[DP_CX] = raw[5]; d[DP_CY] = raw[6];
+    // constants of complex_deriv_dual (piemd.py:202-207) hoisted out of the pixel loop
+    d[DP_SQE] = gl_sqrt(e);
+    d[DP_Q] = q; d[DP_IQ] = T(1) / q;
+    d[DP_IOPE2] = T(1) / ((T(1) + e) * (T(1) + e));
+    d[DP_IOME2] = T(1) / ((T(1) - e) * (T(1) - e));
+    d[DP_ZCI] = -T(0.5) * (T(1) - e * e) / d[DP_SQE];
   } else {
     d[DP_C] = T(1); d[DP_S] = T(0); d[DP_E] = T(0);
     d[DP_CX] = raw[3]; d[DP_CY] = raw[4];
+    d[DP_SQE] = T(0); d[DP_Q] = T(1); d[DP_IQ] = T(1); d[DP_IOPE2] = T(1); d[DP_IOME2] = T(1); d[DP_ZCI] = T(0);
   }
+  d[DP_RC2] = rc * rc; d[DP_RT2] = rt * rt;
 }
 template <class T>
 GL_HD void dpie_prep_bwd(const T* raw, const T* d, const T* g, T* graw, bool ellipse) {
@@ -778,38 +787,40 @@ GL_HD void dpis_bwd(const T* d, const T* x, const T* y, const T* gax, const T* g
 }
 
 // complex_deriv_dual (piemd.py:201-255) on rotated coordinates; returns the unscaled (re, im).
+// Per-member constants (sqrt(e), q, 1/q, 1/(1+-e)^2, zci, rc^2, rt^2) come from the derived block;
+// the per-pixel work is 2 rsqrt, 1 rcp, 1 lg2 and one atan2.
+template <class T>
+GL_HD T gl_sqrt_pos(T x) { return x * gl_rsqrt_fast(x); }   // x > 0
 template <class T>
 struct DpieFw {
-  T sqe, q, ope2, ome2, zci, rem2, sc, st, a, b_, c_, d_, e_, f_, aa, bb, cc, dd, norm, aaa, bbb, norm2, zr_re, zr_im;
+  T sc, st, a, b_, c_, d_, e_, f_, aa, bb, cc, dd, inorm, aaa, bbb, inorm2, zr_re, zr_im;
 };
 template <class T>
-GL_HD void dpie_core_fwd(T x, T y, T rc, T rt, T e, DpieFw<T>& W, T& re, T& im) {
-  W.sqe = gl_sqrt(e);
-  W.q = (T(1) - e) / (T(1) + e);
-  W.ope2 = (T(1) + e) * (T(1) + e);
-  W.ome2 = (T(1) - e) * (T(1) - e);
-  W.rem2 = x * x / W.ope2 + y * y / W.ome2;
-  W.zci = -T(0.5) * (T(1) - e * e) / W.sqe;
-  W.sc = gl_sqrt(rc * rc + W.rem2);
-  W.st = gl_sqrt(rt * rt + W.rem2);
-  W.a = W.q * x;                                 // znum_rc_re
-  W.b_ = T(2) * W.sqe * W.sc - y / W.q;          // znum_rc_im
-  W.c_ = x;                                      // zden_rc_re
-  W.d_ = T(2) * rc * W.sqe - y;                  // zden_rc_im
-  W.e_ = T(2) * W.sqe * W.st - y / W.q;          // znum_rcut_im
-  W.f_ = T(2) * rt * W.sqe - y;                  // zden_rcut_im
-  W.aa = W.a * W.c_ - W.b_ * W.f_;
-  W.bb = W.a * W.f_ + W.b_ * W.c_;
-  W.cc = W.a * W.c_ - W.d_ * W.e_;
-  W.dd = W.a * W.d_ + W.c_ * W.e_;
-  W.norm = W.cc * W.cc + W.dd * W.dd;
-  W.aaa = (W.aa * W.cc + W.bb * W.dd) / W.norm;
-  W.bbb = (W.bb * W.cc - W.aa * W.dd) / W.norm;
-  W.norm2 = W.aaa * W.aaa + W.bbb * W.bbb;
-  W.zr_re = gl_log(gl_sqrt(W.norm2));
+GL_HD void dpie_core_fwd(const T* d, T x, T y, DpieFw<T>& W, T& re, T& im) {
+  const T sqe = d[DP_SQE], rc = d[DP_RC], rt = d[DP_RT];
+  const T rem2 = gl_fma(x * x, d[DP_IOPE2], y * y * d[DP_IOME2]);
+  W.sc = gl_sqrt_pos(d[DP_RC2] + rem2);
+  W.st = gl_sqrt_pos(d[DP_RT2] + rem2);
+  const T yq = y * d[DP_IQ];
+  W.a = d[DP_Q] * x;                               // znum_rc_re
+  W.b_ = gl_fma(T(2) * sqe, W.sc, -yq);            // znum_rc_im
+  W.c_ = x;                                        // zden_rc_re
+  W.d_ = gl_fma(T(2) * rc, sqe, -y);               // zden_rc_im
+  W.e_ = gl_fma(T(2) * sqe, W.st, -yq);            // znum_rcut_im
+  W.f_ = gl_fma(T(2) * rt, sqe, -y);               // zden_rcut_im
+  W.aa = gl_fma(W.a, W.c_, -(W.b_ * W.f_));
+  W.bb = gl_fma(W.a, W.f_, W.b_ * W.c_);
+  W.cc = gl_fma(W.a, W.c_, -(W.d_ * W.e_));
+  W.dd = gl_fma(W.a, W.d_, W.c_ * W.e_);
+  W.inorm = gl_div_fast(T(1), gl_fma(W.cc, W.cc, W.dd * W.dd));
+  W.aaa = gl_fma(W.aa, W.cc, W.bb * W.dd) * W.inorm;
+  W.bbb = gl_fma(W.bb, W.cc, -(W.aa * W.dd)) * W.inorm;
+  const T norm2 = gl_fma(W.aaa, W.aaa, W.bbb * W.bbb);
+  W.inorm2 = gl_div_fast(T(1), norm2);
+  W.zr_re = T(0.5 * GL_LN2) * gl_log2_fast(norm2);
   W.zr_im = gl_atan2(W.bbb, W.aaa);
-  re = -W.zci * W.zr_im;
-  im = W.zci * W.zr_re;
+  re = -d[DP_ZCI] * W.zr_im;
+  im = d[DP_ZCI] * W.zr_re;
 }
 template <class T, int NP>
 GL_HD void dpie_fwd(const T* d, const T* x, const T* y, T* ax, T* ay) {
@@ -817,67 +828,73 @@ GL_HD void dpie_fwd(const T* d, const T* x, const T* y, T* ax, T* ay) {
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
     T dx = x[j] - d[DP_CX], dy = y[j] - d[DP_CY];
-    T xr = dx * c + dy * s, yr = -dx * s + dy * c;
+    T xr = gl_fma(dx, c, dy * s), yr = gl_fma(dy, c, -(dx * s));
     DpieFw<T> W; T re, im;
-    dpie_core_fwd(xr, yr, d[DP_RC], d[DP_RT], d[DP_E], W, re, im);
-    ax[j] = scale * (re * c - im * s);
-    ay[j] = scale * (re * s + im * c);
+    dpie_core_fwd(d, xr, yr, W, re, im);
+    ax[j] = scale * gl_fma(re, c, -(im * s));
+    ay[j] = scale * gl_fma(re, s, im * c);
   }
 }
 template <class T, int NP>
 GL_HD void dpie_bwd(const T* d, const T* x, const T* y, const T* gax, const T* gay, T* g) {
-  T c = d[DP_C], s = d[DP_S], scale = d[DP_SCALE], rc = d[DP_RC], rt = d[DP_RT], e = d[DP_E];
+  const T c = d[DP_C], s = d[DP_S], scale = d[DP_SCALE], rc = d[DP_RC], rt = d[DP_RT], e = d[DP_E];
+  const T sqe = d[DP_SQE], q = d[DP_Q], iq = d[DP_IQ], iope2 = d[DP_IOPE2], iome2 = d[DP_IOME2], zci = d[DP_ZCI];
+  // d(constant)/de, applied per pixel to fold every e-dependence into the single dvar e
+  const T dsqe = T(0.5) / sqe;
+  const T dzci = T(0.5) * (T(1) - e * e) / (sqe * sqe) * dsqe + e / sqe;   // d zci / d e
+  const T dq = -T(2) / ((T(1) + e) * (T(1) + e));
+  const T diope2 = -T(2) * iope2 / (T(1) + e), diome2 = T(2) * iome2 / (T(1) - e);
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
     T dx = x[j] - d[DP_CX], dy = y[j] - d[DP_CY];
-    T xr = dx * c + dy * s, yr = -dx * s + dy * c;
+    T xr = gl_fma(dx, c, dy * s), yr = gl_fma(dy, c, -(dx * s));
     DpieFw<T> W; T re, im;
-    dpie_core_fwd(xr, yr, rc, rt, e, W, re, im);
-    T ux = re * c - im * s, uy = re * s + im * c;     // rotated back, unscaled
-    g[DPG_SCALE] += gax[j] * ux + gay[j] * uy;
+    dpie_core_fwd(d, xr, yr, W, re, im);
+    T ux = gl_fma(re, c, -(im * s)), uy = gl_fma(re, s, im * c);     // rotated back, unscaled
+    g[DPG_SCALE] += gl_fma(gax[j], ux, gay[j] * uy);
     T gux = gax[j] * scale, guy = gay[j] * scale;
-    g[DPG_PHI] += -gux * uy + guy * ux;
-    T gre = gux * c + guy * s, gim = -gux * s + guy * c;
+    g[DPG_PHI] += gl_fma(guy, ux, -(gux * uy));
+    T gre = gl_fma(gux, c, guy * s), gim = gl_fma(guy, c, -(gux * s));
     // re = -zci zr_im ; im = zci zr_re
-    T gzci = -gre * W.zr_im + gim * W.zr_re;
-    T gzr_im = -gre * W.zci, gzr_re = gim * W.zci;
+    T gzci = gl_fma(gim, W.zr_re, -(gre * W.zr_im));
+    T gzr_im = -gre * zci, gzr_re = gim * zci;
     // zr_re = 0.5 log(norm2), zr_im = atan2(bbb, aaa)
-    T gaaa = (gzr_re * W.aaa - gzr_im * W.bbb) / W.norm2;
-    T gbbb = (gzr_re * W.bbb + gzr_im * W.aaa) / W.norm2;
+    T gaaa = gl_fma(gzr_re, W.aaa, -(gzr_im * W.bbb)) * W.inorm2;
+    T gbbb = gl_fma(gzr_re, W.bbb, gzr_im * W.aaa) * W.inorm2;
     // aaa = (aa cc + bb dd)/norm, bbb = (bb cc - aa dd)/norm
-    T gaa = (gaaa * W.cc - gbbb * W.dd) / W.norm;
-    T gbb = (gaaa * W.dd + gbbb * W.cc) / W.norm;
-    T gnorm = -(gaaa * W.aaa + gbbb * W.bbb) / W.norm;
-    T gcc = (gaaa * W.aa + gbbb * W.bb) / W.norm + gnorm * T(2) * W.cc;
-    T gdd = (gaaa * W.bb - gbbb * W.aa) / W.norm + gnorm * T(2) * W.dd;
+    T gaa = gl_fma(gaaa, W.cc, -(gbbb * W.dd)) * W.inorm;
+    T gbb = gl_fma(gaaa, W.dd, gbbb * W.cc) * W.inorm;
+    T gnorm = -gl_fma(gaaa, W.aaa, gbbb * W.bbb) * W.inorm;
+    T gcc = gl_fma(gl_fma(gaaa, W.aa, gbbb * W.bb), W.inorm, gnorm * T(2) * W.cc);
+    T gdd = gl_fma(gl_fma(gaaa, W.bb, -(gbbb * W.aa)), W.inorm, gnorm * T(2) * W.dd);
     // aa = a c - b f ; bb = a f + b c ; cc = a c - d e ; dd = a d + c e
-    T ga = gaa * W.c_ + gbb * W.f_ + gcc * W.c_ + gdd * W.d_;
-    T gb = -gaa * W.f_ + gbb * W.c_;
-    T gc = gaa * W.a + gbb * W.b_ + gcc * W.a + gdd * W.e_;
-    T gd = -gcc * W.e_ + gdd * W.a;
-    T ge_ = -gcc * W.d_ + gdd * W.c_;
-    T gf = -gaa * W.b_ + gbb * W.a;
+    T ga = gl_fma(gaa + gcc, W.c_, gl_fma(gbb, W.f_, gdd * W.d_));
+    T gb = gl_fma(gbb, W.c_, -(gaa * W.f_));
+    T gc = gl_fma(gaa + gcc, W.a, gl_fma(gbb, W.b_, gdd * W.e_));
+    T gd = gl_fma(gdd, W.a, -(gcc * W.e_));
+    T ge_ = gl_fma(gdd, W.c_, -(gcc * W.d_));
+    T gf = gl_fma(gbb, W.a, -(gaa * W.b_));
     // a = q x ; b = 2 sqe sc - y/q ; c = x ; d = 2 rc sqe - y ; e = 2 sqe st - y/q ; f = 2 rt sqe - y
-    T gq = ga * xr + (gb + ge_) * yr / (W.q * W.q);
-    T gx = ga * W.q + gc;
-    T gy = -(gb + ge_) / W.q - gd - gf;
-    T gsqe = T(2) * (gb * W.sc + ge_ * W.st + gd * rc + gf * rt);
-    T gsc = gb * T(2) * W.sqe, gst = ge_ * T(2) * W.sqe;
-    g[DPG_RC] += gd * T(2) * W.sqe + gsc * rc / W.sc;
-    g[DPG_RT] += gf * T(2) * W.sqe + gst * rt / W.st;
-    T grem2 = gsc * T(0.5) / W.sc + gst * T(0.5) / W.st;
-    // rem2 = x^2/(1+e)^2 + y^2/(1-e)^2
-    gx += grem2 * T(2) * xr / W.ope2;
-    gy += grem2 * T(2) * yr / W.ome2;
-    T ge = grem2 * (-T(2) * xr * xr / (W.ope2 * (T(1) + e)) + T(2) * yr * yr / (W.ome2 * (T(1) - e)));
-    // zci = -0.5 (1 - e^2)/sqe ; sqe = sqrt(e) ; q = (1-e)/(1+e)
-    gsqe += gzci * T(0.5) * (T(1) - e * e) / (W.sqe * W.sqe);
-    ge += gzci * e / W.sqe;
-    ge += gsqe * T(0.5) / W.sqe;
-    ge += gq * (-T(2) / ((T(1) + e) * (T(1) + e)));
+    T gbe = gb + ge_;
+    T gq = gl_fma(ga, xr, gbe * yr * (iq * iq));
+    T gx = gl_fma(ga, q, gc);
+    T gy = -gl_fma(gbe, iq, gd + gf);
+    T gsqe = T(2) * gl_fma(gb, W.sc, gl_fma(ge_, W.st, gl_fma(gd, rc, gf * rt)));
+    T gsc = gb * T(2) * sqe, gst = ge_ * T(2) * sqe;
+    T isc = gl_div_fast(T(1), W.sc), ist = gl_div_fast(T(1), W.st);
+    g[DPG_RC] += gl_fma(gd * T(2), sqe, gsc * rc * isc);
+    g[DPG_RT] += gl_fma(gf * T(2), sqe, gst * rt * ist);
+    T grem2 = T(0.5) * gl_fma(gsc, isc, gst * ist);
+    // rem2 = x^2 iope2 + y^2 iome2
+    gx = gl_fma(grem2 * T(2) * xr, iope2, gx);
+    gy = gl_fma(grem2 * T(2) * yr, iome2, gy);
+    T ge = grem2 * gl_fma(xr * xr, diope2, yr * yr * diome2);
+    ge = gl_fma(gzci, dzci, ge);
+    ge = gl_fma(gsqe, dsqe, ge);
+    ge = gl_fma(gq, dq, ge);
     g[DPG_E] += ge;
-    g[DPG_PHI] += gx * yr - gy * xr;
-    T gdx = gx * c - gy * s, gdy = gx * s + gy * c;
+    g[DPG_PHI] += gl_fma(gx, yr, -(gy * xr));
+    T gdx = gl_fma(gx, c, -(gy * s)), gdy = gl_fma(gx, s, gy * c);
     g[DPG_CX] -= gdx; g[DPG_CY] -= gdy;
   }
 }

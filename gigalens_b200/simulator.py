@@ -287,13 +287,17 @@ class LensSimulator(LensSimulatorInterface):
     # -- reference API
     def simulate(self, params, no_deflection=False):
         """``tf/simulator.py:109-156``.  Returns ``(bs, n, n)`` (``(n, n)`` when bs == 1, like ``tf.squeeze``)."""
-        if no_deflection:
-            raise NotImplementedError("no_deflection is not wired through the C ABI yet")
         torch = self._torch
         mat = self._params_matrix(params)
         n = self.numPix
         img = torch.empty((self.bs, n, n), dtype=torch.float32, device=self.device)
-        _cabi.check(self._lib.gl_simulate(self._plan, mat.data_ptr(), img.data_ptr(), self._stream()), self._lib)
+        if no_deflection:
+            self.set_option("no_deflection", 1)
+        try:
+            _cabi.check(self._lib.gl_simulate(self._plan, mat.data_ptr(), img.data_ptr(), self._stream()), self._lib)
+        finally:
+            if no_deflection:
+                self.set_option("no_deflection", 0)
         return img.squeeze()
 
     def simulate_ss(self, params):
@@ -341,14 +345,20 @@ class LensSimulator(LensSimulatorInterface):
         """``tf/simulator.py:158-240``: solve the linear light amplitudes against ``observed_image``
         with weights ``1/err_map`` and return the best-fitting image ``(bs, n, n)`` (squeezed), or the
         amplitudes ``(bs, D)`` with ``return_coeffs``."""
-        if return_stacked or no_deflection:
-            raise NotImplementedError("return_stacked / no_deflection are not wired through the C ABI yet")
+        if return_stacked:
+            raise NotImplementedError("return_stacked is not wired through the C ABI yet")
         torch = self._torch
         self._install_lstsq_data(observed_image, err_map)
         mat = self._params_matrix(params)
         n = self.numPix
         img = torch.empty((self.bs, n, n), dtype=torch.float32, device=self.device)
         coef = torch.empty((self.bs, self.depth), dtype=torch.float32, device=self.device)
-        _cabi.check(self._lib.gl_lstsq_simulate(self._plan, mat.data_ptr(), img.data_ptr(), coef.data_ptr(), self._stream()),
-                    self._lib)
+        if no_deflection:
+            self.set_option("no_deflection", 1)
+        try:
+            _cabi.check(self._lib.gl_lstsq_simulate(self._plan, mat.data_ptr(), img.data_ptr(), coef.data_ptr(),
+                                                    self._stream()), self._lib)
+        finally:
+            if no_deflection:
+                self.set_option("no_deflection", 0)
         return coef if return_coeffs else img.squeeze()

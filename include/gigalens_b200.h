@@ -122,7 +122,10 @@ int gl_plan_set_likelihood(gl_plan* plan, const gl_like_config* like);
 /* prior / bijector leaves in z-column order (tf/model.py:76-87); d = n_leaves */
 int gl_plan_set_prior(gl_plan* plan, const gl_prior_leaf* leaves, int32_t n_leaves);
 /* Options.  "epl_batch_max" = 1: EPL series length from the batch maximum of f exactly like
- * tf/profiles/mass/epl.py:37 (default 0: per-sample length, identical to fp32 rounding). */
+ * tf/profiles/mass/epl.py:37 (default 0: per-sample length, identical to fp32 rounding).
+ * "no_deflection" = 1: evaluate source light at the image-plane position (simulate(..., no_deflection=True),
+ * tf/simulator.py:125-126).  "lstsq" = 1: the log-likelihood entry points use the linear-amplitude solve
+ * (BackwardProbModel, tf/model.py:242-273). */
 int gl_plan_set_option(gl_plan* plan, const char* name, int32_t value);
 void gl_plan_destroy(gl_plan* plan);
 const char* gl_last_error(void);

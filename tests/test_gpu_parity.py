@@ -270,3 +270,21 @@ def test_lstsq_simulate_and_backward_model(n_max, interpolate, with_lens_light):
     assert_parity(chi2[:, None], chi32[:, None], chi64[:, None], 1e-5, "red chi2", chi64p[:, None], axis=1)
     for k in range(z.shape[1]):
         assert_parity(dz[:, k], dz32[:, k], dz64[:, k], 1e-4, f"dz[{k}]", dz64p[:, k])
+
+
+def test_lstsq_chunked_passes_match_single_pass():
+    """The component stack is processed in sample chunks sized by a memory budget; results must not
+    depend on the chunking."""
+    bs = 7
+    wl = workloads.c3_workload(n_max=4)
+    pmod = BackwardProbModel(wl["prior"], wl["observed"], wl["background_rms"], wl["exp_time"])
+    z = torch.as_tensor(pmod.bij_inverse(wl["prior"].sample(bs, seed=8)), device="cuda")
+    outs = []
+    for chunk in (0, 3):
+        sim = LensSimulator(wl["phys_model"], wl["sim_config"], bs=bs)
+        if chunk:
+            sim.set_option("lstsq_chunk", chunk)
+        outs.append([t.cpu().numpy() for t in pmod.log_prob_and_grad(sim, z)])
+        outs[-1].append(sim.lstsq_simulate(pmod.bij_forward(sim, z), wl["observed"], pmod.err_map).cpu().numpy())
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
