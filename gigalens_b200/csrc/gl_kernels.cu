@@ -895,26 +895,33 @@ int gl_simulate_host(gl_plan* p, const float* params_host, float* image_host) {
   return 0;
 }
 
+// lstsq workspace, allocated on first use (sized by a memory budget; see "lstsq_chunk")
+static int gl_lstsq_alloc(gl_plan* p) {
+  if (p->d_comps) return 0;
+  const int D = p->prog.depth, npx = p->n * p->n;
+  if (D <= 0) return gl_fail("lstsq: the model has no linear light component");
+  const size_t per_sample = (size_t)D * p->npix * sizeof(float);
+  size_t cb = (size_t)6 << 30;
+  cb = cb / per_sample;
+  if (cb < 1) cb = 1;
+  if (p->lq_chunk_req > 0) cb = (size_t)p->lq_chunk_req;
+  if (cb > (size_t)p->bs) cb = p->bs;
+  p->lq_chunk = (int)cb;
+  GL_CUDA(cudaMalloc((void**)&p->d_R, cb * (size_t)D * npx * sizeof(float)));
+  GL_CUDA(cudaMalloc((void**)&p->d_gram, cb * (size_t)(D + 1) * (D + 1) * sizeof(float)));
+  GL_CUDA(cudaMalloc((void**)&p->d_coef, (size_t)p->bs * D * sizeof(float)));
+  GL_CUDA(cudaMalloc((void**)&p->d_ll, (size_t)p->bs * 2 * sizeof(float)));
+  GL_CUDA(cudaMalloc((void**)&p->d_comps, cb * per_sample));
+  return 0;
+}
+
 static int gl_lstsq_forward(gl_plan* p, const float* params, float* image, float* coeffs_out, float* loglike,
                             float* red_chi2, bool want_gimg, cudaStream_t st) {
   if (!p->has_like || !p->d_err) return gl_fail("lstsq: needs gl_plan_set_likelihood with observed image and error_map");
   const int D = p->prog.depth, npx = p->n * p->n;
   if (D <= 0) return gl_fail("lstsq: the model has no linear light component");
   if (D + 1 > 128 || D > 104) return gl_fail("lstsq: more than 104 linear components are not supported yet");
-  if (!p->d_comps) {
-    const size_t per_sample = (size_t)D * p->npix * sizeof(float);
-    size_t cb = (size_t)6 << 30;
-    cb = cb / per_sample;
-    if (cb < 1) cb = 1;
-    if (p->lq_chunk_req > 0) cb = (size_t)p->lq_chunk_req;
-    if (cb > (size_t)p->bs) cb = p->bs;
-    p->lq_chunk = (int)cb;
-    GL_CUDA(cudaMalloc((void**)&p->d_comps, cb * per_sample));
-    GL_CUDA(cudaMalloc((void**)&p->d_R, cb * (size_t)D * npx * sizeof(float)));
-    GL_CUDA(cudaMalloc((void**)&p->d_gram, cb * (size_t)(D + 1) * (D + 1) * sizeof(float)));
-    GL_CUDA(cudaMalloc((void**)&p->d_coef, (size_t)p->bs * D * sizeof(float)));
-    GL_CUDA(cudaMalloc((void**)&p->d_ll, (size_t)p->bs * 2 * sizeof(float)));
-  }
+  if (gl_lstsq_alloc(p)) return 1;
   if (gl_run_prep(p, params, st)) return 1;
   const size_t smem_der = (size_t)p->prog.der_total * sizeof(float);
   GL_FEAT_DISPATCH(p->feat_idx, {
@@ -950,6 +957,7 @@ static int gl_lstsq_forward(gl_plan* p, const float* params, float* image, float
 // log-like (+ gradient) of BackwardProbModel; shares the tail (k_sample_bwd) with the forward model.
 static int gl_lstsq_loglike_core(gl_plan* p, const float* params, float* loglike, float* red_chi2, float* dparams,
                                  const float* z, float* logp, float* dz, cudaStream_t st) {
+  if (gl_lstsq_alloc(p)) return 1;   // before taking workspace pointers
   float* ll = loglike ? loglike : p->d_ll;
   float* chi = red_chi2 ? red_chi2 : p->d_ll + p->bs;
   const bool grad = dparams != nullptr;
