@@ -85,6 +85,64 @@ GL_HD double gl_rsqrt_fast(double x) { return 1.0 / sqrt(x); }
 #define GL_LN2 0.69314718055994531
 #define GL_LOG2E 1.4426950408889634
 
+
+// ---------------------------------------------------------------------------------------------
+// lane types.  The per-pixel functions of the hot profiles (EPL, SHEAR, SERSIC) are templates over
+// a lane type V and the scalar type S = gl_scalar_t<V> of the per-sample constants:
+//   V = S = float / double : one pixel per lane slot (generic kernels, host harness)
+//   V = GlF2, S = float    : TWO pixels per lane slot; every +, *, fma is one packed FFMA2 / FMUL2 /
+//                            FADD2 (sm_100+), i.e. half the issue slots of the issue-bound kernels.
+// Per-pixel conditionals are written as selects (gl_where_*), so the same source serves both.
+// ---------------------------------------------------------------------------------------------
+struct GlF2 {
+  float x, y;
+  GL_HD GlF2() {}
+  GL_HD GlF2(float a) : x(a), y(a) {}
+  GL_HD GlF2(float a, float b) : x(a), y(b) {}
+};
+#if defined(__CUDA_ARCH__)
+GL_HD GlF2 operator+(GlF2 a, GlF2 b) { float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y)); return GlF2(r.x, r.y); }
+GL_HD GlF2 operator*(GlF2 a, GlF2 b) { float2 r = __fmul2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y)); return GlF2(r.x, r.y); }
+GL_HD GlF2 gl_fma(GlF2 a, GlF2 b, GlF2 c) {
+  float2 r = __ffma2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y), make_float2(c.x, c.y));
+  return GlF2(r.x, r.y);
+}
+#else
+GL_HD GlF2 operator+(GlF2 a, GlF2 b) { return GlF2(a.x + b.x, a.y + b.y); }
+GL_HD GlF2 operator*(GlF2 a, GlF2 b) { return GlF2(a.x * b.x, a.y * b.y); }
+GL_HD GlF2 gl_fma(GlF2 a, GlF2 b, GlF2 c) { return GlF2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+#endif
+GL_HD GlF2 operator-(GlF2 a) { return GlF2(-a.x, -a.y); }
+GL_HD GlF2 operator-(GlF2 a, GlF2 b) { return a + (-b); }
+GL_HD GlF2& operator+=(GlF2& a, GlF2 b) { a = a + b; return a; }
+GL_HD GlF2& operator-=(GlF2& a, GlF2 b) { a = a - b; return a; }
+GL_HD GlF2& operator*=(GlF2& a, GlF2 b) { a = a * b; return a; }
+GL_HD GlF2 gl_log2_fast(GlF2 a) { return GlF2(gl_log2_fast(a.x), gl_log2_fast(a.y)); }
+GL_HD GlF2 gl_exp2_fast(GlF2 a) { return GlF2(gl_exp2_fast(a.x), gl_exp2_fast(a.y)); }
+GL_HD GlF2 gl_rsqrt_fast(GlF2 a) { return GlF2(gl_rsqrt_fast(a.x), gl_rsqrt_fast(a.y)); }
+GL_HD GlF2 gl_div_fast(GlF2 a, GlF2 b) { return GlF2(gl_div_fast(a.x, b.x), gl_div_fast(a.y, b.y)); }
+GL_HD GlF2 gl_min(GlF2 a, GlF2 b) { return GlF2(fminf(a.x, b.x), fminf(a.y, b.y)); }
+GL_HD GlF2 gl_max(GlF2 a, GlF2 b) { return GlF2(fmaxf(a.x, b.x), fmaxf(a.y, b.y)); }
+// per-lane selects: (a > t ? vt : vf), (lo <= a <= hi ? vt : vf)
+GL_HD GlF2 gl_where_gt(GlF2 a, float t, GlF2 vt, GlF2 vf) { return GlF2(a.x > t ? vt.x : vf.x, a.y > t ? vt.y : vf.y); }
+GL_HD GlF2 gl_where_in(GlF2 a, float lo, float hi, GlF2 vt, GlF2 vf) {
+  return GlF2((a.x >= lo && a.x <= hi) ? vt.x : vf.x, (a.y >= lo && a.y <= hi) ? vt.y : vf.y);
+}
+GL_HD float gl_hsum(GlF2 a) { return a.x + a.y; }
+GL_HD float gl_where_gt(float a, float t, float vt, float vf) { return a > t ? vt : vf; }
+GL_HD double gl_where_gt(double a, double t, double vt, double vf) { return a > t ? vt : vf; }
+GL_HD float gl_where_in(float a, float lo, float hi, float vt, float vf) { return (a >= lo && a <= hi) ? vt : vf; }
+GL_HD double gl_where_in(double a, double lo, double hi, double vt, double vf) { return (a >= lo && a <= hi) ? vt : vf; }
+GL_HD float gl_hsum(float a) { return a; }
+GL_HD double gl_hsum(double a) { return a; }
+template <class V> struct gl_scalar_of { typedef V type; };
+template <> struct gl_scalar_of<GlF2> { typedef float type; };
+template <class V> struct gl_lanes_of { enum { value = 1 }; };
+template <> struct gl_lanes_of<GlF2> { enum { value = 2 }; };
+GL_HD float gl_lane(float a, int) { return a; }
+GL_HD double gl_lane(double a, int) { return a; }
+GL_HD float gl_lane(GlF2 a, int i) { return i ? a.y : a.x; }
+
 // Profile type ids (same values as include/gigalens_b200.h).
 enum {
   GLT_EPL = 1, GLT_SHEAR = 2, GLT_SIE = 3, GLT_SIS = 4, GLT_NFW = 5, GLT_NFW_ELLIPSE = 6, GLT_DPIS = 7, GLT_DPIE = 8,
