@@ -225,6 +225,12 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_fwd(GlProgram P, int n
 struct DevFlush {
   float* s_acc;   // this warp's accumulator row in shared memory
   int lane;
+  __device__ __forceinline__ void operator()(const GlF2* acc2, int n, int off) {   // two-pixel lanes: fold first
+    float acc[GL_MAX_DVARS];
+#pragma unroll
+    for (int k = 0; k < GL_MAX_DVARS; ++k) acc[k] = acc2[k].x + acc2[k].y;
+    (*this)(acc, n, off);
+  }
   __device__ __forceinline__ void operator()(const float* acc, int n, int off) {
     const unsigned FULL = 0xffffffffu;
     const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
@@ -284,6 +290,98 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_bwd(GlProgram P, int n
     float s = 0.f;
     for (int w = 0; w < nw; ++w) s += s_acc[w * P.g_total + k];
     out[k] = s;
+  }
+}
+
+// Two-pixel packed variants (lane type GlF2): each thread owns PPT/2 pairs of ADJACENT pixels, every
+// per-pixel +, *, fma issues as one FFMA2 / FMUL2 / FADD2.  Used when the program only contains
+// profiles whose arithmetic is written over the lane type (feature set FS0) and npix is even.
+template <int PPT, unsigned F>
+__global__ void __launch_bounds__(GLK_THREADS) k_raytrace_fwd_p(GlProgram P, int npix, const float* __restrict__ grid_x,
+                                                                const float* __restrict__ grid_y,
+                                                                const unsigned char* __restrict__ ss_mask,
+                                                                const float* __restrict__ derived, int no_deflection,
+                                                                float* __restrict__ ss_img) {
+  extern __shared__ __align__(16) float s_der[];
+  const int b = blockIdx.y;
+  const float* dsrc = derived + (size_t)b * P.der_total;
+  for (int i = threadIdx.x; i < P.der_total; i += blockDim.x) s_der[i] = dsrc[i];
+  __syncthreads();
+  constexpr int NV = PPT / 2;
+  const int npair = npix >> 1;
+  const int per_batch = GLK_THREADS * NV;
+  const int nbatch = (npair + per_batch - 1) / per_batch;
+  float2* dst = reinterpret_cast<float2*>(ss_img + (size_t)b * npix);
+  const float2* gx2 = reinterpret_cast<const float2*>(grid_x);
+  const float2* gy2 = reinterpret_cast<const float2*>(grid_y);
+  for (int batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
+    GlF2 x[NV], y[NV], v[NV];
+    int pr[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      pr[j] = batch * per_batch + j * GLK_THREADS + threadIdx.x;
+      const int p = pr[j] < npair ? pr[j] : 0;
+      const float2 a = __ldg(gx2 + p), c = __ldg(gy2 + p);
+      x[j] = GlF2(a.x, a.y); y[j] = GlF2(c.x, c.y);
+    }
+    gl_pix_image<GlF2, NV, F>(P, s_der, x, y, no_deflection != 0, v);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      if (pr[j] < npair) {
+        float o0 = v[j].x, o1 = v[j].y;
+        if (o0 != o0) o0 = 0.f;
+        if (o1 != o1) o1 = 0.f;
+        if (ss_mask) { if (!ss_mask[2 * pr[j]]) o0 = 0.f; if (!ss_mask[2 * pr[j] + 1]) o1 = 0.f; }
+        dst[pr[j]] = make_float2(o0, o1);
+      }
+    }
+  }
+}
+
+template <int PPT, unsigned F>
+__global__ void __launch_bounds__(GLK_THREADS) k_raytrace_bwd_p(GlProgram P, int npix, const float* __restrict__ grid_x,
+                                                                const float* __restrict__ grid_y,
+                                                                const unsigned char* __restrict__ ss_mask,
+                                                                const float* __restrict__ derived, int no_deflection,
+                                                                const float* __restrict__ gss, float* __restrict__ gpart) {
+  extern __shared__ __align__(16) float smem[];
+  float* s_der = smem;
+  float* s_acc = smem + P.der_total;
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = GLK_THREADS / 32;
+  const float* dsrc = derived + (size_t)b * P.der_total;
+  for (int i = threadIdx.x; i < P.der_total; i += blockDim.x) s_der[i] = dsrc[i];
+  for (int i = threadIdx.x; i < nw * P.g_total; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  DevFlush flush{s_acc + warp * P.g_total, lane};
+  constexpr int NV = PPT / 2;
+  const int npair = npix >> 1;
+  const int per_batch = GLK_THREADS * NV;
+  const int nbatch = (npair + per_batch - 1) / per_batch;
+  const float2* gsrc = reinterpret_cast<const float2*>(gss + (size_t)b * npix);
+  const float2* gx2 = reinterpret_cast<const float2*>(grid_x);
+  const float2* gy2 = reinterpret_cast<const float2*>(grid_y);
+  for (int batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
+    GlF2 x[NV], y[NV], gs[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int pr = batch * per_batch + j * GLK_THREADS + threadIdx.x;
+      const bool in = pr < npair;
+      const int p = in ? pr : 0;
+      const float2 a = __ldg(gx2 + p), c = __ldg(gy2 + p);
+      x[j] = GlF2(a.x, a.y); y[j] = GlF2(c.x, c.y);
+      float2 gv = in ? __ldg(gsrc + p) : make_float2(0.f, 0.f);
+      if (ss_mask && in) { if (!ss_mask[2 * p]) gv.x = 0.f; if (!ss_mask[2 * p + 1]) gv.y = 0.f; }
+      gs[j] = GlF2(gv.x, gv.y);
+    }
+    gl_pix_image_bwd<GlF2, NV, F>(P, s_der, x, y, gs, no_deflection != 0, flush);
+  }
+  __syncthreads();
+  float* out = gpart + ((size_t)b * gridDim.x + blockIdx.x) * P.g_total;
+  for (int k = threadIdx.x; k < P.g_total; k += blockDim.x) {
+    float s2 = 0.f;
+    for (int w = 0; w < nw; ++w) s2 += s_acc[w * P.g_total + k];
+    out[k] = s2;
   }
 }
 
@@ -370,6 +468,7 @@ struct gl_plan {
   // lstsq workspace (allocated on first use)
   int lstsq = 0;
   int no_deflection = 0;
+  int use_packed = 1;
   int lq_chunk = 0;
   int lq_chunk_req = 0;
   float* d_comps = nullptr; float* d_R = nullptr; float* d_gram = nullptr; float* d_coef = nullptr; float* d_w = nullptr;
@@ -622,6 +721,7 @@ int gl_plan_set_option(gl_plan* p, const char* name, int32_t value) {
   if (!strcmp(name, "epl_batch_max")) { p->epl_batch_max = value; return 0; }
   if (!strcmp(name, "lstsq")) { p->lstsq = value; return 0; }
   if (!strcmp(name, "no_deflection")) { p->no_deflection = value; return 0; }
+  if (!strcmp(name, "packed_math")) { p->use_packed = value; return 0; }   // 0: scalar-lane kernels (A/B testing)
   if (!strcmp(name, "lstsq_chunk")) {   // samples per pass of the lstsq component stack (0 = size by memory budget)
     if (p->d_comps) return gl_fail("gl_plan_set_option: lstsq_chunk must be set before the first lstsq call");
     p->lq_chunk_req = value; return 0;
@@ -707,6 +807,13 @@ static int gl_run_prep(gl_plan* p, const float* params, cudaStream_t st) {
 static int gl_run_raytrace_fwd(gl_plan* p, float* ss_out, int no_deflection, cudaStream_t st) {
   dim3 grid(p->chunks, p->bs);
   const size_t smem = (size_t)p->prog.der_total * sizeof(float);
+  if (p->feat_idx == 0 && (p->npix % 2) == 0 && p->use_packed) {
+    if (smem > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_fwd_p<4, GL_FS0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_raytrace_fwd_p<4, GL_FS0><<<grid, GLK_THREADS, smem, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,
+                                                                 p->d_derived, no_deflection, ss_out);
+    GL_LAUNCH_CHECK("k_raytrace_fwd_p");
+    return 0;
+  }
   GL_FEAT_DISPATCH(p->feat_idx, {
     if (smem > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_fwd<4, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_raytrace_fwd<4, F><<<grid, GLK_THREADS, smem, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask, p->d_derived,
@@ -719,6 +826,13 @@ static int gl_run_raytrace_fwd(gl_plan* p, float* ss_out, int no_deflection, cud
 static int gl_run_raytrace_bwd(gl_plan* p, const float* gss, int no_deflection, cudaStream_t st) {
   dim3 grid(p->chunks, p->bs);
   const size_t smem = (size_t)(p->prog.der_total + (GLK_THREADS / 32) * p->prog.g_total) * sizeof(float);
+  if (p->feat_idx == 0 && (p->npix % 2) == 0 && p->use_packed) {
+    if (smem > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_bwd_p<4, GL_FS0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_raytrace_bwd_p<4, GL_FS0><<<grid, GLK_THREADS, smem, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,
+                                                                 p->d_derived, no_deflection, gss, p->d_gpart);
+    GL_LAUNCH_CHECK("k_raytrace_bwd_p");
+    return 0;
+  }
   GL_FEAT_DISPATCH(p->feat_idx, {
     if (smem > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_bwd<4, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_raytrace_bwd<4, F><<<grid, GLK_THREADS, smem, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask, p->d_derived,
@@ -930,7 +1044,7 @@ static int gl_lstsq_forward(gl_plan* p, const float* params, float* image, float
   const int nt = (D + 1 + 3) / 4;
   const size_t smem_gram = (size_t)GLL_PT * nt * 4 * sizeof(float);
   const int npair = ((D + 1) & ~1) / 2;
-  const size_t smem_solve = (size_t)(2 * D * D + 2 * (npair + 1)) * sizeof(double) + (size_t)(2 * (npair + 1) + 2) * sizeof(int) + 4 * sizeof(double);
+  const size_t smem_solve = (size_t)(2 * D * (D | 1) + 2 * (npair + 1)) * sizeof(double) + (size_t)(2 * (npair + 1) + 2) * sizeof(int) + 4 * sizeof(double);
   if (smem_solve > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_pinv_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve));
   for (int b0 = 0; b0 < p->bs; b0 += p->lq_chunk) {
     const int nb = (p->bs - b0 < p->lq_chunk) ? p->bs - b0 : p->lq_chunk;
@@ -943,7 +1057,7 @@ static int gl_lstsq_forward(gl_plan* p, const float* params, float* image, float
     if (gl_run_conv_fwd(p, p->d_comps, 1.f, p->d_R, false, nullptr, st, nb * D)) return 1;
     k_gram<<<nb, GLL_THREADS, smem_gram, st>>>(D, npx, p->d_R, p->d_w, p->d_obs, p->d_gram);
     GL_LAUNCH_CHECK("k_gram");
-    k_pinv_solve<<<nb, 128, smem_solve, st>>>(D, p->d_gram, 1e-6, 30, p->d_coef + (size_t)b0 * D);
+    k_pinv_solve<<<nb, 128, smem_solve, st>>>(D, p->d_gram, 1e-6, 16, p->d_coef + (size_t)b0 * D);
     GL_LAUNCH_CHECK("k_pinv_solve");
     k_lstsq_image<<<nb, GLL_THREADS, (size_t)D * sizeof(float), st>>>(
         D, npx, p->d_R, p->d_coef + (size_t)b0 * D, p->d_obs, p->d_err, image ? image + (size_t)b0 * npx : nullptr,

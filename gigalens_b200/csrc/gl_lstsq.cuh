@@ -129,10 +129,11 @@ __global__ void __launch_bounds__(GLL_THREADS) k_gram(int D, int npx, const floa
 __global__ void __launch_bounds__(128) k_pinv_solve(int D, const float* __restrict__ gram, double rcond, int max_sweeps,
                                                     float* __restrict__ coeffs) {
   extern __shared__ __align__(16) double s_d[];
-  double* A = s_d;                 // [D][D]
-  double* V = A + D * D;           // [D][D]
-  double* cs = V + D * D;          // [m/2][2] rotation (c, s) per pair
-  int* pq = reinterpret_cast<int*>(cs + 2 * ((D + 1) / 2 + 1));   // [m/2][2]
+  const int LD = D | 1;            // odd leading dimension: column walks (stride LD doubles) hit distinct banks
+  double* A = s_d;                 // [D][LD]
+  double* V = A + D * LD;          // [D][LD]
+  double* cs = V + D * LD;         // [m/2 + 1][2] rotation (c, s) per pair; reused for y at the end
+  int* pq = reinterpret_cast<int*>(cs + 2 * ((D + 1) / 2 + 1));   // [m/2 + 1][2]
   double* red = reinterpret_cast<double*>(pq + 2 * ((D + 1) / 2 + 1) + 2);   // [4]
   const int b = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
   const int Dx = D + 1;
@@ -140,25 +141,26 @@ __global__ void __launch_bounds__(128) k_pinv_solve(int D, const float* __restri
   for (int e = tid; e < D * D; e += nthr) {
     const int i = e / D, j = e - i * D;
     // symmetrise (the two triangles of the fp32 Gram matrix can differ by rounding)
-    A[e] = 0.5 * ((double)G[(size_t)i * Dx + j] + (double)G[(size_t)j * Dx + i]);
-    V[e] = (i == j) ? 1.0 : 0.0;
+    A[i * LD + j] = 0.5 * ((double)G[(size_t)i * Dx + j] + (double)G[(size_t)j * Dx + i]);
+    V[i * LD + j] = (i == j) ? 1.0 : 0.0;
   }
   __syncthreads();
   const int m = (D + 1) & ~1, npair = m / 2;
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
-    // convergence: off-diagonal mass relative to the diagonal
+    // convergence: off-diagonal mass relative to the diagonal (1e-11 in norm: eigenvalues are then
+    // converged far below the 1e-6 rcond cut and below fp32 resolution of the result)
     if (tid < 32) {
       double off = 0.0, dg = 0.0;
       for (int e = tid; e < D * D; e += 32) {
         const int i = e / D, j = e - i * D;
-        const double v = A[e] * A[e];
+        const double v = A[i * LD + j] * A[i * LD + j];
         if (i == j) dg += v; else off += v;
       }
       for (int o = 16; o > 0; o >>= 1) { off += __shfl_xor_sync(0xffffffffu, off, o); dg += __shfl_xor_sync(0xffffffffu, dg, o); }
       if (tid == 0) { red[0] = off; red[1] = dg; }
     }
     __syncthreads();
-    if (red[0] <= 1e-30 * red[1]) break;
+    if (red[0] <= 1e-22 * red[1]) break;
     for (int round = 0; round < m - 1; ++round) {
       if (tid < npair) {
         int p, q;
@@ -167,9 +169,9 @@ __global__ void __launch_bounds__(128) k_pinv_solve(int D, const float* __restri
         if (p > q) { const int t = p; p = q; q = t; }
         double c = 1.0, s = 0.0;
         if (q < D) {
-          const double apq = A[p * D + q];
+          const double apq = A[p * LD + q];
           if (fabs(apq) > 1e-300) {
-            const double tau = (A[q * D + q] - A[p * D + p]) / (2.0 * apq);
+            const double tau = (A[q * LD + q] - A[p * LD + p]) / (2.0 * apq);
             const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
             c = 1.0 / sqrt(1.0 + t * t);
             s = t * c;
@@ -179,16 +181,16 @@ __global__ void __launch_bounds__(128) k_pinv_solve(int D, const float* __restri
         pq[2 * tid] = p; pq[2 * tid + 1] = q;
       }
       __syncthreads();
-      // columns: A <- A J, V <- V J
+      // columns: A <- A J, V <- V J   (k fastest across threads: stride LD, conflict-free)
       for (int e = tid; e < npair * D; e += nthr) {
         const int pr = e / D, k = e - pr * D;
         const int p = pq[2 * pr], q = pq[2 * pr + 1];
         if (q >= D) continue;
         const double c = cs[2 * pr], s = cs[2 * pr + 1];
-        const double akp = A[k * D + p], akq = A[k * D + q];
-        A[k * D + p] = c * akp - s * akq; A[k * D + q] = s * akp + c * akq;
-        const double vkp = V[k * D + p], vkq = V[k * D + q];
-        V[k * D + p] = c * vkp - s * vkq; V[k * D + q] = s * vkp + c * vkq;
+        const double akp = A[k * LD + p], akq = A[k * LD + q];
+        A[k * LD + p] = c * akp - s * akq; A[k * LD + q] = s * akp + c * akq;
+        const double vkp = V[k * LD + p], vkq = V[k * LD + q];
+        V[k * LD + p] = c * vkp - s * vkq; V[k * LD + q] = s * vkp + c * vkq;
       }
       __syncthreads();
       // rows: A <- J^T A
@@ -197,33 +199,32 @@ __global__ void __launch_bounds__(128) k_pinv_solve(int D, const float* __restri
         const int p = pq[2 * pr], q = pq[2 * pr + 1];
         if (q >= D) continue;
         const double c = cs[2 * pr], s = cs[2 * pr + 1];
-        const double apk = A[p * D + k], aqk = A[q * D + k];
-        A[p * D + k] = c * apk - s * aqk; A[q * D + k] = s * apk + c * aqk;
+        const double apk = A[p * LD + k], aqk = A[q * LD + k];
+        A[p * LD + k] = c * apk - s * aqk; A[q * LD + k] = s * apk + c * aqk;
       }
       __syncthreads();
     }
   }
   __syncthreads();
   // lambda_i = A_ii; y = V^T h; coeffs = V (y / lambda) over kept eigenvalues
-  double* y = cs;   // reuse: needs D doubles -> cs has only ~D+2; use red-adjacent space carefully
-  // (cs holds 2*(npair+1) >= D + 2 doubles, enough for D)
+  double* y = cs;   // cs holds 2*(npair+1) >= D + 2 doubles
   if (tid == 0) {
     double lmax = 0.0;
-    for (int i = 0; i < D; ++i) lmax = fmax(lmax, fabs(A[i * D + i]));
+    for (int i = 0; i < D; ++i) lmax = fmax(lmax, fabs(A[i * LD + i]));
     red[2] = lmax;
   }
   __syncthreads();
   const double cut = rcond * red[2];
   for (int i = tid; i < D; i += nthr) {
     double acc = 0.0;
-    for (int k = 0; k < D; ++k) acc += V[k * D + i] * (double)G[(size_t)k * Dx + D];
-    const double lam = A[i * D + i];
+    for (int k = 0; k < D; ++k) acc += V[k * LD + i] * (double)G[(size_t)k * Dx + D];
+    const double lam = A[i * LD + i];
     y[i] = (fabs(lam) > cut) ? acc / lam : 0.0;
   }
   __syncthreads();
   for (int k = tid; k < D; k += nthr) {
     double acc = 0.0;
-    for (int i = 0; i < D; ++i) acc += V[k * D + i] * y[i];
+    for (int i = 0; i < D; ++i) acc += V[k * LD + i] * y[i];
     coeffs[(size_t)b * D + k] = (float)acc;
   }
 }

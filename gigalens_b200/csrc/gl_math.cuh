@@ -297,41 +297,40 @@ GL_HD void epl_prep_bwd(const T* raw, const T* d, const T* g, T* graw) {
 
 // Shared per-pixel geometry of the EPL forward / adjoint.  R = clip(sqrt(R2), 1e-10, 1e10) enters
 // only through log2(R2) (prefactor) and 1/sqrt(R2) (cos/sin of the polar angle), so no sqrt is taken.
-template <class T>
+// V is the lane type (float, double, or the two-pixel pack GlF2), S its scalar type.
+template <class V>
 struct EplGeom {
-  T xr, yr, qx, R2, ir, l2r2, Cs, Ss, wr, wi;   // ir = 1/R0 (0 when R0 == 0), l2r2 = log2(clamped R^2)
+  V xr, yr, qx, R2, ir, l2r2, Cs, Ss, wr, wi;   // ir = 1/R0 (0 when R0 == 0), l2r2 = log2(clamped R^2)
 };
-template <class T>
-GL_HD void epl_geom(const T* d, T x, T y, EplGeom<T>& G) {
-  T dx = x - d[EPL_CX], dy = y - d[EPL_CY];
-  T c = d[EPL_C], s = d[EPL_S];
+template <class V, class S>
+GL_HD void epl_geom(const S* d, V x, V y, EplGeom<V>& G) {
+  V dx = x - V(d[EPL_CX]), dy = y - V(d[EPL_CY]);
+  V c = V(d[EPL_C]), s = V(d[EPL_S]);
   G.xr = gl_fma(dx, c, dy * s);
   G.yr = gl_fma(dy, c, -(dx * s));
-  G.qx = d[EPL_Q] * G.xr;
+  G.qx = V(d[EPL_Q]) * G.xr;
   G.R2 = gl_fma(G.qx, G.qx, G.yr * G.yr);
-  if (G.R2 > T(0)) {
-    G.ir = gl_rsqrt_fast(G.R2);
-    G.Cs = G.qx * G.ir; G.Ss = G.yr * G.ir;   // cos/sin of atan2(yr, q xr)
-  } else {
-    G.ir = T(0); G.Cs = T(1); G.Ss = T(0);    // atan2(0, 0) = 0
-  }
-  G.l2r2 = gl_log2_fast(gl_min(gl_max(G.R2, T(1e-20)), T(1e20)));
+  G.ir = gl_where_gt(G.R2, S(0), gl_rsqrt_fast(G.R2), V(S(0)));
+  G.Cs = gl_where_gt(G.R2, S(0), G.qx * G.ir, V(S(1)));   // cos/sin of atan2(yr, q xr); atan2(0,0) = 0
+  G.Ss = G.yr * G.ir;
+  G.l2r2 = gl_log2_fast(gl_min(gl_max(G.R2, V(S(1e-20))), V(S(1e20))));
   G.wr = gl_fma(G.Cs, G.Cs, -(G.Ss * G.Ss));
-  G.wi = T(2) * G.Cs * G.Ss;
+  G.wi = V(S(2)) * G.Cs * G.Ss;
 }
 
-template <class T, int NP>
-GL_HD void epl_fwd(const T* d, int ts, const T* x, const T* y, T* ax, T* ay) {
-  EplGeom<T> G[NP];
-  T Pr[NP], Pi[NP];
+template <class V, int NP>
+GL_HD void epl_fwd(const typename gl_scalar_of<V>::type* d, int ts, const V* x, const V* y, V* ax, V* ay) {
+  typedef typename gl_scalar_of<V>::type S;
+  EplGeom<V> G[NP];
+  V Pr[NP], Pi[NP];
   const int N = (int)d[EPL_N];
-  const T* A = d + EPL_TAB;
+  const S* A = d + EPL_TAB;
   (void)ts;
 #pragma unroll
-  for (int j = 0; j < NP; ++j) { epl_geom(d, x[j], y[j], G[j]); Pr[j] = A[N]; Pi[j] = T(0); }
+  for (int j = 0; j < NP; ++j) { epl_geom<V, S>(d, x[j], y[j], G[j]); Pr[j] = V(A[N]); Pi[j] = V(S(0)); }
   bool done = false;
 #ifdef GL_HAVE_F32X2
-  if constexpr (sizeof(T) == 4 && (NP % 2) == 0) {
+  if constexpr (sizeof(V) == 4 && (NP % 2) == 0) {   // scalar float lanes: pack pixel pairs for the series only
     GlC2 P2[NP / 2]; float2 wr2[NP / 2], wi2[NP / 2];
 #pragma unroll
     for (int h = 0; h < NP / 2; ++h) {
@@ -352,41 +351,42 @@ GL_HD void epl_fwd(const T* d, int ts, const T* x, const T* y, T* ax, T* ay) {
 #endif
   if (!done)
   for (int n = N - 1; n >= 0; --n) {
-    T a = A[n];
+    const V a = V(A[n]);
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
-      T pr = gl_fma(Pr[j], G[j].wr, gl_fma(-Pi[j], G[j].wi, a));
-      T pi = gl_fma(Pr[j], G[j].wi, Pi[j] * G[j].wr);
+      V pr = gl_fma(Pr[j], G[j].wr, gl_fma(-Pi[j], G[j].wi, a));
+      V pi = gl_fma(Pr[j], G[j].wi, Pi[j] * G[j].wr);
       Pr[j] = pr; Pi[j] = pi;
     }
   }
-  T c = d[EPL_C], s = d[EPL_S], l2b = d[EPL_LOG2B], tm1 = d[EPL_T] - T(1), pref0 = d[EPL_PREF0];
+  const V c = V(d[EPL_C]), s = V(d[EPL_S]), l2b = V(d[EPL_LOG2B]), tm1 = V(d[EPL_T] - S(1)), pref0 = V(d[EPL_PREF0]);
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
-    T fx = gl_fma(G[j].Cs, Pr[j], -(G[j].Ss * Pi[j]));
-    T fy = gl_fma(G[j].Cs, Pi[j], G[j].Ss * Pr[j]);
-    T pref = pref0 * gl_exp2_fast(tm1 * gl_fma(T(-0.5), G[j].l2r2, l2b));   // (b/R)^(t-1)
-    fx *= pref; fy *= pref;
+    V fx = gl_fma(G[j].Cs, Pr[j], -(G[j].Ss * Pi[j]));
+    V fy = gl_fma(G[j].Cs, Pi[j], G[j].Ss * Pr[j]);
+    V pref = pref0 * gl_exp2_fast(tm1 * gl_fma(V(S(-0.5)), G[j].l2r2, l2b));   // (b/R)^(t-1)
+    fx = fx * pref; fy = fy * pref;
     ax[j] = gl_fma(fx, c, -(fy * s));
     ay[j] = gl_fma(fx, s, fy * c);
   }
 }
 
-// Adjoint: (gax, gay) is the cotangent of the deflection; accumulates into g[EPLG_*].
-template <class T, int NP>
-GL_HD void epl_bwd(const T* d, int ts, const T* x, const T* y, const T* gax, const T* gay, T* g) {
-  EplGeom<T> G[NP];
-  T Pr[NP], Pi[NP], Fr[NP], Fi[NP], Tr[NP], Ti[NP];
+// Adjoint: (gax, gay) is the cotangent of the deflection; accumulates into g[EPLG_*] (lane-wise).
+template <class V, int NP>
+GL_HD void epl_bwd(const typename gl_scalar_of<V>::type* d, int ts, const V* x, const V* y, const V* gax, const V* gay, V* g) {
+  typedef typename gl_scalar_of<V>::type S;
+  EplGeom<V> G[NP];
+  V Pr[NP], Pi[NP], Fr[NP], Fi[NP], Tr[NP], Ti[NP];
   const int N = (int)d[EPL_N];
-  const T* A = d + EPL_TAB; const T* Af = A + ts; const T* At = Af + ts;
+  const S* A = d + EPL_TAB; const S* Af = A + ts; const S* At = Af + ts;
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
-    epl_geom(d, x[j], y[j], G[j]);
-    Pr[j] = A[N]; Pi[j] = T(0); Fr[j] = Af[N]; Fi[j] = T(0); Tr[j] = At[N]; Ti[j] = T(0);
+    epl_geom<V, S>(d, x[j], y[j], G[j]);
+    Pr[j] = V(A[N]); Pi[j] = V(S(0)); Fr[j] = V(Af[N]); Fi[j] = V(S(0)); Tr[j] = V(At[N]); Ti[j] = V(S(0));
   }
   bool done = false;
 #ifdef GL_HAVE_F32X2
-  if constexpr (sizeof(T) == 4 && (NP % 2) == 0) {
+  if constexpr (sizeof(V) == 4 && (NP % 2) == 0) {
     GlC2 P2[NP / 2], F2[NP / 2], T2[NP / 2]; float2 wr2[NP / 2], wi2[NP / 2];
 #pragma unroll
     for (int h = 0; h < NP / 2; ++h) {
@@ -415,55 +415,56 @@ GL_HD void epl_bwd(const T* d, int ts, const T* x, const T* y, const T* gax, con
 #endif
   if (!done)
   for (int n = N - 1; n >= 0; --n) {
-    T a = A[n], af = Af[n], at = At[n];
+    const V a = V(A[n]), af = V(Af[n]), at = V(At[n]);
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
-      T wr = G[j].wr, wi = G[j].wi;
-      T pr = gl_fma(Pr[j], wr, gl_fma(-Pi[j], wi, a)), pi = gl_fma(Pr[j], wi, Pi[j] * wr);
-      T fr = gl_fma(Fr[j], wr, gl_fma(-Fi[j], wi, af)), fi = gl_fma(Fr[j], wi, Fi[j] * wr);
-      T tr = gl_fma(Tr[j], wr, gl_fma(-Ti[j], wi, at)), ti = gl_fma(Tr[j], wi, Ti[j] * wr);
+      V wr = G[j].wr, wi = G[j].wi;
+      V pr = gl_fma(Pr[j], wr, gl_fma(-Pi[j], wi, a)), pi = gl_fma(Pr[j], wi, Pi[j] * wr);
+      V fr = gl_fma(Fr[j], wr, gl_fma(-Fi[j], wi, af)), fi = gl_fma(Fr[j], wi, Fi[j] * wr);
+      V tr = gl_fma(Tr[j], wr, gl_fma(-Ti[j], wi, at)), ti = gl_fma(Tr[j], wi, Ti[j] * wr);
       Pr[j] = pr; Pi[j] = pi; Fr[j] = fr; Fi[j] = fi; Tr[j] = tr; Ti[j] = ti;
     }
   }
-  T c = d[EPL_C], s = d[EPL_S], q = d[EPL_Q], l2b = d[EPL_LOG2B], tm1 = d[EPL_T] - T(1), pref0 = d[EPL_PREF0], f = d[EPL_F];
-  T tm1_over_b = tm1 / d[EPL_B];
+  const V c = V(d[EPL_C]), s = V(d[EPL_S]), q = V(d[EPL_Q]), l2b = V(d[EPL_LOG2B]), tm1 = V(d[EPL_T] - S(1));
+  const V pref0 = V(d[EPL_PREF0]), f2 = V(S(2) * d[EPL_F]);
+  const V tm1_over_b = V((d[EPL_T] - S(1)) / d[EPL_B]);
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
-    const EplGeom<T>& E = G[j];
+    const EplGeom<V>& E = G[j];
     // forward values
-    T fx = gl_fma(E.Cs, Pr[j], -(E.Ss * Pi[j])), fy = gl_fma(E.Cs, Pi[j], E.Ss * Pr[j]);      // u P
-    T l2br = gl_fma(T(-0.5), E.l2r2, l2b);            // log2(b/R)
-    T pw = gl_exp2_fast(tm1 * l2br);
-    T pref = pref0 * pw;
-    T Fx = fx * pref, Fy = fy * pref;
-    T ax = gl_fma(Fx, c, -(Fy * s)), ay = gl_fma(Fx, s, Fy * c);
+    V fx = gl_fma(E.Cs, Pr[j], -(E.Ss * Pi[j])), fy = gl_fma(E.Cs, Pi[j], E.Ss * Pr[j]);      // u P
+    V l2br = gl_fma(V(S(-0.5)), E.l2r2, l2b);            // log2(b/R)
+    V pw = gl_exp2_fast(tm1 * l2br);
+    V pref = pref0 * pw;
+    V Fx = fx * pref, Fy = fy * pref;
+    V ax = gl_fma(Fx, c, -(Fy * s)), ay = gl_fma(Fx, s, Fy * c);
     // back-rotation by -phi
     g[EPLG_PHI] += gl_fma(gay[j], ax, -(gax[j] * ay));
-    T gFx = gl_fma(gax[j], c, gay[j] * s), gFy = gl_fma(gay[j], c, -(gax[j] * s));
+    V gFx = gl_fma(gax[j], c, gay[j] * s), gFy = gl_fma(gay[j], c, -(gax[j] * s));
     // prefactor
-    T gpref = gl_fma(gFx, fx, gFy * fy);
-    T gr = gFx * pref, gi = gFy * pref;               // cotangent of u P (complex pair)
+    V gpref = gl_fma(gFx, fx, gFy * fy);
+    V gr = gFx * pref, gi = gFy * pref;               // cotangent of u P (complex pair)
     g[EPLG_PREF0] += gpref * pw;
-    T gpwpw = gpref * pref;                           // gpw * pw
-    g[EPLG_T] += gpwpw * (l2br * T(GL_LN2));
+    V gpwpw = gpref * pref;                           // gpw * pw
+    g[EPLG_T] += gpwpw * (l2br * V(S(GL_LN2)));
     g[EPLG_B] += gpwpw * tm1_over_b;
-    bool r_free = (E.R2 >= T(1e-20)) && (E.R2 <= T(1e20));
-    T gR_over_R = r_free ? -gpwpw * tm1 * (E.ir * E.ir) : T(0);   // gR / R0
+    V ir2 = E.ir * E.ir;
+    V gR_over_R = gl_where_in(E.R2, S(1e-20), S(1e20), -(gpwpw * tm1 * ir2), V(S(0)));   // gR / R0 (0 where R is clamped)
     // series: F = u P(w; f, t).  <g, u X> = Re(conj(g) u X) for X = dP/df, dP/dt
-    T hr = gl_fma(gr, E.Cs, gi * E.Ss), hi = gl_fma(gi, E.Cs, -(gr * E.Ss));   // conj(u) g
+    V hr = gl_fma(gr, E.Cs, gi * E.Ss), hi = gl_fma(gi, E.Cs, -(gr * E.Ss));   // conj(u) g
     g[EPLG_F] += gl_fma(hr, Fr[j], hi * Fi[j]);
     g[EPLG_T] += gl_fma(hr, Tr[j], hi * Ti[j]);
     // d/d(ang): dF = i u (P + 2 w P_w) d(ang), with w P_w = f dP/df
-    T Zr = gl_fma(T(2) * f, Fr[j], Pr[j]), Zi = gl_fma(T(2) * f, Fi[j], Pi[j]);
-    T gang = gl_fma(hi, Zr, -(hr * Zi));              // Re(conj(g) i u Z)
+    V Zr = gl_fma(f2, Fr[j], Pr[j]), Zi = gl_fma(f2, Fi[j], Pi[j]);
+    V gang = gl_fma(hi, Zr, -(hr * Zi));              // Re(conj(g) i u Z)
     // ang = atan2(yr, qx), R0 = hypot(qx, yr):  d(ang) = (qx dyr - yr dqx)/R0^2, dR0 = (qx dqx + yr dyr)/R0
-    T ga = gang * (E.ir * E.ir);
-    T gqx = gl_fma(gR_over_R, E.qx, -(ga * E.yr));
-    T gyr = gl_fma(gR_over_R, E.yr, ga * E.qx);
+    V ga = gang * ir2;
+    V gqx = gl_fma(gR_over_R, E.qx, -(ga * E.yr));
+    V gyr = gl_fma(gR_over_R, E.yr, ga * E.qx);
     g[EPLG_Q] += gqx * E.xr;
-    T gxr = gqx * q;
+    V gxr = gqx * q;
     g[EPLG_PHI] += gl_fma(gxr, E.yr, -(gyr * E.xr));
-    T gdx = gl_fma(gxr, c, -(gyr * s)), gdy = gl_fma(gxr, s, gyr * c);
+    V gdx = gl_fma(gxr, c, -(gyr * s)), gdy = gl_fma(gxr, s, gyr * c);
     g[EPLG_CX] -= gdx;
     g[EPLG_CY] -= gdy;
   }
@@ -472,21 +473,22 @@ GL_HD void epl_bwd(const T* d, int ts, const T* x, const T* y, const T* gax, con
 // =============================================================================================
 // SHEAR  (tf/profiles/mass/shear.py:14-16)   raw = d = dvars = (gamma1, gamma2)
 // =============================================================================================
-template <class T, int NP>
-GL_HD void shear_fwd(const T* d, const T* x, const T* y, T* ax, T* ay) {
+template <class V, int NP>
+GL_HD void shear_fwd(const typename gl_scalar_of<V>::type* d, const V* x, const V* y, V* ax, V* ay) {
+  const V g1 = V(d[0]), g2 = V(d[1]);
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
-    ax[j] = d[0] * x[j] + d[1] * y[j];
-    ay[j] = d[1] * x[j] - d[0] * y[j];
+    ax[j] = gl_fma(g1, x[j], g2 * y[j]);
+    ay[j] = gl_fma(g2, x[j], -(g1 * y[j]));
   }
 }
-template <class T, int NP>
-GL_HD void shear_bwd(const T* d, const T* x, const T* y, const T* gax, const T* gay, T* g) {
+template <class V, int NP>
+GL_HD void shear_bwd(const typename gl_scalar_of<V>::type* d, const V* x, const V* y, const V* gax, const V* gay, V* g) {
   (void)d;
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
-    g[0] += gax[j] * x[j] - gay[j] * y[j];
-    g[1] += gax[j] * y[j] + gay[j] * x[j];
+    g[0] += gl_fma(gax[j], x[j], -(gay[j] * y[j]));
+    g[1] += gl_fma(gax[j], y[j], gay[j] * x[j]);
   }
 }
 
@@ -1001,51 +1003,56 @@ GL_HD void sersic_prep_bwd(const T* raw, const T* d, const T* g, T* graw, bool e
   }
 }
 // (R/Rs)^(1/n) = 2^((0.5/n) log2(R^2/Rs^2)) and exp(-bn (p-1)) = 2^(-bn log2e (p-1)): no sqrt, no powf.
-template <class T, int NP>
-GL_HD void sersic_fwd(const T* d, const T* x, const T* y, T* out) {
-  T c = d[SER_C], s = d[SER_S], irs2 = d[SER_IRS] * d[SER_IRS], hin = T(0.5) * d[SER_IN];
+template <class V, int NP>
+GL_HD void sersic_fwd(const typename gl_scalar_of<V>::type* d, const V* x, const V* y, V* out) {
+  typedef typename gl_scalar_of<V>::type S;
+  const V c = V(d[SER_C]), s = V(d[SER_S]), irs2 = V(d[SER_IRS] * d[SER_IRS]), hin = V(S(0.5) * d[SER_IN]);
+  const V cx = V(d[SER_CX]), cy = V(d[SER_CY]), sq = V(d[SER_SQ]), isq = V(d[SER_ISQ]), ie = V(d[SER_IE]), nbl = V(d[SER_NBL]);
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
-    T dx = x[j] - d[SER_CX], dy = y[j] - d[SER_CY];
-    T xt1 = gl_fma(c, dx, s * dy) * d[SER_SQ];
-    T xt2 = gl_fma(c, dy, -(s * dx)) * d[SER_ISQ];
-    T u2 = gl_fma(xt1, xt1, xt2 * xt2) * irs2;
-    T p = gl_exp2_fast(hin * gl_log2_fast(u2));
-    out[j] = gl_fma(d[SER_IE], gl_exp2_fast(d[SER_NBL] * (p - T(1))), out[j]);
+    V dx = x[j] - cx, dy = y[j] - cy;
+    V xt1 = gl_fma(c, dx, s * dy) * sq;
+    V xt2 = gl_fma(c, dy, -(s * dx)) * isq;
+    V u2 = gl_fma(xt1, xt1, xt2 * xt2) * irs2;
+    V p = gl_exp2_fast(hin * gl_log2_fast(u2));
+    out[j] = gl_fma(ie, gl_exp2_fast(nbl * (p - V(S(1)))), out[j]);
   }
 }
 // gI: cotangent of the surface brightness.  gx/gy (may be null): += cotangent of the coordinates.
-template <class T, int NP>
-GL_HD void sersic_bwd(const T* d, const T* x, const T* y, const T* gI, T* g, T* gx, T* gy) {
-  T c = d[SER_C], s = d[SER_S], sq = d[SER_SQ], isq = d[SER_ISQ], irs = d[SER_IRS], bn = d[SER_BN];
-  T irs2 = irs * irs, hin = T(0.5) * d[SER_IN];
+template <class V, int NP>
+GL_HD void sersic_bwd(const typename gl_scalar_of<V>::type* d, const V* x, const V* y, const V* gI, V* g, V* gx, V* gy) {
+  typedef typename gl_scalar_of<V>::type S;
+  const V c = V(d[SER_C]), s = V(d[SER_S]), sq = V(d[SER_SQ]), isq = V(d[SER_ISQ]), irs = V(d[SER_IRS]), bn = V(d[SER_BN]);
+  const V irs2 = irs * irs, hin = V(S(0.5) * d[SER_IN]), cx = V(d[SER_CX]), cy = V(d[SER_CY]), ie = V(d[SER_IE]), nbl = V(d[SER_NBL]);
+  const V isq2 = isq * isq, two_irs = V(S(2)) * irs;
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
-    T dx = x[j] - d[SER_CX], dy = y[j] - d[SER_CY];
-    T xr = gl_fma(c, dx, s * dy), yr = gl_fma(c, dy, -(s * dx));
-    T xt1 = xr * sq, xt2 = yr * isq;
-    T r2 = gl_fma(xt1, xt1, xt2 * xt2);
-    T u2 = r2 * irs2;
-    T L2 = gl_log2_fast(u2);
-    T p = gl_exp2_fast(hin * L2);
-    T E = gl_exp2_fast(d[SER_NBL] * (p - T(1)));
+    V dx = x[j] - cx, dy = y[j] - cy;
+    V xr = gl_fma(c, dx, s * dy), yr = gl_fma(c, dy, -(s * dx));
+    V xt1 = xr * sq, xt2 = yr * isq;
+    V r2 = gl_fma(xt1, xt1, xt2 * xt2);
+    V u2 = r2 * irs2;
+    V L2 = gl_log2_fast(u2);
+    V p = gl_exp2_fast(hin * L2);
+    V pm1 = p - V(S(1));
+    V E = gl_exp2_fast(nbl * pm1);
     g[SERG_IE] += gI[j] * E;
-    T garg = gI[j] * d[SER_IE] * E;
-    g[SERG_BN] -= garg * (p - T(1));
-    T gpp = -garg * bn * p;                       // gp * p
-    if (u2 > T(0)) {
-      g[SERG_IN] += gpp * (T(0.5 * GL_LN2) * L2);
-      T gu2 = gl_div_fast(gpp * hin, u2);
-      g[SERG_IRS] += gu2 * r2 * T(2) * irs;
-      T gr2 = gu2 * irs2 * T(2);
-      T gxt1 = gr2 * xt1, gxt2 = gr2 * xt2;
-      g[SERG_SQ] += gl_fma(gxt1, xr, -(gxt2 * yr * isq * isq));
-      T gxr = gxt1 * sq, gyr = gxt2 * isq;
-      g[SERG_PHI] += gl_fma(gxr, yr, -(gyr * xr));
-      T gdx = gl_fma(gxr, c, -(gyr * s)), gdy = gl_fma(gxr, s, gyr * c);
-      g[SERG_CX] -= gdx; g[SERG_CY] -= gdy;
-      if (gx) { gx[j] += gdx; gy[j] += gdy; }
-    }
+    V garg = gI[j] * ie * E;
+    g[SERG_BN] -= garg * pm1;
+    V gpp = -(garg * bn * p);                      // gp * p
+    // R = 0 (u2 == 0): the reference's gradient is NaN there (measure zero); contributes 0 here
+    V L2s = gl_where_gt(u2, S(0), L2, V(S(0)));
+    V gu2 = gl_where_gt(u2, S(0), gl_div_fast(gpp * hin, u2), V(S(0)));
+    g[SERG_IN] += gpp * (V(S(0.5 * GL_LN2)) * L2s);
+    g[SERG_IRS] += gu2 * r2 * two_irs;
+    V gr2 = gu2 * irs2 * V(S(2));
+    V gxt1 = gr2 * xt1, gxt2 = gr2 * xt2;
+    g[SERG_SQ] += gl_fma(gxt1, xr, -(gxt2 * yr * isq2));
+    V gxr = gxt1 * sq, gyr = gxt2 * isq;
+    g[SERG_PHI] += gl_fma(gxr, yr, -(gyr * xr));
+    V gdx = gl_fma(gxr, c, -(gyr * s)), gdy = gl_fma(gxr, s, gyr * c);
+    g[SERG_CX] -= gdx; g[SERG_CY] -= gdy;
+    if (gx) { gx[j] += gdx; gy[j] += gdy; }
   }
 }
 
@@ -1231,7 +1238,7 @@ GL_HD void gl_prep_bwd(int type, unsigned flags, const T* raw, const T* d, const
 
 // deflection of one lens entry at NP points (d = derived block of the entry)
 template <class T, int NP, unsigned F>
-GL_HD void gl_lens_fwd(int type, int ts, const T* d, const T* x, const T* y, T* ax, T* ay) {
+GL_HD void gl_lens_fwd(int type, int ts, const typename gl_scalar_of<T>::type* d, const T* x, const T* y, T* ax, T* ay) {
 #pragma unroll
   for (int j = 0; j < NP; ++j) { ax[j] = T(0); ay[j] = T(0); }
   switch (type) {
@@ -1246,7 +1253,7 @@ GL_HD void gl_lens_fwd(int type, int ts, const T* d, const T* x, const T* y, T* 
   }
 }
 template <class T, int NP, unsigned F>
-GL_HD void gl_lens_bwd(int type, int ts, const T* d, const T* x, const T* y, const T* gax, const T* gay, T* g) {
+GL_HD void gl_lens_bwd(int type, int ts, const typename gl_scalar_of<T>::type* d, const T* x, const T* y, const T* gax, const T* gay, T* g) {
   switch (type) {
     case GLT_EPL: if constexpr ((F & GLF_EPL) != 0) epl_bwd<T, NP>(d, ts, x, y, gax, gay, g); break;
     case GLT_SHEAR: if constexpr ((F & GLF_SHEAR) != 0) shear_bwd<T, NP>(d, x, y, gax, gay, g); break;

@@ -133,7 +133,7 @@ GL_HD void gl_sample_prep_bwd(const GlProgram& P, const TP* params, int bs, int 
 // ---------------------------------------------------------------------------------------------
 // beta = theta - sum_i alpha_i(theta)   (src/gigalens/tf/simulator.py:72-78)
 template <class T, int NP, unsigned F>
-GL_HD void gl_pix_beta(const GlProgram& P, const T* der, const T* x, const T* y, T* bx, T* by) {
+GL_HD void gl_pix_beta(const GlProgram& P, const typename gl_scalar_of<T>::type* der, const T* x, const T* y, T* bx, T* by) {
 #pragma unroll
   for (int j = 0; j < NP; ++j) { bx[j] = x[j]; by[j] = y[j]; }
   for (int i = 0; i < P.n_lens; ++i) {
@@ -150,7 +150,7 @@ GL_HD void gl_pix_beta(const GlProgram& P, const T* der, const T* x, const T* y,
 
 // Supersampled surface brightness before the NaN scrub (tf/simulator.py:124-138), non-lstsq mode.
 template <class T, int NP, unsigned F>
-GL_HD void gl_pix_image(const GlProgram& P, const T* der, const T* x, const T* y, bool no_deflection, T* out) {
+GL_HD void gl_pix_image(const GlProgram& P, const typename gl_scalar_of<T>::type* der, const T* x, const T* y, bool no_deflection, T* out) {
   T bx[NP], by[NP];
   if (no_deflection) {
 #pragma unroll
@@ -214,7 +214,7 @@ GL_HD void gl_point_components(const GlProgram& P, const T* der, T x, T y, T bx,
 // pixels.  `flush(acc, n, off)` receives the NP-pixel partial cotangent of dvars [off, off+n) --
 // the host harness adds it into a vector, the CUDA kernel warp-reduces it into shared memory.
 template <class T, int NP, unsigned F, class Flush>
-GL_HD void gl_pix_image_bwd(const GlProgram& P, const T* der, const T* x, const T* y, const T* gS,
+GL_HD void gl_pix_image_bwd(const GlProgram& P, const typename gl_scalar_of<T>::type* der, const T* x, const T* y, const T* gS,
                             bool no_deflection, Flush& flush) {
   T bx[NP], by[NP], Gx[NP], Gy[NP];
   if (no_deflection) {

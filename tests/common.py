@@ -120,6 +120,24 @@ def host_run(cm: CompiledModel, mat, gx, gy, g_ss=None, dtype=np.float64, no_def
     return dict(ss=ss, gparams=gparams, beta=beta, comps=comps)
 
 
+def host_run_packed(cm: CompiledModel, mat, gx, gy, g_ss=None):
+    """Same as host_run(dtype=float32) but through the two-pixel packed lane type (GlF2)."""
+    lib = hostcheck_lib()
+    mat = np.ascontiguousarray(mat, dtype=np.float32)
+    P, bs = mat.shape
+    gx = np.ascontiguousarray(gx, dtype=np.float32)
+    gy = np.ascontiguousarray(gy, dtype=np.float32)
+    npix = gx.size
+    ss = np.zeros((bs, npix), dtype=np.float32)
+    gparams = np.zeros((P, bs), dtype=np.float32) if g_ss is not None else None
+    g_ss_c = np.ascontiguousarray(g_ss, dtype=np.float32) if g_ss is not None else None
+    vp = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+    rc = lib.glh_run_f32x2(C.byref(cm.desc), C.c_int(bs), vp(mat), C.c_int(npix), vp(gx), vp(gy), vp(ss), vp(g_ss_c), vp(gparams))
+    if rc != 0:
+        raise RuntimeError(lib.glh_last_error().decode())
+    return dict(ss=ss, gparams=gparams)
+
+
 # ---------------------------------------------------------------- parity rule
 def ulp_perturb(mat, seed=99):
     """The same fp32 inputs moved by +-1/2 ulp(fp32) relative: an input error no fp32 computation can

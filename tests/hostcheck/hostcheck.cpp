@@ -78,7 +78,49 @@ static int run(const gl_model_desc* m, int bs, const T* params, int npix, const 
   return 0;
 }
 
+// The two-pixel packed lane type (GlF2) through the same drivers: host build of the code path the
+// k_raytrace_*_p kernels instantiate (feature set EPL | SHEAR | SERSIC only).
+struct HostFlush2 {
+  float* g;
+  void operator()(const GlF2* acc, int n, int off) { for (int k = 0; k < n; ++k) g[off + k] += acc[k].x + acc[k].y; }
+};
+static int run_packed(const gl_model_desc* m, int bs, const float* params, int npix, const float* gx, const float* gy,
+                      float* ss_out, const float* g_ss, float* gparams) {
+  constexpr unsigned F = GLF_EPL | GLF_SHEAR | GLF_SERSIC;
+  GlBuilt B;
+  std::string e = gl_build_program(m, B);
+  if (!e.empty()) { g_err = e; return 1; }
+  GlProgram& P = B.prog;
+  for (int i = 0; i < P.n_prof; ++i)
+    if ((gl_feature_of(P.prof[i].type) & F) == 0 || P.prof[i].n_members > 0) { g_err = "packed lanes: unsupported profile"; return 1; }
+  if (npix % 2) { g_err = "packed lanes need an even pixel count"; return 1; }
+  std::vector<float> der(P.der_total), g(P.g_total > 0 ? P.g_total : 1);
+  for (int b = 0; b < bs; ++b) {
+    gl_sample_prep<float, float>(P, params, bs, b, nullptr, nullptr, nullptr, der.data());
+    std::fill(g.begin(), g.end(), 0.f);
+    HostFlush2 fl{g.data()};
+    for (int p = 0; p < npix; p += 2) {
+      GlF2 x[1] = {GlF2(gx[p], gx[p + 1])}, y[1] = {GlF2(gy[p], gy[p + 1])}, v[1];
+      if (ss_out) {
+        gl_pix_image<GlF2, 1, F>(P, der.data(), x, y, false, v);
+        ss_out[(size_t)b * npix + p] = (v[0].x != v[0].x) ? 0.f : v[0].x;
+        ss_out[(size_t)b * npix + p + 1] = (v[0].y != v[0].y) ? 0.f : v[0].y;
+      }
+      if (g_ss && gparams) {
+        GlF2 gs[1] = {GlF2(g_ss[(size_t)b * npix + p], g_ss[(size_t)b * npix + p + 1])};
+        gl_pix_image_bwd<GlF2, 1, F>(P, der.data(), x, y, gs, false, fl);
+      }
+    }
+    if (g_ss && gparams) gl_sample_prep_bwd<float, float>(P, params, bs, b, nullptr, nullptr, der.data(), g.data(), gparams);
+  }
+  return 0;
+}
+
 extern "C" {
+int glh_run_f32x2(const gl_model_desc* m, int bs, const float* params, int npix, const float* gx, const float* gy,
+                  float* ss_out, const float* g_ss, float* gparams) {
+  return run_packed(m, bs, params, npix, gx, gy, ss_out, g_ss, gparams);
+}
 const char* glh_last_error() { return g_err.c_str(); }
 int glh_depth(const gl_model_desc* m) { GlBuilt B; std::string e = gl_build_program(m, B); if (!e.empty()) { g_err = e; return -1; } return B.prog.depth; }
 int glh_run_f64(const gl_model_desc* m, int bs, const double* params, int npix, const double* gx, const double* gy,

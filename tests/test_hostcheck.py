@@ -115,3 +115,19 @@ def test_lstsq_component_stack(interpolate):
     ref = st.reshape(2, -1, st.shape[-1]).permute(0, 2, 1).numpy()
     out = host_run(cm, mat, sim.img_X[:, 0].numpy(), sim.img_Y[:, 0].numpy(), want_comps=True)
     assert np.max(np.abs(out["comps"] - ref)) / np.max(np.abs(ref)) < (1e-12 if interpolate else 1e-7)
+
+
+@pytest.mark.parametrize("name", ["c2", "constants"])
+def test_packed_lane_instantiation_matches_scalar(name):
+    """The two-pixel packed lane type (what k_raytrace_*_p instantiate) runs the same source as the
+    scalar lanes; on the host both are plain fp32, so results must agree to rounding."""
+    pm = MODELS[name]()
+    mat = draw_matrix(CompiledModel(pm), 3, seed=5).astype(np.float32)
+    cm, gx, gy, S64, G, g64 = _reference(pm, mat.astype(np.float64), torch.float64, 5)
+    a = host_run(cm, mat, gx, gy, g_ss=G, dtype=np.float32)
+    b = common.host_run_packed(cm, mat, gx, gy, g_ss=G)
+    assert np.max(np.abs(a["ss"] - b["ss"])) <= 1e-6 * np.max(np.abs(a["ss"]))
+    for k in range(cm.n_params):
+        sc = np.max(np.abs(g64[k]))
+        assert np.max(np.abs(a["gparams"][k] - b["gparams"][k])) <= 2e-5 * sc, cm.slot_keys[k]
+        assert np.max(np.abs(b["gparams"][k] - g64[k])) <= max(1e-4, 10 * np.max(np.abs(a["gparams"][k] - g64[k]))) * sc
