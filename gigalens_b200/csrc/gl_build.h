@@ -40,7 +40,7 @@ inline bool gl_is_mass(int t) { return t >= GLT_EPL && t <= GLT_DPIE; }
 inline bool gl_is_light(int t) { return t == GLT_SERSIC || t == GLT_SERSIC_ELLIPSE || t == GLT_SHAPELETS; }
 
 // Returns "" on success, else an error message.
-inline std::string gl_build_program(const gl_model_desc* m, GlBuilt& out) {
+inline std::string gl_build_program(const gl_model_desc* m, GlBuilt& out, bool use_fwdmode = true) {
   if (!m) return "model descriptor is NULL";
   GlProgram& P = out.prog;
   P = GlProgram();
@@ -109,7 +109,11 @@ inline std::string gl_build_program(const gl_model_desc* m, GlBuilt& out) {
     pr.g_off = g;
     const int nm = pr.n_members > 0 ? pr.n_members : 1;
     der += pr.der_size * nm;
-    g += pr.n_dvars * nm;
+    // The first dPIE scaling-relation group is differentiated in forward mode (gl_math.cuh dpie_fwd_jac):
+    // its cotangent block is just the three base scaling parameters.
+    pr.fwdmode = 0;
+    if (pr.n_members > 0 && pr.type == GLT_DPIE && !P.has_fwdmode && use_fwdmode) { pr.fwdmode = 1; P.has_fwdmode = 1; }
+    g += pr.fwdmode ? 3 : pr.n_dvars * nm;
   }
   P.der_total = (der + 3) & ~3;
   P.g_total = g;

@@ -350,7 +350,8 @@ GL_HD void epl_fwd(const typename gl_scalar_of<V>::type* d, int ts, const V* x, 
   }
 #endif
   if (!done)
-  for (int n = N - 1; n >= 0; --n) {
+#pragma unroll 2
+  for (int n = N - 1; n >= 0; --n) {   // unrolled by two so the loop-carried (P_re, P_im) ping-pong without register copies
     const V a = V(A[n]);
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
@@ -414,6 +415,7 @@ GL_HD void epl_bwd(const typename gl_scalar_of<V>::type* d, int ts, const V* x, 
   }
 #endif
   if (!done)
+#pragma unroll 2
   for (int n = N - 1; n >= 0; --n) {
     const V a = V(A[n]), af = V(Af[n]), at = V(At[n]);
 #pragma unroll
@@ -743,7 +745,8 @@ GL_HD void nfw_bwd(const T* d, const T* x, const T* y, const T* gax, const T* ga
 //   dvars: cx, cy, phi, scale, rc, rt, e
 // =============================================================================================
 enum { DP_CX = 0, DP_CY, DP_C, DP_S, DP_SCALE, DP_RC, DP_RT, DP_E,
-       DP_SQE, DP_Q, DP_IQ, DP_IOPE2, DP_IOME2, DP_ZCI, DP_RC2, DP_RT2, DP_SIZE = 16 };   // second row: per-member constants of e, rc, rt
+       DP_SQE, DP_Q, DP_IQ, DP_IOPE2, DP_IOME2, DP_ZCI, DP_RC2, DP_RT2,
+       DP_M = 16, DP_SIZE = 28 };   // DP_M: 3x3 d(scale, rc, rt)/d(base scaling params) of a scaling-relation member   // second row: per-member constants of e, rc, rt
 enum { DPG_CX = 0, DPG_CY, DPG_PHI, DPG_SCALE, DPG_RC, DPG_RT, DPG_E };
 #define GL_DPIE_RMIN 0.0001
 // _sort_ra_rs (piemd.py:51-60): returns the sorted/floored radii and the selection pattern needed
@@ -956,6 +959,59 @@ GL_HD void dpie_bwd(const T* d, const T* x, const T* y, const T* gax, const T* g
     g[DPG_PHI] += gl_fma(gx, yr, -(gy * xr));
     T gdx = gl_fma(gx, c, -(gy * s)), gdy = gl_fma(gx, s, gy * c);
     g[DPG_CX] -= gdx; g[DPG_CY] -= gdy;
+  }
+}
+
+// Forward-mode variant for scaling-relation members (scaling_relation.py:57-70): a catalogue member
+// has exactly three free inputs -- the group's base (theta_E, r_core, r_cut) -- so instead of the
+// reverse sweep (forward recompute + adjoint per member and a cotangent flush per member) the beta
+// pass carries the 2x3 Jacobian of the group deflection w.r.t. the base parameters:
+//     J[:, k] += sum_j  d(alpha_m)/d(scale, rc, rt)_j * M_m[j][k],
+// with M_m = d(scale, rc, rt)_m / d(base)_k precomputed per (sample, member) in the derived block.
+// d(alpha)/d(rc|rt) follows from z = num/den, zr = log z:  dz = (num' - z den')/den, dzr = dz / z.
+template <class T, int NP>
+GL_HD void dpie_fwd_jac(const T* d, const T* x, const T* y, T* ax, T* ay, T (*Jx)[NP], T (*Jy)[NP]) {
+  const T c = d[DP_C], s = d[DP_S], scale = d[DP_SCALE], zci = d[DP_ZCI], two_sqe = T(2) * d[DP_SQE];
+  const T* M = d + DP_M;
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    T dx = x[j] - d[DP_CX], dy = y[j] - d[DP_CY];
+    T xr = gl_fma(dx, c, dy * s), yr = gl_fma(dy, c, -(dx * s));
+    DpieFw<T> W; T re, im;
+    dpie_core_fwd(d, xr, yr, W, re, im);
+    ax[j] = scale * gl_fma(re, c, -(im * s));
+    ay[j] = scale * gl_fma(re, s, im * c);
+    // tangents of (re, im) w.r.t. rc and rt
+    T tre[2], tim[2];
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      T naa, nbb, ncc, ndd;   // num' = naa + i nbb, den' = ncc + i ndd
+      if (w == 0) {           // d/d rc: b' = 2 sqe rc/sc, d' = 2 sqe
+        const T bp = two_sqe * d[DP_RC] * gl_div_fast(T(1), W.sc);
+        naa = -(bp * W.f_); nbb = bp * W.c_; ncc = -(two_sqe * W.e_); ndd = W.a * two_sqe;
+      } else {                // d/d rt: e' = 2 sqe rt/st, f' = 2 sqe
+        const T ep = two_sqe * d[DP_RT] * gl_div_fast(T(1), W.st);
+        naa = -(W.b_ * two_sqe); nbb = W.a * two_sqe; ncc = -(W.d_ * ep); ndd = W.c_ * ep;
+      }
+      // t = num' - z den'
+      const T tr = naa - gl_fma(W.aaa, ncc, -(W.bbb * ndd));
+      const T ti = nbb - gl_fma(W.aaa, ndd, W.bbb * ncc);
+      // dz = t conj(den) / |den|^2
+      const T dzr_ = gl_fma(tr, W.cc, ti * W.dd) * W.inorm;
+      const T dzi_ = gl_fma(ti, W.cc, -(tr * W.dd)) * W.inorm;
+      // d(log z) = dz conj(z) / |z|^2
+      const T lr = gl_fma(dzr_, W.aaa, dzi_ * W.bbb) * W.inorm2;
+      const T li = gl_fma(dzi_, W.aaa, -(dzr_ * W.bbb)) * W.inorm2;
+      tre[w] = -zci * li; tim[w] = zci * lr;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      // rotated-frame tangent of alpha_m/1 w.r.t. base parameter k, then rotate back
+      const T vr = gl_fma(M[k], re, scale * gl_fma(M[3 + k], tre[0], M[6 + k] * tre[1]));
+      const T vi = gl_fma(M[k], im, scale * gl_fma(M[3 + k], tim[0], M[6 + k] * tim[1]));
+      Jx[k][j] += gl_fma(vr, c, -(vi * s));
+      Jy[k][j] += gl_fma(vr, s, vi * c);
+    }
   }
 }
 

@@ -26,6 +26,7 @@ struct GlProf {
   int n_members;   // 0 = plain profile
   int member_off;  // offset into the member-factor array ([n_raw][n_members] per entry)
   int amp_off;     // Shapelets: offset into the amp-slot array
+  int fwdmode;     // scaling-relation group differentiated in forward mode (3 dvars = the base scaling params)
   int comp_off;    // light profiles: index of the first linear component (lstsq stack channel)
   const float* table;  // Shapelets(interpolate=True): [n_max+1][6000] basis table (device / host pointer)
   int slot[GL_MAX_RAW];
@@ -39,6 +40,7 @@ struct GlProgram {
   int g_total;     // floats per sample in the dvar-cotangent vector
   int n_params;    // P
   int depth;       // number of linear light components (lstsq)
+  int has_fwdmode; // some scaling-relation group is differentiated in forward mode
   GlProf prof[GL_MAX_PROF];
 };
 
@@ -83,8 +85,20 @@ GL_HD void gl_sample_prep(const GlProgram& P, const TP* params, int bs, int b, c
     for (int m = 0; m < nm; ++m) {
       T raw[GL_MAX_RAW];
       gl_gather_raw<T, TP>(pr, params, bs, b, member_factor, m, raw);
-      gl_prep<T>(pr.type, pr.flags, pr.niter, raw, der + pr.der_off + m * pr.der_size,
-                 epl_fmax ? T(epl_fmax[i]) : T(-1));
+      T* dm = der + pr.der_off + m * pr.der_size;
+      gl_prep<T>(pr.type, pr.flags, pr.niter, raw, dm, epl_fmax ? T(epl_fmax[i]) : T(-1));
+      if (pr.n_members > 0 && pr.type == GLT_DPIE) {
+        // M[j][k] = d(scale, rc, rt)_j / d(base theta_E, r_core, r_cut)_k for this member
+        for (int jj = 0; jj < 3; ++jj) {
+          T gu[GL_MAX_DVARS], graw[GL_MAX_RAW];
+          for (int k = 0; k < GL_MAX_DVARS; ++k) gu[k] = T(0);
+          for (int k = 0; k < GL_MAX_RAW; ++k) graw[k] = T(0);
+          gu[DPG_SCALE + jj] = T(1);
+          dpie_prep_bwd<T>(raw, dm, gu, graw, true);
+          for (int k = 0; k < 3; ++k)
+            dm[DP_M + 3 * jj + k] = graw[k] * T(member_factor[pr.member_off + k * pr.n_members + m]);
+        }
+      }
     }
   }
 }
@@ -113,6 +127,11 @@ GL_HD void gl_sample_prep_bwd(const GlProgram& P, const TP* params, int bs, int 
     const int nm = pr.n_members > 0 ? pr.n_members : 1;
     T gbase[GL_MAX_RAW];
     for (int k = 0; k < GL_MAX_RAW; ++k) gbase[k] = T(0);
+    if (pr.fwdmode) {
+      for (int k = 0; k < 3; ++k)
+        if (pr.slot[k] >= 0) gparams[(size_t)pr.slot[k] * bs + b] += TP(g[pr.g_off + k]);
+      continue;
+    }
     for (int m = 0; m < nm; ++m) {
       T raw[GL_MAX_RAW], graw[GL_MAX_RAW];
       gl_gather_raw<T, TP>(pr, params, bs, b, member_factor, m, raw);
@@ -142,6 +161,32 @@ GL_HD void gl_pix_beta(const GlProgram& P, const typename gl_scalar_of<T>::type*
     for (int m = 0; m < nm; ++m) {
       T ax[NP], ay[NP];
       gl_lens_fwd<T, NP, F>(pr.type, pr.ts, der + pr.der_off + m * pr.der_size, x, y, ax, ay);
+#pragma unroll
+      for (int j = 0; j < NP; ++j) { bx[j] -= ax[j]; by[j] -= ay[j]; }
+    }
+  }
+}
+
+// beta as above, plus the 2x3 Jacobian of the forward-mode group's deflection w.r.t. its base params
+template <class T, int NP, unsigned F>
+GL_HD void gl_pix_beta_jac(const GlProgram& P, const typename gl_scalar_of<T>::type* der, const T* x, const T* y, T* bx, T* by,
+                           T (*Jx)[NP], T (*Jy)[NP]) {
+#pragma unroll
+  for (int j = 0; j < NP; ++j) { bx[j] = x[j]; by[j] = y[j]; }
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int j = 0; j < NP; ++j) { Jx[k][j] = T(0); Jy[k][j] = T(0); }
+  for (int i = 0; i < P.n_lens; ++i) {
+    const GlProf& pr = P.prof[i];
+    const int nm = pr.n_members > 0 ? pr.n_members : 1;
+    for (int m = 0; m < nm; ++m) {
+      T ax[NP], ay[NP];
+      bool done = false;
+      if constexpr ((F & GLF_DPIE) != 0 && sizeof(T) == sizeof(typename gl_scalar_of<T>::type)) {
+        if (pr.fwdmode) { dpie_fwd_jac<T, NP>(der + pr.der_off + m * pr.der_size, x, y, ax, ay, Jx, Jy); done = true; }
+      }
+      if (!done) gl_lens_fwd<T, NP, F>(pr.type, pr.ts, der + pr.der_off + m * pr.der_size, x, y, ax, ay);
 #pragma unroll
       for (int j = 0; j < NP; ++j) { bx[j] -= ax[j]; by[j] -= ay[j]; }
     }
@@ -217,11 +262,16 @@ template <class T, int NP, unsigned F, class Flush>
 GL_HD void gl_pix_image_bwd(const GlProgram& P, const typename gl_scalar_of<T>::type* der, const T* x, const T* y, const T* gS,
                             bool no_deflection, Flush& flush) {
   T bx[NP], by[NP], Gx[NP], Gy[NP];
+  T Jx[3][NP], Jy[3][NP];
+  bool have_jac = false;
   if (no_deflection) {
 #pragma unroll
     for (int j = 0; j < NP; ++j) { bx[j] = x[j]; by[j] = y[j]; }
   } else {
-    gl_pix_beta<T, NP, F>(P, der, x, y, bx, by);
+    if constexpr ((F & GLF_DPIE) != 0) {
+      if (P.has_fwdmode) { gl_pix_beta_jac<T, NP, F>(P, der, x, y, bx, by, Jx, Jy); have_jac = true; }
+    }
+    if (!have_jac) gl_pix_beta<T, NP, F>(P, der, x, y, bx, by);
   }
 #pragma unroll
   for (int j = 0; j < NP; ++j) { Gx[j] = T(0); Gy[j] = T(0); }
@@ -266,6 +316,19 @@ GL_HD void gl_pix_image_bwd(const GlProgram& P, const typename gl_scalar_of<T>::
   for (int j = 0; j < NP; ++j) { Gx[j] = -Gx[j]; Gy[j] = -Gy[j]; }
   for (int i = 0; i < P.n_lens; ++i) {
     const GlProf& pr = P.prof[i];
+    if constexpr ((F & GLF_DPIE) != 0) {
+      if (have_jac && pr.fwdmode) {   // forward-mode group: contract the carried Jacobian with the cotangent
+        T acc[GL_MAX_DVARS];
+#pragma unroll
+        for (int k = 0; k < GL_MAX_DVARS; ++k) acc[k] = T(0);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+          for (int j = 0; j < NP; ++j) acc[k] += gl_fma(Gx[j], Jx[k][j], Gy[j] * Jy[k][j]);
+        flush(acc, 3, pr.g_off);
+        continue;
+      }
+    }
     const int nm = pr.n_members > 0 ? pr.n_members : 1;
     for (int m = 0; m < nm; ++m) {
       T acc[GL_MAX_DVARS];
