@@ -173,12 +173,14 @@ def run_cuda(args):
             torch.cuda.synchronize()
 
     # ---- device-resident throughput -----------------------------------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()                      # clocks are sampled under load: warm-up + timed region
     for _ in range(max(args.warmup, 3)):
         out = pmod.log_prob_and_grad(sim, z)
     sync_all()
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
+    pmod._bind(sim)
+    sim.set_option("timing", min(args.steps, 256))     # CUDA events around every kernel of the timed steps
     launches0 = lib.gl_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -188,6 +190,11 @@ def run_cuda(args):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     launches = lib.gl_launch_count() - launches0
+    stage = (C.c_float * 7)()
+    ncalls = C.c_int32(0)
+    _cabi.check(lib.gl_plan_get_timings(sim._plan, stage, C.byref(ncalls)), lib)
+    sim.set_option("timing", 0)
+    stage_ms = [stage[k] / max(1, ncalls.value) for k in range(7)]
     sync_all()
     clocks = sampler.stop() if sampler else None
     t = torch.tensor([ms], device="cuda")
@@ -222,7 +229,7 @@ def run_cuda(args):
     # ---- roofline of the dominant kernel (ray-shooting adjoint), timed live --------------------
     roof = None
     if rank == 0:
-        roof = kernel_roofline(sim, pmod, z, lib)
+        roof = kernel_roofline(sim, stage_ms, ms / args.steps, d)
 
     if rank != 0:
         return
@@ -248,62 +255,56 @@ def run_cuda(args):
     print(json.dumps(line))
 
 
-def kernel_roofline(sim, pmod, z, lib):
-    """Per-kernel device times of one step (CUDA events on the launch stream around each C-ABI stage
-    are not exposed, so time the stages through the public entry points that isolate them) and the
-    roofline of the dominant kernel.  Algorithmic bytes / flops per eval are DESIGN.md's figures."""
-    import torch
+STAGES = ["k_unconstrain", "k_prep", "k_raytrace_fwd", "k_conv_fwd", "k_conv_bwd", "k_raytrace_bwd", "k_sample_bwd"]
 
+
+def kernel_roofline(sim, stage_ms, step_ms, d):
+    """Roofline of the dominant kernel (the ray-tracing adjoint) from its CUDA-event time measured on
+    the launch stream inside the timed region (gl_plan_get_timings), with DESIGN.md's algorithmic
+    bytes / flops per eval.  `traffic` is the ncu DRAM byte count of the same kernel (profiles/)."""
     peaks = _peaks() or {}
     bs = sim.bs
     npix = (sim.numPix * sim.supersample) ** 2
+    dom = max(range(len(STAGES)), key=lambda k: stage_ms[k])
+    name = STAGES[dom]
+    # algorithmic HBM bytes per eval of each kernel (DESIGN.md section 3): N = ss pixels, P = pixels
     P = sim.numPix ** 2
-
-    def timeit(fn, reps=10):
-        for _ in range(3):
-            fn()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(reps):
-            fn()
-        b.record()
-        torch.cuda.synchronize()
-        return a.elapsed_time(b) / reps
-
-    params = pmod.bij_forward(sim, z)
-    mat = sim._params_matrix(params)
-    t_ss = timeit(lambda: sim.simulate_ss(mat))                    # prep + raytrace_fwd
-    t_sim = timeit(lambda: sim.simulate(mat))                      # + conv_fwd
-    t_fwd = timeit(lambda: pmod.log_prob(sim, z))                  # + unconstrain, likelihood
-    t_all = timeit(lambda: pmod.log_prob_and_grad(sim, z))         # + conv_bwd, raytrace_bwd, sample_bwd
-    t_bwd = t_all - t_fwd
-    # ncu launch list (profiles/) gives the split of t_bwd between conv_bwd and raytrace_bwd; the
-    # adjoint ray-tracing kernel is the dominant one.  Algorithmic traffic of that kernel per eval:
-    # read dL/dss (4 N) + grid (8 N, L2-resident) + derived block; write partial gradients.
-    bytes_per_eval_step = 16 * npix + 8 * P + 8 * z.shape[1] * 4
-    flops_per_eval = 34e6  # SURVEY.md §8d / DESIGN.md: 24 MFLOP profile fwd+bwd + 9.7 MFLOP conv fwd+bwd
+    alg_bytes = {"k_raytrace_fwd": 4 * npix, "k_conv_fwd": 4 * npix + 8 * P, "k_conv_bwd": 4 * P + 4 * npix,
+                 "k_raytrace_bwd": 4 * npix + 4 * 196}.get(name, 4 * npix)
+    # nominal flops per eval (hand count, FMA = 2; SURVEY.md section 8d): profile fwd 8.0 M, profile bwd 16 M, conv 4.87 M each way
+    alg_flops = {"k_raytrace_fwd": 8.0e6, "k_conv_fwd": 4.87e6, "k_conv_bwd": 4.87e6, "k_raytrace_bwd": 16.0e6}.get(name, 0.0)
+    ms = stage_ms[dom]
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
     sm_mhz = peaks.get("sm_max_mhz", 1965.0)
     fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
-    hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    achieved_gbs = bytes_per_eval_step * bs / (t_all * 1e-3) / 1e9
+    achieved_gbs = alg_bytes * bs / (ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["kernels"]
+        key = name + ("_p" if name.startswith("k_raytrace") else "")
+        traffic = tr.get(key, tr.get(name, {})).get("traffic_bytes")
+    except Exception:
+        pass
+    which = "of measured" if _peaks() else "of fallback"
     return {
-        "kernel_ms": {"prep+raytrace_fwd": t_ss, "conv_fwd": t_sim - t_ss, "forward_total": t_fwd,
-                      "backward_total(conv_bwd+raytrace_bwd+sample_bwd)": t_bwd, "step_total": t_all},
-        "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved_gbs / hbm_peak, "traffic": None,
-                     "note": "whole step; the path is FP32-FMA/SFU bound (see roofline_fp32), HBM GB/s reported as north_star asks; "
-                             + ("peak of measured" if _peaks() else "peak of fallback")},
-        "fp32": {"bound": "fp32_fma", "achieved": flops_per_eval * bs / (t_all * 1e-3) / 1e12, "peak": fp32_peak,
-                 "unit": "TFLOP/s", "frac": flops_per_eval * bs / (t_all * 1e-3) / 1e12 / fp32_peak,
-                 "note": "nominal 34 MFLOP/eval (hand count, FMA=2) over the whole step; peak = 148 SM x 128 lanes x 2 x max SM clock"},
+        "kernel_ms": {STAGES[k]: stage_ms[k] for k in range(len(STAGES))},
+        "roofline": {"bound": "hbm", "kernel": name, "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": achieved_gbs / hbm_peak, "traffic": traffic, "kernel_ms": ms,
+                     "kernel_share_of_step": ms / step_ms,
+                     "note": f"algorithmic {alg_bytes} B/eval x {bs} evals per launch / CUDA-event time of the kernel; peak {which}. "
+                             "The kernel is FP32-issue bound, not HBM bound (DESIGN.md 3.1): see roofline_fp32"},
+        "fp32": {"bound": "fp32_fma", "kernel": name, "achieved": alg_flops * bs / (ms * 1e-3) / 1e12, "peak": fp32_peak,
+                 "unit": "TFLOP/s", "frac": alg_flops * bs / (ms * 1e-3) / 1e12 / fp32_peak,
+                 "note": "nominal hand-counted flops/eval (FMA=2) of the same kernel; peak = 148 SM x 128 lanes x 2 x max SM clock (derived, not measured)",
+                 "whole_step": {"achieved": 34e6 * bs / (step_ms * 1e-3) / 1e12, "frac": 34e6 * bs / (step_ms * 1e-3) / 1e12 / fp32_peak,
+                                "flops_per_eval": 34e6}},
     }
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     args = ap.parse_args()

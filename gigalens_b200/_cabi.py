@@ -95,7 +95,7 @@ EXPORTED_SYMBOLS = [
     "gl_plan_create", "gl_plan_set_likelihood", "gl_plan_set_prior", "gl_plan_destroy", "gl_last_error",
     "gl_abi_version", "gl_launch_count", "gl_simulate", "gl_simulate_ss", "gl_beta", "gl_eval_points",
     "gl_loglike_grad", "gl_logprob_grad", "gl_unconstrain", "gl_logprob_grad_host", "gl_simulate_host",
-    "gl_lstsq_simulate", "gl_lstsq_loglike_grad", "gl_plan_depth", "gl_plan_set_option",
+    "gl_lstsq_simulate", "gl_lstsq_loglike_grad", "gl_plan_depth", "gl_plan_set_option", "gl_plan_get_timings",
 ]
 
 _LIB = None
@@ -127,6 +127,7 @@ def load():
     lib.gl_plan_set_likelihood.argtypes = [vp, C.POINTER(LikeConfig)]
     lib.gl_plan_set_prior.argtypes = [vp, C.POINTER(PriorLeaf), i32]
     lib.gl_plan_set_option.argtypes = [vp, C.c_char_p, i32]
+    lib.gl_plan_get_timings.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int32)]
     lib.gl_plan_destroy.argtypes = [vp]
     lib.gl_plan_destroy.restype = None
     lib.gl_simulate.argtypes = [vp, fp, fp, vp]

@@ -469,6 +469,9 @@ struct gl_plan {
   int lstsq = 0;
   int no_deflection = 0;
   int use_packed = 1;
+  // optional per-stage timing with CUDA events on the launch stream (bench.py roofline)
+  int tm_slots = 0, tm_calls = 0, tm_have0 = 0;
+  std::vector<cudaEvent_t> tm_ev;   // [tm_slots][GL_NSTAGE + 1]
   int lq_chunk = 0;
   int lq_chunk_req = 0;
   float* d_comps = nullptr; float* d_R = nullptr; float* d_gram = nullptr; float* d_coef = nullptr; float* d_w = nullptr;
@@ -487,6 +490,7 @@ static void gl_free_plan(gl_plan* p) {
   if (p->d_leaves) cudaFree(p->d_leaves);
   if (p->d_amp_slot) cudaFree(p->d_amp_slot);
   if (p->d_perm) cudaFree(p->d_perm);
+  for (cudaEvent_t e : p->tm_ev) cudaEventDestroy(e);
   if (p->d_tables) cudaFree(p->d_tables);
   delete p;
 }
@@ -511,6 +515,13 @@ static const unsigned kFeatSets[] = {GL_FS0, GL_FS1, GL_FS2, GL_FS3};
     case 2: { constexpr unsigned F = GL_FS2; __VA_ARGS__; } break; \
     default: { constexpr unsigned F = GL_FS3; __VA_ARGS__; } break; \
   }
+
+#define GL_NSTAGE 7   // unconstrain, prep, raytrace_fwd, conv_fwd, conv_bwd, raytrace_bwd, sample_bwd
+#define GL_TM(p, st, k)                                                                         \
+  do {                                                                                           \
+    if ((p)->tm_slots > 0)                                                                       \
+      cudaEventRecord((p)->tm_ev[(size_t)((p)->tm_calls % (p)->tm_slots) * (GL_NSTAGE + 1) + (k)], st); \
+  } while (0)
 
 static const int kConvA[] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 11, 13, 16, 20, 25, 32};
 
@@ -721,6 +732,16 @@ int gl_plan_set_option(gl_plan* p, const char* name, int32_t value) {
   if (!strcmp(name, "epl_batch_max")) { p->epl_batch_max = value; return 0; }
   if (!strcmp(name, "lstsq")) { p->lstsq = value; return 0; }
   if (!strcmp(name, "no_deflection")) { p->no_deflection = value; return 0; }
+  if (!strcmp(name, "timing")) {   // value = number of calls to keep event sets for (0 = off)
+    for (cudaEvent_t e : p->tm_ev) cudaEventDestroy(e);
+    p->tm_ev.clear(); p->tm_slots = 0; p->tm_calls = 0;
+    if (value > 0) {
+      p->tm_ev.resize((size_t)value * (GL_NSTAGE + 1));
+      for (auto& e : p->tm_ev) if (cudaEventCreate(&e) != cudaSuccess) return gl_fail("gl_plan_set_option: cudaEventCreate failed");
+      p->tm_slots = value;
+    }
+    return 0;
+  }
   if (!strcmp(name, "packed_math")) { p->use_packed = value; return 0; }   // 0: scalar-lane kernels (A/B testing)
   if (!strcmp(name, "lstsq_chunk")) {   // samples per pass of the lstsq component stack (0 = size by memory budget)
     if (p->d_comps) return gl_fail("gl_plan_set_option: lstsq_chunk must be set before the first lstsq call");
@@ -941,18 +962,48 @@ static int gl_loglike_core(gl_plan* p, const float* params, float* loglike, floa
   if (!p->has_like) return gl_fail("log-likelihood requested but gl_plan_set_likelihood was never called");
   if (p->lstsq) return gl_lstsq_loglike_core(p, params, loglike, red_chi2, dparams, z, logp, dz, st);
   const bool grad = dparams != nullptr;
+  GL_TM(p, st, 1);
   if (gl_run_prep(p, params, st)) return 1;
+  GL_TM(p, st, 2);
   if (gl_run_raytrace_fwd(p, p->d_ss, p->no_deflection, st)) return 1;
+  GL_TM(p, st, 3);
   if (gl_run_conv_fwd(p, p->d_ss, p->conversion_factor, p->d_img, true, grad ? p->d_gimg : nullptr, st)) return 1;
+  GL_TM(p, st, 4);
   if (grad) {
     if (gl_run_conv_bwd(p, p->d_gimg, p->conversion_factor, p->d_ss, st)) return 1;
+    GL_TM(p, st, 5);
     if (gl_run_raytrace_bwd(p, p->d_ss, p->no_deflection, st)) return 1;
+  } else {
+    GL_TM(p, st, 5);
   }
+  GL_TM(p, st, 6);
   const int tb = 128, gb = (p->bs + tb - 1) / tb;
   k_sample_bwd<<<gb, tb, 0, st>>>(p->prog, p->bs, params, p->d_member_factor, p->d_amp_slot, p->d_derived, p->d_gpart, p->chunks, p->d_gsum,
                                   p->d_like_part, p->gf.tiles_x * p->gf.tiles_y, p->n_pix_used, loglike, red_chi2, dparams,
                                   p->d, p->d_leaves, z, z ? p->d_logprior : nullptr, logp, dz);
   GL_LAUNCH_CHECK("k_sample_bwd");
+  GL_TM(p, st, 7);
+  if (p->tm_slots > 0) p->tm_calls++;
+  return 0;
+}
+
+/* Sum of per-stage device times (ms) over the calls recorded since "timing" was switched on; stages:
+ * unconstrain, prep, raytrace_fwd, conv_fwd, conv_bwd, raytrace_bwd, sample_bwd.  Synchronises. */
+int gl_plan_get_timings(gl_plan* p, float* ms_out, int32_t* ncalls_out) {
+  if (!p || !ms_out) return gl_fail("gl_plan_get_timings: NULL argument");
+  GL_CUDA(cudaSetDevice(p->device));
+  GL_CUDA(cudaDeviceSynchronize());
+  for (int k = 0; k < GL_NSTAGE; ++k) ms_out[k] = 0.f;
+  const int n = p->tm_calls < p->tm_slots ? p->tm_calls : p->tm_slots;
+  for (int c = 0; c < n; ++c)
+    for (int k = 0; k < GL_NSTAGE; ++k) {
+      float ms = 0.f;
+      const cudaEvent_t* ev = &p->tm_ev[(size_t)c * (GL_NSTAGE + 1)];
+      if (k == 0) { if (!p->tm_have0) continue; }
+      if (cudaEventElapsedTime(&ms, ev[k], ev[k + 1]) == cudaSuccess) ms_out[k] += ms;
+    }
+  if (ncalls_out) *ncalls_out = n;
+  p->tm_calls = 0;
   return 0;
 }
 
@@ -979,6 +1030,8 @@ int gl_logprob_grad(gl_plan* p, const float* z_dev, float* logp_dev, float* red_
   GL_CUDA(cudaSetDevice(p->device));
   cudaStream_t st = (cudaStream_t)stream;
   const int tb = 128, gb = (p->bs + tb - 1) / tb;
+  GL_TM(p, st, 0);
+  p->tm_have0 = 1;
   k_unconstrain<<<gb, tb, 0, st>>>(p->bs, p->d, p->d_leaves, z_dev, p->d_params, p->d_logprior);
   GL_LAUNCH_CHECK("k_unconstrain");
   return gl_loglike_core(p, p->d_params, nullptr, red_chi2_dev, dz_dev ? p->d_dparams : nullptr, z_dev, logp_dev, dz_dev, st);

@@ -127,6 +127,11 @@ int gl_plan_set_prior(gl_plan* plan, const gl_prior_leaf* leaves, int32_t n_leav
  * tf/simulator.py:125-126).  "lstsq" = 1: the log-likelihood entry points use the linear-amplitude solve
  * (BackwardProbModel, tf/model.py:242-273). */
 int gl_plan_set_option(gl_plan* plan, const char* name, int32_t value);
+/* Measurement aid: after gl_plan_set_option(plan, "timing", n) every log-likelihood call records CUDA
+ * events around its kernels on the launch stream; this returns the summed device time (ms) of the 7
+ * stages (unconstrain, prep, raytrace_fwd, conv_fwd, conv_bwd, raytrace_bwd, sample_bwd) over the last
+ * <= n calls and resets the counter.  Synchronises the device. */
+int gl_plan_get_timings(gl_plan* plan, float* ms_out, int32_t* ncalls_out);
 void gl_plan_destroy(gl_plan* plan);
 const char* gl_last_error(void);
 int32_t gl_abi_version(void);
