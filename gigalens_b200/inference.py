@@ -182,7 +182,7 @@ class ModellingSequence:
             # log q(z(eps)) = -|eps|^2/2 - sum log L_ii - d/2 log 2pi.  The hot-path gradient enters
             # through the surrogate term <stop_grad(dlogp/dz), z>.
             logq = -0.5 * (eps ** 2).sum(1) - torch.log(torch.diagonal(L)).sum() - 0.5 * d * math.log(2 * math.pi)
-            good = torch.isfinite(logp)
+            good = torch.isfinite(logp) & torch.isfinite(dz).all(1)    # drop samples whose value or gradient is not finite
             dz = torch.where(good[:, None], dz, torch.zeros_like(dz))
             surrogate = (logq.sum() - (dz * z).sum()) / n_vi
             (g,) = torch.autograd.grad(surrogate, theta)
@@ -192,7 +192,7 @@ class ModellingSequence:
                 dist.all_reduce(packed)   # the one collective of SVI: [ELBO, grad_mu, grad_L]
             losses.append(float(packed[0]))
             with torch.no_grad():
-                optimizer.step(theta, packed[1:])
+                optimizer.step(theta, torch.nan_to_num(packed[1:], nan=0.0, posinf=0.0, neginf=0.0))
         m, L = build(theta.detach())
         return SurrogateMVN(m, L), losses
 
@@ -216,7 +216,13 @@ class ModellingSequence:
         gen = torch.Generator(device=dev)
         gen.manual_seed(seed * 1000003 + rank)
         cov = q_z.covariance().to(dev)
-        Lc = torch.linalg.cholesky(cov)
+        if not bool(torch.isfinite(cov).all()):
+            raise FloatingPointError("HMC: the surrogate covariance is not finite (SVI diverged)")
+        cov = 0.5 * (cov + cov.T)
+        Lc, info = torch.linalg.cholesky_ex(cov)
+        if int(info) != 0:   # fp32 round-off on a nearly singular surrogate: add a relative jitter
+            cov = cov + 1e-6 * torch.diag(torch.diagonal(cov))
+            Lc = torch.linalg.cholesky(cov)
         d = cov.shape[0]
         z = q_z.sample(nloc, generator=gen).to(dev)
         logp, _, grad = pm.log_prob_and_grad(sim, z)

@@ -288,3 +288,29 @@ def test_lstsq_chunked_passes_match_single_pass():
         outs[-1].append(sim.lstsq_simulate(pmod.bij_forward(sim, z), wl["observed"], pmod.err_map).cpu().numpy())
     for a, b in zip(*outs):
         assert np.array_equal(a, b)
+
+
+def test_lstsq_rank_deficient_uses_pinv_cut():
+    """Two identical linear components make X^T X singular: the rcond = 1e-6 cut of tf.linalg.pinv is
+    active and the minimum-norm amplitudes split evenly between the twins (general Jacobi path)."""
+    bs = 3
+    fixed = dict(R_sersic=0.9, n_sersic=3.0, e1=0.05, e2=-0.1, center_x=0.02, center_y=-0.03)
+    wl = workloads.c3_workload(n_max=3)
+    pm = PhysicalModel(wl["phys_model"].lenses, [sersic.SersicEllipse(use_lstsq=True), sersic.SersicEllipse(use_lstsq=True)],
+                       wl["phys_model"].source_light, lens_light_constants=[dict(fixed), dict(fixed)])
+    sim = LensSimulator(pm, wl["sim_config"], bs=bs)
+    pmod = BackwardProbModel(wl["prior"], wl["observed"], wl["background_rms"], wl["exp_time"])
+    z = pmod.bij_inverse(wl["prior"].sample(bs, seed=4))
+    params = pmod.bij_forward(sim, torch.as_tensor(z, device="cuda"))
+    params["lens_light"] = [{}, {}]
+    coef = sim.lstsq_simulate(params, wl["observed"], pmod.err_map, return_coeffs=True).cpu().numpy()
+    img = sim.lstsq_simulate(params, wl["observed"], pmod.err_map).cpu().numpy()
+    assert np.allclose(coef[:, 0], coef[:, 1], rtol=1e-4)          # twins share the amplitude
+    wl2 = dict(wl, phys_model=pm)
+    osim, opm = oracle_bridge.build_oracle_backward(wl2, bs, torch.float64)
+    p, _ = opm.prior.forward(torch.as_tensor(z.astype(np.float64)))
+    p["lens_light"] = [{}, {}]
+    rc = osim.lstsq_simulate(p, opm.observed_image, opm.err_map, return_coeffs=True).numpy()
+    ri = osim.lstsq_simulate(p, opm.observed_image, opm.err_map).numpy()
+    assert rel_max(img, ri) < 1e-5
+    assert np.max(np.abs(coef - rc)) / np.max(np.abs(rc)) < 1e-4
