@@ -118,5 +118,6 @@ inline std::string gl_build_program(const gl_model_desc* m, GlBuilt& out, bool u
   P.der_total = (der + 3) & ~3;
   P.g_total = g;
   P.depth = depth;
+  P.comp_mask = 3;
   return "";
 }

@@ -732,6 +732,10 @@ int gl_plan_set_option(gl_plan* p, const char* name, int32_t value) {
   if (!strcmp(name, "epl_batch_max")) { p->epl_batch_max = value; return 0; }
   if (!strcmp(name, "lstsq")) { p->lstsq = value; return 0; }
   if (!strcmp(name, "no_deflection")) { p->no_deflection = value; return 0; }
+  if (!strcmp(name, "components")) {   // gl_simulate only: 1 = lens light, 2 = source light, 3 = both
+    if (value < 1 || value > 3) return gl_fail("gl_plan_set_option: components must be 1, 2 or 3");
+    p->prog.comp_mask = value; return 0;
+  }
   if (!strcmp(name, "timing")) {   // value = number of calls to keep event sets for (0 = off)
     for (cudaEvent_t e : p->tm_ev) cudaEventDestroy(e);
     p->tm_ev.clear(); p->tm_slots = 0; p->tm_calls = 0;

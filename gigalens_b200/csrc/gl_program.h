@@ -41,6 +41,7 @@ struct GlProgram {
   int n_params;    // P
   int depth;       // number of linear light components (lstsq)
   int has_fwdmode; // some scaling-relation group is differentiated in forward mode
+  int comp_mask;   // which light groups gl_pix_image adds: bit 0 lens light, bit 1 source light (simulate_* variants)
   GlProf prof[GL_MAX_PROF];
 };
 
@@ -208,6 +209,7 @@ GL_HD void gl_pix_image(const GlProgram& P, const typename gl_scalar_of<T>::type
   for (int i = P.n_lens; i < P.n_prof; ++i) {
     const GlProf& pr = P.prof[i];
     const bool src = i >= P.n_lens + P.n_ll;
+    if (!(P.comp_mask & (src ? 2 : 1))) continue;
     const T* px = src ? bx : x;
     const T* py = src ? by : y;
     switch (pr.type) {

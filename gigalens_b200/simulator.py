@@ -300,6 +300,32 @@ class LensSimulator(LensSimulatorInterface):
                 self.set_option("no_deflection", 0)
         return img.squeeze()
 
+    def _simulate_variant(self, params, components, no_deflection, missing_ok):
+        torch = self._torch
+        mat = self._params_matrix(params, missing_ok)
+        n = self.numPix
+        img = torch.empty((self.bs, n, n), dtype=torch.float32, device=self.device)
+        self.set_option("components", components)
+        self.set_option("no_deflection", int(no_deflection))
+        try:
+            _cabi.check(self._lib.gl_simulate(self._plan, mat.data_ptr(), img.data_ptr(), self._stream()), self._lib)
+        finally:
+            self.set_option("components", 3)
+            self.set_option("no_deflection", 0)
+        return img.squeeze()
+
+    def simulate_source(self, params):
+        """``tf/simulator.py:242-266``: the unlensed source light (evaluated at the image-plane grid)."""
+        return self._simulate_variant(params, 2, True, ("lens_mass", "lens_light"))
+
+    def simulate_lens_light(self, params):
+        """``tf/simulator.py:268-293``."""
+        return self._simulate_variant(params, 1, True, ("lens_mass", "source_light"))
+
+    def simulate_images(self, params):
+        """``tf/simulator.py:295-328``: the lensed source only."""
+        return self._simulate_variant(params, 2, False, ("lens_light",))
+
     def simulate_ss(self, params):
         """Supersampled pre-convolution image ``(bs, n*ss, n*ss)`` (``tf/simulator.py:124-141``)."""
         torch = self._torch

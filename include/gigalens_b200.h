@@ -124,7 +124,9 @@ int gl_plan_set_prior(gl_plan* plan, const gl_prior_leaf* leaves, int32_t n_leav
 /* Options.  "epl_batch_max" = 1: EPL series length from the batch maximum of f exactly like
  * tf/profiles/mass/epl.py:37 (default 0: per-sample length, identical to fp32 rounding).
  * "no_deflection" = 1: evaluate source light at the image-plane position (simulate(..., no_deflection=True),
- * tf/simulator.py:125-126).  "lstsq" = 1: the log-likelihood entry points use the linear-amplitude solve
+ * tf/simulator.py:125-126).  "components" = 1 | 2 | 3: gl_simulate adds only the lens light / only the
+ * source light / both (simulate_lens_light, simulate_images, simulate_source: tf/simulator.py:242-328).
+ * "lstsq" = 1: the log-likelihood entry points use the linear-amplitude solve
  * (BackwardProbModel, tf/model.py:242-273). */
 int gl_plan_set_option(gl_plan* plan, const char* name, int32_t value);
 /* Measurement aid: after gl_plan_set_option(plan, "timing", n) every log-likelihood call records CUDA

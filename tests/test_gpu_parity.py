@@ -314,3 +314,20 @@ def test_lstsq_rank_deficient_uses_pinv_cut():
     ri = osim.lstsq_simulate(p, opm.observed_image, opm.err_map).numpy()
     assert rel_max(img, ri) < 1e-5
     assert np.max(np.abs(coef - rc)) / np.max(np.abs(rc)) < 1e-4
+
+
+def test_simulate_variants_add_up():
+    """simulate_lens_light + simulate_images == simulate; simulate_source == simulate(no_deflection)
+    minus the lens light (tf/simulator.py:242-328)."""
+    wl = workloads.c2_workload()
+    bs = 3
+    sim = LensSimulator(wl["phys_model"], wl["sim_config"], bs=bs)
+    params = wl["prior"].sample(bs, seed=6)
+    full = sim.simulate(params).cpu().numpy()
+    ll = sim.simulate_lens_light(params).cpu().numpy()
+    im = sim.simulate_images(params).cpu().numpy()
+    src = sim.simulate_source(params).cpu().numpy()
+    nod = sim.simulate(params, no_deflection=True).cpu().numpy()
+    assert np.allclose(ll + im, full, rtol=1e-5, atol=1e-5 * np.abs(full).max())
+    assert np.allclose(src + ll, nod, rtol=1e-5, atol=1e-5 * np.abs(nod).max())
+    assert not np.allclose(nod, full, rtol=1e-3)
