@@ -142,7 +142,7 @@ struct GlLikeArgs {
 //   grid = tiles_x * tiles_y * n_images (tile fastest), block = ntx*nty threads (rounded up to a warp multiple)
 //   part [bs][tiles][2] = (chi2, normalization) partial sums of this tile
 template <int A>
-__global__ void __launch_bounds__(256, 2) k_conv_fwd(GlConvGeom g, const float* __restrict__ ss_img, const float* __restrict__ wts,
+__global__ void __maxnreg__(96) k_conv_fwd(GlConvGeom g, const float* __restrict__ ss_img, const float* __restrict__ wts,
                                                   float scale, float* __restrict__ img, GlLikeArgs like,
                                                   float* __restrict__ part, float* __restrict__ gimg) {
   extern __shared__ __align__(16) float smem[];
@@ -169,16 +169,34 @@ __global__ void __launch_bounds__(256, 2) k_conv_fwd(GlConvGeom g, const float* 
     const int sy = (pyi + g.pad) / g.ss, sx = (pxi + g.pad) / g.ss;
     const float* src = src_b + (size_t)q * g.n * g.n;
     const unsigned buf_u32 = (unsigned)__cvta_generic_to_shared(buf);
-    for (int li = warp; li < g.in_rows; li += nw) {
-      const int ri = oy0 + li - sy;
-      const bool row_ok = ri >= 0 && ri < g.n;
-      const float* srow = src + (size_t)min(max(ri, 0), g.n - 1) * g.n;
-      const unsigned drow = buf_u32 + (unsigned)(li * g.in_pitch) * 4u;
-      for (int lj = lane; lj < g.in_pitch; lj += 32) {
-        const int cj = ox0 + lj - sx;
-        const bool ok = row_ok && cj >= 0 && cj < g.n;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(drow + 4u * lj), "l"(srow + min(max(cj, 0), g.n - 1)),
-                     "r"(ok ? 4u : 0u) : "memory");
+    if (((g.n | ox0 | sx) & 1) == 0) {
+      // 8-byte copies: n, ox0 and the phase shift are even, so element pairs are aligned on both sides
+      // and lie entirely inside or entirely outside the image.  Per-lane column bookkeeping is hoisted.
+      const int npair = g.in_pitch >> 1;
+      const int cj0 = ox0 - sx + 2 * lane;          // image column of this lane's first pair
+      for (int li = warp; li < g.in_rows; li += nw) {
+        const int ri = oy0 + li - sy;
+        const bool row_ok = ri >= 0 && ri < g.n;
+        const float* srow = src + (size_t)min(max(ri, 0), g.n - 1) * g.n;
+        const unsigned drow = buf_u32 + (unsigned)(li * g.in_pitch) * 4u + 8u * lane;
+        for (int pj = lane, cj = cj0, k = 0; pj < npair; pj += 32, cj += 64, ++k) {
+          const bool ok = row_ok && cj >= 0 && cj < g.n;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(drow + 256u * k), "l"(srow + min(max(cj, 0), g.n - 2)),
+                       "r"(ok ? 8u : 0u) : "memory");
+        }
+      }
+    } else {
+      for (int li = warp; li < g.in_rows; li += nw) {
+        const int ri = oy0 + li - sy;
+        const bool row_ok = ri >= 0 && ri < g.n;
+        const float* srow = src + (size_t)min(max(ri, 0), g.n - 1) * g.n;
+        const unsigned drow = buf_u32 + (unsigned)(li * g.in_pitch) * 4u;
+        for (int lj = lane; lj < g.in_pitch; lj += 32) {
+          const int cj = ox0 + lj - sx;
+          const bool ok = row_ok && cj >= 0 && cj < g.n;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(drow + 4u * lj), "l"(srow + min(max(cj, 0), g.n - 1)),
+                       "r"(ok ? 4u : 0u) : "memory");
+        }
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
