@@ -234,7 +234,7 @@ def run_cuda(args):
     if rank != 0:
         return
     cpu = None
-    if world == 1 or True:
+    if world == 1:  # the CPU baseline is reported at N=1 only (rank 0)
         rate, med, cores = cpu_reference_rate(32, 3)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "bs=32 slice of the batch, median of 3 (torch-CPU fp32 oracle port with autograd)"}

@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_fwd(GlProgram P, int n
                                                               const float* __restrict__ grid_y,
                                                               const unsigned char* __restrict__ ss_mask,
                                                               const float* __restrict__ derived, int no_deflection,
-                                                              float* __restrict__ ss_img) {
+                                                              float* __restrict__ ss_img, int* __restrict__ nan_count) {
   extern __shared__ __align__(16) float s_der[];
   const int b = blockIdx.y;
   const float* dsrc = derived + (size_t)b * P.der_total;
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_fwd(GlProgram P, int n
     for (int j = 0; j < PPT; ++j) {
       if (pix[j] < npix) {
         float o = v[j];
-        if (o != o) o = 0.f;                                   // tf.where(is_nan(img), 0, img)  (tf/simulator.py:140)
+        if (o != o) { o = 0.f; if (nan_count) atomicAdd(nan_count + b, 1); }   // tf.where(is_nan(img), 0, img)  (tf/simulator.py:140)
         if (ss_mask && !ss_mask[pix[j]]) o = 0.f;              // pixels outside pix_region are never evaluated (:34-44)
         dst[pix[j]] = o;
       }
@@ -258,7 +258,8 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_bwd(GlProgram P, int n
                                                               const float* __restrict__ grid_y,
                                                               const unsigned char* __restrict__ ss_mask,
                                                               const float* __restrict__ derived, int no_deflection,
-                                                              const float* __restrict__ gss, float* __restrict__ gpart) {
+                                                              const float* __restrict__ gss, float* __restrict__ gpart,
+                                                              const int* __restrict__ nan_count) {
   extern __shared__ __align__(16) float smem[];
   float* s_der = smem;                               // [der_total]
   float* s_acc = smem + P.der_total;                 // [nwarps][g_total]
@@ -269,6 +270,7 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_bwd(GlProgram P, int n
   for (int i = threadIdx.x; i < nw * P.g_total; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
   DevFlush flush{s_acc + warp * P.g_total, lane};
+  const bool had_nan = nan_count && nan_count[b] > 0;
   const int per_batch = GLK_THREADS * PPT;
   const int nbatch = (npix + per_batch - 1) / per_batch;
   const float* gsrc = gss + (size_t)b * npix;
@@ -281,6 +283,12 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_bwd(GlProgram P, int n
       const int p = pix < npix ? pix : 0;
       x[j] = __ldg(grid_x + p); y[j] = __ldg(grid_y + p);
       gs[j] = ok ? __ldg(gsrc + p) : 0.f;
+    }
+    if (had_nan) {   // tf.where(is_nan(img), 0, img): a scrubbed pixel passes no gradient (rare: re-evaluate the forward)
+      float v[PPT];
+      gl_pix_image<float, PPT, F>(P, s_der, x, y, no_deflection != 0, v);
+#pragma unroll
+      for (int j = 0; j < PPT; ++j) if (v[j] != v[j]) gs[j] = 0.f;
     }
     gl_pix_image_bwd<float, PPT, F>(P, s_der, x, y, gs, no_deflection != 0, flush);
   }
@@ -301,7 +309,7 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_fwd_p(GlProgram P, int
                                                                 const float* __restrict__ grid_y,
                                                                 const unsigned char* __restrict__ ss_mask,
                                                                 const float* __restrict__ derived, int no_deflection,
-                                                                float* __restrict__ ss_img) {
+                                                                float* __restrict__ ss_img, int* __restrict__ nan_count) {
   extern __shared__ __align__(16) float s_der[];
   const int b = blockIdx.y;
   const float* dsrc = derived + (size_t)b * P.der_total;
@@ -329,8 +337,8 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_fwd_p(GlProgram P, int
     for (int j = 0; j < NV; ++j) {
       if (pr[j] < npair) {
         float o0 = v[j].x, o1 = v[j].y;
-        if (o0 != o0) o0 = 0.f;
-        if (o1 != o1) o1 = 0.f;
+        if (o0 != o0) { o0 = 0.f; if (nan_count) atomicAdd(nan_count + b, 1); }
+        if (o1 != o1) { o1 = 0.f; if (nan_count) atomicAdd(nan_count + b, 1); }
         if (ss_mask) { if (!ss_mask[2 * pr[j]]) o0 = 0.f; if (!ss_mask[2 * pr[j] + 1]) o1 = 0.f; }
         dst[pr[j]] = make_float2(o0, o1);
       }
@@ -343,7 +351,8 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_bwd_p(GlProgram P, int
                                                                 const float* __restrict__ grid_y,
                                                                 const unsigned char* __restrict__ ss_mask,
                                                                 const float* __restrict__ derived, int no_deflection,
-                                                                const float* __restrict__ gss, float* __restrict__ gpart) {
+                                                                const float* __restrict__ gss, float* __restrict__ gpart,
+                                                                const int* __restrict__ nan_count) {
   extern __shared__ __align__(16) float smem[];
   float* s_der = smem;
   float* s_acc = smem + P.der_total;
@@ -354,6 +363,7 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_bwd_p(GlProgram P, int
   for (int i = threadIdx.x; i < nw * P.g_total; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
   DevFlush flush{s_acc + warp * P.g_total, lane};
+  const bool had_nan = nan_count && nan_count[b] > 0;
   constexpr int NV = PPT / 2;
   const int npair = npix >> 1;
   const int per_batch = GLK_THREADS * NV;
@@ -373,6 +383,12 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_bwd_p(GlProgram P, int
       float2 gv = in ? __ldg(gsrc + p) : make_float2(0.f, 0.f);
       if (ss_mask && in) { if (!ss_mask[2 * p]) gv.x = 0.f; if (!ss_mask[2 * p + 1]) gv.y = 0.f; }
       gs[j] = GlF2(gv.x, gv.y);
+    }
+    if (had_nan) {
+      GlF2 v[NV];
+      gl_pix_image<GlF2, NV, F>(P, s_der, x, y, no_deflection != 0, v);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) { if (v[j].x != v[j].x) gs[j].x = 0.f; if (v[j].y != v[j].y) gs[j].y = 0.f; }
     }
     gl_pix_image_bwd<GlF2, NV, F>(P, s_der, x, y, gs, no_deflection != 0, flush);
   }
@@ -436,6 +452,7 @@ struct gl_plan {
   float* d_member_factor = nullptr;
   int* d_amp_slot = nullptr;
   int* d_perm = nullptr;
+  int* d_nan = nullptr;      // [bs] NaN-scrubbed ss pixels of the last forward pass
   float* d_tables = nullptr;
   float* d_wf = nullptr; float* d_wb = nullptr;     // forward / flipped taps [nph][A][wpitch]
   int A = 1, pad = 0;
@@ -490,6 +507,7 @@ static void gl_free_plan(gl_plan* p) {
   if (p->d_leaves) cudaFree(p->d_leaves);
   if (p->d_amp_slot) cudaFree(p->d_amp_slot);
   if (p->d_perm) cudaFree(p->d_perm);
+  if (p->d_nan) cudaFree(p->d_nan);
   for (cudaEvent_t e : p->tm_ev) cudaEventDestroy(e);
   if (p->d_tables) cudaFree(p->d_tables);
   delete p;
@@ -720,6 +738,7 @@ int gl_plan_create(const gl_model_desc* model, const gl_sim_config* sim, int32_t
   GL_TRY(cudaMalloc((void**)&p->d_gpart, (size_t)bs * p->chunks * (p->prog.g_total + 1) * sizeof(float)));
   GL_TRY(cudaMalloc((void**)&p->d_gsum, (size_t)bs * (p->prog.g_total + 1) * sizeof(float)));
   GL_TRY(cudaMalloc((void**)&p->d_logprior, (size_t)bs * sizeof(float)));
+  GL_TRY(cudaMalloc((void**)&p->d_nan, (size_t)bs * sizeof(int)));
   GL_TRY(cudaMalloc((void**)&p->d_fmax, GL_MAX_PROF * sizeof(float)));
   GL_TRY(cudaMemset(p->d_logprior, 0, (size_t)bs * sizeof(float)));
 #undef GL_TRY
@@ -831,18 +850,19 @@ static int gl_run_prep(gl_plan* p, const float* params, cudaStream_t st) {
 
 static int gl_run_raytrace_fwd(gl_plan* p, float* ss_out, int no_deflection, cudaStream_t st) {
   dim3 grid(p->chunks, p->bs);
+  GL_CUDA(cudaMemsetAsync(p->d_nan, 0, (size_t)p->bs * sizeof(int), st));
   const size_t smem = (size_t)p->prog.der_total * sizeof(float);
   if (p->feat_idx == 0 && (p->npix % 2) == 0 && p->use_packed) {
     if (smem > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_fwd_p<4, GL_FS0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_raytrace_fwd_p<4, GL_FS0><<<grid, GLK_THREADS, smem, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,
-                                                                 p->d_derived, no_deflection, ss_out);
+                                                                 p->d_derived, no_deflection, ss_out, p->d_nan);
     GL_LAUNCH_CHECK("k_raytrace_fwd_p");
     return 0;
   }
   GL_FEAT_DISPATCH(p->feat_idx, {
     if (smem > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_fwd<4, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_raytrace_fwd<4, F><<<grid, GLK_THREADS, smem, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask, p->d_derived,
-                                                          no_deflection, ss_out);
+                                                          no_deflection, ss_out, p->d_nan);
   })
   GL_LAUNCH_CHECK("k_raytrace_fwd");
   return 0;
@@ -854,14 +874,14 @@ static int gl_run_raytrace_bwd(gl_plan* p, const float* gss, int no_deflection, 
   if (p->feat_idx == 0 && (p->npix % 2) == 0 && p->use_packed) {
     if (smem > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_bwd_p<4, GL_FS0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_raytrace_bwd_p<4, GL_FS0><<<grid, GLK_THREADS, smem, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,
-                                                                 p->d_derived, no_deflection, gss, p->d_gpart);
+                                                                 p->d_derived, no_deflection, gss, p->d_gpart, p->d_nan);
     GL_LAUNCH_CHECK("k_raytrace_bwd_p");
     return 0;
   }
   GL_FEAT_DISPATCH(p->feat_idx, {
     if (smem > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_bwd<4, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_raytrace_bwd<4, F><<<grid, GLK_THREADS, smem, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask, p->d_derived,
-                                                          no_deflection, gss, p->d_gpart);
+                                                          no_deflection, gss, p->d_gpart, p->d_nan);
   })
   GL_LAUNCH_CHECK("k_raytrace_bwd");
   return 0;

@@ -331,3 +331,31 @@ def test_simulate_variants_add_up():
     assert np.allclose(ll + im, full, rtol=1e-5, atol=1e-5 * np.abs(full).max())
     assert np.allclose(src + ll, nod, rtol=1e-5, atol=1e-5 * np.abs(nod).max())
     assert not np.allclose(nod, full, rtol=1e-3)
+
+
+@pytest.mark.parametrize("packed", [1, 0])
+def test_nan_pixels_are_scrubbed_and_pass_no_gradient(packed):
+    """tf.where(is_nan(img), 0, img) (tf/simulator.py:140): a sample whose source amplitude is NaN
+    gives a zero image, a finite likelihood and no gradient; its neighbours are untouched."""
+    wl = workloads.c2_workload()
+    bs = 4
+    sim = LensSimulator(wl["phys_model"], wl["sim_config"], bs=bs)
+    sim.set_option("packed_math", packed)
+    pmod = ForwardProbModel(wl["prior"], wl["observed"], background_rms=0.2, exp_time=100.0)
+    cm = sim.compiled
+    mat = cm.flatten(wl["prior"].sample(bs, seed=11), bs, torch, "cpu").numpy()
+    clean = [t.cpu().numpy() for t in pmod.loglike_and_grad(sim, torch.as_tensor(mat, device="cuda"))]
+    bad = mat.copy()
+    k_ie = [i for i, k in enumerate(cm.slot_keys) if "source" in str(k) and "Ie" in str(k)][0]
+    bad[k_ie, 1] = np.nan
+    dev = torch.as_tensor(bad, device="cuda")
+    img = sim.simulate(dev).cpu().numpy().reshape(bs, -1)
+    ll, chi2, g = (t.cpu().numpy() for t in pmod.loglike_and_grad(sim, dev))
+    assert np.all(img[1] == 0.0) and np.isfinite(img).all()
+    assert np.isfinite(ll).all() and np.isfinite(chi2).all()
+    assert np.all(g[:, 1] == 0.0)
+    keep = [0, 2, 3]
+    assert np.array_equal(ll[keep], clean[0][keep]) and np.array_equal(g[:, keep], clean[2][:, keep])
+    # and the next clean call is not polluted by the previous one's NaN count
+    again = [t.cpu().numpy() for t in pmod.loglike_and_grad(sim, torch.as_tensor(mat, device="cuda"))]
+    assert np.array_equal(again[2], clean[2])
