@@ -336,7 +336,9 @@ def test_simulate_variants_add_up():
 @pytest.mark.parametrize("packed", [1, 0])
 def test_nan_pixels_are_scrubbed_and_pass_no_gradient(packed):
     """tf.where(is_nan(img), 0, img) (tf/simulator.py:140): a sample whose source amplitude is NaN
-    gives a zero image, a finite likelihood and no gradient; its neighbours are untouched."""
+    gives a zero image and a finite likelihood; the scrubbed pixels pass a zero cotangent, so the lens-light
+    gradient is exactly 0 and everything that multiplies the NaN is NaN - the same pattern autograd gives the
+    oracle; the neighbouring samples are untouched."""
     wl = workloads.c2_workload()
     bs = 4
     sim = LensSimulator(wl["phys_model"], wl["sim_config"], bs=bs)
@@ -353,7 +355,10 @@ def test_nan_pixels_are_scrubbed_and_pass_no_gradient(packed):
     ll, chi2, g = (t.cpu().numpy() for t in pmod.loglike_and_grad(sim, dev))
     assert np.all(img[1] == 0.0) and np.isfinite(img).all()
     assert np.isfinite(ll).all() and np.isfinite(chi2).all()
-    assert np.all(g[:, 1] == 0.0)
+    _, _, _, g_or = oracle_bridge.loglike_and_grad_matrix(wl, cm, bad, torch.float32)
+    assert np.isnan(g_or[:, 1]).any() and np.isnan(g[:, 1]).any()   # 0 * NaN stays NaN in both
+    ll_rows = [i for i, k in enumerate(cm.slot_keys) if k[0] == "lens_light"]
+    assert np.all(g[ll_rows, 1] == 0.0) and np.all(g_or[ll_rows, 1] == 0.0)
     keep = [0, 2, 3]
     assert np.array_equal(ll[keep], clean[0][keep]) and np.array_equal(g[:, keep], clean[2][:, keep])
     # and the next clean call is not polluted by the previous one's NaN count
