@@ -22,6 +22,7 @@
 #include "gl_build.h"
 #include "gl_conv.cuh"
 #include "gl_lstsq.cuh"
+#include "gl_positions.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // error handling / bookkeeping
@@ -132,38 +133,54 @@ __global__ void k_prep(GlProgram P, int bs, const float* __restrict__ params, co
   gl_sample_prep<float, float>(P, params, bs, b, member_factor, amp_slot, epl_fmax, derived + (size_t)b * P.der_total);
 }
 
-// partial sums -> loglike, red_chi2, dparams / dz, logp; one thread per sample.
+// partial sums -> loglike, red_chi2, dparams / dz, logp; one thread per sample.  Combines the pixel
+// likelihood with the image-position likelihood as ForwardProbModel.log_prob does (tf/model.py:150-163):
+// log-likes add, the reduced chi^2 is the mean of the included terms.
 __global__ void k_sample_bwd(GlProgram P, int bs, const float* __restrict__ params, const float* __restrict__ member_factor,
                              const int* __restrict__ amp_slot, const float* __restrict__ derived, const float* __restrict__ gpart, int nchunk,
                              float* __restrict__ gsum /*[bs][g_total] scratch*/, const float* __restrict__ like_part,
                              int ntile, float n_pix_used, float* __restrict__ loglike, float* __restrict__ red_chi2,
                              float* __restrict__ dparams, int d, const GlLeaf* __restrict__ leaves,
                              const float* __restrict__ z, const float* __restrict__ logprior, float* __restrict__ logp,
-                             float* __restrict__ dz) {
+                             float* __restrict__ dz, int include_pixels, const float* __restrict__ pos_ll,
+                             const float* __restrict__ pos_chi2, const float* __restrict__ dpos) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= bs) return;
-  float ll;
-  if (like_part) {
-    float chi2 = 0.f, norm = 0.f;
-    for (int t = 0; t < ntile; ++t) {
-      chi2 += like_part[((size_t)b * ntile + t) * 2];
-      norm += like_part[((size_t)b * ntile + t) * 2 + 1];
+  float ll = 0.f, rc = 0.f;
+  int n_chi = 0;
+  if (include_pixels) {
+    if (like_part) {
+      float chi2 = 0.f, norm = 0.f;
+      for (int t = 0; t < ntile; ++t) {
+        chi2 += like_part[((size_t)b * ntile + t) * 2];
+        norm += like_part[((size_t)b * ntile + t) * 2 + 1];
+      }
+      ll = -0.5f * (chi2 + norm);
+      rc = chi2 / n_pix_used;
+    } else {
+      ll = loglike[b];   // lstsq path: k_lstsq_image already wrote log-like and red chi^2
+      rc = red_chi2 ? red_chi2[b] : 0.f;
     }
-    ll = -0.5f * (chi2 + norm);
-    if (loglike) loglike[b] = ll;
-    if (red_chi2) red_chi2[b] = chi2 / n_pix_used;
-  } else {
-    ll = loglike[b];   // lstsq path: k_lstsq_image already wrote log-like and red chi^2
+    ++n_chi;
   }
+  if (pos_ll) { ll += pos_ll[b]; rc += pos_chi2[b]; ++n_chi; }
+  if (loglike) loglike[b] = ll;
+  if (red_chi2) red_chi2[b] = rc / (float)n_chi;
   if (logp) logp[b] = ll + (logprior ? logprior[b] : 0.f);
   if (!dparams) return;
-  float* g = gsum + (size_t)b * P.g_total;
-  for (int k = 0; k < P.g_total; ++k) {
-    float s = 0.f;
-    for (int c = 0; c < nchunk; ++c) s += gpart[((size_t)b * nchunk + c) * P.g_total + k];
-    g[k] = s;
+  if (include_pixels) {
+    float* g = gsum + (size_t)b * P.g_total;
+    for (int k = 0; k < P.g_total; ++k) {
+      float s = 0.f;
+      for (int c = 0; c < nchunk; ++c) s += gpart[((size_t)b * nchunk + c) * P.g_total + k];
+      g[k] = s;
+    }
+    gl_sample_prep_bwd<float, float>(P, params, bs, b, member_factor, amp_slot, derived + (size_t)b * P.der_total, g, dparams);
+  } else {
+    for (int k = 0; k < P.n_params; ++k) dparams[(size_t)k * bs + b] = 0.f;
   }
-  gl_sample_prep_bwd<float, float>(P, params, bs, b, member_factor, amp_slot, derived + (size_t)b * P.der_total, g, dparams);
+  if (dpos)
+    for (int k = 0; k < P.n_params; ++k) dparams[(size_t)k * bs + b] += dpos[(size_t)k * bs + b];
   if (dz) {
     for (int k = 0; k < d; ++k) {
       const GlLeaf L = leaves[k];
@@ -453,6 +470,13 @@ struct gl_plan {
   int* d_amp_slot = nullptr;
   int* d_perm = nullptr;
   int* d_nan = nullptr;      // [bs] NaN-scrubbed ss pixels of the last forward pass
+  // image-position likelihood (gl_plan_set_positions)
+  int include_pixels = 1, include_positions = 0;
+  int pos_npts = 0, pos_nsys = 0;
+  float pos_n_position = 0.f;
+  int* d_pos_off = nullptr;
+  float* d_pos_x = nullptr; float* d_pos_y = nullptr; float* d_pos_ex = nullptr; float* d_pos_ey = nullptr;
+  float* d_pos_ll = nullptr; float* d_pos_chi = nullptr; float* d_pos_grad = nullptr;   // [bs], [bs], [P][bs]
   float* d_tables = nullptr;
   float* d_wf = nullptr; float* d_wb = nullptr;     // forward / flipped taps [nph][A][wpitch]
   int A = 1, pad = 0;
@@ -508,6 +532,8 @@ static void gl_free_plan(gl_plan* p) {
   if (p->d_amp_slot) cudaFree(p->d_amp_slot);
   if (p->d_perm) cudaFree(p->d_perm);
   if (p->d_nan) cudaFree(p->d_nan);
+  for (void* q : {(void*)p->d_pos_off, (void*)p->d_pos_x, (void*)p->d_pos_y, (void*)p->d_pos_ex, (void*)p->d_pos_ey, (void*)p->d_pos_ll,
+                  (void*)p->d_pos_chi, (void*)p->d_pos_grad}) if (q) cudaFree(q);
   for (cudaEvent_t e : p->tm_ev) cudaEventDestroy(e);
   if (p->d_tables) cudaFree(p->d_tables);
   delete p;
@@ -765,6 +791,11 @@ int gl_plan_set_option(gl_plan* p, const char* name, int32_t value) {
     }
     return 0;
   }
+  if (!strcmp(name, "include_pixels")) { p->include_pixels = value != 0; return 0; }       // ForwardProbModel(include_pixels=...)
+  if (!strcmp(name, "include_positions")) {                                               // ForwardProbModel(include_positions=...)
+    if (value && p->pos_npts == 0) return gl_fail("gl_plan_set_option: include_positions needs gl_plan_set_positions first");
+    p->include_positions = value != 0; return 0;
+  }
   if (!strcmp(name, "packed_math")) { p->use_packed = value; return 0; }   // 0: scalar-lane kernels (A/B testing)
   if (!strcmp(name, "lstsq_chunk")) {   // samples per pass of the lstsq component stack (0 = size by memory budget)
     if (p->d_comps) return gl_fail("gl_plan_set_option: lstsq_chunk must be set before the first lstsq call");
@@ -799,6 +830,39 @@ int gl_plan_set_likelihood(gl_plan* p, const gl_like_config* like) {
     GL_CUDA(gl_upload(&p->d_w, w.data(), nn));
   }
   p->has_like = true;
+  return 0;
+}
+
+
+/* Centroids of the multiply-imaged sources: ForwardProbModel(centroids_x, centroids_y, centroids_errors_x,
+ * centroids_errors_y) (tf/model.py:69-74); host arrays, images of all systems concatenated. */
+int gl_plan_set_positions(gl_plan* p, int32_t n_systems, const int32_t* n_images, const float* x, const float* y,
+                          const float* err_x, const float* err_y) {
+  if (!p || n_systems <= 0 || !n_images || !x || !y || !err_x || !err_y) return gl_fail("gl_plan_set_positions: bad argument");
+  GL_CUDA(cudaSetDevice(p->device));
+  std::vector<int> off(n_systems + 1, 0);
+  for (int s = 0; s < n_systems; ++s) {
+    if (n_images[s] < 1 || n_images[s] > 64) return gl_fail("gl_plan_set_positions: a system needs 1..64 images");
+    off[s + 1] = off[s] + n_images[s];
+  }
+  const int npts = off[n_systems];
+  for (int i = 0; i < npts; ++i)
+    if (!(err_x[i] != 0.f) || !(err_y[i] != 0.f)) return gl_fail("gl_plan_set_positions: centroid errors must be non-zero");
+  for (void** q : {(void**)&p->d_pos_off, (void**)&p->d_pos_x, (void**)&p->d_pos_y, (void**)&p->d_pos_ex, (void**)&p->d_pos_ey})
+    if (*q) { cudaFree(*q); *q = nullptr; }
+  GL_CUDA(gl_upload(&p->d_pos_off, off.data(), off.size()));
+  GL_CUDA(gl_upload(&p->d_pos_x, x, (size_t)npts));
+  GL_CUDA(gl_upload(&p->d_pos_y, y, (size_t)npts));
+  GL_CUDA(gl_upload(&p->d_pos_ex, err_x, (size_t)npts));
+  GL_CUDA(gl_upload(&p->d_pos_ey, err_y, (size_t)npts));
+  if (!p->d_pos_ll) {
+    GL_CUDA(cudaMalloc((void**)&p->d_pos_ll, (size_t)p->bs * sizeof(float)));
+    GL_CUDA(cudaMalloc((void**)&p->d_pos_chi, (size_t)p->bs * sizeof(float)));
+    GL_CUDA(cudaMalloc((void**)&p->d_pos_grad, (size_t)p->bs * (p->prog.n_params > 0 ? p->prog.n_params : 1) * sizeof(float)));
+  }
+  p->pos_npts = npts; p->pos_nsys = n_systems;
+  p->pos_n_position = 2.f * (float)npts;   // n_position = 2 * size(concat(centroids_x))  (tf/model.py:74)
+  p->include_positions = 1;
   return 0;
 }
 
@@ -845,6 +909,21 @@ static int gl_run_prep(gl_plan* p, const float* params, cudaStream_t st) {
   }
   k_prep<<<gb, tb, 0, st>>>(p->prog, p->bs, params, p->d_member_factor, p->d_amp_slot, fmax, p->d_derived);
   GL_LAUNCH_CHECK("k_prep");
+  return 0;
+}
+
+// stats_positions of every sample (one warp per sample, FP64): log-like, chi2/n_position and, when
+// dparams != null, d(log-like)/d(params) [P][bs].
+static int gl_run_positions(gl_plan* p, const float* params, float* loglike, float* red_chi2, float* dparams, cudaStream_t st) {
+  if (p->pos_npts == 0) return gl_fail("image-position likelihood requested but gl_plan_set_positions was never called");
+  const size_t smem = sizeof(double) * ((size_t)p->prog.der_total + 12 * (size_t)p->pos_npts + 2 * (size_t)p->pos_nsys +
+                                        (size_t)(GLP_THREADS + 1) * p->prog.g_total);
+  if (smem > 200 * 1024) return gl_fail("gl_run_positions: model too large for the positions kernel's shared memory");
+  if (smem > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_positions, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_positions<<<p->bs, GLP_THREADS, smem, st>>>(p->prog, p->bs, params, p->d_member_factor, p->d_amp_slot, p->pos_npts, p->pos_nsys,
+                                                p->d_pos_off, p->d_pos_x, p->d_pos_y, p->d_pos_ex, p->d_pos_ey, p->pos_n_position,
+                                                loglike, red_chi2, dparams);
+  GL_LAUNCH_CHECK("k_positions");
   return 0;
 }
 
@@ -979,21 +1058,50 @@ int gl_eval_points(gl_plan* p, const float* params_dev, int32_t npts, const floa
   return 0;
 }
 
+/* LensSimulator.magnification / convergence / shear inputs (tf/simulator.py:80-107): the Hessian
+ * (f_xx, f_xy, f_yx, f_yy) of the summed deflection at npts points shared by all samples; out [bs][npts]. */
+int gl_hessian(gl_plan* p, const float* params_dev, int32_t npts, const float* x_dev, const float* y_dev, float* fxx, float* fxy,
+               float* fyx, float* fyy, void* stream) {
+  if (!p || !params_dev || !x_dev || !y_dev || !fxx || !fxy || !fyx || !fyy || npts <= 0) return gl_fail("gl_hessian: bad argument");
+  GL_CUDA(cudaSetDevice(p->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = (size_t)p->prog.der_total * sizeof(double);
+  if (smem > 200 * 1024) return gl_fail("gl_hessian: model too large");
+  if (smem > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_hessian, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((npts + 127) / 128 > 64 ? 64 : (npts + 127) / 128, p->bs);
+  k_hessian<<<grid, 128, smem, st>>>(p->prog, p->bs, params_dev, p->d_member_factor, p->d_amp_slot, npts, x_dev, y_dev, fxx, fxy, fyx, fyy);
+  GL_LAUNCH_CHECK("k_hessian");
+  return 0;
+}
+
+/* ForwardProbModel.stats_positions alone (tf/model.py:103-124): loglike / red_chi2 [bs], dparams [P][bs] or NULL. */
+int gl_positions_loglike_grad(gl_plan* p, const float* params_dev, float* loglike_dev, float* red_chi2_dev, float* dparams_dev,
+                              void* stream) {
+  if (!p || !params_dev || !loglike_dev || !red_chi2_dev) return gl_fail("gl_positions_loglike_grad: NULL argument");
+  GL_CUDA(cudaSetDevice(p->device));
+  return gl_run_positions(p, params_dev, loglike_dev, red_chi2_dev, dparams_dev, (cudaStream_t)stream);
+}
+
 static int gl_lstsq_loglike_core(gl_plan* p, const float* params, float* loglike, float* red_chi2, float* dparams,
                                  const float* z, float* logp, float* dz, cudaStream_t st);
 static int gl_loglike_core(gl_plan* p, const float* params, float* loglike, float* red_chi2, float* dparams,
                            const float* z, float* logp, float* dz, cudaStream_t st) {
-  if (!p->has_like) return gl_fail("log-likelihood requested but gl_plan_set_likelihood was never called");
-  if (p->lstsq) return gl_lstsq_loglike_core(p, params, loglike, red_chi2, dparams, z, logp, dz, st);
+  const bool pix = p->include_pixels != 0, pos = p->include_positions != 0;
+  if (!pix && !pos) return gl_fail("log-likelihood requested with include_pixels = include_positions = 0");
+  if (pix && !p->has_like) return gl_fail("log-likelihood requested but gl_plan_set_likelihood was never called");
+  if (p->lstsq) {
+    if (pos || !pix) return gl_fail("the lstsq (BackwardProbModel) path has no image-position term (tf/model.py:242-273)");
+    return gl_lstsq_loglike_core(p, params, loglike, red_chi2, dparams, z, logp, dz, st);
+  }
   const bool grad = dparams != nullptr;
   GL_TM(p, st, 1);
-  if (gl_run_prep(p, params, st)) return 1;
+  if (pix && gl_run_prep(p, params, st)) return 1;
   GL_TM(p, st, 2);
-  if (gl_run_raytrace_fwd(p, p->d_ss, p->no_deflection, st)) return 1;
+  if (pix && gl_run_raytrace_fwd(p, p->d_ss, p->no_deflection, st)) return 1;
   GL_TM(p, st, 3);
-  if (gl_run_conv_fwd(p, p->d_ss, p->conversion_factor, p->d_img, true, grad ? p->d_gimg : nullptr, st)) return 1;
+  if (pix && gl_run_conv_fwd(p, p->d_ss, p->conversion_factor, p->d_img, true, grad ? p->d_gimg : nullptr, st)) return 1;
   GL_TM(p, st, 4);
-  if (grad) {
+  if (grad && pix) {
     if (gl_run_conv_bwd(p, p->d_gimg, p->conversion_factor, p->d_ss, st)) return 1;
     GL_TM(p, st, 5);
     if (gl_run_raytrace_bwd(p, p->d_ss, p->no_deflection, st)) return 1;
@@ -1001,10 +1109,12 @@ static int gl_loglike_core(gl_plan* p, const float* params, float* loglike, floa
     GL_TM(p, st, 5);
   }
   GL_TM(p, st, 6);
+  if (pos && gl_run_positions(p, params, p->d_pos_ll, p->d_pos_chi, grad ? p->d_pos_grad : nullptr, st)) return 1;
   const int tb = 128, gb = (p->bs + tb - 1) / tb;
   k_sample_bwd<<<gb, tb, 0, st>>>(p->prog, p->bs, params, p->d_member_factor, p->d_amp_slot, p->d_derived, p->d_gpart, p->chunks, p->d_gsum,
                                   p->d_like_part, p->gf.tiles_x * p->gf.tiles_y, p->n_pix_used, loglike, red_chi2, dparams,
-                                  p->d, p->d_leaves, z, z ? p->d_logprior : nullptr, logp, dz);
+                                  p->d, p->d_leaves, z, z ? p->d_logprior : nullptr, logp, dz, pix ? 1 : 0,
+                                  pos ? p->d_pos_ll : nullptr, pos ? p->d_pos_chi : nullptr, (pos && grad) ? p->d_pos_grad : nullptr);
   GL_LAUNCH_CHECK("k_sample_bwd");
   GL_TM(p, st, 7);
   if (p->tm_slots > 0) p->tm_calls++;
@@ -1162,7 +1272,7 @@ static int gl_lstsq_loglike_core(gl_plan* p, const float* params, float* loglike
   }
   k_sample_bwd<<<gb, tb, 0, st>>>(p->prog, p->bs, params, p->d_member_factor, p->d_amp_slot, p->d_derived, p->d_gpart, p->chunks,
                                   p->d_gsum, nullptr, 0, 1.f, ll, chi, dparams, p->d, p->d_leaves, z,
-                                  z ? p->d_logprior : nullptr, logp, dz);
+                                  z ? p->d_logprior : nullptr, logp, dz, 1, nullptr, nullptr, nullptr);
   GL_LAUNCH_CHECK("k_sample_bwd");
   return 0;
 }

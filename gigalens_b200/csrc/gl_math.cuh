@@ -170,6 +170,62 @@ GL_HD float gl_lane(float a, int) { return a; }
 GL_HD double gl_lane(double a, int) { return a; }
 GL_HD float gl_lane(GlF2 a, int i) { return i ? a.y : a.x; }
 
+// ---------------------------------------------------------------------------------------------
+// GlDual<S>: a lane type carrying a value and ONE directional derivative (forward-mode AD).
+// Instantiating the per-pixel code with V = GlDual<S> (the per-sample constants stay plain S) gives
+//   * X_fwd<GlDual>: the deflection and its derivative along a coordinate direction, i.e. one column
+//     of the lensing Hessian (MassProfile.hessian, src/gigalens/tf/profile.py:9-30 and the analytic
+//     versions in sis.py / shear.py / nfw.py / piemd.py) -- magnification, convergence, shear maps;
+//   * X_bwd<GlDual>: the directional derivative of the hand adjoint, which is exactly the parameter
+//     gradient of anything that depends on the Hessian (the image-position likelihood with its
+//     magnification-scaled errors, tf/model.py:103-124).
+// Only the tiny point workloads use it (tens of image positions per sample), never the pixel path.
+// Operators are in-class friends so that mixed S (op) GlDual expressions convert implicitly.
+// ---------------------------------------------------------------------------------------------
+template <class S>
+struct GlDual {
+  S v, d;
+  GL_HD GlDual() {}
+  GL_HD GlDual(S a) : v(a), d(S(0)) {}
+  GL_HD GlDual(S a, S b) : v(a), d(b) {}
+  friend GL_HD GlDual operator+(GlDual a, GlDual b) { return GlDual(a.v + b.v, a.d + b.d); }
+  friend GL_HD GlDual operator-(GlDual a, GlDual b) { return GlDual(a.v - b.v, a.d - b.d); }
+  friend GL_HD GlDual operator*(GlDual a, GlDual b) { return GlDual(a.v * b.v, a.v * b.d + a.d * b.v); }
+  friend GL_HD GlDual operator/(GlDual a, GlDual b) { S r = a.v / b.v; return GlDual(r, (a.d - r * b.d) / b.v); }
+  friend GL_HD GlDual operator-(GlDual a) { return GlDual(-a.v, -a.d); }
+  friend GL_HD GlDual& operator+=(GlDual& a, GlDual b) { a.v += b.v; a.d += b.d; return a; }
+  friend GL_HD GlDual& operator-=(GlDual& a, GlDual b) { a.v -= b.v; a.d -= b.d; return a; }
+  friend GL_HD GlDual& operator*=(GlDual& a, GlDual b) { a = a * b; return a; }
+  friend GL_HD bool operator<(GlDual a, GlDual b) { return a.v < b.v; }
+  friend GL_HD bool operator>(GlDual a, GlDual b) { return a.v > b.v; }
+  friend GL_HD bool operator<=(GlDual a, GlDual b) { return a.v <= b.v; }
+  friend GL_HD bool operator>=(GlDual a, GlDual b) { return a.v >= b.v; }
+  friend GL_HD bool operator==(GlDual a, GlDual b) { return a.v == b.v; }
+  friend GL_HD GlDual gl_sqrt(GlDual a) { S r = gl_sqrt(a.v); return GlDual(r, a.d / (S(2) * r)); }
+  friend GL_HD GlDual gl_rsqrt_fast(GlDual a) { S r = gl_rsqrt_fast(a.v); return GlDual(r, S(-0.5) * r * r * r * a.d); }
+  friend GL_HD GlDual gl_exp(GlDual a) { S e = gl_exp(a.v); return GlDual(e, e * a.d); }
+  friend GL_HD GlDual gl_exp2_fast(GlDual a) { S e = gl_exp2_fast(a.v); return GlDual(e, e * a.d * S(GL_LN2)); }
+  friend GL_HD GlDual gl_log(GlDual a) { return GlDual(gl_log(a.v), a.d / a.v); }
+  friend GL_HD GlDual gl_log2_fast(GlDual a) { return GlDual(gl_log2_fast(a.v), a.d / a.v * S(GL_LOG2E)); }
+  friend GL_HD GlDual gl_atan2(GlDual y, GlDual x) { return GlDual(gl_atan2(y.v, x.v), (x.v * y.d - y.v * x.d) / (x.v * x.v + y.v * y.v)); }
+  friend GL_HD GlDual gl_atan2_fast(GlDual y, GlDual x) { return GlDual(gl_atan2_fast(y.v, x.v), (x.v * y.d - y.v * x.d) / (x.v * x.v + y.v * y.v)); }
+  friend GL_HD GlDual gl_atan(GlDual a) { return GlDual(gl_atan(a.v), a.d / (S(1) + a.v * a.v)); }
+  friend GL_HD GlDual gl_atanh(GlDual a) { return GlDual(gl_atanh(a.v), a.d / (S(1) - a.v * a.v)); }
+  friend GL_HD GlDual gl_acosh(GlDual a) { return GlDual(gl_acosh(a.v), a.d / gl_sqrt(a.v * a.v - S(1))); }
+  friend GL_HD GlDual gl_acos(GlDual a) { return GlDual(gl_acos(a.v), -a.d / gl_sqrt(S(1) - a.v * a.v)); }
+  friend GL_HD GlDual gl_cos(GlDual a) { return GlDual(gl_cos(a.v), -gl_sin(a.v) * a.d); }
+  friend GL_HD GlDual gl_sin(GlDual a) { return GlDual(gl_sin(a.v), gl_cos(a.v) * a.d); }
+  friend GL_HD GlDual gl_abs(GlDual a) { return a.v < S(0) ? -a : a; }
+  friend GL_HD GlDual gl_min(GlDual a, GlDual b) { return (b.v < a.v) ? b : a; }
+  friend GL_HD GlDual gl_max(GlDual a, GlDual b) { return (b.v > a.v) ? b : a; }
+  friend GL_HD GlDual gl_div_fast(GlDual a, GlDual b) { return a / b; }
+  friend GL_HD GlDual gl_fma(GlDual a, GlDual b, GlDual c) { return GlDual(gl_fma(a.v, b.v, c.v), gl_fma(a.v, b.d, gl_fma(a.d, b.v, c.d))); }
+  friend GL_HD bool gl_isnan(GlDual a) { return a.v != a.v; }
+  friend GL_HD GlDual gl_where_gt(GlDual a, S t, GlDual vt, GlDual vf) { return a.v > t ? vt : vf; }
+  friend GL_HD GlDual gl_where_in(GlDual a, S lo, S hi, GlDual vt, GlDual vf) { return (a.v >= lo && a.v <= hi) ? vt : vf; }
+};
+template <class S> struct gl_scalar_of<GlDual<S>> { typedef S type; };
+
 // Profile type ids (same values as include/gigalens_b200.h).
 enum {
   GLT_EPL = 1, GLT_SHEAR = 2, GLT_SIE = 3, GLT_SIS = 4, GLT_NFW = 5, GLT_NFW_ELLIPSE = 6, GLT_DPIS = 7, GLT_DPIE = 8,
@@ -525,7 +581,7 @@ GL_HD void shear_bwd(const typename gl_scalar_of<V>::type* d, const V* x, const 
 // SIS  (tf/profiles/mass/sis.py:12-17)   raw = d = dvars = (theta_E, cx, cy)
 // =============================================================================================
 template <class T, int NP>
-GL_HD void sis_fwd(const T* d, const T* x, const T* y, T* ax, T* ay) {
+GL_HD void sis_fwd(const typename gl_scalar_of<T>::type* d, const T* x, const T* y, T* ax, T* ay) {
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
     T dx = x[j] - d[1], dy = y[j] - d[2];
@@ -535,7 +591,7 @@ GL_HD void sis_fwd(const T* d, const T* x, const T* y, T* ax, T* ay) {
   }
 }
 template <class T, int NP>
-GL_HD void sis_bwd(const T* d, const T* x, const T* y, const T* gax, const T* gay, T* g) {
+GL_HD void sis_bwd(const typename gl_scalar_of<T>::type* d, const T* x, const T* y, const T* gax, const T* gay, T* g) {
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
     T dx = x[j] - d[1], dy = y[j] - d[2];
@@ -582,7 +638,7 @@ GL_HD void sie_prep_bwd(const T* raw, const T* d, const T* g, T* graw) {
   graw[3] = g[SIEG_CX]; graw[4] = g[SIEG_CY];
 }
 template <class T, int NP>
-GL_HD void sie_fwd(const T* d, const T* x, const T* y, T* ax, T* ay) {
+GL_HD void sie_fwd(const typename gl_scalar_of<T>::type* d, const T* x, const T* y, T* ax, T* ay) {
   T c = d[SIE_C], s = d[SIE_S], q = d[SIE_Q], w = d[SIE_W], bw = d[SIE_B] / d[SIE_W];
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
@@ -595,7 +651,7 @@ GL_HD void sie_fwd(const T* d, const T* x, const T* y, T* ax, T* ay) {
   }
 }
 template <class T, int NP>
-GL_HD void sie_bwd(const T* d, const T* x, const T* y, const T* gax, const T* gay, T* g) {
+GL_HD void sie_bwd(const typename gl_scalar_of<T>::type* d, const T* x, const T* y, const T* gax, const T* gay, T* g) {
   T c = d[SIE_C], s = d[SIE_S], q = d[SIE_Q], w = d[SIE_W], b = d[SIE_B];
   T bw = b / w;
 #pragma unroll
@@ -708,7 +764,7 @@ GL_HD T nfw_g(T X, T& dg) {
   return T(1);
 }
 template <class T, int NP>
-GL_HD void nfw_fwd(const T* d, const T* x, const T* y, T* ax, T* ay) {
+GL_HD void nfw_fwd(const typename gl_scalar_of<T>::type* d, const T* x, const T* y, T* ax, T* ay) {
   T c = d[NFW_C], s = d[NFW_S], s1 = d[NFW_S1], s2 = d[NFW_S2];
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
@@ -723,7 +779,7 @@ GL_HD void nfw_fwd(const T* d, const T* x, const T* y, T* ax, T* ay) {
   }
 }
 template <class T, int NP>
-GL_HD void nfw_bwd(const T* d, const T* x, const T* y, const T* gax, const T* gay, T* g) {
+GL_HD void nfw_bwd(const typename gl_scalar_of<T>::type* d, const T* x, const T* y, const T* gax, const T* gay, T* g) {
   T c = d[NFW_C], s = d[NFW_S], s1 = d[NFW_S1], s2 = d[NFW_S2], Rs = d[NFW_RS], pref = d[NFW_PREF];
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
@@ -843,7 +899,7 @@ GL_HD void dpie_prep_bwd(const T* raw, const T* d, const T* g, T* graw, bool ell
   }
 }
 template <class T, int NP>
-GL_HD void dpis_fwd(const T* d, const T* x, const T* y, T* ax, T* ay) {
+GL_HD void dpis_fwd(const typename gl_scalar_of<T>::type* d, const T* x, const T* y, T* ax, T* ay) {
   T rc = d[DP_RC], rt = d[DP_RT], scale = d[DP_SCALE];
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
@@ -855,7 +911,7 @@ GL_HD void dpis_fwd(const T* d, const T* x, const T* y, T* ax, T* ay) {
   }
 }
 template <class T, int NP>
-GL_HD void dpis_bwd(const T* d, const T* x, const T* y, const T* gax, const T* gay, T* g) {
+GL_HD void dpis_bwd(const typename gl_scalar_of<T>::type* d, const T* x, const T* y, const T* gax, const T* gay, T* g) {
   T rc = d[DP_RC], rt = d[DP_RT], scale = d[DP_SCALE];
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
@@ -886,7 +942,7 @@ struct DpieFw {
   T sc, st, a, b_, c_, d_, e_, f_, aa, bb, cc, dd, inorm, aaa, bbb, inorm2, zr_re, zr_im;
 };
 template <class T>
-GL_HD void dpie_core_fwd(const T* d, T x, T y, DpieFw<T>& W, T& re, T& im) {
+GL_HD void dpie_core_fwd(const typename gl_scalar_of<T>::type* d, T x, T y, DpieFw<T>& W, T& re, T& im) {
   const T sqe = d[DP_SQE], rc = d[DP_RC], rt = d[DP_RT];
   const T rem2 = gl_fma(x * x, d[DP_IOPE2], y * y * d[DP_IOME2]);
   W.sc = gl_sqrt_pos(d[DP_RC2] + rem2);
@@ -913,7 +969,7 @@ GL_HD void dpie_core_fwd(const T* d, T x, T y, DpieFw<T>& W, T& re, T& im) {
   im = d[DP_ZCI] * W.zr_re;
 }
 template <class T, int NP>
-GL_HD void dpie_fwd(const T* d, const T* x, const T* y, T* ax, T* ay) {
+GL_HD void dpie_fwd(const typename gl_scalar_of<T>::type* d, const T* x, const T* y, T* ax, T* ay) {
   T c = d[DP_C], s = d[DP_S], scale = d[DP_SCALE];
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
@@ -926,7 +982,7 @@ GL_HD void dpie_fwd(const T* d, const T* x, const T* y, T* ax, T* ay) {
   }
 }
 template <class T, int NP>
-GL_HD void dpie_bwd(const T* d, const T* x, const T* y, const T* gax, const T* gay, T* g) {
+GL_HD void dpie_bwd(const typename gl_scalar_of<T>::type* d, const T* x, const T* y, const T* gax, const T* gay, T* g) {
   const T c = d[DP_C], s = d[DP_S], scale = d[DP_SCALE], rc = d[DP_RC], rt = d[DP_RT], e = d[DP_E];
   const T sqe = d[DP_SQE], q = d[DP_Q], iq = d[DP_IQ], iope2 = d[DP_IOPE2], iome2 = d[DP_IOME2], zci = d[DP_ZCI];
   // d(constant)/de, applied per pixel to fold every e-dependence into the single dvar e
@@ -997,9 +1053,9 @@ GL_HD void dpie_bwd(const T* d, const T* x, const T* y, const T* gax, const T* g
 // with M_m = d(scale, rc, rt)_m / d(base)_k precomputed per (sample, member) in the derived block.
 // d(alpha)/d(rc|rt) follows from z = num/den, zr = log z:  dz = (num' - z den')/den, dzr = dz / z.
 template <class T, int NP>
-GL_HD void dpie_fwd_jac(const T* d, const T* x, const T* y, T* ax, T* ay, T (*Jx)[NP], T (*Jy)[NP]) {
+GL_HD void dpie_fwd_jac(const typename gl_scalar_of<T>::type* d, const T* x, const T* y, T* ax, T* ay, T (*Jx)[NP], T (*Jy)[NP]) {
   const T c = d[DP_C], s = d[DP_S], scale = d[DP_SCALE], zci = d[DP_ZCI], two_sqe = T(2) * d[DP_SQE];
-  const T* M = d + DP_M;
+  const typename gl_scalar_of<T>::type* M = d + DP_M;
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
     T dx = x[j] - d[DP_CX], dy = y[j] - d[DP_CY];

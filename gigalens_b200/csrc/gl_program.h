@@ -341,3 +341,98 @@ GL_HD void gl_pix_image_bwd(const GlProgram& P, const typename gl_scalar_of<T>::
     }
   }
 }
+
+// ---------------------------------------------------------------------------------------------
+// image-position likelihood (ForwardProbModel.stats_positions, src/gigalens/tf/model.py:103-124):
+// point drivers on the forward-mode lane type GlDual.  Tens of points per sample -- not a hot path,
+// but it needs d(beta)/d(theta) (the lensing Hessian, LensSimulator.magnification,
+// tf/simulator.py:80-91) and the parameter gradient of a function of that Hessian.
+// ---------------------------------------------------------------------------------------------
+// beta and the Hessian H = (f_xx, f_xy, f_yx, f_yy) = (d ax/dx, d ax/dy, d ay/dx, d ay/dy) of the summed
+// deflection at one point: two forward-mode sweeps (tf/profile.py:9-30 does the same with a tape).
+template <class S, unsigned F>
+GL_HD void gl_point_hessian(const GlProgram& P, const S* der, S x, S y, S& bx, S& by, S* H) {
+  typedef GlDual<S> D;
+  D X[1], Y[1], BX[1], BY[1];
+  X[0] = D(x, S(1)); Y[0] = D(y, S(0));
+  gl_pix_beta<D, 1, F>(P, der, X, Y, BX, BY);
+  bx = BX[0].v; by = BY[0].v;
+  H[0] = S(1) - BX[0].d; H[2] = -BY[0].d;
+  X[0] = D(x, S(0)); Y[0] = D(y, S(1));
+  gl_pix_beta<D, 1, F>(P, der, X, Y, BX, BY);
+  H[1] = -BX[0].d; H[3] = S(1) - BY[0].d;
+}
+
+// One multiply-imaged source system with n images (tf/model.py:107-122): source-plane scatter about
+// the barycentre, errors err = centroid_error / magnification.  Adds to chi2 / norm and writes the
+// cotangents of log_like = -(chi2 + norm)/2 w.r.t. beta and H of every image.
+template <class S>
+GL_HD void gl_positions_system(int n, const S* bx, const S* by, const S* H, const S* ex, const S* ey, S& chi2, S& norm,
+                               S* gbx, S* gby, S* gH) {
+  const S two_pi = S(6.283185307179586);
+  S mx = S(0), my = S(0);
+  for (int i = 0; i < n; ++i) { mx += bx[i]; my += by[i]; }
+  mx /= S(n); my /= S(n);
+  S sax = S(0), say = S(0);
+  for (int i = 0; i < n; ++i) {
+    const S* h = H + 4 * i;
+    const S det = (S(1) - h[0]) * (S(1) - h[3]) - h[1] * h[2];
+    const S mu = S(1) / det;
+    const S dx = bx[i] - mx, dy = by[i] - my;
+    const S errx = ex[i] / mu, erry = ey[i] / mu;
+    const S rx = dx / errx, ry = dy / erry;
+    chi2 += rx * rx + ry * ry;
+    norm += gl_log(two_pi * errx * errx) + gl_log(two_pi * erry * erry);
+    if (gbx) {
+      const S ax = -rx / errx, ay = -ry / erry;            // d log_like / d (beta - barycentre)
+      gbx[i] = ax; gby[i] = ay; sax += ax; say += ay;
+      const S gmu = -(rx * rx + ry * ry) / mu + S(2) / mu;   // chi2 ~ mu^2, norm ~ -4 log|mu|
+      const S gdet = -gmu * mu * mu;
+      gH[4 * i + 0] = -gdet * (S(1) - h[3]);
+      gH[4 * i + 3] = -gdet * (S(1) - h[0]);
+      gH[4 * i + 1] = -gdet * h[2];
+      gH[4 * i + 2] = -gdet * h[1];
+    }
+  }
+  if (gbx) for (int i = 0; i < n; ++i) { gbx[i] -= sax / S(n); gby[i] -= say / S(n); }
+}
+
+// Parameter gradient of one image point: (gbx, gby) = cotangent of beta, gH = cotangent of H.  Runs
+// the hand adjoint of every deflector on dual numbers along x and along y; the tangent of the adjoint
+// output is   d^2 alpha/(d theta_dir d p)^T . gH[., dir]  +  d alpha/d p ^T . (-g_beta / 2)   per sweep.
+// flush(acc, n, off) receives scalar partial cotangents of dvars [off, off+n), as in gl_pix_image_bwd.
+template <class S, unsigned F, class Flush>
+GL_HD void gl_point_positions_bwd(const GlProgram& P, const S* der, S x, S y, S gbx, S gby, const S* gH, Flush& flush) {
+  typedef GlDual<S> D;
+  for (int dir = 0; dir < 2; ++dir) {
+    D X[1], Y[1], GX[1], GY[1];
+    X[0] = D(x, dir == 0 ? S(1) : S(0)); Y[0] = D(y, dir == 1 ? S(1) : S(0));
+    GX[0] = D(gH[dir], S(-0.5) * gbx);
+    GY[0] = D(gH[2 + dir], S(-0.5) * gby);
+    for (int i = 0; i < P.n_lens; ++i) {
+      const GlProf& pr = P.prof[i];
+      const int nm = pr.n_members > 0 ? pr.n_members : 1;
+      S base[GL_MAX_DVARS];
+#pragma unroll
+      for (int k = 0; k < GL_MAX_DVARS; ++k) base[k] = S(0);
+      for (int m = 0; m < nm; ++m) {
+        D acc[GL_MAX_DVARS];
+#pragma unroll
+        for (int k = 0; k < GL_MAX_DVARS; ++k) acc[k] = D(S(0));
+        const S* dm = der + pr.der_off + m * pr.der_size;
+        gl_lens_bwd<D, 1, F>(pr.type, pr.ts, dm, X, Y, GX, GY, acc);
+        if (pr.fwdmode) {   // scaling-relation member: chain (scale, rc, rt) -> the group's three base parameters
+          const S* M = dm + DP_M;
+          for (int jj = 0; jj < 3; ++jj)
+            for (int k = 0; k < 3; ++k) base[k] += acc[DPG_SCALE + jj].d * M[3 * jj + k];
+        } else {
+          S a[GL_MAX_DVARS];
+#pragma unroll
+          for (int k = 0; k < GL_MAX_DVARS; ++k) a[k] = acc[k].d;
+          flush(a, pr.n_dvars, pr.g_off + m * pr.n_dvars);
+        }
+      }
+      if (pr.fwdmode) flush(base, 3, pr.g_off);
+    }
+  }
+}

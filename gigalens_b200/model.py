@@ -170,62 +170,97 @@ def _autograd_wrap(torch, fn, z):
 
 
 class ForwardProbModel(ProbabilisticModel):
-    """``src/gigalens/tf/model.py:12-194``: pixel likelihood with the *simulated* image as the
-    variance estimate.  ``include_positions`` (image-position likelihood) is SURVEY.md §8f "next"
-    and not built yet; unlike the reference its default here is therefore ``False``."""
+    """``src/gigalens/tf/model.py:12-194``: pixel likelihood with the *simulated* image as the variance
+    estimate (``stats_pixels``) and/or the image-position likelihood of multiply-imaged sources
+    (``stats_positions``).  The reference defaults ``include_positions=True`` and then fails without
+    centroids; here the default (``None``) means "on when centroids are given"."""
 
     def __init__(self, prior, observed_image=None, background_rms=None, exp_time=None, error_map=None,
                  centroids_x=None, centroids_y=None, centroids_errors_x=None, centroids_errors_y=None,
-                 include_pixels=True, include_positions=False):
+                 include_pixels=True, include_positions=None):
         super().__init__(prior)
-        if include_positions:
-            raise NotImplementedError("image-position likelihood (stats_positions) is not built yet")
-        if not include_pixels:
-            raise NotImplementedError("include_pixels=False leaves no likelihood term")
-        self.include_pixels = include_pixels
-        self.include_positions = include_positions
-        self.observed_image = np.ascontiguousarray(observed_image, dtype=np.float32)
-        self.error_map = None if error_map is None else np.ascontiguousarray(error_map, dtype=np.float32)
-        self.background_rms = None if background_rms is None else float(np.float32(background_rms))
-        self.exp_time = None if exp_time is None else float(np.float32(exp_time))
-        if self.error_map is None and (self.background_rms is None or self.exp_time is None):
-            raise ValueError("give either error_map or background_rms and exp_time")
+        if include_positions is None:
+            include_positions = centroids_x is not None
+        if not include_pixels and not include_positions:
+            raise ValueError("include_pixels=False and include_positions=False leave no likelihood term")
+        self.include_pixels = bool(include_pixels)
+        self.include_positions = bool(include_positions)
+        self.observed_image = self.error_map = self.background_rms = self.exp_time = None
+        if self.include_pixels:  # tf/model.py:62-68
+            self.observed_image = np.ascontiguousarray(observed_image, dtype=np.float32)
+            self.error_map = None if error_map is None else np.ascontiguousarray(error_map, dtype=np.float32)
+            self.background_rms = None if background_rms is None else float(np.float32(background_rms))
+            self.exp_time = None if exp_time is None else float(np.float32(exp_time))
+            if self.error_map is None and (self.background_rms is None or self.exp_time is None):
+                raise ValueError("give either error_map or background_rms and exp_time")
+        self.centroids_x = self.centroids_y = self.centroids_errors_x = self.centroids_errors_y = None
+        if self.include_positions:  # tf/model.py:69-74
+            if any(v is None for v in (centroids_x, centroids_y, centroids_errors_x, centroids_errors_y)):
+                raise ValueError("include_positions=True needs centroids_x, centroids_y, centroids_errors_x, centroids_errors_y")
+            f32 = lambda group: [np.atleast_1d(np.asarray(c, dtype=np.float32)) for c in group]
+            self.centroids_x, self.centroids_y = f32(centroids_x), f32(centroids_y)
+            self.centroids_errors_x, self.centroids_errors_y = f32(centroids_errors_x), f32(centroids_errors_y)
+            self.n_position = 2 * sum(c.size for c in self.centroids_x)
 
-    def init_centroids(self, bs):  # tf/model.py:187-194 (no-op without positions)
+    def init_centroids(self, bs):
+        """``tf/model.py:185-194`` tiles the centroids over the batch; the CUDA kernels share one copy between
+        all samples, so there is nothing to do (kept for script compatibility)."""
         return None
 
     def _install_likelihood(self, simulator):
-        lc = _cabi.LikeConfig()
-        lc.observed = self.observed_image.ctypes.data_as(C.POINTER(C.c_float))
-        if self.error_map is not None:
-            lc.error_map = self.error_map.ctypes.data_as(C.POINTER(C.c_float))
-        lc.background_rms = self.background_rms or 0.0
-        lc.exp_time = self.exp_time or 1.0
-        n = simulator.numPix
-        if self.observed_image.shape != (n, n):
-            raise ValueError(f"observed_image must be ({n}, {n})")
-        _cabi.check(simulator._lib.gl_plan_set_likelihood(simulator._plan, C.byref(lc)), simulator._lib)
+        if self.include_pixels:
+            lc = _cabi.LikeConfig()
+            lc.observed = self.observed_image.ctypes.data_as(C.POINTER(C.c_float))
+            if self.error_map is not None:
+                lc.error_map = self.error_map.ctypes.data_as(C.POINTER(C.c_float))
+            lc.background_rms = self.background_rms or 0.0
+            lc.exp_time = self.exp_time or 1.0
+            n = simulator.numPix
+            if self.observed_image.shape != (n, n):
+                raise ValueError(f"observed_image must be ({n}, {n})")
+            _cabi.check(simulator._lib.gl_plan_set_likelihood(simulator._plan, C.byref(lc)), simulator._lib)
+        if self.include_positions:
+            simulator.set_positions(self.centroids_x, self.centroids_y, self.centroids_errors_x, self.centroids_errors_y)
         simulator.set_option("lstsq", 0)
+        simulator.set_option("include_pixels", int(self.include_pixels))
+        simulator.set_option("include_positions", int(self.include_positions))
+
+    def _own(self, simulator):
+        if simulator._like_owner is not self:
+            self._install_likelihood(simulator)
+            simulator._like_owner = self
+
+    def stats_positions(self, simulator, params):
+        """``tf/model.py:103-124`` -> ``(log_like, red_chi2)``, both ``(bs,)``."""
+        if not self.include_positions:
+            raise ValueError("this model was built with include_positions=False")
+        self._own(simulator)
+        return simulator.positions_loglike(params)
 
     def stats_pixels(self, simulator, params):
         """``tf/model.py:89-101`` -> ``(log_like, red_chi2)``, both ``(bs,)``."""
         torch = simulator._torch
-        if simulator._like_owner is not self:
-            self._install_likelihood(simulator)
-            simulator._like_owner = self
+        if not self.include_pixels:
+            raise ValueError("this model was built with include_pixels=False")
+        self._own(simulator)
         mat = simulator._params_matrix(params)
         ll = torch.empty((simulator.bs,), dtype=torch.float32, device=simulator.device)
         chi = torch.empty_like(ll)
-        _cabi.check(simulator._lib.gl_loglike_grad(simulator._plan, mat.data_ptr(), ll.data_ptr(), chi.data_ptr(), None,
-                                                   simulator._stream()), simulator._lib)
+        if self.include_positions:
+            simulator.set_option("include_positions", 0)
+        try:
+            _cabi.check(simulator._lib.gl_loglike_grad(simulator._plan, mat.data_ptr(), ll.data_ptr(), chi.data_ptr(), None,
+                                                       simulator._stream()), simulator._lib)
+        finally:
+            if self.include_positions:
+                simulator.set_option("include_positions", 1)
         return ll, chi
 
     def loglike_and_grad(self, simulator, params):
-        """log-likelihood, red_chi2 and d(log_like)/d(params) as a ``[P][bs]`` matrix."""
+        """log-likelihood (pixels and/or positions as configured), red_chi2 and d(log_like)/d(params) as a
+        ``[P][bs]`` matrix."""
         torch = simulator._torch
-        if simulator._like_owner is not self:
-            self._install_likelihood(simulator)
-            simulator._like_owner = self
+        self._own(simulator)
         mat = simulator._params_matrix(params)
         ll = torch.empty((simulator.bs,), dtype=torch.float32, device=simulator.device)
         chi = torch.empty_like(ll)
@@ -236,7 +271,15 @@ class ForwardProbModel(ProbabilisticModel):
 
     def log_like(self, simulator, z):
         """``tf/model.py:169-180``."""
-        return self.stats_pixels(simulator, self.bij_forward(simulator, z))[0]
+        params = self.bij_forward(simulator, z)
+        self._own(simulator)
+        mat = simulator._params_matrix(params)
+        torch = simulator._torch
+        ll = torch.empty((simulator.bs,), dtype=torch.float32, device=simulator.device)
+        chi = torch.empty_like(ll)
+        _cabi.check(simulator._lib.gl_loglike_grad(simulator._plan, mat.data_ptr(), ll.data_ptr(), chi.data_ptr(), None,
+                                                   simulator._stream()), simulator._lib)
+        return ll
 
 
 class BackwardProbModel(ProbabilisticModel):
@@ -259,6 +302,8 @@ class BackwardProbModel(ProbabilisticModel):
             raise ValueError(f"observed_image must be ({n}, {n})")
         _cabi.check(simulator._lib.gl_plan_set_likelihood(simulator._plan, C.byref(lc)), simulator._lib)
         simulator.set_option("lstsq", 1)   # log-prob entry points use the linear-amplitude solve
+        simulator.set_option("include_pixels", 1)
+        simulator.set_option("include_positions", 0)
 
     def loglike_and_grad(self, simulator, params):
         """log-likelihood, red_chi2 and d(log_like)/d(non-linear params) ``[P][bs]``."""

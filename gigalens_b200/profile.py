@@ -40,7 +40,7 @@ def _eval_points(kind, profile, x, y, kwargs):
     yf = np.broadcast_to(y, shape).reshape(-1)
     names = [p for p in profile.params if p in kwargs]
     consts = {}
-    if kind == "mass":
+    if kind in ("mass", "hessian"):
         pm = _model.PhysicalModel([profile], [], [])
         params = {"lens_mass": [{k: kwargs[k] for k in names}]}
     else:
@@ -51,6 +51,9 @@ def _eval_points(kind, profile, x, y, kwargs):
     for v in kwargs.values():
         bs = max(bs, int(np.size(v)))
     sim = _sim.LensSimulator(pm, _sim.SimulatorConfig(delta_pix=1.0, num_pix=2), bs=bs)
+    if kind == "hessian":
+        H = sim.hessian(xf, yf, params["lens_mass"])
+        return tuple(h.reshape((bs,) + shape).squeeze(0) if bs == 1 else h.reshape((bs,) + shape) for h in H)
     out = sim.eval_points(params, xf, yf, mode=1 if kind == "mass" else 2)
     if kind == "mass":
         ax, ay = out
@@ -90,3 +93,20 @@ class MassProfile(Parameterized, ABC):
     def deriv(self, x, y, **kwargs):
         """Deflection ``(alpha_x, alpha_y)`` at points ``(x, y)``; see :meth:`LightProfile.light`."""
         return _eval_points("mass", self, x, y, kwargs)
+
+    def hessian(self, x, y, **kwargs):
+        """``(f_xx, f_xy, f_yx, f_yy)``: the Jacobian of :meth:`deriv` (``tf/profile.py:9-30``; the analytic
+        ``hessian`` overrides of SIS / Shear / NFW / dPIE are the same function).  The reference's analytic
+        ``DPIS.hessian`` scales kappa by ``(r_core + r_cut)/r_cut`` relative to its own ``deriv``
+        (``piemd.py:72-73``); this returns the Jacobian."""
+        return _eval_points("hessian", self, x, y, kwargs)
+
+    def convergence(self, x, y, **kwargs):
+        """``tf/profile.py:32-36``."""
+        f_xx, _, _, f_yy = self.hessian(x, y, **kwargs)
+        return (f_xx + f_yy) / 2
+
+    def shear(self, x, y, **kwargs):
+        """``tf/profile.py:38-43``."""
+        f_xx, f_xy, _, f_yy = self.hessian(x, y, **kwargs)
+        return (f_xx - f_yy) / 2, f_xy

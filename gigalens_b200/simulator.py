@@ -352,6 +352,56 @@ class LensSimulator(LensSimulatorInterface):
         """``tf/simulator.py:72-78`` at points ``(x, y)`` shared by all samples -> ``(bs, npts)`` each."""
         return self.eval_points({"lens_mass": lens_params}, x, y, mode=0, missing_ok=("lens_light", "source_light"))
 
+    def hessian(self, x, y, lens_params: List[Dict]):
+        """``(f_xx, f_xy, f_yx, f_yy)`` of the summed deflection at points ``(x, y)`` shared by all samples,
+        ``(bs, npts)`` each -- the sum the reference's ``magnification`` / ``convergence`` / ``shear`` build
+        from every profile's ``hessian`` (``tf/simulator.py:80-107``).  FP64 forward-mode duals on the GPU."""
+        torch = self._torch
+        mat = self._params_matrix({"lens_mass": lens_params}, ("lens_light", "source_light"))
+        xt = torch.as_tensor(np.asarray(x, dtype=np.float32).reshape(-1)).to(self.device)
+        yt = torch.as_tensor(np.asarray(y, dtype=np.float32).reshape(-1)).to(self.device)
+        npts = xt.numel()
+        H = [torch.empty((self.bs, npts), dtype=torch.float32, device=self.device) for _ in range(4)]
+        _cabi.check(self._lib.gl_hessian(self._plan, mat.data_ptr(), npts, xt.data_ptr(), yt.data_ptr(),
+                                         *(h.data_ptr() for h in H), self._stream()), self._lib)
+        return tuple(H)
+
+    def magnification(self, x, y, lens_params: List[Dict]):
+        """``tf/simulator.py:80-91``: ``1 / det(I - H)``; infinite on critical curves, like the reference."""
+        f_xx, f_xy, f_yx, f_yy = self.hessian(x, y, lens_params)
+        return 1.0 / ((1 - f_xx) * (1 - f_yy) - f_xy * f_yx)
+
+    def convergence(self, x, y, lens_params: List[Dict]):
+        """``tf/simulator.py:93-98``: ``kappa = (f_xx + f_yy) / 2``."""
+        f_xx, _, _, f_yy = self.hessian(x, y, lens_params)
+        return (f_xx + f_yy) / 2
+
+    def shear(self, x, y, lens_params: List[Dict]):
+        """``tf/simulator.py:100-107``: ``gamma1 = (f_xx - f_yy) / 2, gamma2 = f_xy``."""
+        f_xx, f_xy, _, f_yy = self.hessian(x, y, lens_params)
+        return (f_xx - f_yy) / 2, f_xy
+
+    def set_positions(self, centroids_x, centroids_y, centroids_errors_x, centroids_errors_y):
+        """Install the image-position data of ``ForwardProbModel`` (``tf/model.py:69-74``) in the plan."""
+        n_img = np.asarray([np.size(c) for c in centroids_x], dtype=np.int32)
+        cat = [np.ascontiguousarray(np.concatenate([np.asarray(c, dtype=np.float32).reshape(-1) for c in group]))
+               for group in (centroids_x, centroids_y, centroids_errors_x, centroids_errors_y)]
+        if any(a.size != int(n_img.sum()) for a in cat):
+            raise ValueError("centroids_x / centroids_y / centroids_errors_x / centroids_errors_y differ in length")
+        fp = lambda a: a.ctypes.data_as(C.c_void_p)
+        _cabi.check(self._lib.gl_plan_set_positions(self._plan, len(n_img), fp(n_img), *(fp(a) for a in cat)), self._lib)
+
+    def positions_loglike(self, params, want_grad=False):
+        """``stats_positions`` alone: (log_like, red_chi2[, d log_like / d params [P][bs]])."""
+        torch = self._torch
+        mat = self._params_matrix(params, ("lens_light", "source_light"))
+        ll = torch.empty(self.bs, dtype=torch.float32, device=self.device)
+        chi = torch.empty(self.bs, dtype=torch.float32, device=self.device)
+        g = torch.empty((self.compiled.n_params, self.bs), dtype=torch.float32, device=self.device) if want_grad else None
+        _cabi.check(self._lib.gl_positions_loglike_grad(self._plan, mat.data_ptr(), ll.data_ptr(), chi.data_ptr(),
+                                                        g.data_ptr() if want_grad else None, self._stream()), self._lib)
+        return (ll, chi, g) if want_grad else (ll, chi)
+
     def _install_lstsq_data(self, observed_image, err_map):
         """(observed, err_map) of lstsq_simulate live in the plan's likelihood slot."""
         obs = np.ascontiguousarray(np.asarray(observed_image.cpu() if hasattr(observed_image, "cpu") else observed_image),

@@ -121,13 +121,21 @@ int gl_plan_create(const gl_model_desc* model, const gl_sim_config* sim, int32_t
 int gl_plan_set_likelihood(gl_plan* plan, const gl_like_config* like);
 /* prior / bijector leaves in z-column order (tf/model.py:76-87); d = n_leaves */
 int gl_plan_set_prior(gl_plan* plan, const gl_prior_leaf* leaves, int32_t n_leaves);
+/* ForwardProbModel(centroids_x, centroids_y, centroids_errors_x, centroids_errors_y): tf/model.py:69-74.
+ * One entry of n_images per multiply-imaged source; x, y, err_x, err_y are HOST arrays with the images of
+ * all systems concatenated (1..64 images per system).  Switches "include_positions" on. */
+int gl_plan_set_positions(gl_plan* plan, int32_t n_systems, const int32_t* n_images, const float* x, const float* y,
+                          const float* err_x, const float* err_y);
 /* Options.  "epl_batch_max" = 1: EPL series length from the batch maximum of f exactly like
  * tf/profiles/mass/epl.py:37 (default 0: per-sample length, identical to fp32 rounding).
  * "no_deflection" = 1: evaluate source light at the image-plane position (simulate(..., no_deflection=True),
  * tf/simulator.py:125-126).  "components" = 1 | 2 | 3: gl_simulate adds only the lens light / only the
  * source light / both (simulate_lens_light, simulate_images, simulate_source: tf/simulator.py:242-328).
  * "lstsq" = 1: the log-likelihood entry points use the linear-amplitude solve
- * (BackwardProbModel, tf/model.py:242-273). */
+ * (BackwardProbModel, tf/model.py:242-273).
+ * "include_pixels" / "include_positions" = 0 | 1: which terms gl_loglike_grad / gl_logprob_grad add
+ * (ForwardProbModel(include_pixels, include_positions), tf/model.py:43-44,150-163): log-likes add and the
+ * reduced chi^2 is the mean of the included terms. */
 int gl_plan_set_option(gl_plan* plan, const char* name, int32_t value);
 /* Measurement aid: after gl_plan_set_option(plan, "timing", n) every log-likelihood call records CUDA
  * events around its kernels on the launch stream; this returns the summed device time (ms) of the 7
@@ -174,6 +182,18 @@ int gl_unconstrain(gl_plan* plan, const float* z_dev, float* params_dev, float* 
  * synchronise.  These are the calls a reference-side binding would make per optimiser step. */
 int gl_logprob_grad_host(gl_plan* plan, const float* z_host, float* logp_host, float* red_chi2_host, float* dz_host);
 int gl_simulate_host(gl_plan* plan, const float* params_host, float* image_host);
+
+/* --- lensing Hessian and image-position likelihood (FP64 forward-mode duals) ------------- */
+/* Hessian of the summed deflection, (f_xx, f_xy, f_yx, f_yy) = (d ax/dx, d ax/dy, d ay/dx, d ay/dy), at npts
+ * points shared by all samples: MassProfile.hessian (tf/profile.py:9-30 and the analytic sis.py:19-29,
+ * shear.py:18-26, nfw.py:78-94, piemd.py:62-83,121-138), summed as LensSimulator.magnification /
+ * convergence / shear do (tf/simulator.py:80-107).  out [bs][npts] each. */
+int gl_hessian(gl_plan* plan, const float* params_dev, int32_t npts, const float* x_dev, const float* y_dev,
+               float* fxx_dev, float* fxy_dev, float* fyx_dev, float* fyy_dev, void* stream);
+/* ForwardProbModel.stats_positions(simulator, params): tf/model.py:103-124.  loglike_dev / red_chi2_dev [bs];
+ * dparams_dev [P][bs] = d(log-like)/d(params), or NULL. */
+int gl_positions_loglike_grad(gl_plan* plan, const float* params_dev, float* loglike_dev, float* red_chi2_dev,
+                              float* dparams_dev, void* stream);
 
 /* --- linear light-amplitude solve ------------------------------------------------------ */
 /* LensSimulator.lstsq_simulate(params, observed_image, err_map, return_coeffs): tf/simulator.py:158-240

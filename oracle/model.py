@@ -175,16 +175,52 @@ class JointPrior:
 
 
 class ForwardProbModel:
-    """``tf/model.py:12-194`` with ``include_positions=False`` (pixel likelihood only)."""
+    """``tf/model.py:12-194``: pixel likelihood (``stats_pixels``) and image-position likelihood
+    (``stats_positions``).  ``include_positions`` defaults to False here because most oracle callers have
+    no centroids; the reference's default is True (``:44``)."""
 
-    def __init__(self, prior: JointPrior, observed_image, background_rms=None, exp_time=None, error_map=None,
-                 dtype=torch.float32):
+    def __init__(self, prior: JointPrior, observed_image=None, background_rms=None, exp_time=None, error_map=None,
+                 centroids_x=None, centroids_y=None, centroids_errors_x=None, centroids_errors_y=None,
+                 include_pixels=True, include_positions=False, dtype=torch.float32):
         self.prior = prior
         self.dtype = dtype
-        self.observed_image = torch.as_tensor(np.asarray(observed_image, dtype=np.float32)).to(dtype)
-        self.error_map = None if error_map is None else torch.as_tensor(np.asarray(error_map, dtype=np.float32)).to(dtype)
-        self.background_rms = None if background_rms is None else float(np.float32(background_rms))
-        self.exp_time = None if exp_time is None else float(np.float32(exp_time))
+        self.include_pixels = include_pixels
+        self.include_positions = include_positions
+        self.observed_image = self.error_map = self.background_rms = self.exp_time = None
+        if include_pixels:
+            self.observed_image = torch.as_tensor(np.asarray(observed_image, dtype=np.float32)).to(dtype)
+            self.error_map = None if error_map is None else torch.as_tensor(np.asarray(error_map, dtype=np.float32)).to(dtype)
+            self.background_rms = None if background_rms is None else float(np.float32(background_rms))
+            self.exp_time = None if exp_time is None else float(np.float32(exp_time))
+        if include_positions:  # :69-74
+            f32 = lambda v: torch.as_tensor(np.asarray(v, dtype=np.float32)).to(dtype)
+            self.centroids_x = [f32(c) for c in centroids_x]
+            self.centroids_y = [f32(c) for c in centroids_y]
+            self.centroids_errors_x = [f32(c) for c in centroids_errors_x]
+            self.centroids_errors_y = [f32(c) for c in centroids_errors_y]
+            self.n_position = 2 * sum(int(c.numel()) for c in self.centroids_x)
+
+    def init_centroids(self, bs):
+        # :185-194  centroids repeated over the batch axis: (n_img,) -> (n_img, bs)
+        if self.include_positions:
+            self.centroids_x_batch = [c[:, None].repeat(1, bs) for c in self.centroids_x]
+            self.centroids_y_batch = [c[:, None].repeat(1, bs) for c in self.centroids_y]
+
+    def stats_positions(self, simulator, params):
+        # :103-124
+        chi2, log_like = 0.0, 0.0
+        for cx, cy, cex, cey in zip(self.centroids_x_batch, self.centroids_y_batch, self.centroids_errors_x,
+                                    self.centroids_errors_y):
+            beta_centroids = torch.stack(simulator.beta(cx, cy, params["lens_mass"]), dim=0)  # (xy, images, bs)
+            beta_centroids = beta_centroids.permute(2, 0, 1)  # batch size, xy, images
+            beta_barycentre = beta_centroids.mean(dim=2, keepdim=True)
+            magnifications = simulator.magnification(cx, cy, params["lens_mass"]).permute(1, 0)  # batch size, images
+            err_map = torch.stack([cex / magnifications, cey / magnifications], dim=1)  # batch size, xy, images
+            chi2_i = (((beta_centroids - beta_barycentre) / err_map) ** 2).sum((-2, -1))
+            normalization_i = torch.log(2 * np.pi * err_map ** 2).sum((-2, -1))
+            log_like = log_like + -1 / 2 * (chi2_i + normalization_i)
+            chi2 = chi2 + chi2_i
+        return log_like, chi2 / self.n_position
 
     def stats_pixels_from_image(self, im_sim, img_region):
         # tf/model.py:91-101
@@ -204,14 +240,25 @@ class ForwardProbModel:
             im_sim = im_sim[None]
         return self.stats_pixels_from_image(im_sim, simulator.img_region)
 
+    def _stats(self, simulator, params):
+        # :150-163
+        log_like, red_chi2, n_chi = 0.0, 0.0, 0
+        if self.include_pixels:
+            ll, rc = self.stats_pixels(simulator, params)
+            log_like, red_chi2, n_chi = log_like + ll, red_chi2 + rc, n_chi + 1
+        if self.include_positions:
+            ll, rc = self.stats_positions(simulator, params)
+            log_like, red_chi2, n_chi = log_like + ll, red_chi2 + rc, n_chi + 1
+        return log_like, red_chi2 / n_chi
+
     def log_prob(self, simulator, z):
         params, _ = self.prior.forward(z)
-        log_like, red_chi2 = self.stats_pixels(simulator, params)
+        log_like, red_chi2 = self._stats(simulator, params)
         return log_like + self.prior.log_prior(z), red_chi2
 
     def log_like(self, simulator, z):
         params, _ = self.prior.forward(z)
-        return self.stats_pixels(simulator, params)[0]
+        return self._stats(simulator, params)[0]
 
 
 class BackwardProbModel:

@@ -28,7 +28,30 @@ def _rotate(x, y, phi):
 # --------------------------------------------------------------------------- mass
 
 
-class EPL:
+class MassBase:
+    """``tf/profile.py:6-43``: default ``hessian`` by differentiating ``deriv`` (``GradientTape`` there, autograd
+    here, graph kept so that the result can itself be differentiated w.r.t. the parameters), and the
+    ``convergence`` / ``shear`` derived from it."""
+
+    def hessian(self, x, y, **kwargs):
+        x = x if x.requires_grad else x.detach().clone().requires_grad_(True)
+        y = y if y.requires_grad else y.detach().clone().requires_grad_(True)
+        fx, fy = self.deriv(x, y, **kwargs)  # tf/profile.py:22-25
+        f_xx, f_xy = torch.autograd.grad(fx.sum(), [x, y], create_graph=True)  # :27
+        f_yx, f_yy = torch.autograd.grad(fy.sum(), [x, y], create_graph=True)  # :28
+        return f_xx, f_xy, f_yx, f_yy
+
+    def convergence(self, x, y, **kwargs):
+        f_xx, f_xy, f_yx, f_yy = self.hessian(x, y, **kwargs)
+        return (f_xx + f_yy) / 2  # :34-35
+
+    def shear(self, x, y, **kwargs):
+        f_xx, f_xy, f_yx, f_yy = self.hessian(x, y, **kwargs)
+        return (f_xx - f_yy) / 2, f_xy  # :40-43
+
+
+
+class EPL(MassBase):
     """``tf/profiles/mass/epl.py:5-64``."""
 
     name = "EPL"
@@ -78,7 +101,7 @@ class EPL:
         return _rotate(f_x, f_y, -phi)  # :57
 
 
-class Shear:
+class Shear(MassBase):
     """``tf/profiles/mass/shear.py:5-26``."""
 
     name = "SHEAR"
@@ -87,8 +110,14 @@ class Shear:
     def deriv(self, x, y, gamma1, gamma2):
         return gamma1 * x + gamma2 * y, gamma2 * x - gamma1 * y  # shear.py:16
 
+    def hessian(self, x, y, gamma1, gamma2):
+        # shear.py:18-26 (kappa = 0)
+        one = torch.ones_like(x)
+        f_xx, f_yy, f_xy = gamma1 * one, -gamma1 * one, gamma2 * one
+        return f_xx, f_xy, f_xy, f_yy
 
-class SIE:
+
+class SIE(MassBase):
     """``tf/profiles/mass/sie.py:5-49`` (core ``s_scale`` is shadowed to 0, ``:15``)."""
 
     name = "SIE"
@@ -115,7 +144,7 @@ class SIE:
         return _rotate(fx, fy, -phi)
 
 
-class SIS:
+class SIS(MassBase):
     """``tf/profiles/mass/sis.py:5-17``."""
 
     name = "SIS"
@@ -131,8 +160,18 @@ class SIS:
         a = torch.where(zero, torch.zeros_like(R), theta_E / torch.where(zero, torch.ones_like(R), R))
         return a * x, a * y
 
+    def hessian(self, x, y, theta_E, center_x, center_y):
+        # sis.py:19-29
+        theta_E = _t(theta_E, x)
+        x, y = x - center_x, y - center_y
+        R = (x ** 2 + y ** 2) ** (3.0 / 2)
+        zero = R == 0
+        a = torch.where(zero, torch.zeros_like(R), theta_E / torch.where(zero, torch.ones_like(R), R))
+        f_xx, f_yy, f_xy = y ** 2 * a, x ** 2 * a, -x * y * a
+        return f_xx, f_xy, f_xy, f_yy
 
-class NFW:
+
+class NFW(MassBase):
     """``tf/profiles/mass/nfw.py:5-52`` (``deriv``, ``nfwAlpha``, ``g_``)."""
 
     name = "NFW"
@@ -168,8 +207,34 @@ class NFW:
         a = torch.where(gt, a2, a)
         return a
 
+    def F_(self, x):
+        # nfw.py:54-76: 1/3 at x == 1
+        lt, gt = x < 1, x > 1
+        x1 = torch.where(lt, x, torch.full_like(x, 0.5))
+        x2 = torch.where(gt, x, torch.full_like(x, 2.0))
+        a1 = 1 / (x1 ** 2 - 1) * (1 - 2 / torch.sqrt(1 - x1 ** 2) * torch.atanh(torch.sqrt((1 - x1) / (1 + x1))))
+        a2 = 1 / (x2 ** 2 - 1) * (1 - 2 / torch.sqrt(x2 ** 2 - 1) * torch.atan(torch.sqrt((x2 - 1) / (1 + x2))))
+        a = torch.ones_like(x) / 3
+        a = torch.where(lt, a1, a)
+        a = torch.where(gt, a2, a)
+        return a
 
-class NFW_ELLIPSE:
+    def hessian(self, x, y, Rs, alpha_Rs, center_x, center_y):
+        # nfw.py:78-94
+        Rs, alpha_Rs = _t(Rs, x), _t(alpha_Rs, x)
+        rho0 = alpha_Rs / (4.0 * Rs ** 2 * (1.0 - math.log(2.0)))
+        Rs = torch.clamp(Rs, min=self._r_min)
+        x, y = x - center_x, y - center_y
+        R = torch.clamp(torch.sqrt(x ** 2 + y ** 2), min=self._c)
+        X = R / Rs
+        gx, Fx = self.g_(X), self.F_(X)
+        kappa = 2 * rho0 * Rs * Fx
+        a = 2 * rho0 * Rs * (2 * gx / X ** 2 - Fx)
+        gamma1, gamma2 = a * (y ** 2 - x ** 2) / R ** 2, -a * 2 * (x * y) / R ** 2
+        return kappa + gamma1, gamma2, gamma2, kappa - gamma1
+
+
+class NFW_ELLIPSE(MassBase):
     """``tf/profiles/mass/nfw.py:97-134``."""
 
     name = "NFW_ELLIPSE"
@@ -208,7 +273,7 @@ def _sort_ra_rs(r_core, r_cut, r_min):
     return r_core, r_cut
 
 
-class DPIS:
+class DPIS(MassBase):
     """``tf/profiles/mass/piemd.py:21-60``."""
 
     name = "dPIS"
@@ -225,8 +290,23 @@ class DPIS:
         alpha_r = scale / r2 * f_a20
         return alpha_r * x, alpha_r * y
 
+    def hessian(self, x, y, theta_E, r_core, r_cut, center_x, center_y):
+        # piemd.py:62-83
+        theta_E, r_core, r_cut = (_t(v, x) for v in (theta_E, r_core, r_cut))
+        r_core, r_cut = _sort_ra_rs(r_core, r_cut, self._r_min)
+        x, y = x - center_x, y - center_y
+        r = torch.clamp(torch.sqrt(x ** 2 + y ** 2), min=self._r_min)
+        scale = theta_E * r_cut / (r_cut - r_core)
+        sc, st = torch.sqrt(r_core ** 2 + r ** 2), torch.sqrt(r_cut ** 2 + r ** 2)
+        gamma = scale / 2 * (2 * (1.0 / (r_core + sc) - 1.0 / (r_cut + st)) - (1 / sc - 1 / st))
+        kappa = scale / 2 * (r_core + r_cut) / r_cut * (1 / sc - 1 / st)
+        sin_imphi = -2 * x * y / r ** 2
+        cos_imphi = (y ** 2 - x ** 2) / r ** 2
+        gamma1, gamma2 = cos_imphi * gamma, sin_imphi * gamma
+        return kappa + gamma1, gamma2, gamma2, kappa - gamma1
 
-class DPIE:
+
+class DPIE(MassBase):
     """``tf/profiles/mass/piemd.py:97-119,183-255``."""
 
     name = "dPIE"
@@ -276,8 +356,50 @@ class DPIE:
         zres_im = zci_im * zr_re + zci_re * zr_im
         return zres_re, zres_im
 
+    def hessian(self, x, y, theta_E, r_core, r_cut, e1, e2, center_x=0, center_y=0):
+        # piemd.py:121-138
+        theta_E, r_core, r_cut, e1, e2 = (_t(v, x) for v in (theta_E, r_core, r_cut, e1, e2))
+        e, q, phi = self._param_conv(e1, e2)
+        x, y = x - center_x, y - center_y
+        x, y = _rotate(x, y, phi)
+        r_core, r_cut = _sort_ra_rs(r_core, r_cut, self._r_min)
+        scale = theta_E * r_cut / (r_cut - r_core)
+        xx_c, xy_c, yy_c = self.complex_hessian_single(x, y, r_core, e, q)
+        xx_t, xy_t, yy_t = self.complex_hessian_single(x, y, r_cut, e, q)
+        f_xx, f_xy, f_yy = scale * (xx_c - xx_t), scale * (xy_c - xy_t), scale * (yy_c - yy_t)
+        return self._hessian_rotate(f_xx, f_xy, f_xy, f_yy, -phi)
 
-class ScalingRelation:
+    @staticmethod
+    def _hessian_rotate(f_xx, f_xy, f_yx, f_yy, phi):
+        # piemd.py:157-181  (R H R^T)
+        cos_2phi, sin_2phi = torch.cos(2 * phi), torch.sin(2 * phi)
+        a = 0.5 * (f_xx + f_yy)
+        b = 0.5 * (f_xx - f_yy) * cos_2phi
+        c = f_xy * sin_2phi
+        d = f_xy * cos_2phi
+        e = 0.5 * (f_xx - f_yy) * sin_2phi
+        return a + b + c, d - e, d - e, a - b - c
+
+    @staticmethod
+    def complex_hessian_single(x, y, r_w, e, q):
+        # piemd.py:257-300
+        sqe = torch.sqrt(e)
+        qinv = 1.0 / q
+        cxro, cyro = (1.0 + e) * (1.0 + e), (1.0 - e) * (1.0 - e)
+        ci = 0.5 * (1.0 - e ** 2) / sqe
+        wrem = torch.sqrt(r_w ** 2 + x ** 2 / cxro + y ** 2 / cyro)
+        den1 = 2.0 * sqe * wrem - y * qinv
+        den1 = q ** 2 * x ** 2 + den1 ** 2
+        num2 = 2.0 * r_w * sqe - y
+        den2 = x ** 2 + num2 ** 2
+        didxre = ci * (q * (2.0 * sqe * x ** 2 / cxro / wrem - 2.0 * sqe * wrem + y * qinv) / den1 + num2 / den2)
+        didyre = ci * ((2 * sqe * x * y * q / cyro / wrem - x) / den1 + x / den2)
+        didyim = ci * ((2 * sqe * wrem * qinv - y * qinv ** 2 - 4 * e * y / cyro
+                        + 2 * sqe * y ** 2 / cyro / wrem * qinv) / den1 - num2 / den2)
+        return didxre, didyre, didyim
+
+
+class ScalingRelation(MassBase):
     """``tf/profiles/mass/scaling_relation.py:6-70``: member-galaxy sum of a wrapped profile."""
 
     def __init__(self, profile, scaling_params, lum_star, scaling_params_power, galaxy_catalogue,
@@ -314,6 +436,16 @@ class ScalingRelation:
             alpha_x = alpha_x + ax.sum(-1)
             alpha_y = alpha_y + ay.sum(-1)
         return alpha_x, alpha_y
+
+    def hessian(self, x, y, **scales):
+        # scaling_relation.py:72-83: member sum of the wrapped profile's hessian
+        H = [torch.zeros_like(x) for _ in range(4)]
+        x, y = x.unsqueeze(-1), y.unsqueeze(-1)
+        for up, c_chunk in zip(self._unscaled_params, self._galaxy_constants):
+            p_chunk = {k: up[k] * _t(scales[k], x).unsqueeze(-1) for k in self.scaling_params}
+            Hc = self.profile.hessian(x, y, **p_chunk, **c_chunk)
+            H = [h + hc.sum(-1) for h, hc in zip(H, Hc)]
+        return tuple(H)
 
 
 class DPIESubhalo(ScalingRelation):

@@ -192,6 +192,35 @@ class OracleSimulator:
             beta_x, beta_y = beta_x - f_xi, beta_y - f_yi
         return beta_x, beta_y
 
+    def hessian(self, x, y, lens_params):
+        # the sum magnification / convergence / shear take over the lens list (tf/simulator.py:80-107)
+        H = [torch.zeros_like(x) for _ in range(4)]
+        for lens, p, c in zip(self.phys_model.lenses, lens_params, self.phys_model.lenses_constants):
+            Hi = lens.hessian(x, y, **p, **self._c(c))
+            H = [h + hi for h, hi in zip(H, Hi)]
+        return tuple(H)
+
+    def magnification(self, x, y, lens_params):
+        # :80-91
+        f_xx, f_xy, f_yx, f_yy = self.hessian(x, y, lens_params)
+        det_A = (1 - f_xx) * (1 - f_yy) - f_xy * f_yx
+        return 1.0 / det_A
+
+    def convergence(self, x, y, lens_params):
+        # :93-98
+        kappa = torch.zeros_like(x)
+        for lens, p, c in zip(self.phys_model.lenses, lens_params, self.phys_model.lenses_constants):
+            kappa = kappa + lens.convergence(x, y, **p, **self._c(c))
+        return kappa
+
+    def shear(self, x, y, lens_params):
+        # :100-107
+        g1, g2 = torch.zeros_like(x), torch.zeros_like(x)
+        for lens, p, c in zip(self.phys_model.lenses, lens_params, self.phys_model.lenses_constants):
+            a, b = lens.shear(x, y, **p, **self._c(c))
+            g1, g2 = g1 + a, g2 + b
+        return g1, g2
+
     def _scatter(self, vals):
         nss = self.num_pix * self.supersample
         img = torch.zeros((nss * nss,) + tuple(vals.shape[1:]), dtype=self.dtype)

@@ -120,6 +120,28 @@ def host_run(cm: CompiledModel, mat, gx, gy, g_ss=None, dtype=np.float64, no_def
     return dict(ss=ss, gparams=gparams, beta=beta, comps=comps)
 
 
+def host_positions(cm: CompiledModel, mat, systems, dtype=np.float64, use_fwdmode=True, want_grad=True):
+    """stats_positions on the host harness.  systems = [(x, y, err_x, err_y), ...] one tuple of (n_img,) arrays
+    per multiply-imaged source.  Returns dict(beta=[bs][2][npts], hess=[bs][4][npts], loglike, chi2, gparams)."""
+    lib = hostcheck_lib()
+    fn = lib.glh_positions_f64 if dtype == np.float64 else lib.glh_positions_f32
+    mat = np.ascontiguousarray(mat, dtype=dtype)
+    P, bs = mat.shape
+    n_img = np.asarray([len(s[0]) for s in systems], dtype=np.int32)
+    cat = [np.ascontiguousarray(np.concatenate([np.asarray(s[k], dtype=dtype) for s in systems])) for k in range(4)]
+    npts = int(n_img.sum())
+    beta = np.zeros((bs, 2, npts), dtype=dtype)
+    hess = np.zeros((bs, 4, npts), dtype=dtype)
+    ll, chi2 = np.zeros(bs, dtype=dtype), np.zeros(bs, dtype=dtype)
+    gparams = np.zeros((P, bs), dtype=dtype) if want_grad else None
+    vp = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+    rc = fn(C.byref(cm.desc), C.c_int(bs), vp(mat), C.c_int(len(systems)), vp(n_img), vp(cat[0]), vp(cat[1]), vp(cat[2]), vp(cat[3]),
+            C.c_int(int(use_fwdmode)), vp(beta), vp(hess), vp(ll), vp(chi2), vp(gparams))
+    if rc != 0:
+        raise RuntimeError(lib.glh_last_error().decode())
+    return dict(beta=beta, hess=hess, loglike=ll, chi2=chi2, gparams=gparams)
+
+
 def host_run_packed(cm: CompiledModel, mat, gx, gy, g_ss=None):
     """Same as host_run(dtype=float32) but through the two-pixel packed lane type (GlF2)."""
     lib = hostcheck_lib()

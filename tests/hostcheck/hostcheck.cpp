@@ -116,6 +116,59 @@ static int run_packed(const gl_model_desc* m, int bs, const float* params, int n
   return 0;
 }
 
+// stats_positions (tf/model.py:103-124) through the dual-number point drivers: beta, Hessian, log-like,
+// chi2 and the parameter gradient for n_sys image systems (points concatenated, n_img per system).
+template <class T>
+static int run_positions(const gl_model_desc* m, int bs, const T* params, int n_sys, const int* n_img, const T* px, const T* py,
+                         const T* ex, const T* ey, int use_fwdmode, T* beta_out, T* hess_out, T* loglike, T* chi2_out, T* gparams) {
+  GlBuilt B;
+  std::string e = gl_build_program(m, B, use_fwdmode != 0);
+  if (!e.empty()) { g_err = e; return 1; }
+  GlProgram& P = B.prog;
+  const float* mf = B.member_factor.empty() ? nullptr : B.member_factor.data();
+  const int* as = B.amp_slot.empty() ? nullptr : B.amp_slot.data();
+  int npts = 0;
+  for (int s = 0; s < n_sys; ++s) npts += n_img[s];
+  std::vector<T> der(P.der_total), g(P.g_total > 0 ? P.g_total : 1), bx(npts), by(npts), H(4 * npts), gbx(npts), gby(npts), gH(4 * npts);
+  for (int b = 0; b < bs; ++b) {
+    gl_sample_prep<T, T>(P, params, bs, b, mf, as, nullptr, der.data());
+    for (int p = 0; p < npts; ++p) {
+      gl_point_hessian<T, GLF_ALL>(P, der.data(), px[p], py[p], bx[p], by[p], &H[4 * p]);
+      if (beta_out) { beta_out[((size_t)b * 2 + 0) * npts + p] = bx[p]; beta_out[((size_t)b * 2 + 1) * npts + p] = by[p]; }
+      if (hess_out) for (int c = 0; c < 4; ++c) hess_out[((size_t)b * 4 + c) * npts + p] = H[4 * p + c];
+    }
+    T chi2 = T(0), norm = T(0);
+    int o = 0;
+    for (int s = 0; s < n_sys; ++s) {
+      gl_positions_system<T>(n_img[s], &bx[o], &by[o], &H[4 * o], ex + o, ey + o, chi2, norm, &gbx[o], &gby[o], &gH[4 * o]);
+      o += n_img[s];
+    }
+    if (loglike) loglike[b] = -(chi2 + norm) / T(2);
+    if (chi2_out) chi2_out[b] = chi2 / T(2 * npts);
+    if (gparams) {
+      std::fill(g.begin(), g.end(), T(0));
+      HostFlush<T> fl{g.data()};
+      for (int p = 0; p < npts; ++p)
+        gl_point_positions_bwd<T, GLF_ALL>(P, der.data(), px[p], py[p], gbx[p], gby[p], &gH[4 * p], fl);
+      gl_sample_prep_bwd<T, T>(P, params, bs, b, mf, as, der.data(), g.data(), gparams);
+    }
+  }
+  return 0;
+}
+
+extern "C" {
+int glh_positions_f64(const gl_model_desc* m, int bs, const double* params, int n_sys, const int* n_img, const double* px,
+                      const double* py, const double* ex, const double* ey, int use_fwdmode, double* beta_out, double* hess_out,
+                      double* loglike, double* chi2, double* gparams) {
+  return run_positions<double>(m, bs, params, n_sys, n_img, px, py, ex, ey, use_fwdmode, beta_out, hess_out, loglike, chi2, gparams);
+}
+int glh_positions_f32(const gl_model_desc* m, int bs, const float* params, int n_sys, const int* n_img, const float* px,
+                      const float* py, const float* ex, const float* ey, int use_fwdmode, float* beta_out, float* hess_out,
+                      float* loglike, float* chi2, float* gparams) {
+  return run_positions<float>(m, bs, params, n_sys, n_img, px, py, ex, ey, use_fwdmode, beta_out, hess_out, loglike, chi2, gparams);
+}
+}
+
 extern "C" {
 int glh_run_f32x2(const gl_model_desc* m, int bs, const float* params, int npix, const float* gx, const float* gy,
                   float* ss_out, const float* g_ss, float* gparams) {

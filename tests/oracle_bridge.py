@@ -39,9 +39,49 @@ def build_oracle(wl, bs, dtype=torch.float32):
     sim = OracleSimulator(om, sc.delta_pix, sc.num_pix, sc.supersample, kernel=sc.kernel,
                           transform_pix2angle=sc.transform_pix2angle, pix_region=sc.pix_region, bs=bs, dtype=dtype)
     prior = to_oracle_prior(wl["prior"])
-    pm = OM.ForwardProbModel(prior, wl["observed"], background_rms=wl.get("background_rms"), exp_time=wl.get("exp_time"),
-                             error_map=wl.get("error_map"), dtype=dtype)
+    cen = wl.get("centroids")   # dict(x=[...], y=[...], ex=[...], ey=[...]): one array per multiply-imaged source
+    pm = OM.ForwardProbModel(prior, wl.get("observed"), background_rms=wl.get("background_rms"), exp_time=wl.get("exp_time"),
+                             error_map=wl.get("error_map"), dtype=dtype, include_pixels=wl.get("include_pixels", True),
+                             include_positions=cen is not None,
+                             **({} if cen is None else dict(centroids_x=cen["x"], centroids_y=cen["y"],
+                                                            centroids_errors_x=cen["ex"], centroids_errors_y=cen["ey"])))
+    pm.init_centroids(bs)
     return sim, pm
+
+
+def find_images(wl, truth, beta_s, half_width, n_grid=48, newton=30):
+    """Image positions of a point source at beta_s under the oracle's lens model at `truth` (fp64): coarse grid
+    search for sign changes of beta - beta_s, Newton refinement with the oracle Hessian, duplicates merged."""
+    osim, _ = build_oracle({**wl, "centroids": None, "include_pixels": True}, 1, torch.float64)
+    lens = [{k: torch.as_tensor([float(v)], dtype=torch.float64) for k, v in d.items()} for d in truth["lens_mass"]]
+    g = np.linspace(-half_width, half_width, n_grid)
+    X, Y = np.meshgrid(g, g)
+    xt = torch.as_tensor(X.reshape(-1, 1)); yt = torch.as_tensor(Y.reshape(-1, 1))
+    bx, by = osim.beta(xt, yt, lens)
+    d2 = ((bx[:, 0] - beta_s[0]) ** 2 + (by[:, 0] - beta_s[1]) ** 2).numpy().reshape(n_grid, n_grid)
+    seeds = []
+    for i in range(1, n_grid - 1):
+        for j in range(1, n_grid - 1):
+            if d2[i, j] == d2[i - 1:i + 2, j - 1:j + 2].min():
+                seeds.append((X[i, j], Y[i, j]))
+    out = []
+    for sx, sy in seeds:
+        th = np.array([sx, sy], dtype=np.float64)
+        ok = False
+        for _ in range(newton):
+            x1 = torch.as_tensor([[th[0]]]); y1 = torch.as_tensor([[th[1]]])
+            bx, by = osim.beta(x1, y1, lens)
+            H = [float(h.detach()) for h in osim.hessian(x1, y1, lens)]
+            r = np.array([float(bx) - beta_s[0], float(by) - beta_s[1]])
+            A = np.array([[1 - H[0], -H[1]], [-H[2], 1 - H[3]]])
+            step = np.linalg.solve(A, r)
+            th = th - step
+            if np.hypot(*step) < 1e-12:
+                ok = True
+                break
+        if ok and np.all(np.abs(th) < half_width) and not any(np.hypot(*(th - o)) < 1e-6 for o in out):
+            out.append(th)
+    return np.array(out)
 
 
 def logprob_and_grad(wl, z, dtype=torch.float32):

@@ -364,3 +364,149 @@ def test_nan_pixels_are_scrubbed_and_pass_no_gradient(packed):
     # and the next clean call is not polluted by the previous one's NaN count
     again = [t.cpu().numpy() for t in pmod.loglike_and_grad(sim, torch.as_tensor(mat, device="cuda"))]
     assert np.array_equal(again[2], clean[2])
+
+
+# ---------------------------------------------------------------------------------------------
+# lensing Hessian, magnification and the image-position likelihood
+# ---------------------------------------------------------------------------------------------
+HESS_CASES = dict(MASS_CASES, epl_shear=lambda: [epl.EPL(50), shear.Shear()], shear=lambda: [shear.Shear()])
+
+
+@pytest.mark.parametrize("case", sorted(HESS_CASES))
+def test_hessian_magnification_convergence_shear(case):
+    """gl_hessian vs the oracle's per-profile hessians (analytic where the reference has them, autodiff
+    otherwise: tf/profile.py:9-30), summed as tf/simulator.py:80-107 does."""
+    bs = 3
+    pm = PhysicalModel(HESS_CASES[case](), [], [sersic.Sersic()])
+    sim = LensSimulator(pm, SimulatorConfig(delta_pix=0.2, num_pix=4), bs=bs)
+    cm = sim.compiled
+    mat = common.draw_matrix(cm, bs, seed=31).astype(np.float32)
+    rng = np.random.default_rng(5)
+    r, t = rng.uniform(0.4, 2.0, 200), rng.uniform(0, 2 * np.pi, 200)
+    x, y = (r * np.cos(t)).astype(np.float32), (r * np.sin(t)).astype(np.float32)
+    params = cm.unflatten(torch.as_tensor(mat, device="cuda"))
+    H = [h.cpu().numpy() for h in sim.hessian(x, y, params["lens_mass"])]
+    mu = sim.magnification(x, y, params["lens_mass"]).cpu().numpy()
+    kappa = sim.convergence(x, y, params["lens_mass"]).cpu().numpy()
+    g1, g2 = (v.cpu().numpy() for v in sim.shear(x, y, params["lens_mass"]))
+    om = common.to_oracle_model(pm, torch.float64)
+    if case == "dpis":   # the reference's analytic DPIS.hessian is not the Jacobian of DPIS.deriv (kappa x (rc+rt)/rt)
+        from oracle import profiles as OP
+        om.lenses[0].hessian = OP.MassBase.hessian.__get__(om.lenses[0])
+    osim = OracleSimulator(om, 0.2, 4, 1, bs=bs, dtype=torch.float64)
+    op, _ = common.matrix_to_pytree(cm, mat.astype(np.float64), torch.float64)
+    X = torch.as_tensor(x.astype(np.float64))[:, None].repeat(1, bs)
+    Y = torch.as_tensor(y.astype(np.float64))[:, None].repeat(1, bs)
+    Ho = [h.detach().numpy().T for h in osim.hessian(X, Y, op["lens_mass"])]
+    scale = max(1.0, max(np.abs(h).max() for h in Ho))
+    for a, b, nm in zip(H, Ho, ("f_xx", "f_xy", "f_yx", "f_yy")):
+        assert np.max(np.abs(a - b)) <= 1e-5 * scale, (nm, np.max(np.abs(a - b)))
+    mu_o = osim.magnification(X, Y, op["lens_mass"]).detach().numpy().T
+    ok = np.abs(mu_o) < 50   # away from critical curves, where 1/det amplifies the fp32 output rounding of H
+    assert np.allclose(mu[ok], mu_o[ok], rtol=2e-4)
+    assert np.allclose(kappa, (Ho[0] + Ho[3]) / 2, atol=1e-5 * scale)
+    assert np.allclose(g1, (Ho[0] - Ho[3]) / 2, atol=1e-5 * scale) and np.allclose(g2, Ho[1], atol=1e-5 * scale)
+
+
+def test_profile_hessian_methods_match_reference_analytic_forms():
+    """MassProfile.hessian / convergence / shear on single profiles (SIS closed form, sis.py:19-29)."""
+    rng = np.random.default_rng(1)
+    x, y = rng.normal(size=500).astype(np.float32), rng.normal(size=500).astype(np.float32)
+    fxx, fxy, fyx, fyy = (t.cpu().numpy() for t in sis.SIS().hessian(x=x, y=y, theta_E=1.3, center_x=0.0, center_y=0.0))
+    r3 = (x.astype(np.float64) ** 2 + y.astype(np.float64) ** 2) ** 1.5
+    assert np.allclose(fxx, 1.3 * y ** 2 / r3, rtol=1e-5, atol=1e-5) and np.allclose(fyy, 1.3 * x ** 2 / r3, rtol=1e-5, atol=1e-5)
+    assert np.allclose(fxy, -1.3 * x * y / r3, rtol=1e-5, atol=1e-5) and np.array_equal(fxy, fyx)
+    kap = sis.SIS().convergence(x=x, y=y, theta_E=1.3, center_x=0.0, center_y=0.0).cpu().numpy()
+    assert np.allclose(kap, 1.3 / (2 * np.sqrt(x.astype(np.float64) ** 2 + y ** 2)), rtol=1e-5)
+    g1, g2 = (t.cpu().numpy() for t in shear.Shear().shear(x=x, y=y, gamma1=0.03, gamma2=-0.02))
+    assert np.allclose(g1, 0.03, atol=1e-7) and np.allclose(g2, -0.02, atol=1e-7)
+
+
+def _c2_positions_workload():
+    """C2 lens model with two quadruply-imaged point sources found at the demo truth (oracle, fp64)."""
+    wl = workloads.c2_workload()
+    cen = dict(x=[], y=[], ex=[], ey=[])
+    for k, beta_s in enumerate([(0.05, 0.03), (-0.12, 0.08)]):
+        img = oracle_bridge.find_images(wl, workloads.DEMO_TRUTH, beta_s, 2.0)
+        assert len(img) >= 2
+        rng = np.random.default_rng(40 + k)
+        img = img + rng.normal(0, 0.01, img.shape)   # astrometric noise
+        cen["x"].append(img[:, 0].astype(np.float32)); cen["y"].append(img[:, 1].astype(np.float32))
+        cen["ex"].append(np.full(len(img), 0.01, np.float32)); cen["ey"].append(np.full(len(img), 0.012, np.float32))
+    return dict(wl, centroids=cen)
+
+
+@pytest.mark.parametrize("include_pixels", [False, True])
+def test_positions_likelihood_logprob_and_grad(include_pixels):
+    """ForwardProbModel(include_positions=True): stats_positions, and log_prob / d log_prob / dz with the
+    position term alone or added to the pixel term (tf/model.py:103-124,150-163)."""
+    wl = dict(_c2_positions_workload(), include_pixels=include_pixels)
+    cen = wl["centroids"]
+    bs = 8
+    sim = LensSimulator(wl["phys_model"], wl["sim_config"], bs=bs)
+    pmod = ForwardProbModel(wl["prior"], wl["observed"] if include_pixels else None, background_rms=0.2, exp_time=100.0,
+                            centroids_x=cen["x"], centroids_y=cen["y"], centroids_errors_x=cen["ex"], centroids_errors_y=cen["ey"],
+                            include_pixels=include_pixels)
+    assert pmod.include_positions
+    # samples scattered tightly around the truth: image positions only make sense near a fitting model
+    z0 = pmod.bij_inverse(workloads.DEMO_TRUTH)
+    z = (z0 + np.random.default_rng(3).normal(0, 0.01, size=(bs, z0.shape[1]))).astype(np.float32)
+    zt = torch.as_tensor(z, device="cuda")
+    logp, chi2, dz = (t.cpu().numpy() for t in pmod.log_prob_and_grad(sim, zt))
+    r_logp, r_chi2, r_dz = oracle_bridge.logprob_and_grad(wl, z.astype(np.float64), torch.float64)
+    s_logp, s_chi2, s_dz = oracle_bridge.logprob_and_grad(wl, z, torch.float32)
+    p_logp, p_chi2, p_dz = oracle_bridge.logprob_and_grad(wl, common.ulp_perturb(z), torch.float64)
+    assert_parity(logp[:, None], s_logp[:, None], r_logp[:, None], 1e-5, "logp", p_logp[:, None], axis=1)
+    assert_parity(chi2[:, None], s_chi2[:, None], r_chi2[:, None], 1e-5, "red chi2", p_chi2[:, None], axis=1)
+    for k in range(z.shape[1]):
+        assert_parity(dz[:, k], s_dz[:, k], r_dz[:, k], 1e-4, f"dz[{k}]", p_dz[:, k])
+    # the position term alone, through stats_positions
+    params = pmod.bij_forward(sim, zt)
+    ll_pos, chi_pos = (t.cpu().numpy() for t in pmod.stats_positions(sim, params))
+    osim, opm = oracle_bridge.build_oracle(wl, bs, torch.float64)
+    op, _ = opm.prior.forward(torch.as_tensor(z.astype(np.float64)))
+    o_ll, o_chi = (t.numpy() for t in opm.stats_positions(osim, op))
+    assert np.allclose(ll_pos, o_ll, rtol=1e-5) and np.allclose(chi_pos, o_chi, rtol=1e-5)
+    if include_pixels:   # stats_pixels still returns the pixel term alone, and the two add up
+        ll_pix, _ = (t.cpu().numpy() for t in pmod.stats_pixels(sim, params))
+        ll_all = pmod.log_like(sim, zt).cpu().numpy()
+        assert np.allclose(ll_pix + ll_pos, ll_all, rtol=1e-6)
+
+
+def test_positions_cluster_model_gradient():
+    """Image-position likelihood of the cluster model (NFW + dPIE scaling-relation members + shear), positions only."""
+    G = 6
+    pm = PhysicalModel([nfw.NFW(), dpie_subhalo.DPIESubhalo(1.0, _catalogue(G)), shear.Shear()], [], [sersic.Sersic()])
+    bs = 5
+    sim = LensSimulator(pm, SimulatorConfig(delta_pix=0.2, num_pix=4), bs=bs)
+    cm = sim.compiled
+    mat = common.draw_matrix(cm, bs, seed=8).astype(np.float32)
+    rng = np.random.default_rng(9)
+    cen = dict(x=[], y=[], ex=[], ey=[])
+    for n in (3, 4, 2):
+        r, t = rng.uniform(0.8, 2.5, n), rng.uniform(0, 2 * np.pi, n)
+        cen["x"].append((r * np.cos(t)).astype(np.float32)); cen["y"].append((r * np.sin(t)).astype(np.float32))
+        cen["ex"].append(rng.uniform(0.02, 0.05, n).astype(np.float32)); cen["ey"].append(rng.uniform(0.02, 0.05, n).astype(np.float32))
+    pmod = ForwardProbModel({"lens_mass": []}, centroids_x=cen["x"], centroids_y=cen["y"], centroids_errors_x=cen["ex"],
+                            centroids_errors_y=cen["ey"], include_pixels=False)
+    ll, chi2, g = (t.cpu().numpy() for t in pmod.loglike_and_grad(sim, torch.as_tensor(mat, device="cuda")))
+
+    def oracle(m, dt):
+        osim = OracleSimulator(common.to_oracle_model(pm, dt), 0.2, 4, 1, bs=bs, dtype=dt)
+        opm = OM.ForwardProbModel(OM.JointPrior({}), include_pixels=False, include_positions=True, dtype=dt,
+                                  centroids_x=cen["x"], centroids_y=cen["y"], centroids_errors_x=cen["ex"], centroids_errors_y=cen["ey"])
+        opm.init_centroids(bs)
+        params, leaf = common.matrix_to_pytree(cm, m, dt, requires_grad=True)
+        rll, rchi = opm.stats_positions(osim, params)
+        rll.sum().backward()
+        return rll.detach().numpy(), rchi.detach().numpy(), leaf.grad.numpy()
+
+    ll64, chi64, g64 = oracle(mat.astype(np.float64), torch.float64)
+    ll32, chi32, g32 = oracle(mat.astype(np.float64), torch.float32)
+    ll64p, chi64p, g64p = oracle(common.ulp_perturb(mat), torch.float64)
+    assert_parity(ll[:, None], ll32[:, None], ll64[:, None], 1e-5, "positions log-like", ll64p[:, None], axis=1)
+    assert_parity(chi2[:, None], chi32[:, None], chi64[:, None], 1e-5, "positions red chi2", chi64p[:, None], axis=1)
+    lens_rows = [k for k, key in enumerate(cm.slot_keys) if key[0] == "lens_mass"]
+    for k in lens_rows:
+        assert_parity(g[k], g32[k], g64[k], 1e-4, f"grad {cm.slot_keys[k]}", g64p[k])
+    assert np.all(g[[k for k in range(cm.n_params) if k not in lens_rows]] == 0)

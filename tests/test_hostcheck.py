@@ -131,3 +131,110 @@ def test_packed_lane_instantiation_matches_scalar(name):
         sc = np.max(np.abs(g64[k]))
         assert np.max(np.abs(a["gparams"][k] - b["gparams"][k])) <= 2e-5 * sc, cm.slot_keys[k]
         assert np.max(np.abs(b["gparams"][k] - g64[k])) <= max(1e-4, 10 * np.max(np.abs(a["gparams"][k] - g64[k]))) * sc
+
+
+# ---------------------------------------------------------------------------------------------
+# image-position likelihood: Hessian by forward-mode duals, gradient by duals through the hand adjoint
+# ---------------------------------------------------------------------------------------------
+def _systems(seed=5):
+    rng = np.random.default_rng(seed)
+    out = []
+    for n in (4, 2, 3):
+        r, t = rng.uniform(0.7, 1.6, n), rng.uniform(0, 2 * np.pi, n)
+        out.append((r * np.cos(t), r * np.sin(t), rng.uniform(0.01, 0.03, n), rng.uniform(0.01, 0.03, n)))
+    return out
+
+
+def _positions_reference(pm, mat, systems, dtype, analytic=True):
+    """Oracle stats_positions (tf/model.py:103-124) + autograd; analytic=False swaps every profile's hessian for
+    the autodiff default of tf/profile.py:9-30."""
+    from oracle import model as OM, profiles as OP
+    bs = mat.shape[1]
+    cm = CompiledModel(pm)
+    om = to_oracle_model(pm, dtype)
+    if not analytic:
+        for lens in om.lenses:
+            lens.hessian = OP.MassBase.hessian.__get__(lens)
+            inner = getattr(lens, "profile", None)
+            if inner is not None:
+                inner.hessian = OP.MassBase.hessian.__get__(inner)
+    sim = OracleSimulator(om, 0.25, 4, 1, bs=bs, dtype=dtype)
+    prob = OM.ForwardProbModel(None, include_pixels=False, include_positions=True, dtype=dtype,
+                               centroids_x=[s[0] for s in systems], centroids_y=[s[1] for s in systems],
+                               centroids_errors_x=[s[2] for s in systems], centroids_errors_y=[s[3] for s in systems])
+    for k in ("centroids_x", "centroids_y", "centroids_errors_x", "centroids_errors_y"):  # keep the fp64 inputs un-rounded
+        setattr(prob, k, [torch.as_tensor(np.asarray(s[i], dtype=np.float64)).to(dtype) for s in systems]
+                if (i := ["centroids_x", "centroids_y", "centroids_errors_x", "centroids_errors_y"].index(k)) >= 0 else None)
+    prob.init_centroids(bs)
+    params, leaf = matrix_to_pytree(cm, mat, dtype, True)
+    ll, chi2 = prob.stats_positions(sim, params)
+    ll.sum().backward()
+    X = torch.cat(prob.centroids_x_batch, 0)
+    Y = torch.cat(prob.centroids_y_batch, 0)
+    params2, _ = matrix_to_pytree(cm, mat, dtype)
+    H = [h.detach().numpy().T for h in sim.hessian(X, Y, params2["lens_mass"])]
+    return dict(loglike=ll.detach().numpy(), chi2=chi2.detach().numpy(), gparams=leaf.grad.numpy(), hess=np.stack(H, 1))
+
+
+POS_MODELS = ["c2", "sis", "sie", "nfw", "nfw_ellipse", "dpie", "constants", "cluster"]
+
+
+@pytest.mark.parametrize("name", POS_MODELS)
+@pytest.mark.parametrize("fwdmode", [True, False])
+def test_positions_likelihood_and_gradient_fp64(name, fwdmode):
+    if not fwdmode and name != "cluster":
+        pytest.skip("forward-mode groups exist only in scaling-relation models")
+    pm = MODELS[name]()
+    cm = CompiledModel(pm)
+    mat = draw_matrix(cm, 3, seed=6)
+    systems = _systems()
+    ref = _positions_reference(pm, mat, systems, torch.float64)
+    out = common.host_positions(cm, mat, systems, np.float64, use_fwdmode=fwdmode)
+    assert np.max(np.abs(out["hess"] - ref["hess"])) < 1e-9 * max(1.0, np.max(np.abs(ref["hess"])))
+    assert np.allclose(out["loglike"], ref["loglike"], rtol=1e-9) and np.allclose(out["chi2"], ref["chi2"], rtol=1e-9)
+    lens_rows = [k for k, key in enumerate(cm.slot_keys) if key[0] == "lens_mass"]
+    for k in lens_rows:
+        assert np.max(np.abs(out["gparams"][k] - ref["gparams"][k])) <= 1e-8 * np.max(np.abs(ref["gparams"][k])), cm.slot_keys[k]
+    other = [k for k in range(cm.n_params) if k not in lens_rows]
+    assert np.all(out["gparams"][other] == 0)
+
+
+def test_positions_dpis_follows_the_jacobian_of_deriv():
+    """The reference's analytic DPIS.hessian (piemd.py:62-83) carries a factor (r_core + r_cut)/r_cut on kappa
+    that its own deriv (and DPIE.hessian in the round limit) does not have; the CUDA path differentiates deriv."""
+    pm = MODELS["dpis"]()
+    cm = CompiledModel(pm)
+    mat = draw_matrix(cm, 3, seed=6)
+    systems = _systems()
+    out = common.host_positions(cm, mat, systems, np.float64)
+    ad = _positions_reference(pm, mat, systems, torch.float64, analytic=False)
+    an = _positions_reference(pm, mat, systems, torch.float64, analytic=True)
+    assert np.max(np.abs(out["hess"] - ad["hess"])) < 1e-10
+    assert np.allclose(out["loglike"], ad["loglike"], rtol=1e-9)
+    assert np.max(np.abs(out["gparams"] - ad["gparams"])) <= 1e-8 * np.max(np.abs(ad["gparams"]))
+    # the analytic version differs in kappa only: f_xx + f_yy scaled, f_xx - f_yy and f_xy equal
+    assert np.allclose(an["hess"][:, 0] - an["hess"][:, 3], ad["hess"][:, 0] - ad["hess"][:, 3], atol=1e-12)
+    assert np.max(np.abs((an["hess"][:, 0] + an["hess"][:, 3]) - (ad["hess"][:, 0] + ad["hess"][:, 3]))) > 1e-4
+
+
+@pytest.mark.parametrize("name", ["c2"])
+def test_positions_float_instantiation(name):
+    """GlDual<float> compiles and tracks the fp32 oracle; the CUDA kernels instantiate GlDual<double> (the cluster
+    model's complex-log dPIE form loses the 1e-5 bound in fp32 near critical curves), which the fp64 tests pin."""
+    pm = MODELS[name]()
+    cm = CompiledModel(pm)
+    mat = draw_matrix(cm, 3, seed=6).astype(np.float32)
+    systems = [tuple(np.asarray(a, dtype=np.float32) for a in s) for s in _systems()]
+    ref = _positions_reference(pm, mat.astype(np.float64), [tuple(a.astype(np.float64) for a in s) for s in systems], torch.float64)
+    sys64 = [tuple(a.astype(np.float64) for a in s) for s in systems]
+    r32 = _positions_reference(pm, mat.astype(np.float64), sys64, torch.float32)
+    rpt = _positions_reference(pm, common.ulp_perturb(mat), sys64, torch.float64)
+    out = common.host_positions(cm, mat, systems, np.float32)
+    # random image positions land near critical curves (|mu| ~ 1e2), which amplifies fp32 rounding: same
+    # metric as everywhere else -- 1e-5 / 1e-4, or a small multiple of the fp32 oracle's own error
+    common.assert_parity(out["loglike"][:, None], r32["loglike"][:, None], ref["loglike"][:, None], 1e-5, "positions log-like",
+                         rpt["loglike"][:, None], axis=1)
+    lens_rows = [k for k, key in enumerate(cm.slot_keys) if key[0] == "lens_mass"]
+    for k in lens_rows:
+        common.assert_parity(out["gparams"][k], r32["gparams"][k], ref["gparams"][k], 1e-4, f"positions grad {cm.slot_keys[k]}",
+                             rpt["gparams"][k])
