@@ -1217,7 +1217,7 @@ static int gl_lstsq_alloc(gl_plan* p) {
 }
 
 static int gl_lstsq_forward(gl_plan* p, const float* params, float* image, float* coeffs_out, float* loglike,
-                            float* red_chi2, bool want_gimg, cudaStream_t st) {
+                            float* red_chi2, bool want_gimg, cudaStream_t st, float* stack_out = nullptr) {
   if (!p->has_like || !p->d_err) return gl_fail("lstsq: needs gl_plan_set_likelihood with observed image and error_map");
   const int D = p->prog.depth, npx = p->n * p->n;
   if (D <= 0) return gl_fail("lstsq: the model has no linear light component");
@@ -1242,6 +1242,10 @@ static int gl_lstsq_forward(gl_plan* p, const float* params, float* image, float
     })
     GL_LAUNCH_CHECK("k_raytrace_comps");
     if (gl_run_conv_fwd(p, p->d_comps, 1.f, p->d_R, false, nullptr, st, nb * D)) return 1;
+    if (stack_out) {   // return_stacked: the convolved, pooled unit-amplitude components, nothing solved
+      GL_CUDA(cudaMemcpyAsync(stack_out + (size_t)b0 * D * npx, p->d_R, (size_t)nb * D * npx * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      continue;
+    }
     k_gram<<<nb, GLL_THREADS, smem_gram, st>>>(D, npx, p->d_R, p->d_w, p->d_obs, p->d_gram);
     GL_LAUNCH_CHECK("k_gram");
     k_pinv_solve<<<nb, 128, smem_solve, st>>>(D, p->d_gram, 1e-6, 16, p->d_coef + (size_t)b0 * D);
@@ -1281,6 +1285,11 @@ int gl_lstsq_simulate(gl_plan* p, const float* params_dev, float* image_dev, flo
   if (!p || !params_dev) return gl_fail("gl_lstsq_simulate: NULL argument");
   GL_CUDA(cudaSetDevice(p->device));
   return gl_lstsq_forward(p, params_dev, image_dev, coeffs_dev, nullptr, nullptr, false, (cudaStream_t)stream);
+}
+int gl_lstsq_stack(gl_plan* p, const float* params_dev, float* stack_dev, void* stream) {
+  if (!p || !params_dev || !stack_dev) return gl_fail("gl_lstsq_stack: NULL argument");
+  GL_CUDA(cudaSetDevice(p->device));
+  return gl_lstsq_forward(p, params_dev, nullptr, nullptr, nullptr, nullptr, false, (cudaStream_t)stream, stack_dev);
 }
 int gl_lstsq_loglike_grad(gl_plan* p, const float* params_dev, float* loglike_dev, float* red_chi2_dev, float* dparams_dev,
                           void* stream) {

@@ -339,8 +339,8 @@ class LensSimulator(LensSimulatorInterface):
         """mode 0: beta, 1: total deflection, 2: surface brightness, at points shared by all samples."""
         torch = self._torch
         mat = self._params_matrix(params, missing_ok)
-        xt = torch.as_tensor(np.asarray(x, dtype=np.float32).reshape(-1)).to(self.device)
-        yt = torch.as_tensor(np.asarray(y, dtype=np.float32).reshape(-1)).to(self.device)
+        xt = torch.as_tensor(np.array(x, dtype=np.float32).reshape(-1)).to(self.device)
+        yt = torch.as_tensor(np.array(y, dtype=np.float32).reshape(-1)).to(self.device)
         npts = xt.numel()
         o0 = torch.empty((self.bs, npts), dtype=torch.float32, device=self.device)
         o1 = torch.empty((self.bs, npts), dtype=torch.float32, device=self.device)
@@ -358,8 +358,8 @@ class LensSimulator(LensSimulatorInterface):
         from every profile's ``hessian`` (``tf/simulator.py:80-107``).  FP64 forward-mode duals on the GPU."""
         torch = self._torch
         mat = self._params_matrix({"lens_mass": lens_params}, ("lens_light", "source_light"))
-        xt = torch.as_tensor(np.asarray(x, dtype=np.float32).reshape(-1)).to(self.device)
-        yt = torch.as_tensor(np.asarray(y, dtype=np.float32).reshape(-1)).to(self.device)
+        xt = torch.as_tensor(np.array(x, dtype=np.float32).reshape(-1)).to(self.device)
+        yt = torch.as_tensor(np.array(y, dtype=np.float32).reshape(-1)).to(self.device)
         npts = xt.numel()
         H = [torch.empty((self.bs, npts), dtype=torch.float32, device=self.device) for _ in range(4)]
         _cabi.check(self._lib.gl_hessian(self._plan, mat.data_ptr(), npts, xt.data_ptr(), yt.data_ptr(),
@@ -420,13 +420,20 @@ class LensSimulator(LensSimulatorInterface):
                        no_deflection=False):
         """``tf/simulator.py:158-240``: solve the linear light amplitudes against ``observed_image``
         with weights ``1/err_map`` and return the best-fitting image ``(bs, n, n)`` (squeezed), or the
-        amplitudes ``(bs, D)`` with ``return_coeffs``."""
-        if return_stacked:
-            raise NotImplementedError("return_stacked is not wired through the C ABI yet")
+        amplitudes ``(bs, D)`` with ``return_coeffs``, or with ``return_stacked`` the convolved, down-sampled
+        unit-amplitude components ``(bs, n, n, D)`` (``:203-229``)."""
         torch = self._torch
         self._install_lstsq_data(observed_image, err_map)
         mat = self._params_matrix(params)
         n = self.numPix
+        if return_stacked:
+            stack = torch.empty((self.bs, self.depth, n, n), dtype=torch.float32, device=self.device)
+            self.set_option("no_deflection", int(no_deflection))
+            try:
+                _cabi.check(self._lib.gl_lstsq_stack(self._plan, mat.data_ptr(), stack.data_ptr(), self._stream()), self._lib)
+            finally:
+                self.set_option("no_deflection", 0)
+            return stack.permute(0, 2, 3, 1)
         img = torch.empty((self.bs, n, n), dtype=torch.float32, device=self.device)
         coef = torch.empty((self.bs, self.depth), dtype=torch.float32, device=self.device)
         if no_deflection:

@@ -199,6 +199,9 @@ int gl_positions_loglike_grad(gl_plan* plan, const float* params_dev, float* log
 /* LensSimulator.lstsq_simulate(params, observed_image, err_map, return_coeffs): tf/simulator.py:158-240
  * (layout jax/simulator.py:171-195).  image_dev [bs][n][n] or NULL; coeffs_dev [bs][D] or NULL. */
 int gl_lstsq_simulate(gl_plan* plan, const float* params_dev, float* image_dev, float* coeffs_dev, void* stream);
+/* lstsq_simulate(..., return_stacked=True): the D convolved, down-sampled unit-amplitude light components
+ * (tf/simulator.py:203-229), stack_dev [bs][D][n][n] (the reference's layout is [bs][n][n][D]). */
+int gl_lstsq_stack(gl_plan* plan, const float* params_dev, float* stack_dev, void* stream);
 /* BackwardProbModel.log_prob likelihood part + gradient w.r.t. the non-linear params: tf/model.py:242-273 */
 int gl_lstsq_loglike_grad(gl_plan* plan, const float* params_dev, float* loglike_dev, float* red_chi2_dev,
                           float* dparams_dev, void* stream);

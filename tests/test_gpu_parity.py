@@ -266,6 +266,13 @@ def test_lstsq_simulate_and_backward_model(n_max, interpolate, with_lens_light):
     c64p, im64p, lp64p, chi64p, dz64p = ref["pert"]
     assert_parity(coef, c32, c64, 1e-5, "coeffs", c64p, axis=1)
     assert_parity(img, im32, im64, 1e-5, "image", im64p, axis=(1, 2))
+    # return_stacked: the convolved, pooled unit-amplitude components (bs, n, n, D)
+    stack = sim.lstsq_simulate(params, wl["observed"], pmod.err_map, return_stacked=True).cpu().numpy()
+    osim, opm = oracle_bridge.build_oracle_backward(wl, bs, torch.float64)
+    p64, _ = opm.prior.forward(torch.as_tensor(z.astype(np.float64)))
+    st64 = osim.lstsq_simulate(p64, opm.observed_image, opm.err_map, return_stacked=True).numpy()
+    assert stack.shape == st64.shape == (bs, 60, 60, sim.depth)
+    assert np.max(np.abs(stack - st64)) <= 1e-5 * np.max(np.abs(st64))
     assert_parity(logp[:, None], lp32[:, None], lp64[:, None], 1e-5, "logp", lp64p[:, None], axis=1)
     assert_parity(chi2[:, None], chi32[:, None], chi64[:, None], 1e-5, "red chi2", chi64p[:, None], axis=1)
     for k in range(z.shape[1]):
@@ -465,7 +472,7 @@ def test_positions_likelihood_logprob_and_grad(include_pixels):
     ll_pos, chi_pos = (t.cpu().numpy() for t in pmod.stats_positions(sim, params))
     osim, opm = oracle_bridge.build_oracle(wl, bs, torch.float64)
     op, _ = opm.prior.forward(torch.as_tensor(z.astype(np.float64)))
-    o_ll, o_chi = (t.numpy() for t in opm.stats_positions(osim, op))
+    o_ll, o_chi = (t.detach().numpy() for t in opm.stats_positions(osim, op))
     assert np.allclose(ll_pos, o_ll, rtol=1e-5) and np.allclose(chi_pos, o_chi, rtol=1e-5)
     if include_pixels:   # stats_pixels still returns the pixel term alone, and the two add up
         ll_pix, _ = (t.cpu().numpy() for t in pmod.stats_pixels(sim, params))
