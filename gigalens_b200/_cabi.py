@@ -11,6 +11,7 @@ GL_MAX_PROFILE_PARAMS = 8
 
 # gl_profile_type
 GL_EPL, GL_SHEAR, GL_SIE, GL_SIS, GL_NFW, GL_NFW_ELLIPSE, GL_DPIS, GL_DPIE = 1, 2, 3, 4, 5, 6, 7, 8
+GL_TNFW, GL_DPIEP = 9, 10
 GL_SERSIC, GL_SERSIC_ELLIPSE, GL_SHAPELETS = 32, 33, 34
 GL_FLAG_USE_LSTSQ, GL_FLAG_INTERPOLATE = 1, 2
 GL_DIST_NORMAL, GL_DIST_LOGNORMAL, GL_DIST_UNIFORM, GL_DIST_TRUNCNORMAL = 0, 1, 2, 3
@@ -25,6 +26,8 @@ RAW_ORDER = {
     GL_NFW_ELLIPSE: ["Rs", "alpha_Rs", "e1", "e2", "center_x", "center_y"],
     GL_DPIS: ["theta_E", "r_core", "r_cut", "center_x", "center_y"],
     GL_DPIE: ["theta_E", "r_core", "r_cut", "e1", "e2", "center_x", "center_y"],
+    GL_TNFW: ["Rs", "alpha_Rs", "r_trunc", "center_x", "center_y"],
+    GL_DPIEP: ["theta_E", "Ra", "Rs", "e1", "e2", "center_x", "center_y"],
     GL_SERSIC: ["R_sersic", "n_sersic", "center_x", "center_y", "Ie"],
     GL_SERSIC_ELLIPSE: ["R_sersic", "n_sersic", "e1", "e2", "center_x", "center_y", "Ie"],
     GL_SHAPELETS: ["beta", "center_x", "center_y"],

@@ -36,7 +36,7 @@ inline void gl_shapelets_table(int n_max, std::vector<float>& out) {
 
 inline int gl_shapelets_layers(int n_max) { return (n_max + 1) * (n_max + 2) / 2; }
 
-inline bool gl_is_mass(int t) { return t >= GLT_EPL && t <= GLT_DPIE; }
+inline bool gl_is_mass(int t) { return t >= GLT_EPL && t <= GLT_DPIEP; }
 inline bool gl_is_light(int t) { return t == GLT_SERSIC || t == GLT_SERSIC_ELLIPSE || t == GLT_SHAPELETS; }
 
 // Returns "" on success, else an error message.

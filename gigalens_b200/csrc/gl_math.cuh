@@ -229,6 +229,7 @@ template <class S> struct gl_scalar_of<GlDual<S>> { typedef S type; };
 // Profile type ids (same values as include/gigalens_b200.h).
 enum {
   GLT_EPL = 1, GLT_SHEAR = 2, GLT_SIE = 3, GLT_SIS = 4, GLT_NFW = 5, GLT_NFW_ELLIPSE = 6, GLT_DPIS = 7, GLT_DPIE = 8,
+  GLT_TNFW = 9, GLT_DPIEP = 10,
   GLT_SERSIC = 32, GLT_SERSIC_ELLIPSE = 33, GLT_SHAPELETS = 34
 };
 
@@ -238,13 +239,14 @@ enum {
 // adjoint or the Shapelets scratch arrays.  GLF_ALL is the generic interpreter.
 enum {
   GLF_EPL = 1, GLF_SHEAR = 2, GLF_SIE = 4, GLF_SIS = 8, GLF_NFW = 16, GLF_DPIS = 32, GLF_DPIE = 64, GLF_SERSIC = 128,
-  GLF_SHAPELETS = 256, GLF_ALL = 511
+  GLF_SHAPELETS = 256, GLF_TNFW = 512, GLF_DPIEP = 1024, GLF_ALL = 2047
 };
 GL_HD unsigned gl_feature_of(int type) {
   switch (type) {
     case GLT_EPL: return GLF_EPL; case GLT_SHEAR: return GLF_SHEAR; case GLT_SIE: return GLF_SIE; case GLT_SIS: return GLF_SIS;
     case GLT_NFW: case GLT_NFW_ELLIPSE: return GLF_NFW; case GLT_DPIS: return GLF_DPIS; case GLT_DPIE: return GLF_DPIE;
     case GLT_SERSIC: case GLT_SERSIC_ELLIPSE: return GLF_SERSIC; case GLT_SHAPELETS: return GLF_SHAPELETS;
+    case GLT_TNFW: return GLF_TNFW; case GLT_DPIEP: return GLF_DPIEP;
   }
   return 0;
 }
@@ -1099,6 +1101,196 @@ GL_HD void dpie_fwd_jac(const typename gl_scalar_of<T>::type* d, const T* x, con
 }
 
 // =============================================================================================
+// TNFW  (tf/profiles/mass/tnfw.py:10-62; the docs call it experimental)
+//   raw  : Rs, alpha_Rs, r_trunc, cx, cy
+//   d[]  : cx, cy, Rs, pref = 4 rho0 Rs = alpha_Rs / (Rs (1 - ln 2)), tau = r_trunc / Rs, and the tau-only
+//          constants pre = tau^2/(tau^2+1)^2, c0 = tau pi + (tau^2-1) ln tau, c1 = (tau^2-1)/tau, ln tau
+//   dvars: cx, cy, Rs, pref, tau
+//   alpha = pref g(X, tau) / X^2 (x, y),  X = max(R, 0.001 Rs) / Rs,  s = sqrt(tau^2 + X^2),
+//   L = ln(X / (tau + s)),  g = pre [ (tau^2 + 2 X^2 - 1) F(X) + c0 + s (c1 L - pi) ]
+// =============================================================================================
+enum { TNFW_CX = 0, TNFW_CY, TNFW_RS, TNFW_PREF, TNFW_TAU, TNFW_PRE, TNFW_C0, TNFW_C1, TNFW_LNT, TNFW_SIZE = 12 };
+enum { TNFWG_CX = 0, TNFWG_CY, TNFWG_RS, TNFWG_PREF, TNFWG_TAU };
+#define GL_PI 3.14159265358979323846
+template <class T>
+GL_HD void tnfw_prep(const T* raw, T* d) {
+  const T Rs = raw[0], tau = raw[2] / raw[0];
+  d[TNFW_CX] = raw[3]; d[TNFW_CY] = raw[4]; d[TNFW_RS] = Rs;
+  d[TNFW_PREF] = raw[1] / (Rs * T(GL_ONE_MINUS_LN2));   // 4 rho0 Rs, rho0 = alpha_Rs / (4 Rs^2 (1 + ln 0.5))
+  d[TNFW_TAU] = tau;
+  const T t2 = tau * tau, lnt = gl_log(tau);
+  d[TNFW_PRE] = t2 / ((t2 + T(1)) * (t2 + T(1)));
+  d[TNFW_C0] = tau * T(GL_PI) + (t2 - T(1)) * lnt;
+  d[TNFW_C1] = (t2 - T(1)) / tau;
+  d[TNFW_LNT] = lnt;
+  d[9] = T(0); d[10] = T(0); d[11] = T(0);
+}
+template <class T>
+GL_HD void tnfw_prep_bwd(const T* raw, const T* d, const T* g, T* graw) {
+  const T Rs = raw[0];
+  graw[1] = g[TNFWG_PREF] / (Rs * T(GL_ONE_MINUS_LN2));
+  graw[2] = g[TNFWG_TAU] / Rs;
+  graw[0] = g[TNFWG_RS] - g[TNFWG_PREF] * d[TNFW_PREF] / Rs - g[TNFWG_TAU] * d[TNFW_TAU] / Rs;
+  graw[3] = g[TNFWG_CX]; graw[4] = g[TNFWG_CY];
+}
+// F(X) of tnfw.py:42-62 (1 at X == 1 exactly, where the scatter leaves the initial value) and dF/dX
+template <class T>
+GL_HD T tnfw_F(T X, T& dF) {
+  T F;
+  if (X < T(1)) { T r = gl_sqrt(T(1) - X * X); F = gl_atanh(r) / r; }
+  else if (X > T(1)) { T r = gl_sqrt(X * X - T(1)); F = gl_atan(r) / r; }
+  else { dF = T(0); return T(1); }
+  dF = (T(1) - X * X * F) / (X * (X * X - T(1)));
+  return F;
+}
+template <class T>
+struct TnfwW { T R0, X, s, L, F, dF, B, gx, a; bool floored; };
+template <class T, class S>
+GL_HD void tnfw_core(const S* d, T dx, T dy, TnfwW<T>& W) {
+  const T Rs = d[TNFW_RS], tau = d[TNFW_TAU];
+  W.R0 = gl_sqrt(dx * dx + dy * dy);
+  const T Rmin = T(0.001) * Rs;
+  W.floored = W.R0 < Rmin;
+  const T R = W.floored ? Rmin : W.R0;
+  W.X = R / Rs;
+  W.s = gl_sqrt(tau * tau + W.X * W.X);
+  W.L = gl_log(W.X / (tau + W.s));
+  W.F = tnfw_F(W.X, W.dF);
+  W.B = (tau * tau + T(2) * W.X * W.X - T(1)) * W.F + T(d[TNFW_C0]) + W.s * (T(d[TNFW_C1]) * W.L - T(GL_PI));
+  W.gx = T(d[TNFW_PRE]) * W.B;
+  W.a = T(d[TNFW_PREF]) * W.gx / (W.X * W.X);
+}
+template <class T, int NP>
+GL_HD void tnfw_fwd(const typename gl_scalar_of<T>::type* d, const T* x, const T* y, T* ax, T* ay) {
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    T dx = x[j] - d[TNFW_CX], dy = y[j] - d[TNFW_CY];
+    TnfwW<T> W;
+    tnfw_core(d, dx, dy, W);
+    ax[j] = W.a * dx; ay[j] = W.a * dy;
+  }
+}
+template <class T, int NP>
+GL_HD void tnfw_bwd(const typename gl_scalar_of<T>::type* d, const T* x, const T* y, const T* gax, const T* gay, T* g) {
+  const T Rs = d[TNFW_RS], tau = d[TNFW_TAU], pref = d[TNFW_PREF], pre = d[TNFW_PRE], c1 = d[TNFW_C1], lnt = d[TNFW_LNT];
+  const T t2 = tau * tau;
+  const T dpre = T(2) * tau * (T(1) - t2) / ((t2 + T(1)) * (t2 + T(1)) * (t2 + T(1)));
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    T dx = x[j] - d[TNFW_CX], dy = y[j] - d[TNFW_CY];
+    TnfwW<T> W;
+    tnfw_core(d, dx, dy, W);
+    const T X = W.X, s = W.s, L = W.L;
+    T ga = gax[j] * dx + gay[j] * dy;
+    T gdx = gax[j] * W.a, gdy = gay[j] * W.a;
+    g[TNFWG_PREF] += ga * W.gx / (X * X);
+    const T ggx = ga * pref / (X * X);
+    const T inner = c1 * L - T(GL_PI);
+    const T dBdX = T(4) * X * W.F + (t2 + T(2) * X * X - T(1)) * W.dF + (X / s) * inner + s * c1 * (T(1) / X - X / (s * (tau + s)));
+    const T dBdt = T(2) * tau * W.F + T(GL_PI) + T(2) * tau * lnt + c1 + (tau / s) * inner + s * (-c1 / s + L * (T(1) + T(1) / t2));
+    const T gX = -T(2) * ga * W.a / X + ggx * pre * dBdX;
+    g[TNFWG_TAU] += ggx * (dpre * W.B + pre * dBdt);
+    g[TNFWG_RS] += -gX * X / Rs;
+    const T gR = gX / Rs;
+    if (W.floored) {
+      g[TNFWG_RS] += gR * T(0.001);
+    } else {
+      gdx += gR * dx / W.R0; gdy += gR * dy / W.R0;
+    }
+    g[TNFWG_CX] -= gdx; g[TNFWG_CY] -= gdy;
+  }
+}
+
+// =============================================================================================
+// dPIEP  (tf/profiles/mass/piep.py:17-56): dPIS with the ellipticity in the potential -- the
+// spherical deflection evaluated at (x sqrt(1-e), y sqrt(1+e)) in the rotated frame and rescaled,
+// exactly the construction of NFW_ELLIPSE around NFW.
+//   raw  : theta_E, Ra, Rs, e1, e2, cx, cy        (deriv argument order, piep.py:33)
+//   d[]  : cx, cy, cos, sin, s1 = sqrt(1-e), s2 = sqrt(1+e), scale = theta_E rt/(rt - rc), rc, rt
+//   dvars: cx, cy, phi, s1, s2, scale, rc, rt
+// =============================================================================================
+enum { PP_CX = 0, PP_CY, PP_C, PP_S, PP_S1, PP_S2, PP_SCALE, PP_RC, PP_RT, PP_SIZE = 12 };
+enum { PPG_CX = 0, PPG_CY, PPG_PHI, PPG_S1, PPG_S2, PPG_SCALE, PPG_RC, PPG_RT };
+template <class T>
+GL_HD void dpiep_prep(const T* raw, T* d) {
+  T rc, rt;
+  dpie_sort(raw[1], raw[2], rc, rt);
+  d[PP_SCALE] = raw[0] * rt / (rt - rc);
+  d[PP_RC] = rc; d[PP_RT] = rt;
+  T phi, q, c;
+  ellip_fwd(raw[3], raw[4], T(0.9999), phi, q, c);
+  T e = gl_abs(T(1) - q * q) / (T(1) + q * q);
+  d[PP_C] = gl_cos(phi); d[PP_S] = gl_sin(phi);
+  d[PP_S1] = gl_sqrt(T(1) - e); d[PP_S2] = gl_sqrt(T(1) + e);
+  d[PP_CX] = raw[5]; d[PP_CY] = raw[6];
+  d[9] = T(0); d[10] = T(0); d[11] = T(0);
+}
+template <class T>
+GL_HD void dpiep_prep_bwd(const T* raw, const T* d, const T* g, T* graw) {
+  const T rc = d[PP_RC], rt = d[PP_RT], theta_E = raw[0];
+  const T dif = rt - rc;
+  graw[0] = g[PPG_SCALE] * rt / dif;
+  const T grt = g[PPG_RT] + g[PPG_SCALE] * theta_E * (-rc) / (dif * dif);
+  const T grc = g[PPG_RC] + g[PPG_SCALE] * theta_E * rt / (dif * dif);
+  dpie_sort_bwd(raw[1], raw[2], grc, grt, graw[1], graw[2]);
+  T phi, q, c;
+  ellip_fwd(raw[3], raw[4], T(0.9999), phi, q, c);
+  const T ge = -g[PPG_S1] / (T(2) * d[PP_S1]) + g[PPG_S2] / (T(2) * d[PP_S2]);
+  const T opq2 = T(1) + q * q;
+  const T gq = ge * (-T(4) * q / (opq2 * opq2));
+  ellip_bwd(raw[3], raw[4], T(0.9999), g[PPG_PHI], gq, graw[3], graw[4]);
+  graw[5] = g[PPG_CX]; graw[6] = g[PPG_CY];
+}
+template <class T, int NP>
+GL_HD void dpiep_fwd(const typename gl_scalar_of<T>::type* d, const T* x, const T* y, T* ax, T* ay) {
+  const T c = d[PP_C], s = d[PP_S], s1 = d[PP_S1], s2 = d[PP_S2], scale = d[PP_SCALE], rc = d[PP_RC], rt = d[PP_RT];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    T dx = x[j] - d[PP_CX], dy = y[j] - d[PP_CY];
+    T xr = (dx * c + dy * s) * s1, yr = (-dx * s + dy * c) * s2;
+    T r2 = xr * xr + yr * yr;
+    T fa = gl_sqrt(r2 + rc * rc) - rc - gl_sqrt(r2 + rt * rt) + rt;
+    T ar = scale / r2 * fa;
+    T fx = ar * xr * s1, fy = ar * yr * s2;
+    ax[j] = fx * c - fy * s; ay[j] = fx * s + fy * c;
+  }
+}
+template <class T, int NP>
+GL_HD void dpiep_bwd(const typename gl_scalar_of<T>::type* d, const T* x, const T* y, const T* gax, const T* gay, T* g) {
+  const T c = d[PP_C], s = d[PP_S], s1 = d[PP_S1], s2 = d[PP_S2], scale = d[PP_SCALE], rc = d[PP_RC], rt = d[PP_RT];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    T dx = x[j] - d[PP_CX], dy = y[j] - d[PP_CY];
+    T xr0 = dx * c + dy * s, yr0 = -dx * s + dy * c;
+    T xr = xr0 * s1, yr = yr0 * s2;
+    T r2 = xr * xr + yr * yr;
+    T sc = gl_sqrt(r2 + rc * rc), st = gl_sqrt(r2 + rt * rt);
+    T fa = sc - rc - st + rt;
+    T ar = scale / r2 * fa;
+    T fx = ar * xr * s1, fy = ar * yr * s2;
+    T ax = fx * c - fy * s, ay = fx * s + fy * c;
+    g[PPG_PHI] += -gax[j] * ay + gay[j] * ax;
+    T gfx = gax[j] * c + gay[j] * s, gfy = -gax[j] * s + gay[j] * c;
+    T gar = gfx * xr * s1 + gfy * yr * s2;
+    T gxr = gfx * ar * s1, gyr = gfy * ar * s2;
+    g[PPG_S1] += gfx * ar * xr;
+    g[PPG_S2] += gfy * ar * yr;
+    g[PPG_SCALE] += gar * fa / r2;
+    T gfa = gar * scale / r2;
+    T gr2 = -gar * ar / r2 + gfa * (T(0.5) / sc - T(0.5) / st);
+    g[PPG_RC] += gfa * (rc / sc - T(1));
+    g[PPG_RT] += gfa * (T(1) - rt / st);
+    gxr += gr2 * T(2) * xr; gyr += gr2 * T(2) * yr;
+    g[PPG_S1] += gxr * xr0;
+    g[PPG_S2] += gyr * yr0;
+    T gxr0 = gxr * s1, gyr0 = gyr * s2;
+    g[PPG_PHI] += gxr0 * yr0 - gyr0 * xr0;
+    T gdx = gxr0 * c - gyr0 * s, gdy = gxr0 * s + gyr0 * c;
+    g[PPG_CX] -= gdx; g[PPG_CY] -= gdy;
+  }
+}
+
+// =============================================================================================
 // SERSIC / SERSIC_ELLIPSE  (tf/profiles/light/sersic.py:29-80)
 //   raw  : R_sersic, n_sersic, [e1, e2,] cx, cy, Ie      (Ie == 1 under use_lstsq, sersic.py:31,76)
 //   d[]  : cx, cy, cos, sin, sq = sqrt(q), isq = 1/sq, 1/R_sersic, 1/n, bn, Ie
@@ -1321,6 +1513,7 @@ GL_HD int gl_n_raw(int type) {
     case GLT_EPL: return 6; case GLT_SHEAR: return 2; case GLT_SIE: return 5; case GLT_SIS: return 3;
     case GLT_NFW: return 4; case GLT_NFW_ELLIPSE: return 6; case GLT_DPIS: return 5; case GLT_DPIE: return 7;
     case GLT_SERSIC: return 5; case GLT_SERSIC_ELLIPSE: return 7; case GLT_SHAPELETS: return 3;
+    case GLT_TNFW: return 5; case GLT_DPIEP: return 7;
   }
   return 0;
 }
@@ -1329,6 +1522,7 @@ GL_HD int gl_n_dvars(int type) {
     case GLT_EPL: return 8; case GLT_SHEAR: return 2; case GLT_SIE: return 6; case GLT_SIS: return 3;
     case GLT_NFW: case GLT_NFW_ELLIPSE: return 7; case GLT_DPIS: case GLT_DPIE: return 7;
     case GLT_SERSIC: case GLT_SERSIC_ELLIPSE: return 8; case GLT_SHAPELETS: return 3;   // + n_layers amplitudes without use_lstsq
+    case GLT_TNFW: return 5; case GLT_DPIEP: return 8;
   }
   return 0;
 }
@@ -1337,6 +1531,7 @@ GL_HD int gl_der_size(int type, int niter, int nmax) {
     case GLT_EPL: return epl_der_size(niter); case GLT_SHEAR: return 4; case GLT_SIE: return SIE_SIZE; case GLT_SIS: return 4;
     case GLT_NFW: case GLT_NFW_ELLIPSE: return NFW_SIZE; case GLT_DPIS: case GLT_DPIE: return DP_SIZE;
     case GLT_SERSIC: case GLT_SERSIC_ELLIPSE: return SER_SIZE; case GLT_SHAPELETS: return shp_der_size(nmax);
+    case GLT_TNFW: return TNFW_SIZE; case GLT_DPIEP: return PP_SIZE;
   }
   return 0;
 }
@@ -1353,6 +1548,8 @@ GL_HD void gl_prep(int type, unsigned flags, int niter, const T* raw, T* d, T ep
     case GLT_NFW_ELLIPSE: nfw_prep(raw, d, true); break;
     case GLT_DPIS: dpie_prep(raw, d, false); break;
     case GLT_DPIE: dpie_prep(raw, d, true); break;
+    case GLT_TNFW: tnfw_prep(raw, d); break;
+    case GLT_DPIEP: dpiep_prep(raw, d); break;
     case GLT_SERSIC: sersic_prep(raw, d, false, (flags & 1u) != 0); break;
     case GLT_SERSIC_ELLIPSE: sersic_prep(raw, d, true, (flags & 1u) != 0); break;
     default: break;
@@ -1369,6 +1566,8 @@ GL_HD void gl_prep_bwd(int type, unsigned flags, const T* raw, const T* d, const
     case GLT_NFW_ELLIPSE: nfw_prep_bwd(raw, d, g, graw, true); break;
     case GLT_DPIS: dpie_prep_bwd(raw, d, g, graw, false); break;
     case GLT_DPIE: dpie_prep_bwd(raw, d, g, graw, true); break;
+    case GLT_TNFW: tnfw_prep_bwd(raw, d, g, graw); break;
+    case GLT_DPIEP: dpiep_prep_bwd(raw, d, g, graw); break;
     case GLT_SERSIC: sersic_prep_bwd(raw, d, g, graw, false, (flags & 1u) != 0); break;
     case GLT_SERSIC_ELLIPSE: sersic_prep_bwd(raw, d, g, graw, true, (flags & 1u) != 0); break;
     default: break;
@@ -1388,6 +1587,8 @@ GL_HD void gl_lens_fwd(int type, int ts, const typename gl_scalar_of<T>::type* d
     case GLT_NFW: case GLT_NFW_ELLIPSE: if constexpr ((F & GLF_NFW) != 0) nfw_fwd<T, NP>(d, x, y, ax, ay); break;
     case GLT_DPIS: if constexpr ((F & GLF_DPIS) != 0) dpis_fwd<T, NP>(d, x, y, ax, ay); break;
     case GLT_DPIE: if constexpr ((F & GLF_DPIE) != 0) dpie_fwd<T, NP>(d, x, y, ax, ay); break;
+    case GLT_TNFW: if constexpr ((F & GLF_TNFW) != 0) tnfw_fwd<T, NP>(d, x, y, ax, ay); break;
+    case GLT_DPIEP: if constexpr ((F & GLF_DPIEP) != 0) dpiep_fwd<T, NP>(d, x, y, ax, ay); break;
     default: break;
   }
 }
@@ -1401,6 +1602,8 @@ GL_HD void gl_lens_bwd(int type, int ts, const typename gl_scalar_of<T>::type* d
     case GLT_NFW: case GLT_NFW_ELLIPSE: if constexpr ((F & GLF_NFW) != 0) nfw_bwd<T, NP>(d, x, y, gax, gay, g); break;
     case GLT_DPIS: if constexpr ((F & GLF_DPIS) != 0) dpis_bwd<T, NP>(d, x, y, gax, gay, g); break;
     case GLT_DPIE: if constexpr ((F & GLF_DPIE) != 0) dpie_bwd<T, NP>(d, x, y, gax, gay, g); break;
+    case GLT_TNFW: if constexpr ((F & GLF_TNFW) != 0) tnfw_bwd<T, NP>(d, x, y, gax, gay, g); break;
+    case GLT_DPIEP: if constexpr ((F & GLF_DPIEP) != 0) dpiep_bwd<T, NP>(d, x, y, gax, gay, g); break;
     default: break;
   }
 }

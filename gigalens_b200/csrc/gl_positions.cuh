@@ -14,7 +14,7 @@
 #include "gl_program.h"
 
 #define GLP_THREADS 32
-constexpr unsigned GLF_LENSES = GLF_EPL | GLF_SHEAR | GLF_SIE | GLF_SIS | GLF_NFW | GLF_DPIS | GLF_DPIE;
+constexpr unsigned GLF_LENSES = GLF_EPL | GLF_SHEAR | GLF_SIE | GLF_SIS | GLF_NFW | GLF_DPIS | GLF_DPIE | GLF_TNFW | GLF_DPIEP;
 
 struct GlRowFlush {   // per-thread cotangent row in shared memory: deterministic, no atomics
   double* row;

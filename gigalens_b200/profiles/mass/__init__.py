@@ -1,1 +1,1 @@
-from . import epl, shear, sie, sis, nfw, piemd, scaling_relation, dpie_subhalo  # noqa: F401
+from . import epl, shear, sie, sis, nfw, piemd, scaling_relation, dpie_subhalo, tnfw, piep  # noqa: F401

@@ -134,8 +134,8 @@ class CompiledModel:
                 d.slot[k] = self._slot(group, pi, name)
             elif name == getattr(prof, "_amp", None) and getattr(prof, "use_lstsq", False):
                 d.constant[k] = 1.0
-            elif type_id == _cabi.GL_DPIE and name in ("center_x", "center_y"):
-                d.constant[k] = 0.0  # DPIE.deriv defaults (piemd.py:106)
+            elif type_id in (_cabi.GL_DPIE, _cabi.GL_DPIEP) and name in ("center_x", "center_y"):
+                d.constant[k] = 0.0  # DPIE.deriv / DPIEP.deriv defaults (piemd.py:106, piep.py:33)
             else:
                 raise KeyError(f"{group}[{pi}] ({prof.name}): parameter '{name}' is neither free nor constant")
         if inner is not None:

@@ -42,6 +42,8 @@ typedef enum {
   GL_NFW_ELLIPSE = 6,  /* Rs, alpha_Rs, e1, e2, center_x, center_y        tf/profiles/mass/nfw.py:99-134 */
   GL_DPIS = 7,         /* theta_E, r_core, r_cut, center_x, center_y      tf/profiles/mass/piemd.py:26-60 */
   GL_DPIE = 8,         /* theta_E, r_core, r_cut, e1, e2, center_x, center_y  tf/profiles/mass/piemd.py:98-119,183-255 */
+  GL_TNFW = 9,         /* Rs, alpha_Rs, r_trunc, center_x, center_y       tf/profiles/mass/tnfw.py:10-62 */
+  GL_DPIEP = 10,       /* theta_E, Ra, Rs, e1, e2, center_x, center_y     tf/profiles/mass/piep.py:17-56 */
   GL_SERSIC = 32,          /* R_sersic, n_sersic, center_x, center_y, Ie          tf/profiles/light/sersic.py:22-35 */
   GL_SERSIC_ELLIPSE = 33,  /* R_sersic, n_sersic, e1, e2, center_x, center_y, Ie  tf/profiles/light/sersic.py:67-80 */
   GL_SHAPELETS = 34        /* beta, center_x, center_y (+ amplitudes)              tf/profiles/light/shapelets.py:17-75 */

@@ -399,6 +399,66 @@ class DPIE(MassBase):
         return didxre, didyre, didyim
 
 
+class TNFW(MassBase):
+    """``tf/profiles/mass/tnfw.py:10-62``."""
+
+    name = "TNFW"
+    params = ["Rs", "alpha_Rs", "r_trunc", "center_x", "center_y"]
+
+    def deriv(self, x, y, Rs, alpha_Rs, r_trunc, center_x, center_y):
+        Rs, alpha_Rs, r_trunc = (_t(v, x) for v in (Rs, alpha_Rs, r_trunc))
+        rho0 = alpha_Rs / (4.0 * Rs ** 2 * (1.0 + math.log(0.5)))  # :18
+        x, y = x - center_x, y - center_y
+        R = torch.sqrt(x ** 2 + y ** 2)
+        R = torch.maximum(R, 0.001 * Rs * torch.ones_like(R))  # :21
+        X = R / Rs
+        tau = r_trunc / Rs
+        L = torch.log(X / (tau + torch.sqrt(tau ** 2 + X ** 2)))  # :25
+        F = self.F(X)
+        gx = (tau ** 2) / (tau ** 2 + 1) ** 2 * (
+            (tau ** 2 + 1 + 2 * (X ** 2 - 1)) * F + tau * np.pi + (tau ** 2 - 1) * torch.log(tau)
+            + torch.sqrt(tau ** 2 + X ** 2) * (-np.pi + L * (tau ** 2 - 1) / tau))  # :27-36
+        a = 4 * rho0 * Rs * gx / X ** 2
+        return a * x, a * y
+
+    @staticmethod
+    def F(x):
+        # :42-62  scatter-update of the x<1 / x>1 entries of a ones tensor
+        lt, gt = x < 1, x > 1
+        x1 = torch.where(lt, x, torch.full_like(x, 0.5))
+        x2 = torch.where(gt, x, torch.full_like(x, 2.0))
+        a1 = 1 / torch.sqrt(1 - x1 ** 2) * torch.atanh(torch.sqrt(1 - x1 ** 2))
+        a2 = 1 / torch.sqrt(x2 ** 2 - 1) * torch.atan(torch.sqrt(x2 ** 2 - 1))
+        a = torch.ones_like(x)
+        a = torch.where(lt, a1, a)
+        a = torch.where(gt, a2, a)
+        return a
+
+
+class DPIEP(MassBase):
+    """``tf/profiles/mass/piep.py:17-56``."""
+
+    name = "dPIE"
+    params = ["theta_E", "Ra", "Rs", "center_x", "center_y", "e1", "e2"]
+
+    def __init__(self):
+        self.spherical = DPIS()
+
+    def deriv(self, x, y, theta_E, Ra, Rs, e1, e2, center_x=0, center_y=0):
+        theta_E, Ra, Rs, e1, e2 = (_t(v, x) for v in (theta_E, Ra, Rs, e1, e2))
+        phi = torch.atan2(e2, e1) / 2  # _param_conv :51-56
+        c = torch.clamp(torch.sqrt(e1 ** 2 + e2 ** 2), max=0.9999)
+        q = (1 - c) / (1 + c)
+        e = torch.abs(1 - q ** 2) / (1 + q ** 2)
+        x, y = x - center_x, y - center_y
+        x, y = _rotate(x, y, phi)
+        x, y = x * torch.sqrt(1 - e), y * torch.sqrt(1 + e)
+        fx, fy = self.spherical.deriv(x, y, theta_E, Ra, Rs, center_x=0, center_y=0)
+        fx = fx * torch.sqrt(1 - e)
+        fy = fy * torch.sqrt(1 + e)
+        return _rotate(fx, fy, -phi)
+
+
 class ScalingRelation(MassBase):
     """``tf/profiles/mass/scaling_relation.py:6-70``: member-galaxy sum of a wrapped profile."""
 

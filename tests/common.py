@@ -12,7 +12,8 @@ from gigalens_b200 import _cabi
 from gigalens_b200.model import PhysicalModel
 from gigalens_b200.profiles.light import sersic as gl_sersic, shapelets as gl_shapelets
 from gigalens_b200.profiles.mass import (dpie_subhalo as gl_sub, epl as gl_epl, nfw as gl_nfw, piemd as gl_piemd,
-                                         scaling_relation as gl_sr, shear as gl_shear, sie as gl_sie, sis as gl_sis)
+                                         scaling_relation as gl_sr, shear as gl_shear, sie as gl_sie, sis as gl_sis,
+                                         tnfw as gl_tnfw, piep as gl_piep)
 from gigalens_b200.simulator import CompiledModel
 from oracle import profiles as OP
 
@@ -27,6 +28,7 @@ def to_oracle_profile(p, dtype=torch.float32):
     table = {
         gl_epl.EPL: lambda: OP.EPL(p.niter), gl_shear.Shear: OP.Shear, gl_sie.SIE: OP.SIE, gl_sis.SIS: OP.SIS,
         gl_nfw.NFW: OP.NFW, gl_nfw.NFW_ELLIPSE: OP.NFW_ELLIPSE, gl_piemd.DPIS: OP.DPIS, gl_piemd.DPIE: OP.DPIE,
+        gl_tnfw.TNFW: OP.TNFW, gl_piep.DPIEP: OP.DPIEP,
         gl_sersic.SersicEllipse: lambda: OP.SersicEllipse(p.use_lstsq), gl_sersic.Sersic: lambda: OP.Sersic(p.use_lstsq),
         gl_shapelets.Shapelets: lambda: OP.Shapelets(p.n_max, p.use_lstsq, p.interpolate, dtype=dtype),
     }
@@ -47,6 +49,7 @@ RANGES = {  # generic, well-conditioned draws per parameter name
     "theta_E": (0.8, 1.6), "gamma": (1.6, 2.4), "e1": (-0.25, 0.25), "e2": (-0.25, 0.25),
     "center_x": (-0.2, 0.2), "center_y": (-0.2, 0.2), "gamma1": (-0.08, 0.08), "gamma2": (-0.08, 0.08),
     "Rs": (0.5, 3.0), "alpha_Rs": (0.5, 2.0), "r_core": (0.02, 0.2), "r_cut": (1.0, 6.0),
+    "r_trunc": (2.0, 8.0), "Ra": (0.02, 0.2),
     "R_sersic": (0.3, 1.2), "n_sersic": (0.8, 5.0), "Ie": (20.0, 300.0), "beta": (0.08, 0.2),
 }
 

@@ -17,7 +17,7 @@ from gigalens_b200 import workloads
 from gigalens_b200.model import ForwardProbModel, PhysicalModel
 from gigalens_b200.model import BackwardProbModel
 from gigalens_b200.profiles.light import sersic, shapelets
-from gigalens_b200.profiles.mass import dpie_subhalo, epl, nfw, piemd, shear, sie, sis
+from gigalens_b200.profiles.mass import dpie_subhalo, epl, nfw, piemd, piep, shear, sie, sis, tnfw
 from gigalens_b200.simulator import LensSimulator, SimulatorConfig
 from oracle import model as OM
 from oracle.simulator import OracleSimulator
@@ -132,6 +132,7 @@ def _catalogue(G=6, seed=7):
 MASS_CASES = {
     "sis": lambda: [sis.SIS()], "sie": lambda: [sie.SIE()], "nfw": lambda: [nfw.NFW()],
     "nfw_ellipse": lambda: [nfw.NFW_ELLIPSE()], "dpis": lambda: [piemd.DPIS()], "dpie": lambda: [piemd.DPIE()],
+    "tnfw": lambda: [tnfw.TNFW()], "dpiep": lambda: [piep.DPIEP()],
     "epl_shear_sis": lambda: [epl.EPL(30), shear.Shear(), sis.SIS()],
     "cluster": lambda: [nfw.NFW(), dpie_subhalo.DPIESubhalo(1.0, _catalogue()), shear.Shear()],
 }

@@ -9,7 +9,7 @@ import torch
 import common
 from common import CompiledModel, PhysicalModel, draw_matrix, host_run, matrix_to_pytree, to_oracle_model
 from gigalens_b200.profiles.light import sersic, shapelets
-from gigalens_b200.profiles.mass import dpie_subhalo, epl, nfw, piemd, shear, sie, sis
+from gigalens_b200.profiles.mass import dpie_subhalo, epl, nfw, piemd, piep, shear, sie, sis, tnfw
 from oracle.simulator import OracleSimulator
 
 SRC = lambda: [sersic.SersicEllipse()]
@@ -30,6 +30,8 @@ MODELS = {
     "nfw_ellipse": lambda: PhysicalModel([nfw.NFW_ELLIPSE()], [], SRC()),
     "dpis": lambda: PhysicalModel([piemd.DPIS()], [], SRC()),
     "dpie": lambda: PhysicalModel([piemd.DPIE()], [], SRC()),
+    "tnfw": lambda: PhysicalModel([tnfw.TNFW()], [], SRC()),
+    "dpiep": lambda: PhysicalModel([piep.DPIEP()], [], SRC()),
     "constants": lambda: PhysicalModel([epl.EPL(20), shear.Shear()], [], [sersic.Sersic()],
                                        lenses_constants=[{"gamma": 2.1, "center_x": 0.05}, {}],
                                        source_light_constants=[{"n_sersic": 1.5}]),
@@ -176,7 +178,7 @@ def _positions_reference(pm, mat, systems, dtype, analytic=True):
     return dict(loglike=ll.detach().numpy(), chi2=chi2.detach().numpy(), gparams=leaf.grad.numpy(), hess=np.stack(H, 1))
 
 
-POS_MODELS = ["c2", "sis", "sie", "nfw", "nfw_ellipse", "dpie", "constants", "cluster"]
+POS_MODELS = ["c2", "sis", "sie", "nfw", "nfw_ellipse", "dpie", "tnfw", "dpiep", "constants", "cluster"]
 
 
 @pytest.mark.parametrize("name", POS_MODELS)
