@@ -109,6 +109,26 @@ __global__ void k_unconstrain(int bs, int d, const GlLeaf* __restrict__ leaves, 
   if (logprior) logprior[b] = lp;
 }
 
+// Chain rule of the bijector for a caller-supplied d(.)/d(params): dz = dparams[slot] * dx/dz (+ d(log prior + fldj)/dz).
+// Lets a driver differentiate the likelihood terms and the prior separately (tempered SMC targets,
+// tf/inference.py:289-302); one thread per sample.
+__global__ void k_chain_grad(int bs, int d, const GlLeaf* __restrict__ leaves, const float* __restrict__ z,
+                             const float* __restrict__ dparams, int with_prior, float* __restrict__ logprior,
+                             float* __restrict__ dz) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= bs) return;
+  float lp = 0.f;
+  for (int k = 0; k < d; ++k) {
+    const GlLeaf L = leaves[k];
+    float x, l, dx, dl;
+    gl_leaf_eval(L, z[(size_t)b * d + k], x, l, dx, dl);
+    lp += l;
+    const float gp = (dparams && L.slot >= 0) ? dparams[(size_t)L.slot * bs + b] : 0.f;
+    dz[(size_t)b * d + k] = gp * dx + (with_prior ? dl : 0.f);
+  }
+  if (logprior) logprior[b] = lp;
+}
+
 // batch maximum of the EPL series ratio f (epl.py:33,37) for the reference-exact trip count
 __global__ void k_epl_fmax(GlProgram P, int bs, const float* __restrict__ params, const float* __restrict__ member_factor,
                            int* __restrict__ fmax_bits) {
@@ -1155,6 +1175,18 @@ int gl_unconstrain(gl_plan* p, const float* z_dev, float* params_dev, float* log
   const int tb = 128, gb = (p->bs + tb - 1) / tb;
   k_unconstrain<<<gb, tb, 0, (cudaStream_t)stream>>>(p->bs, p->d, p->d_leaves, z_dev, params_dev, logprior_dev);
   GL_LAUNCH_CHECK("k_unconstrain");
+  return 0;
+}
+
+/* dz = (d params / d z)^T dparams (+ d log_prior / d z when with_prior); dparams_dev may be NULL (prior gradient only). */
+int gl_chain_grad(gl_plan* p, const float* z_dev, const float* dparams_dev, int32_t with_prior, float* logprior_dev, float* dz_dev,
+                  void* stream) {
+  if (!p || !z_dev || !dz_dev) return gl_fail("gl_chain_grad: NULL argument");
+  if (!p->d_leaves) return gl_fail("gl_chain_grad: gl_plan_set_prior was never called");
+  GL_CUDA(cudaSetDevice(p->device));
+  const int tb = 128, gb = (p->bs + tb - 1) / tb;
+  k_chain_grad<<<gb, tb, 0, (cudaStream_t)stream>>>(p->bs, p->d, p->d_leaves, z_dev, dparams_dev, with_prior, logprior_dev, dz_dev);
+  GL_LAUNCH_CHECK("k_chain_grad");
   return 0;
 }
 

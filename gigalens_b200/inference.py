@@ -11,7 +11,8 @@ the samples / chains; NCCL carries only the small reductions the algorithms need
          (``src/gigalens/jax/inference.py:126-128``).
 * HMC  - per step all-reduce of the acceptance statistic (dual averaging) and the ChEES moments,
          so that adaptation equals the single-device run.
-SMC (``tf/inference.py:184-302``) is out of scope.
+* SMC  - per stage one all-gather of the particles and their cached terms (resampling mixes particles
+         across ranks) and all-reduces of the tempering / tuning statistics.
 """
 import math
 
@@ -297,3 +298,191 @@ class ModellingSequence:
                 samples[it - num_burnin_steps] = z
         stats["n_evals"] = n_evals
         return samples, stats
+
+
+    # ------------------------------------------------------------------ SMC
+    def SMC(self, start=None, num_particles=1000, num_ensembles=1, num_leapfrog_steps=10, post_sampling_steps=100,
+            ess_threshold_ratio=0.8, max_sampling_per_stage=8, target="pixels", auxiliar="positions", seed=1,
+            max_stage=100, min_sampling_per_stage=1, optimal_accept=0.651):
+        """``tf/inference.py:184-302``: adaptively tempered sequential Monte Carlo from the prior to the
+        posterior with an auxiliary likelihood, followed by ``post_sampling_steps`` HMC steps.
+
+        The stage target is ``prior + aux + beta (like - aux)`` (``make_tempered_target_log_prob_fn_with_auxiliar``,
+        ``:289-302``): with ``auxiliar='positions'`` the particles are first pulled to models that reproduce the image
+        positions and the pixel likelihood is switched on gradually.  The outer algorithm restates
+        ``tfp.experimental.mcmc.sample_sequential_monte_carlo`` (tensorflow-probability >= 0.19, not vendored in the
+        reference): per ensemble, the next inverse temperature is found by bisection so that the effective sample size
+        of the incremental weights ``exp((beta' - beta) like)`` equals ``ess_threshold_ratio N`` (the reference call
+        hard-codes 0.8 and ``max_num_steps=8`` whatever its own arguments say -- those are the defaults here);
+        systematic resampling; HMC mutation with ``num_leapfrog_steps`` and per-particle step size
+        ``scaling_i * std(z) / num_leapfrog_steps`` (``gen_make_hmc_kernel_fn``); ``simple_heuristic_tuning`` of the
+        scalings and of the number of mutation steps (``optimal_accept=0.651``).  Like TFP, the incremental weights use
+        the target likelihood only (the auxiliary term enters the mutation target, not the weights).
+
+        Returns ``(samples, info)``: samples ``(post_sampling_steps, n_local, d)`` of this rank's particles, or the
+        final particle cloud ``(num_particles, num_ensembles, d)`` when ``post_sampling_steps == 0``."""
+        import torch
+
+        dist, rank, world = _dist()
+        pm = self.prob_model
+        E, P_ = int(num_ensembles), int(num_particles)
+        N = E * P_
+        if start is None:
+            z_all = np.asarray(pm.bij_inverse(pm.prior.sample(N, seed=seed)), dtype=np.float32)
+        else:
+            flat = np.asarray(start.cpu() if hasattr(start, "cpu") else start, dtype=np.float32)
+            flat = flat.reshape(-1, flat.shape[-1])
+            z_all = flat[np.random.default_rng(seed).integers(0, flat.shape[0], size=N)]   # tf.random.categorical(:201-203)
+        d = z_all.shape[1]
+        lo, hi = _shard(N, rank, world)
+        nloc = hi - lo
+        sim = self._simulator_cls(self.phys_model, self.sim_config, bs=nloc)
+        dev = sim.device
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(seed * 1000003 + rank)
+        shared = torch.Generator(device="cpu")
+        shared.manual_seed(seed)                                   # resampling offsets: identical on every rank
+        ens_all = torch.arange(N, device=dev) % E                  # particle n belongs to ensemble n % E (reshape (P, E))
+        sizes = [_shard(N, r, world)[1] - _shard(N, r, world)[0] for r in range(world)]
+
+        def gather(t):
+            if world == 1:
+                return t
+            pad = torch.zeros((max(sizes),) + tuple(t.shape[1:]), device=dev, dtype=t.dtype)
+            pad[: t.shape[0]] = t
+            parts = [torch.empty_like(pad) for _ in range(world)]
+            dist.all_gather(parts, pad)
+            return torch.cat([q[:n] for q, n in zip(parts, sizes)], 0)
+
+        def terms(zz):
+            lp, glp = pm.log_prior_and_grad(sim, zz)
+            ll, gll = pm.term_and_grad(sim, zz, target)
+            la, gla = pm.term_and_grad(sim, zz, auxiliar)
+            scrub = lambda v, g: (torch.where(torch.isfinite(v), v, torch.full_like(v, -float("inf"))),
+                                  torch.nan_to_num(g, nan=0.0, posinf=0.0, neginf=0.0))
+            (lp, glp), (ll, gll), (la, gla) = scrub(lp, glp), scrub(ll, gll), scrub(la, gla)
+            return torch.stack([lp, ll, la], 1).clone(), torch.stack([glp, gll, gla], 1).clone()   # (n, 3), (n, 3, d)
+
+        def tempered(val, grd, b):           # b: (n,) inverse temperature of each particle's ensemble
+            v = val[:, 0] + val[:, 2] + b * (val[:, 1] - val[:, 2])
+            g = grd[:, 0] + grd[:, 2] + b[:, None] * (grd[:, 1] - grd[:, 2])
+            return torch.where(torch.isnan(v), torch.full_like(v, -float("inf")), v), g
+
+        def hmc_steps(z, val, grd, b, eps, n_steps):
+            """n_steps HMC transitions (identity mass) of the local particles; returns the log mean accept prob."""
+            acc_sum = torch.zeros(z.shape[0], device=dev)
+            n_eval = 0
+            for _ in range(n_steps):
+                lp0, g0 = tempered(val, grd, b)
+                p0 = torch.randn(z.shape, device=dev, generator=gen)
+                zc, pc = z.clone(), p0 + 0.5 * eps * g0
+                for leap in range(num_leapfrog_steps):
+                    zc = zc + eps * pc
+                    vc, gc = terms(zc)
+                    n_eval += z.shape[0]
+                    lpc, gcur = tempered(vc, gc, b)
+                    pc = pc + (eps if leap < num_leapfrog_steps - 1 else 0.5 * eps) * gcur
+                log_acc = (lpc - 0.5 * (pc ** 2).sum(1)) - (lp0 - 0.5 * (p0 ** 2).sum(1))
+                log_acc = torch.where(torch.isfinite(log_acc), log_acc, torch.full_like(log_acc, -float("inf")))
+                accept = torch.log(torch.rand(z.shape[0], device=dev, generator=gen)) < log_acc
+                z = torch.where(accept[:, None], zc, z)
+                val = torch.where(accept[:, None], vc, val)
+                grd = torch.where(accept[:, None, None], gc, grd)
+                acc_sum += torch.exp(torch.clamp(log_acc, max=0.0))
+            return z, val, grd, torch.log(torch.clamp(acc_sum / max(n_steps, 1), min=1e-30)), n_eval
+
+        z = torch.as_tensor(z_all[lo:hi], device=dev).clone()
+        val, grd = terms(z)
+        beta = torch.zeros(E, device=dev)
+        log_scal = torch.full((nloc,), math.log(min(1.0, 2.38 ** 2 / d)), device=dev)
+        n_steps, stage, n_evals = int(max_sampling_per_stage), 0, nloc
+        log_evidence = torch.zeros(E, device=dev)
+        info = {"inverse_temperature": [], "num_steps": [], "accept_prob": []}
+        log_acc_loc = None
+        while bool((beta < 1).any()) and stage < max_stage:
+            # ---- all particles on every rank (small: N x (1 + 3 + 3d + d) floats)
+            Z, V, G, LS = gather(z), gather(val), gather(grd), gather(log_scal)
+            ll = V[:, 1].double()
+            new_beta = beta.clone()
+            idx_all = torch.arange(N, device=dev)
+            for e in range(E):
+                m = ens_all == e
+                le = ll[m]
+                le = torch.where(torch.isfinite(le), le, torch.full_like(le, -1e300))
+
+                def ess_ratio(delta):
+                    lw = delta * le
+                    lw = lw - torch.logsumexp(lw, 0)
+                    return float(torch.exp(-torch.logsumexp(2 * lw, 0))) / le.numel()
+
+                b0, room = float(beta[e]), 1.0 - float(beta[e])
+                if room <= 0:
+                    continue
+                if ess_ratio(room) >= ess_threshold_ratio:
+                    delta = room
+                else:
+                    a_, c_ = 0.0, room
+                    for _ in range(50):
+                        mid = 0.5 * (a_ + c_)
+                        if ess_ratio(mid) >= ess_threshold_ratio:
+                            a_ = mid
+                        else:
+                            c_ = mid
+                    delta = max(a_, 1e-12)
+                new_beta[e] = min(1.0, b0 + delta)
+                lw = delta * le
+                log_evidence[e] += float(torch.logsumexp(lw, 0) - math.log(le.numel()))
+                w = torch.softmax(lw, 0)
+                # systematic resampling (tfe.mcmc.resample_systematic): one uniform offset per ensemble
+                n_e = le.numel()
+                u0 = float(torch.rand(1, generator=shared))
+                pts = (torch.arange(n_e, device=dev, dtype=torch.float64) + u0) / n_e
+                pick = torch.searchsorted(torch.cumsum(w, 0), pts).clamp_(max=n_e - 1)
+                idx_all[m] = idx_all[m][pick]
+            beta = new_beta
+            sel = idx_all[lo:hi]
+            z, val, grd, log_scal = Z[sel].clone(), V[sel].clone(), G[sel].clone(), LS[sel].clone()
+            # ---- tuning (simple_heuristic_tuning) from the previous stage's acceptance
+            if log_acc_loc is not None:
+                LA = gather(log_acc_loc)[sel]
+                tot = torch.zeros(2 * E + 1, device=dev)
+                ens_loc = ens_all[lo:hi]
+                tot[:E].index_add_(0, ens_loc, torch.exp(log_scal))
+                tot[E:2 * E].index_add_(0, ens_loc, torch.exp(LA))
+                tot[2 * E] = float(nloc)
+                if world > 1:
+                    dist.all_reduce(tot)
+                per_e = N / E
+                avg_scal, avg_acc = tot[:E] / per_e, tot[E:2 * E] / per_e
+                log_scal = math.log(0.5) + torch.logaddexp(torch.log(avg_scal[ens_loc]) + (avg_acc[ens_loc] - optimal_accept),
+                                                           log_scal + (torch.exp(LA) - optimal_accept))
+                a = float(avg_acc.mean().clamp(1e-6, 1 - 1e-6))
+                n_steps = int(min(max_sampling_per_stage, max(min_sampling_per_stage, math.ceil(math.log1p(-0.99) / math.log1p(-a)))))
+            # ---- mutation: step size = scaling * std(z) / L, std over ALL particles of the ensemble
+            Zs = gather(z)
+            std = torch.stack([Zs[ens_all == e].std(0, unbiased=False) for e in range(E)], 0)      # (E, d)
+            ens_loc = ens_all[lo:hi]
+            eps = torch.exp(log_scal)[:, None] * std[ens_loc] / float(num_leapfrog_steps)
+            z, val, grd, log_acc_loc, ne = hmc_steps(z, val, grd, beta[ens_loc], eps, n_steps)
+            n_evals += ne
+            stage += 1
+            info["inverse_temperature"].append(beta.cpu().tolist())
+            info["num_steps"].append(n_steps)
+            info["accept_prob"].append(float(torch.exp(log_acc_loc).mean()))
+        info.update(stages=stage, log_evidence=log_evidence.cpu().tolist())
+        if post_sampling_steps <= 0:
+            info["n_evals"] = n_evals
+            return gather(z).reshape(P_, E, d), info
+        # ---- HMC on the full posterior prior + like with the final step sizes (:262-286)
+        Zs = gather(z)
+        std = torch.stack([Zs[ens_all == e].std(0, unbiased=False) for e in range(E)], 0)
+        ens_loc = ens_all[lo:hi]
+        eps = torch.exp(log_scal)[:, None] * std[ens_loc] / float(num_leapfrog_steps)
+        ones = torch.ones(nloc, device=dev)
+        samples = torch.empty((post_sampling_steps, nloc, d), device=dev)
+        for it in range(post_sampling_steps):
+            z, val, grd, la_, ne = hmc_steps(z, val, grd, ones, eps, 1)
+            n_evals += ne
+            samples[it] = z
+        info["n_evals"] = n_evals
+        return samples, info

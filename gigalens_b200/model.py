@@ -150,6 +150,27 @@ class ProbabilisticModel:
         return lp
 
 
+    def log_prior_and_grad(self, simulator, z):
+        """``log_prior(z)`` and its gradient w.r.t. ``z`` (bijector chain rule only, ``gl_chain_grad``)."""
+        torch = simulator._torch
+        self._bind(simulator)
+        z = torch.as_tensor(z, dtype=torch.float32, device=simulator.device).contiguous()
+        lp = torch.empty((simulator.bs,), dtype=torch.float32, device=simulator.device)
+        dz = torch.empty_like(z)
+        _cabi.check(simulator._lib.gl_chain_grad(simulator._plan, z.data_ptr(), None, 1, lp.data_ptr(), dz.data_ptr(),
+                                                 simulator._stream()), simulator._lib)
+        return lp, dz
+
+    def chain_to_z(self, simulator, z, dparams):
+        """``(d params / d z)^T dparams``: pull a ``[P][bs]`` parameter gradient back to ``z`` (no prior term)."""
+        torch = simulator._torch
+        self._bind(simulator)
+        dz = torch.empty_like(z)
+        _cabi.check(simulator._lib.gl_chain_grad(simulator._plan, z.data_ptr(), dparams.data_ptr(), 0, None, dz.data_ptr(),
+                                                 simulator._stream()), simulator._lib)
+        return dz
+
+
 def _autograd_wrap(torch, fn, z):
     """Attach the hand-written gradient to autograd when ``z`` requires grad."""
 
@@ -255,6 +276,38 @@ class ForwardProbModel(ProbabilisticModel):
             if self.include_positions:
                 simulator.set_option("include_positions", 1)
         return ll, chi
+
+    def term_and_grad(self, simulator, z, term):
+        """One likelihood term and its gradient w.r.t. ``z``: ``term`` is ``'pixels'`` (``stats_pixels``),
+        ``'positions'`` (``stats_positions``) or ``'none'`` (zeros) -- the target / auxiliary choices of
+        ``ModellingSequence.SMC`` (``tf/inference.py:208-214``).  Returns ``(log_like (bs,), dz (bs, d))``."""
+        torch = simulator._torch
+        z = torch.as_tensor(z, dtype=torch.float32, device=simulator.device).contiguous()
+        if term == "none":
+            return torch.zeros(simulator.bs, device=simulator.device), torch.zeros_like(z)
+        params = self.bij_forward(simulator, z)
+        self._own(simulator)
+        mat = simulator._params_matrix(params)
+        if term == "positions":
+            if not self.include_positions:
+                raise ValueError("term 'positions' needs a model built with centroids")
+            ll, _, g = simulator.positions_loglike(mat, want_grad=True)
+        elif term == "pixels":
+            if not self.include_pixels:
+                raise ValueError("term 'pixels' needs a model built with an observed image")
+            ll = torch.empty((simulator.bs,), dtype=torch.float32, device=simulator.device)
+            chi, g = torch.empty_like(ll), torch.empty_like(mat)
+            if self.include_positions:
+                simulator.set_option("include_positions", 0)
+            try:
+                _cabi.check(simulator._lib.gl_loglike_grad(simulator._plan, mat.data_ptr(), ll.data_ptr(), chi.data_ptr(),
+                                                           g.data_ptr(), simulator._stream()), simulator._lib)
+            finally:
+                if self.include_positions:
+                    simulator.set_option("include_positions", 1)
+        else:
+            raise ValueError(f"unknown likelihood term {term!r}")
+        return ll, self.chain_to_z(simulator, z, g)
 
     def loglike_and_grad(self, simulator, params):
         """log-likelihood (pixels and/or positions as configured), red_chi2 and d(log_like)/d(params) as a

@@ -179,6 +179,11 @@ int gl_logprob_grad(gl_plan* plan, const float* z_dev, float* logp_dev, float* r
                     void* stream);
 /* bij.forward(z) -> params[P][bs] and log_prior(z) [bs] (either output may be NULL): tf/model.py:148,164-166,183-185 */
 int gl_unconstrain(gl_plan* plan, const float* z_dev, float* params_dev, float* logprior_dev, void* stream);
+/* Chain rule of the bijector alone: dz[bs][d] = (d params/d z)^T dparams_dev[P][bs] (+ d(log_prior + fldj)/dz when
+ * with_prior != 0); dparams_dev may be NULL (prior gradient only); logprior_dev [bs] or NULL.  The pieces a
+ * tempered target prior + aux + beta (like - aux) needs (tf/inference.py:289-302). */
+int gl_chain_grad(gl_plan* plan, const float* z_dev, const float* dparams_dev, int32_t with_prior, float* logprior_dev,
+                  float* dz_dev, void* stream);
 
 /* Host-buffer convenience wrappers (pinned or pageable host memory): copy in, run, copy out,
  * synchronise.  These are the calls a reference-side binding would make per optimiser step. */

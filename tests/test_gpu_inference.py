@@ -67,3 +67,45 @@ def test_map_improves_fit_on_demo_image():
     seq.MAP(Adam(PolynomialDecay(1e-2, 150, 2e-3)), n_samples=64, num_steps=150, seed=0,
             callback=lambda i, chi: hist.append(float(torch.nan_to_num(chi, nan=1e30).min())))
     assert hist[-1] < 0.2 * hist[0] and hist[-1] < 10.0
+
+
+def _positions_setup():
+    """C2 model with one quadruply imaged point source: centroids from a 4-image cross around the Einstein ring."""
+    prior, phys = workloads.demo_prior(), workloads.demo_phys_model()
+    cx, cy = [np.array([1.1, -1.1, 0.05, -0.05], np.float32)], [np.array([0.05, -0.05, 1.1, -1.1], np.float32)]
+    err = [np.full(4, 0.05, np.float32)]
+    prob = ForwardProbModel(prior, workloads.load_demo_image(), background_rms=0.2, exp_time=100.0,
+                            centroids_x=cx, centroids_y=cy, centroids_errors_x=err, centroids_errors_y=err)
+    return prior, phys, prob, workloads.demo_sim_config()
+
+
+def test_separable_terms_add_up_to_log_prob():
+    """prior + pixels + positions (ModellingSequence.SMC's building blocks, tf/inference.py:208-233) equal the fused
+    log_prob and its gradient."""
+    prior, phys, prob, cfg = _positions_setup()
+    bs = 6
+    sim = LensSimulator(phys, cfg, bs=bs)
+    z = torch.as_tensor(prob.bij_inverse(prior.sample(bs, seed=4)), device="cuda")
+    logp, _, dz = prob.log_prob_and_grad(sim, z)
+    lp, glp = prob.log_prior_and_grad(sim, z)
+    l1, g1 = prob.term_and_grad(sim, z, "pixels")
+    l2, g2 = prob.term_and_grad(sim, z, "positions")
+    l0, g0 = prob.term_and_grad(sim, z, "none")
+    assert torch.allclose(lp, prob.log_prior(sim, z)) and float(l0.abs().max()) == 0 and float(g0.abs().max()) == 0
+    tot, gtot = (lp + l1 + l2).cpu().numpy(), (glp + g1 + g2).cpu().numpy()
+    assert np.allclose(tot, logp.cpu().numpy(), rtol=2e-6)
+    scale = np.abs(dz.cpu().numpy()).max(0)
+    assert np.all(np.abs(gtot - dz.cpu().numpy()) <= 1e-5 * scale)
+
+
+def test_smc_with_position_auxiliary_runs_and_tempers_to_one():
+    prior, phys, prob, cfg = _positions_setup()
+    seq = ModellingSequence(phys, prob, cfg)
+    samples, info = seq.SMC(num_particles=48, num_ensembles=1, num_leapfrog_steps=3, post_sampling_steps=4,
+                            max_sampling_per_stage=2, max_stage=40, seed=1)
+    assert samples.shape == (4, 48, 22) and bool(torch.isfinite(samples).all())
+    betas = np.asarray(info["inverse_temperature"])[:, 0]
+    assert np.all(np.diff(betas) >= 0) and 0 < betas[0] <= 1 and info["stages"] <= 40
+    cloud, info2 = seq.SMC(num_particles=32, num_leapfrog_steps=2, post_sampling_steps=0, max_sampling_per_stage=1,
+                           max_stage=3, target="positions", auxiliar="none", seed=2)
+    assert cloud.shape == (32, 1, 22) and info2["stages"] <= 3
