@@ -1143,8 +1143,34 @@ GL_HD T tnfw_F(T X, T& dF) {
   dF = (T(1) - X * X * F) / (X * (X * X - T(1)));
   return F;
 }
+// The bracket of g(X, tau) cancels to O(X^2 log X) for small X while its terms are O(1) (the same
+// cancellation as NFW's ln(X/2) + F(X), with more terms): in fp32 the deflection inside X ~ 0.03 has no
+// correct digits left.  The TNFW pixel functions therefore run in the promoted type (fp32 -> FP64, which
+// is full-rate enough on B200 for an optional profile) and recompute the tau-only constants there.
+template <class T> struct gl_promote { typedef T type; };
+template <> struct gl_promote<float> { typedef double type; };
+template <> struct gl_promote<GlDual<float> > { typedef GlDual<double> type; };
+GL_HD double gl_up(float a) { return (double)a; }
+GL_HD double gl_up(double a) { return a; }
+GL_HD GlDual<double> gl_up(GlDual<float> a) { return GlDual<double>((double)a.v, (double)a.d); }
+GL_HD GlDual<double> gl_up(GlDual<double> a) { return a; }
+template <class T> struct gl_narrow_t { template <class C> static GL_HD T f(C c) { return (T)c; } };
+template <class S> struct gl_narrow_t<GlDual<S> > { template <class C> static GL_HD GlDual<S> f(C c) { return GlDual<S>((S)c.v, (S)c.d); } };
+
 template <class T>
 struct TnfwW { T R0, X, s, L, F, dF, B, gx, a; bool floored; };
+// dd[]: the derived block in the compute precision CS, tau-only constants recomputed
+template <class S, class CS>
+GL_HD void tnfw_consts(const S* d, CS* dd) {
+  dd[TNFW_CX] = CS(d[TNFW_CX]); dd[TNFW_CY] = CS(d[TNFW_CY]); dd[TNFW_RS] = CS(d[TNFW_RS]);
+  dd[TNFW_PREF] = CS(d[TNFW_PREF]);
+  const CS tau = CS(d[TNFW_TAU]), t2 = tau * tau, lnt = gl_log(tau);
+  dd[TNFW_TAU] = tau;
+  dd[TNFW_PRE] = t2 / ((t2 + CS(1)) * (t2 + CS(1)));
+  dd[TNFW_C0] = (t2 - CS(1)) * lnt;            // tau*pi is folded into pi (tau - s) = -pi X^2 / (tau + s) per pixel
+  dd[TNFW_C1] = (t2 - CS(1)) / tau;
+  dd[TNFW_LNT] = lnt;
+}
 template <class T, class S>
 GL_HD void tnfw_core(const S* d, T dx, T dy, TnfwW<T>& W) {
   const T Rs = d[TNFW_RS], tau = d[TNFW_TAU];
@@ -1156,48 +1182,58 @@ GL_HD void tnfw_core(const S* d, T dx, T dy, TnfwW<T>& W) {
   W.s = gl_sqrt(tau * tau + W.X * W.X);
   W.L = gl_log(W.X / (tau + W.s));
   W.F = tnfw_F(W.X, W.dF);
-  W.B = (tau * tau + T(2) * W.X * W.X - T(1)) * W.F + T(d[TNFW_C0]) + W.s * (T(d[TNFW_C1]) * W.L - T(GL_PI));
+  W.B = (tau * tau + T(2) * W.X * W.X - T(1)) * W.F + T(d[TNFW_C0]) - T(GL_PI) * W.X * W.X / (tau + W.s) + W.s * T(d[TNFW_C1]) * W.L;
   W.gx = T(d[TNFW_PRE]) * W.B;
   W.a = T(d[TNFW_PREF]) * W.gx / (W.X * W.X);
 }
 template <class T, int NP>
 GL_HD void tnfw_fwd(const typename gl_scalar_of<T>::type* d, const T* x, const T* y, T* ax, T* ay) {
+  typedef typename gl_promote<T>::type C;
+  typedef typename gl_scalar_of<C>::type CS;
+  CS dd[TNFW_SIZE];
+  tnfw_consts(d, dd);
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
-    T dx = x[j] - d[TNFW_CX], dy = y[j] - d[TNFW_CY];
-    TnfwW<T> W;
-    tnfw_core(d, dx, dy, W);
-    ax[j] = W.a * dx; ay[j] = W.a * dy;
+    C dx = gl_up(x[j]) - dd[TNFW_CX], dy = gl_up(y[j]) - dd[TNFW_CY];
+    TnfwW<C> W;
+    tnfw_core(dd, dx, dy, W);
+    ax[j] = gl_narrow_t<T>::f(W.a * dx); ay[j] = gl_narrow_t<T>::f(W.a * dy);
   }
 }
 template <class T, int NP>
 GL_HD void tnfw_bwd(const typename gl_scalar_of<T>::type* d, const T* x, const T* y, const T* gax, const T* gay, T* g) {
-  const T Rs = d[TNFW_RS], tau = d[TNFW_TAU], pref = d[TNFW_PREF], pre = d[TNFW_PRE], c1 = d[TNFW_C1], lnt = d[TNFW_LNT];
-  const T t2 = tau * tau;
-  const T dpre = T(2) * tau * (T(1) - t2) / ((t2 + T(1)) * (t2 + T(1)) * (t2 + T(1)));
+  typedef typename gl_promote<T>::type C;
+  typedef typename gl_scalar_of<C>::type CS;
+  CS dd[TNFW_SIZE];
+  tnfw_consts(d, dd);
+  const C Rs = dd[TNFW_RS], tau = dd[TNFW_TAU], pref = dd[TNFW_PREF], pre = dd[TNFW_PRE], c1 = dd[TNFW_C1], lnt = dd[TNFW_LNT];
+  const C t2 = tau * tau;
+  const C dpre = C(2) * tau * (C(1) - t2) / ((t2 + C(1)) * (t2 + C(1)) * (t2 + C(1)));
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
-    T dx = x[j] - d[TNFW_CX], dy = y[j] - d[TNFW_CY];
-    TnfwW<T> W;
-    tnfw_core(d, dx, dy, W);
-    const T X = W.X, s = W.s, L = W.L;
-    T ga = gax[j] * dx + gay[j] * dy;
-    T gdx = gax[j] * W.a, gdy = gay[j] * W.a;
-    g[TNFWG_PREF] += ga * W.gx / (X * X);
-    const T ggx = ga * pref / (X * X);
-    const T inner = c1 * L - T(GL_PI);
-    const T dBdX = T(4) * X * W.F + (t2 + T(2) * X * X - T(1)) * W.dF + (X / s) * inner + s * c1 * (T(1) / X - X / (s * (tau + s)));
-    const T dBdt = T(2) * tau * W.F + T(GL_PI) + T(2) * tau * lnt + c1 + (tau / s) * inner + s * (-c1 / s + L * (T(1) + T(1) / t2));
-    const T gX = -T(2) * ga * W.a / X + ggx * pre * dBdX;
-    g[TNFWG_TAU] += ggx * (dpre * W.B + pre * dBdt);
-    g[TNFWG_RS] += -gX * X / Rs;
-    const T gR = gX / Rs;
+    C dx = gl_up(x[j]) - dd[TNFW_CX], dy = gl_up(y[j]) - dd[TNFW_CY];
+    const C gx_ = gl_up(gax[j]), gy_ = gl_up(gay[j]);
+    TnfwW<C> W;
+    tnfw_core(dd, dx, dy, W);
+    const C X = W.X, s = W.s, L = W.L;
+    C ga = gx_ * dx + gy_ * dy;
+    C gdx = gx_ * W.a, gdy = gy_ * W.a;
+    g[TNFWG_PREF] += gl_narrow_t<T>::f(ga * W.gx / (X * X));
+    const C ggx = ga * pref / (X * X);
+    const C inner = c1 * L - C(GL_PI);
+    const C dBdX = C(4) * X * W.F + (t2 + C(2) * X * X - C(1)) * W.dF + (X / s) * inner + s * c1 * (C(1) / X - X / (s * (tau + s)));
+    const C dBdt = C(2) * tau * W.F + C(GL_PI) + C(2) * tau * lnt + c1 + (tau / s) * inner + s * (-c1 / s + L * (C(1) + C(1) / t2));
+    const C gX = -C(2) * ga * W.a / X + ggx * pre * dBdX;
+    C gRs = -gX * X / Rs;
+    const C gR = gX / Rs;
     if (W.floored) {
-      g[TNFWG_RS] += gR * T(0.001);
+      gRs += gR * C(0.001);
     } else {
       gdx += gR * dx / W.R0; gdy += gR * dy / W.R0;
     }
-    g[TNFWG_CX] -= gdx; g[TNFWG_CY] -= gdy;
+    g[TNFWG_TAU] += gl_narrow_t<T>::f(ggx * (dpre * W.B + pre * dBdt));
+    g[TNFWG_RS] += gl_narrow_t<T>::f(gRs);
+    g[TNFWG_CX] -= gl_narrow_t<T>::f(gdx); g[TNFWG_CY] -= gl_narrow_t<T>::f(gdy);
   }
 }
 
