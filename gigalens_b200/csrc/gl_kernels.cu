@@ -951,10 +951,16 @@ static int gl_run_raytrace_fwd(gl_plan* p, float* ss_out, int no_deflection, cud
   dim3 grid(p->chunks, p->bs);
   GL_CUDA(cudaMemsetAsync(p->d_nan, 0, (size_t)p->bs * sizeof(int), st));
   const size_t smem = (size_t)p->prog.der_total * sizeof(float);
-  if (p->feat_idx == 0 && (p->npix % 2) == 0 && p->use_packed) {
-    if (smem > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_fwd_p<4, GL_FS0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_raytrace_fwd_p<4, GL_FS0><<<grid, GLK_THREADS, smem, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,
-                                                                 p->d_derived, no_deflection, ss_out, p->d_nan);
+  if ((p->feat_idx == 0 || p->feat_idx == 2) && (p->npix % 2) == 0 && p->use_packed) {   // two pixels per lane slot (FFMA2)
+    if (p->feat_idx == 0) {
+      if (smem > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_fwd_p<4, GL_FS0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_raytrace_fwd_p<4, GL_FS0><<<grid, GLK_THREADS, smem, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,
+                                                                   p->d_derived, no_deflection, ss_out, p->d_nan);
+    } else {
+      if (smem > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_fwd_p<4, GL_FS2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_raytrace_fwd_p<4, GL_FS2><<<grid, GLK_THREADS, smem, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,
+                                                                   p->d_derived, no_deflection, ss_out, p->d_nan);
+    }
     GL_LAUNCH_CHECK("k_raytrace_fwd_p");
     return 0;
   }
@@ -970,10 +976,16 @@ static int gl_run_raytrace_fwd(gl_plan* p, float* ss_out, int no_deflection, cud
 static int gl_run_raytrace_bwd(gl_plan* p, const float* gss, int no_deflection, cudaStream_t st) {
   dim3 grid(p->chunks, p->bs);
   const size_t smem = (size_t)(p->prog.der_total + (GLK_THREADS / 32) * p->prog.g_total) * sizeof(float);
-  if (p->feat_idx == 0 && (p->npix % 2) == 0 && p->use_packed) {
-    if (smem > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_bwd_p<4, GL_FS0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_raytrace_bwd_p<4, GL_FS0><<<grid, GLK_THREADS, smem, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,
-                                                                 p->d_derived, no_deflection, gss, p->d_gpart, p->d_nan);
+  if ((p->feat_idx == 0 || p->feat_idx == 2) && (p->npix % 2) == 0 && p->use_packed) {
+    if (p->feat_idx == 0) {
+      if (smem > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_bwd_p<4, GL_FS0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_raytrace_bwd_p<4, GL_FS0><<<grid, GLK_THREADS, smem, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,
+                                                                   p->d_derived, no_deflection, gss, p->d_gpart, p->d_nan);
+    } else {
+      if (smem > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_bwd_p<4, GL_FS2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_raytrace_bwd_p<4, GL_FS2><<<grid, GLK_THREADS, smem, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,
+                                                                   p->d_derived, no_deflection, gss, p->d_gpart, p->d_nan);
+    }
     GL_LAUNCH_CHECK("k_raytrace_bwd_p");
     return 0;
   }

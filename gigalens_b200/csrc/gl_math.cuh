@@ -148,6 +148,7 @@ GL_HD GlF2 gl_log2_fast(GlF2 a) { return GlF2(gl_log2_fast(a.x), gl_log2_fast(a.
 GL_HD GlF2 gl_exp2_fast(GlF2 a) { return GlF2(gl_exp2_fast(a.x), gl_exp2_fast(a.y)); }
 GL_HD GlF2 gl_rsqrt_fast(GlF2 a) { return GlF2(gl_rsqrt_fast(a.x), gl_rsqrt_fast(a.y)); }
 GL_HD GlF2 gl_div_fast(GlF2 a, GlF2 b) { return GlF2(gl_div_fast(a.x, b.x), gl_div_fast(a.y, b.y)); }
+GL_HD GlF2 gl_atan2_fast(GlF2 y, GlF2 x) { return GlF2(gl_atan2_fast(y.x, x.x), gl_atan2_fast(y.y, x.y)); }
 GL_HD GlF2 gl_min(GlF2 a, GlF2 b) { return GlF2(fminf(a.x, b.x), fminf(a.y, b.y)); }
 GL_HD GlF2 gl_max(GlF2 a, GlF2 b) { return GlF2(fmaxf(a.x, b.x), fmaxf(a.y, b.y)); }
 // per-lane selects: (a > t ? vt : vf), (lo <= a <= hi ? vt : vf)
@@ -822,6 +823,39 @@ GL_HD void nfw_bwd(const typename gl_scalar_of<T>::type* d, const T* x, const T*
   }
 }
 
+// Lane adaptor: NFW has per-pixel branches (g(X) piecewise) and no packed implementation -- it is one halo
+// next to tens of dPIE members -- so the two pixels of a GlF2 lane slot are evaluated as scalars.
+template <class T, int NP>
+struct NfwLane {
+  typedef typename gl_scalar_of<T>::type S;
+  static GL_HD void fwd(const S* d, const T* x, const T* y, T* ax, T* ay) { nfw_fwd<T, NP>(d, x, y, ax, ay); }
+  static GL_HD void bwd(const S* d, const T* x, const T* y, const T* gax, const T* gay, T* g) { nfw_bwd<T, NP>(d, x, y, gax, gay, g); }
+};
+template <int NP>
+struct NfwLane<GlF2, NP> {
+  static GL_HD void fwd(const float* d, const GlF2* x, const GlF2* y, GlF2* ax, GlF2* ay) {
+    float xs[2 * NP], ys[2 * NP], as[2 * NP], bs[2 * NP];
+#pragma unroll
+    for (int j = 0; j < NP; ++j) { xs[2 * j] = x[j].x; xs[2 * j + 1] = x[j].y; ys[2 * j] = y[j].x; ys[2 * j + 1] = y[j].y; }
+    nfw_fwd<float, 2 * NP>(d, xs, ys, as, bs);
+#pragma unroll
+    for (int j = 0; j < NP; ++j) { ax[j] = GlF2(as[2 * j], as[2 * j + 1]); ay[j] = GlF2(bs[2 * j], bs[2 * j + 1]); }
+  }
+  static GL_HD void bwd(const float* d, const GlF2* x, const GlF2* y, const GlF2* gax, const GlF2* gay, GlF2* g) {
+    float xs[2 * NP], ys[2 * NP], as[2 * NP], bs[2 * NP], g8[GL_MAX_DVARS];
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      xs[2 * j] = x[j].x; xs[2 * j + 1] = x[j].y; ys[2 * j] = y[j].x; ys[2 * j + 1] = y[j].y;
+      as[2 * j] = gax[j].x; as[2 * j + 1] = gax[j].y; bs[2 * j] = gay[j].x; bs[2 * j + 1] = gay[j].y;
+    }
+#pragma unroll
+    for (int k = 0; k < GL_MAX_DVARS; ++k) g8[k] = 0.f;
+    nfw_bwd<float, 2 * NP>(d, xs, ys, as, bs, g8);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) g[k] += GlF2(g8[k], 0.f);
+  }
+};
+
 // =============================================================================================
 // dPIS / dPIE  (tf/profiles/mass/piemd.py:33-60, 105-119, 183-255)
 //   raw  : theta_E, r_core, r_cut, [e1, e2,] cx, cy
@@ -943,61 +977,67 @@ template <class T>
 struct DpieFw {
   T sc, st, a, b_, c_, d_, e_, f_, aa, bb, cc, dd, inorm, aaa, bbb, inorm2, zr_re, zr_im;
 };
+// T is the lane type (float, double, GlDual, or the two-pixel pack GlF2), S the scalar type of the constants.
 template <class T>
 GL_HD void dpie_core_fwd(const typename gl_scalar_of<T>::type* d, T x, T y, DpieFw<T>& W, T& re, T& im) {
-  const T sqe = d[DP_SQE], rc = d[DP_RC], rt = d[DP_RT];
-  const T rem2 = gl_fma(x * x, d[DP_IOPE2], y * y * d[DP_IOME2]);
-  W.sc = gl_sqrt_pos(d[DP_RC2] + rem2);
-  W.st = gl_sqrt_pos(d[DP_RT2] + rem2);
-  const T yq = y * d[DP_IQ];
-  W.a = d[DP_Q] * x;                               // znum_rc_re
-  W.b_ = gl_fma(T(2) * sqe, W.sc, -yq);            // znum_rc_im
-  W.c_ = x;                                        // zden_rc_re
-  W.d_ = gl_fma(T(2) * rc, sqe, -y);               // zden_rc_im
-  W.e_ = gl_fma(T(2) * sqe, W.st, -yq);            // znum_rcut_im
-  W.f_ = gl_fma(T(2) * rt, sqe, -y);               // zden_rcut_im
+  typedef typename gl_scalar_of<T>::type S;
+  const S two_sqe = S(2) * d[DP_SQE];
+  const T rem2 = gl_fma(x * x, T(d[DP_IOPE2]), y * y * T(d[DP_IOME2]));
+  W.sc = gl_sqrt_pos(T(d[DP_RC2]) + rem2);
+  W.st = gl_sqrt_pos(T(d[DP_RT2]) + rem2);
+  const T yq = y * T(d[DP_IQ]);
+  W.a = T(d[DP_Q]) * x;                             // znum_rc_re
+  W.b_ = gl_fma(T(two_sqe), W.sc, -yq);             // znum_rc_im
+  W.c_ = x;                                         // zden_rc_re
+  W.d_ = T(two_sqe * d[DP_RC]) - y;                 // zden_rc_im
+  W.e_ = gl_fma(T(two_sqe), W.st, -yq);             // znum_rcut_im
+  W.f_ = T(two_sqe * d[DP_RT]) - y;                 // zden_rcut_im
   W.aa = gl_fma(W.a, W.c_, -(W.b_ * W.f_));
   W.bb = gl_fma(W.a, W.f_, W.b_ * W.c_);
   W.cc = gl_fma(W.a, W.c_, -(W.d_ * W.e_));
   W.dd = gl_fma(W.a, W.d_, W.c_ * W.e_);
-  W.inorm = gl_div_fast(T(1), gl_fma(W.cc, W.cc, W.dd * W.dd));
+  W.inorm = gl_div_fast(T(S(1)), gl_fma(W.cc, W.cc, W.dd * W.dd));
   W.aaa = gl_fma(W.aa, W.cc, W.bb * W.dd) * W.inorm;
   W.bbb = gl_fma(W.bb, W.cc, -(W.aa * W.dd)) * W.inorm;
   const T norm2 = gl_fma(W.aaa, W.aaa, W.bbb * W.bbb);
-  W.inorm2 = gl_div_fast(T(1), norm2);
-  W.zr_re = T(0.5 * GL_LN2) * gl_log2_fast(norm2);
+  W.inorm2 = gl_div_fast(T(S(1)), norm2);
+  W.zr_re = T(S(0.5 * GL_LN2)) * gl_log2_fast(norm2);
   W.zr_im = gl_atan2_fast(W.bbb, W.aaa);
-  re = -d[DP_ZCI] * W.zr_im;
-  im = d[DP_ZCI] * W.zr_re;
+  re = -(T(d[DP_ZCI]) * W.zr_im);
+  im = T(d[DP_ZCI]) * W.zr_re;
 }
 template <class T, int NP>
 GL_HD void dpie_fwd(const typename gl_scalar_of<T>::type* d, const T* x, const T* y, T* ax, T* ay) {
-  T c = d[DP_C], s = d[DP_S], scale = d[DP_SCALE];
+  const T c = T(d[DP_C]), s = T(d[DP_S]), scale = T(d[DP_SCALE]), cx = T(d[DP_CX]), cy = T(d[DP_CY]);
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
-    T dx = x[j] - d[DP_CX], dy = y[j] - d[DP_CY];
+    T dx = x[j] - cx, dy = y[j] - cy;
     T xr = gl_fma(dx, c, dy * s), yr = gl_fma(dy, c, -(dx * s));
     DpieFw<T> W; T re, im;
-    dpie_core_fwd(d, xr, yr, W, re, im);
+    dpie_core_fwd<T>(d, xr, yr, W, re, im);
     ax[j] = scale * gl_fma(re, c, -(im * s));
     ay[j] = scale * gl_fma(re, s, im * c);
   }
 }
 template <class T, int NP>
 GL_HD void dpie_bwd(const typename gl_scalar_of<T>::type* d, const T* x, const T* y, const T* gax, const T* gay, T* g) {
-  const T c = d[DP_C], s = d[DP_S], scale = d[DP_SCALE], rc = d[DP_RC], rt = d[DP_RT], e = d[DP_E];
-  const T sqe = d[DP_SQE], q = d[DP_Q], iq = d[DP_IQ], iope2 = d[DP_IOPE2], iome2 = d[DP_IOME2], zci = d[DP_ZCI];
+  typedef typename gl_scalar_of<T>::type S;
+  const S e_s = d[DP_E], sqe_s = d[DP_SQE];
+  const T c = T(d[DP_C]), s = T(d[DP_S]), scale = T(d[DP_SCALE]), rc = T(d[DP_RC]), rt = T(d[DP_RT]);
+  const T sqe = T(sqe_s), q = T(d[DP_Q]), iq = T(d[DP_IQ]), iope2 = T(d[DP_IOPE2]), iome2 = T(d[DP_IOME2]), zci = T(d[DP_ZCI]);
+  const T cx = T(d[DP_CX]), cy = T(d[DP_CY]), iq2 = T(d[DP_IQ] * d[DP_IQ]), two = T(S(2)), half = T(S(0.5));
   // d(constant)/de, applied per pixel to fold every e-dependence into the single dvar e
-  const T dsqe = T(0.5) / sqe;
-  const T dzci = T(0.5) * (T(1) - e * e) / (sqe * sqe) * dsqe + e / sqe;   // d zci / d e
-  const T dq = -T(2) / ((T(1) + e) * (T(1) + e));
-  const T diope2 = -T(2) * iope2 / (T(1) + e), diome2 = T(2) * iome2 / (T(1) - e);
+  const S dsqe_s = S(0.5) / sqe_s;
+  const T dsqe = T(dsqe_s);
+  const T dzci = T(S(0.5) * (S(1) - e_s * e_s) / (sqe_s * sqe_s) * dsqe_s + e_s / sqe_s);   // d zci / d e
+  const T dq = T(-S(2) / ((S(1) + e_s) * (S(1) + e_s)));
+  const T diope2 = T(-S(2) * d[DP_IOPE2] / (S(1) + e_s)), diome2 = T(S(2) * d[DP_IOME2] / (S(1) - e_s));
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
-    T dx = x[j] - d[DP_CX], dy = y[j] - d[DP_CY];
+    T dx = x[j] - cx, dy = y[j] - cy;
     T xr = gl_fma(dx, c, dy * s), yr = gl_fma(dy, c, -(dx * s));
     DpieFw<T> W; T re, im;
-    dpie_core_fwd(d, xr, yr, W, re, im);
+    dpie_core_fwd<T>(d, xr, yr, W, re, im);
     T ux = gl_fma(re, c, -(im * s)), uy = gl_fma(re, s, im * c);     // rotated back, unscaled
     g[DPG_SCALE] += gl_fma(gax[j], ux, gay[j] * uy);
     T gux = gax[j] * scale, guy = gay[j] * scale;
@@ -1005,16 +1045,16 @@ GL_HD void dpie_bwd(const typename gl_scalar_of<T>::type* d, const T* x, const T
     T gre = gl_fma(gux, c, guy * s), gim = gl_fma(guy, c, -(gux * s));
     // re = -zci zr_im ; im = zci zr_re
     T gzci = gl_fma(gim, W.zr_re, -(gre * W.zr_im));
-    T gzr_im = -gre * zci, gzr_re = gim * zci;
+    T gzr_im = -(gre * zci), gzr_re = gim * zci;
     // zr_re = 0.5 log(norm2), zr_im = atan2(bbb, aaa)
     T gaaa = gl_fma(gzr_re, W.aaa, -(gzr_im * W.bbb)) * W.inorm2;
     T gbbb = gl_fma(gzr_re, W.bbb, gzr_im * W.aaa) * W.inorm2;
     // aaa = (aa cc + bb dd)/norm, bbb = (bb cc - aa dd)/norm
     T gaa = gl_fma(gaaa, W.cc, -(gbbb * W.dd)) * W.inorm;
     T gbb = gl_fma(gaaa, W.dd, gbbb * W.cc) * W.inorm;
-    T gnorm = -gl_fma(gaaa, W.aaa, gbbb * W.bbb) * W.inorm;
-    T gcc = gl_fma(gl_fma(gaaa, W.aa, gbbb * W.bb), W.inorm, gnorm * T(2) * W.cc);
-    T gdd = gl_fma(gl_fma(gaaa, W.bb, -(gbbb * W.aa)), W.inorm, gnorm * T(2) * W.dd);
+    T gnorm = -(gl_fma(gaaa, W.aaa, gbbb * W.bbb) * W.inorm);
+    T gcc = gl_fma(gl_fma(gaaa, W.aa, gbbb * W.bb), W.inorm, gnorm * two * W.cc);
+    T gdd = gl_fma(gl_fma(gaaa, W.bb, -(gbbb * W.aa)), W.inorm, gnorm * two * W.dd);
     // aa = a c - b f ; bb = a f + b c ; cc = a c - d e ; dd = a d + c e
     T ga = gl_fma(gaa + gcc, W.c_, gl_fma(gbb, W.f_, gdd * W.d_));
     T gb = gl_fma(gbb, W.c_, -(gaa * W.f_));
@@ -1024,18 +1064,18 @@ GL_HD void dpie_bwd(const typename gl_scalar_of<T>::type* d, const T* x, const T
     T gf = gl_fma(gbb, W.a, -(gaa * W.b_));
     // a = q x ; b = 2 sqe sc - y/q ; c = x ; d = 2 rc sqe - y ; e = 2 sqe st - y/q ; f = 2 rt sqe - y
     T gbe = gb + ge_;
-    T gq = gl_fma(ga, xr, gbe * yr * (iq * iq));
+    T gq = gl_fma(ga, xr, gbe * yr * iq2);
     T gx = gl_fma(ga, q, gc);
     T gy = -gl_fma(gbe, iq, gd + gf);
-    T gsqe = T(2) * gl_fma(gb, W.sc, gl_fma(ge_, W.st, gl_fma(gd, rc, gf * rt)));
-    T gsc = gb * T(2) * sqe, gst = ge_ * T(2) * sqe;
-    T isc = gl_div_fast(T(1), W.sc), ist = gl_div_fast(T(1), W.st);
-    g[DPG_RC] += gl_fma(gd * T(2), sqe, gsc * rc * isc);
-    g[DPG_RT] += gl_fma(gf * T(2), sqe, gst * rt * ist);
-    T grem2 = T(0.5) * gl_fma(gsc, isc, gst * ist);
+    T gsqe = two * gl_fma(gb, W.sc, gl_fma(ge_, W.st, gl_fma(gd, rc, gf * rt)));
+    T gsc = gb * two * sqe, gst = ge_ * two * sqe;
+    T isc = gl_div_fast(T(S(1)), W.sc), ist = gl_div_fast(T(S(1)), W.st);
+    g[DPG_RC] += gl_fma(gd * two, sqe, gsc * rc * isc);
+    g[DPG_RT] += gl_fma(gf * two, sqe, gst * rt * ist);
+    T grem2 = half * gl_fma(gsc, isc, gst * ist);
     // rem2 = x^2 iope2 + y^2 iome2
-    gx = gl_fma(grem2 * T(2) * xr, iope2, gx);
-    gy = gl_fma(grem2 * T(2) * yr, iome2, gy);
+    gx = gl_fma(grem2 * two * xr, iope2, gx);
+    gy = gl_fma(grem2 * two * yr, iome2, gy);
     T ge = grem2 * gl_fma(xr * xr, diope2, yr * yr * diome2);
     ge = gl_fma(gzci, dzci, ge);
     ge = gl_fma(gsqe, dsqe, ge);
@@ -1056,14 +1096,16 @@ GL_HD void dpie_bwd(const typename gl_scalar_of<T>::type* d, const T* x, const T
 // d(alpha)/d(rc|rt) follows from z = num/den, zr = log z:  dz = (num' - z den')/den, dzr = dz / z.
 template <class T, int NP>
 GL_HD void dpie_fwd_jac(const typename gl_scalar_of<T>::type* d, const T* x, const T* y, T* ax, T* ay, T (*Jx)[NP], T (*Jy)[NP]) {
-  const T c = d[DP_C], s = d[DP_S], scale = d[DP_SCALE], zci = d[DP_ZCI], two_sqe = T(2) * d[DP_SQE];
-  const typename gl_scalar_of<T>::type* M = d + DP_M;
+  typedef typename gl_scalar_of<T>::type S;
+  const T c = T(d[DP_C]), s = T(d[DP_S]), scale = T(d[DP_SCALE]), zci = T(d[DP_ZCI]), two_sqe = T(S(2) * d[DP_SQE]);
+  const T cx = T(d[DP_CX]), cy = T(d[DP_CY]), bp0 = T(S(2) * d[DP_SQE] * d[DP_RC]), ep0 = T(S(2) * d[DP_SQE] * d[DP_RT]);
+  const S* M = d + DP_M;
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
-    T dx = x[j] - d[DP_CX], dy = y[j] - d[DP_CY];
+    T dx = x[j] - cx, dy = y[j] - cy;
     T xr = gl_fma(dx, c, dy * s), yr = gl_fma(dy, c, -(dx * s));
     DpieFw<T> W; T re, im;
-    dpie_core_fwd(d, xr, yr, W, re, im);
+    dpie_core_fwd<T>(d, xr, yr, W, re, im);
     ax[j] = scale * gl_fma(re, c, -(im * s));
     ay[j] = scale * gl_fma(re, s, im * c);
     // tangents of (re, im) w.r.t. rc and rt
@@ -1072,10 +1114,10 @@ GL_HD void dpie_fwd_jac(const typename gl_scalar_of<T>::type* d, const T* x, con
     for (int w = 0; w < 2; ++w) {
       T naa, nbb, ncc, ndd;   // num' = naa + i nbb, den' = ncc + i ndd
       if (w == 0) {           // d/d rc: b' = 2 sqe rc/sc, d' = 2 sqe
-        const T bp = two_sqe * d[DP_RC] * gl_div_fast(T(1), W.sc);
+        const T bp = bp0 * gl_div_fast(T(S(1)), W.sc);
         naa = -(bp * W.f_); nbb = bp * W.c_; ncc = -(two_sqe * W.e_); ndd = W.a * two_sqe;
       } else {                // d/d rt: e' = 2 sqe rt/st, f' = 2 sqe
-        const T ep = two_sqe * d[DP_RT] * gl_div_fast(T(1), W.st);
+        const T ep = ep0 * gl_div_fast(T(S(1)), W.st);
         naa = -(W.b_ * two_sqe); nbb = W.a * two_sqe; ncc = -(W.d_ * ep); ndd = W.c_ * ep;
       }
       // t = num' - z den'
@@ -1087,13 +1129,13 @@ GL_HD void dpie_fwd_jac(const typename gl_scalar_of<T>::type* d, const T* x, con
       // d(log z) = dz conj(z) / |z|^2
       const T lr = gl_fma(dzr_, W.aaa, dzi_ * W.bbb) * W.inorm2;
       const T li = gl_fma(dzi_, W.aaa, -(dzr_ * W.bbb)) * W.inorm2;
-      tre[w] = -zci * li; tim[w] = zci * lr;
+      tre[w] = -(zci * li); tim[w] = zci * lr;
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       // rotated-frame tangent of alpha_m/1 w.r.t. base parameter k, then rotate back
-      const T vr = gl_fma(M[k], re, scale * gl_fma(M[3 + k], tre[0], M[6 + k] * tre[1]));
-      const T vi = gl_fma(M[k], im, scale * gl_fma(M[3 + k], tim[0], M[6 + k] * tim[1]));
+      const T vr = gl_fma(T(M[k]), re, scale * gl_fma(T(M[3 + k]), tre[0], T(M[6 + k]) * tre[1]));
+      const T vi = gl_fma(T(M[k]), im, scale * gl_fma(T(M[3 + k]), tim[0], T(M[6 + k]) * tim[1]));
       Jx[k][j] += gl_fma(vr, c, -(vi * s));
       Jy[k][j] += gl_fma(vr, s, vi * c);
     }
@@ -1620,7 +1662,7 @@ GL_HD void gl_lens_fwd(int type, int ts, const typename gl_scalar_of<T>::type* d
     case GLT_SHEAR: if constexpr ((F & GLF_SHEAR) != 0) shear_fwd<T, NP>(d, x, y, ax, ay); break;
     case GLT_SIE: if constexpr ((F & GLF_SIE) != 0) sie_fwd<T, NP>(d, x, y, ax, ay); break;
     case GLT_SIS: if constexpr ((F & GLF_SIS) != 0) sis_fwd<T, NP>(d, x, y, ax, ay); break;
-    case GLT_NFW: case GLT_NFW_ELLIPSE: if constexpr ((F & GLF_NFW) != 0) nfw_fwd<T, NP>(d, x, y, ax, ay); break;
+    case GLT_NFW: case GLT_NFW_ELLIPSE: if constexpr ((F & GLF_NFW) != 0) NfwLane<T, NP>::fwd(d, x, y, ax, ay); break;
     case GLT_DPIS: if constexpr ((F & GLF_DPIS) != 0) dpis_fwd<T, NP>(d, x, y, ax, ay); break;
     case GLT_DPIE: if constexpr ((F & GLF_DPIE) != 0) dpie_fwd<T, NP>(d, x, y, ax, ay); break;
     case GLT_TNFW: if constexpr ((F & GLF_TNFW) != 0) tnfw_fwd<T, NP>(d, x, y, ax, ay); break;
@@ -1635,7 +1677,7 @@ GL_HD void gl_lens_bwd(int type, int ts, const typename gl_scalar_of<T>::type* d
     case GLT_SHEAR: if constexpr ((F & GLF_SHEAR) != 0) shear_bwd<T, NP>(d, x, y, gax, gay, g); break;
     case GLT_SIE: if constexpr ((F & GLF_SIE) != 0) sie_bwd<T, NP>(d, x, y, gax, gay, g); break;
     case GLT_SIS: if constexpr ((F & GLF_SIS) != 0) sis_bwd<T, NP>(d, x, y, gax, gay, g); break;
-    case GLT_NFW: case GLT_NFW_ELLIPSE: if constexpr ((F & GLF_NFW) != 0) nfw_bwd<T, NP>(d, x, y, gax, gay, g); break;
+    case GLT_NFW: case GLT_NFW_ELLIPSE: if constexpr ((F & GLF_NFW) != 0) NfwLane<T, NP>::bwd(d, x, y, gax, gay, g); break;
     case GLT_DPIS: if constexpr ((F & GLF_DPIS) != 0) dpis_bwd<T, NP>(d, x, y, gax, gay, g); break;
     case GLT_DPIE: if constexpr ((F & GLF_DPIE) != 0) dpie_bwd<T, NP>(d, x, y, gax, gay, g); break;
     case GLT_TNFW: if constexpr ((F & GLF_TNFW) != 0) tnfw_bwd<T, NP>(d, x, y, gax, gay, g); break;

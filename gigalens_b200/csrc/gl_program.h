@@ -184,7 +184,7 @@ GL_HD void gl_pix_beta_jac(const GlProgram& P, const typename gl_scalar_of<T>::t
     for (int m = 0; m < nm; ++m) {
       T ax[NP], ay[NP];
       bool done = false;
-      if constexpr ((F & GLF_DPIE) != 0 && sizeof(T) == sizeof(typename gl_scalar_of<T>::type)) {
+      if constexpr ((F & GLF_DPIE) != 0) {
         if (pr.fwdmode) { dpie_fwd_jac<T, NP>(der + pr.der_off + m * pr.der_size, x, y, ax, ay, Jx, Jy); done = true; }
       }
       if (!done) gl_lens_fwd<T, NP, F>(pr.type, pr.ts, der + pr.der_off + m * pr.der_size, x, y, ax, ay);

@@ -79,24 +79,25 @@ static int run(const gl_model_desc* m, int bs, const T* params, int npix, const 
 }
 
 // The two-pixel packed lane type (GlF2) through the same drivers: host build of the code path the
-// k_raytrace_*_p kernels instantiate (feature set EPL | SHEAR | SERSIC only).
+// k_raytrace_*_p kernels instantiate (EPL | SHEAR | SERSIC, and the cluster set NFW | DPIE | SHEAR | SERSIC).
 struct HostFlush2 {
   float* g;
   void operator()(const GlF2* acc, int n, int off) { for (int k = 0; k < n; ++k) g[off + k] += acc[k].x + acc[k].y; }
 };
 static int run_packed(const gl_model_desc* m, int bs, const float* params, int npix, const float* gx, const float* gy,
                       float* ss_out, const float* g_ss, float* gparams) {
-  constexpr unsigned F = GLF_EPL | GLF_SHEAR | GLF_SERSIC;
+  constexpr unsigned F = GLF_EPL | GLF_SHEAR | GLF_SERSIC | GLF_NFW | GLF_DPIE;   // union of the packed kernels' feature sets
   GlBuilt B;
   std::string e = gl_build_program(m, B);
   if (!e.empty()) { g_err = e; return 1; }
   GlProgram& P = B.prog;
   for (int i = 0; i < P.n_prof; ++i)
-    if ((gl_feature_of(P.prof[i].type) & F) == 0 || P.prof[i].n_members > 0) { g_err = "packed lanes: unsupported profile"; return 1; }
+    if ((gl_feature_of(P.prof[i].type) & F) == 0) { g_err = "packed lanes: unsupported profile"; return 1; }
   if (npix % 2) { g_err = "packed lanes need an even pixel count"; return 1; }
+  const float* mf = B.member_factor.empty() ? nullptr : B.member_factor.data();
   std::vector<float> der(P.der_total), g(P.g_total > 0 ? P.g_total : 1);
   for (int b = 0; b < bs; ++b) {
-    gl_sample_prep<float, float>(P, params, bs, b, nullptr, nullptr, nullptr, der.data());
+    gl_sample_prep<float, float>(P, params, bs, b, mf, nullptr, nullptr, der.data());
     std::fill(g.begin(), g.end(), 0.f);
     HostFlush2 fl{g.data()};
     for (int p = 0; p < npix; p += 2) {
@@ -111,7 +112,7 @@ static int run_packed(const gl_model_desc* m, int bs, const float* params, int n
         gl_pix_image_bwd<GlF2, 1, F>(P, der.data(), x, y, gs, false, fl);
       }
     }
-    if (g_ss && gparams) gl_sample_prep_bwd<float, float>(P, params, bs, b, nullptr, nullptr, der.data(), g.data(), gparams);
+    if (g_ss && gparams) gl_sample_prep_bwd<float, float>(P, params, bs, b, mf, nullptr, der.data(), g.data(), gparams);
   }
   return 0;
 }

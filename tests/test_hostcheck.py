@@ -119,7 +119,7 @@ def test_lstsq_component_stack(interpolate):
     assert np.max(np.abs(out["comps"] - ref)) / np.max(np.abs(ref)) < (1e-12 if interpolate else 1e-7)
 
 
-@pytest.mark.parametrize("name", ["c2", "constants"])
+@pytest.mark.parametrize("name", ["c2", "constants", "cluster", "nfw", "dpie"])
 def test_packed_lane_instantiation_matches_scalar(name):
     """The two-pixel packed lane type (what k_raytrace_*_p instantiate) runs the same source as the
     scalar lanes; on the host both are plain fp32, so results must agree to rounding."""
