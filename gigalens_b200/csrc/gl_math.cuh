@@ -148,7 +148,29 @@ GL_HD GlF2 gl_log2_fast(GlF2 a) { return GlF2(gl_log2_fast(a.x), gl_log2_fast(a.
 GL_HD GlF2 gl_exp2_fast(GlF2 a) { return GlF2(gl_exp2_fast(a.x), gl_exp2_fast(a.y)); }
 GL_HD GlF2 gl_rsqrt_fast(GlF2 a) { return GlF2(gl_rsqrt_fast(a.x), gl_rsqrt_fast(a.y)); }
 GL_HD GlF2 gl_div_fast(GlF2 a, GlF2 b) { return GlF2(gl_div_fast(a.x, b.x), gl_div_fast(a.y, b.y)); }
+#if defined(__CUDA_ARCH__)
+GL_HD GlF2 gl_atan2_fast(GlF2 y, GlF2 x) {   // the polynomial of the scalar version on packed lanes; octant fix-up per lane
+  const float ax0 = fabsf(x.x), ay0 = fabsf(y.x), ax1 = fabsf(x.y), ay1 = fabsf(y.y);
+  const float mx0 = fmaxf(ax0, ay0), mx1 = fmaxf(ax1, ay1);
+  const GlF2 t = GlF2(fminf(ax0, ay0), fminf(ax1, ay1)) * GlF2(mx0 > 0.f ? __fdividef(1.f, mx0) : 0.f, mx1 > 0.f ? __fdividef(1.f, mx1) : 0.f);
+  const GlF2 s = t * t;
+  GlF2 p = GlF2(0.0029327620286494493f);
+  p = gl_fma(p, s, GlF2(-0.016413191333413124f));
+  p = gl_fma(p, s, GlF2(0.04327824339270592f));
+  p = gl_fma(p, s, GlF2(-0.07556900382041931f));
+  p = gl_fma(p, s, GlF2(0.10667487233877182f));
+  p = gl_fma(p, s, GlF2(-0.14211106300354004f));
+  p = gl_fma(p, s, GlF2(0.19993694126605988f));
+  p = gl_fma(p, s, GlF2(-0.3333313763141632f));
+  p = gl_fma(p, s, GlF2(1.0f));
+  const GlF2 r = p * t;
+  float r0 = (ay0 > ax0) ? 1.5707963267948966f - r.x : r.x, r1 = (ay1 > ax1) ? 1.5707963267948966f - r.y : r.y;
+  r0 = (x.x < 0.f) ? 3.141592653589793f - r0 : r0; r1 = (x.y < 0.f) ? 3.141592653589793f - r1 : r1;
+  return GlF2(copysignf(r0, y.x), copysignf(r1, y.y));
+}
+#else
 GL_HD GlF2 gl_atan2_fast(GlF2 y, GlF2 x) { return GlF2(gl_atan2_fast(y.x, x.x), gl_atan2_fast(y.y, x.y)); }
+#endif
 GL_HD GlF2 gl_min(GlF2 a, GlF2 b) { return GlF2(fminf(a.x, b.x), fminf(a.y, b.y)); }
 GL_HD GlF2 gl_max(GlF2 a, GlF2 b) { return GlF2(fmaxf(a.x, b.x), fmaxf(a.y, b.y)); }
 // per-lane selects: (a > t ? vt : vf), (lo <= a <= hi ? vt : vf)
