@@ -1,0 +1,176 @@
+// gl_gram_tc.cuh -- the batched normal-equation matrix of lstsq_simulate on the 5th-generation tensor
+// cores (tcgen05 + TMEM), the one place north_star puts tensor cores.
+//
+//   gram[b] = A A^T,  A = [X Y]^T  ((D+1) x P, row c = channel c of R[b] times W, last row = obs * W)
+//   (tf/simulator.py:232-235: X^T X and X^T Y in one product.)
+//
+// One CTA (4 warps) per sample.  A is K-major in HBM already (every channel image is contiguous in the
+// pixel index), so the same shared-memory tile serves as both MMA operands: D[128 x N] += A_tile[128 x 8] *
+// A_tile[N x 8]^T with M = 128 (rows >= D+1 are zero), N = D+1 rounded up to 16, kind::tf32, fp32
+// accumulators in TMEM.  TF32 keeps 11 significand bits, far short of the 1e-5 parity bound after the
+// pseudo-inverse, so each fp32 value is split v = hi + lo (both TF32-representable) and every K-slice
+// issues three MMAs: hi*hi + hi*lo + lo*hi ("3xTF32"; the dropped lo*lo term is 2^-22 relative).
+//
+// Shared-memory operand layout: the canonical K-major, no-swizzle UMMA layout -- 8-row x 16-byte core
+// matrices; here a K-chunk (4 pixels = 16 bytes) of all 128 rows forms one 2 KB panel, so
+// LBO (next 16 bytes in K) = 2048 B and SBO (next 8 rows) = 128 B.  Loads are float4 per (row, chunk) with
+// each quarter-warp writing 8 consecutive rows of one panel (conflict-free 16-byte stores) and each warp
+// reading 64 contiguous bytes of 8 channel rows (full sectors).  Two stages: the CUDA cores convert /
+// split stage s+1 while the tensor core consumes stage s; tcgen05.commit -> mbarrier frees a stage.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define GTC_THREADS 128
+#define GTC_KC 32                                  // pixels per stage
+#define GTC_PANEL 2048                             // bytes: 128 rows x 16 B
+#define GTC_TILE (GTC_PANEL * (GTC_KC / 4))        // one hi or lo tile: 16 KB
+#define GTC_STAGE (2 * GTC_TILE)                   // hi + lo
+#define GTC_SMEM (2 * GTC_STAGE + 64)              // two stages + barriers / tmem pointer
+
+__device__ __forceinline__ uint32_t gtc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float gtc_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout)
+__device__ __forceinline__ uint64_t gtc_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);                 // start address            [0,14)
+  d |= (uint64_t)(GTC_PANEL >> 4) << 16;                    // leading byte offset (K)  [16,30)
+  d |= (uint64_t)(128 >> 4) << 32;                          // stride byte offset (M/N) [32,46)
+  d |= (uint64_t)1 << 46;                                   // descriptor version (Blackwell)
+  return d;                                                 // base offset 0, layout type 0 = no swizzle
+}
+__device__ __forceinline__ void gtc_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+      :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void gtc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(gtc_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool gtc_wait(uint64_t* bar, uint32_t parity) {   // bounded spin: a broken pipeline must not hang the GPU
+  const uint32_t a = gtc_smem_u32(bar);
+  for (int it = 0; it < (1 << 22); ++it) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    if (ok) return true;
+  }
+  return false;
+}
+
+// grid = number of samples in the chunk, block = 128.  err_flag: set to 1 if a barrier wait timed out.
+__global__ void __launch_bounds__(GTC_THREADS) k_gram_tc(int D, int npx, const float* __restrict__ R, const float* __restrict__ w,
+                                                        const float* __restrict__ obs, float* __restrict__ gram,
+                                                        int* __restrict__ err_flag) {
+  extern __shared__ __align__(1024) unsigned char gtc_smem[];
+  unsigned char* smem = gtc_smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * GTC_STAGE);     // [0,1]: stage free, [2]: accumulator complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 2 * GTC_STAGE + 32);
+  const int tid = threadIdx.x, warp = tid >> 5, b = blockIdx.x;
+  const int Dx = D + 1;
+  const int N = (Dx + 15) & ~15;
+  const float* Rb = R + (size_t)b * D * npx;
+  // zero both stages once: rows > D stay zero for the whole kernel
+  for (int i = tid; i < 2 * GTC_STAGE / 16; i += GTC_THREADS) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (tid == 0) {
+    for (int i = 0; i < 3; ++i)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(gtc_smem_u32(bars + i)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" :: "r"(gtc_smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+  // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N, M = 128
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const int nstage = (npx + GTC_KC - 1) / GTC_KC;
+  const int nitem = Dx * (GTC_KC / 4);             // (row, 16-byte chunk) items per stage
+  bool ok = true;
+  uint32_t phase[2] = {0u, 0u};
+  for (int st = 0; st < nstage; ++st) {
+    const int s = st & 1;
+    unsigned char* hi = smem + s * GTC_STAGE;
+    unsigned char* lo = hi + GTC_TILE;
+    if (st >= 2) {                                  // the MMAs that read this stage two iterations ago must have retired
+      ok = gtc_wait(bars + s, phase[s]) && ok;
+      phase[s] ^= 1u;
+    }
+    const int p0 = st * GTC_KC;
+    for (int it = tid; it < nitem; it += GTC_THREADS) {
+      // item -> (row group, chunk, row in group): a quarter-warp covers 8 consecutive rows of one panel
+      const int r0 = it & 7, kc = (it >> 3) & 7, row = (it >> 6) * 8 + r0;
+      if (row >= Dx) continue;
+      const int p = p0 + kc * 4;
+      float v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float x = 0.f;
+        if (p + q < npx) {
+          const float wv = __ldg(w + p + q);
+          if (row < D) { x = __ldg(Rb + (size_t)row * npx + p + q); if (x != x) x = 0.f; x *= wv; }   // NaN scrub (:228)
+          else x = __ldg(obs + p + q) * wv;
+        }
+        v[q] = x;
+      }
+      float4 h, l;
+      h.x = gtc_tf32(v[0]); h.y = gtc_tf32(v[1]); h.z = gtc_tf32(v[2]); h.w = gtc_tf32(v[3]);
+      l.x = gtc_tf32(v[0] - h.x); l.y = gtc_tf32(v[1] - h.y); l.z = gtc_tf32(v[2] - h.z); l.w = gtc_tf32(v[3] - h.w);
+      const int off = kc * GTC_PANEL + row * 16;
+      *reinterpret_cast<float4*>(hi + off) = h;
+      *reinterpret_cast<float4*>(lo + off) = l;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core (async proxy)
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t ah = gtc_smem_u32(hi), al = gtc_smem_u32(lo);
+#pragma unroll
+      for (int j = 0; j < GTC_KC / 8; ++j) {        // K = 8 per MMA = two 16-byte chunks = two panels
+        const uint64_t dh = gtc_desc(ah + j * 2 * GTC_PANEL), dl = gtc_desc(al + j * 2 * GTC_PANEL);
+        gtc_mma(tmem, dh, dh, idesc, (st | j) != 0);
+        gtc_mma(tmem, dh, dl, idesc, 1u);
+        gtc_mma(tmem, dl, dh, idesc, 1u);
+      }
+      gtc_commit(bars + s);
+      if (st == nstage - 1) gtc_commit(bars + 2);
+    }
+  }
+  // ---- epilogue: accumulator complete -> registers -> gram[b]
+  ok = gtc_wait(bars + 2, 0u) && ok;
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (ok) {
+    const int row = warp * 32 + (tid & 31);          // TMEM lane == accumulator row; warp w owns lanes 32w .. 32w+31
+    float* out = gram + (size_t)b * Dx * Dx;
+    for (int c0 = 0; c0 < N; c0 += 16) {
+      uint32_t r[16];
+      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+          : "r"(taddr) : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (row < Dx) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+          if (c0 + q < Dx) out[(size_t)row * Dx + c0 + q] = __uint_as_float(r[q]);
+      }
+    }
+  } else {   // a barrier wait timed out: fail loudly (NaN Gram -> NaN amplitudes and likelihood), never silently
+    float* out = gram + (size_t)b * Dx * Dx;
+    for (int i = tid; i < Dx * Dx; i += GTC_THREADS) out[i] = __int_as_float(0x7fc00000);
+    if (tid == 0 && err_flag) *err_flag = 1;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" :: "r"(tmem) : "memory");
+}

@@ -23,6 +23,7 @@
 #include "gl_conv.cuh"
 #include "gl_lstsq.cuh"
 #include "gl_positions.cuh"
+#include "gl_gram_tc.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // error handling / bookkeeping
@@ -491,6 +492,7 @@ struct gl_plan {
   int* d_perm = nullptr;
   int* d_nan = nullptr;      // [bs] NaN-scrubbed ss pixels of the last forward pass
   // image-position likelihood (gl_plan_set_positions)
+  int gram_tc = 0;           // lstsq normal equations on the tensor cores (tcgen05, 3xTF32) instead of FP32 FMA
   int include_pixels = 1, include_positions = 0;
   int pos_npts = 0, pos_nsys = 0;
   float pos_n_position = 0.f;
@@ -816,6 +818,7 @@ int gl_plan_set_option(gl_plan* p, const char* name, int32_t value) {
     if (value && p->pos_npts == 0) return gl_fail("gl_plan_set_option: include_positions needs gl_plan_set_positions first");
     p->include_positions = value != 0; return 0;
   }
+  if (!strcmp(name, "gram_tc")) { p->gram_tc = value != 0; return 0; }
   if (!strcmp(name, "packed_math")) { p->use_packed = value; return 0; }   // 0: scalar-lane kernels (A/B testing)
   if (!strcmp(name, "lstsq_chunk")) {   // samples per pass of the lstsq component stack (0 = size by memory budget)
     if (p->d_comps) return gl_fail("gl_plan_set_option: lstsq_chunk must be set before the first lstsq call");
@@ -1290,8 +1293,14 @@ static int gl_lstsq_forward(gl_plan* p, const float* params, float* image, float
       GL_CUDA(cudaMemcpyAsync(stack_out + (size_t)b0 * D * npx, p->d_R, (size_t)nb * D * npx * sizeof(float), cudaMemcpyDeviceToDevice, st));
       continue;
     }
-    k_gram<<<nb, GLL_THREADS, smem_gram, st>>>(D, npx, p->d_R, p->d_w, p->d_obs, p->d_gram);
-    GL_LAUNCH_CHECK("k_gram");
+    if (p->gram_tc) {
+      GL_CUDA(cudaFuncSetAttribute(k_gram_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, GTC_SMEM));
+      k_gram_tc<<<nb, GTC_THREADS, GTC_SMEM, st>>>(D, npx, p->d_R, p->d_w, p->d_obs, p->d_gram, nullptr);
+      GL_LAUNCH_CHECK("k_gram_tc");
+    } else {
+      k_gram<<<nb, GLL_THREADS, smem_gram, st>>>(D, npx, p->d_R, p->d_w, p->d_obs, p->d_gram);
+      GL_LAUNCH_CHECK("k_gram");
+    }
     k_pinv_solve<<<nb, 128, smem_solve, st>>>(D, p->d_gram, 1e-6, 16, p->d_coef + (size_t)b0 * D);
     GL_LAUNCH_CHECK("k_pinv_solve");
     k_lstsq_image<<<nb, GLL_THREADS, (size_t)D * sizeof(float), st>>>(

@@ -518,3 +518,34 @@ def test_positions_cluster_model_gradient():
     for k in lens_rows:
         assert_parity(g[k], g32[k], g64[k], 1e-4, f"grad {cm.slot_keys[k]}", g64p[k])
     assert np.all(g[[k for k in range(cm.n_params) if k not in lens_rows]] == 0)
+
+
+@pytest.mark.parametrize("n_max", [10, 3])
+def test_lstsq_tensor_core_gram(n_max):
+    """The tcgen05 / TMEM Gram kernel (3xTF32 split, gl_gram_tc.cuh) against the FP32-FMA Gram and the oracle:
+    image, amplitudes, log-prob and gradient must hold the same parity bounds."""
+    bs = 6
+    wl = workloads.c3_workload(n_max=n_max, observed=workloads.c3_observation(n_max=n_max))
+    pmod = BackwardProbModel(wl["prior"], wl["observed"], wl["background_rms"], wl["exp_time"])
+    z = pmod.bij_inverse(wl["prior"].sample(bs, seed=2))
+    zdev = torch.as_tensor(z, device="cuda")
+    res = {}
+    for tc in (0, 1):
+        sim = LensSimulator(wl["phys_model"], wl["sim_config"], bs=bs)
+        sim.set_option("gram_tc", tc)
+        params = pmod.bij_forward(sim, zdev)
+        res[tc] = dict(coef=sim.lstsq_simulate(params, wl["observed"], pmod.err_map, return_coeffs=True).cpu().numpy(),
+                       img=sim.lstsq_simulate(params, wl["observed"], pmod.err_map).cpu().numpy(),
+                       lp=[t.cpu().numpy() for t in pmod.log_prob_and_grad(sim, zdev)])
+    assert np.isfinite(res[1]["img"]).all() and np.isfinite(res[1]["lp"][0]).all()   # a stalled pipeline would give NaN
+    lp64, chi64, dz64 = oracle_bridge.backward_logprob_and_grad(wl, z.astype(np.float64), torch.float64)
+    osim, opm = oracle_bridge.build_oracle_backward(wl, bs, torch.float64)
+    p64, _ = opm.prior.forward(torch.as_tensor(z.astype(np.float64)))
+    im64 = osim.lstsq_simulate(p64, opm.observed_image, opm.err_map).numpy()
+    err = {tc: dict(img=rel_max(res[tc]["img"], im64), lp=np.max(np.abs(res[tc]["lp"][0] - lp64) / np.abs(lp64)),
+                    dz=np.max(np.abs(res[tc]["lp"][2] - dz64) / np.abs(dz64).max(0))) for tc in (0, 1)}
+    print("gram parity fp32-FMA vs tcgen05:", err)
+    # the tensor-core path may not be worse than the bound, nor much worse than the FP32-FMA path
+    assert err[1]["img"] <= max(1e-5, 3 * err[0]["img"]), err
+    assert err[1]["lp"] <= max(1e-5, 3 * err[0]["lp"]), err
+    assert err[1]["dz"] <= max(1e-4, 3 * err[0]["dz"]), err
