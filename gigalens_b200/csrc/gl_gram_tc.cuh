@@ -26,7 +26,7 @@
 #define GTC_PANEL 2048                             // bytes: 128 rows x 16 B
 #define GTC_TILE (GTC_PANEL * (GTC_KC / 4))        // one hi or lo tile: 16 KB
 #define GTC_STAGE (2 * GTC_TILE)                   // hi + lo
-#define GTC_SMEM (2 * GTC_STAGE + 64)              // two stages + barriers / tmem pointer
+#define GTC_SMEM (2 * GTC_STAGE + 64)              // two stages + 4 barriers + tmem pointer
 
 __device__ __forceinline__ uint32_t gtc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ float gtc_tf32(float v) {
@@ -63,27 +63,53 @@ __device__ __forceinline__ bool gtc_wait(uint64_t* bar, uint32_t parity) {   // 
   return false;
 }
 
-// grid = number of samples in the chunk, block = 128.  err_flag: set to 1 if a barrier wait timed out.
+// The tensor core's fp32 accumulation is not round-to-nearest: over a 3600-pixel chain the Gram drifts by
+// ~4e-5 relative (measured, linear in the chain length), which the pseudo-inverse amplifies past the 1e-5
+// parity bound.  So the chain is cut into segments of GTC_SEG stages (64 pixels): two TMEM accumulators
+// ping-pong, and while the tensor core works on segment g the threads drain segment g-1 (tcgen05.ld) and add
+// it to per-thread fp32 registers with round-to-nearest adds (thread r owns Gram row r).
+#define GTC_SEG 2
+#define GTC_ACC_COLS 128                           // TMEM column stride between the two accumulators
+
+template <int NB>
+__device__ __forceinline__ void gtc_drain(uint32_t taddr, float (&acc)[NB * 16]) {
+#pragma unroll
+  for (int cb = 0; cb < NB; ++cb) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr + (uint32_t)(cb * 16)) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int q = 0; q < 16; ++q) acc[cb * 16 + q] += __uint_as_float(r[q]);
+  }
+}
+
+// grid = number of samples in the chunk, block = 128; NB = N / 16 column blocks (N = D+1 rounded up to 16).
+// err_flag (may be null): set to 1 if a barrier wait timed out.
+template <int NB>
 __global__ void __launch_bounds__(GTC_THREADS) k_gram_tc(int D, int npx, const float* __restrict__ R, const float* __restrict__ w,
                                                         const float* __restrict__ obs, float* __restrict__ gram,
                                                         int* __restrict__ err_flag) {
   extern __shared__ __align__(1024) unsigned char gtc_smem[];
   unsigned char* smem = gtc_smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * GTC_STAGE);     // [0,1]: stage free, [2]: accumulator complete
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * GTC_STAGE);     // [0,1]: stage free, [2,3]: accumulator a complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 2 * GTC_STAGE + 32);
   const int tid = threadIdx.x, warp = tid >> 5, b = blockIdx.x;
   const int Dx = D + 1;
-  const int N = (Dx + 15) & ~15;
+  constexpr int N = NB * 16;
   const float* Rb = R + (size_t)b * D * npx;
   // zero both stages once: rows > D stay zero for the whole kernel
   for (int i = tid; i < 2 * GTC_STAGE / 16; i += GTC_THREADS) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (tid == 0) {
-    for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < 4; ++i)
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(gtc_smem_u32(bars + i)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" :: "r"(gtc_smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" :: "r"(gtc_smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -93,11 +119,16 @@ __global__ void __launch_bounds__(GTC_THREADS) k_gram_tc(int D, int npx, const f
   // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N, M = 128
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   const int nstage = (npx + GTC_KC - 1) / GTC_KC;
-  const int nitem = Dx * (GTC_KC / 4);             // (row, 16-byte chunk) items per stage
+  const int nseg = (nstage + GTC_SEG - 1) / GTC_SEG;
+  const int nitem = ((Dx + 7) / 8) * 8 * (GTC_KC / 4);   // (row, 16-byte chunk) items per stage, whole 8-row groups
+  const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);   // TMEM lane == accumulator row; warp w owns lanes 32w..32w+31
+  float acc[NB * 16];
+#pragma unroll
+  for (int i = 0; i < NB * 16; ++i) acc[i] = 0.f;
   bool ok = true;
-  uint32_t phase[2] = {0u, 0u};
+  uint32_t phase[2] = {0u, 0u}, aphase[2] = {0u, 0u};
   for (int st = 0; st < nstage; ++st) {
-    const int s = st & 1;
+    const int s = st & 1, seg = st / GTC_SEG, a = seg & 1;
     unsigned char* hi = smem + s * GTC_STAGE;
     unsigned char* lo = hi + GTC_TILE;
     if (st >= 2) {                                  // the MMAs that read this stage two iterations ago must have retired
@@ -129,48 +160,68 @@ __global__ void __launch_bounds__(GTC_THREADS) k_gram_tc(int D, int npx, const f
       *reinterpret_cast<float4*>(lo + off) = l;
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core (async proxy)
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t ah = gtc_smem_u32(hi), al = gtc_smem_u32(lo);
+      const uint32_t dacc = tmem + (uint32_t)(a * GTC_ACC_COLS);
+      const bool first = (st % GTC_SEG) == 0;       // a new segment overwrites its accumulator
 #pragma unroll
       for (int j = 0; j < GTC_KC / 8; ++j) {        // K = 8 per MMA = two 16-byte chunks = two panels
         const uint64_t dh = gtc_desc(ah + j * 2 * GTC_PANEL), dl = gtc_desc(al + j * 2 * GTC_PANEL);
-        gtc_mma(tmem, dh, dh, idesc, (st | j) != 0);
-        gtc_mma(tmem, dh, dl, idesc, 1u);
-        gtc_mma(tmem, dl, dh, idesc, 1u);
+        gtc_mma(dacc, dh, dh, idesc, (first && j == 0) ? 0u : 1u);
+        gtc_mma(dacc, dh, dl, idesc, 1u);
+        gtc_mma(dacc, dl, dh, idesc, 1u);
       }
       gtc_commit(bars + s);
-      if (st == nstage - 1) gtc_commit(bars + 2);
+      if ((st % GTC_SEG) == GTC_SEG - 1 || st == nstage - 1) gtc_commit(bars + 2 + a);
+    }
+    // drain the previous segment while the tensor core works on this one
+    if ((st % GTC_SEG) == 0 && seg >= 1) {
+      const int pa = a ^ 1;
+      ok = gtc_wait(bars + 2 + pa, aphase[pa]) && ok;
+      aphase[pa] ^= 1u;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      gtc_drain<NB>(lane_base + (uint32_t)(pa * GTC_ACC_COLS), acc);
     }
   }
-  // ---- epilogue: accumulator complete -> registers -> gram[b]
-  ok = gtc_wait(bars + 2, 0u) && ok;
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  {   // last segment
+    const int pa = (nseg - 1) & 1;
+    ok = gtc_wait(bars + 2 + pa, aphase[pa]) && ok;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    gtc_drain<NB>(lane_base + (uint32_t)(pa * GTC_ACC_COLS), acc);
+  }
+  float* out = gram + (size_t)b * Dx * Dx;
   if (ok) {
-    const int row = warp * 32 + (tid & 31);          // TMEM lane == accumulator row; warp w owns lanes 32w .. 32w+31
-    float* out = gram + (size_t)b * Dx * Dx;
-    for (int c0 = 0; c0 < N; c0 += 16) {
-      uint32_t r[16];
-      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-          : "r"(taddr) : "memory");
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (row < Dx) {
+    if (tid < Dx) {
 #pragma unroll
-        for (int q = 0; q < 16; ++q)
-          if (c0 + q < Dx) out[(size_t)row * Dx + c0 + q] = __uint_as_float(r[q]);
-      }
+      for (int q = 0; q < NB * 16; ++q)
+        if (q < Dx) out[(size_t)tid * Dx + q] = acc[q];
     }
   } else {   // a barrier wait timed out: fail loudly (NaN Gram -> NaN amplitudes and likelihood), never silently
-    float* out = gram + (size_t)b * Dx * Dx;
     for (int i = tid; i < Dx * Dx; i += GTC_THREADS) out[i] = __int_as_float(0x7fc00000);
     if (tid == 0 && err_flag) *err_flag = 1;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" :: "r"(tmem) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" :: "r"(tmem) : "memory");
+}
+
+// host-side launch: pick the column-block count for D
+static inline cudaError_t gl_launch_gram_tc(int nb, int D, int npx, const float* R, const float* w, const float* obs, float* gram,
+                                            int* err_flag, cudaStream_t st) {
+  const int NBv = (D + 1 + 15) / 16;
+#define GTC_CASE(n)                                                                                                 \
+  case n: {                                                                                                         \
+    cudaError_t e = cudaFuncSetAttribute(k_gram_tc<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, GTC_SMEM);      \
+    if (e != cudaSuccess) return e;                                                                                 \
+    k_gram_tc<n><<<nb, GTC_THREADS, GTC_SMEM, st>>>(D, npx, R, w, obs, gram, err_flag);                             \
+    return cudaGetLastError();                                                                                      \
+  }
+  switch (NBv) {
+    GTC_CASE(1) GTC_CASE(2) GTC_CASE(3) GTC_CASE(4) GTC_CASE(5) GTC_CASE(6) GTC_CASE(7)
+    default: return cudaErrorInvalidValue;
+  }
+#undef GTC_CASE
 }

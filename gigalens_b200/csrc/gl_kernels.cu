@@ -492,7 +492,7 @@ struct gl_plan {
   int* d_perm = nullptr;
   int* d_nan = nullptr;      // [bs] NaN-scrubbed ss pixels of the last forward pass
   // image-position likelihood (gl_plan_set_positions)
-  int gram_tc = 0;           // lstsq normal equations on the tensor cores (tcgen05, 3xTF32) instead of FP32 FMA
+  int gram_tc = 1;           // lstsq normal equations on the tensor cores (tcgen05, 3xTF32); 0 = FP32-FMA k_gram (A/B testing)
   int include_pixels = 1, include_positions = 0;
   int pos_npts = 0, pos_nsys = 0;
   float pos_n_position = 0.f;
@@ -1294,9 +1294,8 @@ static int gl_lstsq_forward(gl_plan* p, const float* params, float* image, float
       continue;
     }
     if (p->gram_tc) {
-      GL_CUDA(cudaFuncSetAttribute(k_gram_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, GTC_SMEM));
-      k_gram_tc<<<nb, GTC_THREADS, GTC_SMEM, st>>>(D, npx, p->d_R, p->d_w, p->d_obs, p->d_gram, nullptr);
-      GL_LAUNCH_CHECK("k_gram_tc");
+      GL_CUDA(gl_launch_gram_tc(nb, D, npx, p->d_R, p->d_w, p->d_obs, p->d_gram, nullptr, st));
+      ++g_launch_count;
     } else {
       k_gram<<<nb, GLL_THREADS, smem_gram, st>>>(D, npx, p->d_R, p->d_w, p->d_obs, p->d_gram);
       GL_LAUNCH_CHECK("k_gram");
