@@ -127,6 +127,36 @@ __global__ void __launch_bounds__(GTC_THREADS) k_gram_tc(int D, int npx, const f
   for (int i = 0; i < NB * 16; ++i) acc[i] = 0.f;
   bool ok = true;
   uint32_t phase[2] = {0u, 0u}, aphase[2] = {0u, 0u};
+  // Software pipeline of the operand loads: the raw values of stage st+1 are fetched into registers (float4 per
+  // (row, chunk) item, up to GTC_MAXI items per thread) before stage st is converted and stored, so the global-load
+  // latency overlaps the split / store / MMA issue of the current stage.
+  constexpr int GTC_MAXI = (NB * 16 + 7) / 8 * 8 * (GTC_KC / 4) / GTC_THREADS + 1;
+  float4 pre[GTC_MAXI], prw[GTC_MAXI];
+  const bool vec_ok = (npx % 4) == 0;               // channel rows are then 16-byte aligned
+  auto fetch = [&](int stage) {
+    const int p0 = stage * GTC_KC;
+#pragma unroll
+    for (int k = 0; k < GTC_MAXI; ++k) {
+      const int it = tid + k * GTC_THREADS;
+      const int r0 = it & 7, kc = (it >> 3) & 7, row = (it >> 6) * 8 + r0;
+      const int p = p0 + kc * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f), wv = v;
+      if (it < nitem && row < Dx && p < npx) {
+        const float* src = (row < D) ? Rb + (size_t)row * npx + p : obs + p;
+        if (vec_ok && p + 3 < npx) {
+          v = __ldg(reinterpret_cast<const float4*>(src));
+          wv = __ldg(reinterpret_cast<const float4*>(w + p));
+        } else {
+          v.x = __ldg(src); wv.x = __ldg(w + p);
+          if (p + 1 < npx) { v.y = __ldg(src + 1); wv.y = __ldg(w + p + 1); }
+          if (p + 2 < npx) { v.z = __ldg(src + 2); wv.z = __ldg(w + p + 2); }
+          if (p + 3 < npx) { v.w = __ldg(src + 3); wv.w = __ldg(w + p + 3); }
+        }
+      }
+      pre[k] = v; prw[k] = wv;
+    }
+  };
+  fetch(0);
   for (int st = 0; st < nstage; ++st) {
     const int s = st & 1, seg = st / GTC_SEG, a = seg & 1;
     unsigned char* hi = smem + s * GTC_STAGE;
@@ -135,22 +165,18 @@ __global__ void __launch_bounds__(GTC_THREADS) k_gram_tc(int D, int npx, const f
       ok = gtc_wait(bars + s, phase[s]) && ok;
       phase[s] ^= 1u;
     }
-    const int p0 = st * GTC_KC;
-    for (int it = tid; it < nitem; it += GTC_THREADS) {
+#pragma unroll
+    for (int k = 0; k < GTC_MAXI; ++k) {
       // item -> (row group, chunk, row in group): a quarter-warp covers 8 consecutive rows of one panel
+      const int it = tid + k * GTC_THREADS;
       const int r0 = it & 7, kc = (it >> 3) & 7, row = (it >> 6) * 8 + r0;
-      if (row >= Dx) continue;
-      const int p = p0 + kc * 4;
-      float v[4];
+      if (it >= nitem || row >= Dx) continue;
+      float v[4] = {pre[k].x, pre[k].y, pre[k].z, pre[k].w};
+      const float wv[4] = {prw[k].x, prw[k].y, prw[k].z, prw[k].w};
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        float x = 0.f;
-        if (p + q < npx) {
-          const float wv = __ldg(w + p + q);
-          if (row < D) { x = __ldg(Rb + (size_t)row * npx + p + q); if (x != x) x = 0.f; x *= wv; }   // NaN scrub (:228)
-          else x = __ldg(obs + p + q) * wv;
-        }
-        v[q] = x;
+        if (v[q] != v[q]) v[q] = 0.f;               // NaN scrub (:228)
+        v[q] *= wv[q];
       }
       float4 h, l;
       h.x = gtc_tf32(v[0]); h.y = gtc_tf32(v[1]); h.z = gtc_tf32(v[2]); h.w = gtc_tf32(v[3]);
@@ -159,6 +185,7 @@ __global__ void __launch_bounds__(GTC_THREADS) k_gram_tc(int D, int npx, const f
       *reinterpret_cast<float4*>(hi + off) = h;
       *reinterpret_cast<float4*>(lo + off) = l;
     }
+    if (st + 1 < nstage) fetch(st + 1);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core (async proxy)
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();

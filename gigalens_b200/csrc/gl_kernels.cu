@@ -538,6 +538,7 @@ struct gl_plan {
   int lq_chunk = 0;
   int lq_chunk_req = 0;
   float* d_comps = nullptr; float* d_R = nullptr; float* d_gram = nullptr; float* d_coef = nullptr; float* d_w = nullptr;
+  int* d_solve_queue = nullptr;   // [1 + chunk]: count, then the samples that need the eigen-solve
   float* d_ll = nullptr;
 };
 
@@ -554,6 +555,7 @@ static void gl_free_plan(gl_plan* p) {
   if (p->d_amp_slot) cudaFree(p->d_amp_slot);
   if (p->d_perm) cudaFree(p->d_perm);
   if (p->d_nan) cudaFree(p->d_nan);
+  if (p->d_solve_queue) cudaFree(p->d_solve_queue);
   for (void* q : {(void*)p->d_pos_off, (void*)p->d_pos_x, (void*)p->d_pos_y, (void*)p->d_pos_ex, (void*)p->d_pos_ey, (void*)p->d_pos_ll,
                   (void*)p->d_pos_chi, (void*)p->d_pos_grad}) if (q) cudaFree(q);
   for (cudaEvent_t e : p->tm_ev) cudaEventDestroy(e);
@@ -1257,6 +1259,7 @@ static int gl_lstsq_alloc(gl_plan* p) {
   p->lq_chunk = (int)cb;
   GL_CUDA(cudaMalloc((void**)&p->d_R, cb * (size_t)D * npx * sizeof(float)));
   GL_CUDA(cudaMalloc((void**)&p->d_gram, cb * (size_t)(D + 1) * (D + 1) * sizeof(float)));
+  GL_CUDA(cudaMalloc((void**)&p->d_solve_queue, (cb + 1) * sizeof(int)));
   GL_CUDA(cudaMalloc((void**)&p->d_coef, (size_t)p->bs * D * sizeof(float)));
   GL_CUDA(cudaMalloc((void**)&p->d_ll, (size_t)p->bs * 2 * sizeof(float)));
   GL_CUDA(cudaMalloc((void**)&p->d_comps, cb * per_sample));
@@ -1300,7 +1303,10 @@ static int gl_lstsq_forward(gl_plan* p, const float* params, float* image, float
       k_gram<<<nb, GLL_THREADS, smem_gram, st>>>(D, npx, p->d_R, p->d_w, p->d_obs, p->d_gram);
       GL_LAUNCH_CHECK("k_gram");
     }
-    k_pinv_solve<<<nb, 128, smem_solve, st>>>(D, p->d_gram, 1e-6, 16, p->d_coef + (size_t)b0 * D);
+    GL_CUDA(cudaMemsetAsync(p->d_solve_queue, 0, sizeof(int), st));   // [0] = count, [1..] = sample indices
+    k_pinv_solve<<<nb, 128, smem_solve, st>>>(D, p->d_gram, 1e-6, 16, p->d_coef + (size_t)b0 * D, 0, p->d_solve_queue + 1, p->d_solve_queue);
+    GL_LAUNCH_CHECK("k_pinv_solve");
+    k_pinv_solve<<<nb, 512, smem_solve, st>>>(D, p->d_gram, 1e-6, 16, p->d_coef + (size_t)b0 * D, 1, p->d_solve_queue + 1, p->d_solve_queue);
     GL_LAUNCH_CHECK("k_pinv_solve");
     k_lstsq_image<<<nb, GLL_THREADS, (size_t)D * sizeof(float), st>>>(
         D, npx, p->d_R, p->d_coef + (size_t)b0 * D, p->d_obs, p->d_err, image ? image + (size_t)b0 * npx : nullptr,

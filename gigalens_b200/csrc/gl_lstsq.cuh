@@ -128,8 +128,13 @@ __global__ void __launch_bounds__(GLL_THREADS) k_gram(int D, int npx, const floa
 // then V diag(1/lambda_i > cut) V^T h.
 // tf.linalg.pinv keeps singular values > rcond * max (src/gigalens/tf/simulator.py:235).
 //   grid = bs, block = 128, smem = 2*D*D doubles + small
-__global__ void __launch_bounds__(128) k_pinv_solve(int D, const float* __restrict__ gram, double rcond, int max_sweeps,
-                                                    float* __restrict__ coeffs) {
+// Two launches per chunk: phase 0 (128 threads per sample) runs the Cholesky fast path and appends the samples whose
+// certificate fails to `queue`; phase 1 (512 threads per sample, grid = chunk, CTAs beyond *count exit at once) runs
+// the eigen-solve for those only.  In the C3 prior ~0.6 % of the draws have a genuinely singular Gram matrix (cond
+// ~5e8); in a single launch those few CTAs ran ~10x longer than the rest and the tail was 90 % of the kernel time.
+__global__ void __launch_bounds__(512) k_pinv_solve(int D, const float* __restrict__ gram, double rcond, int max_sweeps,
+                                                    float* __restrict__ coeffs, int phase, int* __restrict__ queue,
+                                                    int* __restrict__ count) {
   extern __shared__ __align__(16) double s_d[];
   const int LD = D | 1;            // odd leading dimension: column walks (stride LD doubles) hit distinct banks
   double* A = s_d;                 // [D][LD]
@@ -137,9 +142,12 @@ __global__ void __launch_bounds__(128) k_pinv_solve(int D, const float* __restri
   double* cs = V + D * LD;         // [m/2 + 1][2] rotation (c, s) per pair; reused for y at the end
   int* pq = reinterpret_cast<int*>(cs + 2 * ((D + 1) / 2 + 1));   // [m/2 + 1][2]
   double* red = reinterpret_cast<double*>(pq + 2 * ((D + 1) / 2 + 1) + 2);   // [4]
-  const int b = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  if (phase == 1 && (int)blockIdx.x >= *count) return;
+  const int b = (phase == 1) ? queue[blockIdx.x] : (int)blockIdx.x;
   const int Dx = D + 1;
   const float* G = gram + (size_t)b * Dx * Dx;
+  if (phase == 0)
   // ---- fast path: when G is provably well conditioned (lambda_min > rcond * lambda_max) the
   // pseudo-inverse IS the inverse, and a Cholesky solve (D^3/3 flops) replaces the eigen-solve
   // (~60 D^3).  Certificate:  lambda_max <= tr(G)  and  lambda_min >= 1 / tr(G^-1) = 1 / ||L^-1||_F^2.
@@ -206,7 +214,8 @@ __global__ void __launch_bounds__(128) k_pinv_solve(int D, const float* __restri
       }
       return;
     }
-    __syncthreads();
+    if (tid == 0) queue[atomicAdd(count, 1)] = b;   // leave it to the phase-1 launch
+    return;
   }
   // ---- general path: symmetric Jacobi eigen-decomposition, pinv with the rcond cut
   for (int e = tid; e < D * D; e += nthr) {
