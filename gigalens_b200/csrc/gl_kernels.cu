@@ -1251,8 +1251,10 @@ static int gl_lstsq_alloc(gl_plan* p) {
   const int D = p->prog.depth, npx = p->n * p->n;
   if (D <= 0) return gl_fail("lstsq: the model has no linear light component");
   const size_t per_sample = (size_t)D * p->npix * sizeof(float);
-  size_t cb = (size_t)6 << 30;
-  cb = cb / per_sample;
+  // component-stack budget: 32 GB of the 180 GB HBM3e, but never more than 40 % of what is free right now
+  size_t budget = (size_t)32 << 30, free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b / 5 * 2 < budget) budget = free_b / 5 * 2;
+  size_t cb = budget / (per_sample + (size_t)D * npx * sizeof(float));
   if (cb < 1) cb = 1;
   if (p->lq_chunk_req > 0) cb = (size_t)p->lq_chunk_req;
   if (cb > (size_t)p->bs) cb = p->bs;

@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(512) k_pinv_solve(int D, const float* __restri
           if (fabs(apq) > 1e-300) {
             const double tau = (A[q * LD + q] - A[p * LD + p]) / (2.0 * apq);
             const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-            c = 1.0 / sqrt(1.0 + t * t);
+            c = rsqrt(1.0 + t * t);
             s = t * c;
           }
         }
@@ -261,26 +261,35 @@ __global__ void __launch_bounds__(512) k_pinv_solve(int D, const float* __restri
         pq[2 * tid] = p; pq[2 * tid + 1] = q;
       }
       __syncthreads();
-      // columns: A <- A J, V <- V J   (k fastest across threads: stride LD, conflict-free)
+      // two-sided rotation A <- J^T A J in ONE pass: the 2x2 block (rows of pair r) x (columns of pair r2) depends
+      // only on itself, so every thread owns whole blocks and no intermediate barrier is needed.
+      for (int r = tid >> 6; r < npair; r += nthr >> 6) {
+        const int p = pq[2 * r], q = pq[2 * r + 1];
+        const double c1 = cs[2 * r], s1 = cs[2 * r + 1];
+        const bool vq = q < D;
+        for (int r2 = tid & 63; r2 < npair; r2 += 64) {
+          const int p2 = pq[2 * r2], q2 = pq[2 * r2 + 1];
+          const double c2 = cs[2 * r2], s2 = cs[2 * r2 + 1];
+          const bool vq2 = q2 < D;
+          const double app = A[p * LD + p2], apq2 = vq2 ? A[p * LD + q2] : 0.0;
+          const double aqp = vq ? A[q * LD + p2] : 0.0, aqq = (vq && vq2) ? A[q * LD + q2] : 0.0;
+          // columns (J on the right), then rows (J^T on the left)
+          const double tpp = c2 * app - s2 * apq2, tpq = s2 * app + c2 * apq2;
+          const double tqp = c2 * aqp - s2 * aqq, tqq = s2 * aqp + c2 * aqq;
+          A[p * LD + p2] = c1 * tpp - s1 * tqp;
+          if (vq2) A[p * LD + q2] = c1 * tpq - s1 * tqq;
+          if (vq) A[q * LD + p2] = s1 * tpp + c1 * tqp;
+          if (vq && vq2) A[q * LD + q2] = s1 * tpq + c1 * tqq;
+        }
+      }
+      // eigenvectors: V <- V J   (k fastest across threads: stride LD, conflict-free)
       for (int e = tid; e < npair * D; e += nthr) {
         const int pr = e / D, k = e - pr * D;
         const int p = pq[2 * pr], q = pq[2 * pr + 1];
         if (q >= D) continue;
         const double c = cs[2 * pr], s = cs[2 * pr + 1];
-        const double akp = A[k * LD + p], akq = A[k * LD + q];
-        A[k * LD + p] = c * akp - s * akq; A[k * LD + q] = s * akp + c * akq;
         const double vkp = V[k * LD + p], vkq = V[k * LD + q];
         V[k * LD + p] = c * vkp - s * vkq; V[k * LD + q] = s * vkp + c * vkq;
-      }
-      __syncthreads();
-      // rows: A <- J^T A
-      for (int e = tid; e < npair * D; e += nthr) {
-        const int pr = e / D, k = e - pr * D;
-        const int p = pq[2 * pr], q = pq[2 * pr + 1];
-        if (q >= D) continue;
-        const double c = cs[2 * pr], s = cs[2 * pr + 1];
-        const double apk = A[p * LD + k], aqk = A[q * LD + k];
-        A[p * LD + k] = c * apk - s * aqk; A[q * LD + k] = s * apk + c * aqk;
       }
       __syncthreads();
     }
