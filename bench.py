@@ -279,11 +279,14 @@ def kernel_roofline(sim, stage_ms, step_ms, d):
     sm_mhz = peaks.get("sm_max_mhz", 1965.0)
     fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
     achieved_gbs = alg_bytes * bs / (ms * 1e-3) / 1e9
-    traffic = None
+    traffic, ncu_pipe = None, None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["kernels"]
         key = name + ("_p" if name.startswith("k_raytrace") else "")
-        traffic = tr.get(key, tr.get(name, {})).get("traffic_bytes")
+        rec = tr.get(key, tr.get(name, {}))
+        traffic = rec.get("traffic_bytes")
+        if "pipe_fma_pct" in rec:   # from the committed ncu --set full capture of the same kernel (profiles/)
+            ncu_pipe = {"sm__pipe_fma_cycles_active_pct": rec["pipe_fma_pct"], "smsp__issue_active_pct": rec["issue_active_pct"]}
     except Exception:
         pass
     which = "of measured" if _peaks() else "of fallback"
@@ -297,6 +300,7 @@ def kernel_roofline(sim, stage_ms, step_ms, d):
         "fp32": {"bound": "fp32_fma", "kernel": name, "achieved": alg_flops * bs / (ms * 1e-3) / 1e12, "peak": fp32_peak,
                  "unit": "TFLOP/s", "frac": alg_flops * bs / (ms * 1e-3) / 1e12 / fp32_peak,
                  "note": "nominal hand-counted flops/eval (FMA=2) of the same kernel; peak = 148 SM x 128 lanes x 2 x max SM clock (derived, not measured)",
+                 "ncu": ncu_pipe,
                  "whole_step": {"achieved": 34e6 * bs / (step_ms * 1e-3) / 1e12, "frac": 34e6 * bs / (step_ms * 1e-3) / 1e12 / fp32_peak,
                                 "flops_per_eval": 34e6}},
     }
