@@ -549,3 +549,14 @@ def test_lstsq_tensor_core_gram(n_max):
     assert err[1]["img"] <= max(1e-5, 3 * err[0]["img"]), err
     assert err[1]["lp"] <= max(1e-5, 3 * err[0]["lp"]), err
     assert err[1]["dz"] <= max(1e-4, 3 * err[0]["dz"]), err
+
+
+def test_tcgen05_gram_probe_binary():
+    """The stand-alone CUDA probe of k_gram_tc (tests/cuda/gram_tc_check.cu, built by __graft_entry__.build()):
+    one-hot layout checks and random Gram matrices up to D = 100 against a host fp64 Gram (< 2e-6 relative)."""
+    import os, subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cuda", "_build", "gram_tc_check")
+    if not os.path.exists(exe):
+        pytest.skip("probe not built (python __graft_entry__.py)")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "PASS" in out.stdout, out.stdout[-2000:]
