@@ -560,3 +560,70 @@ def test_tcgen05_gram_probe_binary():
         pytest.skip("probe not built (python __graft_entry__.py)")
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "PASS" in out.stdout, out.stdout[-2000:]
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json's full sizes: size-independent properties (the oracle cannot run these in seconds)
+# ---------------------------------------------------------------------------------------------
+def test_c2_full_batch_4096_properties():
+    """bs = 4096 (configs[1]): run-to-run determinism, independence of the batch composition (a sample's result
+    does not depend on its neighbours or on how the batch is sharded), exact linearity of the image in the light
+    amplitudes, and a directional finite-difference check of the gradient."""
+    wl = workloads.c2_workload()
+    bs = 4096
+    sim = LensSimulator(wl["phys_model"], wl["sim_config"], bs=bs)
+    pmod = ForwardProbModel(wl["prior"], wl["observed"], background_rms=0.2, exp_time=100.0)
+    z = torch.as_tensor(pmod.bij_inverse(wl["prior"].sample(bs, seed=0)), device="cuda")
+    a = [t.clone() for t in pmod.log_prob_and_grad(sim, z)]
+    b = [t.clone() for t in pmod.log_prob_and_grad(sim, z)]
+    assert all(torch.equal(x, y) for x, y in zip(a, b))                      # deterministic: no float atomics
+    assert bool(torch.isfinite(a[0]).all()) and bool(torch.isfinite(a[2]).all())
+    # shards: two halves on their own plans == the full batch, bit for bit (what multi-GPU sharding relies on)
+    half = LensSimulator(wl["phys_model"], wl["sim_config"], bs=bs // 2)
+    lo = [t.clone() for t in pmod.log_prob_and_grad(half, z[: bs // 2].contiguous())]
+    hi = [t.clone() for t in pmod.log_prob_and_grad(half, z[bs // 2:].contiguous())]
+    for k in range(3):
+        assert torch.equal(torch.cat([lo[k], hi[k]], 0), a[k])
+    small = LensSimulator(wl["phys_model"], wl["sim_config"], bs=64)
+    sub = pmod.log_prob_and_grad(small, z[1000:1064].contiguous())
+    assert torch.equal(sub[0], a[0][1000:1064]) and torch.equal(sub[2], a[2][1000:1064])
+    # image linearity: doubling both light amplitudes doubles the image exactly (power-of-two scaling is exact in fp32)
+    params = pmod.bij_forward(sim, z)
+    img = sim.simulate(params)
+    p2 = {g: [dict(d) for d in params[g]] for g in params}
+    p2["lens_light"][0]["Ie"] = params["lens_light"][0]["Ie"] * 2
+    p2["source_light"][0]["Ie"] = params["source_light"][0]["Ie"] * 2
+    assert torch.equal(sim.simulate(p2), img * 2)
+    # directional derivative: (logp(z + h v) - logp(z - h v)) / 2h  vs  <dz, v>, median over the batch (fp32 differences)
+    v = torch.randn(z.shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    v = v / v.norm(dim=1, keepdim=True)
+    h = 2e-3
+    lp_p = pmod.log_prob(sim, z + h * v)[0].double()
+    lp_m = pmod.log_prob(sim, z - h * v)[0].double()
+    fd = (lp_p - lp_m) / (2 * h)
+    an = (a[2].double() * v.double()).sum(1)
+    rel = ((fd - an).abs() / an.abs().clamp_min(1.0)).cpu().numpy()
+    assert np.median(rel) < 2e-3, np.median(rel)
+
+
+def test_c4_cluster_full_size_properties():
+    """200x200, ss = 2, 30 members, bs = 1024 (configs[3]): determinism, batch independence, and the packed two-pixel
+    kernels against the scalar-lane kernels."""
+    obs = workloads.c4_observation()
+    wl = workloads.c4_workload(observed=obs)
+    bs = 1024
+    sim = LensSimulator(wl["phys_model"], wl["sim_config"], bs=bs)
+    pmod = ForwardProbModel(wl["prior"], wl["observed"], background_rms=wl["background_rms"], exp_time=wl["exp_time"])
+    z = torch.as_tensor(pmod.bij_inverse(wl["prior"].sample(bs, seed=0)), device="cuda")
+    a = [t.clone() for t in pmod.log_prob_and_grad(sim, z)]
+    b = [t.clone() for t in pmod.log_prob_and_grad(sim, z)]
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    assert bool(torch.isfinite(a[0]).all()) and bool(torch.isfinite(a[2]).all())
+    small = LensSimulator(wl["phys_model"], wl["sim_config"], bs=8)
+    sub = pmod.log_prob_and_grad(small, z[500:508].contiguous())
+    assert torch.equal(sub[0], a[0][500:508]) and torch.equal(sub[2], a[2][500:508])
+    sim.set_option("packed_math", 0)
+    s = [t.clone() for t in pmod.log_prob_and_grad(sim, z)]
+    lp_rel = ((s[0] - a[0]).abs() / a[0].abs()).max().item()
+    dz_rel = ((s[2] - a[2]).abs().max(0).values / a[2].abs().max(0).values).max().item()
+    assert lp_rel < 1e-5 and dz_rel < 1e-4, (lp_rel, dz_rel)
