@@ -640,3 +640,31 @@ def test_c4_cluster_full_size_properties():
           " dz rel median/99%/max", np.median(dz_rel), np.percentile(dz_rel, 99), dz_rel.max())
     assert np.median(lp_rel) < 1e-6 and np.percentile(lp_rel, 99) < 1e-5
     assert np.median(dz_rel) < 1e-5 and np.percentile(dz_rel, 99) < 1e-4
+
+
+@pytest.mark.parametrize("tag,include_pixels", [("pos", False), ("both", True)])
+def test_positions_golden_vectors(tag, include_pixels):
+    """Committed golden vectors of the image-position likelihood (tests/golden/positions_golden.npz)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "positions_golden.npz"))
+    split = np.cumsum(g["n_img"])[:-1]
+    wl = workloads.c2_workload()
+    bs = g["z"].shape[0]
+    sim = LensSimulator(wl["phys_model"], wl["sim_config"], bs=bs)
+    pmod = ForwardProbModel(wl["prior"], wl["observed"] if include_pixels else None, background_rms=0.2, exp_time=100.0,
+                            centroids_x=np.split(g["cx"], split), centroids_y=np.split(g["cy"], split),
+                            centroids_errors_x=np.split(g["ex"], split), centroids_errors_y=np.split(g["ey"], split),
+                            include_pixels=include_pixels)
+    logp, chi2, dz = (t.cpu().numpy() for t in pmod.log_prob_and_grad(sim, torch.as_tensor(g["z"], device="cuda")))
+    assert_parity(logp[:, None], g[f"logp32_{tag}"][:, None], g[f"logp_{tag}"][:, None], 1e-5, "logp", g[f"logp_pert_{tag}"][:, None], axis=1)
+    assert np.allclose(chi2, g[f"chi2_{tag}"], rtol=1e-4)
+    for k in range(dz.shape[1]):
+        assert_parity(dz[:, k], g[f"dz32_{tag}"][:, k], g[f"dz_{tag}"][:, k], 1e-4, f"dz[{k}]", g[f"dz_pert_{tag}"][:, k])
+    # Hessian / magnification at the truth
+    cm = sim.compiled
+    sim1 = LensSimulator(wl["phys_model"], wl["sim_config"], bs=1)
+    params = sim1.compiled.unflatten(cm.flatten(workloads.DEMO_TRUTH, 1, torch, "cuda"))
+    H = np.stack([h.cpu().numpy()[0] for h in sim1.hessian(g["cx"], g["cy"], params["lens_mass"])], 0)
+    assert np.max(np.abs(H - g["hessian_truth"])) < 1e-5
+    mu = sim1.magnification(g["cx"], g["cy"], params["lens_mass"]).cpu().numpy()[0]
+    assert np.allclose(mu, g["magnification_truth"], rtol=2e-4)

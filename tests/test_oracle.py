@@ -184,3 +184,41 @@ def test_golden_vectors_reproduce():
     lp, chi, dz = oracle_bridge.logprob_and_grad(wl, gold["z"].astype(np.float64), torch.float64)
     assert np.allclose(lp, gold["logp"], rtol=1e-12) and np.allclose(dz, gold["dz"], rtol=1e-9, atol=1e-9)
     assert np.allclose(chi, gold["red_chi2"], rtol=1e-12)
+
+
+def _positions_golden():
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "positions_golden.npz"))
+    split = np.cumsum(g["n_img"])[:-1]
+    cen = dict(x=np.split(g["cx"], split), y=np.split(g["cy"], split), ex=np.split(g["ex"], split), ey=np.split(g["ey"], split))
+    return g, cen
+
+
+@pytest.mark.parametrize("tag,include_pixels", [("pos", False), ("both", True)])
+def test_positions_golden_pins_the_oracle(tag, include_pixels):
+    """tests/golden/positions_golden.npz (make_golden_positions.py): stats_positions alone and added to the pixel term."""
+    import oracle_bridge
+    from gigalens_b200 import workloads
+    g, cen = _positions_golden()
+    wl = dict(workloads.c2_workload(), centroids=cen, include_pixels=include_pixels)
+    lp, chi, dz = oracle_bridge.logprob_and_grad(wl, g["z"].astype(np.float64), torch.float64)
+    assert np.allclose(lp, g[f"logp_{tag}"], rtol=1e-12) and np.allclose(chi, g[f"chi2_{tag}"], rtol=1e-12)
+    assert np.allclose(dz, g[f"dz_{tag}"], rtol=1e-9, atol=1e-9 * np.abs(g[f"dz_{tag}"]).max())
+
+
+def test_hessian_golden_through_the_device_arithmetic():
+    """Golden Hessian / magnification at the image positions (truth parameters) vs the dual-number point driver (fp64)."""
+    import common
+    from gigalens_b200 import workloads
+    from gigalens_b200.simulator import CompiledModel
+    g, cen = _positions_golden()
+    wl = workloads.c2_workload()
+    cm = CompiledModel(wl["phys_model"])
+    mat = cm.flatten(workloads.DEMO_TRUTH, 1, torch, "cpu").numpy().astype(np.float64)
+    systems = [(cen["x"][s].astype(np.float64), cen["y"][s].astype(np.float64), cen["ex"][s].astype(np.float64),
+                cen["ey"][s].astype(np.float64)) for s in range(len(cen["x"]))]
+    out = common.host_positions(cm, mat, systems, np.float64, want_grad=False)
+    H = out["hess"][0]
+    # (flatten() rounds the truth parameters to fp32; the golden values used the python floats)
+    assert np.max(np.abs(H - g["hessian_truth"])) < 2e-7
+    mu = 1.0 / ((1 - H[0]) * (1 - H[3]) - H[1] * H[2])
+    assert np.allclose(mu, g["magnification_truth"], rtol=5e-6)
