@@ -291,6 +291,40 @@ struct DevFlush {
   }
 };
 
+// tf.where(is_nan(img), 0, img) (tf/simulator.py:140) in the adjoint: a scrubbed pixel passes no gradient.  The
+// forward kernels count scrubbed pixels per sample; for the (rare) samples that had any, this kernel re-evaluates
+// the forward and zeroes the cotangent of the scrubbed pixels before the adjoint kernel reads it.  CTAs of clean
+// samples exit at once, and the adjoint kernels stay free of the forward code (registers, instruction cache).
+template <int PPT, unsigned F>
+__global__ void __launch_bounds__(GLK_THREADS) k_nan_cotangent_mask(GlProgram P, int npix, const float* __restrict__ grid_x,
+                                                                    const float* __restrict__ grid_y,
+                                                                    const float* __restrict__ derived, int no_deflection,
+                                                                    float* __restrict__ gss, const int* __restrict__ nan_count) {
+  extern __shared__ __align__(16) float s_der[];
+  const int b = blockIdx.y;
+  if (nan_count[b] == 0) return;
+  const float* dsrc = derived + (size_t)b * P.der_total;
+  for (int i = threadIdx.x; i < P.der_total; i += blockDim.x) s_der[i] = dsrc[i];
+  __syncthreads();
+  const int per_batch = GLK_THREADS * PPT;
+  const int nbatch = (npix + per_batch - 1) / per_batch;
+  float* g = gss + (size_t)b * npix;
+  for (int batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
+    float x[PPT], y[PPT], v[PPT];
+    int pix[PPT];
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+      pix[j] = batch * per_batch + j * GLK_THREADS + threadIdx.x;
+      const int p = pix[j] < npix ? pix[j] : 0;
+      x[j] = __ldg(grid_x + p); y[j] = __ldg(grid_y + p);
+    }
+    gl_pix_image<float, PPT, F>(P, s_der, x, y, no_deflection != 0, v);
+#pragma unroll
+    for (int j = 0; j < PPT; ++j)
+      if (pix[j] < npix && v[j] != v[j]) g[pix[j]] = 0.f;
+  }
+}
+
 template <int PPT, unsigned F>
 __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_bwd(GlProgram P, int npix, const float* __restrict__ grid_x,
                                                               const float* __restrict__ grid_y,
@@ -308,7 +342,6 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_bwd(GlProgram P, int n
   for (int i = threadIdx.x; i < nw * P.g_total; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
   DevFlush flush{s_acc + warp * P.g_total, lane};
-  const bool had_nan = nan_count && nan_count[b] > 0;
   const int per_batch = GLK_THREADS * PPT;
   const int nbatch = (npix + per_batch - 1) / per_batch;
   const float* gsrc = gss + (size_t)b * npix;
@@ -321,12 +354,6 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_bwd(GlProgram P, int n
       const int p = pix < npix ? pix : 0;
       x[j] = __ldg(grid_x + p); y[j] = __ldg(grid_y + p);
       gs[j] = ok ? __ldg(gsrc + p) : 0.f;
-    }
-    if (had_nan) {   // tf.where(is_nan(img), 0, img): a scrubbed pixel passes no gradient (rare: re-evaluate the forward)
-      float v[PPT];
-      gl_pix_image<float, PPT, F>(P, s_der, x, y, no_deflection != 0, v);
-#pragma unroll
-      for (int j = 0; j < PPT; ++j) if (v[j] != v[j]) gs[j] = 0.f;
     }
     gl_pix_image_bwd<float, PPT, F>(P, s_der, x, y, gs, no_deflection != 0, flush);
   }
@@ -401,7 +428,6 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_bwd_p(GlProgram P, int
   for (int i = threadIdx.x; i < nw * P.g_total; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
   DevFlush flush{s_acc + warp * P.g_total, lane};
-  const bool had_nan = nan_count && nan_count[b] > 0;
   constexpr int NV = PPT / 2;
   const int npair = npix >> 1;
   const int per_batch = GLK_THREADS * NV;
@@ -421,12 +447,6 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_bwd_p(GlProgram P, int
       float2 gv = in ? __ldg(gsrc + p) : make_float2(0.f, 0.f);
       if (ss_mask && in) { if (!ss_mask[2 * p]) gv.x = 0.f; if (!ss_mask[2 * p + 1]) gv.y = 0.f; }
       gs[j] = GlF2(gv.x, gv.y);
-    }
-    if (had_nan) {
-      GlF2 v[NV];
-      gl_pix_image<GlF2, NV, F>(P, s_der, x, y, no_deflection != 0, v);
-#pragma unroll
-      for (int j = 0; j < NV; ++j) { if (v[j].x != v[j].x) gs[j].x = 0.f; if (v[j].y != v[j].y) gs[j].y = 0.f; }
     }
     gl_pix_image_bwd<GlF2, NV, F>(P, s_der, x, y, gs, no_deflection != 0, flush);
   }
@@ -978,8 +998,17 @@ static int gl_run_raytrace_fwd(gl_plan* p, float* ss_out, int no_deflection, cud
   return 0;
 }
 
-static int gl_run_raytrace_bwd(gl_plan* p, const float* gss, int no_deflection, cudaStream_t st) {
+static int gl_run_raytrace_bwd(gl_plan* p, float* gss, int no_deflection, cudaStream_t st) {
   dim3 grid(p->chunks, p->bs);
+  {   // NaN-scrubbed pixels pass no gradient: exits immediately for samples without any (nan_count from the forward pass)
+    const size_t smem_m = (size_t)p->prog.der_total * sizeof(float);
+    GL_FEAT_DISPATCH(p->feat_idx, {
+      if (smem_m > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_nan_cotangent_mask<4, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m));
+      k_nan_cotangent_mask<4, F><<<dim3(1, p->bs), GLK_THREADS, smem_m, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_derived,
+                                                                   no_deflection, gss, p->d_nan);
+    })
+    GL_LAUNCH_CHECK("k_nan_cotangent_mask");
+  }
   const size_t smem = (size_t)(p->prog.der_total + (GLK_THREADS / 32) * p->prog.g_total) * sizeof(float);
   if ((p->feat_idx == 0 || p->feat_idx == 2) && (p->npix % 2) == 0 && p->use_packed) {
     if (p->feat_idx == 0) {
