@@ -51,6 +51,8 @@ inline std::string gl_build_program(const gl_model_desc* m, GlBuilt& out, bool u
   if (P.n_prof > GL_MAX_PROF) return "too many profiles (max " + std::to_string(GL_MAX_PROF) + ")";
   if (m->n_params < 0) return "negative n_params";
   int der = 0, g = 0, depth = 0;
+  P.scr_prof = -1;
+  P.epl_tol = 1e-12f;
   for (int i = 0; i < P.n_prof; ++i) {
     const gl_profile_desc* src = i < P.n_lens ? &m->lens[i]
                                  : i < P.n_lens + P.n_ll ? &m->lens_light[i - P.n_lens]
@@ -64,6 +66,7 @@ inline std::string gl_build_program(const gl_model_desc* m, GlBuilt& out, bool u
     pr.niter = src->niter > 0 ? src->niter : 50;
     if (pr.type == GLT_EPL && pr.niter > 200) return "EPL niter cap above 200 is not supported";
     pr.ts = epl_table_stride(pr.niter);
+    if (pr.type == GLT_EPL && src->n_members == 0 && is_lens && P.scr_prof < 0) P.scr_prof = i;
     pr.n_max = src->n_max;
     pr.n_members = src->n_members;
     if (pr.n_members < 0) return "negative n_members";

@@ -219,6 +219,11 @@ __global__ void k_sample_bwd(GlProgram P, int bs, const float* __restrict__ para
 //   grid = (chunks, bs); a CTA walks pixel batches  chunk, chunk + chunks, ...
 // ---------------------------------------------------------------------------------------------
 #define GLK_THREADS 256
+// shared-memory layout of the adjoint ray-tracing kernels (floats): [der_total][nwarps * g_total][series scratch]
+__host__ __device__ inline int gl_scr_offset(const GlProgram& P) { return (P.der_total + (GLK_THREADS / 32) * P.g_total + 3) & ~3; }
+__host__ __device__ inline int gl_bwd_smem_floats(const GlProgram& P, int ppt) {
+  return gl_scr_offset(P) + (P.scr_prof >= 0 ? GL_EPL_NSTATE * ppt * GLK_THREADS : 0);
+}
 
 template <int PPT, unsigned F>
 __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_fwd(GlProgram P, int npix, const float* __restrict__ grid_x,
@@ -342,6 +347,8 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_bwd(GlProgram P, int n
   for (int i = threadIdx.x; i < nw * P.g_total; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
   DevFlush flush{s_acc + warp * P.g_total, lane};
+  // series state of the EPL entry, parked by the forward sweep for the adjoint sweep: [GL_EPL_NSTATE * PPT][threads]
+  float* scr = (P.scr_prof >= 0) ? smem + gl_scr_offset(P) + threadIdx.x : nullptr;
   const int per_batch = GLK_THREADS * PPT;
   const int nbatch = (npix + per_batch - 1) / per_batch;
   const float* gsrc = gss + (size_t)b * npix;
@@ -355,7 +362,7 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_bwd(GlProgram P, int n
       x[j] = __ldg(grid_x + p); y[j] = __ldg(grid_y + p);
       gs[j] = ok ? __ldg(gsrc + p) : 0.f;
     }
-    gl_pix_image_bwd<float, PPT, F>(P, s_der, x, y, gs, no_deflection != 0, flush);
+    gl_pix_image_bwd<float, PPT, F>(P, s_der, x, y, gs, no_deflection != 0, flush, scr, GLK_THREADS);
   }
   __syncthreads();
   float* out = gpart + ((size_t)b * gridDim.x + blockIdx.x) * P.g_total;
@@ -429,6 +436,7 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_bwd_p(GlProgram P, int
   __syncthreads();
   DevFlush flush{s_acc + warp * P.g_total, lane};
   constexpr int NV = PPT / 2;
+  GlF2* scr = (P.scr_prof >= 0) ? reinterpret_cast<GlF2*>(smem + gl_scr_offset(P)) + threadIdx.x : nullptr;   // [GL_EPL_NSTATE * NV][threads]
   const int npair = npix >> 1;
   const int per_batch = GLK_THREADS * NV;
   const int nbatch = (npair + per_batch - 1) / per_batch;
@@ -448,7 +456,7 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_bwd_p(GlProgram P, int
       if (ss_mask && in) { if (!ss_mask[2 * p]) gv.x = 0.f; if (!ss_mask[2 * p + 1]) gv.y = 0.f; }
       gs[j] = GlF2(gv.x, gv.y);
     }
-    gl_pix_image_bwd<GlF2, NV, F>(P, s_der, x, y, gs, no_deflection != 0, flush);
+    gl_pix_image_bwd<GlF2, NV, F>(P, s_der, x, y, gs, no_deflection != 0, flush, scr, GLK_THREADS);
   }
   __syncthreads();
   float* out = gpart + ((size_t)b * gridDim.x + blockIdx.x) * P.g_total;
@@ -819,6 +827,10 @@ int gl_plan_create(const gl_model_desc* model, const gl_sim_config* sim, int32_t
 int gl_plan_set_option(gl_plan* p, const char* name, int32_t value) {
   if (!p || !name) return gl_fail("gl_plan_set_option: NULL argument");
   if (!strcmp(name, "epl_batch_max")) { p->epl_batch_max = value; return 0; }
+  if (!strcmp(name, "epl_tol_exp10")) {   // EPL series terms below 10^-value are dropped (12 = the reference's constant, epl.py:37)
+    if (value < 6 || value > 30) return gl_fail("gl_plan_set_option: epl_tol_exp10 must be in [6, 30]");
+    p->prog.epl_tol = powf(10.f, -(float)value); return 0;
+  }
   if (!strcmp(name, "lstsq")) { p->lstsq = value; return 0; }
   if (!strcmp(name, "no_deflection")) { p->no_deflection = value; return 0; }
   if (!strcmp(name, "components")) {   // gl_simulate only: 1 = lens light, 2 = source light, 3 = both
@@ -1009,7 +1021,7 @@ static int gl_run_raytrace_bwd(gl_plan* p, float* gss, int no_deflection, cudaSt
     })
     GL_LAUNCH_CHECK("k_nan_cotangent_mask");
   }
-  const size_t smem = (size_t)(p->prog.der_total + (GLK_THREADS / 32) * p->prog.g_total) * sizeof(float);
+  const size_t smem = (size_t)gl_bwd_smem_floats(p->prog, 4) * sizeof(float);
   if ((p->feat_idx == 0 || p->feat_idx == 2) && (p->npix % 2) == 0 && p->use_packed) {
     if (p->feat_idx == 0) {
       if (smem > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_bwd_p<4, GL_FS0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

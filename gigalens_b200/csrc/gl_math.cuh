@@ -121,7 +121,7 @@ GL_HD double gl_atan2_fast(double y, double x) { return atan2(y, x); }
 //                            FADD2 (sm_100+), i.e. half the issue slots of the issue-bound kernels.
 // Per-pixel conditionals are written as selects (gl_where_*), so the same source serves both.
 // ---------------------------------------------------------------------------------------------
-struct GlF2 {
+struct alignas(8) GlF2 {
   float x, y;
   GL_HD GlF2() {}
   GL_HD GlF2(float a) : x(a), y(a) {}
@@ -305,38 +305,34 @@ GL_HD void ellip_bwd(T e1, T e2, T cmax, T gphi, T gq, T& ge1, T& ge2) {
 // =============================================================================================
 // EPL  (src/gigalens/tf/profiles/mass/epl.py:19-57)
 //   raw  : theta_E, gamma, e1, e2, center_x, center_y
-//   d[]  : cx, cy, cos(phi), sin(phi), q, b, t, pref0 = 2b/(1+q), f, N (trip count),
-//          then three tables of stride ts:  A_n, dA_n/df, dA_n/dt   (n = 0..N)
+//   d[]  : cx, cy, cos(phi), sin(phi), q, b, t, pref0 = 2b/(1+q), f, N (trip count), log2 b, R_N,
+//          then two tables of stride ts:  Bq_m = A_{m+1}/f,  Bt_m = dA_{m+1}/dt   (m = 0..N-1)
 //   dvars: cx, cy, phi, q, b, t, f, pref0
-// The reference iterates Omega_n = c_n Rot(2 ang) Omega_{n-1}, c_n = -f (2n-(2-t))/(2n+(2-t)), and
+// The reference iterates Omega_n = c_n Rot(2 ang) Omega_{n-1}, c_n = -f (2n-s)/(2n+s), s = 2-t, and
 // sums Omega_0..Omega_N.  With u = e^{i ang}, w = u^2 and A_n = prod_{k<=n} c_k (per-sample
-// constants) that sum is u * P(w), P(w) = sum_n A_n w^n, which we evaluate by complex Horner:
-// 4 FMA per trip instead of the recurrence's 8, and no per-pixel state beyond (P_re, P_im).
+// constants) that sum is u * P(w), P(w) = sum_n A_n w^n = 1 + f w Q(w), Q = sum_m Bq_m w^m, which we
+// evaluate by complex Horner: 4 FMA per trip instead of the recurrence's 8, and no per-pixel state
+// beyond (Q_re, Q_im).
+//
+// Adjoint.  dP/dt needs its own series T = w sum_m Bt_m w^m.  dP/df (and w dP/dw = f dP/df) does
+// not: c_n (2n+s) = -f (2n-s) makes the truncated sum satisfy the first-order relation
+//     2 D (1 + f w) = f w [ R_N w^N - (s Q + t P) ],   D = w dP/dw = f dP/df,  R_N = A_N (2N+2-s),
+// so dP/df = w [R_N w^N - (s Q + t P)] / (2 (1 + f w)) in closed form (well conditioned: no
+// division by f, no P - 1).  R_N w^N is the footprint of the truncation; it is below rounding unless
+// the iteration cap cuts the series short, and is evaluated (binary powering) only for such samples.
 // =============================================================================================
-enum { EPL_CX = 0, EPL_CY, EPL_C, EPL_S, EPL_Q, EPL_B, EPL_T, EPL_PREF0, EPL_F, EPL_N, EPL_LOG2B, EPL_TAB = 12 };
+enum { EPL_CX = 0, EPL_CY, EPL_C, EPL_S, EPL_Q, EPL_B, EPL_T, EPL_PREF0, EPL_F, EPL_N, EPL_LOG2B, EPL_RN, EPL_TAB = 12 };
 enum { EPLG_CX = 0, EPLG_CY, EPLG_PHI, EPLG_Q, EPLG_B, EPLG_T, EPLG_F, EPLG_PREF0 };
-
-// Complex Horner step P <- P w + a for TWO pixels at once with Blackwell's packed fp32 FMA (FFMA2,
-// sm_100+): the series loops are issue-bound, and one FFMA2 retires two FMAs per issue slot.
-#if defined(__CUDA_ARCH__)
-#define GL_HAVE_F32X2 1
-struct GlC2 { float2 r, i; };   // (re, im) of two pixels
-__device__ __forceinline__ void gl_horner2(GlC2& P, const float2 wr, const float2 wi, const float a) {
-  const float2 a2 = make_float2(a, a);
-  const float2 nPi = make_float2(-P.i.x, -P.i.y);
-  const float2 pr = __ffma2_rn(P.r, wr, __ffma2_rn(nPi, wi, a2));
-  const float2 pi = __ffma2_rn(P.r, wi, __fmul2_rn(P.i, wr));
-  P.r = pr; P.i = pi;
-}
-#endif
+#define GL_EPL_NSTATE 4   // per-pixel series state (Q_re, Q_im, T'_re, T'_im) a forward pass can hand to the adjoint
 
 GL_HD int epl_table_stride(int niter_cap) { return ((niter_cap + 1) + 3) & ~3; }
-GL_HD int epl_der_size(int niter_cap) { return EPL_TAB + 3 * epl_table_stride(niter_cap); }
+GL_HD int epl_der_size(int niter_cap) { return EPL_TAB + 2 * epl_table_stride(niter_cap); }
 
-// Trip count of `tf.while_loop(i < niter, i0 = 1.0, maximum_iterations=cap)` (epl.py:37,47-54).
+// Trip count of `tf.while_loop(i < niter, i0 = 1.0, maximum_iterations=cap)` (epl.py:37,47-54);
+// tol = 1e-12 is the reference's constant.
 template <class T>
-GL_HD int epl_trip_count(T fmax, int cap) {
-  T niter = gl_log(T(1e-12)) / gl_log(fmax) + T(2);
+GL_HD int epl_trip_count(T fmax, int cap, T tol) {
+  T niter = gl_log(tol) / gl_log(fmax) + T(2);
   if (!(niter > T(1))) return 0;  // also catches NaN / -inf
   T n = gl_ceil(niter) - T(1);
   if (n > T(cap)) return cap;
@@ -344,9 +340,9 @@ GL_HD int epl_trip_count(T fmax, int cap) {
 }
 
 // fmax_batch < 0  => use this sample's own f (default; differs from the reference's batch-global
-// count only by series terms below 1e-12, SURVEY.md §7 "Iteration count semantics").
+// count only by series terms below tol, SURVEY.md §7 "Iteration count semantics").
 template <class T>
-GL_HD void epl_prep(const T* raw, T* d, int niter_cap, T fmax_batch) {
+GL_HD void epl_prep(const T* raw, T* d, int niter_cap, T fmax_batch, T tol) {
   T theta_E = raw[0], gamma = raw[1], e1 = raw[2], e2 = raw[3];
   T phi, q, c;
   ellip_fwd(e1, e2, T(1), phi, q, c);
@@ -359,29 +355,31 @@ GL_HD void epl_prep(const T* raw, T* d, int niter_cap, T fmax_batch) {
   d[EPL_Q] = q; d[EPL_B] = b; d[EPL_T] = t;
   d[EPL_PREF0] = (T(2) * b) / (T(1) + q);
   d[EPL_F] = f;
-  int N = epl_trip_count(fmax_batch < T(0) ? f : fmax_batch, niter_cap);
+  int N = epl_trip_count(fmax_batch < T(0) ? f : fmax_batch, niter_cap, tol);
   d[EPL_N] = T(N);
-  d[EPL_LOG2B] = gl_log(b) * T(GL_LOG2E); d[11] = T(0);
+  d[EPL_LOG2B] = gl_log(b) * T(GL_LOG2E);
   const int ts = epl_table_stride(niter_cap);
-  T* A = d + EPL_TAB; T* Af = A + ts; T* At = Af + ts;
+  T* Bq = d + EPL_TAB; T* Bt = Bq + ts;
   T s = T(2) - t;
-  T a = T(1), af = T(0), at = T(0);
-  A[0] = a; Af[0] = af; At[0] = at;
-  for (int n = 1; n < ts; ++n) {
+  T a = T(1), at = T(0), bq = T(0);   // A_n, dA_n/dt, A_n / f
+  for (int n = 1; n <= ts; ++n) {
     if (n <= N) {
       T tn = T(2 * n);
       T kap = -(tn - s) / (tn + s);           // c_n = f * kap
       T cn = f * kap;
       T dcdt = -f * T(4 * n) / ((tn + s) * (tn + s));
-      T a1 = a * cn;
-      T af1 = af * cn + a * kap;
-      T at1 = at * cn + a * dcdt;
-      a = a1; af = af1; at = at1;
-      A[n] = a; Af[n] = af; At[n] = at;
+      at = at * cn + a * dcdt;
+      bq = (n == 1) ? kap : bq * cn;
+      a = a * cn;
+      Bq[n - 1] = bq; Bt[n - 1] = at;
     } else {
-      A[n] = T(0); Af[n] = T(0); At[n] = T(0);
+      Bq[n - 1] = T(0); Bt[n - 1] = T(0);
     }
   }
+  // truncation footprint in the closed-form f-derivative; dropped when below a tenth of an ulp of the O(1) sum
+  const T RN = a * (T(2 * N + 2) - s);
+  const T eps = sizeof(T) == 4 ? T(1.2e-7) : T(2.3e-16);
+  d[EPL_RN] = (gl_abs(RN) > T(0.1) * eps) ? RN : T(0);
 }
 
 template <class T>
@@ -426,53 +424,94 @@ GL_HD void epl_geom(const S* d, V x, V y, EplGeom<V>& G) {
   G.wi = V(S(2)) * G.Cs * G.Ss;
 }
 
-template <class V, int NP>
-GL_HD void epl_fwd(const typename gl_scalar_of<V>::type* d, int ts, const V* x, const V* y, V* ax, V* ay) {
-  typedef typename gl_scalar_of<V>::type S;
-  EplGeom<V> G[NP];
-  V Pr[NP], Pi[NP];
-  const int N = (int)d[EPL_N];
-  const S* A = d + EPL_TAB;
-  (void)ts;
-#pragma unroll
-  for (int j = 0; j < NP; ++j) { epl_geom<V, S>(d, x[j], y[j], G[j]); Pr[j] = V(A[N]); Pi[j] = V(S(0)); }
-  bool done = false;
-#ifdef GL_HAVE_F32X2
-  if constexpr (sizeof(V) == 4 && (NP % 2) == 0) {   // scalar float lanes: pack pixel pairs for the series only
-    GlC2 P2[NP / 2]; float2 wr2[NP / 2], wi2[NP / 2];
-#pragma unroll
-    for (int h = 0; h < NP / 2; ++h) {
-      P2[h].r = make_float2(Pr[2 * h], Pr[2 * h + 1]); P2[h].i = make_float2(0.f, 0.f);
-      wr2[h] = make_float2(G[2 * h].wr, G[2 * h + 1].wr); wi2[h] = make_float2(G[2 * h].wi, G[2 * h + 1].wi);
-    }
-    for (int n = N - 1; n >= 0; --n) {
-      const float a = A[n];
-#pragma unroll
-      for (int h = 0; h < NP / 2; ++h) gl_horner2(P2[h], wr2[h], wi2[h], a);
-    }
-#pragma unroll
-    for (int h = 0; h < NP / 2; ++h) {
-      Pr[2 * h] = P2[h].r.x; Pr[2 * h + 1] = P2[h].r.y; Pi[2 * h] = P2[h].i.x; Pi[2 * h + 1] = P2[h].i.y;
-    }
-    done = true;
-  }
+// Complex Horner step P <- P w + a for TWO pixels at once with Blackwell's packed fp32 FMA (FFMA2,
+// sm_100+): the series loops are issue-bound, and one FFMA2 retires two FMAs per issue slot.
+#if defined(__CUDA_ARCH__)
+#define GL_HAVE_F32X2 1
+struct GlC2 { float2 r, i; };   // (re, im) of two pixels
+__device__ __forceinline__ void gl_horner2(GlC2& P, const float2 wr, const float2 wi, const float a) {
+  const float2 a2 = make_float2(a, a);
+  const float2 nPi = make_float2(-P.i.x, -P.i.y);
+  const float2 pr = __ffma2_rn(P.r, wr, __ffma2_rn(nPi, wi, a2));
+  const float2 pi = __ffma2_rn(P.r, wi, __fmul2_rn(P.i, wr));
+  P.r = pr; P.i = pi;
+}
 #endif
-  if (!done)
-#pragma unroll 2
-  for (int n = N - 1; n >= 0; --n) {   // unrolled by two so the loop-carried (P_re, P_im) ping-pong without register copies
-    const V a = V(A[n]);
+
+// Q = sum_m Bq_m w^m and (WANT_T) T' = sum_m Bt_m w^m, m = 0..N-1, at NP lanes.
+template <class V, int NP, bool WANT_T>
+GL_HD void epl_series(const typename gl_scalar_of<V>::type* d, int ts, const EplGeom<V>* G, V* Qr, V* Qi, V* Tr, V* Ti) {
+  typedef typename gl_scalar_of<V>::type S;
+  const int N = (int)d[EPL_N];
+  const S* Bq = d + EPL_TAB; const S* Bt = Bq + ts;
+  if (N <= 0) {
 #pragma unroll
-    for (int j = 0; j < NP; ++j) {
-      V pr = gl_fma(Pr[j], G[j].wr, gl_fma(-Pi[j], G[j].wi, a));
-      V pi = gl_fma(Pr[j], G[j].wi, Pi[j] * G[j].wr);
-      Pr[j] = pr; Pi[j] = pi;
-    }
+    for (int j = 0; j < NP; ++j) { Qr[j] = V(S(0)); Qi[j] = V(S(0)); if constexpr (WANT_T) { Tr[j] = V(S(0)); Ti[j] = V(S(0)); } }
+    return;
   }
-  const V c = V(d[EPL_C]), s = V(d[EPL_S]), l2b = V(d[EPL_LOG2B]), tm1 = V(d[EPL_T] - S(1)), pref0 = V(d[EPL_PREF0]);
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
-    V fx = gl_fma(G[j].Cs, Pr[j], -(G[j].Ss * Pi[j]));
-    V fy = gl_fma(G[j].Cs, Pi[j], G[j].Ss * Pr[j]);
+    Qr[j] = V(Bq[N - 1]); Qi[j] = V(S(0));
+    if constexpr (WANT_T) { Tr[j] = V(Bt[N - 1]); Ti[j] = V(S(0)); }
+  }
+#ifdef GL_HAVE_F32X2
+  if constexpr (sizeof(V) == 4 && (NP % 2) == 0) {   // scalar float lanes: pack pixel pairs for the series only
+    GlC2 Q2[NP / 2], T2[NP / 2]; float2 wr2[NP / 2], wi2[NP / 2];
+#pragma unroll
+    for (int h = 0; h < NP / 2; ++h) {
+      Q2[h].r = make_float2(Qr[2 * h], Qr[2 * h + 1]); Q2[h].i = make_float2(0.f, 0.f);
+      if constexpr (WANT_T) { T2[h].r = make_float2(Tr[2 * h], Tr[2 * h + 1]); T2[h].i = make_float2(0.f, 0.f); }
+      wr2[h] = make_float2(G[2 * h].wr, G[2 * h + 1].wr); wi2[h] = make_float2(G[2 * h].wi, G[2 * h + 1].wi);
+    }
+    for (int n = N - 2; n >= 0; --n) {
+      const float a = Bq[n], at = Bt[n];
+#pragma unroll
+      for (int h = 0; h < NP / 2; ++h) {
+        gl_horner2(Q2[h], wr2[h], wi2[h], a);
+        if constexpr (WANT_T) gl_horner2(T2[h], wr2[h], wi2[h], at);
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < NP / 2; ++h) {
+      Qr[2 * h] = Q2[h].r.x; Qr[2 * h + 1] = Q2[h].r.y; Qi[2 * h] = Q2[h].i.x; Qi[2 * h + 1] = Q2[h].i.y;
+      if constexpr (WANT_T) { Tr[2 * h] = T2[h].r.x; Tr[2 * h + 1] = T2[h].r.y; Ti[2 * h] = T2[h].i.x; Ti[2 * h + 1] = T2[h].i.y; }
+    }
+    return;
+  }
+#endif
+#pragma unroll 2
+  for (int n = N - 2; n >= 0; --n) {   // unrolled by two so the loop-carried pairs ping-pong without register copies
+    const V a = V(Bq[n]);
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      V qr = gl_fma(Qr[j], G[j].wr, gl_fma(-Qi[j], G[j].wi, a));
+      V qi = gl_fma(Qr[j], G[j].wi, Qi[j] * G[j].wr);
+      Qr[j] = qr; Qi[j] = qi;
+    }
+    if constexpr (WANT_T) {
+      const V at = V(Bt[n]);
+#pragma unroll
+      for (int j = 0; j < NP; ++j) {
+        V tr = gl_fma(Tr[j], G[j].wr, gl_fma(-Ti[j], G[j].wi, at));
+        V ti = gl_fma(Tr[j], G[j].wi, Ti[j] * G[j].wr);
+        Tr[j] = tr; Ti[j] = ti;
+      }
+    }
+  }
+}
+
+// deflection from the geometry and Q (P = 1 + f w Q)
+template <class V, int NP>
+GL_HD void epl_alpha(const typename gl_scalar_of<V>::type* d, const EplGeom<V>* G, const V* Qr, const V* Qi, V* ax, V* ay) {
+  typedef typename gl_scalar_of<V>::type S;
+  const V c = V(d[EPL_C]), s = V(d[EPL_S]), l2b = V(d[EPL_LOG2B]), tm1 = V(d[EPL_T] - S(1)), pref0 = V(d[EPL_PREF0]);
+  const V f = V(d[EPL_F]);
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    const V zr = f * G[j].wr, zi = f * G[j].wi;
+    const V Pr = gl_fma(zr, Qr[j], gl_fma(-zi, Qi[j], V(S(1)))), Pi = gl_fma(zr, Qi[j], zi * Qr[j]);
+    V fx = gl_fma(G[j].Cs, Pr, -(G[j].Ss * Pi));
+    V fy = gl_fma(G[j].Cs, Pi, G[j].Ss * Pr);
     V pref = pref0 * gl_exp2_fast(tm1 * gl_fma(V(S(-0.5)), G[j].l2r2, l2b));   // (b/R)^(t-1)
     fx = fx * pref; fy = fy * pref;
     ax[j] = gl_fma(fx, c, -(fy * s));
@@ -480,69 +519,70 @@ GL_HD void epl_fwd(const typename gl_scalar_of<V>::type* d, int ts, const V* x, 
   }
 }
 
-// Adjoint: (gax, gay) is the cotangent of the deflection; accumulates into g[EPLG_*] (lane-wise).
 template <class V, int NP>
-GL_HD void epl_bwd(const typename gl_scalar_of<V>::type* d, int ts, const V* x, const V* y, const V* gax, const V* gay, V* g) {
+GL_HD void epl_fwd(const typename gl_scalar_of<V>::type* d, int ts, const V* x, const V* y, V* ax, V* ay) {
   typedef typename gl_scalar_of<V>::type S;
   EplGeom<V> G[NP];
-  V Pr[NP], Pi[NP], Fr[NP], Fi[NP], Tr[NP], Ti[NP];
-  const int N = (int)d[EPL_N];
-  const S* A = d + EPL_TAB; const S* Af = A + ts; const S* At = Af + ts;
+  V Qr[NP], Qi[NP];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) epl_geom<V, S>(d, x[j], y[j], G[j]);
+  epl_series<V, NP, false>(d, ts, G, Qr, Qi, (V*)nullptr, (V*)nullptr);
+  epl_alpha<V, NP>(d, G, Qr, Qi, ax, ay);
+}
+
+// Forward that also runs the T' series and parks (Q, T') in scr[k * scr_stride], k < GL_EPL_NSTATE * NP,
+// for epl_bwd_load: the adjoint kernels need the deflection first (source-plane position) and the
+// series again later, and the series is the expensive part.
+template <class V, int NP>
+GL_HD void epl_fwd_save(const typename gl_scalar_of<V>::type* d, int ts, const V* x, const V* y, V* ax, V* ay, V* scr, int scr_stride) {
+  typedef typename gl_scalar_of<V>::type S;
+  EplGeom<V> G[NP];
+  V Qr[NP], Qi[NP], Tr[NP], Ti[NP];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) epl_geom<V, S>(d, x[j], y[j], G[j]);
+  epl_series<V, NP, true>(d, ts, G, Qr, Qi, Tr, Ti);
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
-    epl_geom<V, S>(d, x[j], y[j], G[j]);
-    Pr[j] = V(A[N]); Pi[j] = V(S(0)); Fr[j] = V(Af[N]); Fi[j] = V(S(0)); Tr[j] = V(At[N]); Ti[j] = V(S(0));
+    scr[(4 * j + 0) * scr_stride] = Qr[j]; scr[(4 * j + 1) * scr_stride] = Qi[j];
+    scr[(4 * j + 2) * scr_stride] = Tr[j]; scr[(4 * j + 3) * scr_stride] = Ti[j];
   }
-  bool done = false;
-#ifdef GL_HAVE_F32X2
-  if constexpr (sizeof(V) == 4 && (NP % 2) == 0) {
-    GlC2 P2[NP / 2], F2[NP / 2], T2[NP / 2]; float2 wr2[NP / 2], wi2[NP / 2];
-#pragma unroll
-    for (int h = 0; h < NP / 2; ++h) {
-      P2[h].r = make_float2(Pr[2 * h], Pr[2 * h + 1]); P2[h].i = make_float2(0.f, 0.f);
-      F2[h].r = make_float2(Fr[2 * h], Fr[2 * h + 1]); F2[h].i = make_float2(0.f, 0.f);
-      T2[h].r = make_float2(Tr[2 * h], Tr[2 * h + 1]); T2[h].i = make_float2(0.f, 0.f);
-      wr2[h] = make_float2(G[2 * h].wr, G[2 * h + 1].wr); wi2[h] = make_float2(G[2 * h].wi, G[2 * h + 1].wi);
-    }
-    for (int n = N - 1; n >= 0; --n) {
-      const float a = A[n], af = Af[n], at = At[n];
-#pragma unroll
-      for (int h = 0; h < NP / 2; ++h) {
-        gl_horner2(P2[h], wr2[h], wi2[h], a);
-        gl_horner2(F2[h], wr2[h], wi2[h], af);
-        gl_horner2(T2[h], wr2[h], wi2[h], at);
-      }
-    }
-#pragma unroll
-    for (int h = 0; h < NP / 2; ++h) {
-      Pr[2 * h] = P2[h].r.x; Pr[2 * h + 1] = P2[h].r.y; Pi[2 * h] = P2[h].i.x; Pi[2 * h + 1] = P2[h].i.y;
-      Fr[2 * h] = F2[h].r.x; Fr[2 * h + 1] = F2[h].r.y; Fi[2 * h] = F2[h].i.x; Fi[2 * h + 1] = F2[h].i.y;
-      Tr[2 * h] = T2[h].r.x; Tr[2 * h + 1] = T2[h].r.y; Ti[2 * h] = T2[h].i.x; Ti[2 * h + 1] = T2[h].i.y;
-    }
-    done = true;
-  }
-#endif
-  if (!done)
-#pragma unroll 2
-  for (int n = N - 1; n >= 0; --n) {
-    const V a = V(A[n]), af = V(Af[n]), at = V(At[n]);
-#pragma unroll
-    for (int j = 0; j < NP; ++j) {
-      V wr = G[j].wr, wi = G[j].wi;
-      V pr = gl_fma(Pr[j], wr, gl_fma(-Pi[j], wi, a)), pi = gl_fma(Pr[j], wi, Pi[j] * wr);
-      V fr = gl_fma(Fr[j], wr, gl_fma(-Fi[j], wi, af)), fi = gl_fma(Fr[j], wi, Fi[j] * wr);
-      V tr = gl_fma(Tr[j], wr, gl_fma(-Ti[j], wi, at)), ti = gl_fma(Tr[j], wi, Ti[j] * wr);
-      Pr[j] = pr; Pi[j] = pi; Fr[j] = fr; Fi[j] = fi; Tr[j] = tr; Ti[j] = ti;
-    }
-  }
+  epl_alpha<V, NP>(d, G, Qr, Qi, ax, ay);
+}
+
+// Adjoint given the series values: (gax, gay) is the cotangent of the deflection; accumulates into
+// g[EPLG_*] (lane-wise).
+template <class V, int NP>
+GL_HD void epl_bwd_core(const typename gl_scalar_of<V>::type* d, const EplGeom<V>* G, const V* Qr, const V* Qi, const V* Tqr,
+                        const V* Tqi, const V* gax, const V* gay, V* g) {
+  typedef typename gl_scalar_of<V>::type S;
   const V c = V(d[EPL_C]), s = V(d[EPL_S]), q = V(d[EPL_Q]), l2b = V(d[EPL_LOG2B]), tm1 = V(d[EPL_T] - S(1));
-  const V pref0 = V(d[EPL_PREF0]), f2 = V(S(2) * d[EPL_F]);
+  const V pref0 = V(d[EPL_PREF0]), f = V(d[EPL_F]), f2 = V(S(2) * d[EPL_F]);
   const V tm1_over_b = V((d[EPL_T] - S(1)) / d[EPL_B]);
+  const V tt = V(d[EPL_T]), ss = V(S(2) - d[EPL_T]);
+  const S RN = d[EPL_RN];
+  const int N = (int)d[EPL_N];
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
     const EplGeom<V>& E = G[j];
+    const V zr = f * E.wr, zi = f * E.wi;                                           // f w
+    const V Pr = gl_fma(zr, Qr[j], gl_fma(-zi, Qi[j], V(S(1)))), Pi = gl_fma(zr, Qi[j], zi * Qr[j]);
+    const V Tr = gl_fma(E.wr, Tqr[j], -(E.wi * Tqi[j])), Ti = gl_fma(E.wr, Tqi[j], E.wi * Tqr[j]);   // dP/dt = w T'
+    // dP/df = w M / (2 (1 + f w)),  M = R_N w^N - (s Q + t P)
+    V Mr = -gl_fma(ss, Qr[j], tt * Pr), Mi = -gl_fma(ss, Qi[j], tt * Pi);
+    if (RN != S(0)) {
+      V pr = V(S(1)), pi = V(S(0)), br = E.wr, bi = E.wi;
+      for (int e = N; e > 0; e >>= 1) {
+        if (e & 1) { const V t0 = gl_fma(pr, br, -(pi * bi)); pi = gl_fma(pr, bi, pi * br); pr = t0; }
+        const V b0 = gl_fma(br, br, -(bi * bi)); bi = V(S(2)) * br * bi; br = b0;
+      }
+      Mr = gl_fma(V(RN), pr, Mr); Mi = gl_fma(V(RN), pi, Mi);
+    }
+    const V dr = zr + V(S(1)), di = zi;
+    const V inv = gl_div_fast(V(S(0.5)), gl_fma(dr, dr, di * di));
+    const V Er = gl_fma(E.wr, Mr, -(E.wi * Mi)), Ei = gl_fma(E.wr, Mi, E.wi * Mr);
+    const V Fr = gl_fma(Er, dr, Ei * di) * inv, Fi = gl_fma(Ei, dr, -(Er * di)) * inv;
     // forward values
-    V fx = gl_fma(E.Cs, Pr[j], -(E.Ss * Pi[j])), fy = gl_fma(E.Cs, Pi[j], E.Ss * Pr[j]);      // u P
+    V fx = gl_fma(E.Cs, Pr, -(E.Ss * Pi)), fy = gl_fma(E.Cs, Pi, E.Ss * Pr);      // u P
     V l2br = gl_fma(V(S(-0.5)), E.l2r2, l2b);            // log2(b/R)
     V pw = gl_exp2_fast(tm1 * l2br);
     V pref = pref0 * pw;
@@ -562,10 +602,10 @@ GL_HD void epl_bwd(const typename gl_scalar_of<V>::type* d, int ts, const V* x, 
     V gR_over_R = gl_where_in(E.R2, S(1e-20), S(1e20), -(gpwpw * tm1 * ir2), V(S(0)));   // gR / R0 (0 where R is clamped)
     // series: F = u P(w; f, t).  <g, u X> = Re(conj(g) u X) for X = dP/df, dP/dt
     V hr = gl_fma(gr, E.Cs, gi * E.Ss), hi = gl_fma(gi, E.Cs, -(gr * E.Ss));   // conj(u) g
-    g[EPLG_F] += gl_fma(hr, Fr[j], hi * Fi[j]);
-    g[EPLG_T] += gl_fma(hr, Tr[j], hi * Ti[j]);
+    g[EPLG_F] += gl_fma(hr, Fr, hi * Fi);
+    g[EPLG_T] += gl_fma(hr, Tr, hi * Ti);
     // d/d(ang): dF = i u (P + 2 w P_w) d(ang), with w P_w = f dP/df
-    V Zr = gl_fma(f2, Fr[j], Pr[j]), Zi = gl_fma(f2, Fi[j], Pi[j]);
+    V Zr = gl_fma(f2, Fr, Pr), Zi = gl_fma(f2, Fi, Pi);
     V gang = gl_fma(hi, Zr, -(hr * Zi));              // Re(conj(g) i u Z)
     // ang = atan2(yr, qx), R0 = hypot(qx, yr):  d(ang) = (qx dyr - yr dqx)/R0^2, dR0 = (qx dqx + yr dyr)/R0
     V ga = gang * ir2;
@@ -578,6 +618,34 @@ GL_HD void epl_bwd(const typename gl_scalar_of<V>::type* d, int ts, const V* x, 
     g[EPLG_CX] -= gdx;
     g[EPLG_CY] -= gdy;
   }
+}
+
+template <class V, int NP>
+GL_HD void epl_bwd(const typename gl_scalar_of<V>::type* d, int ts, const V* x, const V* y, const V* gax, const V* gay, V* g) {
+  typedef typename gl_scalar_of<V>::type S;
+  EplGeom<V> G[NP];
+  V Qr[NP], Qi[NP], Tr[NP], Ti[NP];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) epl_geom<V, S>(d, x[j], y[j], G[j]);
+  epl_series<V, NP, true>(d, ts, G, Qr, Qi, Tr, Ti);
+  epl_bwd_core<V, NP>(d, G, Qr, Qi, Tr, Ti, gax, gay, g);
+}
+
+// Adjoint from the series state epl_fwd_save parked for the same pixels.
+template <class V, int NP>
+GL_HD void epl_bwd_load(const typename gl_scalar_of<V>::type* d, int ts, const V* x, const V* y, const V* gax, const V* gay, V* g,
+                        const V* scr, int scr_stride) {
+  typedef typename gl_scalar_of<V>::type S;
+  (void)ts;
+  EplGeom<V> G[NP];
+  V Qr[NP], Qi[NP], Tr[NP], Ti[NP];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    epl_geom<V, S>(d, x[j], y[j], G[j]);
+    Qr[j] = scr[(4 * j + 0) * scr_stride]; Qi[j] = scr[(4 * j + 1) * scr_stride];
+    Tr[j] = scr[(4 * j + 2) * scr_stride]; Ti[j] = scr[(4 * j + 3) * scr_stride];
+  }
+  epl_bwd_core<V, NP>(d, G, Qr, Qi, Tr, Ti, gax, gay, g);
 }
 
 // =============================================================================================
@@ -1638,9 +1706,9 @@ GL_HD int gl_der_size(int type, int niter, int nmax) {
 
 // raw -> derived for the simple (non-scaled, non-shapelets) types
 template <class T>
-GL_HD void gl_prep(int type, unsigned flags, int niter, const T* raw, T* d, T epl_fmax) {
+GL_HD void gl_prep(int type, unsigned flags, int niter, const T* raw, T* d, T epl_fmax, T epl_tol) {
   switch (type) {
-    case GLT_EPL: epl_prep(raw, d, niter, epl_fmax); break;
+    case GLT_EPL: epl_prep(raw, d, niter, epl_fmax, epl_tol); break;
     case GLT_SHEAR: d[0] = raw[0]; d[1] = raw[1]; d[2] = T(0); d[3] = T(0); break;
     case GLT_SIE: sie_prep(raw, d); break;
     case GLT_SIS: d[0] = raw[0]; d[1] = raw[1]; d[2] = raw[2]; d[3] = T(0); break;
@@ -1676,11 +1744,14 @@ GL_HD void gl_prep_bwd(int type, unsigned flags, const T* raw, const T* d, const
 
 // deflection of one lens entry at NP points (d = derived block of the entry)
 template <class T, int NP, unsigned F>
-GL_HD void gl_lens_fwd(int type, int ts, const typename gl_scalar_of<T>::type* d, const T* x, const T* y, T* ax, T* ay) {
+GL_HD void gl_lens_fwd(int type, int ts, const typename gl_scalar_of<T>::type* d, const T* x, const T* y, T* ax, T* ay,
+                       T* scr = nullptr, int scr_stride = 0) {
 #pragma unroll
   for (int j = 0; j < NP; ++j) { ax[j] = T(0); ay[j] = T(0); }
   switch (type) {
-    case GLT_EPL: if constexpr ((F & GLF_EPL) != 0) epl_fwd<T, NP>(d, ts, x, y, ax, ay); break;
+    case GLT_EPL: if constexpr ((F & GLF_EPL) != 0) {
+      if (scr) epl_fwd_save<T, NP>(d, ts, x, y, ax, ay, scr, scr_stride); else epl_fwd<T, NP>(d, ts, x, y, ax, ay);
+    } break;
     case GLT_SHEAR: if constexpr ((F & GLF_SHEAR) != 0) shear_fwd<T, NP>(d, x, y, ax, ay); break;
     case GLT_SIE: if constexpr ((F & GLF_SIE) != 0) sie_fwd<T, NP>(d, x, y, ax, ay); break;
     case GLT_SIS: if constexpr ((F & GLF_SIS) != 0) sis_fwd<T, NP>(d, x, y, ax, ay); break;
@@ -1693,9 +1764,12 @@ GL_HD void gl_lens_fwd(int type, int ts, const typename gl_scalar_of<T>::type* d
   }
 }
 template <class T, int NP, unsigned F>
-GL_HD void gl_lens_bwd(int type, int ts, const typename gl_scalar_of<T>::type* d, const T* x, const T* y, const T* gax, const T* gay, T* g) {
+GL_HD void gl_lens_bwd(int type, int ts, const typename gl_scalar_of<T>::type* d, const T* x, const T* y, const T* gax, const T* gay, T* g,
+                       const T* scr = nullptr, int scr_stride = 0) {
   switch (type) {
-    case GLT_EPL: if constexpr ((F & GLF_EPL) != 0) epl_bwd<T, NP>(d, ts, x, y, gax, gay, g); break;
+    case GLT_EPL: if constexpr ((F & GLF_EPL) != 0) {
+      if (scr) epl_bwd_load<T, NP>(d, ts, x, y, gax, gay, g, scr, scr_stride); else epl_bwd<T, NP>(d, ts, x, y, gax, gay, g);
+    } break;
     case GLT_SHEAR: if constexpr ((F & GLF_SHEAR) != 0) shear_bwd<T, NP>(d, x, y, gax, gay, g); break;
     case GLT_SIE: if constexpr ((F & GLF_SIE) != 0) sie_bwd<T, NP>(d, x, y, gax, gay, g); break;
     case GLT_SIS: if constexpr ((F & GLF_SIS) != 0) sis_bwd<T, NP>(d, x, y, gax, gay, g); break;

@@ -42,6 +42,8 @@ struct GlProgram {
   int depth;       // number of linear light components (lstsq)
   int has_fwdmode; // some scaling-relation group is differentiated in forward mode
   int comp_mask;   // which light groups gl_pix_image adds: bit 0 lens light, bit 1 source light (simulate_* variants)
+  int scr_prof;    // lens entry whose series state the adjoint kernels carry from their forward sweep (first plain EPL), or -1
+  float epl_tol;   // EPL series: terms below this are dropped (1e-12 = the reference's constant, epl.py:37)
   GlProf prof[GL_MAX_PROF];
 };
 
@@ -87,7 +89,7 @@ GL_HD void gl_sample_prep(const GlProgram& P, const TP* params, int bs, int b, c
       T raw[GL_MAX_RAW];
       gl_gather_raw<T, TP>(pr, params, bs, b, member_factor, m, raw);
       T* dm = der + pr.der_off + m * pr.der_size;
-      gl_prep<T>(pr.type, pr.flags, pr.niter, raw, dm, epl_fmax ? T(epl_fmax[i]) : T(-1));
+      gl_prep<T>(pr.type, pr.flags, pr.niter, raw, dm, epl_fmax ? T(epl_fmax[i]) : T(-1), T(P.epl_tol));
       if (pr.n_members > 0 && pr.type == GLT_DPIE) {
         // M[j][k] = d(scale, rc, rt)_j / d(base theta_E, r_core, r_cut)_k for this member
         for (int jj = 0; jj < 3; ++jj) {
@@ -153,7 +155,8 @@ GL_HD void gl_sample_prep_bwd(const GlProgram& P, const TP* params, int bs, int 
 // ---------------------------------------------------------------------------------------------
 // beta = theta - sum_i alpha_i(theta)   (src/gigalens/tf/simulator.py:72-78)
 template <class T, int NP, unsigned F>
-GL_HD void gl_pix_beta(const GlProgram& P, const typename gl_scalar_of<T>::type* der, const T* x, const T* y, T* bx, T* by) {
+GL_HD void gl_pix_beta(const GlProgram& P, const typename gl_scalar_of<T>::type* der, const T* x, const T* y, T* bx, T* by,
+                       T* scr = nullptr, int scr_stride = 0) {
 #pragma unroll
   for (int j = 0; j < NP; ++j) { bx[j] = x[j]; by[j] = y[j]; }
   for (int i = 0; i < P.n_lens; ++i) {
@@ -161,7 +164,8 @@ GL_HD void gl_pix_beta(const GlProgram& P, const typename gl_scalar_of<T>::type*
     const int nm = pr.n_members > 0 ? pr.n_members : 1;
     for (int m = 0; m < nm; ++m) {
       T ax[NP], ay[NP];
-      gl_lens_fwd<T, NP, F>(pr.type, pr.ts, der + pr.der_off + m * pr.der_size, x, y, ax, ay);
+      // the entry that owns the series scratch (P.scr_prof) parks its series state for the adjoint
+      gl_lens_fwd<T, NP, F>(pr.type, pr.ts, der + pr.der_off + m * pr.der_size, x, y, ax, ay, (i == P.scr_prof) ? scr : (T*)nullptr, scr_stride);
 #pragma unroll
       for (int j = 0; j < NP; ++j) { bx[j] -= ax[j]; by[j] -= ay[j]; }
     }
@@ -262,7 +266,7 @@ GL_HD void gl_point_components(const GlProgram& P, const T* der, T x, T y, T bx,
 // the host harness adds it into a vector, the CUDA kernel warp-reduces it into shared memory.
 template <class T, int NP, unsigned F, class Flush>
 GL_HD void gl_pix_image_bwd(const GlProgram& P, const typename gl_scalar_of<T>::type* der, const T* x, const T* y, const T* gS,
-                            bool no_deflection, Flush& flush) {
+                            bool no_deflection, Flush& flush, T* scr = nullptr, int scr_stride = 0) {
   T bx[NP], by[NP], Gx[NP], Gy[NP];
   T Jx[3][NP], Jy[3][NP];
   bool have_jac = false;
@@ -273,7 +277,8 @@ GL_HD void gl_pix_image_bwd(const GlProgram& P, const typename gl_scalar_of<T>::
     if constexpr ((F & GLF_DPIE) != 0) {
       if (P.has_fwdmode) { gl_pix_beta_jac<T, NP, F>(P, der, x, y, bx, by, Jx, Jy); have_jac = true; }
     }
-    if (!have_jac) gl_pix_beta<T, NP, F>(P, der, x, y, bx, by);
+    if (have_jac) scr = nullptr;
+    else gl_pix_beta<T, NP, F>(P, der, x, y, bx, by, scr, scr_stride);
   }
 #pragma unroll
   for (int j = 0; j < NP; ++j) { Gx[j] = T(0); Gy[j] = T(0); }
@@ -336,7 +341,7 @@ GL_HD void gl_pix_image_bwd(const GlProgram& P, const typename gl_scalar_of<T>::
       T acc[GL_MAX_DVARS];
 #pragma unroll
       for (int k = 0; k < GL_MAX_DVARS; ++k) acc[k] = T(0);
-      gl_lens_bwd<T, NP, F>(pr.type, pr.ts, der + pr.der_off + m * pr.der_size, x, y, Gx, Gy, acc);
+      gl_lens_bwd<T, NP, F>(pr.type, pr.ts, der + pr.der_off + m * pr.der_size, x, y, Gx, Gy, acc, (i == P.scr_prof) ? scr : (const T*)nullptr, scr_stride);
       flush(acc, pr.n_dvars, pr.g_off + m * pr.n_dvars);
     }
   }

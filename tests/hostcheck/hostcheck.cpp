@@ -70,7 +70,8 @@ static int run(const gl_model_desc* m, int bs, const T* params, int npix, const 
       }
       if (g_ss && gparams) {
         T gs[1] = {g_ss[(size_t)b * npix + p]};
-        gl_pix_image_bwd<T, 1, GLF_ALL>(P, der.data(), x, y, gs, no_deflection != 0, fl);
+        T scr[GL_EPL_NSTATE];   // series state handed from the forward sweep to the adjoint, as in the kernels
+        gl_pix_image_bwd<T, 1, GLF_ALL>(P, der.data(), x, y, gs, no_deflection != 0, fl, scr, 1);
       }
     }
     if (g_ss && gparams) gl_sample_prep_bwd<T, T>(P, params, bs, b, mf, as, der.data(), g.data(), gparams);
@@ -109,7 +110,8 @@ static int run_packed(const gl_model_desc* m, int bs, const float* params, int n
       }
       if (g_ss && gparams) {
         GlF2 gs[1] = {GlF2(g_ss[(size_t)b * npix + p], g_ss[(size_t)b * npix + p + 1])};
-        gl_pix_image_bwd<GlF2, 1, F>(P, der.data(), x, y, gs, false, fl);
+        GlF2 scr[GL_EPL_NSTATE];
+        gl_pix_image_bwd<GlF2, 1, F>(P, der.data(), x, y, gs, false, fl, scr, 1);
       }
     }
     if (g_ss && gparams) gl_sample_prep_bwd<float, float>(P, params, bs, b, mf, nullptr, der.data(), g.data(), gparams);

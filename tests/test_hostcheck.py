@@ -35,6 +35,9 @@ MODELS = {
     "constants": lambda: PhysicalModel([epl.EPL(20), shear.Shear()], [], [sersic.Sersic()],
                                        lenses_constants=[{"gamma": 2.1, "center_x": 0.05}, {}],
                                        source_light_constants=[{"n_sersic": 1.5}]),
+    # strongly elliptical lens with a short iteration cap: the truncated series differs from the infinite one at the
+    # 1e-2 level, so the closed-form f-derivative needs its truncation term R_N w^N (gl_math.cuh, EPL)
+    "epl_capped": lambda: PhysicalModel([epl.EPL(12)], [], SRC(), lenses_constants=[{"e1": 0.45, "e2": -0.3}]),
     "shapelets": lambda: PhysicalModel([epl.EPL(30), shear.Shear()], [sersic.Sersic()], [shapelets.Shapelets(4, interpolate=False)]),
     "shapelets_interp": lambda: PhysicalModel([sis.SIS()], [], [shapelets.Shapelets(5, interpolate=True)]),
     "cluster": lambda: PhysicalModel([nfw.NFW(), dpie_subhalo.DPIESubhalo(1.0, _catalogue()), shear.Shear()], [], SRC()),
