@@ -22,6 +22,7 @@
 // steady state ~90% of issued instructions are FFMA (FP32-FMA bound; north_star forbids tensor
 // cores here), and HBM sees each ss pixel once per direction.
 #pragma once
+#include <cuda.h>          // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 
 #define GLC_RX 4
@@ -49,6 +50,7 @@ struct GlConvGeom {
   int tiles_x, tiles_y;
   int in_rows, in_pitch;   // smem input tile: rows = th + A - 1, pitch = roundup4(tw + A - 1)
   int wpitch;   // roundup4(A)
+  int tma_pitch;     // forward, TMA staging: row pitch of the staged tile (in_pitch + 4)
   int phase_stride;  // forward only: floats between phase sub-images (in_rows*in_pitch padded so that the
                      // de-interleaving stores of one warp fall into distinct banks)
   int rc0;      // adjoint only: first padded-phase row/column (pad / ss)
@@ -69,17 +71,28 @@ struct GlConvGeom {
 __host__ __device__ constexpr int glc_ulen(int A) { return (A + 2 * GLC_RY - 2 + 3) & ~3; }   // floats per U copy
 // taps table: [phase][b][copy(2)][ulen]
 
-template <int A, int MASK>
+// LW = floats per strip load: 4 (LDS.128, strip origin 16-byte aligned) or 2 (LDS.64, 8-byte aligned origin -- the
+// TMA-staged tile, whose first column is rounded down to the unit's 16-byte coordinate granularity).
+template <int A, int MASK, int LW>
 __device__ __forceinline__ void corr_row2(const float* __restrict__ inrow, const float* __restrict__ urow /* &U[0][copy][j0e] */,
                                           float2 (&acc2)[GLC_RP][GLC_RX]) {
   constexpr int SL = (GLC_RX + A - 1 + 3) & ~3;
   constexpr int UL = glc_ulen(A);
   float strip[SL];
-  const float4* src = reinterpret_cast<const float4*>(inrow);
+  if constexpr (LW == 4) {
+    const float4* src = reinterpret_cast<const float4*>(inrow);
 #pragma unroll
-  for (int v = 0; v < SL / 4; ++v) {
-    float4 t = src[v];
-    strip[4 * v] = t.x; strip[4 * v + 1] = t.y; strip[4 * v + 2] = t.z; strip[4 * v + 3] = t.w;
+    for (int v = 0; v < SL / 4; ++v) {
+      float4 t = src[v];
+      strip[4 * v] = t.x; strip[4 * v + 1] = t.y; strip[4 * v + 2] = t.z; strip[4 * v + 3] = t.w;
+    }
+  } else {
+    const float2* src = reinterpret_cast<const float2*>(inrow);
+#pragma unroll
+    for (int v = 0; v < SL / 2; ++v) {
+      float2 t = src[v];
+      strip[2 * v] = t.x; strip[2 * v + 1] = t.y;
+    }
   }
 #pragma unroll
   for (int b = 0; b < A; ++b) {
@@ -99,7 +112,7 @@ __device__ __forceinline__ void corr_row2(const float* __restrict__ inrow, const
 }
 
 // acc2 += correlation of the thread's strip (origin `in`) with the taps of one phase (table `u`).
-template <int A>
+template <int A, int LW = 4>
 __device__ __forceinline__ void corr_rows2(const float* __restrict__ in, int pitch, const float* __restrict__ u,
                                            float2 (&acc2)[GLC_RP][GLC_RX]) {
   constexpr int UL = glc_ulen(A);
@@ -113,17 +126,17 @@ __device__ __forceinline__ void corr_rows2(const float* __restrict__ in, int pit
     const int hi_r = row < GLC_RY - 1 ? row : GLC_RY - 1;
     const int lo_p = lo_r >> 1, hi_p = hi_r >> 1;
     const float* inrow = in + row * pitch;
-    if (lo_p == 0 && hi_p == GLC_RP - 1) corr_row2<A, (1 << GLC_RP) - 1>(inrow, up, acc2);
+    if (lo_p == 0 && hi_p == GLC_RP - 1) corr_row2<A, (1 << GLC_RP) - 1, LW>(inrow, up, acc2);
     else {
       int mask = 0;
       for (int q = lo_p; q <= hi_p; ++q) mask |= 1 << q;
       switch (mask) {
-        case 1: corr_row2<A, 1>(inrow, up, acc2); break;
-        case 2: corr_row2<A, 2>(inrow, up, acc2); break;
-        case 3: corr_row2<A, 3>(inrow, up, acc2); break;
-        case 4: corr_row2<A, 4>(inrow, up, acc2); break;
-        case 6: corr_row2<A, 6>(inrow, up, acc2); break;
-        default: corr_row2<A, 7>(inrow, up, acc2); break;
+        case 1: corr_row2<A, 1, LW>(inrow, up, acc2); break;
+        case 2: corr_row2<A, 2, LW>(inrow, up, acc2); break;
+        case 3: corr_row2<A, 3, LW>(inrow, up, acc2); break;
+        case 4: corr_row2<A, 4, LW>(inrow, up, acc2); break;
+        case 6: corr_row2<A, 6, LW>(inrow, up, acc2); break;
+        default: corr_row2<A, 7, LW>(inrow, up, acc2); break;
       }
     }
   }
@@ -137,6 +150,64 @@ struct GlLikeArgs {
   float inv_exp;            // 1 / exp_time
   int enabled;
 };
+
+// Epilogue shared by the forward kernels: x scale, image store, chi^2 / normalisation partial sums of this tile
+// and dL/d(image) (tf/model.py:91-101).
+__device__ __forceinline__ void glc_fwd_epilogue(const GlConvGeom& g, const float2 (&acc2)[GLC_RP][GLC_RX], bool active, int b, int tile,
+                                                 int ntiles, int oy0, int ox0, int ty, int tx, float scale, float* __restrict__ img,
+                                                 const GlLikeArgs& like, float* __restrict__ part, float* __restrict__ gimg,
+                                                 float (*s_red)[8]) {
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  float chi2 = 0.f, norm = 0.f;
+  if (active) {
+#pragma unroll
+    for (int r = 0; r < GLC_RY; ++r) {
+      const int oy = oy0 + ty * GLC_RY + r;
+#pragma unroll
+      for (int c = 0; c < GLC_RX; ++c) {
+        const int ox = ox0 + tx * GLC_RX + c;
+        if (oy < g.n && ox < g.n) {
+          const float v = ((r & 1) ? acc2[r >> 1][c].y : acc2[r >> 1][c].x) * scale;
+          const size_t o = (size_t)oy * g.n + ox;
+          if (img) img[(size_t)b * g.n * g.n + o] = v;
+          if (like.enabled) {
+            const float m = like.mask ? (like.mask[o] ? 1.f : 0.f) : 1.f;
+            const float res = v - like.observed[o];
+            float var, dvar;
+            if (like.error_map) { const float e = like.error_map[o]; var = e * e; dvar = 0.f; }
+            else {
+              // err = sqrt(bg^2 + I/t), var = err^2 (tf/model.py:95-98); negative => NaN like the reference
+              const float e = sqrtf(like.bg2 + v * like.inv_exp); var = e * e; dvar = like.inv_exp;
+            }
+            const float q = res / sqrtf(var);
+            chi2 += q * q * m;
+            norm += logf(6.283185307179586f * var) * m;
+            if (gimg) {
+              // d(-0.5*(chi2+norm))/dI
+              const float gi = -0.5f * m * (2.f * res / var - (res * res) / (var * var) * dvar + dvar / var);
+              gimg[(size_t)b * g.n * g.n + o] = gi;
+            }
+          }
+        }
+      }
+    }
+  }
+  if (like.enabled && part) {
+    for (int off = 16; off > 0; off >>= 1) {
+      chi2 += __shfl_xor_sync(0xffffffffu, chi2, off);
+      norm += __shfl_xor_sync(0xffffffffu, norm, off);
+    }
+    const int warp = tid >> 5, lane = tid & 31, nw = (nthr + 31) >> 5;
+    if (lane == 0) { s_red[0][warp] = chi2; s_red[1][warp] = norm; }
+    __syncthreads();
+    if (tid == 0) {
+      float c2 = 0.f, nm = 0.f;
+      for (int w2 = 0; w2 < nw; ++w2) { c2 += s_red[0][w2]; nm += s_red[1][w2]; }
+      float* p = part + ((size_t)b * ntiles + tile) * 2;
+      p[0] = c2; p[1] = nm;
+    }
+  }
+}
 
 // Forward: ss image -> pooled image (x scale), optional likelihood partial sums and dL/d(image).
 //   grid = tiles_x * tiles_y * n_images (tile fastest), block = ntx*nty threads (rounded up to a warp multiple)
@@ -229,55 +300,116 @@ __global__ void __maxnreg__(96) k_conv_fwd(GlConvGeom g, const float* __restrict
     __syncthreads();
   }
 
-  float chi2 = 0.f, norm = 0.f;
-  if (active) {
+  glc_fwd_epilogue(g, acc2, active, b, tile, ntiles, oy0, ox0, ty, tx, scale, img, like, part, gimg, s_red);
+}
+
+// ---- TMA (cp.async.bulk.tensor) + mbarrier plumbing of the forward kernel ---------------------------
+__device__ __forceinline__ unsigned glc_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void glc_mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(glc_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void glc_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(glc_smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Bounded wait (a broken pipeline must not hang the GPU): false on time-out.
+__device__ __forceinline__ bool glc_mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned a = glc_smem_u32(bar);
+  for (int spin = 0; spin < (1 << 22); ++spin) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    if (ok) return true;
+  }
+  return false;
+}
+__device__ __forceinline__ void glc_tma_load_3d(void* dst, const CUtensorMap* tmap, int c0, int c1, int c2, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(glc_smem_u32(dst)), "l"(tmap), "r"(glc_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void glc_bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(glc_smem_u32(dst)), "l"(src), "r"(bytes), "r"(glc_smem_u32(bar)) : "memory");
+}
+
+// Forward kernel with TMA staging.  The supersampled buffer is a 3-D tensor (n, n, n_images * ss^2) of phase
+// sub-images; one elected thread asks the TMA unit for the (in_pitch x in_rows) halo tile of a phase at signed
+// coordinates (ox0 - sx, oy0 - sy, b * ss^2 + q) -- the SAME zero padding is the unit's out-of-bounds fill --
+// and for the tap table (1-D bulk copy).  Completion is an mbarrier transaction count, so the other threads
+// issue nothing but FFMA2 / LDS until they wait on the barrier of the phase they need: the per-element
+// address arithmetic and bounds tests of k_conv_fwd's cp.async loader (a quarter of its instructions) are gone.
+// The unit wants the innermost coordinate on a 16-byte boundary (measured: anything else faults), so the tile
+// starts at the column rounded down to a multiple of 4 and is 4 columns wider (pitch tma_pitch); the thread
+// strips then start r = 0 or 2 floats into it and are read with LDS.64.
+// Needs n % 4 == 0 (16-byte global strides), even shifts and a tile of at most 256 x 256; otherwise k_conv_fwd runs.
+template <int A>
+__global__ void __maxnreg__(96) k_conv_fwd_tma(const __grid_constant__ CUtensorMap tmap, GlConvGeom g, const float* __restrict__ wts,
+                                               float scale, float* __restrict__ img, GlLikeArgs like,
+                                               float* __restrict__ part, float* __restrict__ gimg) {
+  extern __shared__ __align__(128) float smem[];
+  const int nph = g.ss * g.ss;
+  const int tstride = g.phase_stride;              // floats per staged tile, a multiple of 32 (128-byte TMA destinations)
+  float* s_in = smem;                              // [2][tstride]  double-buffered phase tile
+  float* s_w = smem + 2 * tstride;                 // [nph][A][2][ulen] packed tap table
+  __shared__ float s_red[2][8];
+  __shared__ __align__(8) unsigned long long s_bar[3];   // tile buffer 0 / 1 full, tap table full
+
+  const int ntiles = g.tiles_x * g.tiles_y;
+  const int b = blockIdx.x / ntiles, tile = blockIdx.x - b * ntiles;
+  const int oy0 = (tile / g.tiles_x) * g.th, ox0 = (tile % g.tiles_x) * g.tw;
+  const int tid = threadIdx.x;
+  constexpr int UTAB = A * 2 * glc_ulen(A);         // floats per phase
+  const unsigned tile_bytes = (unsigned)(g.in_rows * g.tma_pitch) * 4u;
+
+  if (tid == 0) {
+    glc_mbar_init(&s_bar[0], 1); glc_mbar_init(&s_bar[1], 1); glc_mbar_init(&s_bar[2], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // image phase (py', px') = (q / ss, q % ss): padded-phase row r holds image row r - sy, sy = (py' + pad) / ss
+  auto issue_phase = [&](int q) {
+    const int pyi = q / g.ss, pxi = q - pyi * g.ss;
+    const int sy = (pyi + g.pad) / g.ss, sx = (pxi + g.pad) / g.ss;
+    glc_mbar_expect_tx(&s_bar[q & 1], tile_bytes);
+    glc_tma_load_3d(s_in + (q & 1) * tstride, &tmap, (ox0 - sx) & ~3, oy0 - sy, b * nph + q, &s_bar[q & 1]);
+  };
+  if (tid == 0) {
+    glc_mbar_expect_tx(&s_bar[2], (unsigned)(nph * UTAB) * 4u);
+    glc_bulk_load(s_w, wts, (unsigned)(nph * UTAB) * 4u, &s_bar[2]);
+    issue_phase(0);
+    if (nph > 1) issue_phase(1);
+  }
+
+  const int ty = tid / g.tpr, tx = tid - ty * g.tpr;
+  const bool active = ty < g.nty && tx < g.ntx;
+  float2 acc2[GLC_RP][GLC_RX];
 #pragma unroll
-    for (int r = 0; r < GLC_RY; ++r) {
-      const int oy = oy0 + ty * GLC_RY + r;
+  for (int r = 0; r < GLC_RP; ++r)
 #pragma unroll
-      for (int c = 0; c < GLC_RX; ++c) {
-        const int ox = ox0 + tx * GLC_RX + c;
-        if (oy < g.n && ox < g.n) {
-          const float v = ((r & 1) ? acc2[r >> 1][c].y : acc2[r >> 1][c].x) * scale;
-          const size_t o = (size_t)oy * g.n + ox;
-          if (img) img[(size_t)b * g.n * g.n + o] = v;
-          if (like.enabled) {
-            const float m = like.mask ? (like.mask[o] ? 1.f : 0.f) : 1.f;
-            const float res = v - like.observed[o];
-            float var, dvar;
-            if (like.error_map) { const float e = like.error_map[o]; var = e * e; dvar = 0.f; }
-            else {
-              // err = sqrt(bg^2 + I/t), var = err^2 (tf/model.py:95-98); negative => NaN like the reference
-              const float e = sqrtf(like.bg2 + v * like.inv_exp); var = e * e; dvar = like.inv_exp;
-            }
-            const float q = res / sqrtf(var);
-            chi2 += q * q * m;
-            norm += logf(6.283185307179586f * var) * m;
-            if (gimg) {
-              // d(-0.5*(chi2+norm))/dI
-              const float gi = -0.5f * m * (2.f * res / var - (res * res) / (var * var) * dvar + dvar / var);
-              gimg[(size_t)b * g.n * g.n + o] = gi;
-            }
-          }
-        }
-      }
+    for (int c = 0; c < GLC_RX; ++c) acc2[r][c] = make_float2(0.f, 0.f);
+  const int origin = ty * GLC_RY * g.tma_pitch + tx * GLC_RX;
+
+  bool ok = glc_mbar_wait(&s_bar[2], 0);
+  for (int q = 0; q < nph; ++q) {
+    ok = glc_mbar_wait(&s_bar[q & 1], (unsigned)(q >> 1) & 1u) && ok;
+    if (active) {
+      // conv phase of this image phase: (py, px) = ((py' + pad) % ss, (px' + pad) % ss)
+      const int pyi = q / g.ss, pxi = q - pyi * g.ss;
+      const int ph = ((pyi + g.pad) % g.ss) * g.ss + (pxi + g.pad) % g.ss;
+      const int r = (ox0 - (pxi + g.pad) / g.ss) & 3;      // columns between the aligned tile start and the first one needed
+      corr_rows2<A, 2>(s_in + (q & 1) * tstride + origin + r, g.tma_pitch, s_w + ph * UTAB, acc2);
+    }
+    if (q + 2 < nph) {
+      __syncthreads();                    // every thread is done with this buffer
+      if (tid == 0) issue_phase(q + 2);
     }
   }
-  if (like.enabled && part) {
-    for (int off = 16; off > 0; off >>= 1) {
-      chi2 += __shfl_xor_sync(0xffffffffu, chi2, off);
-      norm += __shfl_xor_sync(0xffffffffu, norm, off);
-    }
-    const int warp = tid >> 5, lane = tid & 31, nw = (nthr + 31) >> 5;
-    if (lane == 0) { s_red[0][warp] = chi2; s_red[1][warp] = norm; }
-    __syncthreads();
-    if (tid == 0) {
-      float c2 = 0.f, nm = 0.f;
-      for (int w2 = 0; w2 < nw; ++w2) { c2 += s_red[0][w2]; nm += s_red[1][w2]; }
-      float* p = part + ((size_t)b * ntiles + tile) * 2;
-      p[0] = c2; p[1] = nm;
-    }
+  if (!ok) {                              // barrier time-out: poison the outputs instead of returning stale data
+#pragma unroll
+    for (int r = 0; r < GLC_RP; ++r)
+#pragma unroll
+      for (int c = 0; c < GLC_RX; ++c) acc2[r][c] = make_float2(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000));
   }
+  glc_fwd_epilogue(g, acc2, active, b, tile, ntiles, oy0, ox0, ty, tx, scale, img, like, part, gimg, s_red);
 }
 
 // Adjoint: dL/d(image) [bs][n][n] -> dL/d(ss image) [bs][hs][hs]  (x scale).

@@ -220,9 +220,12 @@ __global__ void k_sample_bwd(GlProgram P, int bs, const float* __restrict__ para
 // ---------------------------------------------------------------------------------------------
 #define GLK_THREADS 256
 // shared-memory layout of the adjoint ray-tracing kernels (floats): [der_total][nwarps * g_total][series scratch]
-__host__ __device__ inline int gl_scr_offset(const GlProgram& P) { return (P.der_total + (GLK_THREADS / 32) * P.g_total + 3) & ~3; }
-__host__ __device__ inline int gl_bwd_smem_floats(const GlProgram& P, int ppt) {
-  return gl_scr_offset(P) + (P.scr_prof >= 0 ? GL_EPL_NSTATE * ppt * GLK_THREADS : 0);
+//   accumulators: one row of g_total floats per warp, or (rows = true, packed kernels) g_total float2 rows of one entry per thread
+__host__ __device__ inline int gl_scr_offset(const GlProgram& P, bool rows = false) {
+  return (P.der_total + (rows ? 2 * GLK_THREADS : GLK_THREADS / 32) * P.g_total + 3) & ~3;
+}
+__host__ __device__ inline int gl_bwd_smem_floats(const GlProgram& P, int ppt, bool rows = false) {
+  return gl_scr_offset(P, rows) + (P.scr_prof >= 0 ? GL_EPL_NSTATE * ppt * GLK_THREADS : 0);
 }
 
 template <int PPT, unsigned F>
@@ -418,7 +421,24 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_fwd_p(GlProgram P, int
   }
 }
 
-template <int PPT, unsigned F>
+// Per-thread accumulator rows in shared memory: rows[k][thread] (float2 = the two packed lanes), one
+// LDS.64 + FADD2 + STS.64 per dvar and pixel batch instead of the lane fold + warp butterfly of
+// DevFlush; the rows are summed once, in fixed order, when the CTA has walked all its batches.
+// Needs g_total * 2 KB of shared memory, so the host picks it only for programs with few dvars.
+struct DevFlushRows {
+  float2* row;   // &rows[0][thread]
+  __device__ __forceinline__ void operator()(const GlF2* acc2, int n, int off) {
+#pragma unroll
+    for (int k = 0; k < GL_MAX_DVARS; ++k) {
+      if (k < n) {
+        float2* p = row + (size_t)(off + k) * GLK_THREADS;
+        *p = __fadd2_rn(*p, make_float2(acc2[k].x, acc2[k].y));
+      }
+    }
+  }
+};
+
+template <int PPT, unsigned F, bool ROWS>
 __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_bwd_p(GlProgram P, int npix, const float* __restrict__ grid_x,
                                                                 const float* __restrict__ grid_y,
                                                                 const unsigned char* __restrict__ ss_mask,
@@ -427,43 +447,61 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_bwd_p(GlProgram P, int
                                                                 const int* __restrict__ nan_count) {
   extern __shared__ __align__(16) float smem[];
   float* s_der = smem;
-  float* s_acc = smem + P.der_total;
+  float* s_acc = smem + P.der_total;   // ROWS: [g_total][threads] float2, else [nwarps][g_total]
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = GLK_THREADS / 32;
   const float* dsrc = derived + (size_t)b * P.der_total;
   for (int i = threadIdx.x; i < P.der_total; i += blockDim.x) s_der[i] = dsrc[i];
-  for (int i = threadIdx.x; i < nw * P.g_total; i += blockDim.x) s_acc[i] = 0.f;
+  const int nacc = ROWS ? 2 * GLK_THREADS * P.g_total : nw * P.g_total;
+  for (int i = threadIdx.x; i < nacc; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
-  DevFlush flush{s_acc + warp * P.g_total, lane};
   constexpr int NV = PPT / 2;
-  GlF2* scr = (P.scr_prof >= 0) ? reinterpret_cast<GlF2*>(smem + gl_scr_offset(P)) + threadIdx.x : nullptr;   // [GL_EPL_NSTATE * NV][threads]
+  GlF2* scr = (P.scr_prof >= 0) ? reinterpret_cast<GlF2*>(smem + gl_scr_offset(P, ROWS)) + threadIdx.x : nullptr;   // [GL_EPL_NSTATE * NV][threads]
   const int npair = npix >> 1;
   const int per_batch = GLK_THREADS * NV;
   const int nbatch = (npair + per_batch - 1) / per_batch;
   const float2* gsrc = reinterpret_cast<const float2*>(gss + (size_t)b * npix);
   const float2* gx2 = reinterpret_cast<const float2*>(grid_x);
   const float2* gy2 = reinterpret_cast<const float2*>(grid_y);
-  for (int batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
-    GlF2 x[NV], y[NV], gs[NV];
+  auto sweep = [&](auto& flush) {
+    for (int batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
+      GlF2 x[NV], y[NV], gs[NV];
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const int pr = batch * per_batch + j * GLK_THREADS + threadIdx.x;
-      const bool in = pr < npair;
-      const int p = in ? pr : 0;
-      const float2 a = __ldg(gx2 + p), c = __ldg(gy2 + p);
-      x[j] = GlF2(a.x, a.y); y[j] = GlF2(c.x, c.y);
-      float2 gv = in ? __ldg(gsrc + p) : make_float2(0.f, 0.f);
-      if (ss_mask && in) { if (!ss_mask[2 * p]) gv.x = 0.f; if (!ss_mask[2 * p + 1]) gv.y = 0.f; }
-      gs[j] = GlF2(gv.x, gv.y);
+      for (int j = 0; j < NV; ++j) {
+        const int pr = batch * per_batch + j * GLK_THREADS + threadIdx.x;
+        const bool in = pr < npair;
+        const int p = in ? pr : 0;
+        const float2 a = __ldg(gx2 + p), c = __ldg(gy2 + p);
+        x[j] = GlF2(a.x, a.y); y[j] = GlF2(c.x, c.y);
+        float2 gv = in ? __ldg(gsrc + p) : make_float2(0.f, 0.f);
+        if (ss_mask && in) { if (!ss_mask[2 * p]) gv.x = 0.f; if (!ss_mask[2 * p + 1]) gv.y = 0.f; }
+        gs[j] = GlF2(gv.x, gv.y);
+      }
+      gl_pix_image_bwd<GlF2, NV, F>(P, s_der, x, y, gs, no_deflection != 0, flush, scr, GLK_THREADS);
     }
-    gl_pix_image_bwd<GlF2, NV, F>(P, s_der, x, y, gs, no_deflection != 0, flush, scr, GLK_THREADS);
-  }
-  __syncthreads();
+  };
   float* out = gpart + ((size_t)b * gridDim.x + blockIdx.x) * P.g_total;
-  for (int k = threadIdx.x; k < P.g_total; k += blockDim.x) {
-    float s2 = 0.f;
-    for (int w = 0; w < nw; ++w) s2 += s_acc[w * P.g_total + k];
-    out[k] = s2;
+  if constexpr (ROWS) {
+    DevFlushRows flush{reinterpret_cast<float2*>(s_acc) + threadIdx.x};
+    sweep(flush);
+    __syncthreads();
+    const float2* rows = reinterpret_cast<const float2*>(s_acc);
+    for (int k = warp; k < P.g_total; k += nw) {
+      float s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < GLK_THREADS / 32; ++i) { const float2 v = rows[(size_t)k * GLK_THREADS + i * 32 + lane]; s2 += v.x + v.y; }
+      for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      if (lane == 0) out[k] = s2;
+    }
+  } else {
+    DevFlush flush{s_acc + warp * P.g_total, lane};
+    sweep(flush);
+    __syncthreads();
+    for (int k = threadIdx.x; k < P.g_total; k += blockDim.x) {
+      float s2 = 0.f;
+      for (int w = 0; w < nw; ++w) s2 += s_acc[w * P.g_total + k];
+      out[k] = s2;
+    }
   }
 }
 
@@ -512,6 +550,7 @@ struct gl_plan {
   bool has_epl = false;
   int feat_idx = 3;
   int epl_batch_max = 0;
+  int row_flush = 0;         // packed adjoint kernels: per-thread accumulator rows in shared memory (0 = warp butterfly, for A/B)
   // static inputs
   float* d_grid_x = nullptr; float* d_grid_y = nullptr;
   unsigned char* d_ss_mask = nullptr; unsigned char* d_mask = nullptr;
@@ -532,7 +571,10 @@ struct gl_plan {
   int A = 1, pad = 0;
   GlConvGeom gf, gb;
   int bwd_rc_start = 0;
-  size_t smem_cf = 0, smem_cb = 0;
+  size_t smem_cf = 0, smem_cb = 0, smem_cf_tma = 0;
+  bool conv_tma_ok = false;  // geometry admits the TMA-staged forward kernel
+  int conv_tma = 1;          // stage the forward conv tiles with TMA (cp.async.bulk.tensor); 0 = cp.async loader (A/B)
+  CUtensorMap tmap_f; const float* tmap_f_base = nullptr; int tmap_f_nimg = -1; bool tmap_f_ok = false;
   int conv_threads_f = 0, conv_threads_b = 0;
   // likelihood
   bool has_like = false;
@@ -687,6 +729,7 @@ int gl_plan_create(const gl_model_desc* model, const gl_sim_config* sim, int32_t
 
   gl_plan* p = new gl_plan();
   p->device = device; p->bs = bs; p->prog = built.prog;
+  p->prog.epl_tol = 1e-9f;   // see "epl_tol_exp10" in include/gigalens_b200.h
   p->n = sim->num_pix; p->ss = sim->supersample; p->hs = p->n * p->ss; p->npix = p->hs * p->hs;
   p->conversion_factor = sim->conversion_factor;
   for (int i = 0; i < p->prog.n_lens; ++i) if (p->prog.prof[i].type == GLT_EPL) p->has_epl = true;
@@ -790,7 +833,11 @@ int gl_plan_create(const gl_model_desc* model, const gl_sim_config* sim, int32_t
     p->gb.rc0 = p->bwd_rc_start;
     p->conv_threads_f = ((p->gf.tpr * p->gf.nty + 31) / 32) * 32;
     p->conv_threads_b = ((p->gb.tpr * p->gb.nty + 31) / 32) * 32;
-    p->gf.phase_stride = p->gf.in_rows * p->gf.in_pitch;
+    p->gf.tma_pitch = p->gf.in_pitch + 4;
+    p->gf.phase_stride = (p->gf.in_rows * p->gf.tma_pitch + 31) & ~31;   // TMA destinations are 128-byte aligned
+    p->conv_tma_ok = (p->n % 4) == 0 && p->gf.tma_pitch <= 256 && p->gf.in_rows <= 256;
+    for (int px = 0; px < ss; ++px) if (((px + p->pad) / ss) & 1) p->conv_tma_ok = false;   // strips must stay 8-byte aligned
+    p->smem_cf_tma = (size_t)(2 * p->gf.phase_stride + nph * UTAB) * sizeof(float);
     p->smem_cf = (size_t)(2 * p->gf.in_rows * p->gf.in_pitch + nph * UTAB) * sizeof(float);
     p->smem_cb = (size_t)(p->gb.in_rows * p->gb.in_pitch + nph * UTAB) * sizeof(float);
   }
@@ -827,6 +874,8 @@ int gl_plan_create(const gl_model_desc* model, const gl_sim_config* sim, int32_t
 int gl_plan_set_option(gl_plan* p, const char* name, int32_t value) {
   if (!p || !name) return gl_fail("gl_plan_set_option: NULL argument");
   if (!strcmp(name, "epl_batch_max")) { p->epl_batch_max = value; return 0; }
+  if (!strcmp(name, "row_flush")) { p->row_flush = value; return 0; }
+  if (!strcmp(name, "conv_tma")) { p->conv_tma = value; return 0; }
   if (!strcmp(name, "epl_tol_exp10")) {   // EPL series terms below 10^-value are dropped (12 = the reference's constant, epl.py:37)
     if (value < 6 || value > 30) return gl_fail("gl_plan_set_option: epl_tol_exp10 must be in [6, 30]");
     p->prog.epl_tol = powf(10.f, -(float)value); return 0;
@@ -1023,15 +1072,18 @@ static int gl_run_raytrace_bwd(gl_plan* p, float* gss, int no_deflection, cudaSt
   }
   const size_t smem = (size_t)gl_bwd_smem_floats(p->prog, 4) * sizeof(float);
   if ((p->feat_idx == 0 || p->feat_idx == 2) && (p->npix % 2) == 0 && p->use_packed) {
-    if (p->feat_idx == 0) {
-      if (smem > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_bwd_p<4, GL_FS0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_raytrace_bwd_p<4, GL_FS0><<<grid, GLK_THREADS, smem, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,
-                                                                   p->d_derived, no_deflection, gss, p->d_gpart, p->d_nan);
-    } else {
-      if (smem > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_bwd_p<4, GL_FS2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_raytrace_bwd_p<4, GL_FS2><<<grid, GLK_THREADS, smem, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,
-                                                                   p->d_derived, no_deflection, gss, p->d_gpart, p->d_nan);
+    // per-thread accumulator rows when two CTAs of them still fit one SM
+    const size_t smem_rows = (size_t)gl_bwd_smem_floats(p->prog, 4, true) * sizeof(float);
+    const bool rows = p->row_flush && smem_rows <= 108 * 1024;
+#define GL_BWD_P(FS, ROWS, SM)                                                                                              \
+    {                                                                                                                       \
+      if ((SM) > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_bwd_p<4, FS, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM))); \
+      k_raytrace_bwd_p<4, FS, ROWS><<<grid, GLK_THREADS, (SM), st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,        \
+                                                                   p->d_derived, no_deflection, gss, p->d_gpart, p->d_nan); \
     }
+    if (p->feat_idx == 0) { if (rows) GL_BWD_P(GL_FS0, true, smem_rows) else GL_BWD_P(GL_FS0, false, smem) }
+    else { if (rows) GL_BWD_P(GL_FS2, true, smem_rows) else GL_BWD_P(GL_FS2, false, smem) }
+#undef GL_BWD_P
     GL_LAUNCH_CHECK("k_raytrace_bwd_p");
     return 0;
   }
@@ -1044,14 +1096,57 @@ static int gl_run_raytrace_bwd(gl_plan* p, float* gss, int no_deflection, cudaSt
   return 0;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry-point query (no link against libcuda)
+typedef CUresult (*gl_tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static gl_tmap_encode_fn gl_tmap_encoder() {
+  static gl_tmap_encode_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (gl_tmap_encode_fn)f;
+  }
+  return fn;
+}
+// 3-D fp32 tensor map (n, n, nimg) over contiguous n x n images, box (box_w, box_h, 1), zero fill outside
+static bool gl_make_image_tmap(CUtensorMap* tm, const float* base, int n, size_t nimg, int box_w, int box_h) {
+  gl_tmap_encode_fn enc = gl_tmap_encoder();
+  if (!enc) return false;
+  const cuuint64_t gdim[3] = {(cuuint64_t)n, (cuuint64_t)n, (cuuint64_t)nimg};
+  const cuuint64_t gstr[2] = {(cuuint64_t)n * 4, (cuuint64_t)n * n * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int A>
 static int gl_launch_conv_fwd_A(gl_plan* p, const float* ss, float scale, float* img, bool like, float* gimg, cudaStream_t st, int nimg) {
-  if (p->smem_cf > 48 * 1024)
-    GL_CUDA(cudaFuncSetAttribute(k_conv_fwd<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cf));
   GlLikeArgs la{};
   la.enabled = like ? 1 : 0;
   if (like) { la.observed = p->d_obs; la.error_map = p->d_err; la.mask = p->d_mask; la.bg2 = p->bg2; la.inv_exp = p->inv_exp; }
   dim3 grid((unsigned)(p->gf.tiles_x * p->gf.tiles_y) * (unsigned)nimg);
+  const int nph = p->ss * p->ss;
+  if (p->conv_tma && p->conv_tma_ok && ((uintptr_t)ss % 16) == 0) {
+    if (p->tmap_f_base != ss || p->tmap_f_nimg != nimg) {   // the map depends on the source buffer only
+      p->tmap_f_ok = gl_make_image_tmap(&p->tmap_f, ss, p->n, (size_t)nimg * nph, p->gf.tma_pitch, p->gf.in_rows);
+      p->tmap_f_base = ss; p->tmap_f_nimg = nimg;
+    }
+    if (p->tmap_f_ok) {
+      if (p->smem_cf_tma > 48 * 1024)
+        GL_CUDA(cudaFuncSetAttribute(k_conv_fwd_tma<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cf_tma));
+      k_conv_fwd_tma<A><<<grid, p->conv_threads_f, p->smem_cf_tma, st>>>(p->tmap_f, p->gf, p->d_wf, scale, img, la,
+                                                                        like ? p->d_like_part : nullptr, gimg);
+      GL_LAUNCH_CHECK("k_conv_fwd_tma");
+      return 0;
+    }
+  }
+  if (p->smem_cf > 48 * 1024)
+    GL_CUDA(cudaFuncSetAttribute(k_conv_fwd<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cf));
   k_conv_fwd<A><<<grid, p->conv_threads_f, p->smem_cf, st>>>(p->gf, ss, p->d_wf, scale, img, la, like ? p->d_like_part : nullptr, gimg);
   GL_LAUNCH_CHECK("k_conv_fwd");
   return 0;

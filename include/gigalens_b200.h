@@ -130,6 +130,12 @@ int gl_plan_set_positions(gl_plan* plan, int32_t n_systems, const int32_t* n_ima
                           const float* err_x, const float* err_y);
 /* Options.  "epl_batch_max" = 1: EPL series length from the batch maximum of f exactly like
  * tf/profiles/mass/epl.py:37 (default 0: per-sample length, identical to fp32 rounding).
+ * "epl_tol_exp10" = k: the EPL series stops at terms below 10^-k.  The reference's constant is 1e-12
+ * (epl.py:37, k = 12) although its sums are fp32; the default here is k = 9: a dropped tail is below
+ * 2e-9 of the O(1) sum (1/30 ulp), and the terms the reference adds beyond that are absorbed by its
+ * own fp32 additions.  k = 12 with "epl_batch_max" = 1 reproduces the reference's trip count exactly.
+ * "row_flush" = 0: the packed adjoint kernels reduce dvar cotangents with the warp butterfly instead
+ * of per-thread shared-memory rows (A/B measurement aid; results agree to fp32 summation order).
  * "no_deflection" = 1: evaluate source light at the image-plane position (simulate(..., no_deflection=True),
  * tf/simulator.py:125-126).  "components" = 1 | 2 | 3: gl_simulate adds only the lens light / only the
  * source light / both (simulate_lens_light, simulate_images, simulate_source: tf/simulator.py:242-328).
