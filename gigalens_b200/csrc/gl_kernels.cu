@@ -575,6 +575,8 @@ struct gl_plan {
   bool conv_tma_ok = false;  // geometry admits the TMA-staged forward kernel
   int conv_tma = 1;          // stage the forward conv tiles with TMA (cp.async.bulk.tensor); 0 = cp.async loader (A/B)
   CUtensorMap tmap_f; const float* tmap_f_base = nullptr; int tmap_f_nimg = -1; bool tmap_f_ok = false;
+  bool conv_tma_b_ok = false; size_t smem_cb_tma = 0;   // same for the adjoint (TMA load of dL/d(image), TMA store of dL/d(ss))
+  CUtensorMap tmap_bi, tmap_bo; const float* tmap_bi_base = nullptr; const float* tmap_bo_base = nullptr; int tmap_b_nimg = -1; bool tmap_b_ok = false;
   int conv_threads_f = 0, conv_threads_b = 0;
   // likelihood
   bool has_like = false;
@@ -840,6 +842,16 @@ int gl_plan_create(const gl_model_desc* model, const gl_sim_config* sim, int32_t
     p->smem_cf_tma = (size_t)(2 * p->gf.phase_stride + nph * UTAB) * sizeof(float);
     p->smem_cf = (size_t)(2 * p->gf.in_rows * p->gf.in_pitch + nph * UTAB) * sizeof(float);
     p->smem_cb = (size_t)(p->gb.in_rows * p->gb.in_pitch + nph * UTAB) * sizeof(float);
+    p->gb.tma_pitch = p->gb.in_pitch + 4;
+    p->gb.phase_stride = (p->gb.in_rows * p->gb.tma_pitch + 31) & ~31;
+    p->gb.out_stride = (p->gb.tw * p->gb.th + 31) & ~31;
+    p->smem_cb_tma = (size_t)(p->gb.phase_stride + p->gb.out_stride + nph * UTAB) * sizeof(float);
+    p->conv_tma_b_ok = (p->n % 4) == 0 && p->gb.tma_pitch <= 256 && p->gb.in_rows <= 256 && p->gb.th <= 256 && (p->gb.rc0 & 1) == 0;
+    for (int px = 0; px < ss; ++px) {   // output tile origins rc0 + dx(px) + k * tw on 16-byte boundaries
+      const int fx = px - p->pad;
+      const int dx = (fx >= 0) ? fx / ss : -((-fx + ss - 1) / ss);
+      if ((p->gb.rc0 + dx) & 3) p->conv_tma_b_ok = false;
+    }
   }
 
   // chunks per sample for the ray-tracing kernels: enough CTAs for ~4 waves, at most one per pixel batch
@@ -1153,9 +1165,24 @@ static int gl_launch_conv_fwd_A(gl_plan* p, const float* ss, float scale, float*
 }
 template <int A>
 static int gl_launch_conv_bwd_A(gl_plan* p, const float* gimg, float scale, float* gss, cudaStream_t st, int nimg) {
+  dim3 grid((unsigned)(p->gb.tiles_x * p->gb.tiles_y) * (unsigned)nimg);
+  const int nph = p->ss * p->ss;
+  if (p->conv_tma && p->conv_tma_b_ok && ((A - 1) & 1) == 0 && ((uintptr_t)gimg % 16) == 0 && ((uintptr_t)gss % 16) == 0) {
+    if (p->tmap_bi_base != gimg || p->tmap_bo_base != gss || p->tmap_b_nimg != nimg) {
+      p->tmap_b_ok = gl_make_image_tmap(&p->tmap_bi, gimg, p->n, (size_t)nimg, p->gb.tma_pitch, p->gb.in_rows) &&
+                     gl_make_image_tmap(&p->tmap_bo, gss, p->n, (size_t)nimg * nph, p->gb.tw, p->gb.th);
+      p->tmap_bi_base = gimg; p->tmap_bo_base = gss; p->tmap_b_nimg = nimg;
+    }
+    if (p->tmap_b_ok) {
+      if (p->smem_cb_tma > 48 * 1024)
+        GL_CUDA(cudaFuncSetAttribute(k_conv_bwd_tma<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cb_tma));
+      k_conv_bwd_tma<A><<<grid, p->conv_threads_b, p->smem_cb_tma, st>>>(p->tmap_bi, p->tmap_bo, p->gb, p->d_wb, scale);
+      GL_LAUNCH_CHECK("k_conv_bwd_tma");
+      return 0;
+    }
+  }
   if (p->smem_cb > 48 * 1024)
     GL_CUDA(cudaFuncSetAttribute(k_conv_bwd<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cb));
-  dim3 grid((unsigned)(p->gb.tiles_x * p->gb.tiles_y) * (unsigned)nimg);
   k_conv_bwd<A><<<grid, p->conv_threads_b, p->smem_cb, st>>>(p->gb, gimg, p->d_wb, scale, nullptr, gss);
   GL_LAUNCH_CHECK("k_conv_bwd");
   return 0;
