@@ -271,7 +271,7 @@ def kernel_roofline(sim, stage_ms, step_ms, d):
     # algorithmic HBM bytes per eval of each kernel: N = ss pixels, P = pixels
     P = sim.numPix ** 2
     alg_bytes = {"k_raytrace_fwd": 4 * npix, "k_conv_fwd": 4 * npix + 8 * P, "k_conv_bwd": 4 * P + 4 * npix,
-                 "k_raytrace_bwd": 4 * npix + 4 * 196}.get(name, 4 * npix)
+                 "k_raytrace_bwd": 4 * npix + 4 * 144}.get(name, 4 * npix)
     # nominal flops per eval (hand count, FMA = 2): profile fwd 8.0 M, profile bwd 16 M, conv 4.87 M each way
     alg_flops = {"k_raytrace_fwd": 8.0e6, "k_conv_fwd": 4.87e6, "k_conv_bwd": 4.87e6, "k_raytrace_bwd": 16.0e6}.get(name, 0.0)
     ms = stage_ms[dom]
@@ -282,8 +282,11 @@ def kernel_roofline(sim, stage_ms, step_ms, d):
     traffic, ncu_pipe = None, None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["kernels"]
-        key = name + ("_p" if name.startswith("k_raytrace") else "")
-        rec = tr.get(key, tr.get(name, {}))
+        rec = {}
+        for key in (name + "_p", name + "_tma", name):   # kernel variants the C2 plan launches
+            if key in tr:
+                rec = tr[key]
+                break
         traffic = rec.get("traffic_bytes")
         if "pipe_fma_pct" in rec:   # from the committed ncu --set full capture of the same kernel (profiles/)
             ncu_pipe = {"sm__pipe_fma_cycles_active_pct": rec["pipe_fma_pct"], "smsp__issue_active_pct": rec["issue_active_pct"]}
@@ -299,7 +302,9 @@ def kernel_roofline(sim, stage_ms, step_ms, d):
                              "The kernel is FP32-issue bound, not HBM bound (DESIGN.md 3.1): see roofline_fp32"},
         "fp32": {"bound": "fp32_fma", "kernel": name, "achieved": alg_flops * bs / (ms * 1e-3) / 1e12, "peak": fp32_peak,
                  "unit": "TFLOP/s", "frac": alg_flops * bs / (ms * 1e-3) / 1e12 / fp32_peak,
-                 "note": "nominal hand-counted flops/eval (FMA=2) of the same kernel; peak = 148 SM x 128 lanes x 2 x max SM clock (derived, not measured)",
+                 "note": "SURVEY 8d's nominal flops/eval (FMA=2) of the REFERENCE algorithm for this kernel; the kernel itself executes fewer "
+                         "(closed-form EPL f-derivative, series state reused from the forward sweep), so this is a rate of useful work -- "
+                         "the pipe occupancy actually measured is `ncu`.  peak = 148 SM x 128 lanes x 2 x max SM clock (derived, not measured)",
                  "ncu": ncu_pipe,
                  "whole_step": {"achieved": 34e6 * bs / (step_ms * 1e-3) / 1e12, "frac": 34e6 * bs / (step_ms * 1e-3) / 1e12 / fp32_peak,
                                 "flops_per_eval": 34e6}},

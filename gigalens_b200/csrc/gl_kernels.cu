@@ -220,9 +220,9 @@ __global__ void k_sample_bwd(GlProgram P, int bs, const float* __restrict__ para
 // ---------------------------------------------------------------------------------------------
 #define GLK_THREADS 256
 // shared-memory layout of the adjoint ray-tracing kernels (floats): [der_total][nwarps * g_total][series scratch]
-//   accumulators: one row of g_total floats per warp, or (rows = true, packed kernels) g_total float2 rows of one entry per thread
+//   accumulators: one row of g_total floats per warp, or (rows = true, packed kernels) a g_total x 33 staging tile per warp
 __host__ __device__ inline int gl_scr_offset(const GlProgram& P, bool rows = false) {
-  return (P.der_total + (rows ? 2 * GLK_THREADS : GLK_THREADS / 32) * P.g_total + 3) & ~3;
+  return (P.der_total + (rows ? 33 : 1) * (GLK_THREADS / 32) * P.g_total + 3) & ~3;
 }
 __host__ __device__ inline int gl_bwd_smem_floats(const GlProgram& P, int ppt, bool rows = false) {
   return gl_scr_offset(P, rows) + (P.scr_prof >= 0 ? GL_EPL_NSTATE * ppt * GLK_THREADS : 0);
@@ -421,20 +421,17 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_fwd_p(GlProgram P, int
   }
 }
 
-// Per-thread accumulator rows in shared memory: rows[k][thread] (float2 = the two packed lanes), one
-// LDS.64 + FADD2 + STS.64 per dvar and pixel batch instead of the lane fold + warp butterfly of
-// DevFlush; the rows are summed once, in fixed order, when the CTA has walked all its batches.
-// Needs g_total * 2 KB of shared memory, so the host picks it only for programs with few dvars.
-struct DevFlushRows {
-  float2* row;   // &rows[0][thread]
+// Staged flush: every lane parks its (lane-folded) partial cotangents in the warp's staging tile
+// stage[dvar][lane] (pitch 33: conflict-free both ways); once per pixel batch lane k sums row k -- 32 LDS + 32 FADD
+// for ALL dvars of the program instead of one 9-shuffle butterfly (with its selects) per profile -- and keeps the
+// running total of dvar k in a register.  Needs nwarps * g_total * 33 floats of shared memory and g_total <= 64.
+#define GLK_STAGE_PITCH 33
+struct DevFlushStage {
+  float* stage;   // &stage[0][lane] of this warp
   __device__ __forceinline__ void operator()(const GlF2* acc2, int n, int off) {
 #pragma unroll
-    for (int k = 0; k < GL_MAX_DVARS; ++k) {
-      if (k < n) {
-        float2* p = row + (size_t)(off + k) * GLK_THREADS;
-        *p = __fadd2_rn(*p, make_float2(acc2[k].x, acc2[k].y));
-      }
-    }
+    for (int k = 0; k < GL_MAX_DVARS; ++k)
+      if (k < n) stage[(off + k) * GLK_STAGE_PITCH] = acc2[k].x + acc2[k].y;
   }
 };
 
@@ -447,12 +444,12 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_bwd_p(GlProgram P, int
                                                                 const int* __restrict__ nan_count) {
   extern __shared__ __align__(16) float smem[];
   float* s_der = smem;
-  float* s_acc = smem + P.der_total;   // ROWS: [g_total][threads] float2, else [nwarps][g_total]
+  float* s_acc = smem + P.der_total;   // ROWS: staging tiles [nwarps][g_total][33], else accumulator rows [nwarps][g_total]
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = GLK_THREADS / 32;
   const float* dsrc = derived + (size_t)b * P.der_total;
   for (int i = threadIdx.x; i < P.der_total; i += blockDim.x) s_der[i] = dsrc[i];
-  const int nacc = ROWS ? 2 * GLK_THREADS * P.g_total : nw * P.g_total;
+  const int nacc = ROWS ? nw * P.g_total * GLK_STAGE_PITCH : nw * P.g_total;
   for (int i = threadIdx.x; i < nacc; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
   constexpr int NV = PPT / 2;
@@ -463,7 +460,7 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_bwd_p(GlProgram P, int
   const float2* gsrc = reinterpret_cast<const float2*>(gss + (size_t)b * npix);
   const float2* gx2 = reinterpret_cast<const float2*>(grid_x);
   const float2* gy2 = reinterpret_cast<const float2*>(grid_y);
-  auto sweep = [&](auto& flush) {
+  auto sweep = [&](auto& flush, auto&& after_batch) {
     for (int batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
       GlF2 x[NV], y[NV], gs[NV];
 #pragma unroll
@@ -478,30 +475,40 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_bwd_p(GlProgram P, int
         gs[j] = GlF2(gv.x, gv.y);
       }
       gl_pix_image_bwd<GlF2, NV, F>(P, s_der, x, y, gs, no_deflection != 0, flush, scr, GLK_THREADS);
+      after_batch();
     }
   };
   float* out = gpart + ((size_t)b * gridDim.x + blockIdx.x) * P.g_total;
   if constexpr (ROWS) {
-    DevFlushRows flush{reinterpret_cast<float2*>(s_acc) + threadIdx.x};
-    sweep(flush);
-    __syncthreads();
-    const float2* rows = reinterpret_cast<const float2*>(s_acc);
-    for (int k = warp; k < P.g_total; k += nw) {
-      float s2 = 0.f;
+    float* stage = s_acc + warp * P.g_total * GLK_STAGE_PITCH;
+    DevFlushStage flush{stage + lane};
+    float tot0 = 0.f, tot1 = 0.f;          // running totals of dvars lane and lane + 32
+    auto row_sum = [&](int k) {
+      const float* r = stage + k * GLK_STAGE_PITCH;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-      for (int i = 0; i < GLK_THREADS / 32; ++i) { const float2 v = rows[(size_t)k * GLK_THREADS + i * 32 + lane]; s2 += v.x + v.y; }
-      for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-      if (lane == 0) out[k] = s2;
-    }
+      for (int i = 0; i < 32; i += 4) { s0 += r[i]; s1 += r[i + 1]; s2 += r[i + 2]; s3 += r[i + 3]; }
+      return (s0 + s1) + (s2 + s3);
+    };
+    sweep(flush, [&]() {
+      __syncwarp();
+      if (lane < P.g_total) tot0 += row_sum(lane);
+      if (lane + 32 < P.g_total) tot1 += row_sum(lane + 32);
+      __syncwarp();
+    });
+    __syncthreads();
+    if (lane < P.g_total) s_acc[warp * P.g_total + lane] = tot0;          // reuse the head of the staging area: [nwarps][g_total]
+    if (lane + 32 < P.g_total) s_acc[warp * P.g_total + lane + 32] = tot1;
+    __syncthreads();
   } else {
     DevFlush flush{s_acc + warp * P.g_total, lane};
-    sweep(flush);
+    sweep(flush, []() {});
     __syncthreads();
-    for (int k = threadIdx.x; k < P.g_total; k += blockDim.x) {
-      float s2 = 0.f;
-      for (int w = 0; w < nw; ++w) s2 += s_acc[w * P.g_total + k];
-      out[k] = s2;
-    }
+  }
+  for (int k = threadIdx.x; k < P.g_total; k += blockDim.x) {
+    float s2 = 0.f;
+    for (int w = 0; w < nw; ++w) s2 += s_acc[w * P.g_total + k];
+    out[k] = s2;
   }
 }
 
@@ -550,7 +557,7 @@ struct gl_plan {
   bool has_epl = false;
   int feat_idx = 3;
   int epl_batch_max = 0;
-  int row_flush = 0;         // packed adjoint kernels: per-thread accumulator rows in shared memory (0 = warp butterfly, for A/B)
+  int row_flush = 1;         // packed adjoint kernels: staged shared-memory flush (0 = warp butterfly per profile, for A/B)
   // static inputs
   float* d_grid_x = nullptr; float* d_grid_y = nullptr;
   unsigned char* d_ss_mask = nullptr; unsigned char* d_mask = nullptr;
@@ -1084,9 +1091,9 @@ static int gl_run_raytrace_bwd(gl_plan* p, float* gss, int no_deflection, cudaSt
   }
   const size_t smem = (size_t)gl_bwd_smem_floats(p->prog, 4) * sizeof(float);
   if ((p->feat_idx == 0 || p->feat_idx == 2) && (p->npix % 2) == 0 && p->use_packed) {
-    // per-thread accumulator rows when two CTAs of them still fit one SM
+    // staged flush (DevFlushStage) when two CTAs of it still fit one SM
     const size_t smem_rows = (size_t)gl_bwd_smem_floats(p->prog, 4, true) * sizeof(float);
-    const bool rows = p->row_flush && smem_rows <= 108 * 1024;
+    const bool rows = p->row_flush && smem_rows <= 108 * 1024 && p->prog.g_total <= 64;
 #define GL_BWD_P(FS, ROWS, SM)                                                                                              \
     {                                                                                                                       \
       if ((SM) > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_bwd_p<4, FS, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM))); \

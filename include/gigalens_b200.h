@@ -134,8 +134,10 @@ int gl_plan_set_positions(gl_plan* plan, int32_t n_systems, const int32_t* n_ima
  * (epl.py:37, k = 12) although its sums are fp32; the default here is k = 9: a dropped tail is below
  * 2e-9 of the O(1) sum (1/30 ulp), and the terms the reference adds beyond that are absorbed by its
  * own fp32 additions.  k = 12 with "epl_batch_max" = 1 reproduces the reference's trip count exactly.
- * "row_flush" = 0: the packed adjoint kernels reduce dvar cotangents with the warp butterfly instead
- * of per-thread shared-memory rows (A/B measurement aid; results agree to fp32 summation order).
+ * "row_flush" = 0: the packed adjoint kernels reduce dvar cotangents with a warp butterfly per profile
+ * instead of the staged shared-memory transposition (A/B measurement aid; results agree to fp32
+ * summation order).  "conv_tma" = 0: the conv kernels stage their tiles with cp.async / plain stores
+ * instead of TMA (A/B; bit-identical results).
  * "no_deflection" = 1: evaluate source light at the image-plane position (simulate(..., no_deflection=True),
  * tf/simulator.py:125-126).  "components" = 1 | 2 | 3: gl_simulate adds only the lens light / only the
  * source light / both (simulate_lens_light, simulate_images, simulate_source: tf/simulator.py:242-328).
