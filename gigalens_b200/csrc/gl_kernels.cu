@@ -227,6 +227,11 @@ __host__ __device__ inline int gl_scr_offset(const GlProgram& P, bool rows = fal
 __host__ __device__ inline int gl_bwd_smem_floats(const GlProgram& P, int ppt, bool rows = false) {
   return gl_scr_offset(P, rows) + (P.scr_prof >= 0 ? GL_EPL_NSTATE * ppt * GLK_THREADS : 0);
 }
+// packed adjoint kernel: per-thread prefetch slots (x, y, dL/dss pairs of the next batch) behind the series scratch
+__host__ __device__ inline int gl_pre_offset(const GlProgram& P, bool rows, int ppt) { return gl_bwd_smem_floats(P, ppt, rows); }
+__host__ __device__ inline int gl_bwd_p_smem_floats(const GlProgram& P, int ppt, bool rows) {
+  return gl_pre_offset(P, rows, ppt) + 3 * ppt * GLK_THREADS;
+}
 
 template <int PPT, unsigned F>
 __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_fwd(GlProgram P, int npix, const float* __restrict__ grid_x,
@@ -460,20 +465,41 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_bwd_p(GlProgram P, int
   const float2* gsrc = reinterpret_cast<const float2*>(gss + (size_t)b * npix);
   const float2* gx2 = reinterpret_cast<const float2*>(grid_x);
   const float2* gy2 = reinterpret_cast<const float2*>(grid_y);
+  // The batch inputs (grid x, y and dL/d(ss) of this thread's pixel pairs) are prefetched one batch ahead with
+  // cp.async into a per-thread shared-memory slot: the slot is read into registers at the top of a batch and
+  // refilled for the next one at once, so the HBM / L2 latency of the loads hides behind a whole batch of
+  // arithmetic (the first consumer of the plain loads was the top stall of the kernel, 7 % of its samples).
+  float2* pre = reinterpret_cast<float2*>(smem + gl_pre_offset(P, ROWS, PPT)) + threadIdx.x;   // [3 * NV][threads]
+  auto prefetch = [&](int batch) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int pr = batch * per_batch + j * GLK_THREADS + threadIdx.x;
+      const unsigned nb = (batch < nbatch && pr < npair) ? 8u : 0u;    // 0 source bytes = zero fill
+      const int p = nb ? pr : 0;
+      const unsigned d0 = (unsigned)__cvta_generic_to_shared(pre + (3 * j) * GLK_THREADS);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d0), "l"(gx2 + p), "r"(nb) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d0 + 8u * GLK_THREADS), "l"(gy2 + p), "r"(nb) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d0 + 16u * GLK_THREADS), "l"(gsrc + p), "r"(nb) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
   auto sweep = [&](auto& flush, auto&& after_batch) {
+    prefetch(blockIdx.x);
     for (int batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
       GlF2 x[NV], y[NV], gs[NV];
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
-        const int pr = batch * per_batch + j * GLK_THREADS + threadIdx.x;
-        const bool in = pr < npair;
-        const int p = in ? pr : 0;
-        const float2 a = __ldg(gx2 + p), c = __ldg(gy2 + p);
+        const float2 a = pre[(3 * j) * GLK_THREADS], c = pre[(3 * j + 1) * GLK_THREADS];
+        float2 gv = pre[(3 * j + 2) * GLK_THREADS];
         x[j] = GlF2(a.x, a.y); y[j] = GlF2(c.x, c.y);
-        float2 gv = in ? __ldg(gsrc + p) : make_float2(0.f, 0.f);
-        if (ss_mask && in) { if (!ss_mask[2 * p]) gv.x = 0.f; if (!ss_mask[2 * p + 1]) gv.y = 0.f; }
+        if (ss_mask) {
+          const int pr = batch * per_batch + j * GLK_THREADS + threadIdx.x;
+          if (pr < npair) { if (!ss_mask[2 * pr]) gv.x = 0.f; if (!ss_mask[2 * pr + 1]) gv.y = 0.f; }
+        }
         gs[j] = GlF2(gv.x, gv.y);
       }
+      prefetch(batch + gridDim.x);
       gl_pix_image_bwd<GlF2, NV, F>(P, s_der, x, y, gs, no_deflection != 0, flush, scr, GLK_THREADS);
       after_batch();
     }
@@ -1089,10 +1115,11 @@ static int gl_run_raytrace_bwd(gl_plan* p, float* gss, int no_deflection, cudaSt
     })
     GL_LAUNCH_CHECK("k_nan_cotangent_mask");
   }
-  const size_t smem = (size_t)gl_bwd_smem_floats(p->prog, 4) * sizeof(float);
+  size_t smem = (size_t)gl_bwd_smem_floats(p->prog, 4) * sizeof(float);
   if ((p->feat_idx == 0 || p->feat_idx == 2) && (p->npix % 2) == 0 && p->use_packed) {
     // staged flush (DevFlushStage) when two CTAs of it still fit one SM
-    const size_t smem_rows = (size_t)gl_bwd_smem_floats(p->prog, 4, true) * sizeof(float);
+    const size_t smem_rows = (size_t)gl_bwd_p_smem_floats(p->prog, 4, true) * sizeof(float);
+    smem = (size_t)gl_bwd_p_smem_floats(p->prog, 4, false) * sizeof(float);
     const bool rows = p->row_flush && smem_rows <= 108 * 1024 && p->prog.g_total <= 64;
 #define GL_BWD_P(FS, ROWS, SM)                                                                                              \
     {                                                                                                                       \
