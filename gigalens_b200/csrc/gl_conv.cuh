@@ -52,6 +52,8 @@ struct GlConvGeom {
   int wpitch;   // roundup4(A)
   int tma_pitch;     // forward, TMA staging: row pitch of the staged tile (in_pitch + 4)
   int out_stride;    // adjoint, TMA staging: floats of the output staging tile (tw*th rounded up to 32)
+  int band_rows;     // adjoint, TMA staging: > 0 = every warp owns band_rows complete tile rows and stores them itself
+  int band_stride;   //   floats between the warps' staging bands (band_rows*tw rounded up to 32)
   int phase_stride;  // forward only: floats between phase sub-images (in_rows*in_pitch padded so that the
                      // de-interleaving stores of one warp fall into distinct banks)
   int rc0;      // adjoint only: first padded-phase row/column (pad / ss)
@@ -520,6 +522,14 @@ __global__ void __launch_bounds__(256, 2) k_conv_bwd_tma(const __grid_constant__
   const int origin = ty * GLC_RY * g.tma_pitch + tx * GLC_RX + ((c0 - (A - 1)) & 3);
   const bool ok = glc_mbar_wait(&s_bar[0], 0);
   if (!ok) scale = __int_as_float(0x7fc00000);          // barrier time-out: poison the result instead of returning stale data
+  // Output path.  When a warp's 32 threads cover complete rows of the thread grid (band_rows > 0) the warp owns a
+  // band of full tile rows: it stages and stores that band by itself (its lane 0 issues the TMA store and waits on its
+  // own bulk group), so after the input barrier the warps never meet again -- two CTA barriers per phase cost 21 % of
+  // the kernel's stall samples.  Otherwise the CTA stages the whole tile and thread 0 stores it.
+  const int warp = tid >> 5, lane = tid & 31;
+  const bool wstore = g.band_rows > 0;
+  float* s_band = wstore ? s_out + warp * g.band_stride : s_out;
+  const int ty_loc = wstore ? ty - warp * (32 / g.tpr) : ty;      // thread row inside the staging area it writes to
   for (int ph = 0; ph < nph; ++ph) {
     float2 acc2[GLC_RP][GLC_RX];
 #pragma unroll
@@ -528,11 +538,11 @@ __global__ void __launch_bounds__(256, 2) k_conv_bwd_tma(const __grid_constant__
       for (int c = 0; c < GLC_RX; ++c) acc2[r][c] = make_float2(0.f, 0.f);
     if (active) corr_rows2<A, 2>(s_in + origin, g.tma_pitch, s_w + ph * UTAB, acc2);
     if (ph > 0) {                                       // the previous phase's store must have read the staging tile
-      if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      __syncthreads();
+      if (wstore) { if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); __syncwarp(); }
+      else { if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); __syncthreads(); }
     }
     if (active) {
-      float4* drow = reinterpret_cast<float4*>(s_out + (ty * GLC_RY) * g.tw + tx * GLC_RX);
+      float4* drow = reinterpret_cast<float4*>(s_band + (ty_loc * GLC_RY) * g.tw + tx * GLC_RX);
       const int rpitch = g.tw >> 2;
 #pragma unroll
       for (int rp = 0; rp < GLC_RP; ++rp) {
@@ -541,8 +551,8 @@ __global__ void __launch_bounds__(256, 2) k_conv_bwd_tma(const __grid_constant__
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the TMA unit
-    __syncthreads();
-    if (tid == 0) {
+    if (wstore) __syncwarp(); else __syncthreads();
+    if (wstore ? (lane == 0 && warp * (32 / g.tpr) < g.nty) : (tid == 0)) {
       // ss pixel (i, j) = (ss*r + py - pad, ss*c + px - pad) lives in image phase (i mod ss, j mod ss) at sub-image
       // pixel (i div ss, j div ss): constant offsets per conv phase, so the tile lands as one box of phase image q
       const int py = ph / g.ss, px = ph - py * g.ss;
@@ -550,10 +560,11 @@ __global__ void __launch_bounds__(256, 2) k_conv_bwd_tma(const __grid_constant__
       const int dy = (fy >= 0) ? fy / g.ss : -((-fy + g.ss - 1) / g.ss);   // floor division
       const int dx = (fx >= 0) ? fx / g.ss : -((-fx + g.ss - 1) / g.ss);
       const int q = (fy - dy * g.ss) * g.ss + (fx - dx * g.ss);
+      const int yb = wstore ? warp * g.band_rows : 0;
       asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
-                   ::"l"(&tm_out), "r"(glc_smem_u32(s_out)), "r"(c0 + dx), "r"(r0 + dy), "r"(b * nph + q) : "memory");
+                   ::"l"(&tm_out), "r"(glc_smem_u32(s_band)), "r"(c0 + dx), "r"(r0 + dy + yb), "r"(b * nph + q) : "memory");
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
   }
-  if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory must outlive the last store's read
+  if (wstore ? lane == 0 : tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory must outlive the last store's read
 }

@@ -878,6 +878,12 @@ int gl_plan_create(const gl_model_desc* model, const gl_sim_config* sim, int32_t
     p->gb.tma_pitch = p->gb.in_pitch + 4;
     p->gb.phase_stride = (p->gb.in_rows * p->gb.tma_pitch + 31) & ~31;
     p->gb.out_stride = (p->gb.tw * p->gb.th + 31) & ~31;
+    p->gb.band_rows = 0; p->gb.band_stride = 0;
+    if (32 % p->gb.tpr == 0 && p->gb.nty % (32 / p->gb.tpr) == 0) {   // a warp = complete thread rows: per-warp band stores
+      p->gb.band_rows = GLC_RY * (32 / p->gb.tpr);
+      p->gb.band_stride = (p->gb.band_rows * p->gb.tw + 31) & ~31;
+      p->gb.out_stride = p->gb.band_stride * (p->conv_threads_b / 32);
+    }
     p->smem_cb_tma = (size_t)(p->gb.phase_stride + p->gb.out_stride + nph * UTAB) * sizeof(float);
     p->conv_tma_b_ok = (p->n % 4) == 0 && p->gb.tma_pitch <= 256 && p->gb.in_rows <= 256 && p->gb.th <= 256 && (p->gb.rc0 & 1) == 0;
     for (int px = 0; px < ss; ++px) {   // output tile origins rc0 + dx(px) + k * tw on 16-byte boundaries
@@ -1204,7 +1210,7 @@ static int gl_launch_conv_bwd_A(gl_plan* p, const float* gimg, float scale, floa
   if (p->conv_tma && p->conv_tma_b_ok && ((A - 1) & 1) == 0 && ((uintptr_t)gimg % 16) == 0 && ((uintptr_t)gss % 16) == 0) {
     if (p->tmap_bi_base != gimg || p->tmap_bo_base != gss || p->tmap_b_nimg != nimg) {
       p->tmap_b_ok = gl_make_image_tmap(&p->tmap_bi, gimg, p->n, (size_t)nimg, p->gb.tma_pitch, p->gb.in_rows) &&
-                     gl_make_image_tmap(&p->tmap_bo, gss, p->n, (size_t)nimg * nph, p->gb.tw, p->gb.th);
+                     gl_make_image_tmap(&p->tmap_bo, gss, p->n, (size_t)nimg * nph, p->gb.tw, p->gb.band_rows > 0 ? p->gb.band_rows : p->gb.th);
       p->tmap_bi_base = gimg; p->tmap_bo_base = gss; p->tmap_b_nimg = nimg;
     }
     if (p->tmap_b_ok) {
