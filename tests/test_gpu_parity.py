@@ -668,3 +668,48 @@ def test_positions_golden_vectors(tag, include_pixels):
     assert np.max(np.abs(H - g["hessian_truth"])) < 1e-5
     mu = sim1.magnification(g["cx"], g["cy"], params["lens_mass"]).cpu().numpy()[0]
     assert np.allclose(mu, g["magnification_truth"], rtol=2e-4)
+
+
+# ---------------------------------------------------------------------------------------------
+# kernel variants: every alternative path must agree with the default one (and so with the oracle)
+# ---------------------------------------------------------------------------------------------
+def _c2_logprob(bs, options, num_pix=60, seed=9):
+    wl = workloads.c2_workload()
+    cfg = wl["sim_config"]
+    obs = wl["observed"]
+    if num_pix != 60:
+        cfg = SimulatorConfig(delta_pix=cfg.delta_pix, num_pix=num_pix, supersample=cfg.supersample, kernel=cfg.kernel)
+        obs = obs[:num_pix, :num_pix]
+    sim = LensSimulator(wl["phys_model"], cfg, bs=bs)
+    for k, v in options.items():
+        sim.set_option(k, v)
+    pmod = ForwardProbModel(wl["prior"], obs, background_rms=0.2, exp_time=100.0)
+    z = torch.as_tensor(pmod.bij_inverse(wl["prior"].sample(bs, seed=seed)), device="cuda")
+    return [t.double().cpu().numpy() for t in pmod.log_prob_and_grad(sim, z)]
+
+
+@pytest.mark.parametrize("num_pix", [60, 48, 30])   # 30: n % 4 != 0, the plan must fall back to the cp.async kernels by itself
+def test_conv_tma_staging_is_bit_identical_to_cp_async(num_pix):
+    a = _c2_logprob(96, {"conv_tma": 1}, num_pix)
+    b = _c2_logprob(96, {"conv_tma": 0}, num_pix)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+def test_staged_flush_matches_butterfly_flush():
+    a = _c2_logprob(128, {"row_flush": 1})
+    b = _c2_logprob(128, {"row_flush": 0})
+    assert np.array_equal(a[0], b[0])
+    scale = np.max(np.abs(b[2]), axis=0)
+    assert np.max(np.max(np.abs(a[2] - b[2]), axis=0) / scale) < 5e-6   # fp32 summation order only
+
+
+def test_epl_series_tolerance_default_matches_reference_count():
+    """epl_tol_exp10 = 9 (default) against the reference's 1e-12 trip count (epl.py:37), per-sample and batch-global."""
+    a = _c2_logprob(256, {})
+    b = _c2_logprob(256, {"epl_tol_exp10": 12})
+    c = _c2_logprob(256, {"epl_tol_exp10": 12, "epl_batch_max": 1})
+    for ref in (b, c):
+        assert np.max(np.abs(a[0] - ref[0]) / np.abs(ref[0])) < 2e-7
+        scale = np.max(np.abs(ref[2]), axis=0)
+        assert np.max(np.max(np.abs(a[2] - ref[2]), axis=0) / scale) < 5e-6
