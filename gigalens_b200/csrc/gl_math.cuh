@@ -70,8 +70,12 @@ GL_HD double gl_fma(double a, double b, double c) { return a * b + c; }   // hos
 #if defined(__CUDA_ARCH__)
 GL_HD float gl_log2_fast(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 GL_HD float gl_exp2_fast(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-GL_HD float gl_div_fast(float a, float b) { return __fdividef(a, b); }
-GL_HD float gl_rsqrt_fast(float x) { return rsqrtf(x); }
+// rcp / rsqrt as the bare MUFU op (.ftz): rsqrtf() and __fdividef() wrap it in range tests and rescaling
+// multiplies for denormal or huge operands (1 FSETP + 2 FMUL per call -- a fifth of the dPIE member loop),
+// which the operands here (squared radii and norms on the arcsecond scale) never are.
+GL_HD float gl_rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+GL_HD float gl_div_fast(float a, float b) { return a * gl_rcp_fast(b); }
+GL_HD float gl_rsqrt_fast(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 #else
 GL_HD float gl_log2_fast(float x) { return log2f(x); }
 GL_HD float gl_exp2_fast(float x) { return exp2f(x); }
@@ -89,7 +93,7 @@ GL_HD double gl_rsqrt_fast(double x) { return 1.0 / sqrt(x); }
 GL_HD float gl_atan2_fast(float y, float x) {
   const float ax = fabsf(x), ay = fabsf(y);
   const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-  const float t = (mx > 0.f) ? __fdividef(mn, mx) : 0.f;
+  const float t = (mx > 0.f) ? mn * gl_rcp_fast(mx) : 0.f;
   const float s = t * t;
   float p = 0.0029327620286494493f;
   p = fmaf(p, s, -0.016413191333413124f);
@@ -152,7 +156,7 @@ GL_HD GlF2 gl_div_fast(GlF2 a, GlF2 b) { return GlF2(gl_div_fast(a.x, b.x), gl_d
 GL_HD GlF2 gl_atan2_fast(GlF2 y, GlF2 x) {   // the polynomial of the scalar version on packed lanes; octant fix-up per lane
   const float ax0 = fabsf(x.x), ay0 = fabsf(y.x), ax1 = fabsf(x.y), ay1 = fabsf(y.y);
   const float mx0 = fmaxf(ax0, ay0), mx1 = fmaxf(ax1, ay1);
-  const GlF2 t = GlF2(fminf(ax0, ay0), fminf(ax1, ay1)) * GlF2(mx0 > 0.f ? __fdividef(1.f, mx0) : 0.f, mx1 > 0.f ? __fdividef(1.f, mx1) : 0.f);
+  const GlF2 t = GlF2(fminf(ax0, ay0), fminf(ax1, ay1)) * GlF2(mx0 > 0.f ? gl_rcp_fast(mx0) : 0.f, mx1 > 0.f ? gl_rcp_fast(mx1) : 0.f);
   const GlF2 s = t * t;
   GlF2 p = GlF2(0.0029327620286494493f);
   p = gl_fma(p, s, GlF2(-0.016413191333413124f));
@@ -1065,7 +1069,7 @@ template <class T>
 GL_HD T gl_sqrt_pos(T x) { return x * gl_rsqrt_fast(x); }   // x > 0
 template <class T>
 struct DpieFw {
-  T sc, st, a, b_, c_, d_, e_, f_, aa, bb, cc, dd, inorm, aaa, bbb, inorm2, zr_re, zr_im;
+  T sc, st, isc, ist, a, b_, c_, d_, e_, f_, aa, bb, cc, dd, inorm, aaa, bbb, inorm2, zr_re, zr_im;   // isc = 1/sc, ist = 1/st
 };
 // T is the lane type (float, double, GlDual, or the two-pixel pack GlF2), S the scalar type of the constants.
 template <class T>
@@ -1073,8 +1077,9 @@ GL_HD void dpie_core_fwd(const typename gl_scalar_of<T>::type* d, T x, T y, Dpie
   typedef typename gl_scalar_of<T>::type S;
   const S two_sqe = S(2) * d[DP_SQE];
   const T rem2 = gl_fma(x * x, T(d[DP_IOPE2]), y * y * T(d[DP_IOME2]));
-  W.sc = gl_sqrt_pos(T(d[DP_RC2]) + rem2);
-  W.st = gl_sqrt_pos(T(d[DP_RT2]) + rem2);
+  const T sc2 = T(d[DP_RC2]) + rem2, st2 = T(d[DP_RT2]) + rem2;   // > 0
+  W.isc = gl_rsqrt_fast(sc2); W.ist = gl_rsqrt_fast(st2);        // the adjoints need the reciprocals as well
+  W.sc = sc2 * W.isc; W.st = st2 * W.ist;
   const T yq = y * T(d[DP_IQ]);
   W.a = T(d[DP_Q]) * x;                             // znum_rc_re
   W.b_ = gl_fma(T(two_sqe), W.sc, -yq);             // znum_rc_im
@@ -1105,8 +1110,9 @@ GL_HD void dpie_fwd(const typename gl_scalar_of<T>::type* d, const T* x, const T
     T xr = gl_fma(dx, c, dy * s), yr = gl_fma(dy, c, -(dx * s));
     DpieFw<T> W; T re, im;
     dpie_core_fwd<T>(d, xr, yr, W, re, im);
-    ax[j] = scale * gl_fma(re, c, -(im * s));
-    ay[j] = scale * gl_fma(re, s, im * c);
+    const T Ar = gl_fma(re, c, -(im * s)), Ai = gl_fma(re, s, im * c);   // (re, im) rotated back: alpha_m = scale * A
+    ax[j] = scale * Ar;
+    ay[j] = scale * Ai;
   }
 }
 template <class T, int NP>
@@ -1159,7 +1165,7 @@ GL_HD void dpie_bwd(const typename gl_scalar_of<T>::type* d, const T* x, const T
     T gy = -gl_fma(gbe, iq, gd + gf);
     T gsqe = two * gl_fma(gb, W.sc, gl_fma(ge_, W.st, gl_fma(gd, rc, gf * rt)));
     T gsc = gb * two * sqe, gst = ge_ * two * sqe;
-    T isc = gl_div_fast(T(S(1)), W.sc), ist = gl_div_fast(T(S(1)), W.st);
+    T isc = W.isc, ist = W.ist;
     g[DPG_RC] += gl_fma(gd * two, sqe, gsc * rc * isc);
     g[DPG_RT] += gl_fma(gf * two, sqe, gst * rt * ist);
     T grem2 = half * gl_fma(gsc, isc, gst * ist);
@@ -1196,38 +1202,39 @@ GL_HD void dpie_fwd_jac(const typename gl_scalar_of<T>::type* d, const T* x, con
     T xr = gl_fma(dx, c, dy * s), yr = gl_fma(dy, c, -(dx * s));
     DpieFw<T> W; T re, im;
     dpie_core_fwd<T>(d, xr, yr, W, re, im);
-    ax[j] = scale * gl_fma(re, c, -(im * s));
-    ay[j] = scale * gl_fma(re, s, im * c);
+    const T Ar = gl_fma(re, c, -(im * s)), Ai = gl_fma(re, s, im * c);   // (re, im) rotated back: alpha_m = scale * A
+    ax[j] = scale * Ar;
+    ay[j] = scale * Ai;
     // tangents of (re, im) w.r.t. rc and rt
     T tre[2], tim[2];
+    const T zsc = zci * scale * W.inorm * W.inorm2;      // tangents below carry the member's scale
 #pragma unroll
     for (int w = 0; w < 2; ++w) {
       T naa, nbb, ncc, ndd;   // num' = naa + i nbb, den' = ncc + i ndd
       if (w == 0) {           // d/d rc: b' = 2 sqe rc/sc, d' = 2 sqe
-        const T bp = bp0 * gl_div_fast(T(S(1)), W.sc);
+        const T bp = bp0 * W.isc;
         naa = -(bp * W.f_); nbb = bp * W.c_; ncc = -(two_sqe * W.e_); ndd = W.a * two_sqe;
       } else {                // d/d rt: e' = 2 sqe rt/st, f' = 2 sqe
-        const T ep = ep0 * gl_div_fast(T(S(1)), W.st);
+        const T ep = ep0 * W.ist;
         naa = -(W.b_ * two_sqe); nbb = W.a * two_sqe; ncc = -(W.d_ * ep); ndd = W.c_ * ep;
       }
       // t = num' - z den'
       const T tr = naa - gl_fma(W.aaa, ncc, -(W.bbb * ndd));
       const T ti = nbb - gl_fma(W.aaa, ndd, W.bbb * ncc);
-      // dz = t conj(den) / |den|^2
-      const T dzr_ = gl_fma(tr, W.cc, ti * W.dd) * W.inorm;
-      const T dzi_ = gl_fma(ti, W.cc, -(tr * W.dd)) * W.inorm;
-      // d(log z) = dz conj(z) / |z|^2
-      const T lr = gl_fma(dzr_, W.aaa, dzi_ * W.bbb) * W.inorm2;
-      const T li = gl_fma(dzi_, W.aaa, -(dzr_ * W.bbb)) * W.inorm2;
-      tre[w] = -(zci * li); tim[w] = zci * lr;
+      // dz = t conj(den) / |den|^2,  d(log z) = dz conj(z) / |z|^2: both real scalings (and zci) applied once
+      const T dzr_ = gl_fma(tr, W.cc, ti * W.dd);
+      const T dzi_ = gl_fma(ti, W.cc, -(tr * W.dd));
+      const T lr = gl_fma(dzr_, W.aaa, dzi_ * W.bbb);
+      const T li = gl_fma(dzi_, W.aaa, -(dzr_ * W.bbb));
+      tre[w] = -(zsc * li); tim[w] = zsc * lr;
     }
+    // rotate the two tangents back once; then every base parameter k is a 3-term combination per component
+    const T B0r = gl_fma(tre[0], c, -(tim[0] * s)), B0i = gl_fma(tre[0], s, tim[0] * c);
+    const T B1r = gl_fma(tre[1], c, -(tim[1] * s)), B1i = gl_fma(tre[1], s, tim[1] * c);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      // rotated-frame tangent of alpha_m/1 w.r.t. base parameter k, then rotate back
-      const T vr = gl_fma(T(M[k]), re, scale * gl_fma(T(M[3 + k]), tre[0], T(M[6 + k]) * tre[1]));
-      const T vi = gl_fma(T(M[k]), im, scale * gl_fma(T(M[3 + k]), tim[0], T(M[6 + k]) * tim[1]));
-      Jx[k][j] += gl_fma(vr, c, -(vi * s));
-      Jy[k][j] += gl_fma(vr, s, vi * c);
+      Jx[k][j] += gl_fma(T(M[k]), Ar, gl_fma(T(M[3 + k]), B0r, T(M[6 + k]) * B1r));
+      Jy[k][j] += gl_fma(T(M[k]), Ai, gl_fma(T(M[3 + k]), B0i, T(M[6 + k]) * B1i));
     }
   }
 }
