@@ -248,6 +248,7 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_fwd(GlProgram P, int n
   const int nbatch = (npix + per_batch - 1) / per_batch;
   float* dst = ss_img + (size_t)b * npix;
   for (int batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
+    if (batch * per_batch + (int)(threadIdx.x & ~31u) >= npix) break;   // this warp has no pixel left (ragged last batch)
     float x[PPT], y[PPT], v[PPT];
     int pix[PPT];
 #pragma unroll
@@ -323,6 +324,7 @@ __global__ void __launch_bounds__(GLK_THREADS) k_nan_cotangent_mask(GlProgram P,
   const int nbatch = (npix + per_batch - 1) / per_batch;
   float* g = gss + (size_t)b * npix;
   for (int batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
+    if (batch * per_batch + (int)(threadIdx.x & ~31u) >= npix) break;   // this warp has no pixel left (ragged last batch)
     float x[PPT], y[PPT], v[PPT];
     int pix[PPT];
 #pragma unroll
@@ -361,6 +363,7 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_bwd(GlProgram P, int n
   const int nbatch = (npix + per_batch - 1) / per_batch;
   const float* gsrc = gss + (size_t)b * npix;
   for (int batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
+    if (batch * per_batch + (int)(threadIdx.x & ~31u) >= npix) break;   // this warp has no pixel left (ragged last batch)
     float x[PPT], y[PPT], gs[PPT];
 #pragma unroll
     for (int j = 0; j < PPT; ++j) {
@@ -403,6 +406,7 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_fwd_p(GlProgram P, int
   const float2* gx2 = reinterpret_cast<const float2*>(grid_x);
   const float2* gy2 = reinterpret_cast<const float2*>(grid_y);
   for (int batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
+    if (batch * per_batch + (int)(threadIdx.x & ~31u) >= npair) break;   // this warp has no pixel left (ragged last batch)
     GlF2 x[NV], y[NV], v[NV];
     int pr[NV];
 #pragma unroll
@@ -441,7 +445,7 @@ struct DevFlushStage {
 };
 
 template <int PPT, unsigned F, bool ROWS>
-__global__ void __launch_bounds__(GLK_THREADS) k_raytrace_bwd_p(GlProgram P, int npix, const float* __restrict__ grid_x,
+__global__ void __launch_bounds__(GLK_THREADS, 2) k_raytrace_bwd_p(GlProgram P, int npix, const float* __restrict__ grid_x,
                                                                 const float* __restrict__ grid_y,
                                                                 const unsigned char* __restrict__ ss_mask,
                                                                 const float* __restrict__ derived, int no_deflection,
@@ -486,6 +490,7 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_bwd_p(GlProgram P, int
   auto sweep = [&](auto& flush, auto&& after_batch) {
     prefetch(blockIdx.x);
     for (int batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
+      if (batch * per_batch + (int)(threadIdx.x & ~31u) >= npair) break;   // this warp has no pixel left (ragged last batch)
       GlF2 x[NV], y[NV], gs[NV];
       asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
@@ -503,6 +508,7 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_bwd_p(GlProgram P, int
       gl_pix_image_bwd<GlF2, NV, F>(P, s_der, x, y, gs, no_deflection != 0, flush, scr, GLK_THREADS);
       after_batch();
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   };
   float* out = gpart + ((size_t)b * gridDim.x + blockIdx.x) * P.g_total;
   if constexpr (ROWS) {
