@@ -176,18 +176,23 @@ __device__ __forceinline__ void glc_fwd_epilogue(const GlConvGeom& g, const floa
           if (like.enabled) {
             const float m = like.mask ? (like.mask[o] ? 1.f : 0.f) : 1.f;
             const float res = v - like.observed[o];
+            // var = err^2 with err = sqrt(bg^2 + I/t) (tf/model.py:95-98) or the fixed error map; a negative variance
+            // gives NaN like the reference.  1/err is one MUFU rsqrt plus a Newton step (full fp32 accuracy) and the
+            // log is lg2 * ln2 (abs. error 2^-22): the IEEE sqrt / four divisions / logf of a literal transcription
+            // were a sixth of this kernel's instructions.
             float var, dvar;
             if (like.error_map) { const float e = like.error_map[o]; var = e * e; dvar = 0.f; }
-            else {
-              // err = sqrt(bg^2 + I/t), var = err^2 (tf/model.py:95-98); negative => NaN like the reference
-              const float e = sqrtf(like.bg2 + v * like.inv_exp); var = e * e; dvar = like.inv_exp;
-            }
-            const float q = res / sqrtf(var);
+            else { var = fmaf(v, like.inv_exp, like.bg2); dvar = like.inv_exp; }
+            float r;
+            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(var));
+            r = r * fmaf(-0.5f * var * r, r, 1.5f);
+            const float ivar = r * r;
+            const float q = res * r;
             chi2 += q * q * m;
-            norm += logf(6.283185307179586f * var) * m;
+            norm += __logf(6.283185307179586f * var) * m;
             if (gimg) {
-              // d(-0.5*(chi2+norm))/dI
-              const float gi = -0.5f * m * (2.f * res / var - (res * res) / (var * var) * dvar + dvar / var);
+              // d(-0.5*(chi2+norm))/dI = -0.5 m (2 res/var - res^2 dvar/var^2 + dvar/var)
+              const float gi = -0.5f * m * ivar * fmaf(-(res * res) * ivar, dvar, fmaf(2.f, res, dvar));
               gimg[(size_t)b * g.n * g.n + o] = gi;
             }
           }
