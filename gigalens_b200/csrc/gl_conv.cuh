@@ -359,7 +359,7 @@ __global__ void __maxnreg__(96) k_conv_fwd_tma(const __grid_constant__ CUtensorM
   float* s_in = smem;                              // [2][tstride]  double-buffered phase tile
   float* s_w = smem + 2 * tstride;                 // [nph][A][2][ulen] packed tap table
   __shared__ float s_red[2][8];
-  __shared__ __align__(8) unsigned long long s_bar[3];   // tile buffer 0 / 1 full, tap table full
+  __shared__ __align__(8) unsigned long long s_bar[5];   // tile buffer 0 / 1 full, tap table full, tile buffer 0 / 1 drained
 
   const int ntiles = g.tiles_x * g.tiles_y;
   const int b = blockIdx.x / ntiles, tile = blockIdx.x - b * ntiles;
@@ -370,6 +370,7 @@ __global__ void __maxnreg__(96) k_conv_fwd_tma(const __grid_constant__ CUtensorM
 
   if (tid == 0) {
     glc_mbar_init(&s_bar[0], 1); glc_mbar_init(&s_bar[1], 1); glc_mbar_init(&s_bar[2], 1);
+    glc_mbar_init(&s_bar[3], (int)(blockDim.x >> 5)); glc_mbar_init(&s_bar[4], (int)(blockDim.x >> 5));   // one arrival per warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -407,8 +408,14 @@ __global__ void __maxnreg__(96) k_conv_fwd_tma(const __grid_constant__ CUtensorM
       corr_rows2<A, 2>(s_in + (q & 1) * tstride + origin + r, g.tma_pitch, s_w + ph * UTAB, acc2);
     }
     if (q + 2 < nph) {
-      __syncthreads();                    // every thread is done with this buffer
-      if (tid == 0) issue_phase(q + 2);
+      // Buffer hand-back without a CTA barrier: every warp reports that it is done with this buffer and moves on to
+      // the next phase (already staged); only thread 0 waits for the five reports before it re-arms the buffer.
+      __syncwarp();
+      if ((tid & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(glc_smem_u32(&s_bar[3 + (q & 1)])) : "memory");
+      if (tid == 0) {
+        ok = glc_mbar_wait(&s_bar[3 + (q & 1)], (unsigned)(q >> 1) & 1u) && ok;
+        issue_phase(q + 2);
+      }
     }
   }
   if (!ok) {                              // barrier time-out: poison the outputs instead of returning stale data
