@@ -163,7 +163,12 @@ def run_cuda(args):
     bs = BS_PER_GPU
     sim = LensSimulator(wl["phys_model"], wl["sim_config"], bs=bs)
     pmod = ForwardProbModel(wl["prior"], wl["observed"], background_rms=wl["background_rms"], exp_time=wl["exp_time"])
-    z_host = torch.as_tensor(pmod.bij_inverse(wl["prior"].sample(bs, seed=rank))).pin_memory()
+    draw = wl["prior"].sample(bs, seed=rank)
+    z_host = torch.as_tensor(pmod.bij_inverse(draw)).pin_memory()
+    # mean EPL series length of this batch (per-sample count at the plan's default tolerance 1e-9, cap 50): enters the nominal flop count
+    _e = np.hypot(np.asarray(draw["lens_mass"][0]["e1"], dtype=np.float64), np.asarray(draw["lens_mass"][0]["e2"], dtype=np.float64))
+    _f = np.clip(_e, 1e-30, 1.0 - 1e-9)
+    mean_trips = float(np.mean(np.clip(np.ceil(np.log(1e-9) / np.log(_f) + 2.0) - 1.0, 0, 50)))
     z = z_host.cuda()
     d = z.shape[1]
 
@@ -230,7 +235,7 @@ def run_cuda(args):
     # ---- roofline of the dominant kernel (ray-shooting adjoint), timed live --------------------
     roof = None
     if rank == 0:
-        roof = kernel_roofline(sim, stage_ms, ms / args.steps, d)
+        roof = kernel_roofline(sim, stage_ms, ms / args.steps, d, mean_trips)
 
     if rank != 0:
         return
@@ -250,7 +255,7 @@ def run_cuda(args):
         "e2e": {"value": bs * world * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": bs * d * 4,
                 "d2h_bytes_per_step": bs * (d + 2) * 4, "api": "gl_logprob_grad_host (pinned host z -> logp, red_chi2, dz)"},
         "gpu_launches": int(launches),
-        "clocks": clocks, "roofline": roof["roofline"], "roofline_fp32": roof["fp32"], "kernel_ms": roof["kernel_ms"],
+        "clocks": clocks, "roofline": roof["roofline"], "roofline_fp32": roof["fp32"], "kernel_ms": roof["kernel_ms"], "roofline_kernels": roof["per_kernel"],
         "cpu_baseline": cpu,
     }
     print(json.dumps(line))
@@ -259,7 +264,7 @@ def run_cuda(args):
 STAGES = ["k_unconstrain", "k_prep", "k_raytrace_fwd", "k_conv_fwd", "k_conv_bwd", "k_raytrace_bwd", "k_sample_bwd"]
 
 
-def kernel_roofline(sim, stage_ms, step_ms, d):
+def kernel_roofline(sim, stage_ms, step_ms, d, mean_trips):
     """Roofline of the dominant kernel (the ray-tracing adjoint) from its CUDA-event time measured on
     the launch stream inside the timed region (gl_plan_get_timings), with DESIGN.md's algorithmic
     bytes / flops per eval.  `traffic` is the ncu DRAM byte count of the same kernel (profiles/)."""
@@ -272,8 +277,13 @@ def kernel_roofline(sim, stage_ms, step_ms, d):
     P = sim.numPix ** 2
     alg_bytes = {"k_raytrace_fwd": 4 * npix, "k_conv_fwd": 4 * npix + 8 * P, "k_conv_bwd": 4 * P + 4 * npix,
                  "k_raytrace_bwd": 4 * npix + 4 * 144}.get(name, 4 * npix)
-    # nominal flops per eval (hand count, FMA = 2): profile fwd 8.0 M, profile bwd 16 M, conv 4.87 M each way
-    alg_flops = {"k_raytrace_fwd": 8.0e6, "k_conv_fwd": 4.87e6, "k_conv_bwd": 4.87e6, "k_raytrace_bwd": 16.0e6}.get(name, 0.0)
+    # nominal flops per eval (SURVEY.md section 8d's hand count, FMA = 2): per ss pixel EPL 60 + 14 I, shear 6, SersicEllipse 45 x 2,
+    # backward = 2 x forward, conv 4.87 M each way.  I = mean series length of THIS batch (SURVEY quotes I = 29, the batch-global
+    # count of the reference; the kernels run per-sample counts, so I = 29 would overstate the work they do)
+    fwd_flops = npix * (60.0 + 14.0 * mean_trips + 6.0 + 90.0)
+    flops_tab = {"k_raytrace_fwd": fwd_flops, "k_conv_fwd": 4.87e6, "k_conv_bwd": 4.87e6, "k_raytrace_bwd": 2.0 * fwd_flops}
+    step_flops = 3.0 * fwd_flops + 2 * 4.87e6
+    alg_flops = flops_tab.get(name, 0.0)
     ms = stage_ms[dom]
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     sm_mhz = peaks.get("sm_max_mhz", 1965.0)
@@ -293,8 +303,26 @@ def kernel_roofline(sim, stage_ms, step_ms, d):
     except Exception:
         pass
     which = "of measured" if _peaks() else "of fallback"
+    # every hot kernel against both ceilings (north_star: FP32 utilisation for the profile kernels, HBM GB/s for the conv / likelihood)
+    all_bytes = {"k_raytrace_fwd": 4 * npix, "k_conv_fwd": 4 * npix + 8 * P, "k_conv_bwd": 4 * P + 4 * npix, "k_raytrace_bwd": 4 * npix + 4 * 144}
+    all_flops = flops_tab
+    per_kernel = {}
+    try:
+        tr_all = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["kernels"]
+    except Exception:
+        tr_all = {}
+    for k, nm in enumerate(STAGES):
+        if nm not in all_bytes or stage_ms[k] <= 0:
+            continue
+        rec = next((tr_all[key] for key in (nm + "_p", nm + "_tma", nm) if key in tr_all), {})
+        gbs = all_bytes[nm] * bs / (stage_ms[k] * 1e-3) / 1e9
+        tf = all_flops[nm] * bs / (stage_ms[k] * 1e-3) / 1e12
+        per_kernel[nm] = {"ms": stage_ms[k], "hbm_GBs": gbs, "hbm_frac": gbs / hbm_peak, "fp32_TFLOPs_nominal": tf,
+                          "fp32_frac_nominal": tf / fp32_peak, "ncu_pipe_fma_pct": rec.get("pipe_fma_pct"),
+                          "ncu_dram_bytes": rec.get("traffic_bytes"), "algorithmic_bytes": all_bytes[nm] * bs}
     return {
         "kernel_ms": {STAGES[k]: stage_ms[k] for k in range(len(STAGES))},
+        "per_kernel": per_kernel,
         "roofline": {"bound": "hbm", "kernel": name, "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved_gbs / hbm_peak, "traffic": traffic, "kernel_ms": ms,
                      "kernel_share_of_step": ms / step_ms,
@@ -302,12 +330,13 @@ def kernel_roofline(sim, stage_ms, step_ms, d):
                              "The kernel is FP32-issue bound, not HBM bound (DESIGN.md 3.1): see roofline_fp32"},
         "fp32": {"bound": "fp32_fma", "kernel": name, "achieved": alg_flops * bs / (ms * 1e-3) / 1e12, "peak": fp32_peak,
                  "unit": "TFLOP/s", "frac": alg_flops * bs / (ms * 1e-3) / 1e12 / fp32_peak,
-                 "note": "SURVEY 8d's nominal flops/eval (FMA=2) of the REFERENCE algorithm for this kernel; the kernel itself executes fewer "
-                         "(closed-form EPL f-derivative, series state reused from the forward sweep), so this is a rate of useful work -- "
+                 "note": "SURVEY 8d's nominal flops/eval formula (FMA=2) at the batch's mean series length; for the adjoint the kernel itself executes "
+                         "fewer (closed-form EPL f-derivative, series state reused from the forward sweep), so this is a rate of useful work -- "
                          "the pipe occupancy actually measured is `ncu`.  peak = 148 SM x 128 lanes x 2 x max SM clock (derived, not measured)",
                  "ncu": ncu_pipe,
-                 "whole_step": {"achieved": 34e6 * bs / (step_ms * 1e-3) / 1e12, "frac": 34e6 * bs / (step_ms * 1e-3) / 1e12 / fp32_peak,
-                                "flops_per_eval": 34e6}},
+                 "mean_epl_trips": mean_trips,
+                 "whole_step": {"achieved": step_flops * bs / (step_ms * 1e-3) / 1e12, "frac": step_flops * bs / (step_ms * 1e-3) / 1e12 / fp32_peak,
+                                "flops_per_eval": step_flops}},
     }
 
 

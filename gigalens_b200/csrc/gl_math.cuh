@@ -565,6 +565,22 @@ GL_HD void epl_bwd_core(const typename gl_scalar_of<V>::type* d, const EplGeom<V
   const V tt = V(d[EPL_T]), ss = V(S(2) - d[EPL_T]);
   const S RN = d[EPL_RN];
   const int N = (int)d[EPL_N];
+  // R_N w^N for the (rare) samples whose series is cut short by the iteration cap -- evaluated for all lanes first so
+  // that the per-pixel code below stays one straight-line block the scheduler can interleave across the NP lanes
+  V wNr[NP], wNi[NP];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) { wNr[j] = V(S(0)); wNi[j] = V(S(0)); }
+  if (RN != S(0)) {
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      V pr = V(S(1)), pi = V(S(0)), br = G[j].wr, bi = G[j].wi;
+      for (int e = N; e > 0; e >>= 1) {
+        if (e & 1) { const V t0 = gl_fma(pr, br, -(pi * bi)); pi = gl_fma(pr, bi, pi * br); pr = t0; }
+        const V b0 = gl_fma(br, br, -(bi * bi)); bi = V(S(2)) * br * bi; br = b0;
+      }
+      wNr[j] = V(RN) * pr; wNi[j] = V(RN) * pi;
+    }
+  }
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
     const EplGeom<V>& E = G[j];
@@ -572,15 +588,7 @@ GL_HD void epl_bwd_core(const typename gl_scalar_of<V>::type* d, const EplGeom<V
     const V Pr = gl_fma(zr, Qr[j], gl_fma(-zi, Qi[j], V(S(1)))), Pi = gl_fma(zr, Qi[j], zi * Qr[j]);
     const V Tr = gl_fma(E.wr, Tqr[j], -(E.wi * Tqi[j])), Ti = gl_fma(E.wr, Tqi[j], E.wi * Tqr[j]);   // dP/dt = w T'
     // dP/df = w M / (2 (1 + f w)),  M = R_N w^N - (s Q + t P)
-    V Mr = -gl_fma(ss, Qr[j], tt * Pr), Mi = -gl_fma(ss, Qi[j], tt * Pi);
-    if (RN != S(0)) {
-      V pr = V(S(1)), pi = V(S(0)), br = E.wr, bi = E.wi;
-      for (int e = N; e > 0; e >>= 1) {
-        if (e & 1) { const V t0 = gl_fma(pr, br, -(pi * bi)); pi = gl_fma(pr, bi, pi * br); pr = t0; }
-        const V b0 = gl_fma(br, br, -(bi * bi)); bi = V(S(2)) * br * bi; br = b0;
-      }
-      Mr = gl_fma(V(RN), pr, Mr); Mi = gl_fma(V(RN), pi, Mi);
-    }
+    const V Mr = wNr[j] - gl_fma(ss, Qr[j], tt * Pr), Mi = wNi[j] - gl_fma(ss, Qi[j], tt * Pi);
     const V dr = zr + V(S(1)), di = zi;
     const V inv = gl_div_fast(V(S(0.5)), gl_fma(dr, dr, di * di));
     const V Er = gl_fma(E.wr, Mr, -(E.wi * Mi)), Ei = gl_fma(E.wr, Mi, E.wi * Mr);
