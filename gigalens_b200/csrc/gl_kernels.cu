@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_bwd(GlProgram P, int n
 // Two-pixel packed variants (lane type GlF2): each thread owns PPT/2 pairs of ADJACENT pixels, every
 // per-pixel +, *, fma issues as one FFMA2 / FMUL2 / FADD2.  Used when the program only contains
 // profiles whose arithmetic is written over the lane type (feature set FS0) and npix is even.
-template <int PPT, unsigned F>
+template <int PPT, unsigned F, bool BS = false>   // BS: straight-line driver of the benchmark-shape program (gl_program.h)
 __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_fwd_p(GlProgram P, int npix, const float* __restrict__ grid_x,
                                                                 const float* __restrict__ grid_y,
                                                                 const unsigned char* __restrict__ ss_mask,
@@ -416,7 +416,8 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_fwd_p(GlProgram P, int
       const float2 a = __ldg(gx2 + p), c = __ldg(gy2 + p);
       x[j] = GlF2(a.x, a.y); y[j] = GlF2(c.x, c.y);
     }
-    gl_pix_image<GlF2, NV, F>(P, s_der, x, y, no_deflection != 0, v);
+    if constexpr (BS) gl_pix_image_bs<GlF2, NV>(P, s_der, x, y, v);
+    else gl_pix_image<GlF2, NV, F>(P, s_der, x, y, no_deflection != 0, v);
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       if (pr[j] < npair) {
@@ -444,7 +445,7 @@ struct DevFlushStage {
   }
 };
 
-template <int PPT, unsigned F, bool ROWS>
+template <int PPT, unsigned F, bool ROWS, bool BS = false>
 __global__ void __launch_bounds__(GLK_THREADS, 2) k_raytrace_bwd_p(GlProgram P, int npix, const float* __restrict__ grid_x,
                                                                 const float* __restrict__ grid_y,
                                                                 const unsigned char* __restrict__ ss_mask,
@@ -505,7 +506,8 @@ __global__ void __launch_bounds__(GLK_THREADS, 2) k_raytrace_bwd_p(GlProgram P, 
         gs[j] = GlF2(gv.x, gv.y);
       }
       prefetch(batch + gridDim.x);
-      gl_pix_image_bwd<GlF2, NV, F>(P, s_der, x, y, gs, no_deflection != 0, flush, scr, GLK_THREADS);
+      if constexpr (BS) gl_pix_image_bwd_bs<GlF2, NV>(P, s_der, x, y, gs, flush, scr, GLK_THREADS);
+      else gl_pix_image_bwd<GlF2, NV, F>(P, s_der, x, y, gs, no_deflection != 0, flush, scr, GLK_THREADS);
       after_batch();
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -589,6 +591,7 @@ struct gl_plan {
   bool has_epl = false;
   int feat_idx = 3;
   int epl_batch_max = 0;
+  int straight_line = 1;     // benchmark-shape programs run the straight-line pixel drivers (0 = interpreter, for A/B)
   int row_flush = 1;         // packed adjoint kernels: staged shared-memory flush (0 = warp butterfly per profile, for A/B)
   // static inputs
   float* d_grid_x = nullptr; float* d_grid_y = nullptr;
@@ -933,6 +936,7 @@ int gl_plan_set_option(gl_plan* p, const char* name, int32_t value) {
   if (!strcmp(name, "epl_batch_max")) { p->epl_batch_max = value; return 0; }
   if (!strcmp(name, "row_flush")) { p->row_flush = value; return 0; }
   if (!strcmp(name, "conv_tma")) { p->conv_tma = value; return 0; }
+  if (!strcmp(name, "straight_line")) { p->straight_line = value; return 0; }
   if (!strcmp(name, "epl_tol_exp10")) {   // EPL series terms below 10^-value are dropped (12 = the reference's constant, epl.py:37)
     if (value < 6 || value > 30) return gl_fail("gl_plan_set_option: epl_tol_exp10 must be in [6, 30]");
     p->prog.epl_tol = powf(10.f, -(float)value); return 0;
@@ -1095,7 +1099,11 @@ static int gl_run_raytrace_fwd(gl_plan* p, float* ss_out, int no_deflection, cud
   GL_CUDA(cudaMemsetAsync(p->d_nan, 0, (size_t)p->bs * sizeof(int), st));
   const size_t smem = (size_t)p->prog.der_total * sizeof(float);
   if ((p->feat_idx == 0 || p->feat_idx == 2) && (p->npix % 2) == 0 && p->use_packed) {   // two pixels per lane slot (FFMA2)
-    if (p->feat_idx == 0) {
+    if (p->feat_idx == 0 && p->straight_line && !no_deflection && gl_is_benchmark_shape(p->prog)) {
+      if (smem > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_fwd_p<4, GL_FS0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_raytrace_fwd_p<4, GL_FS0, true><<<grid, GLK_THREADS, smem, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,
+                                                                         p->d_derived, no_deflection, ss_out, p->d_nan);
+    } else if (p->feat_idx == 0) {
       if (smem > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_fwd_p<4, GL_FS0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k_raytrace_fwd_p<4, GL_FS0><<<grid, GLK_THREADS, smem, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,
                                                                    p->d_derived, no_deflection, ss_out, p->d_nan);
@@ -1139,6 +1147,11 @@ static int gl_run_raytrace_bwd(gl_plan* p, float* gss, int no_deflection, cudaSt
       k_raytrace_bwd_p<4, FS, ROWS><<<grid, GLK_THREADS, (SM), st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,        \
                                                                    p->d_derived, no_deflection, gss, p->d_gpart, p->d_nan); \
     }
+    if (p->feat_idx == 0 && rows && p->straight_line && !no_deflection && gl_is_benchmark_shape(p->prog)) {
+      if (smem_rows > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_bwd_p<4, GL_FS0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
+      k_raytrace_bwd_p<4, GL_FS0, true, true><<<grid, GLK_THREADS, smem_rows, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,
+                                                                                  p->d_derived, no_deflection, gss, p->d_gpart, p->d_nan);
+    } else
     if (p->feat_idx == 0) { if (rows) GL_BWD_P(GL_FS0, true, smem_rows) else GL_BWD_P(GL_FS0, false, smem) }
     else { if (rows) GL_BWD_P(GL_FS2, true, smem_rows) else GL_BWD_P(GL_FS2, false, smem) }
 #undef GL_BWD_P

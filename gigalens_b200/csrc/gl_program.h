@@ -348,6 +348,59 @@ GL_HD void gl_pix_image_bwd(const GlProgram& P, const typename gl_scalar_of<T>::
 }
 
 // ---------------------------------------------------------------------------------------------
+// Straight-line drivers for the GIGA-Lens benchmark shape (tf-demo.ipynb / BASELINE configs[1]):
+//   lenses [EPL, Shear], lens light [Sersic | SersicEllipse], source light [Sersic | SersicEllipse].
+// Same building blocks and the same order of floating-point operations as the interpreting drivers above, but no
+// profile loop, no type switch and compile-time flush widths, so the whole pixel body is a few large basic blocks
+// the scheduler can interleave (the interpreter's loop control, cotangent zeroing and descriptor loads were ~10 % of
+// the adjoint kernel's instructions).  Every other program runs the interpreter.
+// ---------------------------------------------------------------------------------------------
+GL_HD bool gl_is_benchmark_shape(const GlProgram& P) {
+  auto ser = [](int t) { return t == GLT_SERSIC || t == GLT_SERSIC_ELLIPSE; };
+  return P.n_lens == 2 && P.n_ll == 1 && P.n_sl == 1 && P.prof[0].type == GLT_EPL && P.prof[0].n_members == 0 &&
+         P.prof[1].type == GLT_SHEAR && P.prof[1].n_members == 0 && ser(P.prof[2].type) && ser(P.prof[3].type) &&
+         P.comp_mask == 3 && P.scr_prof == 0;
+}
+template <class T, int NP>
+GL_HD void gl_pix_image_bs(const GlProgram& P, const typename gl_scalar_of<T>::type* der, const T* x, const T* y, T* out) {
+  T ax[NP], ay[NP], sx[NP], sy[NP], bx[NP], by[NP];
+  epl_fwd<T, NP>(der + P.prof[0].der_off, P.prof[0].ts, x, y, ax, ay);
+  shear_fwd<T, NP>(der + P.prof[1].der_off, x, y, sx, sy);
+#pragma unroll
+  for (int j = 0; j < NP; ++j) { bx[j] = (x[j] - ax[j]) - sx[j]; by[j] = (y[j] - ay[j]) - sy[j]; out[j] = T(0); }
+  sersic_fwd<T, NP>(der + P.prof[2].der_off, x, y, out);
+  sersic_fwd<T, NP>(der + P.prof[3].der_off, bx, by, out);
+}
+template <class T, int NP, class Flush>
+GL_HD void gl_pix_image_bwd_bs(const GlProgram& P, const typename gl_scalar_of<T>::type* der, const T* x, const T* y, const T* gS,
+                               Flush& flush, T* scr, int scr_stride) {
+  T ax[NP], ay[NP], sx[NP], sy[NP], bx[NP], by[NP], Gx[NP], Gy[NP];
+  epl_fwd_save<T, NP>(der + P.prof[0].der_off, P.prof[0].ts, x, y, ax, ay, scr, scr_stride);
+  shear_fwd<T, NP>(der + P.prof[1].der_off, x, y, sx, sy);
+#pragma unroll
+  for (int j = 0; j < NP; ++j) { bx[j] = (x[j] - ax[j]) - sx[j]; by[j] = (y[j] - ay[j]) - sy[j]; Gx[j] = T(0); Gy[j] = T(0); }
+  T acc[GL_MAX_DVARS];
+#pragma unroll
+  for (int k = 0; k < GL_MAX_DVARS; ++k) acc[k] = T(0);
+  sersic_bwd<T, NP>(der + P.prof[2].der_off, x, y, gS, acc, (T*)nullptr, (T*)nullptr);
+  flush(acc, 8, P.prof[2].g_off);
+#pragma unroll
+  for (int k = 0; k < GL_MAX_DVARS; ++k) acc[k] = T(0);
+  sersic_bwd<T, NP>(der + P.prof[3].der_off, bx, by, gS, acc, Gx, Gy);
+  flush(acc, 8, P.prof[3].g_off);
+#pragma unroll
+  for (int j = 0; j < NP; ++j) { Gx[j] = -Gx[j]; Gy[j] = -Gy[j]; }
+#pragma unroll
+  for (int k = 0; k < GL_MAX_DVARS; ++k) acc[k] = T(0);
+  epl_bwd_load<T, NP>(der + P.prof[0].der_off, P.prof[0].ts, x, y, Gx, Gy, acc, scr, scr_stride);
+  flush(acc, 8, P.prof[0].g_off);
+#pragma unroll
+  for (int k = 0; k < GL_MAX_DVARS; ++k) acc[k] = T(0);
+  shear_bwd<T, NP>(der + P.prof[1].der_off, x, y, Gx, Gy, acc);
+  flush(acc, 2, P.prof[1].g_off);
+}
+
+// ---------------------------------------------------------------------------------------------
 // image-position likelihood (ForwardProbModel.stats_positions, src/gigalens/tf/model.py:103-124):
 // point drivers on the forward-mode lane type GlDual.  Tens of points per sample -- not a hot path,
 // but it needs d(beta)/d(theta) (the lensing Hessian, LensSimulator.magnification,

@@ -145,8 +145,9 @@ def host_positions(cm: CompiledModel, mat, systems, dtype=np.float64, use_fwdmod
     return dict(beta=beta, hess=hess, loglike=ll, chi2=chi2, gparams=gparams)
 
 
-def host_run_packed(cm: CompiledModel, mat, gx, gy, g_ss=None):
-    """Same as host_run(dtype=float32) but through the two-pixel packed lane type (GlF2)."""
+def host_run_packed(cm: CompiledModel, mat, gx, gy, g_ss=None, straight_line=False):
+    """Same as host_run(dtype=float32) but through the two-pixel packed lane type (GlF2); ``straight_line`` runs the
+    benchmark-shape drivers (gl_pix_image_bs / gl_pix_image_bwd_bs) instead of the interpreter."""
     lib = hostcheck_lib()
     mat = np.ascontiguousarray(mat, dtype=np.float32)
     P, bs = mat.shape
@@ -157,7 +158,7 @@ def host_run_packed(cm: CompiledModel, mat, gx, gy, g_ss=None):
     gparams = np.zeros((P, bs), dtype=np.float32) if g_ss is not None else None
     g_ss_c = np.ascontiguousarray(g_ss, dtype=np.float32) if g_ss is not None else None
     vp = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
-    rc = lib.glh_run_f32x2(C.byref(cm.desc), C.c_int(bs), vp(mat), C.c_int(npix), vp(gx), vp(gy), vp(ss), vp(g_ss_c), vp(gparams))
+    rc = (lib.glh_run_f32x2_bs if straight_line else lib.glh_run_f32x2)(C.byref(cm.desc), C.c_int(bs), vp(mat), C.c_int(npix), vp(gx), vp(gy), vp(ss), vp(g_ss_c), vp(gparams))
     if rc != 0:
         raise RuntimeError(lib.glh_last_error().decode())
     return dict(ss=ss, gparams=gparams)

@@ -86,7 +86,7 @@ struct HostFlush2 {
   void operator()(const GlF2* acc, int n, int off) { for (int k = 0; k < n; ++k) g[off + k] += acc[k].x + acc[k].y; }
 };
 static int run_packed(const gl_model_desc* m, int bs, const float* params, int npix, const float* gx, const float* gy,
-                      float* ss_out, const float* g_ss, float* gparams) {
+                      float* ss_out, const float* g_ss, float* gparams, int straight_line = 0) {
   constexpr unsigned F = GLF_EPL | GLF_SHEAR | GLF_SERSIC | GLF_NFW | GLF_DPIE;   // union of the packed kernels' feature sets
   GlBuilt B;
   std::string e = gl_build_program(m, B);
@@ -95,6 +95,7 @@ static int run_packed(const gl_model_desc* m, int bs, const float* params, int n
   for (int i = 0; i < P.n_prof; ++i)
     if ((gl_feature_of(P.prof[i].type) & F) == 0) { g_err = "packed lanes: unsupported profile"; return 1; }
   if (npix % 2) { g_err = "packed lanes need an even pixel count"; return 1; }
+  if (straight_line && !gl_is_benchmark_shape(P)) { g_err = "straight-line drivers: not the benchmark-shape program"; return 1; }
   const float* mf = B.member_factor.empty() ? nullptr : B.member_factor.data();
   std::vector<float> der(P.der_total), g(P.g_total > 0 ? P.g_total : 1);
   for (int b = 0; b < bs; ++b) {
@@ -104,14 +105,16 @@ static int run_packed(const gl_model_desc* m, int bs, const float* params, int n
     for (int p = 0; p < npix; p += 2) {
       GlF2 x[1] = {GlF2(gx[p], gx[p + 1])}, y[1] = {GlF2(gy[p], gy[p + 1])}, v[1];
       if (ss_out) {
-        gl_pix_image<GlF2, 1, F>(P, der.data(), x, y, false, v);
+        if (straight_line) gl_pix_image_bs<GlF2, 1>(P, der.data(), x, y, v);
+        else gl_pix_image<GlF2, 1, F>(P, der.data(), x, y, false, v);
         ss_out[(size_t)b * npix + p] = (v[0].x != v[0].x) ? 0.f : v[0].x;
         ss_out[(size_t)b * npix + p + 1] = (v[0].y != v[0].y) ? 0.f : v[0].y;
       }
       if (g_ss && gparams) {
         GlF2 gs[1] = {GlF2(g_ss[(size_t)b * npix + p], g_ss[(size_t)b * npix + p + 1])};
         GlF2 scr[GL_EPL_NSTATE];
-        gl_pix_image_bwd<GlF2, 1, F>(P, der.data(), x, y, gs, false, fl, scr, 1);
+        if (straight_line) gl_pix_image_bwd_bs<GlF2, 1>(P, der.data(), x, y, gs, fl, scr, 1);
+        else gl_pix_image_bwd<GlF2, 1, F>(P, der.data(), x, y, gs, false, fl, scr, 1);
       }
     }
     if (g_ss && gparams) gl_sample_prep_bwd<float, float>(P, params, bs, b, mf, nullptr, der.data(), g.data(), gparams);
@@ -176,6 +179,11 @@ extern "C" {
 int glh_run_f32x2(const gl_model_desc* m, int bs, const float* params, int npix, const float* gx, const float* gy,
                   float* ss_out, const float* g_ss, float* gparams) {
   return run_packed(m, bs, params, npix, gx, gy, ss_out, g_ss, gparams);
+}
+// the straight-line drivers of the benchmark-shape program (gl_pix_image_bs / gl_pix_image_bwd_bs), packed lanes
+int glh_run_f32x2_bs(const gl_model_desc* m, int bs, const float* params, int npix, const float* gx, const float* gy,
+                     float* ss_out, const float* g_ss, float* gparams) {
+  return run_packed(m, bs, params, npix, gx, gy, ss_out, g_ss, gparams, 1);
 }
 const char* glh_last_error() { return g_err.c_str(); }
 int glh_depth(const gl_model_desc* m) { GlBuilt B; std::string e = gl_build_program(m, B); if (!e.empty()) { g_err = e; return -1; } return B.prog.depth; }

@@ -713,3 +713,11 @@ def test_epl_series_tolerance_default_matches_reference_count():
         assert np.max(np.abs(a[0] - ref[0]) / np.abs(ref[0])) < 2e-7
         scale = np.max(np.abs(ref[2]), axis=0)
         assert np.max(np.max(np.abs(a[2] - ref[2]), axis=0) / scale) < 5e-6
+
+
+def test_straight_line_drivers_are_bit_identical_to_the_interpreter():
+    """Benchmark-shape programs run gl_pix_image_bs / gl_pix_image_bwd_bs (no profile loop); same blocks, same order."""
+    a = _c2_logprob(192, {"straight_line": 1})
+    b = _c2_logprob(192, {"straight_line": 0})
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)

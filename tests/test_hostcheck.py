@@ -136,6 +136,9 @@ def test_packed_lane_instantiation_matches_scalar(name):
         sc = np.max(np.abs(g64[k]))
         assert np.max(np.abs(a["gparams"][k] - b["gparams"][k])) <= 2e-5 * sc, cm.slot_keys[k]
         assert np.max(np.abs(b["gparams"][k] - g64[k])) <= max(1e-4, 10 * np.max(np.abs(a["gparams"][k] - g64[k]))) * sc
+    if name == "c2":   # the straight-line drivers of the benchmark shape: same blocks, same operation order => identical
+        c = common.host_run_packed(cm, mat, gx, gy, g_ss=G, straight_line=True)
+        assert np.array_equal(b["ss"], c["ss"]) and np.array_equal(b["gparams"], c["gparams"])
 
 
 # ---------------------------------------------------------------------------------------------
