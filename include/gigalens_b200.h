@@ -137,7 +137,9 @@ int gl_plan_set_positions(gl_plan* plan, int32_t n_systems, const int32_t* n_ima
  * "row_flush" = 0: the packed adjoint kernels reduce dvar cotangents with a warp butterfly per profile
  * instead of the staged shared-memory transposition (A/B measurement aid; results agree to fp32
  * summation order).  "conv_tma" = 0: the conv kernels stage their tiles with cp.async / plain stores
- * instead of TMA (A/B; bit-identical results).
+ * instead of TMA (A/B; bit-identical results).  "straight_line" = 0: programs of the benchmark shape
+ * (lenses [EPL, Shear], one Sersic(Ellipse) lens light, one Sersic(Ellipse) source) run the interpreting
+ * pixel drivers like every other program instead of the straight-line ones (A/B; bit-identical results).
  * "no_deflection" = 1: evaluate source light at the image-plane position (simulate(..., no_deflection=True),
  * tf/simulator.py:125-126).  "components" = 1 | 2 | 3: gl_simulate adds only the lens light / only the
  * source light / both (simulate_lens_light, simulate_images, simulate_source: tf/simulator.py:242-328).
