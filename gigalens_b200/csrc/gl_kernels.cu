@@ -218,6 +218,9 @@ __global__ void k_sample_bwd(GlProgram P, int bs, const float* __restrict__ para
 // thread per batch for ILP, per-sample derived constants staged in shared memory.
 //   grid = (chunks, bs); a CTA walks pixel batches  chunk, chunk + chunks, ...
 // ---------------------------------------------------------------------------------------------
+// Dynamic shared memory above 48 KB needs cudaFuncAttributeMaxDynamicSharedMemorySize; the limit applies to static +
+// dynamic bytes, and the kernels carry up to ~1 KB of static shared memory (reduction scratch, mbarriers), so every
+// launch opts in from 40 KB of dynamic shared memory upwards (a 48.4 KB tile + 1 KB static used to fail to launch).
 #define GLK_THREADS 256
 // shared-memory layout of the adjoint ray-tracing kernels (floats): [der_total][nwarps * g_total][series scratch]
 //   accumulators: one row of g_total floats per warp, or (rows = true, packed kernels) a g_total x 33 staging tile per warp
@@ -1086,7 +1089,7 @@ static int gl_run_positions(gl_plan* p, const float* params, float* loglike, flo
   const size_t smem = sizeof(double) * ((size_t)p->prog.der_total + 12 * (size_t)p->pos_npts + 2 * (size_t)p->pos_nsys +
                                         (size_t)(GLP_THREADS + 1) * p->prog.g_total);
   if (smem > 200 * 1024) return gl_fail("gl_run_positions: model too large for the positions kernel's shared memory");
-  if (smem > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_positions, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 40 * 1024) GL_CUDA(cudaFuncSetAttribute(k_positions, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_positions<<<p->bs, GLP_THREADS, smem, st>>>(p->prog, p->bs, params, p->d_member_factor, p->d_amp_slot, p->pos_npts, p->pos_nsys,
                                                 p->d_pos_off, p->d_pos_x, p->d_pos_y, p->d_pos_ex, p->d_pos_ey, p->pos_n_position,
                                                 loglike, red_chi2, dparams);
@@ -1100,15 +1103,15 @@ static int gl_run_raytrace_fwd(gl_plan* p, float* ss_out, int no_deflection, cud
   const size_t smem = (size_t)p->prog.der_total * sizeof(float);
   if ((p->feat_idx == 0 || p->feat_idx == 2) && (p->npix % 2) == 0 && p->use_packed) {   // two pixels per lane slot (FFMA2)
     if (p->feat_idx == 0 && p->straight_line && !no_deflection && gl_is_benchmark_shape(p->prog)) {
-      if (smem > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_fwd_p<4, GL_FS0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      if (smem > 40 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_fwd_p<4, GL_FS0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k_raytrace_fwd_p<4, GL_FS0, true><<<grid, GLK_THREADS, smem, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,
                                                                          p->d_derived, no_deflection, ss_out, p->d_nan);
     } else if (p->feat_idx == 0) {
-      if (smem > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_fwd_p<4, GL_FS0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      if (smem > 40 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_fwd_p<4, GL_FS0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k_raytrace_fwd_p<4, GL_FS0><<<grid, GLK_THREADS, smem, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,
                                                                    p->d_derived, no_deflection, ss_out, p->d_nan);
     } else {
-      if (smem > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_fwd_p<4, GL_FS2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      if (smem > 40 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_fwd_p<4, GL_FS2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k_raytrace_fwd_p<4, GL_FS2><<<grid, GLK_THREADS, smem, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,
                                                                    p->d_derived, no_deflection, ss_out, p->d_nan);
     }
@@ -1116,7 +1119,7 @@ static int gl_run_raytrace_fwd(gl_plan* p, float* ss_out, int no_deflection, cud
     return 0;
   }
   GL_FEAT_DISPATCH(p->feat_idx, {
-    if (smem > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_fwd<4, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 40 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_fwd<4, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_raytrace_fwd<4, F><<<grid, GLK_THREADS, smem, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask, p->d_derived,
                                                           no_deflection, ss_out, p->d_nan);
   })
@@ -1129,7 +1132,7 @@ static int gl_run_raytrace_bwd(gl_plan* p, float* gss, int no_deflection, cudaSt
   {   // NaN-scrubbed pixels pass no gradient: exits immediately for samples without any (nan_count from the forward pass)
     const size_t smem_m = (size_t)p->prog.der_total * sizeof(float);
     GL_FEAT_DISPATCH(p->feat_idx, {
-      if (smem_m > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_nan_cotangent_mask<4, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m));
+      if (smem_m > 40 * 1024) GL_CUDA(cudaFuncSetAttribute(k_nan_cotangent_mask<4, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m));
       k_nan_cotangent_mask<4, F><<<dim3(1, p->bs), GLK_THREADS, smem_m, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_derived,
                                                                    no_deflection, gss, p->d_nan);
     })
@@ -1143,12 +1146,12 @@ static int gl_run_raytrace_bwd(gl_plan* p, float* gss, int no_deflection, cudaSt
     const bool rows = p->row_flush && smem_rows <= 108 * 1024 && p->prog.g_total <= 64;
 #define GL_BWD_P(FS, ROWS, SM)                                                                                              \
     {                                                                                                                       \
-      if ((SM) > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_bwd_p<4, FS, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM))); \
+      if ((SM) > 40 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_bwd_p<4, FS, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM))); \
       k_raytrace_bwd_p<4, FS, ROWS><<<grid, GLK_THREADS, (SM), st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,        \
                                                                    p->d_derived, no_deflection, gss, p->d_gpart, p->d_nan); \
     }
     if (p->feat_idx == 0 && rows && p->straight_line && !no_deflection && gl_is_benchmark_shape(p->prog)) {
-      if (smem_rows > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_bwd_p<4, GL_FS0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
+      if (smem_rows > 40 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_bwd_p<4, GL_FS0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
       k_raytrace_bwd_p<4, GL_FS0, true, true><<<grid, GLK_THREADS, smem_rows, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,
                                                                                   p->d_derived, no_deflection, gss, p->d_gpart, p->d_nan);
     } else
@@ -1159,7 +1162,7 @@ static int gl_run_raytrace_bwd(gl_plan* p, float* gss, int no_deflection, cudaSt
     return 0;
   }
   GL_FEAT_DISPATCH(p->feat_idx, {
-    if (smem > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_bwd<4, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 40 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_bwd<4, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_raytrace_bwd<4, F><<<grid, GLK_THREADS, smem, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask, p->d_derived,
                                                           no_deflection, gss, p->d_gpart, p->d_nan);
   })
@@ -1208,7 +1211,7 @@ static int gl_launch_conv_fwd_A(gl_plan* p, const float* ss, float scale, float*
       p->tmap_f_base = ss; p->tmap_f_nimg = nimg;
     }
     if (p->tmap_f_ok) {
-      if (p->smem_cf_tma > 48 * 1024)
+      if (p->smem_cf_tma > 40 * 1024)
         GL_CUDA(cudaFuncSetAttribute(k_conv_fwd_tma<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cf_tma));
       k_conv_fwd_tma<A><<<grid, p->conv_threads_f, p->smem_cf_tma, st>>>(p->tmap_f, p->gf, p->d_wf, scale, img, la,
                                                                         like ? p->d_like_part : nullptr, gimg);
@@ -1216,7 +1219,7 @@ static int gl_launch_conv_fwd_A(gl_plan* p, const float* ss, float scale, float*
       return 0;
     }
   }
-  if (p->smem_cf > 48 * 1024)
+  if (p->smem_cf > 40 * 1024)
     GL_CUDA(cudaFuncSetAttribute(k_conv_fwd<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cf));
   k_conv_fwd<A><<<grid, p->conv_threads_f, p->smem_cf, st>>>(p->gf, ss, p->d_wf, scale, img, la, like ? p->d_like_part : nullptr, gimg);
   GL_LAUNCH_CHECK("k_conv_fwd");
@@ -1233,14 +1236,14 @@ static int gl_launch_conv_bwd_A(gl_plan* p, const float* gimg, float scale, floa
       p->tmap_bi_base = gimg; p->tmap_bo_base = gss; p->tmap_b_nimg = nimg;
     }
     if (p->tmap_b_ok) {
-      if (p->smem_cb_tma > 48 * 1024)
+      if (p->smem_cb_tma > 40 * 1024)
         GL_CUDA(cudaFuncSetAttribute(k_conv_bwd_tma<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cb_tma));
       k_conv_bwd_tma<A><<<grid, p->conv_threads_b, p->smem_cb_tma, st>>>(p->tmap_bi, p->tmap_bo, p->gb, p->d_wb, scale);
       GL_LAUNCH_CHECK("k_conv_bwd_tma");
       return 0;
     }
   }
-  if (p->smem_cb > 48 * 1024)
+  if (p->smem_cb > 40 * 1024)
     GL_CUDA(cudaFuncSetAttribute(k_conv_bwd<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cb));
   k_conv_bwd<A><<<grid, p->conv_threads_b, p->smem_cb, st>>>(p->gb, gimg, p->d_wb, scale, nullptr, gss);
   GL_LAUNCH_CHECK("k_conv_bwd");
@@ -1326,7 +1329,7 @@ int gl_hessian(gl_plan* p, const float* params_dev, int32_t npts, const float* x
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = (size_t)p->prog.der_total * sizeof(double);
   if (smem > 200 * 1024) return gl_fail("gl_hessian: model too large");
-  if (smem > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_hessian, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 40 * 1024) GL_CUDA(cudaFuncSetAttribute(k_hessian, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((npts + 127) / 128 > 64 ? 64 : (npts + 127) / 128, p->bs);
   k_hessian<<<grid, 128, smem, st>>>(p->prog, p->bs, params_dev, p->d_member_factor, p->d_amp_slot, npts, x_dev, y_dev, fxx, fxy, fyx, fyy);
   GL_LAUNCH_CHECK("k_hessian");
@@ -1500,13 +1503,13 @@ static int gl_lstsq_forward(gl_plan* p, const float* params, float* image, float
   if (gl_run_prep(p, params, st)) return 1;
   const size_t smem_der = (size_t)p->prog.der_total * sizeof(float);
   GL_FEAT_DISPATCH(p->feat_idx, {
-    if (smem_der > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_comps<4, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_der));
+    if (smem_der > 40 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_comps<4, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_der));
   })
   const int nt = (D + 1 + 3) / 4;
   const size_t smem_gram = (size_t)GLL_PT * nt * 4 * sizeof(float);
   const int npair = ((D + 1) & ~1) / 2;
   const size_t smem_solve = (size_t)(2 * D * (D | 1) + 2 * (npair + 1)) * sizeof(double) + (size_t)(2 * (npair + 1) + 2) * sizeof(int) + 4 * sizeof(double);
-  if (smem_solve > 48 * 1024) GL_CUDA(cudaFuncSetAttribute(k_pinv_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve));
+  if (smem_solve > 40 * 1024) GL_CUDA(cudaFuncSetAttribute(k_pinv_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve));
   for (int b0 = 0; b0 < p->bs; b0 += p->lq_chunk) {
     const int nb = (p->bs - b0 < p->lq_chunk) ? p->bs - b0 : p->lq_chunk;
     dim3 grid(p->chunks, nb);

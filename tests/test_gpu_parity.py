@@ -721,3 +721,32 @@ def test_straight_line_drivers_are_bit_identical_to_the_interpreter():
     b = _c2_logprob(192, {"straight_line": 0})
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("num_pix,K,ss", [(12, 3, 1), (20, 9, 2), (36, 5, 3), (36, 21, 2), (64, 9, 2), (20, 13, 4)])
+def test_conv_geometries_match_oracle(num_pix, K, ss):
+    """PSF conv / pooling / likelihood over image sizes, PSF sizes and supersampling factors (tile shapes, tap-count
+    instances, TMA and cp.async staging, the >48 KB shared-memory opt-in) against the fp64 oracle."""
+    wl = dict(workloads.c2_workload())
+    rng = np.random.default_rng(num_pix * 100 + K)
+    g = np.exp(-0.5 * (np.arange(K) - K // 2) ** 2 / (0.15 * K + 0.5) ** 2)
+    psf = np.outer(g, g) * (1 + 0.05 * rng.standard_normal((K, K)))
+    psf = (psf / psf.sum()).astype(np.float32)
+    wl["sim_config"] = SimulatorConfig(delta_pix=3.9 / num_pix, num_pix=num_pix, supersample=ss, kernel=psf)
+    wl["observed"] = rng.normal(1.0, 0.3, (num_pix, num_pix))
+    bs = 4
+    sim = LensSimulator(wl["phys_model"], wl["sim_config"], bs=bs)
+    pmod = ForwardProbModel(wl["prior"], wl["observed"], background_rms=0.2, exp_time=100.0)
+    cm = sim.compiled
+    mat = cm.flatten(wl["prior"].sample(bs, seed=4), bs, torch, "cpu").numpy()
+    dev = torch.as_tensor(mat, device="cuda")
+    img = sim.simulate(dev).cpu().numpy().reshape(bs, num_pix, num_pix)
+    ll, chi2, grad = (t.cpu().numpy() for t in pmod.loglike_and_grad(sim, dev))
+    ll32, chi32, im32, g32 = oracle_bridge.loglike_and_grad_matrix(wl, cm, mat, torch.float32)
+    ll64, chi64, im64, g64 = oracle_bridge.loglike_and_grad_matrix(wl, cm, mat.astype(np.float64), torch.float64)
+    llp, chip, imp, gp = oracle_bridge.loglike_and_grad_matrix(wl, cm, common.ulp_perturb(mat), torch.float64)
+    im32, im64, imp = (v.reshape(bs, num_pix, num_pix) for v in (im32, im64, imp))
+    assert_parity(img, im32, im64, 1e-5, "image", imp, axis=(1, 2))
+    assert_parity(ll[:, None], ll32[:, None], ll64[:, None], 1e-5, "log-like", llp[:, None], axis=1)
+    for k in range(cm.n_params):
+        assert_parity(grad[k], g32[k], g64[k], 1e-4, f"grad {cm.slot_keys[k]}", gp[k])
