@@ -1069,7 +1069,7 @@ int gl_plan_set_prior(gl_plan* p, const gl_prior_leaf* leaves, int32_t n_leaves)
 // launch helpers
 // ---------------------------------------------------------------------------------------------
 static int gl_run_prep(gl_plan* p, const float* params, cudaStream_t st) {
-  const int tb = 128, gb = (p->bs + tb - 1) / tb;
+  const int tb = 32, gb = (p->bs + tb - 1) / tb;   // one warp per CTA: a batch of a few thousand samples spreads over all SMs
   const float* fmax = nullptr;
   if (p->has_epl && p->epl_batch_max) {
     GL_CUDA(cudaMemsetAsync(p->d_fmax, 0, GL_MAX_PROF * sizeof(float), st));
@@ -1372,7 +1372,7 @@ static int gl_loglike_core(gl_plan* p, const float* params, float* loglike, floa
   }
   GL_TM(p, st, 6);
   if (pos && gl_run_positions(p, params, p->d_pos_ll, p->d_pos_chi, grad ? p->d_pos_grad : nullptr, st)) return 1;
-  const int tb = 128, gb = (p->bs + tb - 1) / tb;
+  const int tb = 32, gb = (p->bs + tb - 1) / tb;   // one warp per CTA: a batch of a few thousand samples spreads over all SMs
   k_sample_bwd<<<gb, tb, 0, st>>>(p->prog, p->bs, params, p->d_member_factor, p->d_amp_slot, p->d_derived, p->d_gpart, p->chunks, p->d_gsum,
                                   p->d_like_part, p->gf.tiles_x * p->gf.tiles_y, p->n_pix_used, loglike, red_chi2, dparams,
                                   p->d, p->d_leaves, z, z ? p->d_logprior : nullptr, logp, dz, pix ? 1 : 0,
@@ -1414,7 +1414,7 @@ int gl_unconstrain(gl_plan* p, const float* z_dev, float* params_dev, float* log
   if (!p || !z_dev) return gl_fail("gl_unconstrain: NULL argument");
   if (!p->d_leaves) return gl_fail("gl_unconstrain: gl_plan_set_prior was never called");
   GL_CUDA(cudaSetDevice(p->device));
-  const int tb = 128, gb = (p->bs + tb - 1) / tb;
+  const int tb = 32, gb = (p->bs + tb - 1) / tb;   // one warp per CTA: a batch of a few thousand samples spreads over all SMs
   k_unconstrain<<<gb, tb, 0, (cudaStream_t)stream>>>(p->bs, p->d, p->d_leaves, z_dev, params_dev, logprior_dev);
   GL_LAUNCH_CHECK("k_unconstrain");
   return 0;
@@ -1426,7 +1426,7 @@ int gl_chain_grad(gl_plan* p, const float* z_dev, const float* dparams_dev, int3
   if (!p || !z_dev || !dz_dev) return gl_fail("gl_chain_grad: NULL argument");
   if (!p->d_leaves) return gl_fail("gl_chain_grad: gl_plan_set_prior was never called");
   GL_CUDA(cudaSetDevice(p->device));
-  const int tb = 128, gb = (p->bs + tb - 1) / tb;
+  const int tb = 32, gb = (p->bs + tb - 1) / tb;   // one warp per CTA: a batch of a few thousand samples spreads over all SMs
   k_chain_grad<<<gb, tb, 0, (cudaStream_t)stream>>>(p->bs, p->d, p->d_leaves, z_dev, dparams_dev, with_prior, logprior_dev, dz_dev);
   GL_LAUNCH_CHECK("k_chain_grad");
   return 0;
@@ -1437,7 +1437,7 @@ int gl_logprob_grad(gl_plan* p, const float* z_dev, float* logp_dev, float* red_
   if (!p->d_leaves) return gl_fail("gl_logprob_grad: gl_plan_set_prior was never called");
   GL_CUDA(cudaSetDevice(p->device));
   cudaStream_t st = (cudaStream_t)stream;
-  const int tb = 128, gb = (p->bs + tb - 1) / tb;
+  const int tb = 32, gb = (p->bs + tb - 1) / tb;   // one warp per CTA: a batch of a few thousand samples spreads over all SMs
   GL_TM(p, st, 0);
   p->tm_have0 = 1;
   k_unconstrain<<<gb, tb, 0, st>>>(p->bs, p->d, p->d_leaves, z_dev, p->d_params, p->d_logprior);
@@ -1552,7 +1552,7 @@ static int gl_lstsq_loglike_core(gl_plan* p, const float* params, float* loglike
   float* chi = red_chi2 ? red_chi2 : p->d_ll + p->bs;
   const bool grad = dparams != nullptr;
   if (gl_lstsq_forward(p, params, nullptr, nullptr, ll, chi, grad, st)) return 1;
-  const int tb = 128, gb = (p->bs + tb - 1) / tb;
+  const int tb = 32, gb = (p->bs + tb - 1) / tb;   // one warp per CTA: a batch of a few thousand samples spreads over all SMs
   if (grad) {
     k_patch_amps<<<gb, tb, 0, st>>>(p->prog, p->bs, p->d_coef, p->d_derived);
     GL_LAUNCH_CHECK("k_patch_amps");
