@@ -222,3 +222,77 @@ def test_hessian_golden_through_the_device_arithmetic():
     assert np.max(np.abs(H - g["hessian_truth"])) < 2e-7
     mu = 1.0 / ((1 - H[0]) * (1 - H[3]) - H[1] * H[2])
     assert np.allclose(mu, g["magnification_truth"], rtol=5e-6)
+
+
+# ---------------------------------------------------------------------------------------------
+# Independent pins (no reference code involved): closed forms from the literature evaluated with scipy,
+# and the two identities every lensing deflection obeys -- alpha is a gradient (curl-free) and its
+# divergence is twice the convergence.
+# ---------------------------------------------------------------------------------------------
+def test_epl_series_matches_hypergeometric_closed_form():
+    """Tessore & Metcalf (2015) eq. 13: in the frame of the ellipse, with R = sqrt(q^2 x^2 + y^2), phi = atan2(y, q x),
+    alpha = 2b/(1+q) (b/R)^(t-1) e^{i phi} 2F1(1, t/2; 2 - t/2; -f e^{2 i phi}),  f = (1-q)/(1+q).  scipy's hyp2f1 is an
+    implementation the series of epl.py:39-54 has never seen."""
+    from scipy.special import hyp2f1
+
+    x, y = pts(400, seed=3)
+    for gamma, e1, e2 in [(2.0, 0.15, -0.1), (1.6, -0.2, 0.25), (2.4, 0.05, 0.3), (1.9, 0.0, 0.0)]:
+        kw = dict(theta_E=1.3, gamma=gamma, e1=e1, e2=e2, center_x=0.07, center_y=-0.04)
+        ax, ay = OP.EPL(200).deriv(x, y, **kw)
+        phi_e = 0.5 * math.atan2(e2, e1)
+        c = min(math.hypot(e1, e2), 1.0)
+        q = (1 - c) / (1 + c)
+        b, t, f = 1.3 * math.sqrt(q), gamma - 1.0, (1 - q) / (1 + q)
+        dx, dy = x.numpy() - 0.07, y.numpy() + 0.04
+        xr = dx * math.cos(phi_e) + dy * math.sin(phi_e)
+        yr = -dx * math.sin(phi_e) + dy * math.cos(phi_e)
+        R = np.sqrt((q * xr) ** 2 + yr ** 2)
+        ang = np.arctan2(yr, q * xr)
+        a = 2 * b / (1 + q) * (b / R) ** (t - 1) * np.exp(1j * ang) * hyp2f1(1.0, t / 2, 2 - t / 2, -f * np.exp(2j * ang))
+        a = a * np.exp(1j * phi_e)   # back to the sky frame
+        assert np.max(np.abs(ax.numpy() - a.real)) < 1e-10 and np.max(np.abs(ay.numpy() - a.imag)) < 1e-10
+
+
+def _div_curl(prof, kw, x, y):
+    x = x.clone().requires_grad_(True); y = y.clone().requires_grad_(True)
+    ax, ay = prof.deriv(x, y, **kw)
+    axx, axy = torch.autograd.grad(ax.sum(), [x, y], retain_graph=True)
+    ayx, ayy = torch.autograd.grad(ay.sum(), [x, y])
+    return (axx + ayy).detach().numpy(), (axy - ayx).detach().numpy(), x.detach().numpy(), y.detach().numpy()
+
+
+def test_deflections_are_curl_free_with_the_analytic_convergence():
+    x, y = pts(300, seed=5)
+    x, y = 2.0 * x, 2.0 * y
+    # EPL: kappa = (2 - t)/2 (b / sqrt(q^2 x'^2 + y'^2))^t in the frame of the ellipse (Tessore & Metcalf eq. 1)
+    kw = dict(theta_E=1.1, gamma=2.2, e1=0.2, e2=0.1, center_x=0.0, center_y=0.0)
+    div, curl, xn, yn = _div_curl(OP.EPL(200), kw, x, y)
+    phi_e = 0.5 * math.atan2(0.1, 0.2); c = math.hypot(0.2, 0.1); q = (1 - c) / (1 + c); t = 1.2; b = 1.1 * math.sqrt(q)
+    xr = xn * math.cos(phi_e) + yn * math.sin(phi_e); yr = -xn * math.sin(phi_e) + yn * math.cos(phi_e)
+    kappa = (2 - t) / 2 * (b / np.sqrt((q * xr) ** 2 + yr ** 2)) ** t
+    assert np.max(np.abs(curl)) < 1e-9 and np.max(np.abs(div - 2 * kappa) / (2 * kappa)) < 1e-9
+    # SIE = the gamma = 2 member of the same family
+    kw = dict(theta_E=0.9, e1=-0.15, e2=0.2, center_x=0.1, center_y=0.0)
+    div, curl, xn, yn = _div_curl(OP.SIE(), kw, x, y)
+    phi_e = 0.5 * math.atan2(0.2, -0.15); c = math.hypot(0.15, 0.2); q = (1 - c) / (1 + c); b = 0.9 * math.sqrt(q)
+    dx = xn - 0.1
+    xr = dx * math.cos(phi_e) + yn * math.sin(phi_e); yr = -dx * math.sin(phi_e) + yn * math.cos(phi_e)
+    kappa = 0.5 * b / np.sqrt((q * xr) ** 2 + yr ** 2)
+    assert np.max(np.abs(curl)) < 1e-9 and np.max(np.abs(div - 2 * kappa) / (2 * kappa)) < 1e-8
+    # NFW (Bartelmann 1996): kappa(X) = 2 rho0 Rs (1 - F(X)) / (X^2 - 1), F = acosh(1/X)/sqrt(1-X^2) | acos(1/X)/sqrt(X^2-1),
+    # with rho0 = alpha_Rs / (4 Rs^2 (1 + ln 1/2))  (nfw.py:15-52)
+    Rs, aRs = 1.7, 0.9
+    div, curl, xn, yn = _div_curl(OP.NFW(), dict(Rs=Rs, alpha_Rs=aRs, center_x=0.0, center_y=0.0), x, y)
+    X = np.sqrt(xn ** 2 + yn ** 2) / Rs
+    F = np.where(X < 1, np.arccosh(1 / np.minimum(X, 1 - 1e-12)) / np.sqrt(np.abs(1 - X ** 2)),
+                 np.arccos(1 / np.maximum(X, 1 + 1e-12)) / np.sqrt(np.abs(X ** 2 - 1)))
+    rho0 = aRs / (4 * Rs ** 2 * (1 + math.log(0.5)))
+    kappa = 2 * rho0 * Rs * (1 - F) / (X ** 2 - 1)
+    assert np.max(np.abs(curl)) < 1e-9 and np.max(np.abs(div - 2 * kappa) / np.abs(2 * kappa)) < 1e-7
+    # the elliptical families without a closed-form kappa here: a potential must exist (curl-free)
+    for prof, kw in [(OP.DPIE(), dict(theta_E=1.0, r_core=0.1, r_cut=2.5, e1=0.2, e2=-0.1, center_x=0.0, center_y=0.1)),
+                     (OP.NFW_ELLIPSE(), dict(Rs=1.5, alpha_Rs=1.0, e1=0.1, e2=0.15, center_x=0.0, center_y=0.0)),
+                     (OP.DPIS(), dict(theta_E=1.0, r_core=0.1, r_cut=2.5, center_x=0.0, center_y=0.1))]:
+        div, curl, _, _ = _div_curl(prof, kw, x, y)
+        assert np.max(np.abs(curl)) < 1e-8 * max(1.0, np.max(np.abs(div))), type(prof).__name__
+        assert np.all(div > 0)       # positive surface density everywhere
