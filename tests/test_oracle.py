@@ -296,3 +296,35 @@ def test_deflections_are_curl_free_with_the_analytic_convergence():
         div, curl, _, _ = _div_curl(prof, kw, x, y)
         assert np.max(np.abs(curl)) < 1e-8 * max(1.0, np.max(np.abs(div))), type(prof).__name__
         assert np.all(div > 0)       # positive surface density everywhere
+
+
+def test_sersic_total_flux_matches_the_closed_form():
+    """Integral of I = Ie exp(-bn ((R/Rs)^(1/n) - 1)) over the plane: 2 pi n Rs^2 Ie e^bn bn^(-2n) Gamma(2n) for any axis
+    ratio (the elliptical radius of sersic.py:66-80 is area preserving: x sqrt(q), y / sqrt(q))."""
+    from scipy.special import gamma as Gamma
+
+    for n, e1, e2 in [(1.0, 0.0, 0.0), (2.0, 0.2, -0.1), (0.7, -0.3, 0.2)]:
+        Rs, Ie = 0.4, 3.0
+        bn = 1.9992 * n - 0.3271
+        want = 2 * math.pi * n * Rs ** 2 * Ie * math.exp(bn) * bn ** (-2 * n) * Gamma(2 * n)
+        # polar grid in the stretched frame would hide the ellipticity convention: integrate on a fine Cartesian grid
+        L, N = 14.0, 2801
+        g = torch.linspace(-L, L, N, dtype=D)
+        X, Y = torch.meshgrid(g, g, indexing="xy")
+        I = OP.SersicEllipse().light(X, Y, R_sersic=Rs, n_sersic=n, e1=e1, e2=e2, center_x=0.013, center_y=-0.021, Ie=Ie)
+        got = float(I.sum()) * (2 * L / (N - 1)) ** 2
+        assert abs(got - want) / want < 3e-3, (n, got, want)      # the cusp at R = 0 limits the grid quadrature
+
+
+def test_shapelet_basis_is_orthonormal():
+    """int B_k B_l dx dy = beta^2 delta_kl for the (n1, n2) ordering of shapelets.py:26-46 (Refregier 2003)."""
+    n_max, beta = 4, 0.3
+    sh = OP.Shapelets(n_max, use_lstsq=True, interpolate=False, dtype=D)
+    L, N = 12.0 * beta, 1201
+    g = torch.linspace(-L, L, N, dtype=D)
+    X, Y = torch.meshgrid(g, g, indexing="xy")
+    B = sh.light(X, Y, center_x=0.0, center_y=0.0, beta=beta).reshape(sh.n_layers, -1)
+    G = (B @ B.T).numpy() * (2 * L / (N - 1)) ** 2 / beta ** 2
+    # the reference rounds the normalisation table to fp32 (shapelets.py:47-48): identity to 1e-6
+    assert np.max(np.abs(G - np.eye(sh.n_layers))) < 1e-6
+    assert sorted(zip(sh.N1, sh.N2)) == sorted((a, b) for a in range(n_max + 1) for b in range(n_max + 1 - a))
