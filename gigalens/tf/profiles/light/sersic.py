@@ -1,0 +1,2 @@
+"""``src/gigalens/tf/profiles/light/sersic.py``."""
+from gigalens_b200.profiles.light.sersic import Sersic, SersicEllipse  # noqa: F401

@@ -100,6 +100,7 @@ EXPORTED_SYMBOLS = [
     "gl_loglike_grad", "gl_logprob_grad", "gl_unconstrain", "gl_logprob_grad_host", "gl_simulate_host",
     "gl_lstsq_simulate", "gl_lstsq_loglike_grad", "gl_plan_depth", "gl_plan_set_option", "gl_plan_get_timings",
     "gl_plan_set_positions", "gl_hessian", "gl_positions_loglike_grad", "gl_lstsq_stack", "gl_chain_grad",
+    "gl_plan_reserve_lstsq", "gl_fp32_peak",
 ]
 
 _LIB = None
@@ -150,6 +151,8 @@ def load():
     lib.gl_plan_set_positions.argtypes = [vp, i32, fp, fp, fp, fp, fp]
     lib.gl_hessian.argtypes = [vp, fp, i32, fp, fp, fp, fp, fp, fp, vp]
     lib.gl_positions_loglike_grad.argtypes = [vp, fp, fp, fp, fp, vp]
+    lib.gl_plan_reserve_lstsq.argtypes = [vp, i32]
+    lib.gl_fp32_peak.argtypes = [i32, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     for name in EXPORTED_SYMBOLS:
         if getattr(lib, name).restype is C.c_int:
             getattr(lib, name).restype = C.c_int

@@ -224,7 +224,8 @@ template <int A>
 __global__ void __maxnreg__(96) k_conv_fwd(GlConvGeom g, const float* __restrict__ ss_img, const float* __restrict__ wts,
                                                   float scale, float* __restrict__ img, GlLikeArgs like,
                                                   float* __restrict__ part, float* __restrict__ gimg) {
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float glc_smem_f[];
+  float* smem = glc_smem_f;
   const int nph = g.ss * g.ss;
   const int tile_size = g.in_rows * g.in_pitch;
   float* s_in = smem;                              // [2][in_rows][in_pitch]  double-buffered phase tile
@@ -353,7 +354,8 @@ template <int A>
 __global__ void __maxnreg__(96) k_conv_fwd_tma(const __grid_constant__ CUtensorMap tmap, GlConvGeom g, const float* __restrict__ wts,
                                                float scale, float* __restrict__ img, GlLikeArgs like,
                                                float* __restrict__ part, float* __restrict__ gimg) {
-  extern __shared__ __align__(128) float smem[];
+  extern __shared__ __align__(128) float glc_smem_ft[];
+  float* smem = glc_smem_ft;
   const int nph = g.ss * g.ss;
   const int tstride = g.phase_stride;              // floats per staged tile, a multiple of 32 (128-byte TMA destinations)
   float* s_in = smem;                              // [2][tstride]  double-buffered phase tile
@@ -436,7 +438,8 @@ __global__ void __launch_bounds__(256, 2) k_conv_bwd(GlConvGeom g, const float* 
                                                   float scale, const unsigned char* __restrict__ ss_mask,
                                                   float* __restrict__ gss) {
   (void)ss_mask;
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float glc_smem_b[];
+  float* smem = glc_smem_b;
   const int nph = g.ss * g.ss;
   float* s_in = smem;                                   // [in_rows][in_pitch]  zero-padded dL/d(image)
   float* s_w = smem + g.in_rows * g.in_pitch;           // [nph][A][2][ulen] packed (flipped) tap table
@@ -506,7 +509,8 @@ __global__ void __launch_bounds__(256, 2) k_conv_bwd(GlConvGeom g, const float* 
 template <int A>
 __global__ void __launch_bounds__(256, 2) k_conv_bwd_tma(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
                                                        GlConvGeom g, const float* __restrict__ wts, float scale) {
-  extern __shared__ __align__(128) float smem[];
+  extern __shared__ __align__(128) float glc_smem_bt[];
+  float* smem = glc_smem_bt;
   const int nph = g.ss * g.ss;
   float* s_in = smem;                                   // [in_rows][tma_pitch]  zero-padded dL/d(image)
   float* s_out = smem + g.phase_stride;                 // [th][tw]  one phase of the result, staged for the TMA store

@@ -235,14 +235,21 @@ __global__ void __launch_bounds__(GTC_THREADS) k_gram_tc(int D, int npx, const f
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" :: "r"(tmem) : "memory");
 }
 
-// host-side launch: pick the column-block count for D
+// once per device (gl_plan_create / the stand-alone probe): opt every instance in to its dynamic shared memory
+static inline cudaError_t gl_gram_tc_init() {
+  cudaError_t e;
+#define GTC_INIT(n) if ((e = cudaFuncSetAttribute(k_gram_tc<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, GTC_SMEM)) != cudaSuccess) return e;
+  GTC_INIT(1) GTC_INIT(2) GTC_INIT(3) GTC_INIT(4) GTC_INIT(5) GTC_INIT(6) GTC_INIT(7)
+#undef GTC_INIT
+  return cudaSuccess;
+}
+
+// host-side launch: pick the column-block count for D (gl_gram_tc_init() must have run on this device)
 static inline cudaError_t gl_launch_gram_tc(int nb, int D, int npx, const float* R, const float* w, const float* obs, float* gram,
                                             int* err_flag, cudaStream_t st) {
   const int NBv = (D + 1 + 15) / 16;
 #define GTC_CASE(n)                                                                                                 \
   case n: {                                                                                                         \
-    cudaError_t e = cudaFuncSetAttribute(k_gram_tc<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, GTC_SMEM);      \
-    if (e != cudaSuccess) return e;                                                                                 \
     k_gram_tc<n><<<nb, GTC_THREADS, GTC_SMEM, st>>>(D, npx, R, w, obs, gram, err_flag);                             \
     return cudaGetLastError();                                                                                      \
   }

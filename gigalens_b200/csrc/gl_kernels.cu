@@ -24,6 +24,7 @@
 #include "gl_lstsq.cuh"
 #include "gl_positions.cuh"
 #include "gl_gram_tc.cuh"
+#include "gl_probe.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // error handling / bookkeeping
@@ -343,17 +344,21 @@ __global__ void __launch_bounds__(GLK_THREADS) k_nan_cotangent_mask(GlProgram P,
   }
 }
 
-template <int PPT, unsigned F>
+// nan_mode (lstsq path, where the reference scrubs NaN per component, tf/simulator.py:200): 0 = every sample;
+// 1 = skip the samples whose forward pass scrubbed a component value (nan_count != 0); the SCRUB instance then runs
+// with nan_mode 2 = ONLY those samples, masking the cotangent per light profile.
+template <int PPT, unsigned F, bool SCRUB = false>
 __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_bwd(GlProgram P, int npix, const float* __restrict__ grid_x,
                                                               const float* __restrict__ grid_y,
                                                               const unsigned char* __restrict__ ss_mask,
                                                               const float* __restrict__ derived, int no_deflection,
                                                               const float* __restrict__ gss, float* __restrict__ gpart,
-                                                              const int* __restrict__ nan_count) {
+                                                              const int* __restrict__ nan_count, int nan_mode) {
   extern __shared__ __align__(16) float smem[];
   float* s_der = smem;                               // [der_total]
   float* s_acc = smem + P.der_total;                 // [nwarps][g_total]
   const int b = blockIdx.y;
+  if (nan_mode && ((nan_count[b] != 0) != (nan_mode == 2))) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = GLK_THREADS / 32;
   const float* dsrc = derived + (size_t)b * P.der_total;
   for (int i = threadIdx.x; i < P.der_total; i += blockDim.x) s_der[i] = dsrc[i];
@@ -376,7 +381,7 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_bwd(GlProgram P, int n
       x[j] = __ldg(grid_x + p); y[j] = __ldg(grid_y + p);
       gs[j] = ok ? __ldg(gsrc + p) : 0.f;
     }
-    gl_pix_image_bwd<float, PPT, F>(P, s_der, x, y, gs, no_deflection != 0, flush, scr, GLK_THREADS);
+    gl_pix_image_bwd<float, PPT, F, DevFlush, SCRUB>(P, s_der, x, y, gs, no_deflection != 0, flush, scr, GLK_THREADS);
   }
   __syncthreads();
   float* out = gpart + ((size_t)b * gridDim.x + blockIdx.x) * P.g_total;
@@ -454,11 +459,12 @@ __global__ void __launch_bounds__(GLK_THREADS, 2) k_raytrace_bwd_p(GlProgram P, 
                                                                 const unsigned char* __restrict__ ss_mask,
                                                                 const float* __restrict__ derived, int no_deflection,
                                                                 const float* __restrict__ gss, float* __restrict__ gpart,
-                                                                const int* __restrict__ nan_count) {
+                                                                const int* __restrict__ nan_count, int nan_mode) {
   extern __shared__ __align__(16) float smem[];
   float* s_der = smem;
   float* s_acc = smem + P.der_total;   // ROWS: staging tiles [nwarps][g_total][33], else accumulator rows [nwarps][g_total]
   const int b = blockIdx.y;
+  if (nan_mode && nan_count[b] != 0) return;   // lstsq path: left to the per-component SCRUB instance of k_raytrace_bwd
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = GLK_THREADS / 32;
   const float* dsrc = derived + (size_t)b * P.der_total;
   for (int i = threadIdx.x; i < P.der_total; i += blockDim.x) s_der[i] = dsrc[i];
@@ -626,7 +632,7 @@ struct gl_plan {
   // likelihood
   bool has_like = false;
   float* d_obs = nullptr; float* d_err = nullptr;
-  float bg2 = 0.f, inv_exp = 0.f, n_pix_used = 0.f;
+  float bg2 = 0.f, inv_exp = 0.f, n_pix_used = 0.f, n_mask_used = 0.f;
   // prior
   int d = 0;
   GlLeaf* d_leaves = nullptr;
@@ -747,7 +753,62 @@ static void gl_pick_tiles(int extent, int A, int nph_in, GlConvGeom& g) {
   }
 }
 
+// Every kernel of the library receives the device's full opt-in dynamic shared-memory limit ONCE per device, at the first
+// gl_plan_create.  The attribute is a permission (occupancy follows from the bytes a launch actually asks for), so no launch
+// path touches function attributes afterwards and two plans with different footprints cannot undo each other's setting.
+template <class K>
+static cudaError_t gl_optin(K kernel, int optin) {
+  cudaFuncAttributes a;
+  cudaError_t e = cudaFuncGetAttributes(&a, kernel);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)a.sharedSizeBytes);
+}
+template <int A>
+static cudaError_t gl_optin_conv(int optin) {
+  cudaError_t e;
+  if ((e = gl_optin(k_conv_fwd_tma<A>, optin)) != cudaSuccess) return e;
+  if ((e = gl_optin(k_conv_fwd<A>, optin)) != cudaSuccess) return e;
+  if ((e = gl_optin(k_conv_bwd_tma<A>, optin)) != cudaSuccess) return e;
+  return gl_optin(k_conv_bwd<A>, optin);
+}
+template <unsigned F>
+static cudaError_t gl_optin_feat(int optin) {
+  cudaError_t e;
+  if ((e = gl_optin(k_raytrace_fwd<4, F>, optin)) != cudaSuccess) return e;
+  if ((e = gl_optin(k_nan_cotangent_mask<4, F>, optin)) != cudaSuccess) return e;
+  if ((e = gl_optin(k_raytrace_bwd<4, F>, optin)) != cudaSuccess) return e;
+  if ((e = gl_optin(k_raytrace_comps<4, F>, optin)) != cudaSuccess) return e;
+  return gl_optin(k_points<F>, optin);
+}
+static int gl_device_init(int device) {
+  static bool done[64] = {false};
+  if (device >= 0 && device < 64 && done[device]) return 0;
+  int optin = 0;
+  GL_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+#define GL_OPT(call) GL_CUDA(call)
+  GL_OPT(gl_optin_feat<GL_FS0>(optin)); GL_OPT(gl_optin_feat<GL_FS1>(optin));
+  GL_OPT(gl_optin_feat<GL_FS2>(optin)); GL_OPT(gl_optin_feat<GL_FS3>(optin));
+  GL_OPT(gl_optin(k_raytrace_bwd<4, GL_FS3, true>, optin));
+  GL_OPT(gl_optin(k_raytrace_fwd_p<4, GL_FS0, true>, optin)); GL_OPT(gl_optin(k_raytrace_fwd_p<4, GL_FS0>, optin));
+  GL_OPT(gl_optin(k_raytrace_fwd_p<4, GL_FS2>, optin));
+  GL_OPT(gl_optin(k_raytrace_bwd_p<4, GL_FS0, true, true>, optin));
+  GL_OPT(gl_optin(k_raytrace_bwd_p<4, GL_FS0, true>, optin)); GL_OPT(gl_optin(k_raytrace_bwd_p<4, GL_FS0, false>, optin));
+  GL_OPT(gl_optin(k_raytrace_bwd_p<4, GL_FS2, true>, optin)); GL_OPT(gl_optin(k_raytrace_bwd_p<4, GL_FS2, false>, optin));
+  GL_OPT(gl_optin_conv<1>(optin)); GL_OPT(gl_optin_conv<2>(optin)); GL_OPT(gl_optin_conv<3>(optin)); GL_OPT(gl_optin_conv<4>(optin));
+  GL_OPT(gl_optin_conv<5>(optin)); GL_OPT(gl_optin_conv<6>(optin)); GL_OPT(gl_optin_conv<7>(optin)); GL_OPT(gl_optin_conv<8>(optin));
+  GL_OPT(gl_optin_conv<9>(optin)); GL_OPT(gl_optin_conv<11>(optin)); GL_OPT(gl_optin_conv<13>(optin)); GL_OPT(gl_optin_conv<16>(optin));
+  GL_OPT(gl_optin_conv<20>(optin)); GL_OPT(gl_optin_conv<25>(optin)); GL_OPT(gl_optin_conv<32>(optin));
+  GL_OPT(gl_optin(k_positions, optin)); GL_OPT(gl_optin(k_hessian, optin)); GL_OPT(gl_optin(k_pinv_solve, optin));
+  GL_OPT(gl_optin(k_gram, optin));
+  GL_OPT(gl_gram_tc_init());
+#undef GL_OPT
+  if (device >= 0 && device < 64) done[device] = true;
+  return 0;
+}
+
 extern "C" {
+
+static int gl_lstsq_reserve(gl_plan* p, int chunk);
 
 const char* gl_last_error(void) { return g_last_error.c_str(); }
 int32_t gl_abi_version(void) { return GL_ABI_VERSION; }
@@ -769,6 +830,7 @@ int gl_plan_create(const gl_model_desc* model, const gl_sim_config* sim, int32_t
     return gl_fail("gl_plan_create: no CUDA device available (this library has no CPU path)");
   if (device < 0 || device >= ndev) return gl_fail("gl_plan_create: device index out of range");
   GL_CUDA(cudaSetDevice(device));
+  if (gl_device_init(device)) return 1;
 
   GlBuilt built;
   std::string err = gl_build_program(model, built);
@@ -821,6 +883,10 @@ int gl_plan_create(const gl_model_desc* model, const gl_sim_config* sim, int32_t
     }
     GL_TRY(gl_upload(&p->d_mask, m.data(), m.size()));
     GL_TRY(gl_upload(&p->d_ss_mask, ms.data(), ms.size()));
+    size_t c = 0; for (unsigned char v : m) c += v;
+    p->n_mask_used = (float)c;   // count_nonzero(img_region)  (tf/model.py:100)
+  } else {
+    p->n_mask_used = (float)((size_t)p->n * p->n);
   }
   if (!built.member_factor.empty()) GL_TRY(gl_upload(&p->d_member_factor, built.member_factor.data(), built.member_factor.size()));
   if (!built.amp_slot.empty()) GL_TRY(gl_upload(&p->d_amp_slot, built.amp_slot.data(), built.amp_slot.size()));
@@ -929,7 +995,13 @@ int gl_plan_create(const gl_model_desc* model, const gl_sim_config* sim, int32_t
   GL_TRY(cudaMalloc((void**)&p->d_nan, (size_t)bs * sizeof(int)));
   GL_TRY(cudaMalloc((void**)&p->d_fmax, GL_MAX_PROF * sizeof(float)));
   GL_TRY(cudaMemset(p->d_logprior, 0, (size_t)bs * sizeof(float)));
+  GL_TRY(cudaMemset(p->d_nan, 0, (size_t)bs * sizeof(int)));
 #undef GL_TRY
+  {   // models built for lstsq_simulate (some light profile has use_lstsq) get their workspace now; others on request
+    bool wants = false;
+    for (int i = p->prog.n_lens; i < p->prog.n_prof; ++i) wants = wants || (p->prog.prof[i].flags & GL_FLAG_USE_LSTSQ);
+    if (wants && gl_lstsq_reserve(p, 0)) { gl_free_plan(p); return 1; }
+  }
   *out = p;
   return 0;
 }
@@ -967,9 +1039,9 @@ int gl_plan_set_option(gl_plan* p, const char* name, int32_t value) {
   }
   if (!strcmp(name, "gram_tc")) { p->gram_tc = value != 0; return 0; }
   if (!strcmp(name, "packed_math")) { p->use_packed = value; return 0; }   // 0: scalar-lane kernels (A/B testing)
-  if (!strcmp(name, "lstsq_chunk")) {   // samples per pass of the lstsq component stack (0 = size by memory budget)
-    if (p->d_comps) return gl_fail("gl_plan_set_option: lstsq_chunk must be set before the first lstsq call");
-    p->lq_chunk_req = value; return 0;
+  if (!strcmp(name, "lstsq_chunk")) {   // samples per pass of the lstsq component stack (0 = size by memory budget): re-reserves
+    if (value < 0) return gl_fail("gl_plan_set_option: lstsq_chunk must be >= 0");
+    return gl_lstsq_reserve(p, value);
   }
   return gl_fail(std::string("gl_plan_set_option: unknown option ") + name);
 }
@@ -985,14 +1057,7 @@ int gl_plan_set_likelihood(gl_plan* p, const gl_like_config* like) {
   else if (!(like->exp_time != 0.f)) return gl_fail("gl_plan_set_likelihood: exp_time must be non-zero without an error map");
   p->bg2 = like->background_rms * like->background_rms;
   p->inv_exp = like->error_map ? 0.f : 1.f / like->exp_time;
-  // count_nonzero(img_region)  (tf/model.py:100)
-  p->n_pix_used = (float)nn;
-  if (p->d_mask) {
-    std::vector<unsigned char> m(nn);
-    GL_CUDA(cudaMemcpy(m.data(), p->d_mask, nn, cudaMemcpyDeviceToHost));
-    size_t c = 0; for (unsigned char v : m) c += v ? 1 : 0;
-    p->n_pix_used = (float)c;
-  }
+  p->n_pix_used = p->n_mask_used;   // count_nonzero(img_region)  (tf/model.py:100), counted at plan creation
   if (p->d_w) { cudaFree(p->d_w); p->d_w = nullptr; }
   if (like->error_map) {
     std::vector<float> w(nn);
@@ -1089,7 +1154,6 @@ static int gl_run_positions(gl_plan* p, const float* params, float* loglike, flo
   const size_t smem = sizeof(double) * ((size_t)p->prog.der_total + 12 * (size_t)p->pos_npts + 2 * (size_t)p->pos_nsys +
                                         (size_t)(GLP_THREADS + 1) * p->prog.g_total);
   if (smem > 200 * 1024) return gl_fail("gl_run_positions: model too large for the positions kernel's shared memory");
-  if (smem > 40 * 1024) GL_CUDA(cudaFuncSetAttribute(k_positions, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_positions<<<p->bs, GLP_THREADS, smem, st>>>(p->prog, p->bs, params, p->d_member_factor, p->d_amp_slot, p->pos_npts, p->pos_nsys,
                                                 p->d_pos_off, p->d_pos_x, p->d_pos_y, p->d_pos_ex, p->d_pos_ey, p->pos_n_position,
                                                 loglike, red_chi2, dparams);
@@ -1103,15 +1167,12 @@ static int gl_run_raytrace_fwd(gl_plan* p, float* ss_out, int no_deflection, cud
   const size_t smem = (size_t)p->prog.der_total * sizeof(float);
   if ((p->feat_idx == 0 || p->feat_idx == 2) && (p->npix % 2) == 0 && p->use_packed) {   // two pixels per lane slot (FFMA2)
     if (p->feat_idx == 0 && p->straight_line && !no_deflection && gl_is_benchmark_shape(p->prog)) {
-      if (smem > 40 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_fwd_p<4, GL_FS0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k_raytrace_fwd_p<4, GL_FS0, true><<<grid, GLK_THREADS, smem, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,
                                                                          p->d_derived, no_deflection, ss_out, p->d_nan);
     } else if (p->feat_idx == 0) {
-      if (smem > 40 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_fwd_p<4, GL_FS0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k_raytrace_fwd_p<4, GL_FS0><<<grid, GLK_THREADS, smem, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,
                                                                    p->d_derived, no_deflection, ss_out, p->d_nan);
     } else {
-      if (smem > 40 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_fwd_p<4, GL_FS2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k_raytrace_fwd_p<4, GL_FS2><<<grid, GLK_THREADS, smem, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,
                                                                    p->d_derived, no_deflection, ss_out, p->d_nan);
     }
@@ -1119,7 +1180,6 @@ static int gl_run_raytrace_fwd(gl_plan* p, float* ss_out, int no_deflection, cud
     return 0;
   }
   GL_FEAT_DISPATCH(p->feat_idx, {
-    if (smem > 40 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_fwd<4, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_raytrace_fwd<4, F><<<grid, GLK_THREADS, smem, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask, p->d_derived,
                                                           no_deflection, ss_out, p->d_nan);
   })
@@ -1127,12 +1187,19 @@ static int gl_run_raytrace_fwd(gl_plan* p, float* ss_out, int no_deflection, cud
   return 0;
 }
 
-static int gl_run_raytrace_bwd(gl_plan* p, float* gss, int no_deflection, cudaStream_t st) {
+// per_component (lstsq path): the reference scrubs NaN per component there (tf/simulator.py:200), so the samples whose
+// forward pass scrubbed anything are left out of the main kernel (nan_mode 1) and handled by the SCRUB instance.
+static int gl_run_raytrace_bwd(gl_plan* p, float* gss, int no_deflection, cudaStream_t st, bool per_component = false) {
   dim3 grid(p->chunks, p->bs);
-  {   // NaN-scrubbed pixels pass no gradient: exits immediately for samples without any (nan_count from the forward pass)
+  const int nan_mode = per_component ? 1 : 0;
+  if (per_component) {
+    const size_t smem_s = (size_t)gl_bwd_smem_floats(p->prog, 4) * sizeof(float);
+    k_raytrace_bwd<4, GL_FS3, true><<<grid, GLK_THREADS, smem_s, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask, p->d_derived,
+                                                                       no_deflection, gss, p->d_gpart, p->d_nan, 2);
+    GL_LAUNCH_CHECK("k_raytrace_bwd<scrub>");
+  } else {   // NaN-scrubbed pixels pass no gradient: exits immediately for samples without any (nan_count from the forward pass)
     const size_t smem_m = (size_t)p->prog.der_total * sizeof(float);
     GL_FEAT_DISPATCH(p->feat_idx, {
-      if (smem_m > 40 * 1024) GL_CUDA(cudaFuncSetAttribute(k_nan_cotangent_mask<4, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m));
       k_nan_cotangent_mask<4, F><<<dim3(1, p->bs), GLK_THREADS, smem_m, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_derived,
                                                                    no_deflection, gss, p->d_nan);
     })
@@ -1146,14 +1213,12 @@ static int gl_run_raytrace_bwd(gl_plan* p, float* gss, int no_deflection, cudaSt
     const bool rows = p->row_flush && smem_rows <= 108 * 1024 && p->prog.g_total <= 64;
 #define GL_BWD_P(FS, ROWS, SM)                                                                                              \
     {                                                                                                                       \
-      if ((SM) > 40 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_bwd_p<4, FS, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM))); \
       k_raytrace_bwd_p<4, FS, ROWS><<<grid, GLK_THREADS, (SM), st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,        \
-                                                                   p->d_derived, no_deflection, gss, p->d_gpart, p->d_nan); \
+                                                                   p->d_derived, no_deflection, gss, p->d_gpart, p->d_nan, nan_mode); \
     }
     if (p->feat_idx == 0 && rows && p->straight_line && !no_deflection && gl_is_benchmark_shape(p->prog)) {
-      if (smem_rows > 40 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_bwd_p<4, GL_FS0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
       k_raytrace_bwd_p<4, GL_FS0, true, true><<<grid, GLK_THREADS, smem_rows, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,
-                                                                                  p->d_derived, no_deflection, gss, p->d_gpart, p->d_nan);
+                                                                                  p->d_derived, no_deflection, gss, p->d_gpart, p->d_nan, nan_mode);
     } else
     if (p->feat_idx == 0) { if (rows) GL_BWD_P(GL_FS0, true, smem_rows) else GL_BWD_P(GL_FS0, false, smem) }
     else { if (rows) GL_BWD_P(GL_FS2, true, smem_rows) else GL_BWD_P(GL_FS2, false, smem) }
@@ -1162,9 +1227,8 @@ static int gl_run_raytrace_bwd(gl_plan* p, float* gss, int no_deflection, cudaSt
     return 0;
   }
   GL_FEAT_DISPATCH(p->feat_idx, {
-    if (smem > 40 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_bwd<4, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_raytrace_bwd<4, F><<<grid, GLK_THREADS, smem, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask, p->d_derived,
-                                                          no_deflection, gss, p->d_gpart, p->d_nan);
+                                                          no_deflection, gss, p->d_gpart, p->d_nan, nan_mode);
   })
   GL_LAUNCH_CHECK("k_raytrace_bwd");
   return 0;
@@ -1211,16 +1275,12 @@ static int gl_launch_conv_fwd_A(gl_plan* p, const float* ss, float scale, float*
       p->tmap_f_base = ss; p->tmap_f_nimg = nimg;
     }
     if (p->tmap_f_ok) {
-      if (p->smem_cf_tma > 40 * 1024)
-        GL_CUDA(cudaFuncSetAttribute(k_conv_fwd_tma<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cf_tma));
       k_conv_fwd_tma<A><<<grid, p->conv_threads_f, p->smem_cf_tma, st>>>(p->tmap_f, p->gf, p->d_wf, scale, img, la,
                                                                         like ? p->d_like_part : nullptr, gimg);
       GL_LAUNCH_CHECK("k_conv_fwd_tma");
       return 0;
     }
   }
-  if (p->smem_cf > 40 * 1024)
-    GL_CUDA(cudaFuncSetAttribute(k_conv_fwd<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cf));
   k_conv_fwd<A><<<grid, p->conv_threads_f, p->smem_cf, st>>>(p->gf, ss, p->d_wf, scale, img, la, like ? p->d_like_part : nullptr, gimg);
   GL_LAUNCH_CHECK("k_conv_fwd");
   return 0;
@@ -1236,15 +1296,11 @@ static int gl_launch_conv_bwd_A(gl_plan* p, const float* gimg, float scale, floa
       p->tmap_bi_base = gimg; p->tmap_bo_base = gss; p->tmap_b_nimg = nimg;
     }
     if (p->tmap_b_ok) {
-      if (p->smem_cb_tma > 40 * 1024)
-        GL_CUDA(cudaFuncSetAttribute(k_conv_bwd_tma<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cb_tma));
       k_conv_bwd_tma<A><<<grid, p->conv_threads_b, p->smem_cb_tma, st>>>(p->tmap_bi, p->tmap_bo, p->gb, p->d_wb, scale);
       GL_LAUNCH_CHECK("k_conv_bwd_tma");
       return 0;
     }
   }
-  if (p->smem_cb > 40 * 1024)
-    GL_CUDA(cudaFuncSetAttribute(k_conv_bwd<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_cb));
   k_conv_bwd<A><<<grid, p->conv_threads_b, p->smem_cb, st>>>(p->gb, gimg, p->d_wb, scale, nullptr, gss);
   GL_LAUNCH_CHECK("k_conv_bwd");
   return 0;
@@ -1329,7 +1385,6 @@ int gl_hessian(gl_plan* p, const float* params_dev, int32_t npts, const float* x
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = (size_t)p->prog.der_total * sizeof(double);
   if (smem > 200 * 1024) return gl_fail("gl_hessian: model too large");
-  if (smem > 40 * 1024) GL_CUDA(cudaFuncSetAttribute(k_hessian, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((npts + 127) / 128 > 64 ? 64 : (npts + 127) / 128, p->bs);
   k_hessian<<<grid, 128, smem, st>>>(p->prog, p->bs, params_dev, p->d_member_factor, p->d_amp_slot, npts, x_dev, y_dev, fxx, fxy, fyx, fyy);
   GL_LAUNCH_CHECK("k_hessian");
@@ -1470,18 +1525,24 @@ int gl_simulate_host(gl_plan* p, const float* params_host, float* image_host) {
   return 0;
 }
 
-// lstsq workspace, allocated on first use (sized by a memory budget; see "lstsq_chunk")
-static int gl_lstsq_alloc(gl_plan* p) {
-  if (p->d_comps) return 0;
+// lstsq workspace (gl_plan_reserve_lstsq; plan creation calls it for models with use_lstsq components): the
+// component stack of `chunk` samples, sized by a memory budget when chunk == 0.  Never called from a data-path entry point.
+static int gl_lstsq_reserve(gl_plan* p, int chunk) {
   const int D = p->prog.depth, npx = p->n * p->n;
   if (D <= 0) return gl_fail("lstsq: the model has no linear light component");
+  GL_CUDA(cudaSetDevice(p->device));
+  if (p->d_comps) {
+    GL_CUDA(cudaDeviceSynchronize());
+    for (float** q : {&p->d_R, &p->d_gram, &p->d_coef, &p->d_ll, &p->d_comps}) { cudaFree(*q); *q = nullptr; }
+    cudaFree(p->d_solve_queue); p->d_solve_queue = nullptr;
+  }
   const size_t per_sample = (size_t)D * p->npix * sizeof(float);
   // component-stack budget: 32 GB of the 180 GB HBM3e, but never more than 40 % of what is free right now
   size_t budget = (size_t)32 << 30, free_b = 0, total_b = 0;
   if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b / 5 * 2 < budget) budget = free_b / 5 * 2;
   size_t cb = budget / (per_sample + (size_t)D * npx * sizeof(float));
   if (cb < 1) cb = 1;
-  if (p->lq_chunk_req > 0) cb = (size_t)p->lq_chunk_req;
+  if (chunk > 0) cb = (size_t)chunk;
   if (cb > (size_t)p->bs) cb = p->bs;
   p->lq_chunk = (int)cb;
   GL_CUDA(cudaMalloc((void**)&p->d_R, cb * (size_t)D * npx * sizeof(float)));
@@ -1491,6 +1552,11 @@ static int gl_lstsq_alloc(gl_plan* p) {
   GL_CUDA(cudaMalloc((void**)&p->d_ll, (size_t)p->bs * 2 * sizeof(float)));
   GL_CUDA(cudaMalloc((void**)&p->d_comps, cb * per_sample));
   return 0;
+}
+static int gl_lstsq_alloc(gl_plan* p) {
+  if (p->d_comps) return 0;
+  if (p->prog.depth <= 0) return gl_fail("lstsq: the model has no linear light component");
+  return gl_fail("lstsq: no workspace -- call gl_plan_reserve_lstsq first (plan creation does it for models with use_lstsq components)");
 }
 
 static int gl_lstsq_forward(gl_plan* p, const float* params, float* image, float* coeffs_out, float* loglike,
@@ -1502,20 +1568,17 @@ static int gl_lstsq_forward(gl_plan* p, const float* params, float* image, float
   if (gl_lstsq_alloc(p)) return 1;
   if (gl_run_prep(p, params, st)) return 1;
   const size_t smem_der = (size_t)p->prog.der_total * sizeof(float);
-  GL_FEAT_DISPATCH(p->feat_idx, {
-    if (smem_der > 40 * 1024) GL_CUDA(cudaFuncSetAttribute(k_raytrace_comps<4, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_der));
-  })
   const int nt = (D + 1 + 3) / 4;
   const size_t smem_gram = (size_t)GLL_PT * nt * 4 * sizeof(float);
   const int npair = ((D + 1) & ~1) / 2;
   const size_t smem_solve = (size_t)(2 * D * (D | 1) + 2 * (npair + 1)) * sizeof(double) + (size_t)(2 * (npair + 1) + 2) * sizeof(int) + 4 * sizeof(double);
-  if (smem_solve > 40 * 1024) GL_CUDA(cudaFuncSetAttribute(k_pinv_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve));
+  GL_CUDA(cudaMemsetAsync(p->d_nan, 0, (size_t)p->bs * sizeof(int), st));   // component values scrubbed per sample (read by the adjoint)
   for (int b0 = 0; b0 < p->bs; b0 += p->lq_chunk) {
     const int nb = (p->bs - b0 < p->lq_chunk) ? p->bs - b0 : p->lq_chunk;
     dim3 grid(p->chunks, nb);
     GL_FEAT_DISPATCH(p->feat_idx, {
       k_raytrace_comps<4, F><<<grid, GLL_THREADS, smem_der, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,
-                                                                 p->d_derived + (size_t)b0 * p->prog.der_total, p->no_deflection, p->d_comps);
+                                                                 p->d_derived + (size_t)b0 * p->prog.der_total, p->no_deflection, p->d_comps, p->d_nan + b0);
     })
     GL_LAUNCH_CHECK("k_raytrace_comps");
     if (gl_run_conv_fwd(p, p->d_comps, 1.f, p->d_R, false, nullptr, st, nb * D)) return 1;
@@ -1557,7 +1620,7 @@ static int gl_lstsq_loglike_core(gl_plan* p, const float* params, float* loglike
     k_patch_amps<<<gb, tb, 0, st>>>(p->prog, p->bs, p->d_coef, p->d_derived);
     GL_LAUNCH_CHECK("k_patch_amps");
     if (gl_run_conv_bwd(p, p->d_gimg, 1.f, p->d_ss, st)) return 1;
-    if (gl_run_raytrace_bwd(p, p->d_ss, p->no_deflection, st)) return 1;
+    if (gl_run_raytrace_bwd(p, p->d_ss, p->no_deflection, st, true)) return 1;
   }
   k_sample_bwd<<<gb, tb, 0, st>>>(p->prog, p->bs, params, p->d_member_factor, p->d_amp_slot, p->d_derived, p->d_gpart, p->chunks,
                                   p->d_gsum, nullptr, 0, 1.f, ll, chi, dparams, p->d, p->d_leaves, z,
@@ -1581,6 +1644,27 @@ int gl_lstsq_loglike_grad(gl_plan* p, const float* params_dev, float* loglike_de
   if (!p || !params_dev) return gl_fail("gl_lstsq_loglike_grad: NULL argument");
   GL_CUDA(cudaSetDevice(p->device));
   return gl_lstsq_loglike_core(p, params_dev, loglike_dev, red_chi2_dev, dparams_dev, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int gl_plan_reserve_lstsq(gl_plan* p, int32_t chunk) {
+  if (!p || chunk < 0) return gl_fail("gl_plan_reserve_lstsq: bad argument");
+  return gl_lstsq_reserve(p, chunk);
+}
+
+int gl_fp32_peak(int32_t device, float* tflops_ffma, float* tflops_ffma2) {
+  if (!tflops_ffma || !tflops_ffma2) return gl_fail("gl_fp32_peak: NULL argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return gl_fail("gl_fp32_peak: no such CUDA device");
+  GL_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  GL_CUDA(cudaGetDeviceProperties(&prop, device));
+  float* sink = nullptr;
+  GL_CUDA(cudaMalloc((void**)&sink, sizeof(float)));
+  cudaError_t e = gl_fp32_probe_run(prop.multiProcessorCount, 5, tflops_ffma, tflops_ffma2, sink);
+  cudaFree(sink);
+  g_launch_count += 12;
+  if (e != cudaSuccess) return gl_fail(std::string("gl_fp32_peak: ") + cudaGetErrorString(e));
+  return 0;
 }
 
 }  // extern "C"

@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(GLL_THREADS) k_raytrace_comps(GlProgram P, int
                                                                 const float* __restrict__ grid_y,
                                                                 const unsigned char* __restrict__ ss_mask,
                                                                 const float* __restrict__ derived, int no_deflection,
-                                                                float* __restrict__ comps) {
+                                                                float* __restrict__ comps, int* __restrict__ nan_count) {
   extern __shared__ __align__(16) float s_der[];
   const int b = blockIdx.y;
   const float* dsrc = derived + (size_t)b * P.der_total;
@@ -53,7 +53,8 @@ __global__ void __launch_bounds__(GLL_THREADS) k_raytrace_comps(GlProgram P, int
     for (int j = 0; j < PPT; ++j) {
       if (pix[j] >= npix) continue;
       const bool keep = !ss_mask || ss_mask[pix[j]];
-      gl_point_components<float, F>(P, s_der, x[j], y[j], bx[j], by[j], dst + pix[j], npix, keep);
+      const int n_nan = gl_point_components<float, F>(P, s_der, x[j], y[j], bx[j], by[j], dst + pix[j], npix, keep);
+      if (n_nan && nan_count) atomicAdd(nan_count + b, n_nan);   // the adjoint treats this sample per component (SCRUB)
     }
   }
 }

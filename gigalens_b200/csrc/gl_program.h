@@ -235,7 +235,8 @@ GL_HD void gl_pix_image(const GlProgram& P, const typename gl_scalar_of<T>::type
 // tf/simulator.py:183-200 with the layout of jax/simulator.py:171-175): out[c * stride], NaN scrubbed
 // (:200); `keep` = false (pixel outside pix_region) writes zeros.
 template <class T, unsigned F>
-GL_HD void gl_point_components(const GlProgram& P, const T* der, T x, T y, T bx, T by, T* out, int stride, bool keep) {
+GL_HD int gl_point_components(const GlProgram& P, const T* der, T x, T y, T bx, T by, T* out, int stride, bool keep) {
+  int n_nan = 0;   // values scrubbed at this pixel (the adjoint passes them no gradient)
   for (int i = P.n_lens; i < P.n_prof; ++i) {
     const GlProf& pr = P.prof[i];
     const bool src = i >= P.n_lens + P.n_ll;
@@ -244,6 +245,7 @@ GL_HD void gl_point_components(const GlProgram& P, const T* der, T x, T y, T bx,
       case GLT_SERSIC: case GLT_SERSIC_ELLIPSE: if constexpr ((F & GLF_SERSIC) != 0) {
         T v[1] = {T(0)}, xx[1] = {px}, yy[1] = {py};
         sersic_fwd<T, 1>(der + pr.der_off, xx, yy, v);
+        if (keep && gl_isnan(v[0])) ++n_nan;
         out[pr.comp_off * stride] = (keep && !gl_isnan(v[0])) ? v[0] : T(0);
       } break;
       case GLT_SHAPELETS: if constexpr ((F & GLF_SHAPELETS) != 0) {
@@ -253,23 +255,30 @@ GL_HD void gl_point_components(const GlProgram& P, const T* der, T x, T y, T bx,
                      (T*)nullptr, (T*)nullptr, (T*)nullptr, (T*)nullptr);
         for (int k = 0; k < L; ++k) {
           const T v = o[k * stride];
+          if (keep && gl_isnan(v)) ++n_nan;
           if (!keep || gl_isnan(v)) o[k * stride] = T(0);
         }
       } break;
       default: break;
     }
   }
+  return n_nan;
 }
 
 // Adjoint of gl_pix_image: gS is the cotangent of the (scrubbed) surface brightness at the NP
 // pixels.  `flush(acc, n, off)` receives the NP-pixel partial cotangent of dvars [off, off+n) --
 // the host harness adds it into a vector, the CUDA kernel warp-reduces it into shared memory.
-template <class T, int NP, unsigned F, class Flush>
+// SCRUB (lstsq path, samples that had NaN components): the reference scrubs the component stack per component
+// (tf/simulator.py:200), so a light profile whose own value is NaN at a pixel receives a zero cotangent there while
+// the other profiles keep theirs.
+template <class T, int NP, unsigned F, class Flush, bool SCRUB = false>
 GL_HD void gl_pix_image_bwd(const GlProgram& P, const typename gl_scalar_of<T>::type* der, const T* x, const T* y, const T* gS,
                             bool no_deflection, Flush& flush, T* scr = nullptr, int scr_stride = 0) {
   T bx[NP], by[NP], Gx[NP], Gy[NP];
   T Jx[3][NP], Jy[3][NP];
   bool have_jac = false;
+  const T* const gS_all = gS;   // SCRUB re-points gS at a per-profile masked copy
+  (void)gS_all;
   if (no_deflection) {
 #pragma unroll
     for (int j = 0; j < NP; ++j) { bx[j] = x[j]; by[j] = y[j]; }
@@ -288,6 +297,23 @@ GL_HD void gl_pix_image_bwd(const GlProgram& P, const typename gl_scalar_of<T>::
     T acc[GL_MAX_DVARS];
 #pragma unroll
     for (int k = 0; k < GL_MAX_DVARS; ++k) acc[k] = T(0);
+    T gM[NP];
+    if constexpr (SCRUB) {   // this profile's own forward value decides which pixels pass a cotangent to it
+      T v[NP];
+#pragma unroll
+      for (int j = 0; j < NP; ++j) v[j] = T(0);
+      if (pr.type == GLT_SHAPELETS) {
+        if constexpr ((F & GLF_SHAPELETS) != 0)
+          for (int j = 0; j < NP; ++j)
+            v[j] = shp_point<T>(der + pr.der_off, pr.table, (pr.flags & 2u) != 0, pr.n_max, src ? bx[j] : x[j], src ? by[j] : y[j],
+                                (T*)nullptr, 0, (const T*)nullptr, (T*)nullptr, (T*)nullptr, (T*)nullptr, (T*)nullptr);
+      } else {
+        if constexpr ((F & GLF_SERSIC) != 0) sersic_fwd<T, NP>(der + pr.der_off, src ? bx : x, src ? by : y, v);
+      }
+#pragma unroll
+      for (int j = 0; j < NP; ++j) gM[j] = gl_isnan(v[j]) ? T(0) : gS_all[j];
+      gS = gM;
+    }
     switch (pr.type) {
       case GLT_SERSIC: case GLT_SERSIC_ELLIPSE:
         if constexpr ((F & GLF_SERSIC) != 0) {

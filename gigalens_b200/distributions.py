@@ -158,12 +158,15 @@ class JointDistribution(Distribution):
         return _flatten(self.model)
 
     def sample(self, sample_shape=(), seed=None):
-        """Pytree of float32 numpy arrays of shape ``sample_shape`` (an int or () like TFP)."""
+        """Pytree of float32 numpy arrays of shape ``sample_shape`` (an int, a tuple or () like TFP; a tuple such as
+        ``(num_particles, num_ensembles)`` -- ``tf/inference.py:199`` -- gives leaves of exactly that shape)."""
         n = int(np.prod(sample_shape)) if np.size(sample_shape) else 1
         rng = np.random.default_rng(seed)
         cols = [np.asarray(d.sample_np(rng, n), dtype=np.float32) for _, d in self.leaves]
         if not np.size(sample_shape):
             cols = [c[0] for c in cols]
+        elif np.ndim(sample_shape) == 1 and len(sample_shape) > 1:
+            cols = [c.reshape(tuple(int(k) for k in sample_shape)) for c in cols]
         return _map_structure(self.model, iter(cols))
 
     def flatten_values(self, values):

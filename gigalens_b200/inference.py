@@ -99,11 +99,15 @@ class ModellingSequence:
         self._simulator_cls = simulator_cls   # injectable so the sharding / collective logic is testable on CPU
 
     # ------------------------------------------------------------------ MAP
-    def MAP(self, optimizer=None, start=None, n_samples=500, num_steps=350, seed=0, gather=True, callback=None):
+    def MAP(self, optimizer=None, start=None, n_samples=500, num_steps=350, seed=0, gather=True, callback=None,
+            scrub_nan_gradients=False):
         """``tf/inference.py:18-45``: per-sample Adam ascent of ``log_prob / event_size``.
 
         ``optimizer``: an :class:`Adam` (or anything with ``step(z, grad)``); default ``Adam(1e-2)``.
         ``start``: physical-parameter pytree with ``n_samples`` leaves, default: prior draws.
+        ``scrub_nan_gradients``: the reference applies gradients as they come, so a sample whose gradient turns NaN
+        stays NaN (Adam is element-wise: its neighbours are unaffected) and drops out through ``np.nanmin``; ``True``
+        zeroes non-finite gradients instead and keeps such a sample where it is.
         Returns the final unconstrained ``z`` ``(n_samples, d)`` (all samples when ``gather``)."""
         import torch
 
@@ -115,12 +119,18 @@ class ModellingSequence:
         lo, hi = _shard(n_samples, rank, world)
         sim = self._simulator_cls(self.phys_model, self.sim_config, bs=hi - lo)
         z = torch.as_tensor(z_all[lo:hi], device=sim.device).clone()
-        event_size = float(torch.count_nonzero(sim.img_region))
+        # tf/inference.py:27-31: pixels count when include_pixels, image positions add n_position
+        event_size = 0.0
+        if getattr(pm, "include_pixels", True):
+            event_size += float(torch.count_nonzero(sim.img_region))
+        if getattr(pm, "include_positions", False):
+            event_size += float(pm.n_position)
         self.last_red_chi2 = None
         for step in range(num_steps):
             logp, red_chi2, dz = pm.log_prob_and_grad(sim, z)
             grad = dz.mul_(-1.0 / (event_size * n_samples))   # d mean(-logp / event_size) / dz
-            grad = torch.nan_to_num_(grad, nan=0.0, posinf=0.0, neginf=0.0)
+            if scrub_nan_gradients:
+                grad = torch.nan_to_num_(grad, nan=0.0, posinf=0.0, neginf=0.0)
             optimizer.step(z, grad)
             if callback is not None:
                 callback(step, red_chi2)
@@ -135,10 +145,17 @@ class ModellingSequence:
         return z
 
     # ------------------------------------------------------------------ SVI
-    def SVI(self, optimizer=None, start_mean=None, n_vi=250, init_scales=1e-3, num_steps=500, seed=2, full_rank=True):
+    def SVI(self, optimizer=None, start_mean=None, n_vi=250, init_scales=1e-3, num_steps=500, seed=2, full_rank=True,
+            start=None):
         """``tf/inference.py:47-93``: fit a (full-rank) Gaussian surrogate by maximising the ELBO with
-        reparameterised samples; returns ``(q_z, losses)``."""
+        reparameterised samples; returns ``(q_z, losses)``.  ``start`` is accepted as an alias of ``start_mean``
+        (the reference's own ``tests/tf/test_model.py:53`` calls it that way)."""
         import torch
+
+        if start_mean is None:
+            start_mean = start
+        if start_mean is None:
+            raise TypeError("SVI needs start_mean")
 
         dist, rank, world = _dist()
         pm = self.prob_model
@@ -162,7 +179,7 @@ class ModellingSequence:
         theta = torch.cat([mu, raw]).requires_grad_(True)
         gen = torch.Generator(device=dev)
         gen.manual_seed(seed * 1000003 + rank)
-        losses = []
+        loss_buf = torch.zeros(num_steps, device=dev)   # the ELBO trace stays on the device: no host sync per step
 
         def build(th):
             m, r = th[:d], th[d:]
@@ -191,11 +208,11 @@ class ModellingSequence:
             packed = torch.cat([loss.detach().reshape(1), g])
             if world > 1:
                 dist.all_reduce(packed)   # the one collective of SVI: [ELBO, grad_mu, grad_L]
-            losses.append(float(packed[0]))
+            loss_buf[step] = packed[0]
             with torch.no_grad():
                 optimizer.step(theta, torch.nan_to_num(packed[1:], nan=0.0, posinf=0.0, neginf=0.0))
         m, L = build(theta.detach())
-        return SurrogateMVN(m, L), losses
+        return SurrogateMVN(m, L), loss_buf.tolist()
 
     # ------------------------------------------------------------------ HMC
     def HMC(self, q_z, init_eps=0.3, init_l=3, n_hmc=50, num_burnin_steps=250, num_results=750, max_leapfrog_steps=30,
@@ -237,17 +254,23 @@ class ModellingSequence:
         n_adapt = int(num_burnin_steps * 0.8)
         log_eps, log_eps_bar, h_bar, mu_da = math.log(init_eps), 0.0, 0.0, math.log(10 * init_eps)
         gamma_da, t0_da, kappa_da = 0.05, 10.0, 0.75     # tfp.mcmc.DualAveragingStepSizeAdaptation defaults
-        traj = init_eps * init_l                          # trajectory length T (ChEES adapts log T with Adam)
-        chees_opt = Adam(0.025)
-        log_T = torch.tensor([math.log(traj)], device=dev)
+        # ChEES adapts log T (T = trajectory length) with a scalar Adam (lr 0.025) on the host: the adaptation state is a
+        # handful of floats, fed by ONE packed device->host read per adaptation step; the sampling phase reads nothing.
+        log_T, log_T_avg = math.log(init_eps * init_l), math.log(init_eps * init_l)
+        ad_m = ad_v = 0.0
         samples = torch.empty((num_results, nloc, d), device=dev)
+        n_total = num_burnin_steps + num_results
+        acc_trace = torch.zeros(n_total, device=dev)
         stats = {"accept_prob": [], "step_size": [], "num_leapfrog": []}
         n_evals = 0
-        for it in range(num_burnin_steps + num_results):
+        nloc_t = torch.tensor([float(nloc)], device=dev)
+        for it in range(n_total):
             eps = math.exp(log_eps)
-            # jittered trajectory (Halton-like, shared by all chains / ranks)
-            u = ((it * 0.6180339887498949) % 1.0) if it < n_adapt else 0.5
-            n_leap = int(max(1, min(max_leapfrog_steps, math.ceil(2.0 * u * float(torch.exp(log_T)) / eps))))
+            # jittered trajectory (Halton sequence, shared by all chains / ranks); TFP keeps the jitter for the sampling
+            # phase and applies it to the averaged trajectory length there
+            u = (it * 0.6180339887498949) % 1.0
+            T_now = math.exp(log_T if it < n_adapt else log_T_avg)
+            n_leap = int(max(1, min(max_leapfrog_steps, math.ceil(2.0 * u * T_now / eps))))
             xi = torch.randn((nloc, d), device=dev, generator=gen)
             p0 = torch.linalg.solve_triangular(Lc.T, xi.T, upper=True).T          # p ~ N(0, Sigma^-1)
             zc, pc, gc, lpc = z.clone(), p0.clone(), grad, logp
@@ -265,19 +288,26 @@ class ModellingSequence:
             accept = torch.log(torch.rand(nloc, device=dev, generator=gen)) < log_acc
             if it < n_adapt:
                 # ChEES (tfp GradientBasedTrajectoryLengthAdaptation): moments over ALL chains
-                tot = allsum(torch.cat([zc.sum(0), z.sum(0), torch.tensor([float(nloc)], device=dev)]))
+                tot = allsum(torch.cat([zc.sum(0), z.sum(0), nloc_t]))
                 mean_prop, mean_prev = tot[:d] / tot[-1], tot[d:2 * d] / tot[-1]
                 xc, yc = zc - mean_prop, z - mean_prev
                 v = pc @ cov
                 dsq = (xc ** 2).sum(1) - (yc ** 2).sum(1)
                 gi = 2.0 * u * dsq * (xc * v).sum(1)
                 gi = torch.where(torch.isfinite(gi), gi, torch.zeros_like(gi))
-                num_den = allsum(torch.stack([(acc_prob * gi).sum(), acc_prob.sum(), acc_prob.sum() * 0 + float(nloc)]))
-                g_T = num_den[0] / torch.clamp(num_den[1], min=1e-20)
-                # ascent on log T (d crit / d log T = T * d crit / dT), normalised like TFP by T^2
-                chees_opt.step(log_T, -(g_T / torch.exp(log_T)).reshape(1))
-                log_T.clamp_(max=math.log(max_leapfrog_steps * eps))
-                mean_acc = float(num_den[1] / num_den[2])
+                num, den, cnt = allsum(torch.cat([(acc_prob * gi).sum().reshape(1), acc_prob.sum().reshape(1), nloc_t])).tolist()
+                acc_trace[it] = den / cnt
+                g_T = num / max(den, 1e-20)
+                # Adam ascent on log T (d crit / d log T = T * d crit / dT), normalised like TFP by T^2
+                g = -(g_T / math.exp(log_T))
+                t_ad = it + 1
+                ad_m = 0.9 * ad_m + 0.1 * g
+                ad_v = 0.999 * ad_v + 0.001 * g * g
+                log_T -= 0.025 * math.sqrt(1 - 0.999 ** t_ad) / (1 - 0.9 ** t_ad) * ad_m / (math.sqrt(ad_v) + 1e-7)
+                log_T = min(log_T, math.log(max_leapfrog_steps * eps))
+                w_avg = t_ad ** -0.5                                                # averaged trajectory length used after adaptation
+                log_T_avg = log_T if it == 0 else (1 - w_avg) * log_T_avg + w_avg * log_T
+                mean_acc = den / cnt
                 if adapt_mode == "dual":
                     t_da = it + 1
                     h_bar = (1 - 1 / (t_da + t0_da)) * h_bar + (target_accept - mean_acc) / (t_da + t0_da)
@@ -288,14 +318,16 @@ class ModellingSequence:
                     log_eps += math.log1p(adapt_rate) if mean_acc > target_accept else -math.log1p(adapt_rate)
                 if it == n_adapt - 1 and adapt_mode == "dual":
                     log_eps = log_eps_bar
+            else:
+                acc_trace[it] = acc_prob.mean()     # this rank's chains; no host read in the sampling phase
             z = torch.where(accept[:, None], zc, z)
             logp = torch.where(accept, lpc, logp)
             grad = torch.where(accept[:, None], gc, grad)
-            stats["accept_prob"].append(float(acc_prob.mean()))
             stats["step_size"].append(eps)
             stats["num_leapfrog"].append(n_leap)
             if it >= num_burnin_steps:
                 samples[it - num_burnin_steps] = z
+        stats["accept_prob"] = acc_trace.tolist()
         stats["n_evals"] = n_evals
         return samples, stats
 

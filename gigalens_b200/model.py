@@ -44,6 +44,25 @@ class PhysicalModel(PhysicalModelBase):
         self.source_light_constants = cast(self.source_light_constants)
 
 
+class _HostBijector:
+    """``prob_model.bij`` as scripts use it between runs (``bij.inverse(prior.sample(n))`` to start a driver,
+    ``bij.forward(z)`` to read a result: ``tests/tf/test_model.py:10-16,36-37``): the default event-space bijector
+    chained with the pack / split of ``tf/model.py:76-87``, on the host in numpy.  Inside the hot path the same map
+    runs in ``k_unconstrain`` (``ProbabilisticModel.bij_forward`` returns device tensors)."""
+
+    def __init__(self, owner):
+        self._owner = owner
+
+    def inverse(self, params):
+        return self._owner.bij_inverse(params)
+
+    def forward(self, z):
+        z = np.asarray(z.detach().cpu() if hasattr(z, "detach") else z, dtype=np.float64)
+        z = z.reshape(-1, self._owner.size)
+        cols = [np.asarray(d.forward_np(z[:, k]), dtype=np.float32) for k, (_, d) in enumerate(self._owner._leaves)]
+        return self._owner.prior.pack(cols)
+
+
 class ProbabilisticModel:
     """``src/gigalens/model.py:47-73`` plus the prior plumbing shared by both concrete models."""
 
@@ -51,9 +70,9 @@ class ProbabilisticModel:
         if not isinstance(prior, tfd.JointDistribution):
             prior = tfd.JointDistribution(prior)
         self.prior = prior
-        self.bij = bij
         self._leaves = prior.leaves  # [(path, distribution)] in tf.nest.flatten order
         self.size = len(self._leaves)
+        self.bij = bij if bij is not None else _HostBijector(self)
 
     # -- path of a prior leaf -> simulator slot key
     @staticmethod
@@ -94,9 +113,11 @@ class ProbabilisticModel:
 
     # -- bijector on the host (pack / unpack like tf/model.py:76-87)
     def bij_inverse(self, params, bs=None):
-        """Physical pytree (leaves scalar or (bs,)) -> unconstrained ``z`` numpy ``(bs, d)``."""
+        """Physical pytree (leaves scalar, ``(bs,)`` or any leading shape, flattened in C order) -> unconstrained
+        ``z`` numpy ``(bs, d)``."""
         vals = self.prior.flatten_values(params)
-        cols = [np.atleast_1d(d.inverse_np(np.asarray(v))) for (_, d), v in zip(self._leaves, vals)]
+        host = lambda v: np.asarray(v.detach().cpu() if hasattr(v, "detach") else v)
+        cols = [np.atleast_1d(d.inverse_np(host(v))).reshape(-1) for (_, d), v in zip(self._leaves, vals)]
         n = max(len(c) for c in cols)
         return np.stack([np.broadcast_to(c, (n,)) for c in cols], 1).astype(np.float32)
 
@@ -193,15 +214,17 @@ def _autograd_wrap(torch, fn, z):
 class ForwardProbModel(ProbabilisticModel):
     """``src/gigalens/tf/model.py:12-194``: pixel likelihood with the *simulated* image as the variance
     estimate (``stats_pixels``) and/or the image-position likelihood of multiply-imaged sources
-    (``stats_positions``).  The reference defaults ``include_positions=True`` and then fails without
-    centroids; here the default (``None``) means "on when centroids are given"."""
+    (``stats_positions``).  Signature and defaults are the reference's (``tf/model.py:32-44``, ``include_positions=True``).
+    The reference then iterates ``centroids_x`` unconditionally and raises ``TypeError`` when no centroids were given --
+    which is how its own notebooks and ``tests/tf/test_model.py`` call it -- so here ``include_positions`` without
+    centroids simply means "no position term"."""
 
     def __init__(self, prior, observed_image=None, background_rms=None, exp_time=None, error_map=None,
                  centroids_x=None, centroids_y=None, centroids_errors_x=None, centroids_errors_y=None,
-                 include_pixels=True, include_positions=None):
+                 include_pixels=True, include_positions=True):
         super().__init__(prior)
-        if include_positions is None:
-            include_positions = centroids_x is not None
+        if include_positions and centroids_x is None:
+            include_positions = False
         if not include_pixels and not include_positions:
             raise ValueError("include_pixels=False and include_positions=False leave no likelihood term")
         self.include_pixels = bool(include_pixels)
@@ -215,6 +238,7 @@ class ForwardProbModel(ProbabilisticModel):
             if self.error_map is None and (self.background_rms is None or self.exp_time is None):
                 raise ValueError("give either error_map or background_rms and exp_time")
         self.centroids_x = self.centroids_y = self.centroids_errors_x = self.centroids_errors_y = None
+        self.centroids_x_batch = self.centroids_y_batch = None
         if self.include_positions:  # tf/model.py:69-74
             if any(v is None for v in (centroids_x, centroids_y, centroids_errors_x, centroids_errors_y)):
                 raise ValueError("include_positions=True needs centroids_x, centroids_y, centroids_errors_x, centroids_errors_y")
@@ -224,9 +248,13 @@ class ForwardProbModel(ProbabilisticModel):
             self.n_position = 2 * sum(c.size for c in self.centroids_x)
 
     def init_centroids(self, bs):
-        """``tf/model.py:185-194`` tiles the centroids over the batch; the CUDA kernels share one copy between
-        all samples, so there is nothing to do (kept for script compatibility)."""
-        return None
+        """``tf/model.py:185-194``: the centroids tiled over the batch, ``(n_img, bs)`` per system, as
+        ``centroids_x_batch`` / ``centroids_y_batch``.  The likelihood kernels share one copy between all samples and do
+        not read these; they exist so that scripts which feed them to ``simulator.beta`` / ``magnification`` (which
+        accept this tiled layout and answer in it) keep working."""
+        if self.include_positions:
+            self.centroids_x_batch = [np.repeat(cx[:, None], bs, axis=-1) for cx in self.centroids_x]
+            self.centroids_y_batch = [np.repeat(cy[:, None], bs, axis=-1) for cy in self.centroids_y]
 
     def _install_likelihood(self, simulator):
         if self.include_pixels:
@@ -354,6 +382,8 @@ class BackwardProbModel(ProbabilisticModel):
         if self.observed_image.shape != (n, n):
             raise ValueError(f"observed_image must be ({n}, {n})")
         _cabi.check(simulator._lib.gl_plan_set_likelihood(simulator._plan, C.byref(lc)), simulator._lib)
+        if not simulator._lstsq_reserved:
+            simulator.reserve_lstsq()
         simulator.set_option("lstsq", 1)   # log-prob entry points use the linear-amplitude solve
         simulator.set_option("include_pixels", 1)
         simulator.set_option("include_positions", 0)

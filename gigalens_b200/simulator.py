@@ -261,6 +261,8 @@ class LensSimulator(LensSimulatorInterface):
         self._plan = plan
         self._like_owner = None
         self._prior_owner = None
+        # the plan reserves the lstsq workspace itself when a light profile has use_lstsq; other models on first use
+        self._lstsq_reserved = any(getattr(p, "use_lstsq", False) for p in list(phys_model.lens_light) + list(phys_model.source_light))
 
     def __del__(self):
         plan = getattr(self, "_plan", None)
@@ -283,6 +285,14 @@ class LensSimulator(LensSimulatorInterface):
 
     def set_option(self, name, value):
         _cabi.check(self._lib.gl_plan_set_option(self._plan, name.encode(), int(value)), self._lib)
+        if name == "lstsq_chunk":
+            self._lstsq_reserved = True
+
+    def reserve_lstsq(self, chunk=0):
+        """``gl_plan_reserve_lstsq``: the component-stack workspace of ``lstsq_simulate`` (a setup call: the data-path
+        entry points never allocate)."""
+        _cabi.check(self._lib.gl_plan_reserve_lstsq(self._plan, int(chunk)), self._lib)
+        self._lstsq_reserved = True
 
     # -- reference API
     def simulate(self, params, no_deflection=False):
@@ -335,18 +345,39 @@ class LensSimulator(LensSimulatorInterface):
         _cabi.check(self._lib.gl_simulate_ss(self._plan, mat.data_ptr(), img.data_ptr(), self._stream()), self._lib)
         return img
 
+    def _points(self, x, y):
+        """Coordinates of ``beta`` / ``hessian`` / ``magnification``: the kernels evaluate points SHARED by all samples and
+        return ``(bs, npts)``.  The reference passes batch-tiled ``(N, bs)`` coordinates (``init_centroids``, ``img_X``) and
+        gets ``(N, bs)`` back: that layout is recognised (second dimension == bs, all columns equal) and the results come
+        back transposed to ``(N, bs)``; genuinely per-sample coordinates are refused instead of being silently
+        flattened."""
+        host = lambda v: np.asarray(v.detach().cpu() if hasattr(v, "detach") else v, dtype=np.float32)
+        x, y = host(x), host(y)
+        if x.shape != y.shape:
+            raise ValueError(f"x and y differ in shape: {x.shape} vs {y.shape}")
+        ref_layout = x.ndim == 2 and x.shape[1] == self.bs and (self.bs > 1 or x.shape[0] >= 1)
+        if ref_layout:
+            if not (np.array_equal(x, np.broadcast_to(x[:, :1], x.shape)) and np.array_equal(y, np.broadcast_to(y[:, :1], y.shape))):
+                raise ValueError("per-sample (N, bs) coordinates are not supported: the points must be shared by all samples "
+                                 "(tile one column over the batch, as the reference's init_centroids does)")
+            x, y = x[:, 0], y[:, 0]
+        torch = self._torch
+        xt = torch.as_tensor(np.ascontiguousarray(x.reshape(-1))).to(self.device)
+        yt = torch.as_tensor(np.ascontiguousarray(y.reshape(-1))).to(self.device)
+        return xt, yt, ref_layout
+
     def eval_points(self, params, x, y, mode=0, missing_ok=()):
-        """mode 0: beta, 1: total deflection, 2: surface brightness, at points shared by all samples."""
+        """mode 0: beta, 1: total deflection, 2: surface brightness, at points shared by all samples
+        (``(bs, npts)``; ``(N, bs)`` when the coordinates came in the reference's tiled ``(N, bs)`` layout)."""
         torch = self._torch
         mat = self._params_matrix(params, missing_ok)
-        xt = torch.as_tensor(np.array(x, dtype=np.float32).reshape(-1)).to(self.device)
-        yt = torch.as_tensor(np.array(y, dtype=np.float32).reshape(-1)).to(self.device)
+        xt, yt, ref_layout = self._points(x, y)
         npts = xt.numel()
         o0 = torch.empty((self.bs, npts), dtype=torch.float32, device=self.device)
         o1 = torch.empty((self.bs, npts), dtype=torch.float32, device=self.device)
         _cabi.check(self._lib.gl_eval_points(self._plan, mat.data_ptr(), npts, xt.data_ptr(), yt.data_ptr(), int(mode),
                                              o0.data_ptr(), o1.data_ptr(), self._stream()), self._lib)
-        return o0, o1
+        return (o0.T, o1.T) if ref_layout else (o0, o1)
 
     def beta(self, x, y, lens_params: List[Dict]):
         """``tf/simulator.py:72-78`` at points ``(x, y)`` shared by all samples -> ``(bs, npts)`` each."""
@@ -358,13 +389,12 @@ class LensSimulator(LensSimulatorInterface):
         from every profile's ``hessian`` (``tf/simulator.py:80-107``).  FP64 forward-mode duals on the GPU."""
         torch = self._torch
         mat = self._params_matrix({"lens_mass": lens_params}, ("lens_light", "source_light"))
-        xt = torch.as_tensor(np.array(x, dtype=np.float32).reshape(-1)).to(self.device)
-        yt = torch.as_tensor(np.array(y, dtype=np.float32).reshape(-1)).to(self.device)
+        xt, yt, ref_layout = self._points(x, y)
         npts = xt.numel()
         H = [torch.empty((self.bs, npts), dtype=torch.float32, device=self.device) for _ in range(4)]
         _cabi.check(self._lib.gl_hessian(self._plan, mat.data_ptr(), npts, xt.data_ptr(), yt.data_ptr(),
                                          *(h.data_ptr() for h in H), self._stream()), self._lib)
-        return tuple(H)
+        return tuple(h.T for h in H) if ref_layout else tuple(H)
 
     def magnification(self, x, y, lens_params: List[Dict]):
         """``tf/simulator.py:80-91``: ``1 / det(I - H)``; infinite on critical curves, like the reference."""
@@ -424,6 +454,8 @@ class LensSimulator(LensSimulatorInterface):
         unit-amplitude components ``(bs, n, n, D)`` (``:203-229``)."""
         torch = self._torch
         self._install_lstsq_data(observed_image, err_map)
+        if not self._lstsq_reserved:
+            self.reserve_lstsq()
         mat = self._params_matrix(params)
         n = self.numPix
         if return_stacked:

@@ -11,7 +11,9 @@
  *     gl_last_error() (thread-local).  No exceptions cross the ABI, no torch types.
  *   - "dev" pointers are CUDA device pointers owned by the caller; "host" pointers are ordinary
  *     host memory.  The plan owns only its workspace and its copies of the static inputs
- *     (grid, mask, PSF, observation, catalogue).  No allocation happens per call.
+ *     (grid, mask, PSF, observation, catalogue).  Memory is allocated only by the setup calls
+ *     (gl_plan_create, gl_plan_set_likelihood / _prior / _positions, gl_plan_reserve_lstsq); the data-path
+ *     entry points (simulate, log-likelihood, log-prob, lstsq) allocate nothing and set no function attributes.
  *   - Kernels are launched asynchronously on the caller's `stream` (a cudaStream_t passed as
  *     void*; NULL = legacy default stream).  No entry point synchronises except the *_host ones.
  *   - A plan is bound to one device and one batch size and is not thread-safe.
@@ -223,6 +225,16 @@ int gl_lstsq_stack(gl_plan* plan, const float* params_dev, float* stack_dev, voi
 int gl_lstsq_loglike_grad(gl_plan* plan, const float* params_dev, float* loglike_dev, float* red_chi2_dev,
                           float* dparams_dev, void* stream);
 int32_t gl_plan_depth(const gl_plan* plan); /* D: number of linear light components */
+/* Workspace of the lstsq entry points: the component stack [chunk][D][(n*ss)^2] and its convolved copy; chunk = samples
+ * per pass, 0 = sized by a memory budget (at most 32 GB / 40 % of the free memory).  gl_plan_create reserves it for models
+ * with a GL_FLAG_USE_LSTSQ light profile; any other model that wants lstsq_simulate (the reference treats every light
+ * profile as a linear component there, tf/simulator.py:183-200) calls this once first.  Re-reserving synchronises. */
+int gl_plan_reserve_lstsq(gl_plan* plan, int32_t chunk);
+
+/* --- measurement aid --------------------------------------------------------------------- */
+/* Measured FP32 FMA peak of `device` in TFLOP/s (FMA = 2): independent register chains, no memory; scalar FFMA and
+ * packed FFMA2 variants, best of 5 launches each, CUDA-event timed.  bench.py's roofline denominator. */
+int gl_fp32_peak(int32_t device, float* tflops_ffma, float* tflops_ffma2);
 
 #ifdef __cplusplus
 }

@@ -260,6 +260,41 @@ class OracleSimulator:
         ret = self._conv_pool(img[:, None])[:, 0]
         return torch.squeeze(ret) * self.conversion_factor  # :156
 
+    def _finish(self, img):
+        """NaN scrub, (bs, H, W) transpose, conv + pool, squeeze, conversion factor: the tail every
+        ``simulate_*`` variant of the reference repeats verbatim (e.g. :251-266)."""
+        img = torch.where(torch.isnan(img), torch.zeros_like(img), img)
+        ret = self._conv_pool(img.permute(2, 0, 1)[:, None])[:, 0]
+        return torch.squeeze(ret) * self.conversion_factor
+
+    def simulate_source(self, params):
+        """tf/simulator.py:242-266: the source light evaluated on the IMAGE-plane grid (no ray-shooting)."""
+        pm = self.phys_model
+        nss = self.num_pix * self.supersample
+        img = torch.zeros((nss, nss, self.bs), dtype=self.dtype)
+        for lm, p, c in zip(pm.source_light, params["source_light"], pm.source_light_constants):
+            img = img + self._scatter(lm.light(self.img_X, self.img_Y, **p, **self._c(c)))
+        return self._finish(img)
+
+    def simulate_lens_light(self, params):
+        """tf/simulator.py:268-293."""
+        pm = self.phys_model
+        nss = self.num_pix * self.supersample
+        img = torch.zeros((nss, nss, self.bs), dtype=self.dtype)
+        for lm, p, c in zip(pm.lens_light, params["lens_light"], pm.lens_light_constants):
+            img = img + self._scatter(lm.light(self.img_X, self.img_Y, **p, **self._c(c)))
+        return self._finish(img)
+
+    def simulate_images(self, params):
+        """tf/simulator.py:295-328: the lensed source only."""
+        pm = self.phys_model
+        beta_x, beta_y = self.beta(self.img_X, self.img_Y, params["lens_mass"])
+        nss = self.num_pix * self.supersample
+        img = torch.zeros((nss, nss, self.bs), dtype=self.dtype)
+        for lm, p, c in zip(pm.source_light, params["source_light"], pm.source_light_constants):
+            img = img + self._scatter(lm.light(beta_x, beta_y, **p, **self._c(c)))
+        return self._finish(img)
+
     def lstsq_stack(self, params, no_deflection=False):
         """(bs, ny, nx, D): every linear light component, unit amplitude, convolved and pooled."""
         lens_params, ll_params, sl_params = self._split(params)

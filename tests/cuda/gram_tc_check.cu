@@ -20,7 +20,8 @@ static int run_case(int D, int npx, int bs, int mode, bool verbose) {
   cudaMalloc(&dR, R.size() * 4); cudaMalloc(&dw, npx * 4); cudaMalloc(&dobs, npx * 4); cudaMalloc(&dG, (size_t)bs * Dx * Dx * 4); cudaMalloc(&derr, 4);
   cudaMemcpy(dR, R.data(), R.size() * 4, cudaMemcpyHostToDevice); cudaMemcpy(dw, w.data(), npx * 4, cudaMemcpyHostToDevice);
   cudaMemcpy(dobs, obs.data(), npx * 4, cudaMemcpyHostToDevice); cudaMemset(dG, 0, (size_t)bs * Dx * Dx * 4); cudaMemset(derr, 0, 4);
-  cudaError_t e = gl_launch_gram_tc(bs, D, npx, dR, dw, dobs, dG, derr, 0);
+  cudaError_t e = gl_gram_tc_init();
+  if (e == cudaSuccess) e = gl_launch_gram_tc(bs, D, npx, dR, dw, dobs, dG, derr, 0);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 2; }
   std::vector<float> G((size_t)bs * Dx * Dx); int err = 0;

@@ -341,6 +341,47 @@ def test_simulate_variants_add_up():
     assert not np.allclose(nod, full, rtol=1e-3)
 
 
+@pytest.mark.parametrize("which", ["c2", "masked_shapelets"])
+def test_simulate_variants_and_no_deflection_match_oracle(which):
+    """simulate_source / simulate_lens_light / simulate_images (tf/simulator.py:242-328) and simulate(no_deflection=True)
+    (:125-126) against the oracle's restatement of each, on the C2 model and on a masked model with two source
+    components (SersicEllipse + free-amplitude Shapelets)."""
+    if which == "c2":
+        wl = workloads.c2_workload()
+        pm, sc, bs = wl["phys_model"], wl["sim_config"], 3
+        sim = LensSimulator(pm, sc, bs=bs)
+        cm = sim.compiled
+        mat = cm.flatten(wl["prior"].sample(bs, seed=6), bs, torch, "cpu").numpy()
+    else:
+        n, bs = 24, 3
+        pm = PhysicalModel([epl.EPL(30), shear.Shear()], [sersic.Sersic()], [sersic.SersicEllipse(), shapelets.Shapelets(3)])
+        mask = (np.random.default_rng(2).uniform(size=(n, n)) > 0.2).astype(np.float32)
+        sc = SimulatorConfig(delta_pix=0.1, num_pix=n, supersample=2, kernel=workloads.load_psf()[4:9, 4:9], pix_region=mask)
+        sim = LensSimulator(pm, sc, bs=bs)
+        cm = sim.compiled
+        mat = common.draw_matrix(cm, bs, seed=13).astype(np.float32)
+    n = sc.num_pix
+    dev_params = cm.unflatten(torch.as_tensor(mat, device="cuda"))
+    got = dict(source=sim.simulate_source(dev_params), lens_light=sim.simulate_lens_light(dev_params),
+               images=sim.simulate_images(dev_params), no_deflection=sim.simulate(dev_params, no_deflection=True),
+               full=sim.simulate(dev_params))
+    got = {k: v.cpu().numpy().reshape(bs, n, n) for k, v in got.items()}
+
+    def oracle(m, dt):
+        osim = OracleSimulator(common.to_oracle_model(pm, dt), sc.delta_pix, n, sc.supersample, kernel=sc.kernel,
+                               pix_region=sc.pix_region, bs=bs, dtype=dt)
+        p, _ = common.matrix_to_pytree(cm, m, dt)
+        with torch.no_grad():
+            out = dict(source=osim.simulate_source(p), lens_light=osim.simulate_lens_light(p), images=osim.simulate_images(p),
+                       no_deflection=osim.simulate(p, no_deflection=True), full=osim.simulate(p))
+        return {k: v.numpy().reshape(bs, n, n) for k, v in out.items()}
+
+    o32, o64, o64p = oracle(mat, torch.float32), oracle(mat.astype(np.float64), torch.float64), oracle(common.ulp_perturb(mat), torch.float64)
+    for k in got:
+        assert_parity(got[k], o32[k], o64[k], 1e-5, f"simulate variant {k}", o64p[k], axis=(1, 2))
+    assert not np.allclose(got["no_deflection"], got["full"], rtol=1e-3)
+
+
 @pytest.mark.parametrize("packed", [1, 0])
 def test_nan_pixels_are_scrubbed_and_pass_no_gradient(packed):
     """tf.where(is_nan(img), 0, img) (tf/simulator.py:140): a sample whose source amplitude is NaN
@@ -640,6 +681,96 @@ def test_c4_cluster_full_size_properties():
           " dz rel median/99%/max", np.median(dz_rel), np.percentile(dz_rel, 99), dz_rel.max())
     assert np.median(lp_rel) < 1e-6 and np.percentile(lp_rel, 99) < 1e-5
     assert np.median(dz_rel) < 1e-5 and np.percentile(dz_rel, 99) < 1e-4
+
+
+def _c4_truth():
+    """The prior draw `workloads.c4_observation()` simulates (seed 11), as a pytree of python floats."""
+    wl = workloads.c4_workload()
+    draw = wl["prior"].sample(1, seed=11)
+    return {g: [{k: float(np.asarray(v).reshape(-1)[0]) for k, v in d.items()} for d in draw[g]] for g in draw}
+
+
+def test_c4_cluster_baseline_geometry_parity():
+    """BASELINE.json configs[3] at its real geometry -- 200x200, ss = 2, +-10 arcsec field, NFW + 30-member dPIE scaling
+    relation + shear -- against the fp32 / fp64 / ulp-perturbed oracle at bs = 4: supersampled image, image, log-like,
+    every d/d(param) row, and log_prob / d log_prob / dz (scaling_relation.py:57-70, piemd.py:183-255)."""
+    obs = workloads.c4_observation()
+    wl = workloads.c4_workload(observed=obs)
+    bs = 4
+    sim = LensSimulator(wl["phys_model"], wl["sim_config"], bs=bs)
+    pmod = ForwardProbModel(wl["prior"], wl["observed"], background_rms=wl["background_rms"], exp_time=wl["exp_time"])
+    cm = sim.compiled
+    z = pmod.bij_inverse(wl["prior"].sample(bs, seed=3))
+    z[0] = pmod.bij_inverse(_c4_truth())[0] + 0.01          # one sample next to the truth (a well-fitting model)
+    zdev = torch.as_tensor(z, device="cuda")
+    mat = sim._params_matrix(pmod.bij_forward(sim, zdev)).cpu().numpy()
+    dev = torch.as_tensor(mat, device="cuda")
+    ss = sim.simulate_ss(dev).cpu().numpy()
+    img = sim.simulate(dev).cpu().numpy().reshape(bs, 200, 200)
+    ll, chi2, g = (t.cpu().numpy() for t in pmod.loglike_and_grad(sim, dev))
+    logp, chi2z, dz = (t.cpu().numpy() for t in pmod.log_prob_and_grad(sim, zdev))
+
+    def oracle(m, dt):
+        osim, _ = oracle_bridge.build_oracle(wl, bs, dt)
+        p, _ = common.matrix_to_pytree(cm, m, dt)
+        with torch.no_grad():
+            s = osim.simulate_ss(p).permute(2, 0, 1).numpy()
+        return (s,) + oracle_bridge.loglike_and_grad_matrix(wl, cm, m, dt)
+
+    ss32, ll32, chi32, im32, g32 = oracle(mat, torch.float32)
+    ss64, ll64, chi64, im64, g64 = oracle(mat.astype(np.float64), torch.float64)
+    ss64p, ll64p, chi64p, im64p, g64p = oracle(common.ulp_perturb(mat), torch.float64)
+    im32, im64, im64p = (v.reshape(bs, 200, 200) for v in (im32, im64, im64p))
+    assert_parity(ss, ss32, ss64, 1e-5, "C4 ss image", ss64p, axis=(1, 2))
+    assert_parity(img, im32, im64, 1e-5, "C4 image", im64p, axis=(1, 2))
+    assert_parity(ll[:, None], ll32[:, None], ll64[:, None], 1e-5, "C4 log-like", ll64p[:, None], axis=1)
+    assert_parity(chi2[:, None], chi32[:, None], chi64[:, None], 1e-5, "C4 red chi2", chi64p[:, None], axis=1)
+    for k in range(cm.n_params):
+        assert_parity(g[k], g32[k], g64[k], 1e-4, f"C4 grad {cm.slot_keys[k]}", g64p[k])
+    # log_prob and its gradient in z (prior + bijector chain on top of the above)
+    r_logp, r_chi2, r_dz = oracle_bridge.logprob_and_grad(wl, z.astype(np.float64), torch.float64)
+    s_logp, s_chi2, s_dz = oracle_bridge.logprob_and_grad(wl, z, torch.float32)
+    p_logp, p_chi2, p_dz = oracle_bridge.logprob_and_grad(wl, common.ulp_perturb(z), torch.float64)
+    assert_parity(logp[:, None], s_logp[:, None], r_logp[:, None], 1e-5, "C4 logp", p_logp[:, None], axis=1)
+    assert_parity(chi2z[:, None], s_chi2[:, None], r_chi2[:, None], 1e-5, "C4 red chi2 (z)", p_chi2[:, None], axis=1)
+    for k in range(z.shape[1]):
+        assert_parity(dz[:, k], s_dz[:, k], r_dz[:, k], 1e-4, f"C4 dz[{k}]", p_dz[:, k])
+
+
+@pytest.mark.parametrize("include_pixels", [False, True])
+def test_c4_cluster_positions_parity(include_pixels):
+    """The image-position term (tf/model.py:103-124) on the C4 model at its real geometry: two multiply-imaged point
+    sources found at the truth by the fp64 oracle, log_prob / dz with the positions alone and added to the pixels."""
+    truth = _c4_truth()
+    wl = workloads.c4_workload(observed=workloads.c4_observation() if include_pixels else None)
+    cen = dict(x=[], y=[], ex=[], ey=[])
+    sx, sy = truth["source_light"][0]["center_x"], truth["source_light"][0]["center_y"]
+    for k, beta_s in enumerate([(sx, sy), (sx + 0.4, sy - 0.3)]):
+        imgs = oracle_bridge.find_images(wl, truth, beta_s, 10.0, n_grid=96)
+        if len(imgs) < 2:
+            continue
+        rng = np.random.default_rng(50 + k)
+        imgs = imgs + rng.normal(0, 0.02, imgs.shape)
+        cen["x"].append(imgs[:, 0].astype(np.float32)); cen["y"].append(imgs[:, 1].astype(np.float32))
+        cen["ex"].append(np.full(len(imgs), 0.03, np.float32)); cen["ey"].append(np.full(len(imgs), 0.04, np.float32))
+    assert len(cen["x"]) >= 1, "no multiply-imaged source found at the C4 truth"
+    wl = dict(wl, centroids=cen, include_pixels=include_pixels)
+    bs = 4
+    sim = LensSimulator(wl["phys_model"], wl["sim_config"], bs=bs)
+    pmod = ForwardProbModel(wl["prior"], wl["observed"] if include_pixels else None, background_rms=wl["background_rms"],
+                            exp_time=wl["exp_time"], centroids_x=cen["x"], centroids_y=cen["y"], centroids_errors_x=cen["ex"],
+                            centroids_errors_y=cen["ey"], include_pixels=include_pixels)
+    z0 = pmod.bij_inverse(truth)
+    z = (z0 + np.random.default_rng(4).normal(0, 0.01, size=(bs, z0.shape[1]))).astype(np.float32)
+    logp, chi2, dz = (t.cpu().numpy() for t in pmod.log_prob_and_grad(sim, torch.as_tensor(z, device="cuda")))
+    r_logp, r_chi2, r_dz = oracle_bridge.logprob_and_grad(wl, z.astype(np.float64), torch.float64)
+    s_logp, s_chi2, s_dz = oracle_bridge.logprob_and_grad(wl, z, torch.float32)
+    p_logp, p_chi2, p_dz = oracle_bridge.logprob_and_grad(wl, common.ulp_perturb(z), torch.float64)
+    tag = "pixels+positions" if include_pixels else "positions"
+    assert_parity(logp[:, None], s_logp[:, None], r_logp[:, None], 1e-5, f"C4 {tag} logp", p_logp[:, None], axis=1)
+    assert_parity(chi2[:, None], s_chi2[:, None], r_chi2[:, None], 1e-5, f"C4 {tag} red chi2", p_chi2[:, None], axis=1)
+    for k in range(z.shape[1]):
+        assert_parity(dz[:, k], s_dz[:, k], r_dz[:, k], 1e-4, f"C4 {tag} dz[{k}]", p_dz[:, k])
 
 
 @pytest.mark.parametrize("tag,include_pixels", [("pos", False), ("both", True)])
