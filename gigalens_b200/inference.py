@@ -97,6 +97,33 @@ class ModellingSequence:
         self.prob_model = prob_model
         self.sim_config = sim_config
         self._simulator_cls = simulator_cls   # injectable so the sharding / collective logic is testable on CPU
+        self._coll_events = None              # measurement aid: CUDA event pairs around every all-reduce (bench.py)
+
+    def time_collectives(self, on=True):
+        """Record CUDA events on the current stream around every all-reduce of SVI / HMC from now on."""
+        self._coll_events = [] if on else None
+
+    def collective_ms(self):
+        """Device time (ms) spent in (waiting for) the all-reduces recorded so far and their count; synchronises."""
+        import torch
+
+        if not self._coll_events:
+            return 0.0, 0
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in self._coll_events), len(self._coll_events)
+
+    def _all_reduce(self, dist, t):
+        if self._coll_events is None or not t.is_cuda:
+            dist.all_reduce(t)
+            return t
+        import torch
+
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.all_reduce(t)
+        e1.record()
+        self._coll_events.append((e0, e1))
+        return t
 
     # ------------------------------------------------------------------ MAP
     def MAP(self, optimizer=None, start=None, n_samples=500, num_steps=350, seed=0, gather=True, callback=None,
@@ -207,7 +234,7 @@ class ModellingSequence:
             loss = (logq - torch.where(good, logp, torch.zeros_like(logp))).sum() / n_vi
             packed = torch.cat([loss.detach().reshape(1), g])
             if world > 1:
-                dist.all_reduce(packed)   # the one collective of SVI: [ELBO, grad_mu, grad_L]
+                self._all_reduce(dist, packed)   # the one collective of SVI: [ELBO, grad_mu, grad_L]
             loss_buf[step] = packed[0]
             with torch.no_grad():
                 optimizer.step(theta, torch.nan_to_num(packed[1:], nan=0.0, posinf=0.0, neginf=0.0))
@@ -248,7 +275,7 @@ class ModellingSequence:
 
         def allsum(t):
             if world > 1:
-                dist.all_reduce(t)
+                self._all_reduce(dist, t)
             return t
 
         n_adapt = int(num_burnin_steps * 0.8)

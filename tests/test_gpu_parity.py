@@ -415,6 +415,46 @@ def test_nan_pixels_are_scrubbed_and_pass_no_gradient(packed):
     assert np.array_equal(again[2], clean[2])
 
 
+def test_lstsq_nan_components_are_scrubbed_per_component():
+    """tf/simulator.py:200 scrubs the lstsq component stack per component: a sample whose SOURCE components are NaN
+    (NaN source centre) keeps the full gradient of its lens-light component -- the same as when the source is moved out of
+    the field -- and the plan carries no NaN bookkeeping over from one call to the next (`d_nan` was never
+    written on this path)."""
+    from gigalens_b200 import distributions as tfd
+    bs = 4
+    wl = workloads.c3_workload(n_max=4)
+    pm = PhysicalModel(wl["phys_model"].lenses, [sersic.SersicEllipse(use_lstsq=True)], wl["phys_model"].source_light)
+    prior = dict(wl["prior"].model)
+    prior["lens_light"] = [dict(R_sersic=tfd.LogNormal(0.0, 0.15), n_sersic=tfd.Uniform(2, 6), e1=tfd.Normal(0, 0.1),
+                                e2=tfd.Normal(0, 0.1), center_x=tfd.Normal(0, 0.05), center_y=tfd.Normal(0, 0.05))]
+    prior = tfd.JointDistributionNamed(prior)
+    sim = LensSimulator(pm, wl["sim_config"], bs=bs)
+    pmod = BackwardProbModel(prior, wl["observed"], wl["background_rms"], wl["exp_time"])
+    cm = sim.compiled
+    mat = cm.flatten(prior.sample(bs, seed=12), bs, torch, "cpu").numpy()
+    k_cx = [i for i, k in enumerate(cm.slot_keys) if k[0] == "source_light" and k[2] == "center_x"][0]
+    ll_rows = [i for i, k in enumerate(cm.slot_keys) if k[0] == "lens_light"]
+    run = lambda m: [t.cpu().numpy() for t in pmod.loglike_and_grad(sim, torch.as_tensor(m, device="cuda"))]
+    # poison the plan's NaN bookkeeping first through the plain simulate path (every pixel of sample 2 scrubbed)
+    poison = mat.copy(); poison[k_cx, 2] = np.nan
+    sim.simulate(torch.as_tensor(poison, device="cuda"))
+    clean = run(mat)
+    assert np.isfinite(clean[0]).all() and np.isfinite(clean[2]).all()
+    nan_src, far_src = mat.copy(), mat.copy()
+    nan_src[k_cx, 1] = np.nan
+    far_src[k_cx, 1] = 1.0e4
+    a, b = run(nan_src), run(far_src)
+    assert np.isfinite(a[0]).all() and np.isfinite(a[1]).all()
+    assert np.allclose(a[0][1], b[0][1], rtol=1e-5) and np.allclose(a[1][1], b[1][1], rtol=1e-5)
+    ga, gb = a[2][ll_rows, 1], b[2][ll_rows, 1]
+    assert np.isfinite(ga).all() and np.abs(gb).max() > 0
+    assert np.max(np.abs(ga - gb)) <= 1e-4 * np.abs(gb).max()
+    keep = [0, 2, 3]
+    assert np.array_equal(a[0][keep], clean[0][keep]) and np.array_equal(a[2][:, keep], clean[2][:, keep])
+    again = run(mat)
+    assert np.array_equal(again[0], clean[0]) and np.array_equal(again[2], clean[2])
+
+
 # ---------------------------------------------------------------------------------------------
 # lensing Hessian, magnification and the image-position likelihood (SURVEY.md section 8f row 1)
 # ---------------------------------------------------------------------------------------------
