@@ -74,10 +74,29 @@ struct GlConvGeom {
 __host__ __device__ constexpr int glc_ulen(int A) { return (A + 2 * GLC_RY - 2 + 3) & ~3; }   // floats per U copy
 // taps table: [phase][b][copy(2)][ulen]
 
+// Where the tap pairs come from.
+//   GlTapsSmem : the packed table staged in shared memory; a pair is one broadcast LDS.64 (one LSU wavefront per 4 FFMA2 --
+//                with the strip loads that put the shared-memory pipe at ~90 % of the FMA pipe's cycles, the co-limiter ncu showed).
+//   GlTapsConst: the same table passed BY VALUE as a __grid_constant__ kernel parameter (constant bank 0).  The index is warp-uniform,
+//                so the compiler loads a pair with LDCU.64 into a uniform register pair and FFMA2 takes that pair as its
+//                operand (`FFMA2 R, R.F32, UR.F32x2, R`): tap traffic leaves the LSU entirely and needs no shared memory.
+//                Used when the table fits the parameter space (NF * 4 <= GLC_CONST_TAP_BYTES).
+#define GLC_CONST_TAP_BYTES (24 * 1024)
+template <int NF> struct alignas(16) GlTapsC { float w[NF > 0 ? NF : 4]; };
+struct GlTapsSmem {
+  const float* u;
+  __device__ __forceinline__ float2 pair(int off) const { return *reinterpret_cast<const float2*>(u + off); }
+};
+template <int NF> struct GlTapsConst {
+  const GlTapsC<NF>& T;
+  int base;
+  __device__ __forceinline__ float2 pair(int off) const { return *reinterpret_cast<const float2*>(&T.w[base + off]); }
+};
+
 // LW = floats per strip load: 4 (LDS.128, strip origin 16-byte aligned) or 2 (LDS.64, 8-byte aligned origin -- the
 // TMA-staged tile, whose first column is rounded down to the unit's 16-byte coordinate granularity).
-template <int A, int MASK, int LW>
-__device__ __forceinline__ void corr_row2(const float* __restrict__ inrow, const float* __restrict__ urow /* &U[0][copy][j0e] */,
+template <int A, int MASK, int LW, class Taps>
+__device__ __forceinline__ void corr_row2(const float* __restrict__ inrow, const Taps& taps, int uoff /* offset of U[0][copy][j0e] */,
                                           float2 (&acc2)[GLC_RP][GLC_RX]) {
   constexpr int SL = (GLC_RX + A - 1 + 3) & ~3;
   constexpr int UL = glc_ulen(A);
@@ -99,11 +118,10 @@ __device__ __forceinline__ void corr_row2(const float* __restrict__ inrow, const
   }
 #pragma unroll
   for (int b = 0; b < A; ++b) {
-    const float2* u2 = reinterpret_cast<const float2*>(urow + b * 2 * UL);
 #pragma unroll
     for (int rp = 0; rp < GLC_RP; ++rp) {
       if ((MASK >> rp) & 1) {
-        const float2 w2 = u2[rp];
+        const float2 w2 = taps.pair(uoff + b * 2 * UL + 2 * rp);
 #pragma unroll
         for (int c = 0; c < GLC_RX; ++c) {
           const float sv = strip[c + b];
@@ -114,9 +132,18 @@ __device__ __forceinline__ void corr_row2(const float* __restrict__ inrow, const
   }
 }
 
-// acc2 += correlation of the thread's strip (origin `in`) with the taps of one phase (table `u`).
-template <int A, int LW = 4>
-__device__ __forceinline__ void corr_rows2(const float* __restrict__ in, int pitch, const float* __restrict__ u,
+// the pairs a ramp-up / ramp-down row reaches form a contiguous range [LO, HI]: one instance per range, picked by a uniform if-chain
+template <int A, int LW, class Taps, int LO = 0, int HI = 0>
+__device__ __forceinline__ void corr_row2_ramp(int lo_p, int hi_p, const float* __restrict__ inrow, const Taps& taps, int uoff,
+                                               float2 (&acc2)[GLC_RP][GLC_RX]) {
+  if (lo_p == LO && hi_p == HI) corr_row2<A, ((1 << (HI + 1)) - 1) & ~((1 << LO) - 1), LW>(inrow, taps, uoff, acc2);
+  else if constexpr (HI + 1 < GLC_RP) corr_row2_ramp<A, LW, Taps, LO, HI + 1>(lo_p, hi_p, inrow, taps, uoff, acc2);
+  else if constexpr (LO + 1 < GLC_RP) corr_row2_ramp<A, LW, Taps, LO + 1, LO + 1>(lo_p, hi_p, inrow, taps, uoff, acc2);
+}
+
+// acc2 += correlation of the thread's strip (origin `in`) with the taps of one phase (`taps` addresses that phase's table).
+template <int A, int LW, class Taps>
+__device__ __forceinline__ void corr_rows2_t(const float* __restrict__ in, int pitch, const Taps& taps,
                                            float2 (&acc2)[GLC_RP][GLC_RX]) {
   constexpr int UL = glc_ulen(A);
   constexpr int ROWS = GLC_RY + A - 1;
@@ -124,25 +151,20 @@ __device__ __forceinline__ void corr_rows2(const float* __restrict__ in, int pit
   for (int row = 0; row < ROWS; ++row) {
     const int j0 = A + GLC_RY - 2 - row;
     // copy 1 holds U shifted left by one float, so an odd j0 reads copy 1 at index j0 - 1 (even)
-    const float* up = (j0 & 1) ? (u + UL + (j0 - 1)) : (u + j0);
+    const int uoff = (j0 & 1) ? (UL + (j0 - 1)) : j0;
     const int lo_r = row - (A - 1) > 0 ? row - (A - 1) : 0;
     const int hi_r = row < GLC_RY - 1 ? row : GLC_RY - 1;
     const int lo_p = lo_r >> 1, hi_p = hi_r >> 1;
     const float* inrow = in + row * pitch;
-    if (lo_p == 0 && hi_p == GLC_RP - 1) corr_row2<A, (1 << GLC_RP) - 1, LW>(inrow, up, acc2);
-    else {
-      int mask = 0;
-      for (int q = lo_p; q <= hi_p; ++q) mask |= 1 << q;
-      switch (mask) {
-        case 1: corr_row2<A, 1, LW>(inrow, up, acc2); break;
-        case 2: corr_row2<A, 2, LW>(inrow, up, acc2); break;
-        case 3: corr_row2<A, 3, LW>(inrow, up, acc2); break;
-        case 4: corr_row2<A, 4, LW>(inrow, up, acc2); break;
-        case 6: corr_row2<A, 6, LW>(inrow, up, acc2); break;
-        default: corr_row2<A, 7, LW>(inrow, up, acc2); break;
-      }
-    }
+    if (lo_p == 0 && hi_p == GLC_RP - 1) corr_row2<A, (1 << GLC_RP) - 1, LW>(inrow, taps, uoff, acc2);
+    else corr_row2_ramp<A, LW, Taps>(lo_p, hi_p, inrow, taps, uoff, acc2);
   }
+}
+// shared-memory table: the signature the cp.async kernels use
+template <int A, int LW = 4>
+__device__ __forceinline__ void corr_rows2(const float* __restrict__ in, int pitch, const float* __restrict__ u,
+                                           float2 (&acc2)[GLC_RP][GLC_RX]) {
+  corr_rows2_t<A, LW>(in, pitch, GlTapsSmem{u}, acc2);
 }
 
 struct GlLikeArgs {
@@ -350,10 +372,13 @@ __device__ __forceinline__ void glc_bulk_load(void* dst, const void* src, unsign
 // starts at the column rounded down to a multiple of 4 and is 4 columns wider (pitch tma_pitch); the thread
 // strips then start r = 0 or 2 floats into it and are read with LDS.64.
 // Needs n % 4 == 0 (16-byte global strides), even shifts and a tile of at most 256 x 256; otherwise k_conv_fwd runs.
-template <int A>
+// NFC > 0: the tap table (NFC floats) arrives as the by-value parameter `ctaps` and is read through the uniform datapath
+// (GlTapsConst); NFC == 0: it is staged in shared memory from `wts` as before.
+template <int A, int NFC = 0>
 __global__ void __maxnreg__(96) k_conv_fwd_tma(const __grid_constant__ CUtensorMap tmap, GlConvGeom g, const float* __restrict__ wts,
                                                float scale, float* __restrict__ img, GlLikeArgs like,
-                                               float* __restrict__ part, float* __restrict__ gimg) {
+                                               float* __restrict__ part, float* __restrict__ gimg,
+                                               const __grid_constant__ GlTapsC<NFC> ctaps) {
   extern __shared__ __align__(128) float glc_smem_ft[];
   float* smem = glc_smem_ft;
   const int nph = g.ss * g.ss;
@@ -384,8 +409,10 @@ __global__ void __maxnreg__(96) k_conv_fwd_tma(const __grid_constant__ CUtensorM
     glc_tma_load_3d(s_in + (q & 1) * tstride, &tmap, (ox0 - sx) & ~3, oy0 - sy, b * nph + q, &s_bar[q & 1]);
   };
   if (tid == 0) {
-    glc_mbar_expect_tx(&s_bar[2], (unsigned)(nph * UTAB) * 4u);
-    glc_bulk_load(s_w, wts, (unsigned)(nph * UTAB) * 4u, &s_bar[2]);
+    if constexpr (NFC == 0) {
+      glc_mbar_expect_tx(&s_bar[2], (unsigned)(nph * UTAB) * 4u);
+      glc_bulk_load(s_w, wts, (unsigned)(nph * UTAB) * 4u, &s_bar[2]);
+    }
     issue_phase(0);
     if (nph > 1) issue_phase(1);
   }
@@ -399,7 +426,8 @@ __global__ void __maxnreg__(96) k_conv_fwd_tma(const __grid_constant__ CUtensorM
     for (int c = 0; c < GLC_RX; ++c) acc2[r][c] = make_float2(0.f, 0.f);
   const int origin = ty * GLC_RY * g.tma_pitch + tx * GLC_RX;
 
-  bool ok = glc_mbar_wait(&s_bar[2], 0);
+  bool ok = true;
+  if constexpr (NFC == 0) ok = glc_mbar_wait(&s_bar[2], 0);
   for (int q = 0; q < nph; ++q) {
     ok = glc_mbar_wait(&s_bar[q & 1], (unsigned)(q >> 1) & 1u) && ok;
     if (active) {
@@ -407,7 +435,8 @@ __global__ void __maxnreg__(96) k_conv_fwd_tma(const __grid_constant__ CUtensorM
       const int pyi = q / g.ss, pxi = q - pyi * g.ss;
       const int ph = ((pyi + g.pad) % g.ss) * g.ss + (pxi + g.pad) % g.ss;
       const int r = (ox0 - (pxi + g.pad) / g.ss) & 3;      // columns between the aligned tile start and the first one needed
-      corr_rows2<A, 2>(s_in + (q & 1) * tstride + origin + r, g.tma_pitch, s_w + ph * UTAB, acc2);
+      if constexpr (NFC > 0) corr_rows2_t<A, 2>(s_in + (q & 1) * tstride + origin + r, g.tma_pitch, GlTapsConst<NFC>{ctaps, ph * UTAB}, acc2);
+      else corr_rows2<A, 2>(s_in + (q & 1) * tstride + origin + r, g.tma_pitch, s_w + ph * UTAB, acc2);
     }
     if (q + 2 < nph) {
       // Buffer hand-back without a CTA barrier: every warp reports that it is done with this buffer and moves on to
@@ -506,9 +535,10 @@ __global__ void __launch_bounds__(256, 2) k_conv_bwd(GlConvGeom g, const float* 
 // cp.async.bulk.tensor store, which clips the tile against the image bounds by itself -- the per-element
 // address arithmetic and range tests of k_conv_bwd's loader and writer (a quarter of its instructions) are gone.
 // Needs n % 4 == 0, an even input shift and output tile origins on 16-byte boundaries; otherwise k_conv_bwd runs.
-template <int A>
+template <int A, int NFC = 0>
 __global__ void __launch_bounds__(256, 2) k_conv_bwd_tma(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
-                                                       GlConvGeom g, const float* __restrict__ wts, float scale) {
+                                                       GlConvGeom g, const float* __restrict__ wts, float scale,
+                                                       const __grid_constant__ GlTapsC<NFC> ctaps) {
   extern __shared__ __align__(128) float glc_smem_bt[];
   float* smem = glc_smem_bt;
   const int nph = g.ss * g.ss;
@@ -528,9 +558,9 @@ __global__ void __launch_bounds__(256, 2) k_conv_bwd_tma(const __grid_constant__
   }
   __syncthreads();
   if (tid == 0) {
-    const unsigned wbytes = (unsigned)(nph * UTAB) * 4u, tbytes = (unsigned)(g.in_rows * g.tma_pitch) * 4u;
+    const unsigned wbytes = NFC == 0 ? (unsigned)(nph * UTAB) * 4u : 0u, tbytes = (unsigned)(g.in_rows * g.tma_pitch) * 4u;
     glc_mbar_expect_tx(&s_bar[0], wbytes + tbytes);
-    glc_bulk_load(s_w, wts, wbytes, &s_bar[0]);
+    if constexpr (NFC == 0) glc_bulk_load(s_w, wts, wbytes, &s_bar[0]);
     glc_tma_load_3d(s_in, &tm_in, (c0 - (A - 1)) & ~3, r0 - (A - 1), b, &s_bar[0]);
   }
   const int ty = tid / g.tpr, tx = tid - ty * g.tpr;
@@ -552,7 +582,10 @@ __global__ void __launch_bounds__(256, 2) k_conv_bwd_tma(const __grid_constant__
     for (int r = 0; r < GLC_RP; ++r)
 #pragma unroll
       for (int c = 0; c < GLC_RX; ++c) acc2[r][c] = make_float2(0.f, 0.f);
-    if (active) corr_rows2<A, 2>(s_in + origin, g.tma_pitch, s_w + ph * UTAB, acc2);
+    if (active) {
+      if constexpr (NFC > 0) corr_rows2_t<A, 2>(s_in + origin, g.tma_pitch, GlTapsConst<NFC>{ctaps, ph * UTAB}, acc2);
+      else corr_rows2<A, 2>(s_in + origin, g.tma_pitch, s_w + ph * UTAB, acc2);
+    }
     if (ph > 0) {                                       // the previous phase's store must have read the staging tile
       if (wstore) { if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); __syncwarp(); }
       else { if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); __syncthreads(); }

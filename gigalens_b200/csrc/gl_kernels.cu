@@ -591,6 +591,11 @@ __global__ void k_points(GlProgram P, int npts, const float* __restrict__ px, co
 // ---------------------------------------------------------------------------------------------
 // plan
 // ---------------------------------------------------------------------------------------------
+// the conv geometry whose tap table travels as a kernel parameter (BASELINE.json: 13 x 13 PSF at ss = 2 => 13 taps per phase)
+#define GLC_A_HOT 13
+#define GLC_SS_HOT 2
+#define GLC_NF_HOT (GLC_SS_HOT * GLC_SS_HOT * GLC_A_HOT * 2 * glc_ulen(GLC_A_HOT))
+static_assert(GLC_NF_HOT * 4 <= GLC_CONST_TAP_BYTES, "hot tap table must fit the kernel parameter space");
 struct gl_plan {
   int device = 0;
   int bs = 0;
@@ -629,6 +634,11 @@ struct gl_plan {
   bool conv_tma_b_ok = false; size_t smem_cb_tma = 0;   // same for the adjoint (TMA load of dL/d(image), TMA store of dL/d(ss))
   CUtensorMap tmap_bi, tmap_bo; const float* tmap_bi_base = nullptr; const float* tmap_bo_base = nullptr; int tmap_b_nimg = -1; bool tmap_b_ok = false;
   int conv_threads_f = 0, conv_threads_b = 0;
+  // tap tables as by-value kernel parameters (uniform-datapath taps, gl_conv.cuh GlTapsConst): the hot geometry A = 13, ss = 2
+  int conv_const = 1;        // 0 = tap table in shared memory (A/B)
+  bool conv_const_ok = false;
+  GlTapsC<GLC_NF_HOT> ct_f, ct_b;
+  size_t smem_cf_tma_c = 0, smem_cb_tma_c = 0;
   // likelihood
   bool has_like = false;
   float* d_obs = nullptr; float* d_err = nullptr;
@@ -798,6 +808,7 @@ static int gl_device_init(int device) {
   GL_OPT(gl_optin_conv<5>(optin)); GL_OPT(gl_optin_conv<6>(optin)); GL_OPT(gl_optin_conv<7>(optin)); GL_OPT(gl_optin_conv<8>(optin));
   GL_OPT(gl_optin_conv<9>(optin)); GL_OPT(gl_optin_conv<11>(optin)); GL_OPT(gl_optin_conv<13>(optin)); GL_OPT(gl_optin_conv<16>(optin));
   GL_OPT(gl_optin_conv<20>(optin)); GL_OPT(gl_optin_conv<25>(optin)); GL_OPT(gl_optin_conv<32>(optin));
+  GL_OPT(gl_optin(k_conv_fwd_tma<GLC_A_HOT, GLC_NF_HOT>, optin)); GL_OPT(gl_optin(k_conv_bwd_tma<GLC_A_HOT, GLC_NF_HOT>, optin));
   GL_OPT(gl_optin(k_positions, optin)); GL_OPT(gl_optin(k_hessian, optin)); GL_OPT(gl_optin(k_pinv_solve, optin));
   GL_OPT(gl_optin(k_gram, optin));
   GL_OPT(gl_gram_tc_init());
@@ -935,6 +946,11 @@ int gl_plan_create(const gl_model_desc* model, const gl_sim_config* sim, int32_t
           }
     GL_TRY(gl_upload(&p->d_wf, wf.data(), wf.size()));
     GL_TRY(gl_upload(&p->d_wb, wb.data(), wb.size()));
+    if (A == GLC_A_HOT && ss == GLC_SS_HOT && (int)wf.size() == GLC_NF_HOT) {
+      memcpy(p->ct_f.w, wf.data(), wf.size() * sizeof(float));
+      memcpy(p->ct_b.w, wb.data(), wb.size() * sizeof(float));
+      p->conv_const_ok = true;
+    }
     GlConvGeom g{};
     g.n = p->n; g.hs = p->hs; g.ss = ss; g.A = A; g.pad = p->pad; g.wpitch = wpitch;
     p->gf = g; p->gb = g;
@@ -951,6 +967,7 @@ int gl_plan_create(const gl_model_desc* model, const gl_sim_config* sim, int32_t
     p->conv_tma_ok = (p->n % 4) == 0 && p->gf.tma_pitch <= 256 && p->gf.in_rows <= 256;
     for (int px = 0; px < ss; ++px) if (((px + p->pad) / ss) & 1) p->conv_tma_ok = false;   // strips must stay 8-byte aligned
     p->smem_cf_tma = (size_t)(2 * p->gf.phase_stride + nph * UTAB) * sizeof(float);
+    p->smem_cf_tma_c = (size_t)(2 * p->gf.phase_stride) * sizeof(float);
     p->smem_cf = (size_t)(2 * p->gf.in_rows * p->gf.in_pitch + nph * UTAB) * sizeof(float);
     p->smem_cb = (size_t)(p->gb.in_rows * p->gb.in_pitch + nph * UTAB) * sizeof(float);
     p->gb.tma_pitch = p->gb.in_pitch + 4;
@@ -963,6 +980,7 @@ int gl_plan_create(const gl_model_desc* model, const gl_sim_config* sim, int32_t
       p->gb.out_stride = p->gb.band_stride * (p->conv_threads_b / 32);
     }
     p->smem_cb_tma = (size_t)(p->gb.phase_stride + p->gb.out_stride + nph * UTAB) * sizeof(float);
+    p->smem_cb_tma_c = (size_t)(p->gb.phase_stride + p->gb.out_stride) * sizeof(float);
     p->conv_tma_b_ok = (p->n % 4) == 0 && p->gb.tma_pitch <= 256 && p->gb.in_rows <= 256 && p->gb.th <= 256 && (p->gb.rc0 & 1) == 0;
     for (int px = 0; px < ss; ++px) {   // output tile origins rc0 + dx(px) + k * tw on 16-byte boundaries
       const int fx = px - p->pad;
@@ -1011,6 +1029,7 @@ int gl_plan_set_option(gl_plan* p, const char* name, int32_t value) {
   if (!strcmp(name, "epl_batch_max")) { p->epl_batch_max = value; return 0; }
   if (!strcmp(name, "row_flush")) { p->row_flush = value; return 0; }
   if (!strcmp(name, "conv_tma")) { p->conv_tma = value; return 0; }
+  if (!strcmp(name, "conv_const_taps")) { p->conv_const = value; return 0; }
   if (!strcmp(name, "straight_line")) { p->straight_line = value; return 0; }
   if (!strcmp(name, "epl_tol_exp10")) {   // EPL series terms below 10^-value are dropped (12 = the reference's constant, epl.py:37)
     if (value < 6 || value > 30) return gl_fail("gl_plan_set_option: epl_tol_exp10 must be in [6, 30]");
@@ -1275,8 +1294,16 @@ static int gl_launch_conv_fwd_A(gl_plan* p, const float* ss, float scale, float*
       p->tmap_f_base = ss; p->tmap_f_nimg = nimg;
     }
     if (p->tmap_f_ok) {
+      if constexpr (A == GLC_A_HOT) {
+        if (p->conv_const && p->conv_const_ok) {
+          k_conv_fwd_tma<A, GLC_NF_HOT><<<grid, p->conv_threads_f, p->smem_cf_tma_c, st>>>(p->tmap_f, p->gf, p->d_wf, scale, img, la,
+                                                                                        like ? p->d_like_part : nullptr, gimg, p->ct_f);
+          GL_LAUNCH_CHECK("k_conv_fwd_tma<const taps>");
+          return 0;
+        }
+      }
       k_conv_fwd_tma<A><<<grid, p->conv_threads_f, p->smem_cf_tma, st>>>(p->tmap_f, p->gf, p->d_wf, scale, img, la,
-                                                                        like ? p->d_like_part : nullptr, gimg);
+                                                                        like ? p->d_like_part : nullptr, gimg, GlTapsC<0>{});
       GL_LAUNCH_CHECK("k_conv_fwd_tma");
       return 0;
     }
@@ -1296,7 +1323,14 @@ static int gl_launch_conv_bwd_A(gl_plan* p, const float* gimg, float scale, floa
       p->tmap_bi_base = gimg; p->tmap_bo_base = gss; p->tmap_b_nimg = nimg;
     }
     if (p->tmap_b_ok) {
-      k_conv_bwd_tma<A><<<grid, p->conv_threads_b, p->smem_cb_tma, st>>>(p->tmap_bi, p->tmap_bo, p->gb, p->d_wb, scale);
+      if constexpr (A == GLC_A_HOT) {
+        if (p->conv_const && p->conv_const_ok) {
+          k_conv_bwd_tma<A, GLC_NF_HOT><<<grid, p->conv_threads_b, p->smem_cb_tma_c, st>>>(p->tmap_bi, p->tmap_bo, p->gb, p->d_wb, scale, p->ct_b);
+          GL_LAUNCH_CHECK("k_conv_bwd_tma<const taps>");
+          return 0;
+        }
+      }
+      k_conv_bwd_tma<A><<<grid, p->conv_threads_b, p->smem_cb_tma, st>>>(p->tmap_bi, p->tmap_bo, p->gb, p->d_wb, scale, GlTapsC<0>{});
       GL_LAUNCH_CHECK("k_conv_bwd_tma");
       return 0;
     }
