@@ -443,7 +443,9 @@ def bench_c5(ctx, args):
     n = C5_GLOBAL_BATCH
     truth = wl["prior"].sample(1, seed=11)   # the draw c4_observation simulates: start the surrogate next to it
     z0 = pmod.bij_inverse(truth)[0] + 0.01
-    svi_steps, hmc_burn, hmc_res = args.c5_svi_steps, 2, args.c5_hmc_steps - 2
+    svi_steps = args.c5_svi_steps
+    hmc_burn = max(2, args.c5_hmc_steps // 3)           # adaptive steps: 80 % of them all-reduce the ChEES / step-size statistics
+    hmc_res = max(1, args.c5_hmc_steps - hmc_burn - 1)
     out = {}
     # ---- SVI
     seq.time_collectives(True)
@@ -465,26 +467,34 @@ def bench_c5(ctx, args):
                      "allreduce": {"count": n_coll, "floats_per_call": 1 + 16 + 16 * 17 // 2, "ms_total": coll_ms,
                                    "share_of_step": coll_ms / ms, "backend": "nccl" if ctx.world > 1 else "none (single rank)"},
                      "elbo_first_last": [losses[0], losses[-1]], "elbo_finite": bool(np.isfinite(losses).all())}
-    # ---- HMC (fixed 5 leapfrogs: trajectory length >> max_leapfrog_steps * eps)
-    seq.time_collectives(True)
-    _sync_all(ctx)
-    e0.record()
-    samples, stats = seq.HMC(q_z, init_eps=0.05, init_l=1000, n_hmc=n, num_burnin_steps=hmc_burn, num_results=hmc_res,
-                             max_leapfrog_steps=5, seed=3)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = _max_over_ranks(ctx, e0.elapsed_time(e1))
-    coll_ms, n_coll = seq.collective_ms()
-    coll_ms = _max_over_ranks(ctx, coll_ms)
-    evals = _sum_over_ranks(ctx, stats["n_evals"])
+    # ---- HMC, two timed calls: (a) adaptive burn-in (dual averaging + ChEES: every step all-reduces its statistics; the
+    # adapted step size decides the leapfrog count), (b) sampling at a fixed step size with 5 leapfrogs per step.
+    phases = {}
+    tot_ms = tot_evals = tot_coll = 0.0
+    for tag, kw in (("adaptive_burnin", dict(init_eps=0.02, init_l=1000, num_burnin_steps=hmc_burn, num_results=1)),
+                    ("sampling_5_leapfrogs", dict(init_eps=0.02, init_l=1000, num_burnin_steps=0, num_results=hmc_res))):
+        seq.time_collectives(True)
+        _sync_all(ctx)
+        e0.record()
+        samples, stats = seq.HMC(q_z, n_hmc=n, max_leapfrog_steps=5, seed=3, **kw)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = _max_over_ranks(ctx, e0.elapsed_time(e1))
+        coll_ms, n_coll = seq.collective_ms()
+        coll_ms = _max_over_ranks(ctx, coll_ms)
+        evals = _sum_over_ranks(ctx, stats["n_evals"]) + n     # + the initial log-prob of the chains
+        phases[tag] = {"steps": kw["num_burnin_steps"] + kw["num_results"], "leapfrogs_per_step": stats["num_leapfrog"], "evals": evals,
+                       "ms": ms, "evals_per_s": evals / (ms * 1e-3),
+                       "allreduce": {"count": n_coll, "ms_total": coll_ms, "share_of_time": coll_ms / ms},
+                       "accept_prob_mean": float(np.mean(stats["accept_prob"])), "samples_finite": bool(torch.isfinite(samples).all())}
+        tot_ms, tot_evals, tot_coll = tot_ms + ms, tot_evals + evals, tot_coll + coll_ms
+    n_steps = sum(p["steps"] for p in phases.values())
     out["c5_hmc"] = {"workload": "HMC (SVI-preconditioned, dual averaging + ChEES) on the C4 cluster model, ModellingSequence.HMC (configs[4])",
-                     "global_batch": n, "batch_per_gpu": n // ctx.world, "steps": hmc_burn + hmc_res,
-                     "leapfrogs_per_step": stats["num_leapfrog"], "evals": evals, "ms_per_step": ms / (hmc_burn + hmc_res),
-                     "value": evals / (ms * 1e-3), "unit": UNIT, "scaling": "strong",
+                     "global_batch": n, "batch_per_gpu": n // ctx.world, "steps": n_steps, "evals": tot_evals, "ms_per_step": tot_ms / n_steps,
+                     "value": tot_evals / (tot_ms * 1e-3), "unit": UNIT, "scaling": "strong",
                      "includes": "plan creation + initial log-prob of the chains + momentum draws / leapfrog updates in torch",
-                     "allreduce": {"count": n_coll, "ms_total": coll_ms, "share_of_step": coll_ms / ms,
-                                   "backend": "nccl" if ctx.world > 1 else "none (single rank)"},
-                     "accept_prob_mean": float(np.mean(stats["accept_prob"])), "samples_finite": bool(torch.isfinite(samples).all())}
+                     "allreduce": {"ms_total": tot_coll, "share_of_step": tot_coll / tot_ms, "backend": "nccl" if ctx.world > 1 else "none (single rank)"},
+                     "phases": phases}
     return out
 
 
@@ -538,7 +548,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--headline-only", action="store_true", help="skip the c3 / c4 / c5 extra keys")
     ap.add_argument("--c5-svi-steps", type=int, default=50)
-    ap.add_argument("--c5-hmc-steps", type=int, default=12)
+    ap.add_argument("--c5-hmc-steps", type=int, default=16)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -635,7 +635,7 @@ struct gl_plan {
   CUtensorMap tmap_bi, tmap_bo; const float* tmap_bi_base = nullptr; const float* tmap_bo_base = nullptr; int tmap_b_nimg = -1; bool tmap_b_ok = false;
   int conv_threads_f = 0, conv_threads_b = 0;
   // tap tables as by-value kernel parameters (uniform-datapath taps, gl_conv.cuh GlTapsConst): the hot geometry A = 13, ss = 2
-  int conv_const = 1;        // 0 = tap table in shared memory (A/B)
+  int conv_const = 0;        // 1 = tap table through the uniform datapath (measured 3.5x SLOWER than broadcast LDS: kept for A/B only)
   bool conv_const_ok = false;
   GlTapsC<GLC_NF_HOT> ct_f, ct_b;
   size_t smem_cf_tma_c = 0, smem_cb_tma_c = 0;

@@ -868,6 +868,15 @@ def test_conv_tma_staging_is_bit_identical_to_cp_async(num_pix):
         assert np.array_equal(x, y)
 
 
+def test_conv_uniform_datapath_taps_are_bit_identical_to_shared_memory_taps():
+    """A = 13, ss = 2 (BASELINE's PSF): the tap table travels as a kernel parameter and is read with LDCU.64 into uniform
+    registers instead of broadcast LDS.64 -- same operands, same order."""
+    a = _c2_logprob(96, {"conv_const_taps": 1})
+    b = _c2_logprob(96, {"conv_const_taps": 0})
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
 def test_staged_flush_matches_butterfly_flush():
     a = _c2_logprob(128, {"row_flush": 1})
     b = _c2_logprob(128, {"row_flush": 0})
