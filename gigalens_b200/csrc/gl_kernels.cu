@@ -16,6 +16,7 @@
 
 #include <cmath>
 #include <cstring>
+#include <type_traits>
 #include <string>
 #include <vector>
 
@@ -233,8 +234,8 @@ __host__ __device__ inline int gl_bwd_smem_floats(const GlProgram& P, int ppt, b
 }
 // packed adjoint kernel: per-thread prefetch slots (x, y, dL/dss pairs of the next batch) behind the series scratch
 __host__ __device__ inline int gl_pre_offset(const GlProgram& P, bool rows, int ppt) { return gl_bwd_smem_floats(P, ppt, rows); }
-__host__ __device__ inline int gl_bwd_p_smem_floats(const GlProgram& P, int ppt, bool rows) {
-  return gl_pre_offset(P, rows, ppt) + 3 * ppt * GLK_THREADS;
+__host__ __device__ inline int gl_bwd_p_smem_floats(const GlProgram& P, int ppt, bool rows, bool tape = false) {
+  return gl_pre_offset(P, rows, ppt) + (tape ? 11 : 3) * ppt * GLK_THREADS;
 }
 
 template <int PPT, unsigned F>
@@ -395,12 +396,15 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_bwd(GlProgram P, int n
 // Two-pixel packed variants (lane type GlF2): each thread owns PPT/2 pairs of ADJACENT pixels, every
 // per-pixel +, *, fma issues as one FFMA2 / FMUL2 / FADD2.  Used when the program only contains
 // profiles whose arithmetic is written over the lane type (feature set FS0) and npix is even.
-template <int PPT, unsigned F, bool BS = false>   // BS: straight-line driver of the benchmark-shape program (gl_program.h)
-__global__ void __launch_bounds__(GLK_THREADS) k_raytrace_fwd_p(GlProgram P, int npix, const float* __restrict__ grid_x,
+// TAPE (programs with a forward-mode scaling-relation group, gradient requested): also writes beta and the group's 2 x 3 Jacobian,
+// tape[b][8][npix] = (beta_x, beta_y, Jx0, Jy0, Jx1, Jy1, Jx2, Jy2), so that the adjoint kernel skips the member loop.
+template <int PPT, unsigned F, bool BS = false, bool TAPE = false>   // BS: straight-line driver of the benchmark-shape program (gl_program.h)
+__global__ void __launch_bounds__(GLK_THREADS, TAPE ? 2 : 1) k_raytrace_fwd_p(GlProgram P, int npix, const float* __restrict__ grid_x,
                                                                 const float* __restrict__ grid_y,
                                                                 const unsigned char* __restrict__ ss_mask,
                                                                 const float* __restrict__ derived, int no_deflection,
-                                                                float* __restrict__ ss_img, int* __restrict__ nan_count) {
+                                                                float* __restrict__ ss_img, int* __restrict__ nan_count,
+                                                                float* __restrict__ tape) {
   extern __shared__ __align__(16) float s_der[];
   const int b = blockIdx.y;
   const float* dsrc = derived + (size_t)b * P.der_total;
@@ -424,7 +428,23 @@ __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_fwd_p(GlProgram P, int
       const float2 a = __ldg(gx2 + p), c = __ldg(gy2 + p);
       x[j] = GlF2(a.x, a.y); y[j] = GlF2(c.x, c.y);
     }
-    if constexpr (BS) gl_pix_image_bs<GlF2, NV>(P, s_der, x, y, v);
+    if constexpr (TAPE) {
+      GlF2 bx[NV], by[NV], Jx[3][NV], Jy[3][NV];
+      gl_pix_image_tape<GlF2, NV, F>(P, s_der, x, y, v, bx, by, Jx, Jy);
+      float2* tp = reinterpret_cast<float2*>(tape + (size_t)b * 8 * npix);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        if (pr[j] < npair) {
+          tp[pr[j]] = make_float2(bx[j].x, bx[j].y);
+          tp[(size_t)npair + pr[j]] = make_float2(by[j].x, by[j].y);
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            tp[(size_t)(2 + 2 * k) * npair + pr[j]] = make_float2(Jx[k][j].x, Jx[k][j].y);
+            tp[(size_t)(3 + 2 * k) * npair + pr[j]] = make_float2(Jy[k][j].x, Jy[k][j].y);
+          }
+        }
+      }
+    } else if constexpr (BS) gl_pix_image_bs<GlF2, NV>(P, s_der, x, y, v);
     else gl_pix_image<GlF2, NV, F>(P, s_der, x, y, no_deflection != 0, v);
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
@@ -453,13 +473,14 @@ struct DevFlushStage {
   }
 };
 
-template <int PPT, unsigned F, bool ROWS, bool BS = false>
+template <int PPT, unsigned F, bool ROWS, bool BS = false, bool TAPE = false>
 __global__ void __launch_bounds__(GLK_THREADS, 2) k_raytrace_bwd_p(GlProgram P, int npix, const float* __restrict__ grid_x,
                                                                 const float* __restrict__ grid_y,
                                                                 const unsigned char* __restrict__ ss_mask,
                                                                 const float* __restrict__ derived, int no_deflection,
                                                                 const float* __restrict__ gss, float* __restrict__ gpart,
-                                                                const int* __restrict__ nan_count, int nan_mode) {
+                                                                const int* __restrict__ nan_count, int nan_mode,
+                                                                const float* __restrict__ tape) {
   extern __shared__ __align__(16) float smem[];
   float* s_der = smem;
   float* s_acc = smem + P.der_total;   // ROWS: staging tiles [nwarps][g_total][33], else accumulator rows [nwarps][g_total]
@@ -483,17 +504,24 @@ __global__ void __launch_bounds__(GLK_THREADS, 2) k_raytrace_bwd_p(GlProgram P, 
   // cp.async into a per-thread shared-memory slot: the slot is read into registers at the top of a batch and
   // refilled for the next one at once, so the HBM / L2 latency of the loads hides behind a whole batch of
   // arithmetic (the first consumer of the plain loads was the top stall of the kernel, 7 % of its samples).
-  float2* pre = reinterpret_cast<float2*>(smem + gl_pre_offset(P, ROWS, PPT)) + threadIdx.x;   // [3 * NV][threads]
+  constexpr int NSLOT = TAPE ? 11 : 3;   // per pixel pair: x, y, dL/d(ss) (+ the 8 tape planes)
+  float2* pre = reinterpret_cast<float2*>(smem + gl_pre_offset(P, ROWS, PPT)) + threadIdx.x;   // [NSLOT * NV][threads]
+  const float2* tp = TAPE ? reinterpret_cast<const float2*>(tape + (size_t)b * 8 * npix) : nullptr;
   auto prefetch = [&](int batch) {
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       const int pr = batch * per_batch + j * GLK_THREADS + threadIdx.x;
       const unsigned nb = (batch < nbatch && pr < npair) ? 8u : 0u;    // 0 source bytes = zero fill
       const int p = nb ? pr : 0;
-      const unsigned d0 = (unsigned)__cvta_generic_to_shared(pre + (3 * j) * GLK_THREADS);
+      const unsigned d0 = (unsigned)__cvta_generic_to_shared(pre + (NSLOT * j) * GLK_THREADS);
       asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d0), "l"(gx2 + p), "r"(nb) : "memory");
       asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d0 + 8u * GLK_THREADS), "l"(gy2 + p), "r"(nb) : "memory");
       asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d0 + 16u * GLK_THREADS), "l"(gsrc + p), "r"(nb) : "memory");
+      if constexpr (TAPE) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d0 + 8u * GLK_THREADS * (3 + k)), "l"(tp + (size_t)k * npair + p), "r"(nb) : "memory");
+      }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -503,10 +531,20 @@ __global__ void __launch_bounds__(GLK_THREADS, 2) k_raytrace_bwd_p(GlProgram P, 
       if (batch * per_batch + (int)(threadIdx.x & ~31u) >= npair) break;   // this warp has no pixel left (ragged last batch)
       GlF2 x[NV], y[NV], gs[NV];
       asm volatile("cp.async.wait_group 0;" ::: "memory");
+      GlF2 tbx[NV], tby[NV], tJx[3][NV], tJy[3][NV];
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
-        const float2 a = pre[(3 * j) * GLK_THREADS], c = pre[(3 * j + 1) * GLK_THREADS];
-        float2 gv = pre[(3 * j + 2) * GLK_THREADS];
+        const float2 a = pre[(NSLOT * j) * GLK_THREADS], c = pre[(NSLOT * j + 1) * GLK_THREADS];
+        float2 gv = pre[(NSLOT * j + 2) * GLK_THREADS];
+        if constexpr (TAPE) {
+          const float2 t0 = pre[(NSLOT * j + 3) * GLK_THREADS], t1 = pre[(NSLOT * j + 4) * GLK_THREADS];
+          tbx[j] = GlF2(t0.x, t0.y); tby[j] = GlF2(t1.x, t1.y);
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const float2 u0 = pre[(NSLOT * j + 5 + 2 * k) * GLK_THREADS], u1 = pre[(NSLOT * j + 6 + 2 * k) * GLK_THREADS];
+            tJx[k][j] = GlF2(u0.x, u0.y); tJy[k][j] = GlF2(u1.x, u1.y);
+          }
+        }
         x[j] = GlF2(a.x, a.y); y[j] = GlF2(c.x, c.y);
         if (ss_mask) {
           const int pr = batch * per_batch + j * GLK_THREADS + threadIdx.x;
@@ -515,7 +553,10 @@ __global__ void __launch_bounds__(GLK_THREADS, 2) k_raytrace_bwd_p(GlProgram P, 
         gs[j] = GlF2(gv.x, gv.y);
       }
       prefetch(batch + gridDim.x);
-      if constexpr (BS) gl_pix_image_bwd_bs<GlF2, NV>(P, s_der, x, y, gs, flush, scr, GLK_THREADS);
+      if constexpr (TAPE)
+        gl_pix_image_bwd<GlF2, NV, F, std::remove_reference_t<decltype(flush)>, false, true>(P, s_der, x, y, gs, false, flush, (GlF2*)nullptr, 0,
+                                                                                              tbx, tby, tJx, tJy);
+      else if constexpr (BS) gl_pix_image_bwd_bs<GlF2, NV>(P, s_der, x, y, gs, flush, scr, GLK_THREADS);
       else gl_pix_image_bwd<GlF2, NV, F>(P, s_der, x, y, gs, no_deflection != 0, flush, scr, GLK_THREADS);
       after_batch();
     }
@@ -614,6 +655,11 @@ struct gl_plan {
   int* d_amp_slot = nullptr;
   int* d_perm = nullptr;
   int* d_nan = nullptr;      // [bs] NaN-scrubbed ss pixels of the last forward pass
+  // tape of the forward-mode group (cluster models): beta + 2 x 3 Jacobian per ss pixel, written by the forward kernel when a
+  // gradient is requested and read by the adjoint kernel, which then never walks the member loop again
+  float* d_tape = nullptr;   // [bs][8][npix]
+  int use_tape = 1;          // 0 = recompute in the adjoint kernel (A/B; also the automatic fallback when the tape does not fit)
+  bool tape_valid = false;   // the last forward pass wrote the tape (same parameters as the adjoint that follows)
   // image-position likelihood (gl_plan_set_positions)
   int gram_tc = 1;           // lstsq normal equations on the tensor cores (tcgen05, 3xTF32); 0 = FP32-FMA k_gram (A/B testing)
   int include_pixels = 1, include_positions = 0;
@@ -688,6 +734,7 @@ static void gl_free_plan(gl_plan* p) {
   if (p->d_amp_slot) cudaFree(p->d_amp_slot);
   if (p->d_perm) cudaFree(p->d_perm);
   if (p->d_nan) cudaFree(p->d_nan);
+  if (p->d_tape) cudaFree(p->d_tape);
   if (p->d_solve_queue) cudaFree(p->d_solve_queue);
   for (void* q : {(void*)p->d_pos_off, (void*)p->d_pos_x, (void*)p->d_pos_y, (void*)p->d_pos_ex, (void*)p->d_pos_ey, (void*)p->d_pos_ll,
                   (void*)p->d_pos_chi, (void*)p->d_pos_grad}) if (q) cudaFree(q);
@@ -800,7 +847,8 @@ static int gl_device_init(int device) {
   GL_OPT(gl_optin_feat<GL_FS2>(optin)); GL_OPT(gl_optin_feat<GL_FS3>(optin));
   GL_OPT(gl_optin(k_raytrace_bwd<4, GL_FS3, true>, optin));
   GL_OPT(gl_optin(k_raytrace_fwd_p<4, GL_FS0, true>, optin)); GL_OPT(gl_optin(k_raytrace_fwd_p<4, GL_FS0>, optin));
-  GL_OPT(gl_optin(k_raytrace_fwd_p<4, GL_FS2>, optin));
+  GL_OPT(gl_optin(k_raytrace_fwd_p<4, GL_FS2>, optin)); GL_OPT(gl_optin(k_raytrace_fwd_p<4, GL_FS2, false, true>, optin));
+  GL_OPT(gl_optin(k_raytrace_bwd_p<4, GL_FS2, true, false, true>, optin)); GL_OPT(gl_optin(k_raytrace_bwd_p<4, GL_FS2, false, false, true>, optin));
   GL_OPT(gl_optin(k_raytrace_bwd_p<4, GL_FS0, true, true>, optin));
   GL_OPT(gl_optin(k_raytrace_bwd_p<4, GL_FS0, true>, optin)); GL_OPT(gl_optin(k_raytrace_bwd_p<4, GL_FS0, false>, optin));
   GL_OPT(gl_optin(k_raytrace_bwd_p<4, GL_FS2, true>, optin)); GL_OPT(gl_optin(k_raytrace_bwd_p<4, GL_FS2, false>, optin));
@@ -1015,6 +1063,14 @@ int gl_plan_create(const gl_model_desc* model, const gl_sim_config* sim, int32_t
   GL_TRY(cudaMemset(p->d_logprior, 0, (size_t)bs * sizeof(float)));
   GL_TRY(cudaMemset(p->d_nan, 0, (size_t)bs * sizeof(int)));
 #undef GL_TRY
+  // tape of the forward-mode group: 32 bytes per ss pixel and sample, if it fits 60 % of the memory that is free now
+  if (p->prog.has_fwdmode && p->feat_idx == 2 && (p->npix % 2) == 0) {
+    const size_t need = (size_t)bs * 8 * p->npix * sizeof(float);
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && need <= free_b / 5 * 3) {
+      if (cudaMalloc((void**)&p->d_tape, need) != cudaSuccess) { p->d_tape = nullptr; cudaGetLastError(); }
+    }
+  }
   {   // models built for lstsq_simulate (some light profile has use_lstsq) get their workspace now; others on request
     bool wants = false;
     for (int i = p->prog.n_lens; i < p->prog.n_prof; ++i) wants = wants || (p->prog.prof[i].flags & GL_FLAG_USE_LSTSQ);
@@ -1030,6 +1086,7 @@ int gl_plan_set_option(gl_plan* p, const char* name, int32_t value) {
   if (!strcmp(name, "row_flush")) { p->row_flush = value; return 0; }
   if (!strcmp(name, "conv_tma")) { p->conv_tma = value; return 0; }
   if (!strcmp(name, "conv_const_taps")) { p->conv_const = value; return 0; }
+  if (!strcmp(name, "tape")) { p->use_tape = value; return 0; }
   if (!strcmp(name, "straight_line")) { p->straight_line = value; return 0; }
   if (!strcmp(name, "epl_tol_exp10")) {   // EPL series terms below 10^-value are dropped (12 = the reference's constant, epl.py:37)
     if (value < 6 || value > 30) return gl_fail("gl_plan_set_option: epl_tol_exp10 must be in [6, 30]");
@@ -1180,20 +1237,28 @@ static int gl_run_positions(gl_plan* p, const float* params, float* loglike, flo
   return 0;
 }
 
-static int gl_run_raytrace_fwd(gl_plan* p, float* ss_out, int no_deflection, cudaStream_t st) {
+static int gl_run_raytrace_fwd(gl_plan* p, float* ss_out, int no_deflection, cudaStream_t st, bool want_tape = false) {
   dim3 grid(p->chunks, p->bs);
   GL_CUDA(cudaMemsetAsync(p->d_nan, 0, (size_t)p->bs * sizeof(int), st));
   const size_t smem = (size_t)p->prog.der_total * sizeof(float);
+  p->tape_valid = false;
+  if (want_tape && p->d_tape && p->use_tape && p->use_packed && p->feat_idx == 2 && !no_deflection && p->prog.comp_mask == 3) {
+    k_raytrace_fwd_p<4, GL_FS2, false, true><<<grid, GLK_THREADS, smem, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,
+                                                                              p->d_derived, 0, ss_out, p->d_nan, p->d_tape);
+    GL_LAUNCH_CHECK("k_raytrace_fwd_p<tape>");
+    p->tape_valid = true;
+    return 0;
+  }
   if ((p->feat_idx == 0 || p->feat_idx == 2) && (p->npix % 2) == 0 && p->use_packed) {   // two pixels per lane slot (FFMA2)
     if (p->feat_idx == 0 && p->straight_line && !no_deflection && gl_is_benchmark_shape(p->prog)) {
       k_raytrace_fwd_p<4, GL_FS0, true><<<grid, GLK_THREADS, smem, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,
-                                                                         p->d_derived, no_deflection, ss_out, p->d_nan);
+                                                                         p->d_derived, no_deflection, ss_out, p->d_nan, nullptr);
     } else if (p->feat_idx == 0) {
       k_raytrace_fwd_p<4, GL_FS0><<<grid, GLK_THREADS, smem, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,
-                                                                   p->d_derived, no_deflection, ss_out, p->d_nan);
+                                                                   p->d_derived, no_deflection, ss_out, p->d_nan, nullptr);
     } else {
       k_raytrace_fwd_p<4, GL_FS2><<<grid, GLK_THREADS, smem, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,
-                                                                   p->d_derived, no_deflection, ss_out, p->d_nan);
+                                                                   p->d_derived, no_deflection, ss_out, p->d_nan, nullptr);
     }
     GL_LAUNCH_CHECK("k_raytrace_fwd_p");
     return 0;
@@ -1230,14 +1295,26 @@ static int gl_run_raytrace_bwd(gl_plan* p, float* gss, int no_deflection, cudaSt
     const size_t smem_rows = (size_t)gl_bwd_p_smem_floats(p->prog, 4, true) * sizeof(float);
     smem = (size_t)gl_bwd_p_smem_floats(p->prog, 4, false) * sizeof(float);
     const bool rows = p->row_flush && smem_rows <= 108 * 1024 && p->prog.g_total <= 64;
+    if (p->tape_valid && p->feat_idx == 2 && !no_deflection && !per_component) {   // beta and the group Jacobian come from the forward kernel's tape
+      const size_t smem_t = (size_t)gl_bwd_p_smem_floats(p->prog, 4, true, true) * sizeof(float);
+      const size_t smem_tn = (size_t)gl_bwd_p_smem_floats(p->prog, 4, false, true) * sizeof(float);
+      if (p->row_flush && smem_t <= 108 * 1024 && p->prog.g_total <= 64)
+        k_raytrace_bwd_p<4, GL_FS2, true, false, true><<<grid, GLK_THREADS, smem_t, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,
+                                                                                       p->d_derived, 0, gss, p->d_gpart, p->d_nan, 0, p->d_tape);
+      else
+        k_raytrace_bwd_p<4, GL_FS2, false, false, true><<<grid, GLK_THREADS, smem_tn, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,
+                                                                                        p->d_derived, 0, gss, p->d_gpart, p->d_nan, 0, p->d_tape);
+      GL_LAUNCH_CHECK("k_raytrace_bwd_p<tape>");
+      return 0;
+    }
 #define GL_BWD_P(FS, ROWS, SM)                                                                                              \
     {                                                                                                                       \
       k_raytrace_bwd_p<4, FS, ROWS><<<grid, GLK_THREADS, (SM), st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,        \
-                                                                   p->d_derived, no_deflection, gss, p->d_gpart, p->d_nan, nan_mode); \
+                                                                   p->d_derived, no_deflection, gss, p->d_gpart, p->d_nan, nan_mode, nullptr); \
     }
     if (p->feat_idx == 0 && rows && p->straight_line && !no_deflection && gl_is_benchmark_shape(p->prog)) {
       k_raytrace_bwd_p<4, GL_FS0, true, true><<<grid, GLK_THREADS, smem_rows, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,
-                                                                                  p->d_derived, no_deflection, gss, p->d_gpart, p->d_nan, nan_mode);
+                                                                                  p->d_derived, no_deflection, gss, p->d_gpart, p->d_nan, nan_mode, nullptr);
     } else
     if (p->feat_idx == 0) { if (rows) GL_BWD_P(GL_FS0, true, smem_rows) else GL_BWD_P(GL_FS0, false, smem) }
     else { if (rows) GL_BWD_P(GL_FS2, true, smem_rows) else GL_BWD_P(GL_FS2, false, smem) }
@@ -1448,7 +1525,7 @@ static int gl_loglike_core(gl_plan* p, const float* params, float* loglike, floa
   GL_TM(p, st, 1);
   if (pix && gl_run_prep(p, params, st)) return 1;
   GL_TM(p, st, 2);
-  if (pix && gl_run_raytrace_fwd(p, p->d_ss, p->no_deflection, st)) return 1;
+  if (pix && gl_run_raytrace_fwd(p, p->d_ss, p->no_deflection, st, grad)) return 1;
   GL_TM(p, st, 3);
   if (pix && gl_run_conv_fwd(p, p->d_ss, p->conversion_factor, p->d_img, true, grad ? p->d_gimg : nullptr, st)) return 1;
   GL_TM(p, st, 4);

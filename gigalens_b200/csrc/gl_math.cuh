@@ -182,6 +182,8 @@ GL_HD GlF2 gl_where_gt(GlF2 a, float t, GlF2 vt, GlF2 vf) { return GlF2(a.x > t 
 GL_HD GlF2 gl_where_in(GlF2 a, float lo, float hi, GlF2 vt, GlF2 vf) {
   return GlF2((a.x >= lo && a.x <= hi) ? vt.x : vf.x, (a.y >= lo && a.y <= hi) ? vt.y : vf.y);
 }
+GL_HD GlF2 gl_where_lt(GlF2 a, float t, GlF2 vt, GlF2 vf) { return GlF2(a.x < t ? vt.x : vf.x, a.y < t ? vt.y : vf.y); }
+GL_HD float gl_where_lt(float a, float t, float vt, float vf) { return a < t ? vt : vf; }
 GL_HD float gl_hsum(GlF2 a) { return a.x + a.y; }
 GL_HD float gl_where_gt(float a, float t, float vt, float vf) { return a > t ? vt : vf; }
 GL_HD double gl_where_gt(double a, double t, double vt, double vf) { return a > t ? vt : vf; }
@@ -925,8 +927,119 @@ GL_HD void nfw_bwd(const typename gl_scalar_of<T>::type* d, const T* x, const T*
   }
 }
 
-// Lane adaptor: NFW has per-pixel branches (g(X) piecewise) and no packed implementation -- it is one halo
-// next to tens of dPIE members -- so the two pixels of a GlF2 lane slot are evaluated as scalars.
+// ---- branch-free fp32 g(X) for the float lane types (float and the two-pixel pack GlF2) -------------------------------------
+// g(X) = ln(X/2) + h(X),  h = acosh(1/X)/sqrt(1-X^2) (X < 1), acos(1/X)/sqrt(X^2-1) (X > 1)          (nfw.py:34-52)
+// The libm transcription above (logf, acoshf / acosf, sqrt, divisions, three-way branch) cost ~150 scalar instructions per pixel
+// and, being scalar, four times that per thread batch: after the member loop left the adjoint kernel (tape) it was three
+// quarters of that kernel's arithmetic.  With u = (1-X)/(1+X):  acosh(1/X) = 2 atanh(sqrt u), acos(1/X) = 2 atan(sqrt -u) and
+// sqrt|1-X^2| = (1+X) sqrt|u|, so  h = 2 S(u)/(1+X)  with ONE analytic function S(u) = sum u^n/(2n+1) on both sides of X = 1.
+// Three per-lane regimes, all evaluated and selected (no branch):
+//   A  |u| <= 0.1 (0.818 <= X <= 1.222): S = 1 + u S1, S1 = sum u^n/(2n+3) (8 terms, 6e-10).  No 0/0 at X = 1: neither in g nor in
+//      dg/dX = X (h-1)/(1-X^2), where (h-1)/(1-X^2) = (2 S1 + 1 + X)/(1+X)^3.
+//   B  X < 0.818: with r = sqrt(1-X^2), w = 1 - r = X^2/(1+r):  g = [ln(1 - w/2) - w ln(X/2)]/r.  The transcription subtracts two
+//      O(|ln X|) numbers to get an O(X^2 |ln X|) result (relative error 2e-3 at X = 0.01 in fp32); this form has no cancellation.
+//      ln(1 - z) is 2 atanh-series terms of q = z/(2-z) for z <= 0.1 and lg2 otherwise.
+//   C  X > 1.222: h = 2 atan(t)/((1+X) t), t = sqrt(-u) in (0.316, 1), atan by the minimax polynomial of gl_atan2_fast.
+// X == 1 exactly keeps the reference's g = 1, dg = 0.  Checked against the fp64 oracle on the host harness.
+template <class V>
+GL_HD void nfw_g_fast(V X, V& g, V& dg) {
+  const V one(1.f), two(2.f);
+  const V X2 = X * X;
+  const V L = V((float)GL_LN2) * gl_log2_fast(X * V(0.5f));
+  const V i1x = gl_div_fast(one, one + X);
+  const V u = (one - X) * i1x;
+  // A
+  V S1 = V(1.f / 17.f);
+  S1 = gl_fma(S1, u, V(1.f / 15.f)); S1 = gl_fma(S1, u, V(1.f / 13.f)); S1 = gl_fma(S1, u, V(1.f / 11.f));
+  S1 = gl_fma(S1, u, V(1.f / 9.f)); S1 = gl_fma(S1, u, V(1.f / 7.f)); S1 = gl_fma(S1, u, V(1.f / 5.f));
+  S1 = gl_fma(S1, u, V(1.f / 3.f));
+  const V hA = two * gl_fma(u, S1, one) * i1x;
+  const V qA = gl_fma(two, S1, one + X) * (i1x * i1x * i1x);
+  // B
+  const V omB = gl_max(one - X2, V(1e-3f));               // clamped: lanes of the other regimes must stay finite
+  const V irB = gl_rsqrt_fast(omB), rB = omB * irB;
+  const V w = X2 * gl_div_fast(one, one + rB), z = w * V(0.5f);
+  const V q = z * gl_div_fast(one, two - z), q2 = q * q;
+  const V ln_s = -(two * q) * gl_fma(q2, gl_fma(q2, gl_fma(q2, V(1.f / 7.f), V(0.2f)), V(1.f / 3.f)), one);
+  const V ln_l = V((float)GL_LN2) * gl_log2_fast(one - z);
+  const V ln1mz = gl_where_gt(z, 0.1f, ln_l, ln_s);
+  const V gB = (ln1mz - w * L) * irB;
+  const V qB = (gB - L - one) * (irB * irB);
+  // C
+  const V nu = gl_max(-u, V(1e-3f));
+  const V it = gl_rsqrt_fast(nu), t = nu * it;
+  const V hC = two * gl_atan2_fast(t, one) * it * i1x;
+  const V qC = gl_div_fast(hC - one, gl_min(one - X2, V(-1e-3f)));
+  // select
+  const V gAC = L + gl_where_gt(u, -0.1f, hA, hC);
+  g = gl_where_gt(u, 0.1f, gB, gAC);
+  const V qq = gl_where_gt(u, 0.1f, qB, gl_where_gt(u, -0.1f, qA, qC));
+  dg = X * qq;
+  // X == 1: g = 1, dg = 0
+  g = gl_where_in(X, 1.f, 1.f, one, g);
+  dg = gl_where_in(X, 1.f, 1.f, V(0.f), dg);
+}
+template <class V, int NP>
+GL_HD void nfw_fwd_fast(const float* d, const V* x, const V* y, V* ax, V* ay) {
+  const V c(d[NFW_C]), s(d[NFW_S]), s1(d[NFW_S1]), s2(d[NFW_S2]), cx(d[NFW_CX]), cy(d[NFW_CY]), pref(d[NFW_PREF]);
+  const V iRs(1.f / d[NFW_RS]);
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    const V dx = x[j] - cx, dy = y[j] - cy;
+    const V xr = gl_fma(dx, c, dy * s) * s1, yr = gl_fma(dy, c, -(dx * s)) * s2;
+    const V R2 = gl_max(gl_fma(xr, xr, yr * yr), V((float)(GL_NFW_RMIN * GL_NFW_RMIN)));   // R = max(r_min, sqrt(.))
+    const V R = R2 * gl_rsqrt_fast(R2);
+    const V X0 = R * iRs, X = gl_max(V((float)GL_NFW_C), X0);
+    V g, dg;
+    nfw_g_fast<V>(X, g, dg);
+    const V a = pref * g * gl_div_fast(V(1.f), X0 * X0);
+    const V fx = a * xr * s1, fy = a * yr * s2;
+    ax[j] = gl_fma(fx, c, -(fy * s)); ay[j] = gl_fma(fx, s, fy * c);
+  }
+}
+template <class V, int NP>
+GL_HD void nfw_bwd_fast(const float* d, const V* x, const V* y, const V* gax, const V* gay, V* g) {
+  const V c(d[NFW_C]), s(d[NFW_S]), s1(d[NFW_S1]), s2(d[NFW_S2]), cx(d[NFW_CX]), cy(d[NFW_CY]), pref(d[NFW_PREF]);
+  const V iRs(1.f / d[NFW_RS]), zero(0.f);
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    const V dx = x[j] - cx, dy = y[j] - cy;
+    const V xr0 = gl_fma(dx, c, dy * s), yr0 = gl_fma(dy, c, -(dx * s));
+    const V xr = xr0 * s1, yr = yr0 * s2;
+    const V R2u = gl_fma(xr, xr, yr * yr);
+    const V R2 = gl_max(R2u, V((float)(GL_NFW_RMIN * GL_NFW_RMIN)));
+    const V iR = gl_rsqrt_fast(R2), R = R2 * iR;
+    const V X0 = R * iRs, X = gl_max(V((float)GL_NFW_C), X0);
+    V gx, dg;
+    nfw_g_fast<V>(X, gx, dg);
+    const V iX0 = gl_div_fast(V(1.f), X0), iX02 = iX0 * iX0;
+    const V a = pref * gx * iX02;
+    const V fx = a * xr * s1, fy = a * yr * s2;
+    const V ax = gl_fma(fx, c, -(fy * s)), ay = gl_fma(fx, s, fy * c);
+    g[NFWG_PHI] += gl_fma(gay[j], ax, -(gax[j] * ay));
+    const V gfx = gl_fma(gax[j], c, gay[j] * s), gfy = gl_fma(gay[j], c, -(gax[j] * s));
+    const V ga = gl_fma(gfx * xr, s1, gfy * yr * s2);                      // fx = a xr s1, fy = a yr s2
+    V gxr = gfx * a * s1, gyr = gfy * a * s2;
+    g[NFWG_S1] += gfx * a * xr;
+    g[NFWG_S2] += gfy * a * yr;
+    g[NFWG_PREF] += ga * gx * iX02;                                       // a = pref g(X) / X0^2
+    const V gX0 = gl_fma(V(-2.f) * ga, a * iX0, gl_where_lt(X0, (float)GL_NFW_C, zero, ga * pref * dg * iX02));
+    g[NFWG_RS] -= gX0 * X0 * iRs;                                         // X0 = R / Rs
+    const V gR = gX0 * iRs;
+    // R = max(r_min, R0): the clamp passes no gradient; above it iR = 1/R0
+    const V gRi = gl_where_lt(R2u, (float)(GL_NFW_RMIN * GL_NFW_RMIN), zero, gR * iR);
+    gxr = gl_fma(gRi, xr, gxr); gyr = gl_fma(gRi, yr, gyr);
+    g[NFWG_S1] += gxr * xr0;
+    g[NFWG_S2] += gyr * yr0;
+    const V gxr0 = gxr * s1, gyr0 = gyr * s2;
+    g[NFWG_PHI] += gl_fma(gxr0, yr0, -(gyr0 * xr0));
+    g[NFWG_CX] -= gl_fma(gxr0, c, -(gyr0 * s));
+    g[NFWG_CY] -= gl_fma(gxr0, s, gyr0 * c);
+  }
+}
+
+// Lane dispatch: fp64 and the forward-mode dual lanes (positions kernels, host harness) run the libm transcription; the fp32 lanes
+// of the pixel kernels (float, and GlF2 = two pixels per FFMA2) run the branch-free form.
 template <class T, int NP>
 struct NfwLane {
   typedef typename gl_scalar_of<T>::type S;
@@ -934,27 +1047,17 @@ struct NfwLane {
   static GL_HD void bwd(const S* d, const T* x, const T* y, const T* gax, const T* gay, T* g) { nfw_bwd<T, NP>(d, x, y, gax, gay, g); }
 };
 template <int NP>
-struct NfwLane<GlF2, NP> {
-  static GL_HD void fwd(const float* d, const GlF2* x, const GlF2* y, GlF2* ax, GlF2* ay) {
-    float xs[2 * NP], ys[2 * NP], as[2 * NP], bs[2 * NP];
-#pragma unroll
-    for (int j = 0; j < NP; ++j) { xs[2 * j] = x[j].x; xs[2 * j + 1] = x[j].y; ys[2 * j] = y[j].x; ys[2 * j + 1] = y[j].y; }
-    nfw_fwd<float, 2 * NP>(d, xs, ys, as, bs);
-#pragma unroll
-    for (int j = 0; j < NP; ++j) { ax[j] = GlF2(as[2 * j], as[2 * j + 1]); ay[j] = GlF2(bs[2 * j], bs[2 * j + 1]); }
+struct NfwLane<float, NP> {
+  static GL_HD void fwd(const float* d, const float* x, const float* y, float* ax, float* ay) { nfw_fwd_fast<float, NP>(d, x, y, ax, ay); }
+  static GL_HD void bwd(const float* d, const float* x, const float* y, const float* gax, const float* gay, float* g) {
+    nfw_bwd_fast<float, NP>(d, x, y, gax, gay, g);
   }
+};
+template <int NP>
+struct NfwLane<GlF2, NP> {
+  static GL_HD void fwd(const float* d, const GlF2* x, const GlF2* y, GlF2* ax, GlF2* ay) { nfw_fwd_fast<GlF2, NP>(d, x, y, ax, ay); }
   static GL_HD void bwd(const float* d, const GlF2* x, const GlF2* y, const GlF2* gax, const GlF2* gay, GlF2* g) {
-    float xs[2 * NP], ys[2 * NP], as[2 * NP], bs[2 * NP], g8[GL_MAX_DVARS];
-#pragma unroll
-    for (int j = 0; j < NP; ++j) {
-      xs[2 * j] = x[j].x; xs[2 * j + 1] = x[j].y; ys[2 * j] = y[j].x; ys[2 * j + 1] = y[j].y;
-      as[2 * j] = gax[j].x; as[2 * j + 1] = gax[j].y; bs[2 * j] = gay[j].x; bs[2 * j + 1] = gay[j].y;
-    }
-#pragma unroll
-    for (int k = 0; k < GL_MAX_DVARS; ++k) g8[k] = 0.f;
-    nfw_bwd<float, 2 * NP>(d, xs, ys, as, bs, g8);
-#pragma unroll
-    for (int k = 0; k < 7; ++k) g[k] += GlF2(g8[k], 0.f);
+    nfw_bwd_fast<GlF2, NP>(d, x, y, gax, gay, g);
   }
 };
 
@@ -967,7 +1070,7 @@ struct NfwLane<GlF2, NP> {
 // =============================================================================================
 enum { DP_CX = 0, DP_CY, DP_C, DP_S, DP_SCALE, DP_RC, DP_RT, DP_E,
        DP_SQE, DP_Q, DP_IQ, DP_IOPE2, DP_IOME2, DP_ZCI, DP_RC2, DP_RT2,
-       DP_M = 16, DP_SIZE = 28 };   // DP_M: 3x3 d(scale, rc, rt)/d(base scaling params) of a scaling-relation member   // second row: per-member constants of e, rc, rt
+       DP_M = 16, DP_FAST = 25, DP_ITHETA = 26, DP_SIZE = 28 };   // DP_FAST / DP_ITHETA: member 0 of a forward-mode group only (gl_sample_prep)   // DP_M: 3x3 d(scale, rc, rt)/d(base scaling params) of a scaling-relation member   // second row: per-member constants of e, rc, rt
 enum { DPG_CX = 0, DPG_CY, DPG_PHI, DPG_SCALE, DPG_RC, DPG_RT, DPG_E };
 #define GL_DPIE_RMIN 0.0001
 // _sort_ra_rs (piemd.py:51-60): returns the sorted/floored radii and the selection pattern needed
@@ -1198,7 +1301,11 @@ GL_HD void dpie_bwd(const typename gl_scalar_of<T>::type* d, const T* x, const T
 //     J[:, k] += sum_j  d(alpha_m)/d(scale, rc, rt)_j * M_m[j][k],
 // with M_m = d(scale, rc, rt)_m / d(base)_k precomputed per (sample, member) in the derived block.
 // d(alpha)/d(rc|rt) follows from z = num/den, zr = log z:  dz = (num' - z den')/den, dzr = dz / z.
-template <class T, int NP>
+// FAST (every member of the group has r_core < r_cut, the usual case; decided per sample in gl_sample_prep): the chain matrix M is
+// sparse -- d(rc)/d(theta_E) = d(rt)/d(theta_E) = d(rc)/d(r_cut) = d(rt)/d(r_core) = 0 -- and the deflection is linear in theta_E, so
+// column 0 of the Jacobian is (group deflection) / theta_E (formed by the caller) and columns 1, 2 take two terms each: 8 FMAs per
+// member-pixel instead of 18.
+template <class T, int NP, bool FAST = false>
 GL_HD void dpie_fwd_jac(const typename gl_scalar_of<T>::type* d, const T* x, const T* y, T* ax, T* ay, T (*Jx)[NP], T (*Jy)[NP]) {
   typedef typename gl_scalar_of<T>::type S;
   const T c = T(d[DP_C]), s = T(d[DP_S]), scale = T(d[DP_SCALE]), zci = T(d[DP_ZCI]), two_sqe = T(S(2) * d[DP_SQE]);
@@ -1239,10 +1346,17 @@ GL_HD void dpie_fwd_jac(const typename gl_scalar_of<T>::type* d, const T* x, con
     // rotate the two tangents back once; then every base parameter k is a 3-term combination per component
     const T B0r = gl_fma(tre[0], c, -(tim[0] * s)), B0i = gl_fma(tre[0], s, tim[0] * c);
     const T B1r = gl_fma(tre[1], c, -(tim[1] * s)), B1i = gl_fma(tre[1], s, tim[1] * c);
+    if constexpr (FAST) {
+      Jx[1][j] = gl_fma(T(M[1]), Ar, gl_fma(T(M[4]), B0r, Jx[1][j]));
+      Jy[1][j] = gl_fma(T(M[1]), Ai, gl_fma(T(M[4]), B0i, Jy[1][j]));
+      Jx[2][j] = gl_fma(T(M[2]), Ar, gl_fma(T(M[8]), B1r, Jx[2][j]));
+      Jy[2][j] = gl_fma(T(M[2]), Ai, gl_fma(T(M[8]), B1i, Jy[2][j]));
+    } else {
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      Jx[k][j] += gl_fma(T(M[k]), Ar, gl_fma(T(M[3 + k]), B0r, T(M[6 + k]) * B1r));
-      Jy[k][j] += gl_fma(T(M[k]), Ai, gl_fma(T(M[3 + k]), B0i, T(M[6 + k]) * B1i));
+      for (int k = 0; k < 3; ++k) {
+        Jx[k][j] += gl_fma(T(M[k]), Ar, gl_fma(T(M[3 + k]), B0r, T(M[6 + k]) * B1r));
+        Jy[k][j] += gl_fma(T(M[k]), Ai, gl_fma(T(M[3 + k]), B0i, T(M[6 + k]) * B1i));
+      }
     }
   }
 }

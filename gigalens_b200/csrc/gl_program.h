@@ -101,7 +101,22 @@ GL_HD void gl_sample_prep(const GlProgram& P, const TP* params, int bs, int b, c
           for (int k = 0; k < 3; ++k)
             dm[DP_M + 3 * jj + k] = graw[k] * T(member_factor[pr.member_off + k * pr.n_members + m]);
         }
+        dm[DP_FAST] = T(0); dm[DP_ITHETA] = T(0);
       }
+    }
+    if (pr.fwdmode) {
+      // sparse chain matrix for every member (r_core < r_cut, so the sort is the identity) and a non-zero base theta_E:
+      // dpie_fwd_jac<FAST> applies (gl_pix_beta_jac reads the flag from member 0's block)
+      T* d0 = der + pr.der_off;
+      bool fast = true;
+      for (int m = 0; m < nm; ++m) {
+        const T* M = der + pr.der_off + m * pr.der_size + DP_M;
+        fast = fast && M[3] == T(0) && M[5] == T(0) && M[6] == T(0) && M[7] == T(0);
+      }
+      const T theta = (pr.slot[0] >= 0) ? T(params[(size_t)pr.slot[0] * bs + b]) : T(pr.constant[0]);
+      fast = fast && theta != T(0) && theta == theta;
+      d0[DP_FAST] = fast ? T(1) : T(0);
+      d0[DP_ITHETA] = fast ? T(1) / theta : T(0);
     }
   }
 }
@@ -161,14 +176,27 @@ GL_HD void gl_pix_beta(const GlProgram& P, const typename gl_scalar_of<T>::type*
   for (int j = 0; j < NP; ++j) { bx[j] = x[j]; by[j] = y[j]; }
   for (int i = 0; i < P.n_lens; ++i) {
     const GlProf& pr = P.prof[i];
-    const int nm = pr.n_members > 0 ? pr.n_members : 1;
-    for (int m = 0; m < nm; ++m) {
-      T ax[NP], ay[NP];
-      // the entry that owns the series scratch (P.scr_prof) parks its series state for the adjoint
-      gl_lens_fwd<T, NP, F>(pr.type, pr.ts, der + pr.der_off + m * pr.der_size, x, y, ax, ay, (i == P.scr_prof) ? scr : (T*)nullptr, scr_stride);
+    if (pr.n_members > 0) {
+      // a scaling-relation group is summed over its members first (scaling_relation.py:61-70 reduces over the member axis) and
+      // then subtracted: the order every driver of this file uses, so that forward, taped forward and adjoint agree bit for bit
+      T gx[NP], gy[NP];
 #pragma unroll
-      for (int j = 0; j < NP; ++j) { bx[j] -= ax[j]; by[j] -= ay[j]; }
+      for (int j = 0; j < NP; ++j) { gx[j] = T(0); gy[j] = T(0); }
+      for (int m = 0; m < pr.n_members; ++m) {
+        T ax[NP], ay[NP];
+        gl_lens_fwd<T, NP, F>(pr.type, pr.ts, der + pr.der_off + m * pr.der_size, x, y, ax, ay);
+#pragma unroll
+        for (int j = 0; j < NP; ++j) { gx[j] += ax[j]; gy[j] += ay[j]; }
+      }
+#pragma unroll
+      for (int j = 0; j < NP; ++j) { bx[j] -= gx[j]; by[j] -= gy[j]; }
+      continue;
     }
+    T ax[NP], ay[NP];
+    // the entry that owns the series scratch (P.scr_prof) parks its series state for the adjoint
+    gl_lens_fwd<T, NP, F>(pr.type, pr.ts, der + pr.der_off, x, y, ax, ay, (i == P.scr_prof) ? scr : (T*)nullptr, scr_stride);
+#pragma unroll
+    for (int j = 0; j < NP; ++j) { bx[j] -= ax[j]; by[j] -= ay[j]; }
   }
 }
 
@@ -185,6 +213,30 @@ GL_HD void gl_pix_beta_jac(const GlProgram& P, const typename gl_scalar_of<T>::t
   for (int i = 0; i < P.n_lens; ++i) {
     const GlProf& pr = P.prof[i];
     const int nm = pr.n_members > 0 ? pr.n_members : 1;
+    if constexpr ((F & GLF_DPIE) != 0) {
+      if (pr.fwdmode && der[pr.der_off + DP_FAST] != typename gl_scalar_of<T>::type(0)) {
+        // sparse chain matrix: accumulate the group deflection and Jacobian columns 1, 2; column 0 = deflection / theta_E
+        T gx[NP], gy[NP];
+#pragma unroll
+        for (int j = 0; j < NP; ++j) { gx[j] = T(0); gy[j] = T(0); }
+        for (int m = 0; m < nm; ++m) {
+          T ax[NP], ay[NP];
+          dpie_fwd_jac<T, NP, true>(der + pr.der_off + m * pr.der_size, x, y, ax, ay, Jx, Jy);
+#pragma unroll
+          for (int j = 0; j < NP; ++j) { gx[j] += ax[j]; gy[j] += ay[j]; }
+        }
+        const T ith = T(der[pr.der_off + DP_ITHETA]);
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+          bx[j] -= gx[j]; by[j] -= gy[j];
+          Jx[0][j] += gx[j] * ith; Jy[0][j] += gy[j] * ith;
+        }
+        continue;
+      }
+    }
+    T gx[NP], gy[NP];
+#pragma unroll
+    for (int j = 0; j < NP; ++j) { gx[j] = T(0); gy[j] = T(0); }
     for (int m = 0; m < nm; ++m) {
       T ax[NP], ay[NP];
       bool done = false;
@@ -193,8 +245,10 @@ GL_HD void gl_pix_beta_jac(const GlProgram& P, const typename gl_scalar_of<T>::t
       }
       if (!done) gl_lens_fwd<T, NP, F>(pr.type, pr.ts, der + pr.der_off + m * pr.der_size, x, y, ax, ay);
 #pragma unroll
-      for (int j = 0; j < NP; ++j) { bx[j] -= ax[j]; by[j] -= ay[j]; }
+      for (int j = 0; j < NP; ++j) { gx[j] += ax[j]; gy[j] += ay[j]; }
     }
+#pragma unroll
+    for (int j = 0; j < NP; ++j) { bx[j] -= gx[j]; by[j] -= gy[j]; }
   }
 }
 
@@ -227,6 +281,25 @@ GL_HD void gl_pix_image(const GlProgram& P, const typename gl_scalar_of<T>::type
                                  (const T*)nullptr, (T*)nullptr, (T*)nullptr, (T*)nullptr, (T*)nullptr);
         break;
       default: break;
+    }
+  }
+}
+
+// gl_pix_image for programs with a forward-mode group, keeping what the adjoint needs ("tape"): beta and the 2 x 3 Jacobian of the
+// group deflection w.r.t. its base parameters.  With the tape in HBM the adjoint kernel never walks the member loop again (at the
+// cluster config the loop is 84 % of both ray-tracing kernels; 8 floats per ss pixel cost 1.6 ms of HBM time per 1024 samples).
+template <class T, int NP, unsigned F>
+GL_HD void gl_pix_image_tape(const GlProgram& P, const typename gl_scalar_of<T>::type* der, const T* x, const T* y, T* out,
+                             T* bx, T* by, T (*Jx)[NP], T (*Jy)[NP]) {
+  gl_pix_beta_jac<T, NP, F>(P, der, x, y, bx, by, Jx, Jy);
+#pragma unroll
+  for (int j = 0; j < NP; ++j) out[j] = T(0);
+  for (int i = P.n_lens; i < P.n_prof; ++i) {
+    const GlProf& pr = P.prof[i];
+    const bool src = i >= P.n_lens + P.n_ll;
+    if (!(P.comp_mask & (src ? 2 : 1))) continue;
+    if (pr.type == GLT_SERSIC || pr.type == GLT_SERSIC_ELLIPSE) {
+      if constexpr ((F & GLF_SERSIC) != 0) sersic_fwd<T, NP>(der + pr.der_off, src ? bx : x, src ? by : y, out);
     }
   }
 }
@@ -271,14 +344,26 @@ GL_HD int gl_point_components(const GlProgram& P, const T* der, T x, T y, T bx, 
 // SCRUB (lstsq path, samples that had NaN components): the reference scrubs the component stack per component
 // (tf/simulator.py:200), so a light profile whose own value is NaN at a pixel receives a zero cotangent there while
 // the other profiles keep theirs.
-template <class T, int NP, unsigned F, class Flush, bool SCRUB = false>
+// TAPE: beta and the forward-mode Jacobian come from the forward kernel's tape (gl_pix_image_tape) instead of being recomputed.
+template <class T, int NP, unsigned F, class Flush, bool SCRUB = false, bool TAPE = false>
 GL_HD void gl_pix_image_bwd(const GlProgram& P, const typename gl_scalar_of<T>::type* der, const T* x, const T* y, const T* gS,
-                            bool no_deflection, Flush& flush, T* scr = nullptr, int scr_stride = 0) {
+                            bool no_deflection, Flush& flush, T* scr = nullptr, int scr_stride = 0,
+                            const T* tape_bx = nullptr, const T* tape_by = nullptr, const T (*tape_Jx)[NP] = nullptr,
+                            const T (*tape_Jy)[NP] = nullptr) {
   T bx[NP], by[NP], Gx[NP], Gy[NP];
   T Jx[3][NP], Jy[3][NP];
   bool have_jac = false;
   const T* const gS_all = gS;   // SCRUB re-points gS at a per-profile masked copy
   (void)gS_all;
+  if constexpr (TAPE) {
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      bx[j] = tape_bx[j]; by[j] = tape_by[j];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { Jx[k][j] = tape_Jx[k][j]; Jy[k][j] = tape_Jy[k][j]; }
+    }
+    have_jac = true; scr = nullptr;
+  } else
   if (no_deflection) {
 #pragma unroll
     for (int j = 0; j < NP; ++j) { bx[j] = x[j]; by[j] = y[j]; }

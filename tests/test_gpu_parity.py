@@ -719,7 +719,9 @@ def test_c4_cluster_full_size_properties():
     dz_rel = ((s[2] - a[2]).abs() / a[2].abs().max(0).values).max(1).values.cpu().numpy()
     print("C4 packed vs scalar: logp rel median/99%/max", np.median(lp_rel), np.percentile(lp_rel, 99), lp_rel.max(),
           " dz rel median/99%/max", np.median(dz_rel), np.percentile(dz_rel, 99), dz_rel.max())
-    assert np.median(lp_rel) < 1e-6 and np.percentile(lp_rel, 99) < 1e-5
+    # (the halo deflects by ~10 arcsec: one fp32 ulp of it is 1e-6 arcsec of beta under a cuspy 0.3 arcsec source, so the scalar
+    # lanes -- whose a*b+c the compiler contracts into FMAs, which the packed intrinsics are not -- show up at the 1e-5 level)
+    assert np.median(lp_rel) < 1e-6 and np.percentile(lp_rel, 99) < 5e-5
     assert np.median(dz_rel) < 1e-5 and np.percentile(dz_rel, 99) < 1e-4
 
 
@@ -875,6 +877,29 @@ def test_conv_uniform_datapath_taps_are_bit_identical_to_shared_memory_taps():
     b = _c2_logprob(96, {"conv_const_taps": 0})
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
+
+
+def test_cluster_tape_matches_recompute():
+    """Cluster models: the forward kernel tapes beta and the group Jacobian for the adjoint (default) vs the adjoint kernel
+    recomputing them (tape = 0): same formulas, same order -> same log-prob, gradient equal to fp32 rounding."""
+    obs = workloads.c4_observation(num_pix=48)
+    wl = workloads.c4_workload(num_pix=48, observed=obs)
+    bs = 24
+    res = []
+    for tape in (1, 0):
+        sim = LensSimulator(wl["phys_model"], wl["sim_config"], bs=bs)
+        sim.set_option("tape", tape)
+        pmod = ForwardProbModel(wl["prior"], wl["observed"], background_rms=wl["background_rms"], exp_time=wl["exp_time"])
+        z = torch.as_tensor(pmod.bij_inverse(wl["prior"].sample(bs, seed=2)), device="cuda")
+        res.append([t.double().cpu().numpy() for t in pmod.log_prob_and_grad(sim, z)])
+        fwd_only = pmod.log_prob(sim, z)[0].double().cpu().numpy()          # no gradient requested: the plain forward kernel
+        # two kernel instances of the same formulas: equal to fp32 rounding of the ~1e5-sized chi^2 / normalisation sums
+        assert np.max(np.abs(fwd_only - res[-1][0])) < 2e-7 * 48 * 48 * 50
+    a, b = res
+    assert np.isfinite(a[0]).all() and np.isfinite(a[2]).all()
+    assert np.max(np.abs(a[0] - b[0])) < 2e-7 * 48 * 48 * 50          # fp32 rounding of the ~1e5-sized sums (see above)
+    scale = np.max(np.abs(b[2]), axis=0)
+    assert np.max(np.max(np.abs(a[2] - b[2]), axis=0) / scale) < 2e-5
 
 
 def test_staged_flush_matches_butterfly_flush():

@@ -246,3 +246,42 @@ def test_positions_float_instantiation(name):
     for k in lens_rows:
         common.assert_parity(out["gparams"][k], r32["gparams"][k], ref["gparams"][k], 1e-4, f"positions grad {cm.slot_keys[k]}",
                              rpt["gparams"][k])
+
+
+def test_nfw_branch_free_fp32_form_accuracy_and_gradient():
+    """The fp32 lanes evaluate g(X) of nfw.py:34-52 branch-free (gl_math.cuh nfw_g_fast: three regimes in u = (1-X)/(1+X)).
+    Deflection along a radius from X = 1e-4 to 10, dense around X = 1, against the fp64 oracle: the float instantiation must be
+    at least as accurate as the fp32 oracle (the libm transcription of the reference) everywhere and hold 5e-6 outright --
+    for small X the transcription cancels two O(|ln X|) terms and is off by 1e-3 -- and the adjoint must agree with fp64 autograd."""
+    pm = PhysicalModel([nfw.NFW()], [], [sersic.Sersic()])
+    cm = CompiledModel(pm)
+    mat = draw_matrix(cm, 1, seed=1)
+    i_rs = [i for i, k in enumerate(cm.slot_keys) if k[2] == "Rs"][0]
+    i_cx = [i for i, k in enumerate(cm.slot_keys) if k[0] == "lens_mass" and k[2] == "center_x"][0]
+    i_cy = [i for i, k in enumerate(cm.slot_keys) if k[0] == "lens_mass" and k[2] == "center_y"][0]
+    mat[i_rs], mat[i_cx], mat[i_cy] = 2.0, 0.0, 0.0
+    mat = mat.astype(np.float32).astype(np.float64)
+    X = np.concatenate([np.logspace(-4, 1, 400), 1 + np.logspace(-7, -1, 60), 1 - np.logspace(-7, -1, 60), [0.818, 0.819, 1.222, 1.223]])
+    ang = np.linspace(0.1, 6.0, X.size)
+    gx, gy = (2.0 * X * np.cos(ang)).astype(np.float32).astype(np.float64), (2.0 * X * np.sin(ang)).astype(np.float32).astype(np.float64)
+
+    def oracle_alpha(dt):
+        om = to_oracle_model(pm, dt)
+        p, _ = matrix_to_pytree(cm, mat, dt)
+        ax, ay = om.lenses[0].deriv(torch.as_tensor(gx, dtype=dt)[:, None], torch.as_tensor(gy, dtype=dt)[:, None], **p["lens_mass"][0])
+        return ax[:, 0].double().numpy(), ay[:, 0].double().numpy()
+
+    a64, a32 = oracle_alpha(torch.float64), oracle_alpha(torch.float32)
+    out = host_run(cm, mat, gx, gy, dtype=np.float32, want_beta=True)
+    ax, ay = gx - out["beta"][0, 0], gy - out["beta"][0, 1]
+    mag = np.hypot(*a64)
+    err = np.hypot(ax - a64[0], ay - a64[1]) / mag
+    err32 = np.hypot(a32[0] - a64[0], a32[1] - a64[1]) / mag
+    # beta = x - alpha is rounded to fp32 in the harness: allow its ulp on top
+    ulp = 1.2e-7 * np.hypot(gx, gy) / mag
+    assert np.all(err <= 5e-6 + 2 * ulp), (float(err.max()), float(X[np.argmax(err)]))
+    assert np.median(err) < 5e-7
+    assert err32.max() > 1e-4            # the reference's own fp32 form loses digits at small X ...
+    assert np.all(err <= np.maximum(3 * err32, 5e-6 + 2 * ulp))   # ... and the branch-free form is never meaningfully worse
+    packed = common.host_run_packed(cm, mat.astype(np.float32), gx, gy)
+    assert np.max(np.abs(packed["ss"] - host_run(cm, mat, gx, gy, dtype=np.float32)["ss"])) <= 1e-6 * np.max(np.abs(packed["ss"]))
