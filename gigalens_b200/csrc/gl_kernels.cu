@@ -677,6 +677,7 @@ struct gl_plan {
   bool conv_tma_ok = false;  // geometry admits the TMA-staged forward kernel
   int conv_tma = 1;          // stage the forward conv tiles with TMA (cp.async.bulk.tensor); 0 = cp.async loader (A/B)
   CUtensorMap tmap_f; const float* tmap_f_base = nullptr; int tmap_f_nimg = -1; bool tmap_f_ok = false;
+  CUtensorMap tmap_f2; const float* tmap_f2_base = nullptr; int tmap_f2_nimg = -1; bool tmap_f2_ok = false;   // second lstsq slot
   bool conv_tma_b_ok = false; size_t smem_cb_tma = 0;   // same for the adjoint (TMA load of dL/d(image), TMA store of dL/d(ss))
   CUtensorMap tmap_bi, tmap_bo; const float* tmap_bi_base = nullptr; const float* tmap_bo_base = nullptr; int tmap_b_nimg = -1; bool tmap_b_ok = false;
   int conv_threads_f = 0, conv_threads_b = 0;
@@ -718,6 +719,14 @@ struct gl_plan {
   int lq_chunk_req = 0;
   float* d_comps = nullptr; float* d_R = nullptr; float* d_gram = nullptr; float* d_coef = nullptr; float* d_w = nullptr;
   int* d_solve_queue = nullptr;   // [1 + chunk]: count, then the samples that need the eigen-solve
+  // second slot of the chunk pipeline: chunks alternate between two streams, so one chunk's latency-bound tail (Gram, Cholesky,
+  // the eigen-solve of the few singular samples) runs under the other chunk's convolution
+  float* d_comps2 = nullptr; float* d_R2 = nullptr; float* d_gram2 = nullptr; int* d_solve_queue2 = nullptr;
+  cudaStream_t lq_stream[2] = {nullptr, nullptr};      // per slot: ray-shooting + convolution (normal priority)
+  cudaStream_t lq_stream_hi[2] = {nullptr, nullptr};   // per slot: Gram / solve / image tail (highest priority: its few CTAs get
+                                                       // the SM slots the other slot's convolution frees, instead of queueing behind it)
+  cudaEvent_t lq_fork = nullptr, lq_done[2] = {nullptr, nullptr}, lq_conv[2] = {nullptr, nullptr};
+  int lq_pipeline = 1;       // 0 = all chunks on the caller's stream (A/B)
   float* d_ll = nullptr;
 };
 
@@ -736,6 +745,15 @@ static void gl_free_plan(gl_plan* p) {
   if (p->d_nan) cudaFree(p->d_nan);
   if (p->d_tape) cudaFree(p->d_tape);
   if (p->d_solve_queue) cudaFree(p->d_solve_queue);
+  if (p->d_solve_queue2) cudaFree(p->d_solve_queue2);
+  for (float* q : {p->d_comps2, p->d_R2, p->d_gram2}) if (q) cudaFree(q);
+  for (int k = 0; k < 2; ++k) {
+    if (p->lq_stream[k]) cudaStreamDestroy(p->lq_stream[k]);
+    if (p->lq_stream_hi[k]) cudaStreamDestroy(p->lq_stream_hi[k]);
+    if (p->lq_done[k]) cudaEventDestroy(p->lq_done[k]);
+    if (p->lq_conv[k]) cudaEventDestroy(p->lq_conv[k]);
+  }
+  if (p->lq_fork) cudaEventDestroy(p->lq_fork);
   for (void* q : {(void*)p->d_pos_off, (void*)p->d_pos_x, (void*)p->d_pos_y, (void*)p->d_pos_ex, (void*)p->d_pos_ey, (void*)p->d_pos_ll,
                   (void*)p->d_pos_chi, (void*)p->d_pos_grad}) if (q) cudaFree(q);
   for (cudaEvent_t e : p->tm_ev) cudaEventDestroy(e);
@@ -1087,6 +1105,7 @@ int gl_plan_set_option(gl_plan* p, const char* name, int32_t value) {
   if (!strcmp(name, "conv_tma")) { p->conv_tma = value; return 0; }
   if (!strcmp(name, "conv_const_taps")) { p->conv_const = value; return 0; }
   if (!strcmp(name, "tape")) { p->use_tape = value; return 0; }
+  if (!strcmp(name, "lstsq_pipeline")) { p->lq_pipeline = value; return 0; }
   if (!strcmp(name, "straight_line")) { p->straight_line = value; return 0; }
   if (!strcmp(name, "epl_tol_exp10")) {   // EPL series terms below 10^-value are dropped (12 = the reference's constant, epl.py:37)
     if (value < 6 || value > 30) return gl_fail("gl_plan_set_option: epl_tol_exp10 must be in [6, 30]");
@@ -1366,6 +1385,13 @@ static int gl_launch_conv_fwd_A(gl_plan* p, const float* ss, float scale, float*
   dim3 grid((unsigned)(p->gf.tiles_x * p->gf.tiles_y) * (unsigned)nimg);
   const int nph = p->ss * p->ss;
   if (p->conv_tma && p->conv_tma_ok && ((uintptr_t)ss % 16) == 0) {
+    if (ss == p->d_comps2 && p->d_comps2) {   // second lstsq slot: its own cache entry (copied into the primary one for the launch)
+      if (p->tmap_f2_base != ss || p->tmap_f2_nimg != nimg) {
+        p->tmap_f2_ok = gl_make_image_tmap(&p->tmap_f2, ss, p->n, (size_t)nimg * nph, p->gf.tma_pitch, p->gf.in_rows);
+        p->tmap_f2_base = ss; p->tmap_f2_nimg = nimg;
+      }
+      p->tmap_f = p->tmap_f2; p->tmap_f_ok = p->tmap_f2_ok; p->tmap_f_base = nullptr; p->tmap_f_nimg = -1;
+    } else
     if (p->tmap_f_base != ss || p->tmap_f_nimg != nimg) {   // the map depends on the source buffer only
       p->tmap_f_ok = gl_make_image_tmap(&p->tmap_f, ss, p->n, (size_t)nimg * nph, p->gf.tma_pitch, p->gf.in_rows);
       p->tmap_f_base = ss; p->tmap_f_nimg = nimg;
@@ -1644,8 +1670,9 @@ static int gl_lstsq_reserve(gl_plan* p, int chunk) {
   GL_CUDA(cudaSetDevice(p->device));
   if (p->d_comps) {
     GL_CUDA(cudaDeviceSynchronize());
-    for (float** q : {&p->d_R, &p->d_gram, &p->d_coef, &p->d_ll, &p->d_comps}) { cudaFree(*q); *q = nullptr; }
+    for (float** q : {&p->d_R, &p->d_gram, &p->d_coef, &p->d_ll, &p->d_comps, &p->d_R2, &p->d_gram2, &p->d_comps2}) { if (*q) cudaFree(*q); *q = nullptr; }
     cudaFree(p->d_solve_queue); p->d_solve_queue = nullptr;
+    if (p->d_solve_queue2) { cudaFree(p->d_solve_queue2); p->d_solve_queue2 = nullptr; }
   }
   const size_t per_sample = (size_t)D * p->npix * sizeof(float);
   // component-stack budget: 32 GB of the 180 GB HBM3e, but never more than 40 % of what is free right now
@@ -1653,8 +1680,14 @@ static int gl_lstsq_reserve(gl_plan* p, int chunk) {
   if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b / 5 * 2 < budget) budget = free_b / 5 * 2;
   size_t cb = budget / (per_sample + (size_t)D * npx * sizeof(float));
   if (cb < 1) cb = 1;
+  // One chunk when the whole batch fits the budget (measured at C3, bs 2048: 23.3 ms; every extra chunk pays the ~2.5 ms
+  // eigen-solve tail of its singular samples again).  When memory forces chunks, they alternate between two slots so that one
+  // chunk's tail runs under the other's convolution (4 chunks: 23.8 ms pipelined vs 31.3 ms back to back).
+  bool two = cb < (size_t)p->bs || (chunk > 0 && chunk < p->bs);
+  if (two && chunk == 0) { cb /= 2; if (cb < 1) cb = 1; }
   if (chunk > 0) cb = (size_t)chunk;
-  if (cb > (size_t)p->bs) cb = p->bs;
+  if (cb >= (size_t)p->bs) { cb = p->bs; two = false; }
+  if (p->bs < 16) two = false;
   p->lq_chunk = (int)cb;
   GL_CUDA(cudaMalloc((void**)&p->d_R, cb * (size_t)D * npx * sizeof(float)));
   GL_CUDA(cudaMalloc((void**)&p->d_gram, cb * (size_t)(D + 1) * (D + 1) * sizeof(float)));
@@ -1662,6 +1695,21 @@ static int gl_lstsq_reserve(gl_plan* p, int chunk) {
   GL_CUDA(cudaMalloc((void**)&p->d_coef, (size_t)p->bs * D * sizeof(float)));
   GL_CUDA(cudaMalloc((void**)&p->d_ll, (size_t)p->bs * 2 * sizeof(float)));
   GL_CUDA(cudaMalloc((void**)&p->d_comps, cb * per_sample));
+  if (two) {
+    GL_CUDA(cudaMalloc((void**)&p->d_R2, cb * (size_t)D * npx * sizeof(float)));
+    GL_CUDA(cudaMalloc((void**)&p->d_gram2, cb * (size_t)(D + 1) * (D + 1) * sizeof(float)));
+    GL_CUDA(cudaMalloc((void**)&p->d_solve_queue2, (cb + 1) * sizeof(int)));
+    GL_CUDA(cudaMalloc((void**)&p->d_comps2, cb * per_sample));
+    int prio_lo = 0, prio_hi = 0;
+    GL_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    for (int k = 0; k < 2; ++k) {
+      if (!p->lq_stream[k]) GL_CUDA(cudaStreamCreateWithPriority(&p->lq_stream[k], cudaStreamNonBlocking, prio_lo));
+      if (!p->lq_stream_hi[k]) GL_CUDA(cudaStreamCreateWithPriority(&p->lq_stream_hi[k], cudaStreamNonBlocking, prio_hi));
+      if (!p->lq_done[k]) GL_CUDA(cudaEventCreateWithFlags(&p->lq_done[k], cudaEventDisableTiming));
+      if (!p->lq_conv[k]) GL_CUDA(cudaEventCreateWithFlags(&p->lq_conv[k], cudaEventDisableTiming));
+    }
+    if (!p->lq_fork) GL_CUDA(cudaEventCreateWithFlags(&p->lq_fork, cudaEventDisableTiming));
+  }
   return 0;
 }
 static int gl_lstsq_alloc(gl_plan* p) {
@@ -1684,35 +1732,62 @@ static int gl_lstsq_forward(gl_plan* p, const float* params, float* image, float
   const int npair = ((D + 1) & ~1) / 2;
   const size_t smem_solve = (size_t)(2 * D * (D | 1) + 2 * (npair + 1)) * sizeof(double) + (size_t)(2 * (npair + 1) + 2) * sizeof(int) + 4 * sizeof(double);
   GL_CUDA(cudaMemsetAsync(p->d_nan, 0, (size_t)p->bs * sizeof(int), st));   // component values scrubbed per sample (read by the adjoint)
-  for (int b0 = 0; b0 < p->bs; b0 += p->lq_chunk) {
+  // Chunks alternate between two slots (buffers + stream): chunk k+1's ray-shooting and convolution fill the SMs while chunk k's
+  // Gram / Cholesky / eigen-solve tail (one CTA per sample, a few long-running CTAs for the singular samples) drains.
+  const bool pipe = p->lq_pipeline && p->d_comps2 && p->lq_chunk < p->bs;
+  if (pipe) {
+    GL_CUDA(cudaEventRecord(p->lq_fork, st));
+    for (int k = 0; k < 2; ++k) {
+      GL_CUDA(cudaStreamWaitEvent(p->lq_stream[k], p->lq_fork, 0));
+      GL_CUDA(cudaStreamWaitEvent(p->lq_stream_hi[k], p->lq_fork, 0));
+    }
+  }
+  int ci = 0;
+  for (int b0 = 0; b0 < p->bs; b0 += p->lq_chunk, ++ci) {
     const int nb = (p->bs - b0 < p->lq_chunk) ? p->bs - b0 : p->lq_chunk;
+    const int slot = pipe ? (ci & 1) : 0;
+    cudaStream_t cs = pipe ? p->lq_stream[slot] : st;        // ray-shooting + convolution
+    cudaStream_t ts = pipe ? p->lq_stream_hi[slot] : st;     // the latency-bound tail
+    float* comps = slot ? p->d_comps2 : p->d_comps;
+    float* Rbuf = slot ? p->d_R2 : p->d_R;
+    float* gram = slot ? p->d_gram2 : p->d_gram;
+    int* queue = slot ? p->d_solve_queue2 : p->d_solve_queue;
+    if (pipe && ci >= 2) GL_CUDA(cudaStreamWaitEvent(cs, p->lq_done[slot], 0));   // the slot's previous tail has read R / Gram
     dim3 grid(p->chunks, nb);
     GL_FEAT_DISPATCH(p->feat_idx, {
-      k_raytrace_comps<4, F><<<grid, GLL_THREADS, smem_der, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,
-                                                                 p->d_derived + (size_t)b0 * p->prog.der_total, p->no_deflection, p->d_comps, p->d_nan + b0);
+      k_raytrace_comps<4, F><<<grid, GLL_THREADS, smem_der, cs>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,
+                                                                 p->d_derived + (size_t)b0 * p->prog.der_total, p->no_deflection, comps, p->d_nan + b0);
     })
     GL_LAUNCH_CHECK("k_raytrace_comps");
-    if (gl_run_conv_fwd(p, p->d_comps, 1.f, p->d_R, false, nullptr, st, nb * D)) return 1;
-    if (stack_out) {   // return_stacked: the convolved, pooled unit-amplitude components, nothing solved
-      GL_CUDA(cudaMemcpyAsync(stack_out + (size_t)b0 * D * npx, p->d_R, (size_t)nb * D * npx * sizeof(float), cudaMemcpyDeviceToDevice, st));
-      continue;
+    if (gl_run_conv_fwd(p, comps, 1.f, Rbuf, false, nullptr, cs, nb * D)) return 1;
+    if (stack_out)   // return_stacked: the convolved, pooled unit-amplitude components, nothing solved
+      GL_CUDA(cudaMemcpyAsync(stack_out + (size_t)b0 * D * npx, Rbuf, (size_t)nb * D * npx * sizeof(float), cudaMemcpyDeviceToDevice, cs));
+    if (pipe) {
+      GL_CUDA(cudaEventRecord(p->lq_conv[slot], cs));
+      GL_CUDA(cudaStreamWaitEvent(ts, p->lq_conv[slot], 0));
     }
-    if (p->gram_tc) {
-      GL_CUDA(gl_launch_gram_tc(nb, D, npx, p->d_R, p->d_w, p->d_obs, p->d_gram, nullptr, st));
-      ++g_launch_count;
-    } else {
-      k_gram<<<nb, GLL_THREADS, smem_gram, st>>>(D, npx, p->d_R, p->d_w, p->d_obs, p->d_gram);
-      GL_LAUNCH_CHECK("k_gram");
+    if (!stack_out) {
+      if (p->gram_tc) {
+        GL_CUDA(gl_launch_gram_tc(nb, D, npx, Rbuf, p->d_w, p->d_obs, gram, nullptr, ts));
+        ++g_launch_count;
+      } else {
+        k_gram<<<nb, GLL_THREADS, smem_gram, ts>>>(D, npx, Rbuf, p->d_w, p->d_obs, gram);
+        GL_LAUNCH_CHECK("k_gram");
+      }
+      GL_CUDA(cudaMemsetAsync(queue, 0, sizeof(int), ts));   // [0] = count, [1..] = sample indices
+      k_pinv_solve<<<nb, 128, smem_solve, ts>>>(D, gram, 1e-6, 16, p->d_coef + (size_t)b0 * D, 0, queue + 1, queue);
+      GL_LAUNCH_CHECK("k_pinv_solve");
+      k_pinv_solve<<<nb, 512, smem_solve, ts>>>(D, gram, 1e-6, 16, p->d_coef + (size_t)b0 * D, 1, queue + 1, queue);
+      GL_LAUNCH_CHECK("k_pinv_solve");
+      k_lstsq_image<<<nb, GLL_THREADS, (size_t)D * sizeof(float), ts>>>(
+          D, npx, Rbuf, p->d_coef + (size_t)b0 * D, p->d_obs, p->d_err, image ? image + (size_t)b0 * npx : nullptr,
+          loglike ? loglike + b0 : nullptr, red_chi2 ? red_chi2 + b0 : nullptr, want_gimg ? p->d_gimg + (size_t)b0 * npx : nullptr);
+      GL_LAUNCH_CHECK("k_lstsq_image");
     }
-    GL_CUDA(cudaMemsetAsync(p->d_solve_queue, 0, sizeof(int), st));   // [0] = count, [1..] = sample indices
-    k_pinv_solve<<<nb, 128, smem_solve, st>>>(D, p->d_gram, 1e-6, 16, p->d_coef + (size_t)b0 * D, 0, p->d_solve_queue + 1, p->d_solve_queue);
-    GL_LAUNCH_CHECK("k_pinv_solve");
-    k_pinv_solve<<<nb, 512, smem_solve, st>>>(D, p->d_gram, 1e-6, 16, p->d_coef + (size_t)b0 * D, 1, p->d_solve_queue + 1, p->d_solve_queue);
-    GL_LAUNCH_CHECK("k_pinv_solve");
-    k_lstsq_image<<<nb, GLL_THREADS, (size_t)D * sizeof(float), st>>>(
-        D, npx, p->d_R, p->d_coef + (size_t)b0 * D, p->d_obs, p->d_err, image ? image + (size_t)b0 * npx : nullptr,
-        loglike ? loglike + b0 : nullptr, red_chi2 ? red_chi2 + b0 : nullptr, want_gimg ? p->d_gimg + (size_t)b0 * npx : nullptr);
-    GL_LAUNCH_CHECK("k_lstsq_image");
+    if (pipe) GL_CUDA(cudaEventRecord(p->lq_done[slot], ts));
+  }
+  if (pipe) {
+    for (int k = 0; k < 2 && k < ci; ++k) GL_CUDA(cudaStreamWaitEvent(st, p->lq_done[k], 0));
   }
   if (coeffs_out) GL_CUDA(cudaMemcpyAsync(coeffs_out, p->d_coef, (size_t)p->bs * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return 0;

@@ -1698,6 +1698,7 @@ GL_HD void sersic_bwd(const typename gl_scalar_of<V>::type* d, const V* x, const
 // table on [-5, 5] (tfp.math.interp_regular_1d_grid semantics, 0 outside).
 // =============================================================================================
 #define GL_SHP_MAXN 20
+#define GL_SHP_NMAX_FAST 10   // orders up to this one (BASELINE's n_max = 10, the demo's 8) run the unrolled, register-resident instance
 #define GL_SHP_TABLE_N 6000
 enum { SHP_CX = 0, SHP_CY, SHP_IB, SHP_NMAX, SHP_TAB = 4 };
 enum { SHPG_CX = 0, SHPG_CY, SHPG_IB, SHPG_AMP = 3 };
@@ -1720,21 +1721,28 @@ GL_HD void shp_prep(const T* raw, T* d, int nmax) {
 
 // h[n] = basis function n at u, dh[n] = its derivative (dh may be null).  Returns false when the
 // point is outside the interpolation table (all components are 0 there).
-template <class T>
+// The loops below are bounded by the compile-time NMAXC (and cut at the run-time order by uniform tests): fully unrolled, the basis
+// arrays hu / hv / dhu / dhv live in registers.  With run-time bounds they were indexed dynamically and lived in local memory
+// (256 bytes of stack per thread): k_raytrace_comps executed ~2500 instructions per pixel for ~600 of real work.
+template <class T, int NMAXC>
 GL_HD void shp_basis_rec(const T* d, int nmax, T u, T* h, T* dh) {
+  constexpr int UNR = (NMAXC <= 10) ? NMAXC + 1 : 1;   // unrolled for the fast instance only
   const T* c1 = d + SHP_TAB; const T* c2 = c1 + (nmax + 1); const T* c3 = c2 + (nmax + 1);
   h[0] = c1[0];
   if (dh) dh[0] = T(0);
   T hm2 = T(0), hm1 = c1[0];
-  for (int n = 1; n <= nmax; ++n) {
+#pragma unroll UNR
+  for (int n = 1; n <= NMAXC; ++n) {
+    if (n > nmax) break;
     T hn = c1[n] * u * hm1 - c2[n] * hm2;
     h[n] = hn;
     if (dh) dh[n] = c3[n] * hm1;
     hm2 = hm1; hm1 = hn;
   }
 }
-template <class T>
+template <class T, int NMAXC>
 GL_HD void shp_basis_interp(const float* table, int nmax, T u, T* h, T* dh) {
+  constexpr int UNR = (NMAXC <= 10) ? NMAXC + 1 : 1;
   const T nm1 = T(GL_SHP_TABLE_N - 1);
   T xi_un = (u - T(-5)) / (T(5) - T(-5)) * nm1;
   bool outside = (xi_un < T(0)) || (xi_un > nm1) || gl_isnan(xi_un);
@@ -1745,41 +1753,53 @@ GL_HD void shp_basis_interp(const float* table, int nmax, T u, T* h, T* dh) {
   int ib = (int)below, ia = (int)above;
   T t = xi - below;
   T slope_scale = nm1 / T(10);
-  for (int n = 0; n <= nmax; ++n) {
+#pragma unroll UNR
+  for (int n = 0; n <= NMAXC; ++n) {
+    if (n > nmax) break;
     T yb = T(table[n * GL_SHP_TABLE_N + ib]), ya = T(table[n * GL_SHP_TABLE_N + ia]);
     h[n] = outside ? T(0) : t * ya + (T(1) - t) * yb;
     if (dh) dh[n] = outside ? T(0) : (ya - yb) * slope_scale;
   }
 }
 
-// Surface brightness sum_k amp_k B_k at one point.  If comps != null, instead writes the L unit-
-// amplitude components B_k to comps[k * stride] (lstsq stack).  If gI != null, runs the adjoint:
-// g[SHPG_*] += cotangents (amplitude cotangents only when gamp != null), *gx/*gy += coordinate cotangents.
-template <class T>
-GL_HD T shp_point(const T* d, const float* table, bool interp, int nmax, T x, T y, T* comps, int stride,
-                  const T* gI, T* g, T* gamp, T* gx, T* gy) {
-  T hu[GL_SHP_MAXN + 1], hv[GL_SHP_MAXN + 1], dhu[GL_SHP_MAXN + 1], dhv[GL_SHP_MAXN + 1];
+// Surface brightness of a Shapelets profile at one point, its unit-amplitude components (comps != null: component k goes to
+// comps[k * stride], NaN-scrubbed and zeroed where !keep like tf/simulator.py:200, scrubbed values counted in *n_nan), and the
+// adjoint (gI != null).  NMAXC: compile-time bound of the order (see above).
+template <class T, int NMAXC>
+GL_HD T shp_point_ct(const T* d, const float* table, bool interp, int nmax, T x, T y, T* comps, int stride,
+                     const T* gI, T* g, T* gamp, T* gx, T* gy, bool keep, int* n_nan) {
+  constexpr int UNR = (NMAXC <= 10) ? NMAXC + 1 : 1;
+  T hu[NMAXC + 1], hv[NMAXC + 1], dhu[NMAXC + 1], dhv[NMAXC + 1];
   const T ib = d[SHP_IB];
   const T dx = x - d[SHP_CX], dy = y - d[SHP_CY];
   const T u = dx * ib, v = dy * ib;
   T fac;
   if (interp) {
-    shp_basis_interp(table, nmax, u, hu, gI ? dhu : (T*)nullptr);
-    shp_basis_interp(table, nmax, v, hv, gI ? dhv : (T*)nullptr);
+    shp_basis_interp<T, NMAXC>(table, nmax, u, hu, gI ? dhu : (T*)nullptr);
+    shp_basis_interp<T, NMAXC>(table, nmax, v, hv, gI ? dhv : (T*)nullptr);
     fac = T(1);
   } else {
-    shp_basis_rec(d, nmax, u, hu, gI ? dhu : (T*)nullptr);
-    shp_basis_rec(d, nmax, v, hv, gI ? dhv : (T*)nullptr);
+    shp_basis_rec<T, NMAXC>(d, nmax, u, hu, gI ? dhu : (T*)nullptr);
+    shp_basis_rec<T, NMAXC>(d, nmax, v, hv, gI ? dhv : (T*)nullptr);
     fac = gl_exp(-(u * u + v * v) / T(2));
   }
   const T* amp = d + shp_amp_off(nmax);
   T I = T(0), Iu = T(0), Iv = T(0);
-  int k = 0;
-  for (int o = 0; o <= nmax; ++o) {
-    for (int n2 = 0; n2 <= o; ++n2, ++k) {
-      const int n1 = o - n2;
+  int nn = 0;
+#pragma unroll UNR
+  for (int o = 0; o <= NMAXC; ++o) {
+    if (o > nmax) break;
+#pragma unroll UNR
+    for (int n2 = 0; n2 <= o; ++n2) {
+      const int n1 = o - n2, k = o * (o + 1) / 2 + n2;
       const T B = hu[n1] * hv[n2];
-      if (comps) { comps[k * stride] = fac * B; continue; }
+      if (comps) {
+        const T c = fac * B;
+        const bool bad = gl_isnan(c);
+        nn += (keep && bad) ? 1 : 0;
+        comps[(size_t)k * stride] = (keep && !bad) ? c : T(0);
+        continue;
+      }
       I += amp[k] * B;
       if (gI) {
         Iu += amp[k] * dhu[n1] * hv[n2];
@@ -1788,7 +1808,7 @@ GL_HD T shp_point(const T* d, const float* table, bool interp, int nmax, T x, T 
       }
     }
   }
-  if (comps) return T(0);
+  if (comps) { if (n_nan) *n_nan += nn; return T(0); }
   I *= fac;
   if (gI) {
     T dIdu = fac * Iu, dIdv = fac * Iv;
@@ -1800,6 +1820,12 @@ GL_HD T shp_point(const T* d, const float* table, bool interp, int nmax, T x, T 
     if (gx) { *gx += gdx; *gy += gdy; }
   }
   return I;
+}
+template <class T>
+GL_HD T shp_point(const T* d, const float* table, bool interp, int nmax, T x, T y, T* comps, int stride,
+                  const T* gI, T* g, T* gamp, T* gx, T* gy, bool keep = true, int* n_nan = nullptr) {
+  if (nmax <= GL_SHP_NMAX_FAST) return shp_point_ct<T, GL_SHP_NMAX_FAST>(d, table, interp, nmax, x, y, comps, stride, gI, g, gamp, gx, gy, keep, n_nan);
+  return shp_point_ct<T, GL_SHP_MAXN>(d, table, interp, nmax, x, y, comps, stride, gI, g, gamp, gx, gy, keep, n_nan);
 }
 
 // ---------------------------------------------------------------------------------------------

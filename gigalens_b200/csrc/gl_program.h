@@ -322,15 +322,9 @@ GL_HD int gl_point_components(const GlProgram& P, const T* der, T x, T y, T bx, 
         out[pr.comp_off * stride] = (keep && !gl_isnan(v[0])) ? v[0] : T(0);
       } break;
       case GLT_SHAPELETS: if constexpr ((F & GLF_SHAPELETS) != 0) {
-        const int L = shp_layers(pr.n_max);
-        T* o = out + pr.comp_off * stride;
+        T* o = out + (size_t)pr.comp_off * stride;
         shp_point<T>(der + pr.der_off, pr.table, (pr.flags & 2u) != 0, pr.n_max, px, py, o, stride, (const T*)nullptr,
-                     (T*)nullptr, (T*)nullptr, (T*)nullptr, (T*)nullptr);
-        for (int k = 0; k < L; ++k) {
-          const T v = o[k * stride];
-          if (keep && gl_isnan(v)) ++n_nan;
-          if (!keep || gl_isnan(v)) o[k * stride] = T(0);
-        }
+                     (T*)nullptr, (T*)nullptr, (T*)nullptr, (T*)nullptr, keep, &n_nan);   // scrubs and counts as it stores
       } break;
       default: break;
     }
