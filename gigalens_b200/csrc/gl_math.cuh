@@ -1303,9 +1303,46 @@ GL_HD void dpie_bwd(const typename gl_scalar_of<T>::type* d, const T* x, const T
 // d(alpha)/d(rc|rt) follows from z = num/den, zr = log z:  dz = (num' - z den')/den, dzr = dz / z.
 // FAST (every member of the group has r_core < r_cut, the usual case; decided per sample in gl_sample_prep): the chain matrix M is
 // sparse -- d(rc)/d(theta_E) = d(rt)/d(theta_E) = d(rc)/d(r_cut) = d(rt)/d(r_core) = 0 -- and the deflection is linear in theta_E, so
-// column 0 of the Jacobian is (group deflection) / theta_E (formed by the caller) and columns 1, 2 take two terms each: 8 FMAs per
-// member-pixel instead of 18.
-template <class T, int NP, bool FAST = false>
+// column 0 of the Jacobian is (group deflection) / theta_E (formed by the caller) and columns 1, 2 take two terms each.
+// The tangents come from the FACTORED form of z = (num_rc / den_rc) (den_rt / num_rt): log z = log num_rc - log den_rc - log num_rt
+// + log den_rt, where only the imaginary parts depend on rc / rt (b' = 2 sqe rc / sc, d' = 2 sqe =: k;  e' = 2 sqe rt / st, f' = k):
+//   d log z / d rc = i b'/num_rc - i k/den_rc = (b' b/N1 - k d/N2) + i (b' a/N1 - k c/N2)
+//   d log z / d rt = -i e'/num_rt + i k/den_rt = (k f/N4 - e' e/N3) + i (k c/N4 - e' a/N3),     N1..N4 = squared moduli of the factors,
+// and (re, im) = i zci log z: 20 packed operations and four MUFU rcp for both tangents instead of 45 through the quotient form.
+// The forward value itself stays on dpie_core_fwd (bit-identical to dpie_fwd).
+template <class T, int NP>
+GL_HD void dpie_fwd_jac_fast(const typename gl_scalar_of<T>::type* d, const T* x, const T* y, T* ax, T* ay, T (*Jx)[NP], T (*Jy)[NP]) {
+  typedef typename gl_scalar_of<T>::type S;
+  const T c = T(d[DP_C]), s = T(d[DP_S]), scale = T(d[DP_SCALE]), cx = T(d[DP_CX]), cy = T(d[DP_CY]);
+  const S zs = d[DP_ZCI] * d[DP_SCALE], k = S(2) * d[DP_SQE];
+  const T krc = T(k * d[DP_RC] * zs), krt = T(k * d[DP_RT] * zs), kz = T(k * zs), one = T(S(1));
+  const S* M = d + DP_M;
+  const T m1 = T(M[1]), m2 = T(M[2]), m4 = T(M[4]), m8 = T(M[8]);
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    T dx = x[j] - cx, dy = y[j] - cy;
+    T xr = gl_fma(dx, c, dy * s), yr = gl_fma(dy, c, -(dx * s));
+    DpieFw<T> W; T re, im;
+    dpie_core_fwd<T>(d, xr, yr, W, re, im);
+    const T Ar = gl_fma(re, c, -(im * s)), Ai = gl_fma(re, s, im * c);
+    ax[j] = scale * Ar;
+    ay[j] = scale * Ai;
+    // tangents of scale * (re, im) w.r.t. rc and rt
+    const T a2 = W.a * W.a, c2 = W.c_ * W.c_;
+    const T iN1 = gl_div_fast(one, gl_fma(W.b_, W.b_, a2)), iN2 = gl_div_fast(one, gl_fma(W.d_, W.d_, c2));
+    const T iN3 = gl_div_fast(one, gl_fma(W.e_, W.e_, a2)), iN4 = gl_div_fast(one, gl_fma(W.f_, W.f_, c2));
+    const T P1 = krc * W.isc * iN1, P2 = kz * iN2, Q1 = krt * W.ist * iN3, Q2 = kz * iN4;
+    const T tre0 = gl_fma(P2, W.c_, -(P1 * W.a)), tim0 = gl_fma(P1, W.b_, -(P2 * W.d_));
+    const T tre1 = gl_fma(Q1, W.a, -(Q2 * W.c_)), tim1 = gl_fma(Q2, W.f_, -(Q1 * W.e_));
+    const T B0r = gl_fma(tre0, c, -(tim0 * s)), B0i = gl_fma(tre0, s, tim0 * c);
+    const T B1r = gl_fma(tre1, c, -(tim1 * s)), B1i = gl_fma(tre1, s, tim1 * c);
+    Jx[1][j] = gl_fma(m1, Ar, gl_fma(m4, B0r, Jx[1][j]));
+    Jy[1][j] = gl_fma(m1, Ai, gl_fma(m4, B0i, Jy[1][j]));
+    Jx[2][j] = gl_fma(m2, Ar, gl_fma(m8, B1r, Jx[2][j]));
+    Jy[2][j] = gl_fma(m2, Ai, gl_fma(m8, B1i, Jy[2][j]));
+  }
+}
+template <class T, int NP>
 GL_HD void dpie_fwd_jac(const typename gl_scalar_of<T>::type* d, const T* x, const T* y, T* ax, T* ay, T (*Jx)[NP], T (*Jy)[NP]) {
   typedef typename gl_scalar_of<T>::type S;
   const T c = T(d[DP_C]), s = T(d[DP_S]), scale = T(d[DP_SCALE]), zci = T(d[DP_ZCI]), two_sqe = T(S(2) * d[DP_SQE]);
@@ -1346,12 +1383,7 @@ GL_HD void dpie_fwd_jac(const typename gl_scalar_of<T>::type* d, const T* x, con
     // rotate the two tangents back once; then every base parameter k is a 3-term combination per component
     const T B0r = gl_fma(tre[0], c, -(tim[0] * s)), B0i = gl_fma(tre[0], s, tim[0] * c);
     const T B1r = gl_fma(tre[1], c, -(tim[1] * s)), B1i = gl_fma(tre[1], s, tim[1] * c);
-    if constexpr (FAST) {
-      Jx[1][j] = gl_fma(T(M[1]), Ar, gl_fma(T(M[4]), B0r, Jx[1][j]));
-      Jy[1][j] = gl_fma(T(M[1]), Ai, gl_fma(T(M[4]), B0i, Jy[1][j]));
-      Jx[2][j] = gl_fma(T(M[2]), Ar, gl_fma(T(M[8]), B1r, Jx[2][j]));
-      Jy[2][j] = gl_fma(T(M[2]), Ai, gl_fma(T(M[8]), B1i, Jy[2][j]));
-    } else {
+    {
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         Jx[k][j] += gl_fma(T(M[k]), Ar, gl_fma(T(M[3 + k]), B0r, T(M[6 + k]) * B1r));

@@ -221,7 +221,7 @@ GL_HD void gl_pix_beta_jac(const GlProgram& P, const typename gl_scalar_of<T>::t
         for (int j = 0; j < NP; ++j) { gx[j] = T(0); gy[j] = T(0); }
         for (int m = 0; m < nm; ++m) {
           T ax[NP], ay[NP];
-          dpie_fwd_jac<T, NP, true>(der + pr.der_off + m * pr.der_size, x, y, ax, ay, Jx, Jy);
+          dpie_fwd_jac_fast<T, NP>(der + pr.der_off + m * pr.der_size, x, y, ax, ay, Jx, Jy);
 #pragma unroll
           for (int j = 0; j < NP; ++j) { gx[j] += ax[j]; gy[j] += ay[j]; }
         }

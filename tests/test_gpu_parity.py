@@ -298,6 +298,26 @@ def test_lstsq_chunked_passes_match_single_pass():
         assert np.array_equal(a, b)
 
 
+def test_lstsq_two_slot_pipeline_matches_single_pass():
+    """When memory forces chunks (here: forced by the option), they alternate between two buffer slots / stream pairs so that one
+    chunk's Gram / solve tail runs under the other's convolution; the results must be the single-pass ones, bit for bit."""
+    bs = 40
+    wl = workloads.c3_workload(n_max=4)
+    pmod = BackwardProbModel(wl["prior"], wl["observed"], wl["background_rms"], wl["exp_time"])
+    z = torch.as_tensor(pmod.bij_inverse(wl["prior"].sample(bs, seed=8)), device="cuda")
+    outs = []
+    for opts in ({}, {"lstsq_chunk": 8}, {"lstsq_chunk": 8, "lstsq_pipeline": 0}, {"lstsq_chunk": 16}):
+        sim = LensSimulator(wl["phys_model"], wl["sim_config"], bs=bs)
+        for k, v in opts.items():
+            sim.set_option(k, v)
+        outs.append([t.cpu().numpy() for t in pmod.log_prob_and_grad(sim, z)])
+        outs[-1].append(sim.lstsq_simulate(pmod.bij_forward(sim, z), wl["observed"], pmod.err_map).cpu().numpy())
+        outs[-1].append(sim.lstsq_simulate(pmod.bij_forward(sim, z), wl["observed"], pmod.err_map, return_stacked=True).cpu().numpy())
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert np.array_equal(a, b)
+
+
 def test_lstsq_rank_deficient_uses_pinv_cut():
     """Two identical linear components make X^T X singular: the rcond = 1e-6 cut of tf.linalg.pinv is
     active and the minimum-norm amplitudes split evenly between the twins (general Jacobi path)."""
