@@ -449,7 +449,7 @@ def bench_c5(ctx, args):
     out = {}
     # ---- SVI
     seq.time_collectives(True)
-    seq.SVI(optimizer=Adam(1e-3), start_mean=z0, n_vi=n, num_steps=2, seed=2)   # warm-up: plan creation, NCCL channel set-up
+    seq.SVI(optimizer=Adam(1e-3), start_mean=z0, n_vi=n, num_steps=2, seed=2)   # warm-up: plan creation (the drivers reuse it), NCCL channels
     seq.time_collectives(True)
     _sync_all(ctx)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -463,7 +463,7 @@ def bench_c5(ctx, args):
     out["c5_svi"] = {"workload": "SVI (full-rank MVN surrogate) on the C4 cluster model, ModellingSequence.SVI (BASELINE.json configs[4])",
                      "global_batch": n, "batch_per_gpu": n // ctx.world, "steps": svi_steps, "ms_per_step": ms / svi_steps,
                      "value": n * svi_steps / (ms * 1e-3), "unit": UNIT, "scaling": "strong",
-                     "includes": "plan creation + per-step surrogate sampling / autograd of the ELBO surrogate / Adam on the host side of the driver",
+                     "includes": "per-step surrogate sampling, autograd of the ELBO surrogate and Adam in torch around the fused log-prob + gradient call",
                      "allreduce": {"count": n_coll, "floats_per_call": 1 + 16 + 16 * 17 // 2, "ms_total": coll_ms,
                                    "share_of_step": coll_ms / ms, "backend": "nccl" if ctx.world > 1 else "none (single rank)"},
                      "elbo_first_last": [losses[0], losses[-1]], "elbo_finite": bool(np.isfinite(losses).all())}
@@ -492,7 +492,7 @@ def bench_c5(ctx, args):
     out["c5_hmc"] = {"workload": "HMC (SVI-preconditioned, dual averaging + ChEES) on the C4 cluster model, ModellingSequence.HMC (configs[4])",
                      "global_batch": n, "batch_per_gpu": n // ctx.world, "steps": n_steps, "evals": tot_evals, "ms_per_step": tot_ms / n_steps,
                      "value": tot_evals / (tot_ms * 1e-3), "unit": UNIT, "scaling": "strong",
-                     "includes": "plan creation + initial log-prob of the chains + momentum draws / leapfrog updates in torch",
+                     "includes": "initial log-prob of the chains + momentum draws / leapfrog updates in torch around the fused log-prob + gradient call",
                      "allreduce": {"ms_total": tot_coll, "share_of_step": tot_coll / tot_ms, "backend": "nccl" if ctx.world > 1 else "none (single rank)"},
                      "phases": phases}
     return out

@@ -281,24 +281,24 @@ __global__ void __launch_bounds__(512) k_pinv_solve(int D, const float* __restri
       __syncthreads();
       // two-sided rotation A <- J^T A J in ONE pass: the 2x2 block (rows of pair r) x (columns of pair r2) depends
       // only on itself, so every thread owns whole blocks and no intermediate barrier is needed.
-      for (int r = tid >> 6; r < npair; r += nthr >> 6) {
+      // (flat over the npair x npair blocks: every lane has work -- the former 8 x 64 mapping left 31 of 64 lanes idle)
+      for (int e = tid; e < npair * npair; e += nthr) {
+        const int r = e / npair, r2 = e - r * npair;
         const int p = pq[2 * r], q = pq[2 * r + 1];
         const double c1 = cs[2 * r], s1 = cs[2 * r + 1];
         const bool vq = q < D;
-        for (int r2 = tid & 63; r2 < npair; r2 += 64) {
-          const int p2 = pq[2 * r2], q2 = pq[2 * r2 + 1];
-          const double c2 = cs[2 * r2], s2 = cs[2 * r2 + 1];
-          const bool vq2 = q2 < D;
-          const double app = A[p * LD + p2], apq2 = vq2 ? A[p * LD + q2] : 0.0;
-          const double aqp = vq ? A[q * LD + p2] : 0.0, aqq = (vq && vq2) ? A[q * LD + q2] : 0.0;
-          // columns (J on the right), then rows (J^T on the left)
-          const double tpp = c2 * app - s2 * apq2, tpq = s2 * app + c2 * apq2;
-          const double tqp = c2 * aqp - s2 * aqq, tqq = s2 * aqp + c2 * aqq;
-          A[p * LD + p2] = c1 * tpp - s1 * tqp;
-          if (vq2) A[p * LD + q2] = c1 * tpq - s1 * tqq;
-          if (vq) A[q * LD + p2] = s1 * tpp + c1 * tqp;
-          if (vq && vq2) A[q * LD + q2] = s1 * tpq + c1 * tqq;
-        }
+        const int p2 = pq[2 * r2], q2 = pq[2 * r2 + 1];
+        const double c2 = cs[2 * r2], s2 = cs[2 * r2 + 1];
+        const bool vq2 = q2 < D;
+        const double app = A[p * LD + p2], apq2 = vq2 ? A[p * LD + q2] : 0.0;
+        const double aqp = vq ? A[q * LD + p2] : 0.0, aqq = (vq && vq2) ? A[q * LD + q2] : 0.0;
+        // columns (J on the right), then rows (J^T on the left)
+        const double tpp = c2 * app - s2 * apq2, tpq = s2 * app + c2 * apq2;
+        const double tqp = c2 * aqp - s2 * aqq, tqq = s2 * aqp + c2 * aqq;
+        A[p * LD + p2] = c1 * tpp - s1 * tqp;
+        if (vq2) A[p * LD + q2] = c1 * tpq - s1 * tqq;
+        if (vq) A[q * LD + p2] = s1 * tpp + c1 * tqp;
+        if (vq && vq2) A[q * LD + q2] = s1 * tpq + c1 * tqq;
       }
       // eigenvectors: V <- V J   (k fastest across threads: stride LD, conflict-free)
       for (int e = tid; e < npair * D; e += nthr) {

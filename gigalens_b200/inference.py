@@ -98,6 +98,17 @@ class ModellingSequence:
         self.sim_config = sim_config
         self._simulator_cls = simulator_cls   # injectable so the sharding / collective logic is testable on CPU
         self._coll_events = None              # measurement aid: CUDA event pairs around every all-reduce (bench.py)
+        self._sim = None                      # the most recent simulator (one plan = tens of GB at the cluster config: reused
+                                              # by the next driver call with the same batch size instead of being re-allocated)
+
+    def _simulator(self, bs):
+        """A simulator for `bs` samples: the previous call's when the batch size matches (plans are immutable), else a new one
+        (the old plan is released first, so two workspaces never coexist)."""
+        if self._sim is not None and getattr(self._sim, "bs", None) == bs:
+            return self._sim
+        self._sim = None
+        self._sim = self._simulator_cls(self.phys_model, self.sim_config, bs=bs)
+        return self._sim
 
     def time_collectives(self, on=True):
         """Record CUDA events on the current stream around every all-reduce of SVI / HMC from now on."""
@@ -144,7 +155,7 @@ class ModellingSequence:
         start = pm.prior.sample(n_samples, seed=seed) if start is None else start
         z_all = pm.bij_inverse(start)
         lo, hi = _shard(n_samples, rank, world)
-        sim = self._simulator_cls(self.phys_model, self.sim_config, bs=hi - lo)
+        sim = self._simulator(hi - lo)
         z = torch.as_tensor(z_all[lo:hi], device=sim.device).clone()
         # tf/inference.py:27-31: pixels count when include_pixels, image positions add n_position
         event_size = 0.0
@@ -188,7 +199,7 @@ class ModellingSequence:
         pm = self.prob_model
         optimizer = optimizer or Adam(1e-3)
         lo, hi = _shard(n_vi, rank, world)
-        sim = self._simulator_cls(self.phys_model, self.sim_config, bs=hi - lo)
+        sim = self._simulator(hi - lo)
         dev = sim.device
         mu = torch.as_tensor(np.asarray(start_mean.detach().cpu() if torch.is_tensor(start_mean) else start_mean),
                              dtype=torch.float32, device=dev).reshape(-1).clone()
@@ -256,7 +267,7 @@ class ModellingSequence:
         pm = self.prob_model
         lo, hi = _shard(n_hmc, rank, world)
         nloc = hi - lo
-        sim = self._simulator_cls(self.phys_model, self.sim_config, bs=nloc)
+        sim = self._simulator(nloc)
         dev = sim.device
         gen = torch.Generator(device=dev)
         gen.manual_seed(seed * 1000003 + rank)
@@ -395,7 +406,7 @@ class ModellingSequence:
         d = z_all.shape[1]
         lo, hi = _shard(N, rank, world)
         nloc = hi - lo
-        sim = self._simulator_cls(self.phys_model, self.sim_config, bs=nloc)
+        sim = self._simulator(nloc)
         dev = sim.device
         gen = torch.Generator(device=dev)
         gen.manual_seed(seed * 1000003 + rank)
