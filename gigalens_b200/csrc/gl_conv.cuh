@@ -167,6 +167,78 @@ __device__ __forceinline__ void corr_rows2(const float* __restrict__ in, int pit
   corr_rows2_t<A, LW>(in, pitch, GlTapsSmem{u}, acc2);
 }
 
+// ---- column-pair scheme ------------------------------------------------------------------------------------------
+// acc[r][cp] holds the output pair (column 2cp, column 2cp+1) of row r.  For tap (a, b) the pair needs the two ADJACENT inputs
+// (strip[2cp+b], strip[2cp+b+1]) and ONE tap:  FFMA2 acc, w[a][b].F32 (scalar broadcast), (s_k, s_k+1).F32x2, acc.  Against the
+// row-pair scheme above: (i) no zero taps -- a row pair spends A+1 FMAs on A taps because its two rows are one tap apart, 7.7 % of
+// the FMA-pipe work at A = 13; (ii) the taps of one (strip row, output row) are one contiguous tap row, read with LDS.128
+// (A/4 wavefronts per 2A FFMA2 instead of one LDS.64 per 4); (iii) ramp rows need no specialised instances: output rows outside
+// [row-A+1, row] are skipped by a uniform test, so the loop body is one block of code per output row.
+// Even input pairs come straight from the LDS.64 / LDS.128 strip loads; odd pairs are re-packed once per strip row.
+#define GLC_CP (GLC_RX / 2)
+__host__ __device__ constexpr int glc_wpitch(int A) { return (A + 3) & ~3; }   // floats per tap row; table: [phase][A][wpitch]
+// `zero` is a run-time 0 (a kernel parameter): the odd pairs are formed as x ^ zero, two LOP3 on the integer pipe, so that they
+// are COMPUTED values with registers of their own.  A plain register re-pack is a copy to ptxas, which coalesces it with the strip
+// registers and then re-aligns the pair with two MOVs in front of almost every FFMA2 that uses it (one MOV per FFMA2 overall).
+template <int A, int LW>
+__device__ __forceinline__ void corr_rows_cp(const float* __restrict__ in, int pitch, const float* __restrict__ w_ph,
+                                             float2 (&acc)[GLC_RY][GLC_CP], unsigned zero) {
+  constexpr int SL = (GLC_RX + A - 1 + 3) & ~3;
+  constexpr int NE = SL / 2;          // even pairs (s[2v], s[2v+1])
+  constexpr int WP = glc_wpitch(A);
+  constexpr int ROWS = GLC_RY + A - 1;
+#pragma unroll 1
+  for (int row = 0; row < ROWS; ++row) {
+    const float* inrow = in + row * pitch;
+    // input pairs as opaque 64-bit registers: even pairs (s[2v], s[2v+1]) straight from the strip loads, odd pairs
+    // (s[2v+1], s[2v+2]) packed ONCE per strip row -- left to itself ptxas re-packs an odd pair with two MOVs in front of almost
+    // every FFMA2 that uses it (one MOV per FFMA2 overall: the kernel became issue-bound)
+    unsigned long long se[NE], so[NE];
+    if constexpr (LW == 4) {
+      const ulonglong2* src = reinterpret_cast<const ulonglong2*>(inrow);
+#pragma unroll
+      for (int v = 0; v < SL / 4; ++v) { const ulonglong2 t = src[v]; se[2 * v] = t.x; se[2 * v + 1] = t.y; }
+    } else {
+      const unsigned long long* src = reinterpret_cast<const unsigned long long*>(inrow);
+#pragma unroll
+      for (int v = 0; v < NE; ++v) se[v] = src[v];
+    }
+#pragma unroll
+    for (int v = 0; v + 1 < NE; ++v)
+      asm("{ .reg .b32 a0, a1, b0, b1; mov.b64 {a0, a1}, %1; mov.b64 {b0, b1}, %2; xor.b32 a1, a1, %3; xor.b32 b0, b0, %3; mov.b64 %0, {a1, b0}; }"
+          : "=l"(so[v]) : "l"(se[v]), "l"(se[v + 1]), "r"(zero));
+    so[NE - 1] = se[NE - 1];   // never used (k <= RX + A - 3 < SL - 1); keeps the array fully defined
+    auto apply = [&](int r, int a) {
+      const float4* wv = reinterpret_cast<const float4*>(w_ph + a * WP);
+      float w[WP];
+#pragma unroll
+      for (int v = 0; v < WP / 4; ++v) { const float4 t = wv[v]; w[4 * v] = t.x; w[4 * v + 1] = t.y; w[4 * v + 2] = t.z; w[4 * v + 3] = t.w; }
+#pragma unroll
+      for (int b = 0; b < A; ++b) {
+#pragma unroll
+        for (int cp = 0; cp < GLC_CP; ++cp) {
+          const int k = 2 * cp + b;
+          const unsigned long long sp = (k & 1) ? so[k >> 1] : se[k >> 1];
+          asm("{ .reg .b64 ww, cc; mov.b64 ww, {%2, %2}; mov.b64 cc, {%0, %1}; fma.rn.f32x2 cc, ww, %3, cc; mov.b64 {%0, %1}, cc; }"
+              : "+f"(acc[r][cp].x), "+f"(acc[r][cp].y) : "f"(w[b]), "l"(sp));
+        }
+      }
+    };
+    if (row >= GLC_RY - 1 && row <= A - 1) {
+      // every output row of the tile is reached: one straight-line block (the odd pairs are packed once, the tap loads of the six
+      // output rows are scheduled ahead of the FFMA2 stream)
+#pragma unroll
+      for (int r = 0; r < GLC_RY; ++r) apply(r, row - r);
+    } else {
+#pragma unroll
+      for (int r = 0; r < GLC_RY; ++r) {
+        const int a = row - r;
+        if (a >= 0 && a < A) apply(r, a);   // warp-uniform
+      }
+    }
+  }
+}
+
 struct GlLikeArgs {
   const float* observed;    // [n*n]
   const float* error_map;   // [n*n] or null

@@ -87,17 +87,21 @@ __device__ __forceinline__ void gtc_drain(uint32_t taddr, float (&acc)[NB * 16])
   }
 }
 
-// grid = number of samples in the chunk, block = 128; NB = N / 16 column blocks (N = D+1 rounded up to 16).
+// grid = ksplit x (number of samples in the chunk), block = 128; NB = N / 16 column blocks (N = D+1 rounded up to 16).
+// ksplit = 1: one CTA per sample, plain stores.  ksplit = 2: two CTAs per sample, each sums half of the pixel segments and ADDS its
+// rows to the (pre-zeroed) Gram with fp32 atomics -- two addends commute, so the result does not depend on which CTA arrives
+// first and stays bit-reproducible.  The kernel is latency-bound (one 128-thread CTA per sample converts, stores and issues;
+// 11 % of the warp slots busy): twice the CTAs hide twice the latency.
 // err_flag (may be null): set to 1 if a barrier wait timed out.
 template <int NB>
 __global__ void __launch_bounds__(GTC_THREADS) k_gram_tc(int D, int npx, const float* __restrict__ R, const float* __restrict__ w,
                                                         const float* __restrict__ obs, float* __restrict__ gram,
-                                                        int* __restrict__ err_flag) {
+                                                        int* __restrict__ err_flag, int ksplit) {
   extern __shared__ __align__(1024) unsigned char gtc_smem[];
   unsigned char* smem = gtc_smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * GTC_STAGE);     // [0,1]: stage free, [2,3]: accumulator a complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 2 * GTC_STAGE + 32);
-  const int tid = threadIdx.x, warp = tid >> 5, b = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, b = blockIdx.x / ksplit, half = blockIdx.x - b * ksplit;
   const int Dx = D + 1;
   constexpr int N = NB * 16;
   const float* Rb = R + (size_t)b * D * npx;
@@ -118,8 +122,13 @@ __global__ void __launch_bounds__(GTC_THREADS) k_gram_tc(int D, int npx, const f
   const uint32_t tmem = *tmem_slot;
   // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N, M = 128
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  const int nstage = (npx + GTC_KC - 1) / GTC_KC;
-  const int nseg = (nstage + GTC_SEG - 1) / GTC_SEG;
+  const int nstage_all = (npx + GTC_KC - 1) / GTC_KC;
+  const int nseg_all = (nstage_all + GTC_SEG - 1) / GTC_SEG;
+  // this CTA's share of the segments: [seg0, seg1), stages [st0, st1)
+  const int seg0 = (nseg_all * half) / ksplit, seg1 = (nseg_all * (half + 1)) / ksplit;
+  const int st0 = seg0 * GTC_SEG, st1 = (seg1 * GTC_SEG < nstage_all) ? seg1 * GTC_SEG : nstage_all;
+  const int nstage = st1 - st0;                      // stages of this CTA (local index st below)
+  const int nseg = seg1 - seg0;
   const int nitem = ((Dx + 7) / 8) * 8 * (GTC_KC / 4);   // (row, 16-byte chunk) items per stage, whole 8-row groups
   const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);   // TMEM lane == accumulator row; warp w owns lanes 32w..32w+31
   float acc[NB * 16];
@@ -134,7 +143,7 @@ __global__ void __launch_bounds__(GTC_THREADS) k_gram_tc(int D, int npx, const f
   float4 pre[GTC_MAXI], prw[GTC_MAXI];
   const bool vec_ok = (npx % 4) == 0;               // channel rows are then 16-byte aligned
   auto fetch = [&](int stage) {
-    const int p0 = stage * GTC_KC;
+    const int p0 = (st0 + stage) * GTC_KC;
 #pragma unroll
     for (int k = 0; k < GTC_MAXI; ++k) {
       const int it = tid + k * GTC_THREADS;
@@ -220,13 +229,19 @@ __global__ void __launch_bounds__(GTC_THREADS) k_gram_tc(int D, int npx, const f
     gtc_drain<NB>(lane_base + (uint32_t)(pa * GTC_ACC_COLS), acc);
   }
   float* out = gram + (size_t)b * Dx * Dx;
-  if (ok) {
+  if (ok && nstage > 0) {
     if (tid < Dx) {
+      if (ksplit == 1) {
 #pragma unroll
-      for (int q = 0; q < NB * 16; ++q)
-        if (q < Dx) out[(size_t)tid * Dx + q] = acc[q];
+        for (int q = 0; q < NB * 16; ++q)
+          if (q < Dx) out[(size_t)tid * Dx + q] = acc[q];
+      } else {
+#pragma unroll
+        for (int q = 0; q < NB * 16; ++q)
+          if (q < Dx) atomicAdd(out + (size_t)tid * Dx + q, acc[q]);
+      }
     }
-  } else {   // a barrier wait timed out: fail loudly (NaN Gram -> NaN amplitudes and likelihood), never silently
+  } else if (!ok) {   // a barrier wait timed out: fail loudly (NaN Gram -> NaN amplitudes and likelihood), never silently
     for (int i = tid; i < Dx * Dx; i += GTC_THREADS) out[i] = __int_as_float(0x7fc00000);
     if (tid == 0 && err_flag) *err_flag = 1;
   }
@@ -245,12 +260,18 @@ static inline cudaError_t gl_gram_tc_init() {
 }
 
 // host-side launch: pick the column-block count for D (gl_gram_tc_init() must have run on this device)
+// ksplit = 2 adds into `gram`: the launcher zeroes it first.
 static inline cudaError_t gl_launch_gram_tc(int nb, int D, int npx, const float* R, const float* w, const float* obs, float* gram,
-                                            int* err_flag, cudaStream_t st) {
+                                            int* err_flag, cudaStream_t st, int ksplit = 2) {
   const int NBv = (D + 1 + 15) / 16;
+  if (npx < 4 * GTC_KC * GTC_SEG) ksplit = 1;       // too few segments to split
+  if (ksplit > 1) {
+    cudaError_t e = cudaMemsetAsync(gram, 0, (size_t)nb * (D + 1) * (D + 1) * sizeof(float), st);
+    if (e != cudaSuccess) return e;
+  }
 #define GTC_CASE(n)                                                                                                 \
   case n: {                                                                                                         \
-    k_gram_tc<n><<<nb, GTC_THREADS, GTC_SMEM, st>>>(D, npx, R, w, obs, gram, err_flag);                             \
+    k_gram_tc<n><<<nb * ksplit, GTC_THREADS, GTC_SMEM, st>>>(D, npx, R, w, obs, gram, err_flag, ksplit);            \
     return cudaGetLastError();                                                                                      \
   }
   switch (NBv) {

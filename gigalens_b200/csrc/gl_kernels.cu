@@ -662,6 +662,7 @@ struct gl_plan {
   bool tape_valid = false;   // the last forward pass wrote the tape (same parameters as the adjoint that follows)
   // image-position likelihood (gl_plan_set_positions)
   int gram_tc = 1;           // lstsq normal equations on the tensor cores (tcgen05, 3xTF32); 0 = FP32-FMA k_gram (A/B testing)
+  int gram_ksplit = 2;       // CTAs per sample of the tensor-core Gram (2 = split the pixel segments in two halves; 1 for A/B)
   int include_pixels = 1, include_positions = 0;
   int pos_npts = 0, pos_nsys = 0;
   float pos_n_position = 0.f;
@@ -1133,6 +1134,7 @@ int gl_plan_set_option(gl_plan* p, const char* name, int32_t value) {
     p->include_positions = value != 0; return 0;
   }
   if (!strcmp(name, "gram_tc")) { p->gram_tc = value != 0; return 0; }
+  if (!strcmp(name, "gram_ksplit")) { p->gram_ksplit = value >= 2 ? 2 : 1; return 0; }
   if (!strcmp(name, "packed_math")) { p->use_packed = value; return 0; }   // 0: scalar-lane kernels (A/B testing)
   if (!strcmp(name, "lstsq_chunk")) {   // samples per pass of the lstsq component stack (0 = size by memory budget): re-reserves
     if (value < 0) return gl_fail("gl_plan_set_option: lstsq_chunk must be >= 0");
@@ -1768,7 +1770,7 @@ static int gl_lstsq_forward(gl_plan* p, const float* params, float* image, float
     }
     if (!stack_out) {
       if (p->gram_tc) {
-        GL_CUDA(gl_launch_gram_tc(nb, D, npx, Rbuf, p->d_w, p->d_obs, gram, nullptr, ts));
+        GL_CUDA(gl_launch_gram_tc(nb, D, npx, Rbuf, p->d_w, p->d_obs, gram, nullptr, ts, p->gram_ksplit));
         ++g_launch_count;
       } else {
         k_gram<<<nb, GLL_THREADS, smem_gram, ts>>>(D, npx, Rbuf, p->d_w, p->d_obs, gram);

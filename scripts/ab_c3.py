@@ -8,7 +8,7 @@ from gigalens_b200.simulator import LensSimulator
 bs = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 wl = workloads.c3_workload(observed=workloads.c3_observation())
 ref = None
-for opts in ({}, {"lstsq_pipeline": 0}, {"lstsq_chunk": bs // 2}, {"lstsq_chunk": bs // 8}, {"lstsq_chunk": bs // 16}, {"lstsq_chunk": bs, "lstsq_pipeline": 0}):
+for opts in ({}, {"gram_ksplit": 1}, {"lstsq_chunk": bs // 2}):
     sim = LensSimulator(wl["phys_model"], wl["sim_config"], bs=bs)
     pm = BackwardProbModel(wl["prior"], wl["observed"], wl["background_rms"], wl["exp_time"])
     z = torch.as_tensor(pm.bij_inverse(wl["prior"].sample(bs, seed=0)), device="cuda")
