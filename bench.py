@@ -261,7 +261,9 @@ def build_roofline(ctx, sim, stage_ms, step_ms, flops_tab, alg_bytes, ncu_key, f
         rec = next((ncu[key] for key in (nm + "_p", nm + "_tma", nm) if key in ncu), {})
         gbs = alg_bytes[nm] * bs / (stage_ms[k] * 1e-3) / 1e9
         tf = flops_tab[nm] * bs / (stage_ms[k] * 1e-3) / 1e12
-        ex = rec.get("executed_flops")   # ncu: 2 x ffma + fmul + fadd thread-instructions (pred on), per launch
+        ex = rec.get("executed_flops")   # ncu source page: FFMA(2) x 2(4) + FMUL(2) / FADD(2) x 1(2) predicated-on thread instructions, per launch
+        if ex and rec.get("ncu_bs"):
+            ex = ex * bs / rec["ncu_bs"]  # the capture ran a smaller batch: work per launch scales with the batch
         per_kernel[nm] = {
             "ms": stage_ms[k], "share_of_step": stage_ms[k] / step_ms,
             "fp32_TFLOPs_useful": tf, "fp32_frac_useful": tf / fp32["peak_TFLOPs"],
@@ -388,6 +390,20 @@ def bench_c4(ctx, args):
     flops = {"k_raytrace_fwd": fwd, "k_conv_fwd": conv, "k_conv_bwd": conv, "k_raytrace_bwd": 2.0 * fwd}
     alg_bytes = {"k_raytrace_fwd": 4 * npix, "k_conv_fwd": 4 * npix + 8 * P, "k_conv_bwd": 4 * P + 4 * npix, "k_raytrace_bwd": 4 * npix}
     roof, per_kernel, whole = build_roofline(ctx, sim, stage_ms, sum(stage_ms), flops, alg_bytes, "c4_kernels", ctx.fp32)
+    # The taped forward kernel carries the member loop of BOTH directions (forward-mode Jacobian), so SURVEY's per-kernel split
+    # (forward N x 2801, adjoint twice that) does not apply to it: its roofline is the EXECUTED flop rate (ncu op counts of the same
+    # kernel, profiles/r02_c4_ncu_summary.md); the nominal count is applied to the whole step (`whole_step`).
+    d = per_kernel.get(roof["kernel"], {})
+    for nm in ("k_raytrace_fwd", "k_raytrace_bwd"):
+        if nm in per_kernel:
+            per_kernel[nm]["fp32_TFLOPs_useful"] = per_kernel[nm]["fp32_frac_useful"] = None
+    if d.get("fp32_TFLOPs_executed"):
+        roof.update(achieved=d["fp32_TFLOPs_executed"], frac=d["fp32_frac_executed"],
+                    note="achieved = FP32 flops the kernel executes (ncu source-page op counts of the same kernel, scaled to this batch) / "
+                         "CUDA-event time inside bench.py; peak = FP32 FMA peak measured in this run.  Half of the kernel's FP32 instructions "
+                         "are FMUL2 / FADD2 (1 flop per lane-cycle) and the XU (MUFU) pipe is co-limiting (57 % busy, ncu): FMA pipe 76 % busy")
+    else:
+        roof.update(achieved=None, frac=None, note="no ncu op counts available (profiles/r02_traffic.json): see whole_step for the nominal rate")
     del sim
     torch.cuda.empty_cache()
     return {"workload": wl["name"] + " (BASELINE.json configs[3])", "batch_per_gpu": bs, "global_batch": bs * ctx.world, "steps": steps,

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(NTHR) k_probe(const float* __restrict__ gin, c
 }
 
 int main() {
-  const int reps = 64, grid = 148 * 4;
+  const int reps = 256, grid = 148 * 4;
   std::vector<float> hin(TILE), hw(8192);
   for (int i = 0; i < TILE; ++i) hin[i] = 0.001f * (i % 97);
   for (int i = 0; i < 8192; ++i) hw[i] = 0.01f * ((i * 7) % 13);
@@ -56,7 +56,7 @@ int main() {
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int mode = 0; mode < 2; ++mode) {
     float best = 1e30f;
-    for (int t = 0; t < 4; ++t) {
+    for (int t = 0; t < 8; ++t) {
       cudaEventRecord(e0);
       if (mode == 0) k_probe<0><<<grid, NTHR, smem>>>(din, dw, dout, reps, 0u); else k_probe<1><<<grid, NTHR, smem>>>(din, dw, dout, reps, 0u);
       cudaEventRecord(e1); cudaEventSynchronize(e1);
