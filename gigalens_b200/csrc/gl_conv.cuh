@@ -537,7 +537,7 @@ __global__ void __maxnreg__(96) k_conv_fwd_tma(const __grid_constant__ CUtensorM
 template <int A>
 __global__ void __launch_bounds__(256, 2) k_conv_bwd(GlConvGeom g, const float* __restrict__ gimg, const float* __restrict__ wts,
                                                   float scale, const unsigned char* __restrict__ ss_mask,
-                                                  float* __restrict__ gss) {
+                                                  float* __restrict__ gss, const int* __restrict__ img_list) {
   (void)ss_mask;
   extern __shared__ __align__(128) float glc_smem_b[];
   float* smem = glc_smem_b;
@@ -545,7 +545,12 @@ __global__ void __launch_bounds__(256, 2) k_conv_bwd(GlConvGeom g, const float* 
   float* s_in = smem;                                   // [in_rows][in_pitch]  zero-padded dL/d(image)
   float* s_w = smem + g.in_rows * g.in_pitch;           // [nph][A][2][ulen] packed (flipped) tap table
   const int ntiles = g.tiles_x * g.tiles_y;
-  const int b = blockIdx.x / ntiles, tile = blockIdx.x - b * ntiles;
+  int b = blockIdx.x / ntiles;
+  const int tile = blockIdx.x - b * ntiles;
+  if (img_list) {                                       // only the listed images: [0] = count, [1..] = image indices
+    if (b >= img_list[0]) return;
+    b = img_list[1 + b];
+  }
   const int r0 = g.rc0 + (tile / g.tiles_x) * g.th, c0 = g.rc0 + (tile % g.tiles_x) * g.tw;
   const int tid = threadIdx.x, nthr = blockDim.x;
 
@@ -610,7 +615,7 @@ __global__ void __launch_bounds__(256, 2) k_conv_bwd(GlConvGeom g, const float* 
 template <int A, int NFC = 0>
 __global__ void __launch_bounds__(256, 2) k_conv_bwd_tma(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
                                                        GlConvGeom g, const float* __restrict__ wts, float scale,
-                                                       const __grid_constant__ GlTapsC<NFC> ctaps) {
+                                                       const __grid_constant__ GlTapsC<NFC> ctaps, const int* __restrict__ img_list) {
   extern __shared__ __align__(128) float glc_smem_bt[];
   float* smem = glc_smem_bt;
   const int nph = g.ss * g.ss;
@@ -619,7 +624,12 @@ __global__ void __launch_bounds__(256, 2) k_conv_bwd_tma(const __grid_constant__
   float* s_w = s_out + g.out_stride;                    // [nph][A][2][ulen] packed (flipped) tap table
   __shared__ __align__(8) unsigned long long s_bar[1];
   const int ntiles = g.tiles_x * g.tiles_y;
-  const int b = blockIdx.x / ntiles, tile = blockIdx.x - b * ntiles;
+  int b = blockIdx.x / ntiles;
+  const int tile = blockIdx.x - b * ntiles;
+  if (img_list) {                                       // only the listed images: [0] = count, [1..] = image indices
+    if (b >= img_list[0]) return;
+    b = img_list[1 + b];
+  }
   const int r0 = g.rc0 + (tile / g.tiles_x) * g.th, c0 = g.rc0 + (tile % g.tiles_x) * g.tw;
   const int tid = threadIdx.x;
   constexpr int UTAB = A * 2 * glc_ulen(A);

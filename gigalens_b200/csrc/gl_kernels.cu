@@ -345,21 +345,23 @@ __global__ void __launch_bounds__(GLK_THREADS) k_nan_cotangent_mask(GlProgram P,
   }
 }
 
-// nan_mode (lstsq path, where the reference scrubs NaN per component, tf/simulator.py:200): 0 = every sample;
-// 1 = skip the samples whose forward pass scrubbed a component value (nan_count != 0); the SCRUB instance then runs
-// with nan_mode 2 = ONLY those samples, masking the cotangent per light profile.
+// Sample selection: a CTA works on sample b iff (nan_count[b] & sel_mask) == sel_want.  Forward-model path: 0, 0 = every sample
+// (nan_count is a count there).  lstsq path: nan_count[b] holds FLAGS -- bit 0: the forward pass scrubbed a NaN component value (the
+// reference scrubs per component, tf/simulator.py:200: such samples go to the SCRUB instance, which masks the cotangent per light
+// profile), bit 1: the sample's amplitudes come from the eigen-solve, which runs on a side stream while the other samples'' adjoint
+// proceeds (gl_lstsq_loglike_core).
 template <int PPT, unsigned F, bool SCRUB = false>
 __global__ void __launch_bounds__(GLK_THREADS) k_raytrace_bwd(GlProgram P, int npix, const float* __restrict__ grid_x,
                                                               const float* __restrict__ grid_y,
                                                               const unsigned char* __restrict__ ss_mask,
                                                               const float* __restrict__ derived, int no_deflection,
                                                               const float* __restrict__ gss, float* __restrict__ gpart,
-                                                              const int* __restrict__ nan_count, int nan_mode) {
+                                                              const int* __restrict__ nan_count, int sel_mask, int sel_want) {
   extern __shared__ __align__(16) float smem[];
   float* s_der = smem;                               // [der_total]
   float* s_acc = smem + P.der_total;                 // [nwarps][g_total]
   const int b = blockIdx.y;
-  if (nan_mode && ((nan_count[b] != 0) != (nan_mode == 2))) return;
+  if (sel_mask && (nan_count[b] & sel_mask) != sel_want) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = GLK_THREADS / 32;
   const float* dsrc = derived + (size_t)b * P.der_total;
   for (int i = threadIdx.x; i < P.der_total; i += blockDim.x) s_der[i] = dsrc[i];
@@ -479,13 +481,13 @@ __global__ void __launch_bounds__(GLK_THREADS, 2) k_raytrace_bwd_p(GlProgram P, 
                                                                 const unsigned char* __restrict__ ss_mask,
                                                                 const float* __restrict__ derived, int no_deflection,
                                                                 const float* __restrict__ gss, float* __restrict__ gpart,
-                                                                const int* __restrict__ nan_count, int nan_mode,
+                                                                const int* __restrict__ nan_count, int sel_mask, int sel_want,
                                                                 const float* __restrict__ tape) {
   extern __shared__ __align__(16) float smem[];
   float* s_der = smem;
   float* s_acc = smem + P.der_total;   // ROWS: staging tiles [nwarps][g_total][33], else accumulator rows [nwarps][g_total]
   const int b = blockIdx.y;
-  if (nan_mode && nan_count[b] != 0) return;   // lstsq path: left to the per-component SCRUB instance of k_raytrace_bwd
+  if (sel_mask && (nan_count[b] & sel_mask) != sel_want) return;   // lstsq path: sample selection (see k_raytrace_bwd)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = GLK_THREADS / 32;
   const float* dsrc = derived + (size_t)b * P.der_total;
   for (int i = threadIdx.x; i < P.der_total; i += blockDim.x) s_der[i] = dsrc[i];
@@ -728,6 +730,13 @@ struct gl_plan {
                                                        // the SM slots the other slot's convolution frees, instead of queueing behind it)
   cudaEvent_t lq_fork = nullptr, lq_done[2] = {nullptr, nullptr}, lq_conv[2] = {nullptr, nullptr};
   int lq_pipeline = 1;       // 0 = all chunks on the caller's stream (A/B)
+  // Gradient path, single chunk: the eigen-solve of the few samples with a singular Gram matrix (one sequential ~2 ms Jacobi each) runs
+  // on lq_tail_stream while the caller's stream takes the other samples through image / adjoint conv / ray-tracing adjoint; the late
+  // samples follow in a second, short pass (gl_lstsq_loglike_core).  lq_tail_pending: the caller's stream still has to wait for lq_tail_done.
+  cudaStream_t lq_tail_stream = nullptr;
+  cudaEvent_t lq_tail_fork = nullptr, lq_tail_done = nullptr;
+  int lq_hide_tail = 1;      // 0 = eigen-solve in line (A/B)
+  bool lq_tail_pending = false;
   float* d_ll = nullptr;
 };
 
@@ -755,6 +764,9 @@ static void gl_free_plan(gl_plan* p) {
     if (p->lq_conv[k]) cudaEventDestroy(p->lq_conv[k]);
   }
   if (p->lq_fork) cudaEventDestroy(p->lq_fork);
+  if (p->lq_tail_stream) cudaStreamDestroy(p->lq_tail_stream);
+  if (p->lq_tail_fork) cudaEventDestroy(p->lq_tail_fork);
+  if (p->lq_tail_done) cudaEventDestroy(p->lq_tail_done);
   for (void* q : {(void*)p->d_pos_off, (void*)p->d_pos_x, (void*)p->d_pos_y, (void*)p->d_pos_ex, (void*)p->d_pos_ey, (void*)p->d_pos_ll,
                   (void*)p->d_pos_chi, (void*)p->d_pos_grad}) if (q) cudaFree(q);
   for (cudaEvent_t e : p->tm_ev) cudaEventDestroy(e);
@@ -1107,6 +1119,7 @@ int gl_plan_set_option(gl_plan* p, const char* name, int32_t value) {
   if (!strcmp(name, "conv_const_taps")) { p->conv_const = value; return 0; }
   if (!strcmp(name, "tape")) { p->use_tape = value; return 0; }
   if (!strcmp(name, "lstsq_pipeline")) { p->lq_pipeline = value; return 0; }
+  if (!strcmp(name, "lstsq_hide_tail")) { p->lq_hide_tail = value; return 0; }
   if (!strcmp(name, "straight_line")) { p->straight_line = value; return 0; }
   if (!strcmp(name, "epl_tol_exp10")) {   // EPL series terms below 10^-value are dropped (12 = the reference's constant, epl.py:37)
     if (value < 6 || value > 30) return gl_fail("gl_plan_set_option: epl_tol_exp10 must be in [6, 30]");
@@ -1292,15 +1305,18 @@ static int gl_run_raytrace_fwd(gl_plan* p, float* ss_out, int no_deflection, cud
   return 0;
 }
 
-// per_component (lstsq path): the reference scrubs NaN per component there (tf/simulator.py:200), so the samples whose
-// forward pass scrubbed anything are left out of the main kernel (nan_mode 1) and handled by the SCRUB instance.
-static int gl_run_raytrace_bwd(gl_plan* p, float* gss, int no_deflection, cudaStream_t st, bool per_component = false) {
+// mode 0: forward-model path (every sample; NaN-scrubbed pixels handled by k_nan_cotangent_mask).  lstsq path (flags in d_nan, see
+// k_raytrace_bwd): mode 1 = every sample, 2 = the samples solved by the Cholesky path, 3 = the samples solved by the eigen-solve;
+// in each the samples with scrubbed components go to the SCRUB instance.
+static int gl_run_raytrace_bwd(gl_plan* p, float* gss, int no_deflection, cudaStream_t st, int mode = 0) {
   dim3 grid(p->chunks, p->bs);
-  const int nan_mode = per_component ? 1 : 0;
+  const bool per_component = mode != 0;
+  const int sel_mask = mode == 0 ? 0 : (mode == 1 ? 1 : 3);
+  const int sel_want = mode == 3 ? 2 : 0;              // main kernel: no NaN flag (and the wanted eigen-solve flag)
   if (per_component) {
     const size_t smem_s = (size_t)gl_bwd_smem_floats(p->prog, 4) * sizeof(float);
     k_raytrace_bwd<4, GL_FS3, true><<<grid, GLK_THREADS, smem_s, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask, p->d_derived,
-                                                                       no_deflection, gss, p->d_gpart, p->d_nan, 2);
+                                                                       no_deflection, gss, p->d_gpart, p->d_nan, sel_mask, sel_want | 1);
     GL_LAUNCH_CHECK("k_raytrace_bwd<scrub>");
   } else {   // NaN-scrubbed pixels pass no gradient: exits immediately for samples without any (nan_count from the forward pass)
     const size_t smem_m = (size_t)p->prog.der_total * sizeof(float);
@@ -1321,21 +1337,21 @@ static int gl_run_raytrace_bwd(gl_plan* p, float* gss, int no_deflection, cudaSt
       const size_t smem_tn = (size_t)gl_bwd_p_smem_floats(p->prog, 4, false, true) * sizeof(float);
       if (p->row_flush && smem_t <= 108 * 1024 && p->prog.g_total <= 64)
         k_raytrace_bwd_p<4, GL_FS2, true, false, true><<<grid, GLK_THREADS, smem_t, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,
-                                                                                       p->d_derived, 0, gss, p->d_gpart, p->d_nan, 0, p->d_tape);
+                                                                                       p->d_derived, 0, gss, p->d_gpart, p->d_nan, 0, 0, p->d_tape);
       else
         k_raytrace_bwd_p<4, GL_FS2, false, false, true><<<grid, GLK_THREADS, smem_tn, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,
-                                                                                        p->d_derived, 0, gss, p->d_gpart, p->d_nan, 0, p->d_tape);
+                                                                                        p->d_derived, 0, gss, p->d_gpart, p->d_nan, 0, 0, p->d_tape);
       GL_LAUNCH_CHECK("k_raytrace_bwd_p<tape>");
       return 0;
     }
 #define GL_BWD_P(FS, ROWS, SM)                                                                                              \
     {                                                                                                                       \
       k_raytrace_bwd_p<4, FS, ROWS><<<grid, GLK_THREADS, (SM), st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,        \
-                                                                   p->d_derived, no_deflection, gss, p->d_gpart, p->d_nan, nan_mode, nullptr); \
+                                                                   p->d_derived, no_deflection, gss, p->d_gpart, p->d_nan, sel_mask, sel_want, nullptr); \
     }
     if (p->feat_idx == 0 && rows && p->straight_line && !no_deflection && gl_is_benchmark_shape(p->prog)) {
       k_raytrace_bwd_p<4, GL_FS0, true, true><<<grid, GLK_THREADS, smem_rows, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask,
-                                                                                  p->d_derived, no_deflection, gss, p->d_gpart, p->d_nan, nan_mode, nullptr);
+                                                                                  p->d_derived, no_deflection, gss, p->d_gpart, p->d_nan, sel_mask, sel_want, nullptr);
     } else
     if (p->feat_idx == 0) { if (rows) GL_BWD_P(GL_FS0, true, smem_rows) else GL_BWD_P(GL_FS0, false, smem) }
     else { if (rows) GL_BWD_P(GL_FS2, true, smem_rows) else GL_BWD_P(GL_FS2, false, smem) }
@@ -1345,7 +1361,7 @@ static int gl_run_raytrace_bwd(gl_plan* p, float* gss, int no_deflection, cudaSt
   }
   GL_FEAT_DISPATCH(p->feat_idx, {
     k_raytrace_bwd<4, F><<<grid, GLK_THREADS, smem, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_ss_mask, p->d_derived,
-                                                          no_deflection, gss, p->d_gpart, p->d_nan, nan_mode);
+                                                          no_deflection, gss, p->d_gpart, p->d_nan, sel_mask, sel_want);
   })
   GL_LAUNCH_CHECK("k_raytrace_bwd");
   return 0;
@@ -1418,7 +1434,7 @@ static int gl_launch_conv_fwd_A(gl_plan* p, const float* ss, float scale, float*
   return 0;
 }
 template <int A>
-static int gl_launch_conv_bwd_A(gl_plan* p, const float* gimg, float scale, float* gss, cudaStream_t st, int nimg) {
+static int gl_launch_conv_bwd_A(gl_plan* p, const float* gimg, float scale, float* gss, cudaStream_t st, int nimg, const int* img_list) {
   dim3 grid((unsigned)(p->gb.tiles_x * p->gb.tiles_y) * (unsigned)nimg);
   const int nph = p->ss * p->ss;
   if (p->conv_tma && p->conv_tma_b_ok && ((A - 1) & 1) == 0 && ((uintptr_t)gimg % 16) == 0 && ((uintptr_t)gss % 16) == 0) {
@@ -1430,17 +1446,17 @@ static int gl_launch_conv_bwd_A(gl_plan* p, const float* gimg, float scale, floa
     if (p->tmap_b_ok) {
       if constexpr (A == GLC_A_HOT) {
         if (p->conv_const && p->conv_const_ok) {
-          k_conv_bwd_tma<A, GLC_NF_HOT><<<grid, p->conv_threads_b, p->smem_cb_tma_c, st>>>(p->tmap_bi, p->tmap_bo, p->gb, p->d_wb, scale, p->ct_b);
+          k_conv_bwd_tma<A, GLC_NF_HOT><<<grid, p->conv_threads_b, p->smem_cb_tma_c, st>>>(p->tmap_bi, p->tmap_bo, p->gb, p->d_wb, scale, p->ct_b, img_list);
           GL_LAUNCH_CHECK("k_conv_bwd_tma<const taps>");
           return 0;
         }
       }
-      k_conv_bwd_tma<A><<<grid, p->conv_threads_b, p->smem_cb_tma, st>>>(p->tmap_bi, p->tmap_bo, p->gb, p->d_wb, scale, GlTapsC<0>{});
+      k_conv_bwd_tma<A><<<grid, p->conv_threads_b, p->smem_cb_tma, st>>>(p->tmap_bi, p->tmap_bo, p->gb, p->d_wb, scale, GlTapsC<0>{}, img_list);
       GL_LAUNCH_CHECK("k_conv_bwd_tma");
       return 0;
     }
   }
-  k_conv_bwd<A><<<grid, p->conv_threads_b, p->smem_cb, st>>>(p->gb, gimg, p->d_wb, scale, nullptr, gss);
+  k_conv_bwd<A><<<grid, p->conv_threads_b, p->smem_cb, st>>>(p->gb, gimg, p->d_wb, scale, nullptr, gss, img_list);
   GL_LAUNCH_CHECK("k_conv_bwd");
   return 0;
 }
@@ -1458,9 +1474,12 @@ static int gl_run_conv_fwd(gl_plan* p, const float* ss, float scale, float* img,
   if (nimg < 0) nimg = p->bs;
   GL_CONV_DISPATCH(gl_launch_conv_fwd_A, p, ss, scale, img, like, gimg, st, nimg);
 }
-static int gl_run_conv_bwd(gl_plan* p, const float* gimg, float scale, float* gss, cudaStream_t st, int nimg = -1) {
+// img_list (device, optional): [0] = count, [1..] = the images to process -- the launch still covers nimg images, CTAs beyond
+// the count exit at once (the count is only known on the device)
+static int gl_run_conv_bwd(gl_plan* p, const float* gimg, float scale, float* gss, cudaStream_t st, int nimg = -1,
+                           const int* img_list = nullptr) {
   if (nimg < 0) nimg = p->bs;
-  GL_CONV_DISPATCH(gl_launch_conv_bwd_A, p, gimg, scale, gss, st, nimg);
+  GL_CONV_DISPATCH(gl_launch_conv_bwd_A, p, gimg, scale, gss, st, nimg, img_list);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1712,6 +1731,13 @@ static int gl_lstsq_reserve(gl_plan* p, int chunk) {
     }
     if (!p->lq_fork) GL_CUDA(cudaEventCreateWithFlags(&p->lq_fork, cudaEventDisableTiming));
   }
+  if (!p->lq_tail_stream) {
+    int prio_lo = 0, prio_hi = 0;
+    GL_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    GL_CUDA(cudaStreamCreateWithPriority(&p->lq_tail_stream, cudaStreamNonBlocking, prio_hi));
+    GL_CUDA(cudaEventCreateWithFlags(&p->lq_tail_fork, cudaEventDisableTiming));
+    GL_CUDA(cudaEventCreateWithFlags(&p->lq_tail_done, cudaEventDisableTiming));
+  }
   return 0;
 }
 static int gl_lstsq_alloc(gl_plan* p) {
@@ -1777,14 +1803,39 @@ static int gl_lstsq_forward(gl_plan* p, const float* params, float* image, float
         GL_LAUNCH_CHECK("k_gram");
       }
       GL_CUDA(cudaMemsetAsync(queue, 0, sizeof(int), ts));   // [0] = count, [1..] = sample indices
-      k_pinv_solve<<<nb, 128, smem_solve, ts>>>(D, gram, 1e-6, 16, p->d_coef + (size_t)b0 * D, 0, queue + 1, queue);
+      float* coef = p->d_coef + (size_t)b0 * D;
+      float* im = image ? image + (size_t)b0 * npx : nullptr;
+      float* llp = loglike ? loglike + b0 : nullptr;
+      float* chip = red_chi2 ? red_chi2 + b0 : nullptr;
+      float* gim = want_gimg ? p->d_gimg + (size_t)b0 * npx : nullptr;
+      const size_t smem_img = (size_t)D * sizeof(float);
+      // Gradient requested, one chunk: the eigen-solve leaves the caller's stream.  Phase 0 flags the samples it queues (bit 1 of
+      // d_nan); the tail stream -- highest priority, and its kernels become ready first, so its few CTAs are resident before the
+      // caller's stream fills the SMs -- runs the eigen-solve, the image / likelihood and the amplitude patch of the queued samples,
+      // while the caller's stream goes on with everything else for the other samples.
+      const bool hide = want_gimg && !pipe && nb == p->bs && p->lq_hide_tail && p->lq_tail_stream != nullptr;
+      k_pinv_solve<<<nb, 128, smem_solve, ts>>>(D, gram, 1e-6, 16, coef, 0, queue + 1, queue, hide ? p->d_nan + b0 : nullptr);
       GL_LAUNCH_CHECK("k_pinv_solve");
-      k_pinv_solve<<<nb, 512, smem_solve, ts>>>(D, gram, 1e-6, 16, p->d_coef + (size_t)b0 * D, 1, queue + 1, queue);
-      GL_LAUNCH_CHECK("k_pinv_solve");
-      k_lstsq_image<<<nb, GLL_THREADS, (size_t)D * sizeof(float), ts>>>(
-          D, npx, Rbuf, p->d_coef + (size_t)b0 * D, p->d_obs, p->d_err, image ? image + (size_t)b0 * npx : nullptr,
-          loglike ? loglike + b0 : nullptr, red_chi2 ? red_chi2 + b0 : nullptr, want_gimg ? p->d_gimg + (size_t)b0 * npx : nullptr);
-      GL_LAUNCH_CHECK("k_lstsq_image");
+      if (hide) {
+        cudaStream_t tl = p->lq_tail_stream;
+        GL_CUDA(cudaEventRecord(p->lq_tail_fork, ts));
+        GL_CUDA(cudaStreamWaitEvent(tl, p->lq_tail_fork, 0));
+        k_pinv_solve<<<nb, 512, smem_solve, tl>>>(D, gram, 1e-6, 16, coef, 1, queue + 1, queue, nullptr);
+        GL_LAUNCH_CHECK("k_pinv_solve");
+        k_lstsq_image<<<nb, GLL_THREADS, smem_img, tl>>>(D, npx, Rbuf, coef, p->d_obs, p->d_err, im, llp, chip, gim, nullptr, queue);
+        GL_LAUNCH_CHECK("k_lstsq_image");
+        k_patch_amps<<<(nb + 31) / 32, 32, 0, tl>>>(p->prog, nb, coef, p->d_derived, nullptr, queue);
+        GL_LAUNCH_CHECK("k_patch_amps");
+        GL_CUDA(cudaEventRecord(p->lq_tail_done, tl));
+        p->lq_tail_pending = true;
+        k_lstsq_image<<<nb, GLL_THREADS, smem_img, ts>>>(D, npx, Rbuf, coef, p->d_obs, p->d_err, im, llp, chip, gim, p->d_nan + b0, nullptr);
+        GL_LAUNCH_CHECK("k_lstsq_image");
+      } else {
+        k_pinv_solve<<<nb, 512, smem_solve, ts>>>(D, gram, 1e-6, 16, coef, 1, queue + 1, queue, nullptr);
+        GL_LAUNCH_CHECK("k_pinv_solve");
+        k_lstsq_image<<<nb, GLL_THREADS, smem_img, ts>>>(D, npx, Rbuf, coef, p->d_obs, p->d_err, im, llp, chip, gim, nullptr, nullptr);
+        GL_LAUNCH_CHECK("k_lstsq_image");
+      }
     }
     if (pipe) GL_CUDA(cudaEventRecord(p->lq_done[slot], ts));
   }
@@ -1805,10 +1856,19 @@ static int gl_lstsq_loglike_core(gl_plan* p, const float* params, float* loglike
   if (gl_lstsq_forward(p, params, nullptr, nullptr, ll, chi, grad, st)) return 1;
   const int tb = 32, gb = (p->bs + tb - 1) / tb;   // one warp per CTA: a batch of a few thousand samples spreads over all SMs
   if (grad) {
-    k_patch_amps<<<gb, tb, 0, st>>>(p->prog, p->bs, p->d_coef, p->d_derived);
+    const bool late = p->lq_tail_pending;   // set by gl_lstsq_forward: some samples' amplitudes come from the tail stream
+    p->lq_tail_pending = false;
+    k_patch_amps<<<gb, tb, 0, st>>>(p->prog, p->bs, p->d_coef, p->d_derived, late ? p->d_nan : nullptr, nullptr);
     GL_LAUNCH_CHECK("k_patch_amps");
-    if (gl_run_conv_bwd(p, p->d_gimg, 1.f, p->d_ss, st)) return 1;
-    if (gl_run_raytrace_bwd(p, p->d_ss, p->no_deflection, st, true)) return 1;
+    if (gl_run_conv_bwd(p, p->d_gimg, 1.f, p->d_ss, st)) return 1;   // (late samples: stale dL/dimage in, overwritten below)
+    if (gl_run_raytrace_bwd(p, p->d_ss, p->no_deflection, st, late ? 2 : 1)) return 1;
+    if (late) {
+      // second pass for the late samples only: their image, likelihood, dL/dimage and patched amplitudes are complete once the
+      // tail stream is done (normally long before: ~2 ms of eigen-solve against ~4 ms of adjoint work on this stream)
+      GL_CUDA(cudaStreamWaitEvent(st, p->lq_tail_done, 0));
+      if (gl_run_conv_bwd(p, p->d_gimg, 1.f, p->d_ss, st, -1, p->d_solve_queue)) return 1;
+      if (gl_run_raytrace_bwd(p, p->d_ss, p->no_deflection, st, 3)) return 1;
+    }
   }
   k_sample_bwd<<<gb, tb, 0, st>>>(p->prog, p->bs, params, p->d_member_factor, p->d_amp_slot, p->d_derived, p->d_gpart, p->chunks,
                                   p->d_gsum, nullptr, 0, 1.f, ll, chi, dparams, p->d, p->d_leaves, z,

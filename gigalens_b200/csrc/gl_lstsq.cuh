@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(GLL_THREADS) k_raytrace_comps(GlProgram P, int
       if (pix[j] >= npix) continue;
       const bool keep = !ss_mask || ss_mask[pix[j]];
       const int n_nan = gl_point_components<float, F>(P, s_der, x[j], y[j], bx[j], by[j], dst + pix[j], npix, keep);
-      if (n_nan && nan_count) atomicAdd(nan_count + b, n_nan);   // the adjoint treats this sample per component (SCRUB)
+      if (n_nan && nan_count) atomicOr(nan_count + b, 1);   // flag bit 0: the adjoint treats this sample per component (SCRUB)
     }
   }
 }
@@ -129,13 +129,14 @@ __global__ void __launch_bounds__(GLL_THREADS) k_gram(int D, int npx, const floa
 // then V diag(1/lambda_i > cut) V^T h.
 // tf.linalg.pinv keeps singular values > rcond * max (src/gigalens/tf/simulator.py:235).
 //   grid = bs, block = 128, smem = 2*D*D doubles + small
+// `flags` (phase 0, optional): bit 1 of flags[b] is set for the samples left to phase 1.
 // Two launches per chunk: phase 0 (128 threads per sample) runs the Cholesky fast path and appends the samples whose
 // certificate fails to `queue`; phase 1 (512 threads per sample, grid = chunk, CTAs beyond *count exit at once) runs
 // the eigen-solve for those only.  In the C3 prior ~0.6 % of the draws have a genuinely singular Gram matrix (cond
 // ~5e8); in a single launch those few CTAs ran ~10x longer than the rest and the tail was 90 % of the kernel time.
 __global__ void __launch_bounds__(512) k_pinv_solve(int D, const float* __restrict__ gram, double rcond, int max_sweeps,
                                                     float* __restrict__ coeffs, int phase, int* __restrict__ queue,
-                                                    int* __restrict__ count) {
+                                                    int* __restrict__ count, int* __restrict__ flags) {
   extern __shared__ __align__(16) double s_d[];
   const int LD = D | 1;            // odd leading dimension: column walks (stride LD doubles) hit distinct banks
   double* A = s_d;                 // [D][LD]
@@ -232,7 +233,10 @@ __global__ void __launch_bounds__(512) k_pinv_solve(int D, const float* __restri
       }
       return;
     }
-    if (tid == 0) queue[atomicAdd(count, 1)] = b;   // leave it to the phase-1 launch
+    if (tid == 0) {
+      queue[atomicAdd(count, 1)] = b;   // leave it to the phase-1 launch
+      if (flags) atomicOr(flags + b, 2);   // flag bit 1: amplitudes arrive late (the eigen-solve runs on a side stream, gl_lstsq_forward)
+    }
     return;
   }
   // ---- general path: symmetric Jacobi eigen-decomposition, pinv with the rcond cut
@@ -342,10 +346,16 @@ __global__ void __launch_bounds__(GLL_THREADS) k_lstsq_image(int D, int npx, con
                                                              const float* __restrict__ coeffs, const float* __restrict__ obs,
                                                              const float* __restrict__ err, float* __restrict__ image,
                                                              float* __restrict__ loglike, float* __restrict__ red_chi2,
-                                                             float* __restrict__ gimg) {
+                                                             float* __restrict__ gimg, const int* __restrict__ flags,
+                                                             const int* __restrict__ list) {
   extern __shared__ float s_c[];   // [D]
   __shared__ float s_red[2][GLL_THREADS / 32];
-  const int b = blockIdx.x, tid = threadIdx.x;
+  // sample selection (gradient path with the eigen-solve on a side stream): `list` = only the listed samples ([0] = count,
+  // [1..] = indices; CTAs beyond the count exit), else `flags` = skip the samples whose amplitudes arrive late (bit 1)
+  int b = blockIdx.x;
+  if (list) { if (b >= list[0]) return; b = list[1 + b]; }
+  else if (flags && (flags[b] & 2)) return;
+  const int tid = threadIdx.x;
   for (int c = tid; c < D; c += blockDim.x) s_c[c] = coeffs[(size_t)b * D + c];
   __syncthreads();
   const float* Rb = R + (size_t)b * D * npx;
@@ -413,9 +423,13 @@ __global__ void __launch_bounds__(GLL_THREADS) k_lstsq_image(int D, int npx, con
 
 // write the solved amplitudes into the derived blocks (Sersic Ie, Shapelets amplitudes) so that the
 // ordinary adjoint kernels differentiate the combined image with the amplitudes frozen.
-__global__ void k_patch_amps(GlProgram P, int bs, const float* __restrict__ coeffs, float* __restrict__ derived) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+// Sample selection as in k_lstsq_image.
+__global__ void k_patch_amps(GlProgram P, int bs, const float* __restrict__ coeffs, float* __restrict__ derived,
+                             const int* __restrict__ flags, const int* __restrict__ list) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= bs) return;
+  if (list) { if (b >= list[0]) return; b = list[1 + b]; }
+  else if (flags && (flags[b] & 2)) return;
   float* der = derived + (size_t)b * P.der_total;
   const float* c = coeffs + (size_t)b * P.depth;
   for (int i = P.n_lens; i < P.n_prof; ++i) {

@@ -318,6 +318,42 @@ def test_lstsq_two_slot_pipeline_matches_single_pass():
             assert np.array_equal(a, b)
 
 
+def test_lstsq_eigen_solve_on_the_tail_stream_matches_in_line():
+    """Gradient path: the eigen-solve of the samples with a singular Gram matrix runs on a side stream while the caller's stream
+    takes the other samples through the adjoint; the late samples follow in a second pass (`lstsq_hide_tail`, default on).
+    Bit-identical to the in-line order -- on a prior batch that has such samples (4 of the first 256 draws of seed 0 fail the
+    Cholesky certificate) and on a model whose every sample is singular (twin components)."""
+    bs = 256
+    wl = workloads.c3_workload(n_max=10, observed=workloads.c3_observation(n_max=10))
+    pmod = BackwardProbModel(wl["prior"], wl["observed"], wl["background_rms"], wl["exp_time"])
+    z = torch.as_tensor(pmod.bij_inverse(wl["prior"].sample(bs, seed=0)), device="cuda")
+    outs = []
+    for hide in (1, 0):
+        sim = LensSimulator(wl["phys_model"], wl["sim_config"], bs=bs)
+        sim.set_option("lstsq_hide_tail", hide)
+        outs.append([t.cpu().numpy() for t in pmod.log_prob_and_grad(sim, z)])
+        outs.append([t.cpu().numpy() for t in pmod.log_prob_and_grad(sim, z)])     # and again on the same plan (flags are per call)
+    assert np.isfinite(outs[0][0]).all() and np.isfinite(outs[0][2]).all()
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert np.array_equal(a, b)
+    # every sample late
+    fixed = dict(R_sersic=0.9, n_sersic=3.0, e1=0.05, e2=-0.1, center_x=0.02, center_y=-0.03)
+    wl3 = workloads.c3_workload(n_max=3)
+    pm = PhysicalModel(wl3["phys_model"].lenses, [sersic.SersicEllipse(use_lstsq=True), sersic.SersicEllipse(use_lstsq=True)],
+                       wl3["phys_model"].source_light, lens_light_constants=[dict(fixed), dict(fixed)])
+    pmod3 = BackwardProbModel(wl3["prior"], wl3["observed"], wl3["background_rms"], wl3["exp_time"])
+    z3 = torch.as_tensor(pmod3.bij_inverse(wl3["prior"].sample(5, seed=4)), device="cuda")
+    outs = []
+    for hide in (1, 0):
+        sim = LensSimulator(pm, wl3["sim_config"], bs=5)
+        sim.set_option("lstsq_hide_tail", hide)
+        outs.append([t.cpu().numpy() for t in pmod3.log_prob_and_grad(sim, z3)])
+    assert np.isfinite(outs[0][0]).all() and np.isfinite(outs[0][2]).all()
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+
+
 def test_lstsq_rank_deficient_uses_pinv_cut():
     """Two identical linear components make X^T X singular: the rcond = 1e-6 cut of tf.linalg.pinv is
     active and the minimum-norm amplitudes split evenly between the twins (general Jacobi path)."""
