@@ -68,14 +68,25 @@ GL_HD double gl_fma(double a, double b, double c) { return a * b + c; }   // hos
 // |y| <= 1, Sersic 1/n and EPL gamma-2), so the result error stays at the 1e-7 level of powf/expf
 // themselves; GPU parity tests hold 1e-5 with them.  The fp64 / host instantiation is exact.
 #if defined(__CUDA_ARCH__)
+#if defined(GL_ACCURATE_LOGEXP)   // experiment switch (scripts/dz_outliers.py): full-precision libm instead of the MUFU approximations
+GL_HD float gl_log2_fast(float x) { return log2f(x); }
+GL_HD float gl_exp2_fast(float x) { return exp2f(x); }
+#else
 GL_HD float gl_log2_fast(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 GL_HD float gl_exp2_fast(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#endif
 // rcp / rsqrt as the bare MUFU op (.ftz): rsqrtf() and __fdividef() wrap it in range tests and rescaling
 // multiplies for denormal or huge operands (1 FSETP + 2 FMUL per call -- a fifth of the dPIE member loop),
 // which the operands here (squared radii and norms on the arcsecond scale) never are.
+#if defined(GL_ACCURATE_RCP)      // experiment switch: IEEE division / square root instead of the MUFU approximations
+GL_HD float gl_rcp_fast(float x) { return __fdiv_rn(1.0f, x); }
+GL_HD float gl_div_fast(float a, float b) { return __fdiv_rn(a, b); }
+GL_HD float gl_rsqrt_fast(float x) { return __fdiv_rn(1.0f, __fsqrt_rn(x)); }
+#else
 GL_HD float gl_rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 GL_HD float gl_div_fast(float a, float b) { return a * gl_rcp_fast(b); }
 GL_HD float gl_rsqrt_fast(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#endif
 #else
 GL_HD float gl_log2_fast(float x) { return log2f(x); }
 GL_HD float gl_exp2_fast(float x) { return exp2f(x); }

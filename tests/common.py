@@ -184,7 +184,9 @@ def assert_parity(cuda, o32, o64, tol, what, o64_perturbed=None, factor=4.0, axi
     `tol` for that input (cuspy Sersic cores under the lens mapping, NFW at X ~ 1, the dPIE log
     ratio): there the bound is `factor` x the fp32 noise floor of the case, measured as the larger of
     (i) the fp32 oracle's own error against the fp64 oracle and (ii) the change of the fp64 oracle
-    when its inputs move by half an fp32 ulp.  The median slice must hold `tol` outright.
+    when its inputs move by half an fp32 ulp (`o64_perturbed`: one result or a list -- e.g. also the fp64 oracle with
+    the ray positions beta moved by one fp32 rounding per pixel, oracle_bridge.logprob_and_grad(beta_noise=...)).
+    The median slice must hold `tol` outright.
 
     Every call is recorded in PARITY_LOG (how many slices needed the noise-floor rule and how far above `tol`
     they landed), so a green run says how much of it was green outright: `profiles/r02_parity.json`."""
@@ -193,8 +195,9 @@ def assert_parity(cuda, o32, o64, tol, what, o64_perturbed=None, factor=4.0, axi
     scale = red(np.abs(o64))
     e_c = np.atleast_1d(red(np.abs(cuda - o64)) / scale)
     floor = np.atleast_1d(red(np.abs(o32 - o64)) / scale)
-    if o64_perturbed is not None:
-        floor = np.maximum(floor, np.atleast_1d(red(np.abs(np.asarray(o64_perturbed, dtype=np.float64) - o64)) / scale))
+    if o64_perturbed is not None:   # one perturbed result, or a list of them (the floor is the largest change)
+        for pert in (o64_perturbed if isinstance(o64_perturbed, (list, tuple)) else [o64_perturbed]):
+            floor = np.maximum(floor, np.atleast_1d(red(np.abs(np.asarray(pert, dtype=np.float64) - o64)) / scale))
     over = e_c > tol                                   # slices that needed the noise-floor rule
     bad = e_c > np.maximum(tol, factor * floor)
     with np.errstate(divide="ignore", invalid="ignore"):
