@@ -4,7 +4,7 @@
 //   gram[b] = A A^T,  A = [X Y]^T  ((D+1) x P, row c = channel c of R[b] times W, last row = obs * W)
 //   (tf/simulator.py:232-235: X^T X and X^T Y in one product.)
 //
-// One CTA (4 warps) per sample.  A is K-major in HBM already (every channel image is contiguous in the
+// One CTA per sample (or per half sample): four converter warps and one MMA-issuer warp (below).  A is K-major in HBM already (every channel image is contiguous in the
 // pixel index), so the same shared-memory tile serves as both MMA operands: D[128 x N] += A_tile[128 x 8] *
 // A_tile[N x 8]^T with M = 128 (rows >= D+1 are zero), N = D+1 rounded up to 16, kind::tf32, fp32
 // accumulators in TMEM.  TF32 keeps 11 significand bits, far short of the 1e-5 parity bound after the
@@ -15,18 +15,64 @@
 // matrices; here a K-chunk (4 pixels = 16 bytes) of all 128 rows forms one 2 KB panel, so
 // LBO (next 16 bytes in K) = 2048 B and SBO (next 8 rows) = 128 B.  Loads are float4 per (row, chunk) with
 // each quarter-warp writing 8 consecutive rows of one panel (conflict-free 16-byte stores) and each warp
-// reading 64 contiguous bytes of 8 channel rows (full sectors).  Two stages: the CUDA cores convert /
-// split stage s+1 while the tensor core consumes stage s; tcgen05.commit -> mbarrier frees a stage.
+// reading 64 contiguous bytes of 8 channel rows (full sectors).
+//
+// Pipeline (round 2).  The first version fetched one stage ahead into registers, had all four warps meet at a CTA barrier per
+// stage and wait while thread 0 issued the MMAs: 4300 cycles per 32-pixel stage, 22 % of the stall samples on that barrier, the
+// tensor pipe 22 % busy; a fifth, MMA-only warp cost the second CTA per SM (five warps of 184 registers do not pack two CTAs into
+// the four register files) and exposed the real limiter: too few bytes in flight (first use of the fetched values = 22 % of the
+// stall samples).  Now:
+//   * raw values travel through a per-thread cp.async ring in shared memory, GTC_DEPTH - 1 = 3 stages (30 KB per CTA) ahead;
+//     every thread reads back exactly the slots it filled, so the ring needs no barrier and no registers;
+//   * hand-offs are mbarriers, never a CTA barrier:
+//       full[s]      warps -> issuer        stage s holds its operands (one arrival per warp, after fence.proxy.async)
+//       free[s]      tcgen05.commit -> warps   the MMAs that read stage s have retired
+//       acc_done[a]  tcgen05.commit -> warps   accumulator a holds a finished 64-pixel segment
+//       acc_free[a]  warps -> issuer        accumulator a has been drained into registers and may be overwritten
+//     the issuer is lane 0 of warp 0; the other warps run ahead of it (up to the stage ring) instead of waiting for it.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#define GTC_THREADS 128
+// timing experiments of the stand-alone probe (tests/cuda/gram_tc_check.cu time): -DGTC_EXP_NMMA=1|2 issues fewer MMAs per slice
+#ifndef GTC_EXP_NMMA
+#define GTC_EXP_NMMA 3
+#endif
+#if GTC_EXP_NMMA >= 2
+#define GTC_EXP_MMA2(x) x
+#else
+#define GTC_EXP_MMA2(x)
+#endif
+#if GTC_EXP_NMMA >= 3
+#define GTC_EXP_MMA3(x) x
+#else
+#define GTC_EXP_MMA3(x)
+#endif
+#ifndef GTC_EXP_SKIP                               // bit mask: 1 no operand loads, 2 no split arithmetic, 4 no accumulator drain, 8 no proxy fence, 32 no operand stores
+#define GTC_EXP_SKIP 0
+#endif
+#ifndef GTC_ISSUER
+#define GTC_ISSUER 1                               // 1: a fifth warp issues the MMAs; 0: lane 0 of warp 0 does, between its conversions
+#endif
+#define GTC_CONV 128                               // converter / drain threads: warp w owns TMEM lanes 32w..32w+31 (accumulator rows)
+#define GTC_THREADS (GTC_CONV + 32 * GTC_ISSUER)
+#ifndef GTC_KC
 #define GTC_KC 32                                  // pixels per stage
+#endif
+#ifndef GTC_NSTAGE
+#define GTC_NSTAGE 2                               // operand stages (hi + lo tiles)
+#endif
+#ifndef GTC_DEPTH
+#define GTC_DEPTH 4                                // raw-value ring: cp.async loads run GTC_DEPTH - 1 stages ahead
+#endif
+#define GTC_CH (GTC_KC / 4)                        // 16-byte chunks (= operand panels) per stage
+#define GTC_RAWI ((80 * GTC_CH + GTC_CONV - 1) / GTC_CONV)   // (row, chunk) items per thread and stage held by the ring: D + 1 <= 80
 #define GTC_PANEL 2048                             // bytes: 128 rows x 16 B
-#define GTC_TILE (GTC_PANEL * (GTC_KC / 4))        // one hi or lo tile: 16 KB
+#define GTC_TILE (GTC_PANEL * GTC_CH)              // one hi or lo tile
 #define GTC_STAGE (2 * GTC_TILE)                   // hi + lo
-#define GTC_SMEM (2 * GTC_STAGE + 64)              // two stages + 4 barriers + tmem pointer
+#define GTC_RAW_STAGE (GTC_RAWI * GTC_CONV * 16)   // bytes of one ring stage: a private float4 slot per thread and item
+#define GTC_NBAR (2 * GTC_NSTAGE + 4)              // full[NSTAGE], free[NSTAGE], acc_done[2], acc_free[2]
+#define GTC_SMEM (GTC_NSTAGE * GTC_STAGE + GTC_DEPTH * GTC_RAW_STAGE + 8 * GTC_NBAR + 16)   // + barriers, tmem pointer, error flag
 
 __device__ __forceinline__ uint32_t gtc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ float gtc_tf32(float v) {
@@ -68,7 +114,7 @@ __device__ __forceinline__ bool gtc_wait(uint64_t* bar, uint32_t parity) {   // 
 // parity bound.  So the chain is cut into segments of GTC_SEG stages (64 pixels): two TMEM accumulators
 // ping-pong, and while the tensor core works on segment g the threads drain segment g-1 (tcgen05.ld) and add
 // it to per-thread fp32 registers with round-to-nearest adds (thread r owns Gram row r).
-#define GTC_SEG 2
+#define GTC_SEG (64 / GTC_KC)                      // stages per segment
 #define GTC_ACC_COLS 128                           // TMEM column stride between the two accumulators
 
 template <int NB>
@@ -90,8 +136,7 @@ __device__ __forceinline__ void gtc_drain(uint32_t taddr, float (&acc)[NB * 16])
 // grid = ksplit x (number of samples in the chunk), block = 128; NB = N / 16 column blocks (N = D+1 rounded up to 16).
 // ksplit = 1: one CTA per sample, plain stores.  ksplit = 2: two CTAs per sample, each sums half of the pixel segments and ADDS its
 // rows to the (pre-zeroed) Gram with fp32 atomics -- two addends commute, so the result does not depend on which CTA arrives
-// first and stays bit-reproducible.  The kernel is latency-bound (one 128-thread CTA per sample converts, stores and issues;
-// 11 % of the warp slots busy): twice the CTAs hide twice the latency.
+// first and stays bit-reproducible.
 // err_flag (may be null): set to 1 if a barrier wait timed out.
 template <int NB>
 __global__ void __launch_bounds__(GTC_THREADS) k_gram_tc(int D, int npx, const float* __restrict__ R, const float* __restrict__ w,
@@ -99,17 +144,30 @@ __global__ void __launch_bounds__(GTC_THREADS) k_gram_tc(int D, int npx, const f
                                                         int* __restrict__ err_flag, int ksplit) {
   extern __shared__ __align__(1024) unsigned char gtc_smem[];
   unsigned char* smem = gtc_smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * GTC_STAGE);     // [0,1]: stage free, [2,3]: accumulator a complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 2 * GTC_STAGE + 32);
-  const int tid = threadIdx.x, warp = tid >> 5, b = blockIdx.x / ksplit, half = blockIdx.x - b * ksplit;
+  unsigned char* raw = smem + GTC_NSTAGE * GTC_STAGE;                      // [GTC_DEPTH][GTC_RAWI][128 threads] float4
+  uint64_t* bars = reinterpret_cast<uint64_t*>(raw + GTC_DEPTH * GTC_RAW_STAGE);
+  uint64_t* bar_full = bars;                         // [NSTAGE]
+  uint64_t* bar_free = bars + GTC_NSTAGE;            // [NSTAGE]
+  uint64_t* bar_acc_done = bars + 2 * GTC_NSTAGE;    // [2]
+  uint64_t* bar_acc_free = bars + 2 * GTC_NSTAGE + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + GTC_NBAR);
+  int* s_err = reinterpret_cast<int*>(tmem_slot + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, b = blockIdx.x / ksplit, half = blockIdx.x - b * ksplit;
   const int Dx = D + 1;
   constexpr int N = NB * 16;
   const float* Rb = R + (size_t)b * D * npx;
-  // zero both stages once: rows > D stay zero for the whole kernel
-  for (int i = tid; i < 2 * GTC_STAGE / 16; i += GTC_THREADS) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  // zero every operand stage once: rows > D stay zero for the whole kernel
+  for (int i = tid; i < GTC_NSTAGE * GTC_STAGE / 16; i += GTC_THREADS) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (tid == 0) {
-    for (int i = 0; i < 4; ++i)
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(gtc_smem_u32(bars + i)));
+    for (int i = 0; i < GTC_NSTAGE; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" :: "r"(gtc_smem_u32(bar_full + i)));      // one arrival per warp
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(gtc_smem_u32(bar_free + i)));      // tcgen05.commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(gtc_smem_u32(bar_acc_done + i)));  // tcgen05.commit
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" :: "r"(gtc_smem_u32(bar_acc_free + i)));  // one arrival per warp
+    }
+    *s_err = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -128,106 +186,160 @@ __global__ void __launch_bounds__(GTC_THREADS) k_gram_tc(int D, int npx, const f
   const int seg0 = (nseg_all * half) / ksplit, seg1 = (nseg_all * (half + 1)) / ksplit;
   const int st0 = seg0 * GTC_SEG, st1 = (seg1 * GTC_SEG < nstage_all) ? seg1 * GTC_SEG : nstage_all;
   const int nstage = st1 - st0;                      // stages of this CTA (local index st below)
-  const int nseg = seg1 - seg0;
-  const int nitem = ((Dx + 7) / 8) * 8 * (GTC_KC / 4);   // (row, 16-byte chunk) items per stage, whole 8-row groups
-  const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);   // TMEM lane == accumulator row; warp w owns lanes 32w..32w+31
+  const int nseg = (nstage + GTC_SEG - 1) / GTC_SEG;
+  bool ok = true;
   float acc[NB * 16];
 #pragma unroll
   for (int i = 0; i < NB * 16; ++i) acc[i] = 0.f;
-  bool ok = true;
-  uint32_t phase[2] = {0u, 0u}, aphase[2] = {0u, 0u};
-  // Software pipeline of the operand loads: the raw values of stage st+1 are fetched into registers (float4 per
-  // (row, chunk) item, up to GTC_MAXI items per thread) before stage st is converted and stored, so the global-load
-  // latency overlaps the split / store / MMA issue of the current stage.
-  constexpr int GTC_MAXI = (NB * 16 + 7) / 8 * 8 * (GTC_KC / 4) / GTC_THREADS + 1;
-  float4 pre[GTC_MAXI], prw[GTC_MAXI];
+  const int nitem = ((Dx + 7) / 8) * 8 * GTC_CH;   // (row, 16-byte chunk) items per stage, whole 8-row groups
+  const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);   // TMEM lane == accumulator row; warp w owns lanes 32w..32w+31
+  // items beyond the ring (D + 1 > 80: more than GTC_RAWI items per thread) are fetched with plain loads at conversion time
+  constexpr int GTC_MAXI = (NB * 16 * GTC_CH + GTC_CONV - 1) / GTC_CONV;
   const bool vec_ok = (npx % 4) == 0;               // channel rows are then 16-byte aligned
-  auto fetch = [&](int stage) {
-    const int p0 = (st0 + stage) * GTC_KC;
+  const uint32_t raw_u32 = gtc_smem_u32(raw) + (uint32_t)tid * 16u;
+  // Item k of this thread is (row, 16-byte chunk) number tid + 128 k: the chunk kc = (tid >> 3) % GTC_CH is the SAME for all of them
+  // and nothing but the pixel offset changes from stage to stage, so rows, operand offsets and validity are computed once.
+  const int kc4 = ((tid >> 3) & (GTC_CH - 1)) * 4;
+  int off[GTC_RAWI];
+  const float* srow[GTC_RAWI];
+  unsigned vmask = 0u;
 #pragma unroll
-    for (int k = 0; k < GTC_MAXI; ++k) {
-      const int it = tid + k * GTC_THREADS;
-      const int r0 = it & 7, kc = (it >> 3) & 7, row = (it >> 6) * 8 + r0;
-      const int p = p0 + kc * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f), wv = v;
-      if (it < nitem && row < Dx && p < npx) {
-        const float* src = (row < D) ? Rb + (size_t)row * npx + p : obs + p;
-        if (vec_ok && p + 3 < npx) {
-          v = __ldg(reinterpret_cast<const float4*>(src));
-          wv = __ldg(reinterpret_cast<const float4*>(w + p));
+  for (int k = 0; k < GTC_RAWI; ++k) {
+    const int it = tid + k * GTC_CONV;
+    const int row = (it / (8 * GTC_CH)) * 8 + (it & 7);
+    const bool valid = it < nitem && row < Dx;
+    off[k] = (kc4 >> 2) * GTC_PANEL + row * 16;
+    srow[k] = valid ? ((row < D) ? Rb + (size_t)row * npx : obs) : Rb;
+    vmask |= (valid ? 1u : 0u) << k;
+  }
+  // cp.async the raw values of local stage `stage` into ring slot stage % GTC_DEPTH (zero fill outside the image / the rows)
+  auto issue_loads = [&](int stage) {
+    if (stage < nstage && !(GTC_EXP_SKIP & 1)) {
+      const int p = (st0 + stage) * GTC_KC + kc4;
+      const uint32_t dst0 = raw_u32 + (uint32_t)(stage % GTC_DEPTH) * GTC_RAW_STAGE;
+#pragma unroll
+      for (int k = 0; k < GTC_RAWI; ++k) {
+        const bool in = ((vmask >> k) & 1u) && p < npx;
+        const float* src = in ? srow[k] + p : Rb;
+        const uint32_t dst = dst0 + (uint32_t)k * (GTC_CONV * 16u);
+        if (vec_ok) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(in ? 16u : 0u) : "memory");
         } else {
-          v.x = __ldg(src); wv.x = __ldg(w + p);
-          if (p + 1 < npx) { v.y = __ldg(src + 1); wv.y = __ldg(w + p + 1); }
-          if (p + 2 < npx) { v.z = __ldg(src + 2); wv.z = __ldg(w + p + 2); }
-          if (p + 3 < npx) { v.w = __ldg(src + 3); wv.w = __ldg(w + p + 3); }
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(dst + 4u * q), "l"(in && p + q < npx ? src + q : Rb),
+                         "r"((in && p + q < npx) ? 4u : 0u) : "memory");
         }
       }
-      pre[k] = v; prw[k] = wv;
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");   // one group per stage, empty past the end: the wait below counts groups
   };
-  fetch(0);
+  int next_drain = 0;                               // segments are drained in order
+  auto drain = [&]() {
+    const int pa = next_drain & 1;
+    ok = gtc_wait(bar_acc_done + pa, (uint32_t)((next_drain >> 1) & 1)) && ok;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (!(GTC_EXP_SKIP & 4)) gtc_drain<NB>(lane_base + (uint32_t)(pa * GTC_ACC_COLS), acc);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(gtc_smem_u32(bar_acc_free + pa)) : "memory");
+    ++next_drain;
+  };
+  // ---- MMA issue for local stage st (one thread): K = 8 per MMA = two 16-byte chunks = two panels; three MMAs per slice (3xTF32)
+  auto issue_stage = [&](int st) {
+    const int s = st % GTC_NSTAGE, use = st / GTC_NSTAGE, seg = st / GTC_SEG, a = seg & 1;
+    const bool first = (st % GTC_SEG) == 0;       // a new segment overwrites its accumulator ...
+    if (first && seg >= 2) ok = gtc_wait(bar_acc_free + a, (uint32_t)(((seg - 2) >> 1) & 1)) && ok;   // ... once its last content is drained
+    ok = gtc_wait(bar_full + s, (uint32_t)(use & 1)) && ok;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t ah = gtc_smem_u32(smem + s * GTC_STAGE), al = ah + GTC_TILE;
+    const uint32_t dacc = tmem + (uint32_t)(a * GTC_ACC_COLS);
+#pragma unroll
+    for (int j = 0; j < GTC_KC / 8; ++j) {
+      const uint64_t dh = gtc_desc(ah + j * 2 * GTC_PANEL), dl = gtc_desc(al + j * 2 * GTC_PANEL);
+      gtc_mma(dacc, dh, dh, idesc, (first && j == 0) ? 0u : 1u);
+      GTC_EXP_MMA2(gtc_mma(dacc, dh, dl, idesc, 1u);)
+      GTC_EXP_MMA3(gtc_mma(dacc, dl, dh, idesc, 1u);)
+    }
+    gtc_commit(bar_free + s);
+    if ((st % GTC_SEG) == GTC_SEG - 1 || st == nstage - 1) gtc_commit(bar_acc_done + a);
+  };
+  if (GTC_ISSUER == 1 && warp == 4) {
+    if (lane == 0) {
+      for (int st = 0; st < nstage; ++st) issue_stage(st);
+      if (!ok) *s_err = 1;
+    }
+  } else {
+#pragma unroll
+  for (int r = 0; r < GTC_DEPTH - 1; ++r) issue_loads(r);
   for (int st = 0; st < nstage; ++st) {
-    const int s = st & 1, seg = st / GTC_SEG, a = seg & 1;
+    const int s = st % GTC_NSTAGE, use = st / GTC_NSTAGE, seg = st / GTC_SEG, a = seg & 1;
     unsigned char* hi = smem + s * GTC_STAGE;
     unsigned char* lo = hi + GTC_TILE;
-    if (st >= 2) {                                  // the MMAs that read this stage two iterations ago must have retired
-      ok = gtc_wait(bars + s, phase[s]) && ok;
-      phase[s] ^= 1u;
+    issue_loads(st + GTC_DEPTH - 1);
+    asm volatile("cp.async.wait_group %0;" :: "n"(GTC_DEPTH - 1) : "memory");    // this stage's own loads have landed
+    const float4* rs = reinterpret_cast<const float4*>(raw + (size_t)(st % GTC_DEPTH) * GTC_RAW_STAGE) + tid;
+    const int p = (st0 + st) * GTC_KC + kc4;          // first pixel of this thread's chunk in this stage
+    float4 wq = make_float4(0.f, 0.f, 0.f, 0.f);      // the weights of the chunk: shared by all items of the thread
+    if (vec_ok && p + 3 < npx) wq = __ldg(reinterpret_cast<const float4*>(w + p));
+    else {
+      if (p < npx) wq.x = __ldg(w + p);
+      if (p + 1 < npx) wq.y = __ldg(w + p + 1);
+      if (p + 2 < npx) wq.z = __ldg(w + p + 2);
+      if (p + 3 < npx) wq.w = __ldg(w + p + 3);
     }
-#pragma unroll
-    for (int k = 0; k < GTC_MAXI; ++k) {
-      // item -> (row group, chunk, row in group): a quarter-warp covers 8 consecutive rows of one panel
-      const int it = tid + k * GTC_THREADS;
-      const int r0 = it & 7, kc = (it >> 3) & 7, row = (it >> 6) * 8 + r0;
-      if (it >= nitem || row >= Dx) continue;
-      float v[4] = {pre[k].x, pre[k].y, pre[k].z, pre[k].w};
-      const float wv[4] = {prw[k].x, prw[k].y, prw[k].z, prw[k].w};
+    if (use >= 1) ok = gtc_wait(bar_free + s, (uint32_t)((use - 1) & 1)) && ok;   // the MMAs that read this stage have retired
+    auto split_store = [&](float4 rv, int o) {
+      float v[4] = {rv.x, rv.y, rv.z, rv.w};
+      const float wv[4] = {wq.x, wq.y, wq.z, wq.w};
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         if (v[q] != v[q]) v[q] = 0.f;               // NaN scrub (:228)
         v[q] *= wv[q];
       }
       float4 h, l;
-      h.x = gtc_tf32(v[0]); h.y = gtc_tf32(v[1]); h.z = gtc_tf32(v[2]); h.w = gtc_tf32(v[3]);
-      l.x = gtc_tf32(v[0] - h.x); l.y = gtc_tf32(v[1] - h.y); l.z = gtc_tf32(v[2] - h.z); l.w = gtc_tf32(v[3] - h.w);
-      const int off = kc * GTC_PANEL + row * 16;
-      *reinterpret_cast<float4*>(hi + off) = h;
-      *reinterpret_cast<float4*>(lo + off) = l;
-    }
-    if (st + 1 < nstage) fetch(st + 1);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core (async proxy)
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (tid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t ah = gtc_smem_u32(hi), al = gtc_smem_u32(lo);
-      const uint32_t dacc = tmem + (uint32_t)(a * GTC_ACC_COLS);
-      const bool first = (st % GTC_SEG) == 0;       // a new segment overwrites its accumulator
-#pragma unroll
-      for (int j = 0; j < GTC_KC / 8; ++j) {        // K = 8 per MMA = two 16-byte chunks = two panels
-        const uint64_t dh = gtc_desc(ah + j * 2 * GTC_PANEL), dl = gtc_desc(al + j * 2 * GTC_PANEL);
-        gtc_mma(dacc, dh, dh, idesc, (first && j == 0) ? 0u : 1u);
-        gtc_mma(dacc, dh, dl, idesc, 1u);
-        gtc_mma(dacc, dl, dh, idesc, 1u);
+      if (GTC_EXP_SKIP & 2) { h = rv; l = rv; }
+      else {
+        h.x = gtc_tf32(v[0]); h.y = gtc_tf32(v[1]); h.z = gtc_tf32(v[2]); h.w = gtc_tf32(v[3]);
+        l.x = gtc_tf32(v[0] - h.x); l.y = gtc_tf32(v[1] - h.y); l.z = gtc_tf32(v[2] - h.z); l.w = gtc_tf32(v[3] - h.w);
       }
-      gtc_commit(bars + s);
-      if ((st % GTC_SEG) == GTC_SEG - 1 || st == nstage - 1) gtc_commit(bars + 2 + a);
+      if (!(GTC_EXP_SKIP & 32)) {
+        *reinterpret_cast<float4*>(hi + o) = h;
+        *reinterpret_cast<float4*>(lo + o) = l;
+      } else if (h.x == 123.456f && l.y == 654.321f) *s_err = 2;   // keep the values alive
+    };
+#pragma unroll
+    for (int k = 0; k < GTC_RAWI; ++k)
+      if ((vmask >> k) & 1u) split_store(rs[k * GTC_CONV], off[k]);
+#pragma unroll
+    for (int k = GTC_RAWI; k < GTC_MAXI; ++k) {       // D + 1 > 80: the items beyond the ring, plain loads
+      const int it = tid + k * GTC_CONV;
+      const int row = (it / (8 * GTC_CH)) * 8 + (it & 7);
+      if (it >= nitem || row >= Dx) continue;
+      float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* src = ((row < D) ? Rb + (size_t)row * npx : obs) + p;
+      if (p < npx) rv.x = __ldg(src);
+      if (p + 1 < npx) rv.y = __ldg(src + 1);
+      if (p + 2 < npx) rv.z = __ldg(src + 2);
+      if (p + 3 < npx) rv.w = __ldg(src + 3);
+      split_store(rv, (kc4 >> 2) * GTC_PANEL + row * 16);
     }
-    // drain the previous segment while the tensor core works on this one
-    if ((st % GTC_SEG) == 0 && seg >= 1) {
-      const int pa = a ^ 1;
-      ok = gtc_wait(bars + 2 + pa, aphase[pa]) && ok;
-      aphase[pa] ^= 1u;
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      gtc_drain<NB>(lane_base + (uint32_t)(pa * GTC_ACC_COLS), acc);
-    }
+    if (!(GTC_EXP_SKIP & 8)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core (async proxy)
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(gtc_smem_u32(bar_full + s)) : "memory");
+    if (GTC_ISSUER == 0 && tid == 0) issue_stage(st);
+    __syncwarp();
+    // drain the previous segment one stage late (at the last stage of this one): its MMAs were issued a whole stage ago
+    if ((st % GTC_SEG) == GTC_SEG - 1 && seg >= 1) drain();
   }
-  {   // last segment
-    const int pa = (nseg - 1) & 1;
-    ok = gtc_wait(bars + 2 + pa, aphase[pa]) && ok;
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    gtc_drain<NB>(lane_base + (uint32_t)(pa * GTC_ACC_COLS), acc);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  while (next_drain < nseg) drain();
+  if (!ok) *s_err = 1;
   }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  ok = (*s_err == 0);
   float* out = gram + (size_t)b * Dx * Dx;
   if (ok && nstage > 0) {
     if (tid < Dx) {
@@ -245,8 +357,6 @@ __global__ void __launch_bounds__(GTC_THREADS) k_gram_tc(int D, int npx, const f
     for (int i = tid; i < Dx * Dx; i += GTC_THREADS) out[i] = __int_as_float(0x7fc00000);
     if (tid == 0 && err_flag) *err_flag = 1;
   }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" :: "r"(tmem) : "memory");
 }
 

@@ -47,7 +47,28 @@ static int run_case(int D, int npx, int bs, int mode, bool verbose) {
   return (worst / scale < 2e-6 && !err) ? 0 : 1;
 }
 
-int main() {
+// `gram_tc_check time [bs]`: device time of the C3-shaped launch (D = 66, 3600 pixels), CUDA events, best of 5
+static int run_timing(int bs) {
+  const int D = 66, npx = 3600, Dx = D + 1;
+  float *dR, *dw, *dobs, *dG;
+  cudaMalloc(&dR, (size_t)bs * D * npx * 4); cudaMalloc(&dw, npx * 4); cudaMalloc(&dobs, npx * 4); cudaMalloc(&dG, (size_t)bs * Dx * Dx * 4);
+  cudaMemset(dR, 0x3c, (size_t)bs * D * npx * 4); cudaMemset(dw, 0x3c, npx * 4); cudaMemset(dobs, 0x3c, npx * 4);
+  if (gl_gram_tc_init() != cudaSuccess) return 2;
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 6; ++rep) {
+    cudaEventRecord(e0);
+    if (gl_launch_gram_tc(bs, D, npx, dR, dw, dobs, dG, nullptr, 0) != cudaSuccess) return 2;
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  printf("timing: D=%d npx=%d bs=%d: %.3f ms  (%.0f GB/s of operand reads)\n", D, npx, bs, best, (double)bs * D * npx * 4 / best / 1e6);
+  return cudaDeviceSynchronize() == cudaSuccess ? 0 : 2;
+}
+
+int main(int argc, char** argv) {
+  if (argc > 1 && argv[1][0] == 't') return run_timing(argc > 2 ? atoi(argv[2]) : 2048);
   int bad = 0;
   bad |= run_case(11, 32, 1, 0, true);     // one stage, one-hot rows: G = diag((c+1)^2)
   bad |= run_case(11, 64, 1, 0, true);
