@@ -149,7 +149,9 @@ int gl_plan_set_positions(gl_plan* plan, int32_t n_systems, const int32_t* n_ima
  * (BackwardProbModel, tf/model.py:242-273).
  * "include_pixels" / "include_positions" = 0 | 1: which terms gl_loglike_grad / gl_logprob_grad add
  * (ForwardProbModel(include_pixels, include_positions), tf/model.py:43-44,150-163): log-likes add and the
- * reduced chi^2 is the mean of the included terms. */
+ * reduced chi^2 is the mean of the included terms.
+ * "lstsq_hide_tail" = 0: the gradient path of the lstsq model runs the eigen-solve of the samples with a singular
+ * Gram matrix in line instead of on its side stream (A/B; bit-identical results). */
 int gl_plan_set_option(gl_plan* plan, const char* name, int32_t value);
 /* Measurement aid: after gl_plan_set_option(plan, "timing", n) every log-likelihood call records CUDA
  * events around its kernels on the launch stream; this returns the summed device time (ms) of the 7
