@@ -320,6 +320,39 @@ def test_lstsq_simulate_and_backward_model(n_max, interpolate, with_lens_light):
         assert_parity(dz[:, k], dz32[:, k], dz64[:, k], 1e-4, f"dz[{k}]", dz64p[:, k])
 
 
+def test_c3_full_batch_per_sample_parity():
+    """BASELINE.json configs[2] at its full size: the bench batch (2048 prior draws of the Shapelets n_max = 10 model, D = 66 linear
+    amplitudes) through BackwardProbModel.log_prob_and_grad, checked PER SAMPLE against the oracle (torch.linalg.pinv + autograd) on
+    every 64th sample.  A sample whose Gram matrix has eigenvalues under the rcond = 1e-6 cut keeps the value parity; its
+    gradient is documented to differ from TF's (which differentiates through the truncated SVD), so the gradient
+    check covers the samples without an active cut."""
+    bs, stride = 2048, 64
+    wl = workloads.c3_workload(n_max=10, observed=workloads.c3_observation(n_max=10))
+    sim = LensSimulator(wl["phys_model"], wl["sim_config"], bs=bs)
+    pmod = BackwardProbModel(wl["prior"], wl["observed"], wl["background_rms"], wl["exp_time"])
+    z = pmod.bij_inverse(wl["prior"].sample(bs, seed=0))
+    logp, chi2, dz = (t.cpu().numpy() for t in pmod.log_prob_and_grad(sim, torch.as_tensor(z, device="cuda")))
+    assert np.isfinite(logp).all() and np.isfinite(dz).all()
+    sub = np.arange(0, bs, stride)
+    zs = z[sub]
+    lp64, chi64, dz64 = oracle_bridge.backward_logprob_and_grad(wl, zs.astype(np.float64), torch.float64)
+    lp32, chi32, dz32 = oracle_bridge.backward_logprob_and_grad(wl, zs, torch.float32)
+    lp64p, chi64p, dz64p = oracle_bridge.backward_logprob_and_grad(wl, common.ulp_perturb(zs), torch.float64)
+    # which of the checked samples have an active pinv cut (fp64 spectrum of the weighted normal equations)
+    osim, opm = oracle_bridge.build_oracle_backward(wl, sub.size, torch.float64)
+    p64, _ = opm.prior.forward(torch.as_tensor(zs.astype(np.float64)))
+    st = osim.lstsq_simulate(p64, opm.observed_image, opm.err_map, return_stacked=True)          # (n, ny, nx, D)
+    X = (st / opm.err_map[None, :, :, None]).reshape(sub.size, -1, st.shape[-1])
+    ev = torch.linalg.eigvalsh(X.transpose(1, 2) @ X).numpy()
+    cut = ev[:, 0] <= 2e-6 * ev[:, -1]              # at or next to the cut (the decision itself is fp32-noisy within a factor ~2)
+    print("C3 bs 2048: checked", sub.size, "samples,", int(cut.sum()), "with eigenvalues at / under the pinv cut:", sub[cut])
+    assert_parity(logp[sub, None], lp32[:, None], lp64[:, None], 1e-5, "C3 logp per sample (bs 2048)", lp64p[:, None], axis=1)
+    assert_parity(chi2[sub, None], chi32[:, None], chi64[:, None], 1e-5, "C3 red chi2 per sample (bs 2048)", chi64p[:, None], axis=1)
+    keep = ~cut
+    assert keep.sum() >= sub.size - 4
+    assert_parity(dz[sub][keep], dz32[keep], dz64[keep], 1e-4, "C3 dz per sample (bs 2048, no active cut)", dz64p[keep], axis=1)
+
+
 def test_lstsq_chunked_passes_match_single_pass():
     """The component stack is processed in sample chunks sized by a memory budget; results must not
     depend on the chunking."""
@@ -873,6 +906,28 @@ def test_c4_cluster_baseline_geometry_parity():
     assert_parity(chi2z[:, None], s_chi2[:, None], r_chi2[:, None], 1e-5, "C4 red chi2 (z)", p_chi2[:, None], axis=1)
     for k in range(z.shape[1]):
         assert_parity(dz[:, k], s_dz[:, k], r_dz[:, k], 1e-4, f"C4 dz[{k}]", p_dz[:, k])
+
+
+def test_c4_full_batch_per_sample_parity():
+    """BASELINE.json configs[3] at its full size: the bench batch (1024 prior draws of the cluster model, 200x200, ss = 2) through
+    log_prob_and_grad, every 256th sample checked per sample against the fp32 / fp64 / perturbed oracle (the fp64 oracle with
+    autograd handles a handful of 160 000-ray samples in seconds)."""
+    bs, stride = 1024, 256
+    wl = workloads.c4_workload(observed=workloads.c4_observation())
+    sim = LensSimulator(wl["phys_model"], wl["sim_config"], bs=bs)
+    pmod = ForwardProbModel(wl["prior"], wl["observed"], background_rms=wl["background_rms"], exp_time=wl["exp_time"])
+    z = pmod.bij_inverse(wl["prior"].sample(bs, seed=0))
+    logp, chi2, dz = (t.cpu().numpy() for t in pmod.log_prob_and_grad(sim, torch.as_tensor(z, device="cuda")))
+    assert np.isfinite(logp).all() and np.isfinite(dz).all()
+    sub = np.arange(0, bs, stride)
+    zs = z[sub]
+    r_logp, r_chi2, r_dz = oracle_bridge.logprob_and_grad(wl, zs.astype(np.float64), torch.float64)
+    s_logp, s_chi2, s_dz = oracle_bridge.logprob_and_grad(wl, zs, torch.float32)
+    pert = [oracle_bridge.logprob_and_grad(wl, common.ulp_perturb(zs), torch.float64),
+            oracle_bridge.logprob_and_grad(wl, zs.astype(np.float64), torch.float64, beta_noise=1.5e-7, noise_seed=1)]
+    assert_parity(logp[sub, None], s_logp[:, None], r_logp[:, None], 1e-5, "C4 logp per sample (bs 1024)", [p[0][:, None] for p in pert], axis=1)
+    assert_parity(chi2[sub, None], s_chi2[:, None], r_chi2[:, None], 1e-5, "C4 red chi2 per sample (bs 1024)", [p[1][:, None] for p in pert], axis=1)
+    assert_parity(dz[sub], s_dz, r_dz, 1e-4, "C4 dz per sample (bs 1024)", [p[2] for p in pert], axis=1)
 
 
 @pytest.mark.parametrize("include_pixels", [False, True])
