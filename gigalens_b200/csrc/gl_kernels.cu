@@ -606,7 +606,9 @@ __global__ void k_unpermute(int npix, int bs, const int* __restrict__ perm, cons
 }
 
 // deflection / beta / surface brightness at arbitrary points shared by all samples
-// mode 0: beta (x - alpha), 1: alpha, 2: surface brightness (lens light at theta + source at beta)
+// mode 0: beta (x - alpha), 1: alpha, 2: surface brightness (lens light at theta + source at beta),
+// 3: the unit-amplitude linear light components (what light() of a use_lstsq profile returns, sersic.py:31-35,
+//    shapelets.py:62-63,72-73): out0[b][c][p]
 template <unsigned F>
 __global__ void k_points(GlProgram P, int npts, const float* __restrict__ px, const float* __restrict__ py,
                          const float* __restrict__ derived, int mode, float* __restrict__ out0, float* __restrict__ out1) {
@@ -621,6 +623,10 @@ __global__ void k_points(GlProgram P, int npts, const float* __restrict__ px, co
       float v[1];
       gl_pix_image<float, 1, F>(P, s_der, x, y, false, v);
       out0[(size_t)b * npts + p] = v[0];
+    } else if (mode == 3) {
+      float bx[1], by[1];
+      gl_pix_beta<float, 1, F>(P, s_der, x, y, bx, by);
+      gl_point_components<float, F>(P, s_der, x[0], y[0], bx[0], by[0], out0 + (size_t)b * P.depth * npts + p, npts, true);
     } else {
       float bx[1], by[1];
       gl_pix_beta<float, 1, F>(P, s_der, x, y, bx, by);
@@ -1524,7 +1530,8 @@ int gl_beta(gl_plan* p, const float* params_dev, int32_t npts, const float* x_de
 int gl_eval_points(gl_plan* p, const float* params_dev, int32_t npts, const float* x_dev, const float* y_dev, int32_t mode,
                    float* out0, float* out1, void* stream) {
   if (!p || !params_dev || !x_dev || !y_dev || !out0 || npts <= 0) return gl_fail("gl_eval_points: bad argument");
-  if (mode < 0 || mode > 2 || (mode != 2 && !out1)) return gl_fail("gl_eval_points: bad mode");
+  if (mode < 0 || mode > 3 || (mode < 2 && !out1)) return gl_fail("gl_eval_points: bad mode");
+  if (mode == 3 && p->prog.depth <= 0) return gl_fail("gl_eval_points: mode 3 needs a light profile with use_lstsq");
   GL_CUDA(cudaSetDevice(p->device));
   cudaStream_t st = (cudaStream_t)stream;
   if (gl_run_prep(p, params_dev, st)) return 1;

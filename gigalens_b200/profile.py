@@ -54,6 +54,11 @@ def _eval_points(kind, profile, x, y, kwargs):
     if kind == "hessian":
         H = sim.hessian(xf, yf, params["lens_mass"])
         return tuple(h.reshape((bs,) + shape).squeeze(0) if bs == 1 else h.reshape((bs,) + shape) for h in H)
+    if kind == "light" and getattr(profile, "use_lstsq", False):
+        # the reference returns the linear components with a leading axis (sersic.py:35, shapelets.py:62-63,72-73)
+        v = sim.eval_points(params, xf, yf, mode=3)[0]                       # (bs, depth, npts)
+        v = v.permute(1, 0, 2).reshape((v.shape[1], bs) + shape)
+        return v.squeeze(1) if bs == 1 else v
     out = sim.eval_points(params, xf, yf, mode=1 if kind == "mass" else 2)
     if kind == "mass":
         ax, ay = out
@@ -83,7 +88,8 @@ class LightProfile(Parameterized, ABC):
 
     def light(self, x, y, **kwargs):
         """Surface brightness at points ``(x, y)`` (shared by all samples); parameters are scalars or
-        ``(bs,)`` arrays.  Returns a CUDA tensor of shape ``x.shape`` (``(bs,)+x.shape`` when bs>1)."""
+        ``(bs,)`` arrays.  Returns a CUDA tensor of shape ``x.shape`` (``(bs,)+x.shape`` when bs>1); a ``use_lstsq`` profile
+        returns its unit-amplitude components with a leading axis of length ``depth``, like the reference."""
         return _eval_points("light", self, x, y, kwargs)
 
 

@@ -368,11 +368,18 @@ class LensSimulator(LensSimulatorInterface):
 
     def eval_points(self, params, x, y, mode=0, missing_ok=()):
         """mode 0: beta, 1: total deflection, 2: surface brightness, at points shared by all samples
-        (``(bs, npts)``; ``(N, bs)`` when the coordinates came in the reference's tiled ``(N, bs)`` layout)."""
+        (``(bs, npts)``; ``(N, bs)`` when the coordinates came in the reference's tiled ``(N, bs)`` layout);
+        mode 3: the unit-amplitude linear components of the ``use_lstsq`` light profiles, ``(bs, depth, npts)``
+        (``(depth, N, bs)`` in the reference layout)."""
         torch = self._torch
         mat = self._params_matrix(params, missing_ok)
         xt, yt, ref_layout = self._points(x, y)
         npts = xt.numel()
+        if mode == 3:
+            o = torch.empty((self.bs, max(1, self.depth), npts), dtype=torch.float32, device=self.device)
+            _cabi.check(self._lib.gl_eval_points(self._plan, mat.data_ptr(), npts, xt.data_ptr(), yt.data_ptr(), 3,
+                                                 o.data_ptr(), None, self._stream()), self._lib)
+            return (o.permute(1, 2, 0),) if ref_layout else (o,)
         o0 = torch.empty((self.bs, npts), dtype=torch.float32, device=self.device)
         o1 = torch.empty((self.bs, npts), dtype=torch.float32, device=self.device)
         _cabi.check(self._lib.gl_eval_points(self._plan, mat.data_ptr(), npts, xt.data_ptr(), yt.data_ptr(), int(mode),

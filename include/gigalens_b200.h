@@ -177,7 +177,9 @@ int gl_beta(gl_plan* plan, const float* params_dev, int32_t npts, const float* x
 
 /* Total deflection (mode 1: out0 = alpha_x, out1 = alpha_y), beta (mode 0) or surface brightness
  * (mode 2: out0 only) at arbitrary points: MassProfile.deriv / LightProfile.light as the reference's
- * profile tests call them (tests/test_profiles.py:14-111).  out* [bs][npts]. */
+ * profile tests call them (tests/test_profiles.py:14-111).  out* [bs][npts].
+ * Mode 3 (out0 only, [bs][depth][npts]): the unit-amplitude linear components that light() of a use_lstsq profile
+ * returns (tf/profiles/light/sersic.py:31-35, shapelets.py:62-63,72-73), NaN-scrubbed like the lstsq stack. */
 int gl_eval_points(gl_plan* plan, const float* params_dev, int32_t npts, const float* x_dev, const float* y_dev,
                    int32_t mode, float* out0_dev, float* out1_dev, void* stream);
 

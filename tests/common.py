@@ -236,3 +236,17 @@ def parity_summary():
                 fraction_over_tol=(tot_o / tot_s) if tot_s else 0.0,
                 max_err_over_floor_of_slices_over_tol=max([t["max_err_over_floor_of_slices_over_tol"] for t in tests.values()] or [0.0]),
                 tests=tests)
+
+
+# ---------------------------------------------------------------- cases shared with tests/golden/make_reference_golden.py
+def spec_profile(cls, ctor):
+    """Product-side descriptor object of a ``(class name, constructor kwargs)`` spec of tests/golden/reference_cases.py."""
+    table = {"EPL": gl_epl.EPL, "Shear": gl_shear.Shear, "SIE": gl_sie.SIE, "SIS": gl_sis.SIS, "NFW": gl_nfw.NFW,
+             "NFW_ELLIPSE": gl_nfw.NFW_ELLIPSE, "DPIS": gl_piemd.DPIS, "DPIE": gl_piemd.DPIE, "TNFW": gl_tnfw.TNFW,
+             "DPIEP": gl_piep.DPIEP, "DPIESubhalo": gl_sub.DPIESubhalo, "Sersic": gl_sersic.Sersic,
+             "SersicEllipse": gl_sersic.SersicEllipse, "Shapelets": gl_shapelets.Shapelets}
+    return table[cls](**ctor)
+
+
+def spec_model(model):
+    return PhysicalModel(*[[spec_profile(c, k) for c, k in model[g]] for g in ("lens_mass", "lens_light", "source_light")])
