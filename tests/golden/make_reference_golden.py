@@ -138,7 +138,8 @@ def run_simulators(out, tag, dtype, psf, demo):
         pre = f"sim/{key}/{tag}"
         img = sim.simulate(params)
         out[f"{pre}/image"] = N(img)
-        out[f"{pre}/image_no_deflection"] = N(sim.simulate(params, no_deflection=True))
+        if not c.get("image_and_likelihood_only"):
+            out[f"{pre}/image_no_deflection"] = N(sim.simulate(params, no_deflection=True))
         if c.get("variants"):
             out[f"{pre}/source"] = N(sim.simulate_source(params))
             out[f"{pre}/lens_light"] = N(sim.simulate_lens_light(params))
@@ -154,6 +155,8 @@ def run_simulators(out, tag, dtype, psf, demo):
         out[f"{pre}/loglike"], out[f"{pre}/red_chi2"] = N(ll), N(chi2)
         g = torch.autograd.grad(ll.sum(), leaves, allow_unused=True)
         out[f"{pre}/grad"] = np.stack([N(torch.zeros(bs, dtype=dtype) if v is None else v) for v in g])
+        if c.get("image_and_likelihood_only"):
+            continue
         # points: beta, magnification, convergence, shear on the centroids (or a few fixed points)
         if cen is not None:
             px, py = np.concatenate(cen["x"]), np.concatenate(cen["y"])

@@ -187,7 +187,34 @@ def simulator_cases(psf, demo):
     cases["cluster"] = dict(model=model, sim=dict(delta_pix=0.2, num_pix=n, supersample=2, kernel=f32(psf), pix_region=None), params=p,
                             observed=f32(rng.normal(0, 0.2, size=(n, n)) + 0.5), noise=dict(background_rms=0.2, exp_time=100.0),
                             centroids=cen, variants=False)
+    # C4 at BASELINE geometry (configs[3]): 200 x 200, ss = 2, +-10 arcsec, NFW + 30-member dPIE scaling relation + shear;
+    # one sample near the prior medians of workloads.c4_prior() (image, likelihood and gradient only: the fixture stays small)
+    model = dict(lens_mass=[("NFW", {}), ("DPIESubhalo", dict(lum_star=1.0, galaxy_catalogue=c4_catalogue())), ("Shear", {})],
+                 lens_light=[], source_light=[("SersicEllipse", dict(use_lstsq=False))])
+    rng = np.random.default_rng(2006)
+    n = 200
+    p = dict(lens_mass=[dict(Rs=f32([10.5]), alpha_Rs=f32([7.6]), center_x=f32([0.3]), center_y=f32([-0.2])),
+                        dict(theta_E=f32([0.85]), r_core=f32([0.052]), r_cut=f32([4.6])),
+                        dict(gamma1=f32([0.03]), gamma2=f32([-0.02]))],
+             lens_light=[],
+             source_light=[dict(R_sersic=f32([0.27]), n_sersic=f32([1.8]), e1=f32([0.1]), e2=f32([-0.12]), center_x=f32([0.6]),
+                                center_y=f32([-0.4]), Ie=f32([140.0]))])
+    cases["c4_baseline"] = dict(model=model, sim=dict(delta_pix=0.1, num_pix=n, supersample=2, kernel=f32(psf), pix_region=None), params=p,
+                                observed=f32(np.abs(rng.normal(0, 0.3, size=(n, n)))), noise=dict(background_rms=0.2, exp_time=100.0),
+                                variants=False, image_and_likelihood_only=True)
     return cases
+
+
+def c4_catalogue(G=30, seed=7):
+    """``gigalens_b200.workloads.cluster_catalogue`` (SURVEY 8d C4), restated here so that this module stays import-free;
+    tests/test_reference_golden.py asserts the two are identical."""
+    rng = np.random.default_rng(seed)
+    cx, cy = rng.uniform(-9, 9, G), rng.uniform(-9, 9, G)
+    e1, e2 = rng.normal(0, 0.1, G), rng.normal(0, 0.1, G)
+    mod = np.sqrt(e1 ** 2 + e2 ** 2)
+    scale = np.clip(mod, 0.02, 0.6) / np.maximum(mod, 1e-12)
+    e1, e2 = e1 * scale, e2 * scale
+    return dict(lum=rng.lognormal(0, 0.5, G).tolist(), center_x=cx.tolist(), center_y=cy.tolist(), e1=e1.tolist(), e2=e2.tolist())
 
 
 def grad_keys(params):

@@ -29,7 +29,9 @@ TOL = {"f32": 2e-6, "f64": 1e-12}
 
 def close(a, ref, tol, what):
     a, ref = np.asarray(a, dtype=np.float64), np.asarray(ref, dtype=np.float64)
-    if ref.ndim < a.ndim:       # Shear.hessian returns the bare (bs,) parameters (shear.py:18-26); the oracle broadcasts over the points
+    if a.size == ref.size:      # bs = 1: the reference squeezes the batch axis away (tf/simulator.py:156)
+        a = a.reshape(ref.shape)
+    elif ref.ndim < a.ndim:     # Shear.hessian returns the bare (bs,) parameters (shear.py:18-26); the oracle broadcasts over the points
         ref = np.broadcast_to(ref[:, None, :], a.shape)
     assert a.shape == ref.shape, (what, a.shape, ref.shape)
     assert np.array_equal(np.isnan(a), np.isnan(ref)), (what, "NaN pattern")
@@ -104,8 +106,9 @@ def test_oracle_simulator_and_likelihood_match_the_executed_reference(key, tag):
     pre = f"sim/{key}/{tag}"
     tol = TOL[tag]
     img = osim.simulate(params)
-    close(img.detach().numpy(), GOLD[f"{pre}/image"], tol, "image")
-    close(osim.simulate(params, no_deflection=True).detach().numpy(), GOLD[f"{pre}/image_no_deflection"], tol, "no_deflection")
+    close(img.detach().numpy().reshape(GOLD[f"{pre}/image"].shape), GOLD[f"{pre}/image"], tol, "image")
+    if not c.get("image_and_likelihood_only"):
+        close(osim.simulate(params, no_deflection=True).detach().numpy(), GOLD[f"{pre}/image_no_deflection"], tol, "no_deflection")
     if c.get("variants"):
         close(osim.simulate_source(params).detach().numpy(), GOLD[f"{pre}/source"], tol, "simulate_source")
         close(osim.simulate_lens_light(params).detach().numpy(), GOLD[f"{pre}/lens_light"], tol, "simulate_lens_light")
@@ -116,8 +119,15 @@ def test_oracle_simulator_and_likelihood_match_the_executed_reference(key, tag):
     g = torch.autograd.grad(ll.sum(), leaves, allow_unused=True)
     g = np.stack([np.zeros(bs) if v is None else v.numpy() for v in g])
     gref = GOLD[f"{pre}/grad"]
-    for (grp, i, k), a, r in zip(RC.grad_keys(c["params"]), g, gref):
-        close(a, r, 100 * tol, f"grad {grp}[{i}].{k}")
+    g64 = GOLD[f"sim/{key}/f64/grad"]
+    for (grp, i, k), a, r, r64 in zip(RC.grad_keys(c["params"]), g, gref, g64):
+        # float32 autodiff through 160 000 rays sums rounding noise in an order-dependent way: at the cluster geometry the
+        # reference's OWN float32 gradient is 1e-2 (one row 0.7) away from its float64 gradient, so two float32 evaluations
+        # can only agree to that noise floor
+        floor = float(np.max(np.abs(r - r64)) / max(np.max(np.abs(r64)), 1e-30)) if tag == "f32" else 0.0
+        close(a, r, max(100 * tol, 2 * floor), f"grad {grp}[{i}].{k}")
+    if c.get("image_and_likelihood_only"):
+        return
     px, py = GOLD[f"sim/{key}/points"]
     X, Y = T(px[:, None].repeat(bs, axis=1), dt), T(py[:, None].repeat(bs, axis=1), dt)
     lens = [{k: v.detach() for k, v in d.items()} for d in params["lens_mass"]]
@@ -133,6 +143,11 @@ def test_oracle_simulator_and_likelihood_match_the_executed_reference(key, tag):
         gp = np.stack([np.zeros(bs) if v is None else v.numpy() for v in gp])
         for (grp, i, k), a, r in zip(RC.grad_keys(c["params"]), gp, GOLD[f"{pre}/pos_grad"]):
             close(a, r, 1000 * tol, f"positions grad {grp}[{i}].{k}")
+
+
+def test_c4_case_uses_the_benchmark_catalogue():
+    from gigalens_b200 import workloads
+    assert RC.c4_catalogue() == workloads.cluster_catalogue(30, 7)
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/src/gigalens"), reason="the reference tree exists only in the build container")
