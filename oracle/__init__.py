@@ -10,21 +10,27 @@ Who may import it: ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
 
 PARITY PINNING STATUS
 ---------------------
-The reference cannot be imported here (tensorflow, tensorflow_probability, jax and
-lenstronomy are not installed and there is no network), and the reference's own tests
-hold no numeric golden vectors for images or log-probabilities (they compare against
-lenstronomy at run time).  The oracle is therefore pinned by:
+tensorflow, tensorflow_probability, jax and lenstronomy are not installable here (no network), and the reference's own
+tests hold no numeric golden vectors for images or log-probabilities (they compare against lenstronomy at run time).
+The oracle is pinned in two ways.
 
-* the framework-free known-answer tests recoverable from ``tests/test_profiles.py``
-  (Sersic half-light identity, EPL(gamma=2,e=0) == SIS == (x/r, y/r), Shear closed form,
-  Shapelets interpolate == recurrence),
-* cross-profile identities (EPL(gamma=2) == SIE, NFW_ELLIPSE(e=0) == NFW, dPIE(e->0) -> dPIS,
-  ScalingRelation(G=1, L=L*) == DPIE),
-* the one image-level pin that exists: reduced chi^2 of ``simulate(truth)`` against the
-  reference asset ``demo.npy`` (tf-demo.ipynb cells 5-9) must be ~1,
-* autograd-vs-finite-difference checks in float64.
+1. **To the reference's own source code, executed.**  ``oracle/tfshim`` is a torch-backed stand-in for the ~60 ``tf.*``
+   functions the reference's profile / simulator / model files call; with it on ``sys.path`` the UNMODIFIED files under
+   ``/root/reference/src/gigalens/`` import and run (``tests/golden/make_reference_golden.py``), once with ``tf.float32`` =
+   float32 and once = float64.  The committed vectors (``tests/golden/reference_golden.npz``: ``deriv`` / ``hessian`` / ``light``
+   of every profile incl. the clamp / branch edge cases, ``simulate`` and its variants on five models up to BASELINE's cluster
+   geometry, ``stats_pixels`` / ``stats_positions`` with autodiff gradients, ``beta`` / magnification / convergence / shear) are
+   reproduced by this oracle to 7e-15 (float64) and to float32 round-off (``tests/test_reference_golden.py``), and by the
+   CUDA path within the parity rule (``tests/test_gpu_reference_golden.py``).  What that pins: every clamp, ``where``, sign,
+   operation order and loop of the reference's files.  What it does not: TensorFlow's own kernels (represented by torch's).
+2. By reference-held fixtures and independent mathematics: the framework-free known-answer tests of
+   ``tests/test_profiles.py``, cross-profile identities, the ``demo.npy`` image-level pin (reduced chi^2 of
+   ``simulate(truth)`` = 0.981 -- the executed reference gives the same number), the EPL series against the hypergeometric
+   closed form, div(alpha) = 2 kappa, Sersic total flux, Shapelets orthonormality, fp64 finite differences.
 
-Everything that lives in third-party code (TFP bijectors/distributions, TF conv/pool/pinv
-semantics, lenstronomy ``subgrid_kernel``/``phi_n``) is restated from its published
-behaviour and is **parity unpinned** against the real libraries; DESIGN.md says the same.
+Still **parity unpinned** (third-party arithmetic that is neither vendored in the reference nor installable): the TFP prior /
+bijector values (``oracle/model.py``), lenstronomy's ``subgrid_kernel`` and ``phi_n`` (restated; the stand-in borrows the
+restatements), ``tf.linalg.pinv`` semantics, and ``lstsq_simulate``'s normal-equation tail -- the reference's
+``lstsq_simulate`` cannot execute as written in either substrate (``tf/simulator.py:183-203`` scatters into a zero-sized
+buffer), so only its inputs (component light, conv / pool) are pinned by (1).  DESIGN.md says the same.
 """
