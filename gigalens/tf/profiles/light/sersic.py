@@ -1,2 +1,2 @@
 """``src/gigalens/tf/profiles/light/sersic.py``."""
-from gigalens_b200.profiles.light.sersic import Sersic, SersicEllipse  # noqa: F401
+from gigalens_b200.profiles.light.sersic import CoreSersic, Sersic, SersicEllipse  # noqa: F401

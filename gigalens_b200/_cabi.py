@@ -7,12 +7,13 @@ CUDA device is present.
 import ctypes as C
 import os
 
-GL_MAX_PROFILE_PARAMS = 8
+GL_MAX_PROFILE_PARAMS = 10
+GL_ABI_VERSION = 2
 
 # gl_profile_type
 GL_EPL, GL_SHEAR, GL_SIE, GL_SIS, GL_NFW, GL_NFW_ELLIPSE, GL_DPIS, GL_DPIE = 1, 2, 3, 4, 5, 6, 7, 8
 GL_TNFW, GL_DPIEP = 9, 10
-GL_SERSIC, GL_SERSIC_ELLIPSE, GL_SHAPELETS = 32, 33, 34
+GL_SERSIC, GL_SERSIC_ELLIPSE, GL_SHAPELETS, GL_CORE_SERSIC = 32, 33, 34, 35
 GL_FLAG_USE_LSTSQ, GL_FLAG_INTERPOLATE = 1, 2
 GL_DIST_NORMAL, GL_DIST_LOGNORMAL, GL_DIST_UNIFORM, GL_DIST_TRUNCNORMAL = 0, 1, 2, 3
 
@@ -31,6 +32,7 @@ RAW_ORDER = {
     GL_SERSIC: ["R_sersic", "n_sersic", "center_x", "center_y", "Ie"],
     GL_SERSIC_ELLIPSE: ["R_sersic", "n_sersic", "e1", "e2", "center_x", "center_y", "Ie"],
     GL_SHAPELETS: ["beta", "center_x", "center_y"],
+    GL_CORE_SERSIC: ["R_sersic", "n_sersic", "Rb", "alpha", "gamma", "e1", "e2", "center_x", "center_y", "Ie"],
 }
 
 
@@ -125,6 +127,9 @@ def load():
     vp, fp, i32 = C.c_void_p, C.c_void_p, C.c_int32
     lib.gl_last_error.restype = C.c_char_p
     lib.gl_abi_version.restype = C.c_int32
+    if lib.gl_abi_version() != GL_ABI_VERSION:
+        raise RuntimeError(f"{path} has ABI version {lib.gl_abi_version()}, this binding needs {GL_ABI_VERSION}: rebuild it "
+                           "(`python -c 'import __graft_entry__ as g; g.build(force=True)'`)")
     lib.gl_launch_count.restype = C.c_int64
     lib.gl_plan_depth.restype = C.c_int32
     lib.gl_plan_depth.argtypes = [vp]

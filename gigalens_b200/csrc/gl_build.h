@@ -37,7 +37,7 @@ inline void gl_shapelets_table(int n_max, std::vector<float>& out) {
 inline int gl_shapelets_layers(int n_max) { return (n_max + 1) * (n_max + 2) / 2; }
 
 inline bool gl_is_mass(int t) { return t >= GLT_EPL && t <= GLT_DPIEP; }
-inline bool gl_is_light(int t) { return t == GLT_SERSIC || t == GLT_SERSIC_ELLIPSE || t == GLT_SHAPELETS; }
+inline bool gl_is_light(int t) { return t == GLT_SERSIC || t == GLT_SERSIC_ELLIPSE || t == GLT_SHAPELETS || t == GLT_CORE_SERSIC; }
 
 // Returns "" on success, else an error message.
 inline std::string gl_build_program(const gl_model_desc* m, GlBuilt& out, bool use_fwdmode = true) {
@@ -78,7 +78,7 @@ inline std::string gl_build_program(const gl_model_desc* m, GlBuilt& out, bool u
       if (pr.slot[k] >= m->n_params) return "profile " + std::to_string(i) + ": slot out of range";
     }
     // a light profile fitted by least squares has no amplitude parameter (profile.py:36-41)
-    if ((pr.flags & GL_FLAG_USE_LSTSQ) && (pr.type == GLT_SERSIC || pr.type == GLT_SERSIC_ELLIPSE)) {
+    if ((pr.flags & GL_FLAG_USE_LSTSQ) && (pr.type == GLT_SERSIC || pr.type == GLT_SERSIC_ELLIPSE || pr.type == GLT_CORE_SERSIC)) {
       pr.slot[nraw - 1] = -1; pr.constant[nraw - 1] = 1.f;
     }
     pr.member_off = (int)out.member_factor.size();

@@ -435,6 +435,7 @@ __global__ void k_patch_amps(GlProgram P, int bs, const float* __restrict__ coef
   for (int i = P.n_lens; i < P.n_prof; ++i) {
     const GlProf& pr = P.prof[i];
     if (pr.type == GLT_SERSIC || pr.type == GLT_SERSIC_ELLIPSE) der[pr.der_off + SER_IE] = c[pr.comp_off];
+    else if (pr.type == GLT_CORE_SERSIC) der[pr.der_off + CS_IE] = c[pr.comp_off];
     else if (pr.type == GLT_SHAPELETS) {
       const int L = shp_layers(pr.n_max);
       for (int k = 0; k < L; ++k) der[pr.der_off + shp_amp_off(pr.n_max) + k] = c[pr.comp_off + k];

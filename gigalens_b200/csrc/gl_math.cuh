@@ -270,7 +270,7 @@ template <class S> struct gl_scalar_of<GlDual<S>> { typedef S type; };
 enum {
   GLT_EPL = 1, GLT_SHEAR = 2, GLT_SIE = 3, GLT_SIS = 4, GLT_NFW = 5, GLT_NFW_ELLIPSE = 6, GLT_DPIS = 7, GLT_DPIE = 8,
   GLT_TNFW = 9, GLT_DPIEP = 10,
-  GLT_SERSIC = 32, GLT_SERSIC_ELLIPSE = 33, GLT_SHAPELETS = 34
+  GLT_SERSIC = 32, GLT_SERSIC_ELLIPSE = 33, GLT_SHAPELETS = 34, GLT_CORE_SERSIC = 35
 };
 
 // Feature bits: which profile families a kernel instantiation contains code for.  The per-pixel
@@ -279,20 +279,20 @@ enum {
 // adjoint or the Shapelets scratch arrays.  GLF_ALL is the generic interpreter.
 enum {
   GLF_EPL = 1, GLF_SHEAR = 2, GLF_SIE = 4, GLF_SIS = 8, GLF_NFW = 16, GLF_DPIS = 32, GLF_DPIE = 64, GLF_SERSIC = 128,
-  GLF_SHAPELETS = 256, GLF_TNFW = 512, GLF_DPIEP = 1024, GLF_ALL = 2047
+  GLF_SHAPELETS = 256, GLF_TNFW = 512, GLF_DPIEP = 1024, GLF_CORESERSIC = 2048, GLF_ALL = 4095
 };
 GL_HD unsigned gl_feature_of(int type) {
   switch (type) {
     case GLT_EPL: return GLF_EPL; case GLT_SHEAR: return GLF_SHEAR; case GLT_SIE: return GLF_SIE; case GLT_SIS: return GLF_SIS;
     case GLT_NFW: case GLT_NFW_ELLIPSE: return GLF_NFW; case GLT_DPIS: return GLF_DPIS; case GLT_DPIE: return GLF_DPIE;
     case GLT_SERSIC: case GLT_SERSIC_ELLIPSE: return GLF_SERSIC; case GLT_SHAPELETS: return GLF_SHAPELETS;
-    case GLT_TNFW: return GLF_TNFW; case GLT_DPIEP: return GLF_DPIEP;
+    case GLT_TNFW: return GLF_TNFW; case GLT_DPIEP: return GLF_DPIEP; case GLT_CORE_SERSIC: return GLF_CORESERSIC;
   }
   return 0;
 }
 
-#define GL_MAX_DVARS 8      // accumulators per profile in the pixel adjoint
-#define GL_MAX_RAW 8
+#define GL_MAX_DVARS 8      // accumulators per profile in the pixel adjoint (CORE_SERSIC flushes its 9th, Ie, separately)
+#define GL_MAX_RAW 10       // == GL_MAX_PROFILE_PARAMS of include/gigalens_b200.h (CORE_SERSIC has 10 raw parameters)
 
 // ---------------------------------------------------------------------------------------------
 // ellipticity (e1, e2) -> (phi, q) and its adjoint  
@@ -1728,6 +1728,103 @@ GL_HD void sersic_bwd(const typename gl_scalar_of<V>::type* d, const V* x, const
 }
 
 // =============================================================================================
+// CORE_SERSIC  (tf/profiles/light/sersic.py:83-132), the formula AS WRITTEN there:
+//   I = Ie (1 + (Rb/R)^alpha)^(gamma/alpha) exp(-bn (R^alpha + Rb^alpha) / (R_sersic^alpha alpha n) - 1)
+//   -- `R_sersic ** alpha ** 1.0` is R_sersic^alpha, 1/(alpha n) is a divisor rather than an exponent and the -1 sits
+//   outside the bn product (SURVEY App. B7 reads this as a slip of the reference; parity means reproducing it, and the
+//   golden vectors of tests/golden/reference_golden.npz come from executing exactly that code).
+//   raw  : R_sersic, n_sersic, Rb, alpha, gamma, e1, e2, cx, cy, Ie      (Ie == 1 under use_lstsq, :117)
+//   d[]  : cx, cy, cos, sin, sq, isq, alpha, goa = gamma/alpha, Rba = Rb^alpha, K = bn / (R_sersic^alpha alpha n), Ie
+//   dvars: cx, cy, phi, sq, alpha (through R^alpha only), goa, Rba, K  |  Ie (a 9th accumulator, flushed on its own)
+// Only the generic interpreter instantiates it (float lanes and the fp64 host harness): libm log / exp, no fast paths.
+// =============================================================================================
+enum { CS_CX = 0, CS_CY, CS_C, CS_S, CS_SQ, CS_ISQ, CS_AL, CS_GOA, CS_RBA, CS_K, CS_IE, CS_SIZE = 12 };
+enum { CSG_CX = 0, CSG_CY, CSG_PHI, CSG_SQ, CSG_AL, CSG_GOA, CSG_RBA, CSG_K, CSG_IE };
+template <class T>
+GL_HD void core_sersic_prep(const T* raw, T* d, bool use_lstsq) {
+  const T Rs = raw[0], n = raw[1], Rb = raw[2], al = raw[3], ga = raw[4];
+  T phi, q, c;
+  ellip_fwd(raw[5], raw[6], T(0.9999), phi, q, c);
+  d[CS_C] = gl_cos(phi); d[CS_S] = gl_sin(phi);
+  d[CS_SQ] = gl_sqrt(q); d[CS_ISQ] = T(1) / gl_sqrt(q);
+  d[CS_CX] = raw[7]; d[CS_CY] = raw[8];
+  d[CS_AL] = al; d[CS_GOA] = ga / al;
+  d[CS_RBA] = gl_pow(Rb, al);
+  const T bn = T(1.9992) * n - T(0.3271);
+  d[CS_K] = bn / (gl_pow(Rs, al) * al * n);
+  d[CS_IE] = use_lstsq ? T(1) : raw[9];
+  d[11] = T(0);
+}
+template <class T>
+GL_HD void core_sersic_prep_bwd(const T* raw, const T* d, const T* g, T* graw, bool use_lstsq) {
+  const T Rs = raw[0], n = raw[1], Rb = raw[2], al = raw[3], ga = raw[4];
+  const T K = d[CS_K], Rba = d[CS_RBA];
+  const T rsa = gl_pow(Rs, al);
+  graw[0] = -g[CSG_K] * K * al / Rs;
+  graw[1] = g[CSG_K] * (T(1.9992) / (rsa * al * n) - K / n);
+  graw[2] = g[CSG_RBA] * al * Rba / Rb;
+  graw[3] = g[CSG_AL] - g[CSG_GOA] * ga / (al * al) + g[CSG_RBA] * Rba * gl_log(Rb) - g[CSG_K] * K * (gl_log(Rs) + T(1) / al);
+  graw[4] = g[CSG_GOA] / al;
+  const T gq = g[CSG_SQ] / (T(2) * d[CS_SQ]);
+  ellip_bwd(raw[5], raw[6], T(0.9999), g[CSG_PHI], gq, graw[5], graw[6]);
+  graw[7] = g[CSG_CX]; graw[8] = g[CSG_CY];
+  graw[9] = use_lstsq ? T(0) : g[CSG_IE];
+}
+template <class V, int NP>
+GL_HD void core_sersic_fwd(const typename gl_scalar_of<V>::type* d, const V* x, const V* y, V* out) {
+  typedef typename gl_scalar_of<V>::type S;
+  const V c = V(d[CS_C]), s = V(d[CS_S]), cx = V(d[CS_CX]), cy = V(d[CS_CY]), sq = V(d[CS_SQ]), isq = V(d[CS_ISQ]);
+  const V hal = V(S(0.5) * d[CS_AL]), goa = V(d[CS_GOA]), rba = V(d[CS_RBA]), K = V(d[CS_K]), ie = V(d[CS_IE]);
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    V dx = x[j] - cx, dy = y[j] - cy;
+    V xt1 = gl_fma(c, dx, s * dy) * sq;
+    V xt2 = gl_fma(c, dy, -(s * dx)) * isq;
+    V r2 = gl_fma(xt1, xt1, xt2 * xt2);
+    V Ra = gl_exp(hal * gl_log(r2));                       // R^alpha
+    V A = gl_exp(goa * gl_log(V(S(1)) + rba / Ra));        // (1 + (Rb/R)^alpha)^(gamma/alpha)
+    out[j] = gl_fma(ie * A, gl_exp(-(K * (Ra + rba)) - V(S(1))), out[j]);
+  }
+}
+// gI: cotangent of the surface brightness; g: the 8 dvars above; gIe: += cotangent of Ie.
+template <class V, int NP>
+GL_HD void core_sersic_bwd(const typename gl_scalar_of<V>::type* d, const V* x, const V* y, const V* gI, V* g, V* gIe, V* gx, V* gy) {
+  typedef typename gl_scalar_of<V>::type S;
+  const V c = V(d[CS_C]), s = V(d[CS_S]), cx = V(d[CS_CX]), cy = V(d[CS_CY]), sq = V(d[CS_SQ]), isq = V(d[CS_ISQ]);
+  const V al = V(d[CS_AL]), hal = V(S(0.5) * d[CS_AL]), goa = V(d[CS_GOA]), rba = V(d[CS_RBA]), K = V(d[CS_K]), ie = V(d[CS_IE]);
+  const V isq2 = isq * isq;
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    V dx = x[j] - cx, dy = y[j] - cy;
+    V xr = gl_fma(c, dx, s * dy), yr = gl_fma(c, dy, -(s * dx));
+    V xt1 = xr * sq, xt2 = yr * isq;
+    V r2 = gl_fma(xt1, xt1, xt2 * xt2);
+    V lr2 = gl_log(r2);
+    V Ra = gl_exp(hal * lr2);
+    V t = rba / Ra;
+    V l1t = gl_log(V(S(1)) + t);
+    V AE = gl_exp(goa * l1t) * gl_exp(-(K * (Ra + rba)) - V(S(1)));
+    gIe[0] += gI[j] * AE;
+    V garg = gI[j] * ie * AE;                               // cotangent of ln I
+    // R = 0: the reference's value is inf / NaN there (measure zero); contributes 0 here, like sersic_bwd
+    V inv1t = V(S(1)) / (V(S(1)) + t);
+    g[CSG_GOA] += gl_where_gt(r2, S(0), garg * l1t, V(S(0)));
+    g[CSG_K] -= gl_where_gt(r2, S(0), garg * (Ra + rba), V(S(0)));
+    g[CSG_RBA] += gl_where_gt(r2, S(0), garg * (goa * inv1t / Ra - K), V(S(0)));
+    V gRa = gl_where_gt(r2, S(0), -garg * (goa * t * inv1t / Ra + K), V(S(0)));     // d lnI / d Ra, times garg
+    g[CSG_AL] += gl_where_gt(r2, S(0), gRa * Ra * V(S(0.5)) * lr2, V(S(0)));
+    V gr2 = gl_where_gt(r2, S(0), gRa * Ra * al / r2, V(S(0)));                     // 2 d/d(r2): gxt = gr2 * xt
+    V gxt1 = gr2 * xt1, gxt2 = gr2 * xt2;
+    g[CSG_SQ] += gl_fma(gxt1, xr, -(gxt2 * yr * isq2));
+    V gxr = gxt1 * sq, gyr = gxt2 * isq;
+    g[CSG_PHI] += gl_fma(gxr, yr, -(gyr * xr));
+    V gdx = gl_fma(gxr, c, -(gyr * s)), gdy = gl_fma(gxr, s, gyr * c);
+    g[CSG_CX] -= gdx; g[CSG_CY] -= gdy;
+    if (gx) { gx[j] += gdx; gy[j] += gdy; }
+  }
+}
+
+// =============================================================================================
 // SHAPELETS  (tf/profiles/light/shapelets.py:20-85)
 //   raw  : beta, center_x, center_y  (+ n_layers amplitudes, staged separately)
 //   d[]  : cx, cy, 1/beta, n_max, then tables c1[n], c2[n], c3[n] (n = 0..n_max) of the normalised
@@ -1879,7 +1976,7 @@ GL_HD int gl_n_raw(int type) {
     case GLT_EPL: return 6; case GLT_SHEAR: return 2; case GLT_SIE: return 5; case GLT_SIS: return 3;
     case GLT_NFW: return 4; case GLT_NFW_ELLIPSE: return 6; case GLT_DPIS: return 5; case GLT_DPIE: return 7;
     case GLT_SERSIC: return 5; case GLT_SERSIC_ELLIPSE: return 7; case GLT_SHAPELETS: return 3;
-    case GLT_TNFW: return 5; case GLT_DPIEP: return 7;
+    case GLT_TNFW: return 5; case GLT_DPIEP: return 7; case GLT_CORE_SERSIC: return 10;
   }
   return 0;
 }
@@ -1888,7 +1985,7 @@ GL_HD int gl_n_dvars(int type) {
     case GLT_EPL: return 8; case GLT_SHEAR: return 2; case GLT_SIE: return 6; case GLT_SIS: return 3;
     case GLT_NFW: case GLT_NFW_ELLIPSE: return 7; case GLT_DPIS: case GLT_DPIE: return 7;
     case GLT_SERSIC: case GLT_SERSIC_ELLIPSE: return 8; case GLT_SHAPELETS: return 3;   // + n_layers amplitudes without use_lstsq
-    case GLT_TNFW: return 5; case GLT_DPIEP: return 8;
+    case GLT_TNFW: return 5; case GLT_DPIEP: return 8; case GLT_CORE_SERSIC: return 9;
   }
   return 0;
 }
@@ -1897,7 +1994,7 @@ GL_HD int gl_der_size(int type, int niter, int nmax) {
     case GLT_EPL: return epl_der_size(niter); case GLT_SHEAR: return 4; case GLT_SIE: return SIE_SIZE; case GLT_SIS: return 4;
     case GLT_NFW: case GLT_NFW_ELLIPSE: return NFW_SIZE; case GLT_DPIS: case GLT_DPIE: return DP_SIZE;
     case GLT_SERSIC: case GLT_SERSIC_ELLIPSE: return SER_SIZE; case GLT_SHAPELETS: return shp_der_size(nmax);
-    case GLT_TNFW: return TNFW_SIZE; case GLT_DPIEP: return PP_SIZE;
+    case GLT_TNFW: return TNFW_SIZE; case GLT_DPIEP: return PP_SIZE; case GLT_CORE_SERSIC: return CS_SIZE;
   }
   return 0;
 }
@@ -1918,6 +2015,7 @@ GL_HD void gl_prep(int type, unsigned flags, int niter, const T* raw, T* d, T ep
     case GLT_DPIEP: dpiep_prep(raw, d); break;
     case GLT_SERSIC: sersic_prep(raw, d, false, (flags & 1u) != 0); break;
     case GLT_SERSIC_ELLIPSE: sersic_prep(raw, d, true, (flags & 1u) != 0); break;
+    case GLT_CORE_SERSIC: core_sersic_prep(raw, d, (flags & 1u) != 0); break;
     default: break;
   }
 }
@@ -1936,6 +2034,7 @@ GL_HD void gl_prep_bwd(int type, unsigned flags, const T* raw, const T* d, const
     case GLT_DPIEP: dpiep_prep_bwd(raw, d, g, graw); break;
     case GLT_SERSIC: sersic_prep_bwd(raw, d, g, graw, false, (flags & 1u) != 0); break;
     case GLT_SERSIC_ELLIPSE: sersic_prep_bwd(raw, d, g, graw, true, (flags & 1u) != 0); break;
+    case GLT_CORE_SERSIC: core_sersic_prep_bwd(raw, d, g, graw, (flags & 1u) != 0); break;
     default: break;
   }
 }

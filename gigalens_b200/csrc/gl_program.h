@@ -274,6 +274,9 @@ GL_HD void gl_pix_image(const GlProgram& P, const typename gl_scalar_of<T>::type
       case GLT_SERSIC: case GLT_SERSIC_ELLIPSE:
         if constexpr ((F & GLF_SERSIC) != 0) sersic_fwd<T, NP>(der + pr.der_off, px, py, out);
         break;
+      case GLT_CORE_SERSIC:
+        if constexpr ((F & GLF_CORESERSIC) != 0) core_sersic_fwd<T, NP>(der + pr.der_off, px, py, out);
+        break;
       case GLT_SHAPELETS:
         if constexpr ((F & GLF_SHAPELETS) != 0)
         for (int j = 0; j < NP; ++j)
@@ -318,6 +321,12 @@ GL_HD int gl_point_components(const GlProgram& P, const T* der, T x, T y, T bx, 
       case GLT_SERSIC: case GLT_SERSIC_ELLIPSE: if constexpr ((F & GLF_SERSIC) != 0) {
         T v[1] = {T(0)}, xx[1] = {px}, yy[1] = {py};
         sersic_fwd<T, 1>(der + pr.der_off, xx, yy, v);
+        if (keep && gl_isnan(v[0])) ++n_nan;
+        out[pr.comp_off * stride] = (keep && !gl_isnan(v[0])) ? v[0] : T(0);
+      } break;
+      case GLT_CORE_SERSIC: if constexpr ((F & GLF_CORESERSIC) != 0) {
+        T v[1] = {T(0)}, xx[1] = {px}, yy[1] = {py};
+        core_sersic_fwd<T, 1>(der + pr.der_off, xx, yy, v);
         if (keep && gl_isnan(v[0])) ++n_nan;
         out[pr.comp_off * stride] = (keep && !gl_isnan(v[0])) ? v[0] : T(0);
       } break;
@@ -386,6 +395,8 @@ GL_HD void gl_pix_image_bwd(const GlProgram& P, const typename gl_scalar_of<T>::
           for (int j = 0; j < NP; ++j)
             v[j] = shp_point<T>(der + pr.der_off, pr.table, (pr.flags & 2u) != 0, pr.n_max, src ? bx[j] : x[j], src ? by[j] : y[j],
                                 (T*)nullptr, 0, (const T*)nullptr, (T*)nullptr, (T*)nullptr, (T*)nullptr, (T*)nullptr);
+      } else if (pr.type == GLT_CORE_SERSIC) {
+        if constexpr ((F & GLF_CORESERSIC) != 0) core_sersic_fwd<T, NP>(der + pr.der_off, src ? bx : x, src ? by : y, v);
       } else {
         if constexpr ((F & GLF_SERSIC) != 0) sersic_fwd<T, NP>(der + pr.der_off, src ? bx : x, src ? by : y, v);
       }
@@ -400,6 +411,14 @@ GL_HD void gl_pix_image_bwd(const GlProgram& P, const typename gl_scalar_of<T>::
           else sersic_bwd<T, NP>(der + pr.der_off, x, y, gS, acc, (T*)nullptr, (T*)nullptr);
         }
         break;
+      case GLT_CORE_SERSIC: if constexpr ((F & GLF_CORESERSIC) != 0) {
+        T a9[GL_MAX_DVARS];      // the 9th dvar (Ie) travels in its own flush
+#pragma unroll
+        for (int k = 0; k < GL_MAX_DVARS; ++k) a9[k] = T(0);
+        if (src) core_sersic_bwd<T, NP>(der + pr.der_off, bx, by, gS, acc, a9, Gx, Gy);
+        else core_sersic_bwd<T, NP>(der + pr.der_off, x, y, gS, acc, a9, (T*)nullptr, (T*)nullptr);
+        flush(a9, 1, pr.g_off + CSG_IE);
+      } break;
       case GLT_SHAPELETS: if constexpr ((F & GLF_SHAPELETS) != 0) {
         const bool want_amp = !(pr.flags & 1u);
         const int L = shp_layers(pr.n_max);
@@ -420,7 +439,7 @@ GL_HD void gl_pix_image_bwd(const GlProgram& P, const typename gl_scalar_of<T>::
       } break;
       default: break;
     }
-    flush(acc, pr.type == GLT_SHAPELETS ? 3 : pr.n_dvars, pr.g_off);
+    flush(acc, pr.type == GLT_SHAPELETS ? 3 : (pr.n_dvars < GL_MAX_DVARS ? pr.n_dvars : GL_MAX_DVARS), pr.g_off);
   }
   if (no_deflection) return;
   // d(beta)/d(lens) = -d(alpha): cotangent of each deflection is (-Gx, -Gy)

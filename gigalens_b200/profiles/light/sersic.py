@@ -21,3 +21,14 @@ class SersicEllipse(Sersic):
     _params = ["R_sersic", "n_sersic", "e1", "e2", "center_x", "center_y"]
     _amp = "Ie"
     _type_id = _cabi.GL_SERSIC_ELLIPSE
+
+
+class CoreSersic(Sersic):
+    """Core-Sersic (reference ``tf/profiles/light/sersic.py:83-132``), evaluated exactly as the reference writes it:
+    ``Ie (1 + (Rb/R)^alpha)^(gamma/alpha) exp(-bn (R^alpha + Rb^alpha) / (R_sersic^alpha alpha n_sersic) - 1)``
+    with ``bn = 1.9992 n_sersic - 0.3271`` and ``R`` the elliptical distance of ``Sersic.distance``."""
+
+    _name = "CORE_SERSIC"
+    _params = ["R_sersic", "n_sersic", "Rb", "alpha", "gamma", "e1", "e2", "center_x", "center_y"]
+    _amp = "Ie"
+    _type_id = _cabi.GL_CORE_SERSIC

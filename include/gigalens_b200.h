@@ -30,8 +30,8 @@
 extern "C" {
 #endif
 
-#define GL_ABI_VERSION 1
-#define GL_MAX_PROFILE_PARAMS 8
+#define GL_ABI_VERSION 2           /* 2: GL_MAX_PROFILE_PARAMS 8 -> 10 (gl_profile_desc layout), GL_CORE_SERSIC, gl_eval_points mode 3 */
+#define GL_MAX_PROFILE_PARAMS 10
 
 /* Profile type ids.  The raw-parameter order of each type is fixed here and mirrors the
  * keyword names of the reference's `deriv` / `light`. */
@@ -48,7 +48,9 @@ typedef enum {
   GL_DPIEP = 10,       /* theta_E, Ra, Rs, e1, e2, center_x, center_y     tf/profiles/mass/piep.py:17-56 */
   GL_SERSIC = 32,          /* R_sersic, n_sersic, center_x, center_y, Ie          tf/profiles/light/sersic.py:22-35 */
   GL_SERSIC_ELLIPSE = 33,  /* R_sersic, n_sersic, e1, e2, center_x, center_y, Ie  tf/profiles/light/sersic.py:67-80 */
-  GL_SHAPELETS = 34        /* beta, center_x, center_y (+ amplitudes)              tf/profiles/light/shapelets.py:17-75 */
+  GL_SHAPELETS = 34,       /* beta, center_x, center_y (+ amplitudes)              tf/profiles/light/shapelets.py:17-75 */
+  GL_CORE_SERSIC = 35      /* R_sersic, n_sersic, Rb, alpha, gamma, e1, e2, center_x, center_y, Ie   tf/profiles/light/sersic.py:83-132
+                            * (the formula exactly as written there, see gl_math.cuh) */
 } gl_profile_type;
 
 #define GL_FLAG_USE_LSTSQ 1u   /* LightProfile.use_lstsq  (src/gigalens/profile.py:36-41) */

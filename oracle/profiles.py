@@ -572,6 +572,23 @@ class SersicEllipse(Sersic):
         return ret[None, ...] if self.use_lstsq else ret
 
 
+class CoreSersic(Sersic):
+    """``tf/profiles/light/sersic.py:83-132``, the expression exactly as written there (``R_sersic ** alpha ** 1.0`` is
+    ``R_sersic^alpha``; the ``1/(alpha n)`` divides and the ``- 1.0`` sits outside the ``bn`` product -- SURVEY App. B7)."""
+
+    name = "CORE_SERSIC"
+    params = ["R_sersic", "n_sersic", "Rb", "alpha", "gamma", "e1", "e2", "center_x", "center_y"]
+
+    def light(self, x, y, R_sersic, n_sersic, Rb, alpha, gamma, e1, e2, center_x, center_y, Ie=None):
+        R_sersic, n_sersic, Rb, alpha, gamma = (_t(v, x) for v in (R_sersic, n_sersic, Rb, alpha, gamma))
+        Ie = torch.ones_like(R_sersic) if self.use_lstsq else _t(Ie, x)
+        R = _sersic_distance(x, y, _t(center_x, x), _t(center_y, x), _t(e1, x), _t(e2, x))
+        bn = 1.9992 * n_sersic - 0.3271
+        ret = (Ie * (1 + (Rb / R) ** alpha) ** (gamma / alpha)
+               * torch.exp(-bn * ((R ** alpha + Rb ** alpha) / R_sersic ** alpha ** 1.0 / (alpha * n_sersic)) - 1.0))
+        return ret[None, ...] if self.use_lstsq else ret
+
+
 def shapelet_phi_n_np(n, x):
     """lenstronomy ``Shapelets.phi_n`` (restated from its published definition; the source is
     not available offline -> parity unpinned): H_n(x) exp(-x^2/2) / sqrt(2^n sqrt(pi) n!)."""

@@ -30,6 +30,7 @@ def to_oracle_profile(p, dtype=torch.float32):
         gl_nfw.NFW: OP.NFW, gl_nfw.NFW_ELLIPSE: OP.NFW_ELLIPSE, gl_piemd.DPIS: OP.DPIS, gl_piemd.DPIE: OP.DPIE,
         gl_tnfw.TNFW: OP.TNFW, gl_piep.DPIEP: OP.DPIEP,
         gl_sersic.SersicEllipse: lambda: OP.SersicEllipse(p.use_lstsq), gl_sersic.Sersic: lambda: OP.Sersic(p.use_lstsq),
+        gl_sersic.CoreSersic: lambda: OP.CoreSersic(p.use_lstsq),
         gl_shapelets.Shapelets: lambda: OP.Shapelets(p.n_max, p.use_lstsq, p.interpolate, dtype=dtype),
     }
     return table[type(p)]()
@@ -51,6 +52,7 @@ RANGES = {  # generic, well-conditioned draws per parameter name
     "Rs": (0.5, 3.0), "alpha_Rs": (0.5, 2.0), "r_core": (0.02, 0.2), "r_cut": (1.0, 6.0),
     "r_trunc": (2.0, 8.0), "Ra": (0.02, 0.2),
     "R_sersic": (0.3, 1.2), "n_sersic": (0.8, 5.0), "Ie": (20.0, 300.0), "beta": (0.08, 0.2),
+    "Rb": (0.05, 0.3), "alpha": (1.0, 3.0), "gamma": (1.6, 2.4),
 }
 
 
@@ -244,7 +246,7 @@ def spec_profile(cls, ctor):
     table = {"EPL": gl_epl.EPL, "Shear": gl_shear.Shear, "SIE": gl_sie.SIE, "SIS": gl_sis.SIS, "NFW": gl_nfw.NFW,
              "NFW_ELLIPSE": gl_nfw.NFW_ELLIPSE, "DPIS": gl_piemd.DPIS, "DPIE": gl_piemd.DPIE, "TNFW": gl_tnfw.TNFW,
              "DPIEP": gl_piep.DPIEP, "DPIESubhalo": gl_sub.DPIESubhalo, "Sersic": gl_sersic.Sersic,
-             "SersicEllipse": gl_sersic.SersicEllipse, "Shapelets": gl_shapelets.Shapelets}
+             "SersicEllipse": gl_sersic.SersicEllipse, "CoreSersic": gl_sersic.CoreSersic, "Shapelets": gl_shapelets.Shapelets}
     return table[cls](**ctor)
 
 

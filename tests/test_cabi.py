@@ -28,12 +28,12 @@ def test_header_and_binding_agree(lib):
     assert declared == set(_cabi.EXPORTED_SYMBOLS), declared ^ set(_cabi.EXPORTED_SYMBOLS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.gl_abi_version() == 1
+    assert lib.gl_abi_version() == 2
 
 
 def test_struct_layout_matches_header():
     # field order/sizes of the ctypes mirrors (a mismatch would silently corrupt plans)
-    assert C.sizeof(_cabi.ProfileDesc) == 4 + 4 + 32 + 32 + 4 + 4 + 8 + 4 + 4 + 8
+    assert C.sizeof(_cabi.ProfileDesc) == 4 + 4 + 40 + 40 + 4 + 4 + 8 + 4 + 4 + 8   # GL_MAX_PROFILE_PARAMS = 10 (ABI version 2)
     assert C.sizeof(_cabi.PriorLeaf) == 24
     assert C.sizeof(_cabi.LikeConfig) == 24
 

@@ -218,6 +218,79 @@ def test_mass_profiles_small_grid(case, ss, use_psf):
         assert_parity(g[k], g32[k], g64[k], 1e-4, f"grad {cm.slot_keys[k]}", g64p[k])
 
 
+@pytest.mark.parametrize("ss,use_psf", [(1, False), (2, True)])
+def test_core_sersic_light_through_the_pipeline(ss, use_psf):
+    """CoreSersic (tf/profiles/light/sersic.py:83-132, the expression as the reference writes it) as lens light and as
+    lensed source: image, log-likelihood and every gradient row against the oracle (which tests/test_reference_golden.py
+    ties to the executed reference)."""
+    n, bs = 20, 4
+    pm = PhysicalModel([epl.EPL(30), shear.Shear()], [sersic.CoreSersic()], [sersic.CoreSersic()])
+    rng = np.random.default_rng(17)
+    mask = (rng.uniform(size=(n, n)) > 0.1).astype(np.float32)
+    sc = SimulatorConfig(delta_pix=0.15, num_pix=n, supersample=ss, kernel=workloads.load_psf()[3:10, 3:10] if use_psf else None,
+                         pix_region=mask)
+    obs = rng.normal(0, 1, size=(n, n)).astype(np.float32) + 5
+    emap = rng.uniform(0.5, 1.5, size=(n, n)).astype(np.float32)
+    sim = LensSimulator(pm, sc, bs=bs)
+    cm = sim.compiled
+    assert cm.n_params == 6 + 2 + 10 + 10
+    mat = common.draw_matrix(cm, bs, seed=23).astype(np.float32)
+    pmod = ForwardProbModel({"lens_mass": []}, obs, error_map=emap)
+    dev = torch.as_tensor(mat, device="cuda")
+    ll, chi2, g = (t.cpu().numpy() for t in pmod.loglike_and_grad(sim, dev))
+    img = sim.simulate(dev).cpu().numpy()
+
+    def oracle(m, dt):
+        osim = OracleSimulator(common.to_oracle_model(pm, dt), sc.delta_pix, n, ss, kernel=sc.kernel, pix_region=mask, bs=bs, dtype=dt)
+        opm = OM.ForwardProbModel(OM.JointPrior({}), obs, error_map=emap, dtype=dt)
+        params, leaf = common.matrix_to_pytree(cm, m, dt, requires_grad=True)
+        im = osim.simulate(params)
+        rll, _ = opm.stats_pixels_from_image(im, osim.img_region)
+        rll.sum().backward()
+        return im.detach().numpy(), rll.detach().numpy(), leaf.grad.numpy()
+
+    im32, ll32, g32 = oracle(mat.astype(np.float64), torch.float32)
+    im64, ll64, g64 = oracle(mat.astype(np.float64), torch.float64)
+    im64p, ll64p, g64p = oracle(common.ulp_perturb(mat), torch.float64)
+    assert_parity(img, im32, im64, 1e-5, "image", im64p, axis=(1, 2))
+    assert_parity(ll[:, None], ll32[:, None], ll64[:, None], 1e-5, "log-like", ll64p[:, None], axis=1)
+    for k in range(cm.n_params):
+        assert_parity(g[k], g32[k], g64[k], 1e-4, f"grad {cm.slot_keys[k]}", g64p[k])
+
+
+def test_core_sersic_as_a_linear_component_of_lstsq_simulate():
+    """CoreSersic(use_lstsq=True) next to a Shapelets source in lstsq_simulate: stack, coefficients and image vs the oracle."""
+    n, bs = 24, 3
+    pm = PhysicalModel([sie.SIE()], [sersic.CoreSersic(use_lstsq=True)], [shapelets.Shapelets(3, use_lstsq=True, interpolate=False)])
+    sc = SimulatorConfig(delta_pix=0.1, num_pix=n, supersample=2, kernel=workloads.load_psf()[4:9, 4:9])
+    sim = LensSimulator(pm, sc, bs=bs)
+    cm = sim.compiled
+    mat = common.draw_matrix(cm, bs, seed=29).astype(np.float32)
+    rng = np.random.default_rng(31)
+    obs = (np.abs(rng.normal(0, 1, size=(n, n))) * 3 + 1).astype(np.float32)
+    err = np.sqrt(0.2 ** 2 + obs / 100.0).astype(np.float32)
+    params = cm.unflatten(torch.as_tensor(mat, device="cuda"))
+    stack = sim.lstsq_simulate(params, obs, err, return_stacked=True).cpu().numpy()
+    coef = sim.lstsq_simulate(params, obs, err, return_coeffs=True).cpu().numpy()
+    img = sim.lstsq_simulate(params, obs, err).cpu().numpy().reshape(bs, n, n)
+
+    def oracle(m, dt):
+        osim = OracleSimulator(common.to_oracle_model(pm, dt), sc.delta_pix, n, 2, kernel=sc.kernel, bs=bs, dtype=dt)
+        p, _ = common.matrix_to_pytree(cm, m, dt)
+        o, e = torch.as_tensor(obs).to(dt), torch.as_tensor(err).to(dt)
+        with torch.no_grad():
+            return (osim.lstsq_simulate(p, o, e, return_stacked=True).numpy(), osim.lstsq_simulate(p, o, e, return_coeffs=True).numpy(),
+                    osim.lstsq_simulate(p, o, e).numpy().reshape(bs, n, n))
+
+    s32, c32, i32 = oracle(mat.astype(np.float64), torch.float32)
+    s64, c64, i64 = oracle(mat.astype(np.float64), torch.float64)
+    s64p, c64p, i64p = oracle(common.ulp_perturb(mat), torch.float64)
+    assert stack.shape == s64.shape, (stack.shape, s64.shape)
+    assert_parity(stack, s32, s64, 1e-5, "lstsq stack", s64p, axis=(1, 2, 3))
+    assert_parity(img, i32, i64, 1e-5, "lstsq image", i64p, axis=(1, 2))
+    assert_parity(coef, c32, c64, 1e-4, "lstsq coefficients", c64p, axis=1)
+
+
 def test_profile_point_evaluation_mirrors_reference_profile_tests():
     """The reference's profile tests call deriv/light on random points (tests/test_profiles.py); the
     same calls here run on the GPU and must match the oracle and the framework-free KATs."""

@@ -20,7 +20,7 @@ def _pts(c):
     return c["x"][:, 0].astype(np.float32), c["y"][:, 0].astype(np.float32)
 
 
-@pytest.mark.parametrize("key", sorted(k for k, c in R.PROFILE_CASES.items() if c["cls"] != "CoreSersic"))
+@pytest.mark.parametrize("key", sorted(R.PROFILE_CASES))
 def test_cuda_profiles_match_the_executed_reference(key):
     c = R.PROFILE_CASES[key]
     prof = common.spec_profile(c["cls"], c["ctor"])

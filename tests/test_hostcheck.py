@@ -41,6 +41,8 @@ MODELS = {
     "shapelets": lambda: PhysicalModel([epl.EPL(30), shear.Shear()], [sersic.Sersic()], [shapelets.Shapelets(4, interpolate=False)]),
     "shapelets_interp": lambda: PhysicalModel([sis.SIS()], [], [shapelets.Shapelets(5, interpolate=True)]),
     "cluster": lambda: PhysicalModel([nfw.NFW(), dpie_subhalo.DPIESubhalo(1.0, _catalogue()), shear.Shear()], [], SRC()),
+    # the reference's core-Sersic expression as written (sersic.py:83-132), as lens light and as source (10 raw parameters, 9 dvars)
+    "core_sersic": lambda: PhysicalModel([sis.SIS(), shear.Shear()], [sersic.CoreSersic()], [sersic.CoreSersic()]),
 }
 
 

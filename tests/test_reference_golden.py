@@ -52,7 +52,7 @@ PROFILE_CASES = RC.profile_cases()
 
 
 @pytest.mark.parametrize("tag", ["f32", "f64"])
-@pytest.mark.parametrize("key", sorted(k for k, c in PROFILE_CASES.items() if c["cls"] != "CoreSersic"))
+@pytest.mark.parametrize("key", sorted(PROFILE_CASES))
 def test_oracle_profiles_match_the_executed_reference(key, tag):
     c = PROFILE_CASES[key]
     dt = DT[tag]
