@@ -11,7 +11,9 @@ Each case runs twice: with ``tf.float32`` = float32 (the reference's arithmetic)
 Not covered: ``lstsq_simulate`` (``tf/simulator.py:158-240``) cannot execute as written -- it scatters the component values
 into a buffer whose leading dimension is 0 (``:183-203``; a real TensorFlow raises the same out-of-range error the stand-in
 does) and the JAX variant concatenates 3-D components onto a 4-D buffer -- so the normal-equation / pinv tail stays restated in
-the oracle (its inputs, the per-component light and the conv / pool, are pinned here); and the TFP prior / bijector arithmetic.
+the oracle -- its inputs, the per-component light and the conv / pool, are pinned here, and the tail itself (weights, normal
+equations, ``pinv(rcond=1e-6)``, recombination: ``:231-240``) is executed from the reference file's source lines on the oracle's
+component stack (``run_lstsq_tail``); and the TFP prior / bijector arithmetic.
 
     python tests/golden/make_reference_golden.py [out.npz]       (needs /root/reference; writes tests/golden/reference_golden.npz)
 
@@ -178,6 +180,39 @@ def run_simulators(out, tag, dtype, psf, demo):
             out[f"{pre}/pos_grad"] = np.stack([N(torch.zeros(bs, dtype=dtype) if v is None else v) for v in gp])
 
 
+def run_lstsq_tail(out, tag, dtype, psf):
+    """Execute the source lines of the reference's ``lstsq_simulate`` from ``W = (1 / err_map)...`` to its end
+    (``tf/simulator.py:231-240``) -- read from the reference file at run time -- on the oracle's component stack."""
+    import inspect
+    import textwrap
+    from types import SimpleNamespace
+
+    from oracle import profiles as OP
+    from oracle.simulator import OracleSimulator
+
+    src = inspect.getsource(ref_sim.LensSimulator.lstsq_simulate)
+    tail = textwrap.dedent(src[src.index("        W = (1 / err_map)"):])
+    ns = {"tf": tf}
+    exec("def lstsq_tail(self, ret, observed_image, err_map, return_coeffs):\n" + textwrap.indent(tail, "    "), ns)
+    tf.set_float(dtype)
+    c = RC.lstsq_tail_case(psf)
+    mk = {"EPL": lambda k: OP.EPL(**k), "Shear": lambda k: OP.Shear(), "SersicEllipse": lambda k: OP.SersicEllipse(**k),
+          "Shapelets": lambda k: OP.Shapelets(k["n_max"], k["use_lstsq"], k["interpolate"], dtype=dtype)}
+    m = c["model"]
+    om = SimpleNamespace(lenses=[mk[a](k) for a, k in m["lens_mass"]], lens_light=[mk[a](k) for a, k in m["lens_light"]],
+                         source_light=[mk[a](k) for a, k in m["source_light"]], lenses_constants=[{}, {}], lens_light_constants=[{}],
+                         source_light_constants=[{}])
+    s = c["sim"]
+    bs = 2
+    osim = OracleSimulator(om, s["delta_pix"], s["num_pix"], s["supersample"], kernel=s["kernel"], bs=bs, dtype=dtype)
+    params = {g: [{k: T(v, dtype) for k, v in d.items()} for d in c["params"][g]] for g in c["params"]}
+    stack = osim.lstsq_stack(params)
+    me = SimpleNamespace(bs=bs, depth=stack.shape[-1])
+    obs, err = T(c["observed"], dtype), T(c["err_map"], dtype)
+    out[f"lstsq_tail/{tag}/coeffs"] = N(ns["lstsq_tail"](me, stack, obs, err, True))
+    out[f"lstsq_tail/{tag}/image"] = N(ns["lstsq_tail"](me, stack, obs, err, False))
+
+
 def generate():
     psf = np.load(os.path.join(REF, "src", "gigalens", "assets", "psf.npy")).astype(np.float32)
     demo = np.load(os.path.join(REF, "src", "gigalens", "assets", "demo.npy")).astype(np.float32)
@@ -185,6 +220,7 @@ def generate():
     for tag, dtype in (("f32", torch.float32), ("f64", torch.float64)):
         run_profiles(out, tag, dtype)
         run_simulators(out, tag, dtype, psf, demo)
+        run_lstsq_tail(out, tag, dtype, psf)
     tf.set_float(torch.float32)
     return out
 

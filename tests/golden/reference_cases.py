@@ -205,6 +205,22 @@ def simulator_cases(psf, demo):
     return cases
 
 
+def lstsq_tail_case(psf):
+    """``lstsq_simulate`` cannot run as written (see make_reference_golden.py), but its tail -- weights, normal equations,
+    ``pinv(rcond=1e-6)``, recombination: ``tf/simulator.py:231-240`` -- can: the generator executes those source lines on a
+    component stack (built by the oracle from this model, whose pieces are pinned individually)."""
+    model = dict(lens_mass=[("EPL", dict(niter=50)), ("Shear", {})], lens_light=[("SersicEllipse", dict(use_lstsq=True))],
+                 source_light=[("Shapelets", dict(n_max=4, use_lstsq=True, interpolate=False))])
+    rng = np.random.default_rng(2007)
+    n = 30
+    p = _draw_model(model, 2, rng)
+    p["source_light"][0]["beta"] = f32([0.15, 0.12])
+    obs = f32(np.abs(rng.normal(0, 1, size=(n, n))) * 3 + 1)
+    err = f32(np.sqrt(0.2 ** 2 + np.clip(obs, 0, np.inf) / 100.0))
+    return dict(model=model, sim=dict(delta_pix=0.13, num_pix=n, supersample=2, kernel=f32(psf[4:9, 4:9]), pix_region=None), params=p,
+                observed=obs, err_map=err)
+
+
 def c4_catalogue(G=30, seed=7):
     """``gigalens_b200.workloads.cluster_catalogue`` (SURVEY 8d C4), restated here so that this module stays import-free;
     tests/test_reference_golden.py asserts the two are identical."""

@@ -145,6 +145,23 @@ def test_oracle_simulator_and_likelihood_match_the_executed_reference(key, tag):
             close(a, r, 1000 * tol, f"positions grad {grp}[{i}].{k}")
 
 
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+def test_oracle_lstsq_tail_matches_the_executed_reference_lines(tag):
+    """tf/simulator.py:231-240 (weights, normal equations, pinv(rcond=1e-6), recombination), executed from the reference
+    file on the oracle's component stack, against the oracle's own tail."""
+    dt = DT[tag]
+    c = RC.lstsq_tail_case(PSF)
+    pm = common.spec_model(c["model"])
+    s = c["sim"]
+    osim = OracleSimulator(common.to_oracle_model(pm, dt), s["delta_pix"], s["num_pix"], s["supersample"], kernel=s["kernel"], bs=2, dtype=dt)
+    params = {g: [{k: T(v, dt) for k, v in d.items()} for d in c["params"][g]] for g in c["params"]}
+    obs, err = T(c["observed"], dt), T(c["err_map"], dt)
+    # the Gram matrix of 16 components has condition ~1e6-1e8: float32 coefficients carry that amplification
+    tol = {"f32": 2e-2, "f64": 1e-9}[tag]
+    close(osim.lstsq_simulate(params, obs, err, return_coeffs=True).numpy(), GOLD[f"lstsq_tail/{tag}/coeffs"], tol, "coeffs")
+    close(osim.lstsq_simulate(params, obs, err).numpy(), GOLD[f"lstsq_tail/{tag}/image"], {"f32": 1e-4, "f64": 1e-11}[tag], "image")
+
+
 def test_c4_case_uses_the_benchmark_catalogue():
     from gigalens_b200 import workloads
     assert RC.c4_catalogue() == workloads.cluster_catalogue(30, 7)
