@@ -157,6 +157,26 @@ def test_prior_densities_integrate_to_one():
         assert abs(float(torch.trapz(torch.exp(lp), z)) - 1) < 2e-4
 
 
+def test_prior_leaf_densities_and_bijectors_match_scipy_and_autodiff():
+    """Independent pin of the restated TFP leaf arithmetic (no TFP here): ``log_prob`` of Normal / LogNormal /
+    TruncatedNormal / Uniform against scipy.stats, the default event-space bijectors (Identity / Exp / Sigmoid(low, high))
+    against their defining maps, and ``forward_log_det_jacobian`` against log|d forward / dz| from autodiff."""
+    from scipy import stats
+    cases = [(OM.Normal(0.3, 0.7), stats.norm(0.3, 0.7), lambda z: z),
+             (OM.LogNormal(math.log(1.25), 0.25), stats.lognorm(s=0.25, scale=1.25), lambda z: torch.exp(z)),
+             (OM.TruncatedNormal(2.0, 0.25, 1.0, 3.0), stats.truncnorm((1.0 - 2.0) / 0.25, (3.0 - 2.0) / 0.25, loc=2.0, scale=0.25),
+              lambda z: 1.0 + 2.0 * torch.sigmoid(z)),
+             (OM.Uniform(0.5, 4.0), stats.uniform(0.5, 3.5), lambda z: 0.5 + 3.5 * torch.sigmoid(z))]
+    z = torch.linspace(-4.0, 4.0, 41, dtype=torch.float64).requires_grad_(True)
+    for d, ref, fwd in cases:
+        x = d.forward(z)
+        assert torch.allclose(x, fwd(z), rtol=1e-13, atol=1e-13), type(d).__name__
+        assert np.allclose(d.log_prob(x).detach().numpy(), ref.logpdf(x.detach().numpy()), rtol=1e-11, atol=1e-11), type(d).__name__
+        (dx,) = torch.autograd.grad(x.sum(), z)
+        assert np.allclose(d.fldj(z).detach().numpy(), np.log(np.abs(dx.numpy())), rtol=1e-10, atol=1e-10), type(d).__name__
+        assert torch.allclose(d.inverse(x), z, atol=1e-8), type(d).__name__
+
+
 def test_logprob_autograd_matches_finite_differences():
     wl = workloads.c2_workload()
     prior = workloads.demo_prior()
