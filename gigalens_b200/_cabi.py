@@ -98,7 +98,7 @@ class PriorLeaf(C.Structure):
 # every symbol include/gigalens_b200.h declares (tests check they are all exported)
 EXPORTED_SYMBOLS = [
     "gl_plan_create", "gl_plan_set_likelihood", "gl_plan_set_prior", "gl_plan_destroy", "gl_last_error",
-    "gl_abi_version", "gl_launch_count", "gl_simulate", "gl_simulate_ss", "gl_beta", "gl_eval_points",
+    "gl_abi_version", "gl_guard_check", "gl_guard_selftest", "gl_launch_count", "gl_simulate", "gl_simulate_ss", "gl_beta", "gl_eval_points",
     "gl_loglike_grad", "gl_logprob_grad", "gl_unconstrain", "gl_logprob_grad_host", "gl_simulate_host",
     "gl_lstsq_simulate", "gl_lstsq_loglike_grad", "gl_plan_depth", "gl_plan_set_option", "gl_plan_get_timings",
     "gl_plan_set_positions", "gl_hessian", "gl_positions_loglike_grad", "gl_lstsq_stack", "gl_chain_grad",
@@ -130,6 +130,8 @@ def load():
     if lib.gl_abi_version() != GL_ABI_VERSION:
         raise RuntimeError(f"{path} has ABI version {lib.gl_abi_version()}, this binding needs {GL_ABI_VERSION}: rebuild it "
                            "(`python -c 'import __graft_entry__ as g; g.build(force=True)'`)")
+    lib.gl_guard_check.restype = C.c_int32
+    lib.gl_guard_selftest.restype = C.c_int32
     lib.gl_launch_count.restype = C.c_int64
     lib.gl_plan_depth.restype = C.c_int32
     lib.gl_plan_depth.argtypes = [vp]

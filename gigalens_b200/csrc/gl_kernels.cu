@@ -47,6 +47,71 @@ static int gl_fail(const std::string& msg) { g_last_error = msg; return 1; }
   } while (0)
 
 // ---------------------------------------------------------------------------------------------
+// guarded allocations (GL_GUARD=1 in the environment): the stand-in for compute-sanitizer's memcheck, which is closed on the
+// GPU pool this was built on.  Every device allocation of the library gets GL_GUARD_BYTES of red zone on both sides, filled
+// with 0xFF (a float NaN, an int -1: a kernel that READS out of bounds poisons its result and fails the parity tests);
+// gl_guard_check() verifies that no kernel WROTE into any red zone.  Off (the default) this is a plain cudaMalloc / cudaFree.
+// ---------------------------------------------------------------------------------------------
+#include <cstdlib>
+#include <map>
+#include <mutex>
+#define GL_GUARD_BYTES ((size_t)65536)
+static std::mutex g_guard_mu;
+static std::map<void*, size_t> g_guard_live;   // user pointer -> user size
+static bool gl_guard_on() {
+  static const bool on = [] { const char* e = getenv("GL_GUARD"); return e && e[0] && e[0] != '0'; }();
+  return on;
+}
+static cudaError_t gl_malloc(void** out, size_t bytes) {
+  if (!gl_guard_on()) return cudaMalloc(out, bytes);
+  const size_t user = (bytes + 255) & ~(size_t)255;
+  char* base = nullptr;
+  cudaError_t e = cudaMalloc((void**)&base, user + 2 * GL_GUARD_BYTES);
+  if (e != cudaSuccess) return e;
+  if ((e = cudaMemset(base, 0xFF, GL_GUARD_BYTES)) != cudaSuccess) return e;
+  if ((e = cudaMemset(base + GL_GUARD_BYTES + bytes, 0xFF, user - bytes + GL_GUARD_BYTES)) != cudaSuccess) return e;
+  *out = base + GL_GUARD_BYTES;
+  std::lock_guard<std::mutex> lk(g_guard_mu);
+  g_guard_live[*out] = bytes;
+  return cudaSuccess;
+}
+static std::string g_guard_sticky;              // first corrupted red zone seen when an allocation was freed
+// verify both red zones of one allocation (device synchronised by the caller); "" = intact
+static std::string gl_guard_verify(const char* user, size_t bytes) {
+  static std::vector<unsigned char> h(GL_GUARD_BYTES + 256);
+  const size_t tail = ((bytes + 255) & ~(size_t)255) - bytes + GL_GUARD_BYTES;
+  for (int side = 0; side < 2; ++side) {
+    const char* src = side ? user + bytes : user - GL_GUARD_BYTES;
+    const size_t n = side ? tail : GL_GUARD_BYTES;
+    if (cudaMemcpy(h.data(), src, n, cudaMemcpyDeviceToHost) != cudaSuccess) return "red zone read-back failed";
+    for (size_t i = 0; i < n; ++i)
+      if (h[i] != 0xFF) {
+        char msg[160];
+        snprintf(msg, sizeof msg, "red zone %s an allocation of %zu bytes was written (offset %td)", side ? "after" : "before", bytes,
+                 side ? (ptrdiff_t)i : (ptrdiff_t)i - (ptrdiff_t)GL_GUARD_BYTES);
+        return msg;
+      }
+  }
+  return "";
+}
+static cudaError_t gl_free(void* q) {
+  if (!gl_guard_on() || !q) return cudaFree(q);
+  {
+    std::lock_guard<std::mutex> lk(g_guard_mu);
+    auto it = g_guard_live.find(q);
+    if (it != g_guard_live.end()) {       // an allocation is checked one last time before it goes away
+      cudaDeviceSynchronize();
+      const std::string e = gl_guard_verify((const char*)q, it->second);
+      if (!e.empty() && g_guard_sticky.empty()) g_guard_sticky = e + " [found at free]";
+      g_guard_live.erase(it);
+    }
+  }
+  return cudaFree((char*)q - GL_GUARD_BYTES);
+}
+#define cudaMalloc(p, n) gl_malloc((void**)(p), (n))
+#define cudaFree(q) gl_free((void*)(q))
+
+// ---------------------------------------------------------------------------------------------
 // prior / bijector leaves
 // ---------------------------------------------------------------------------------------------
 struct GlLeaf { int dist; int slot; float a, b, low, high, log_norm; };
@@ -908,6 +973,41 @@ static int gl_lstsq_reserve(gl_plan* p, int chunk);
 
 const char* gl_last_error(void) { return g_last_error.c_str(); }
 int32_t gl_abi_version(void) { return GL_ABI_VERSION; }
+
+// Red zones of every live device allocation of the library (GL_GUARD=1): returns the number of live guarded allocations,
+// or -1 with gl_last_error() naming the first corrupted one; 0 when guarding is off.  Synchronises the device.
+int32_t gl_guard_check(void) {
+  if (!gl_guard_on()) return 0;
+  if (cudaDeviceSynchronize() != cudaSuccess) { gl_fail(std::string("gl_guard_check: ") + cudaGetErrorString(cudaGetLastError())); return -1; }
+  std::lock_guard<std::mutex> lk(g_guard_mu);
+  if (!g_guard_sticky.empty()) { gl_fail(g_guard_sticky); return -1; }
+  for (auto& kv : g_guard_live) {
+    const std::string e = gl_guard_verify((const char*)kv.first, kv.second);
+    if (!e.empty()) { gl_fail(e); return -1; }
+  }
+  return (int32_t)g_guard_live.size();
+}
+
+// Positive control of the red zones: a kernel writes one float past the end of (before the start of) a guarded buffer and
+// gl_guard_check() must report it.  Returns 0 when both overruns are detected and a clean buffer passes, 1 otherwise
+// (2 when guarding is off).
+__global__ void k_guard_selftest(float* p, long idx) { p[idx] = 1.0f; }
+int32_t gl_guard_selftest(void) {
+  if (!gl_guard_on()) return 2;
+  const std::string keep = g_last_error;
+  int bad = 0;
+  for (int side = 0; side < 3; ++side) {
+    float* buf = nullptr;
+    if (cudaMalloc(&buf, 1000 * sizeof(float)) != cudaSuccess) return 1;
+    k_guard_selftest<<<1, 1>>>(buf, side == 0 ? 0 : side == 1 ? 1000 : -1);
+    const int32_t r = gl_guard_check();
+    if ((side == 0) != (r >= 0)) ++bad;     // in-bounds write: clean; either overrun: reported
+    cudaFree(buf);
+    { std::lock_guard<std::mutex> lk(g_guard_mu); g_guard_sticky.clear(); }   // the deliberate overrun is not a finding
+  }
+  g_last_error = keep;
+  return bad ? 1 : 0;
+}
 int64_t gl_launch_count(void) { return g_launch_count; }
 int32_t gl_plan_depth(const gl_plan* plan) { return plan ? plan->prog.depth : 0; }
 

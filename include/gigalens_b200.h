@@ -163,6 +163,12 @@ int gl_plan_get_timings(gl_plan* plan, float* ms_out, int32_t* ncalls_out);
 void gl_plan_destroy(gl_plan* plan);
 const char* gl_last_error(void);
 int32_t gl_abi_version(void);
+/* Debug aid (no reference counterpart): with GL_GUARD=1 in the environment every device allocation of the library carries
+ * 64 KB red zones filled with 0xFF; this verifies them (returns the number of live guarded allocations, -1 + gl_last_error()
+ * if a kernel wrote into one, 0 when guarding is off).  Synchronises the device. */
+int32_t gl_guard_check(void);
+/* Positive control: deliberately overruns a guarded scratch buffer by one float on either side; 0 = both detected. */
+int32_t gl_guard_selftest(void);
 /* number of kernels the library has launched in this process (bench.py's gpu_launches) */
 int64_t gl_launch_count(void);
 

@@ -1180,3 +1180,16 @@ def test_conv_geometries_match_oracle(num_pix, K, ss):
     assert_parity(ll[:, None], ll32[:, None], ll64[:, None], 1e-5, "log-like", llp[:, None], axis=1)
     for k in range(cm.n_params):
         assert_parity(grad[k], g32[k], g64[k], 1e-4, f"grad {cm.slot_keys[k]}", gp[k])
+
+
+def test_red_zone_guard_detects_a_deliberate_overrun():
+    """Positive control of the memcheck stand-in (GL_GUARD=1; tests/conftest.py verifies the red zones after every GPU test):
+    one float written past either end of a guarded buffer must be reported."""
+    import os
+    from gigalens_b200 import _cabi
+    lib = _cabi.load()
+    r = lib.gl_guard_selftest()
+    if os.environ.get("GL_GUARD", "0") in ("", "0"):
+        assert r == 2 and lib.gl_guard_check() == 0
+    else:
+        assert r == 0
