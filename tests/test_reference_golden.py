@@ -161,6 +161,16 @@ def test_oracle_lstsq_tail_matches_the_executed_reference_lines(tag):
     close(osim.lstsq_simulate(params, obs, err).numpy(), GOLD[f"lstsq_tail/{tag}/image"], TOL[tag], "image")
 
 
+def test_tensorflow_stand_in_matches_independent_statements_of_the_tf_semantics():
+    """oracle/tfshim/selfcheck.py: SAME-padded NHWC conv / depthwise conv / pooling against explicit numpy loops, the scatter
+    family and one-argument where against numpy indexing, nest.flatten's key order, while_loop's contract, GradientTape,
+    pinv(rcond) against numpy.linalg, interp_regular_1d_grid against numpy.interp.  A subprocess: the module name ``tensorflow``
+    must not leak into the test process."""
+    out = subprocess.run([sys.executable, os.path.join(common.ROOT, "oracle", "tfshim", "selfcheck.py")], capture_output=True, text=True,
+                         cwd=os.path.join(common.ROOT, "oracle"))
+    assert out.returncode == 0 and "all checks passed" in out.stdout, out.stdout + out.stderr
+
+
 def test_c4_case_uses_the_benchmark_catalogue():
     from gigalens_b200 import workloads
     assert RC.c4_catalogue() == workloads.cluster_catalogue(30, 7)
