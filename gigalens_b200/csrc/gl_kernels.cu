@@ -383,30 +383,34 @@ template <int PPT, unsigned F>
 __global__ void __launch_bounds__(GLK_THREADS) k_nan_cotangent_mask(GlProgram P, int npix, const float* __restrict__ grid_x,
                                                                     const float* __restrict__ grid_y,
                                                                     const float* __restrict__ derived, int no_deflection,
-                                                                    float* __restrict__ gss, const int* __restrict__ nan_count) {
+                                                                    float* __restrict__ gss, const int* __restrict__ nan_count, int bs) {
   extern __shared__ __align__(16) float s_der[];
-  const int b = blockIdx.y;
-  if (nan_count[b] == 0) return;
-  const float* dsrc = derived + (size_t)b * P.der_total;
-  for (int i = threadIdx.x; i < P.der_total; i += blockDim.x) s_der[i] = dsrc[i];
-  __syncthreads();
-  const int per_batch = GLK_THREADS * PPT;
-  const int nbatch = (npix + per_batch - 1) / per_batch;
-  float* g = gss + (size_t)b * npix;
-  for (int batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
-    if (batch * per_batch + (int)(threadIdx.x & ~31u) >= npix) break;   // this warp has no pixel left (ragged last batch)
-    float x[PPT], y[PPT], v[PPT];
-    int pix[PPT];
+  // a few CTAs walk the samples (the common case is "no sample has a scrubbed pixel": 4096 one-CTA-per-sample launches cost 8 us
+  // to find that out, 592 CTAs that read the flags cost 3)
+  for (int b = blockIdx.y; b < bs; b += gridDim.y) {
+    if (nan_count[b] == 0) continue;       // uniform over the CTA
+    __syncthreads();                       // the previous sample's s_der readers are done
+    const float* dsrc = derived + (size_t)b * P.der_total;
+    for (int i = threadIdx.x; i < P.der_total; i += blockDim.x) s_der[i] = dsrc[i];
+    __syncthreads();
+    const int per_batch = GLK_THREADS * PPT;
+    const int nbatch = (npix + per_batch - 1) / per_batch;
+    float* g = gss + (size_t)b * npix;
+    for (int batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
+      if (batch * per_batch + (int)(threadIdx.x & ~31u) >= npix) break;   // this warp has no pixel left (ragged last batch)
+      float x[PPT], y[PPT], v[PPT];
+      int pix[PPT];
 #pragma unroll
-    for (int j = 0; j < PPT; ++j) {
-      pix[j] = batch * per_batch + j * GLK_THREADS + threadIdx.x;
-      const int p = pix[j] < npix ? pix[j] : 0;
-      x[j] = __ldg(grid_x + p); y[j] = __ldg(grid_y + p);
+      for (int j = 0; j < PPT; ++j) {
+        pix[j] = batch * per_batch + j * GLK_THREADS + threadIdx.x;
+        const int p = pix[j] < npix ? pix[j] : 0;
+        x[j] = __ldg(grid_x + p); y[j] = __ldg(grid_y + p);
+      }
+      gl_pix_image<float, PPT, F>(P, s_der, x, y, no_deflection != 0, v);
+#pragma unroll
+      for (int j = 0; j < PPT; ++j)
+        if (pix[j] < npix && v[j] != v[j]) g[pix[j]] = 0.f;
     }
-    gl_pix_image<float, PPT, F>(P, s_der, x, y, no_deflection != 0, v);
-#pragma unroll
-    for (int j = 0; j < PPT; ++j)
-      if (pix[j] < npix && v[j] != v[j]) g[pix[j]] = 0.f;
   }
 }
 
@@ -1427,8 +1431,8 @@ static int gl_run_raytrace_bwd(gl_plan* p, float* gss, int no_deflection, cudaSt
   } else {   // NaN-scrubbed pixels pass no gradient: exits immediately for samples without any (nan_count from the forward pass)
     const size_t smem_m = (size_t)p->prog.der_total * sizeof(float);
     GL_FEAT_DISPATCH(p->feat_idx, {
-      k_nan_cotangent_mask<4, F><<<dim3(1, p->bs), GLK_THREADS, smem_m, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y, p->d_derived,
-                                                                   no_deflection, gss, p->d_nan);
+      k_nan_cotangent_mask<4, F><<<dim3(1, p->bs < 592 ? p->bs : 592), GLK_THREADS, smem_m, st>>>(p->prog, p->npix, p->d_grid_x, p->d_grid_y,
+                                                                                         p->d_derived, no_deflection, gss, p->d_nan, p->bs);
     })
     GL_LAUNCH_CHECK("k_nan_cotangent_mask");
   }
