@@ -219,7 +219,9 @@ class LensSimulator(LensSimulatorInterface):
         T = np.eye(2) * sim_config.delta_pix if sim_config.transform_pix2angle is None \
             else np.asarray(sim_config.transform_pix2angle)
         self.transform_pix2angle = (T / float(self.supersample)).astype(np.float32)
-        self.conversion_factor = float(np.float32(np.linalg.det(T.astype(np.float32))))  # tf/simulator.py:27-29
+        # tf/simulator.py:27-29: the default transform is a float32 tensor (tf.eye(2) * delta_pix), a user-supplied array keeps its own
+        # dtype through tf.linalg.det; either way the determinant is then cast to float32
+        self.conversion_factor = float(np.float32(np.linalg.det(T.astype(np.float32) if sim_config.transform_pix2angle is None else T)))
         nss = n * self.supersample
         if sim_config.pix_region is None:
             img_region = np.ones((n, n), dtype=np.float32)

@@ -151,8 +151,9 @@ class OracleSimulator:
         self.wcs = LensWCS(n=num_pix, supersample=supersample, transform_pix2angle=transform_pix2angle,
                            pix_scale=delta_pix)
         T = np.eye(2) * delta_pix if transform_pix2angle is None else np.asarray(transform_pix2angle)
-        # :27-29  det of the un-supersampled transform, cast to fp32
-        self.conversion_factor = float(np.float32(np.linalg.det(T.astype(np.float32))))
+        # :27-29  det of the un-supersampled transform, cast to fp32 (the default transform is a float32 tensor, tf.eye(2) * delta_pix;
+        # a user-supplied array keeps its own dtype through tf.linalg.det)
+        self.conversion_factor = float(np.float32(np.linalg.det(T.astype(np.float32) if transform_pix2angle is None else T)))
         nss = num_pix * self.supersample
         if pix_region is None:  # :34-42
             region = np.ones((nss, nss), dtype=bool)

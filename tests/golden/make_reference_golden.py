@@ -125,7 +125,7 @@ def build(c, dtype, bs):
     phys = in_f32_then(dtype, lambda: ref_model.PhysicalModel(mk(m["lens_mass"]), mk(m["lens_light"]), mk(m["source_light"])))
     s = c["sim"]
     cfg = SimulatorConfig(delta_pix=s["delta_pix"], num_pix=s["num_pix"], supersample=s["supersample"], kernel=s["kernel"],
-                          pix_region=s["pix_region"])
+                          pix_region=s["pix_region"], transform_pix2angle=s.get("transform_pix2angle"))
     return phys, in_f32_then(dtype, lambda: ref_sim.LensSimulator(phys, cfg, bs=bs))
 
 

@@ -187,6 +187,18 @@ def simulator_cases(psf, demo):
     cases["cluster"] = dict(model=model, sim=dict(delta_pix=0.2, num_pix=n, supersample=2, kernel=f32(psf), pix_region=None), params=p,
                             observed=f32(rng.normal(0, 0.2, size=(n, n)) + 0.5), noise=dict(background_rms=0.2, exp_time=100.0),
                             centroids=cen, variants=False)
+    # a rotated, sheared, non-symmetric pixel -> angle transform (simulator.py:32-55: the einsum of pix2angle applies the TRANSPOSE of
+    # the supersampled transform; conversion_factor = det of the un-supersampled one, tf/simulator.py:27-29)
+    model = dict(lens_mass=[("EPL", dict(niter=50)), ("Shear", {})], lens_light=[("Sersic", dict(use_lstsq=False))],
+                 source_light=[("SersicEllipse", dict(use_lstsq=False))])
+    rng = np.random.default_rng(2008)
+    n = 18
+    p = _draw_model(model, 2, rng)
+    ang = 0.4
+    T = 0.11 * np.array([[np.cos(ang), -1.15 * np.sin(ang)], [0.85 * np.sin(ang), np.cos(ang)]])
+    cases["rotated_wcs"] = dict(model=model, sim=dict(delta_pix=0.11, num_pix=n, supersample=2, kernel=f32(psf[4:9, 4:9]), pix_region=None,
+                                                      transform_pix2angle=T), params=p,
+                                observed=f32(rng.normal(0, 1, size=(n, n)) + 4), noise=dict(background_rms=0.25, exp_time=80.0), variants=False)
     # C4 at BASELINE geometry (configs[3]): 200 x 200, ss = 2, +-10 arcsec, NFW + 30-member dPIE scaling relation + shear;
     # one sample near the prior medians of workloads.c4_prior() (image, likelihood and gradient only: the fixture stays small)
     model = dict(lens_mass=[("NFW", {}), ("DPIESubhalo", dict(lum_star=1.0, galaxy_catalogue=c4_catalogue())), ("Shear", {})],

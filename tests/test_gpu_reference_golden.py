@@ -78,7 +78,8 @@ def test_cuda_simulator_and_likelihood_match_the_executed_reference(key):
     bs = len(c["params"][keys[0][0]][keys[0][1]][keys[0][2]])
     sc = SimulatorConfig(delta_pix=s["delta_pix"], num_pix=n, supersample=s["supersample"],
                          kernel=None if s["kernel"] is None else s["kernel"].astype(np.float32),
-                         pix_region=None if s["pix_region"] is None else s["pix_region"].astype(np.float32))
+                         pix_region=None if s["pix_region"] is None else s["pix_region"].astype(np.float32),
+                         transform_pix2angle=s.get("transform_pix2angle"))
     sim = LensSimulator(pm, sc, bs=bs)
     cm = sim.compiled
     mat = _matrix(cm, c["params"], bs)

@@ -77,7 +77,7 @@ def build_oracle_case(c, dt):
     pm = common.spec_model(c["model"])
     s = c["sim"]
     osim = OracleSimulator(common.to_oracle_model(pm, dt), s["delta_pix"], s["num_pix"], s["supersample"], kernel=s["kernel"],
-                           pix_region=s["pix_region"], bs=bs, dtype=dt)
+                           pix_region=s["pix_region"], transform_pix2angle=s.get("transform_pix2angle"), bs=bs, dtype=dt)
     cen = c.get("centroids")
     kw = dict(error_map=c["error_map"]) if "error_map" in c else dict(background_rms=c["noise"]["background_rms"], exp_time=c["noise"]["exp_time"])
     if cen is not None:
