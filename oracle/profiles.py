@@ -482,9 +482,11 @@ class ScalingRelation(MassBase):
                  for k in self.not_scaling_params})
             # fp32 constants in the reference (:52-54); computed in fp32 then promoted so that the fp64
             # arbiter run sees the same catalogue-derived inputs as the fp32 run.
-            lum32 = np.asarray(galaxy_catalogue["lum"], dtype=np.float32)[chunk]
+            # (torch float32 pow, like the tensors of the executed reference: numpy's powf differs from it by an ulp for
+            # powers other than 1/2)
+            lum32 = torch.as_tensor(np.asarray(galaxy_catalogue["lum"], dtype=np.float32)[chunk])
             self._unscaled_params.append(
-                {k: torch.as_tensor((lum32 / np.float32(lum_star)) ** np.float32(self.power[k])).to(dtype)
+                {k: ((lum32 / lum_star) ** torch.tensor(self.power[k], dtype=torch.float32)).to(dtype)
                  for k in self.scaling_params})
 
     def deriv(self, x, y, **scales):

@@ -247,8 +247,12 @@ def spec_profile(cls, ctor):
              "NFW_ELLIPSE": gl_nfw.NFW_ELLIPSE, "DPIS": gl_piemd.DPIS, "DPIE": gl_piemd.DPIE, "TNFW": gl_tnfw.TNFW,
              "DPIEP": gl_piep.DPIEP, "DPIESubhalo": gl_sub.DPIESubhalo, "Sersic": gl_sersic.Sersic,
              "SersicEllipse": gl_sersic.SersicEllipse, "CoreSersic": gl_sersic.CoreSersic, "Shapelets": gl_shapelets.Shapelets}
+    if cls == "ScaledSIS":
+        return gl_sr.ScalingRelation(gl_sis.SIS(), ["theta_E"], ctor["lum_star"], ctor["scaling_params_power"], ctor["galaxy_catalogue"])
     return table[cls](**ctor)
 
 
-def spec_model(model):
-    return PhysicalModel(*[[spec_profile(c, k) for c, k in model[g]] for g in ("lens_mass", "lens_light", "source_light")])
+def spec_model(model, constants=None):
+    kw = {} if constants is None else dict(lenses_constants=constants["lens_mass"], lens_light_constants=constants["lens_light"],
+                                           source_light_constants=constants["source_light"])
+    return PhysicalModel(*[[spec_profile(c, k) for c, k in model[g]] for g in ("lens_mass", "lens_light", "source_light")], **kw)

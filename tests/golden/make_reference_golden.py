@@ -40,7 +40,7 @@ import gigalens.tf.simulator as ref_sim  # noqa: E402
 from gigalens.simulator import SimulatorConfig  # noqa: E402
 from gigalens.tf.profiles.light import sersic as r_sersic, shapelets as r_shapelets  # noqa: E402
 from gigalens.tf.profiles.mass import (dpie_subhalo as r_sub, epl as r_epl, nfw as r_nfw, piemd as r_piemd, piep as r_piep,  # noqa: E402
-                                       shear as r_shear, sie as r_sie, sis as r_sis, tnfw as r_tnfw)
+                                       scaling_relation as r_sr, shear as r_shear, sie as r_sie, sis as r_sis, tnfw as r_tnfw)
 
 import reference_cases as RC  # noqa: E402
 
@@ -49,6 +49,7 @@ CLASSES = {
     "DPIS": r_piemd.DPIS, "DPIE": r_piemd.DPIE, "TNFW": r_tnfw.TNFW, "DPIEP": r_piep.DPIEP, "DPIESubhalo": r_sub.DPIESubhalo,
     "Sersic": r_sersic.Sersic, "SersicEllipse": r_sersic.SersicEllipse, "CoreSersic": r_sersic.CoreSersic,
     "Shapelets": r_shapelets.Shapelets,
+    "ScaledSIS": lambda **k: r_sr.ScalingRelation(profile=r_sis.SIS(), scaling_params=["theta_E"], **k),
 }
 
 
@@ -122,7 +123,10 @@ def run_profiles(out, tag, dtype):
 def build(c, dtype, bs):
     m = c["model"]
     mk = lambda lst: [make(cls, ctor, dtype) for cls, ctor in lst]  # noqa: E731
-    phys = in_f32_then(dtype, lambda: ref_model.PhysicalModel(mk(m["lens_mass"]), mk(m["lens_light"]), mk(m["source_light"])))
+    k = c.get("constants")
+    kw = {} if k is None else dict(lenses_constants=k["lens_mass"], lens_light_constants=k["lens_light"], source_light_constants=k["source_light"])
+    profs = [mk(m[g]) for g in ("lens_mass", "lens_light", "source_light")]     # (each make() switches the float type back itself)
+    phys = in_f32_then(dtype, lambda: ref_model.PhysicalModel(*profs, **kw))
     s = c["sim"]
     cfg = SimulatorConfig(delta_pix=s["delta_pix"], num_pix=s["num_pix"], supersample=s["supersample"], kernel=s["kernel"],
                           pix_region=s["pix_region"], transform_pix2angle=s.get("transform_pix2angle"))

@@ -33,6 +33,7 @@ PARAMS = {   # parameter names per class, in the reference's ``_params`` order (
     "SersicEllipse": ["R_sersic", "n_sersic", "e1", "e2", "center_x", "center_y", "Ie"],
     "CoreSersic": ["R_sersic", "n_sersic", "Rb", "alpha", "gamma", "e1", "e2", "center_x", "center_y", "Ie"],
     "Shapelets": ["beta", "center_x", "center_y"],
+    "ScaledSIS": ["theta_E"],      # ScalingRelation(profile=SIS(), scaling_params=["theta_E"], ...): a generic scaling relation
 }
 
 
@@ -199,6 +200,28 @@ def simulator_cases(psf, demo):
     cases["rotated_wcs"] = dict(model=model, sim=dict(delta_pix=0.11, num_pix=n, supersample=2, kernel=f32(psf[4:9, 4:9]), pix_region=None,
                                                       transform_pix2angle=T), params=p,
                                 observed=f32(rng.normal(0, 1, size=(n, n)) + 4), noise=dict(background_rms=0.25, exp_time=80.0), variants=False)
+    # per-profile constants merged into the call (tf/simulator.py:75-76,129-138), an EPL whose series is cut by `niter` (maximum_iterations,
+    # epl.py:50) at strong ellipticity, a generic ScalingRelation around SIS with its own power / L*, pooling without a PSF, and a
+    # table-interpolated Shapelets source whose argument leaves the +-5 table (fill value 0, shapelets.py:58-60)
+    model = dict(lens_mass=[("EPL", dict(niter=6)),
+                            ("ScaledSIS", dict(lum_star=1.3, scaling_params_power={"theta_E": 0.6},
+                                               galaxy_catalogue={k: v for k, v in catalogue(4, 9, 0.8).items() if k in ("lum", "center_x", "center_y")})),
+                            ("Shear", {})],
+                 lens_light=[], source_light=[("Sersic", dict(use_lstsq=False)), ("Shapelets", dict(n_max=3, use_lstsq=False, interpolate=True))])
+    rng = np.random.default_rng(2009)
+    n = 20
+    p = _draw_model(model, 3, rng)
+    p["lens_mass"][0]["e1"] = f32([0.45, -0.3, 0.1])
+    p["lens_mass"][0]["e2"] = f32([-0.3, 0.4, 0.05])
+    p["lens_mass"][1]["theta_E"] = f32([0.12, 0.2, 0.08])
+    consts = dict(lens_mass=[{"gamma": 2.15, "center_x": 0.04}, {}, {}], lens_light=[], source_light=[{"n_sersic": 1.5}, {}])
+    for g in consts:
+        for d, cdict in zip(p[g], consts[g]):
+            for k in cdict:
+                d.pop(k)
+    cases["constants_capped"] = dict(model=model, constants=consts, sim=dict(delta_pix=0.1, num_pix=n, supersample=2, kernel=None, pix_region=None),
+                                     params=p, observed=f32(rng.normal(0, 1, size=(n, n)) + 4), noise=dict(background_rms=0.3, exp_time=60.0),
+                                     variants=False)
     # C4 at BASELINE geometry (configs[3]): 200 x 200, ss = 2, +-10 arcsec, NFW + 30-member dPIE scaling relation + shear;
     # one sample near the prior medians of workloads.c4_prior() (image, likelihood and gradient only: the fixture stays small)
     model = dict(lens_mass=[("NFW", {}), ("DPIESubhalo", dict(lum_star=1.0, galaxy_catalogue=c4_catalogue())), ("Shear", {})],

@@ -73,7 +73,7 @@ def test_cuda_simulator_and_likelihood_match_the_executed_reference(key):
     c = R.SIM_CASES[key]
     s = c["sim"]
     n = s["num_pix"]
-    pm = common.spec_model(c["model"])
+    pm = common.spec_model(c["model"], c.get("constants"))
     keys = RC.grad_keys(c["params"])
     bs = len(c["params"][keys[0][0]][keys[0][1]][keys[0][2]])
     sc = SimulatorConfig(delta_pix=s["delta_pix"], num_pix=n, supersample=s["supersample"],

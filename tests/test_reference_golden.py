@@ -74,7 +74,7 @@ SIM_CASES = RC.simulator_cases(PSF, DEMO)
 def build_oracle_case(c, dt):
     keys = RC.grad_keys(c["params"])
     bs = len(c["params"][keys[0][0]][keys[0][1]][keys[0][2]])
-    pm = common.spec_model(c["model"])
+    pm = common.spec_model(c["model"], c.get("constants"))
     s = c["sim"]
     osim = OracleSimulator(common.to_oracle_model(pm, dt), s["delta_pix"], s["num_pix"], s["supersample"], kernel=s["kernel"],
                            pix_region=s["pix_region"], transform_pix2angle=s.get("transform_pix2angle"), bs=bs, dtype=dt)
