@@ -1,4 +1,4 @@
-"""C3 (lstsq) step time with the eigen-solve on the tail stream / in line and with forced chunks: python scripts/ab_c3.py [bs]"""
+"""C3 (lstsq) step time with the eigen-solve on the tail stream / in line and with forced chunks: python scripts/ab_c3.py [bs [chunk ...]]"""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -8,7 +8,8 @@ from gigalens_b200.simulator import LensSimulator
 bs = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 wl = workloads.c3_workload(observed=workloads.c3_observation())
 ref = None
-for opts in ({}, {"lstsq_hide_tail": 0}, {"lstsq_chunk": bs // 2}):
+CH = [int(a) for a in sys.argv[2:]]
+for opts in ([{}, {"lstsq_hide_tail": 0}, {"lstsq_chunk": bs // 2}] if not CH else [{}] + [{"lstsq_chunk": c} for c in CH]):
     sim = LensSimulator(wl["phys_model"], wl["sim_config"], bs=bs)
     pm = BackwardProbModel(wl["prior"], wl["observed"], wl["background_rms"], wl["exp_time"])
     z = torch.as_tensor(pm.bij_inverse(wl["prior"].sample(bs, seed=0)), device="cuda")
