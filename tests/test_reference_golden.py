@@ -183,5 +183,10 @@ def test_committed_fixture_is_what_the_reference_produces_today(tmp_path):
     subprocess.check_call([sys.executable, os.path.join(common.HERE, "golden", "make_reference_golden.py"), str(out)], cwd=str(tmp_path))
     new = np.load(out)
     assert sorted(new.files) == sorted(GOLD.files)
-    for k in new.files:
-        assert np.array_equal(new[k], GOLD[k], equal_nan=True), k
+    for k in new.files:      # not bit-exact: torch's CPU reductions depend on the thread count of the machine
+        a, g = np.asarray(new[k], dtype=np.float64), np.asarray(GOLD[k], dtype=np.float64)
+        fin = np.isfinite(g)
+        assert a.shape == g.shape and np.array_equal(np.isfinite(a), fin), k
+        scale = max(float(np.max(np.abs(g[fin]))), 1e-30) if fin.any() else 1.0
+        tol = 1e-3 if ("/f32/" in k and "grad" in k) else 1e-5 if "/f32/" in k else 1e-10
+        assert not fin.any() or float(np.max(np.abs(a[fin] - g[fin]))) <= tol * scale, k
