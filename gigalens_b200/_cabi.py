@@ -101,7 +101,7 @@ EXPORTED_SYMBOLS = [
     "gl_abi_version", "gl_guard_check", "gl_guard_selftest", "gl_launch_count", "gl_simulate", "gl_simulate_ss", "gl_beta", "gl_eval_points",
     "gl_loglike_grad", "gl_logprob_grad", "gl_unconstrain", "gl_logprob_grad_host", "gl_simulate_host",
     "gl_lstsq_simulate", "gl_lstsq_loglike_grad", "gl_plan_depth", "gl_plan_set_option", "gl_plan_get_timings",
-    "gl_plan_set_positions", "gl_hessian", "gl_positions_loglike_grad", "gl_lstsq_stack", "gl_chain_grad",
+    "gl_plan_set_positions", "gl_hessian", "gl_positions_loglike_grad", "gl_lstsq_stack", "gl_chain_grad", "gl_adam_step",
     "gl_plan_reserve_lstsq", "gl_fp32_peak",
 ]
 
@@ -154,6 +154,7 @@ def load():
     lib.gl_lstsq_simulate.argtypes = [vp, fp, fp, fp, vp]
     lib.gl_lstsq_loglike_grad.argtypes = [vp, fp, fp, fp, fp, vp]
     lib.gl_chain_grad.argtypes = [vp, fp, fp, i32, fp, fp, vp]
+    lib.gl_adam_step.argtypes = [fp, fp, fp, fp, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, i32, vp]
     lib.gl_lstsq_stack.argtypes = [vp, fp, fp, vp]
     lib.gl_plan_set_positions.argtypes = [vp, i32, fp, fp, fp, fp, fp]
     lib.gl_hessian.argtypes = [vp, fp, i32, fp, fp, fp, fp, fp, fp, vp]

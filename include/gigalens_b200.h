@@ -208,6 +208,13 @@ int gl_unconstrain(gl_plan* plan, const float* z_dev, float* params_dev, float* 
  * tempered target prior + aux + beta (like - aux) needs (tf/inference.py:289-302). */
 int gl_chain_grad(gl_plan* plan, const float* z_dev, const float* dparams_dev, int32_t with_prior, float* logprior_dev,
                   float* dz_dev, void* stream);
+/* One Adam update of ModellingSequence.MAP (tf/inference.py:34-37, optimizer.apply_gradients on the per-sample loss) in one launch,
+ * element-wise on n floats (all device pointers; x, m, v updated in place): g = grad * grad_scale (non-finite -> 0 when
+ * scrub_nan), m = b1 m + (1 - b1) g, v = b2 v + (1 - b2) g^2, x -= alpha m / (sqrt(v) + eps); the caller folds the bias
+ * correction into alpha = lr sqrt(1 - b2^t) / (1 - b1^t) (Keras' Adam).  The scalars are doubles so that 1 - beta is formed before
+ * the float32 cast (1.f - 0.999f is off by 1.3e-5). */
+int gl_adam_step(float* x_dev, const float* grad_dev, float* m_dev, float* v_dev, int64_t n, double grad_scale, double beta1, double beta2,
+                 double alpha, double eps, int32_t scrub_nan, void* stream);
 
 /* Host-buffer convenience wrappers (pinned or pageable host memory): copy in, run, copy out,
  * synchronise.  These are the calls a reference-side binding would make per optimiser step. */

@@ -109,3 +109,28 @@ def test_smc_with_position_auxiliary_runs_and_tempers_to_one():
     cloud, info2 = seq.SMC(num_particles=32, num_leapfrog_steps=2, post_sampling_steps=0, max_sampling_per_stage=1,
                            max_stage=3, target="positions", auxiliar="none", seed=2)
     assert cloud.shape == (32, 1, 22) and info2["stages"] <= 3
+
+
+def test_fused_adam_kernel_matches_the_torch_formulation():
+    """gl_adam_step (one launch) against the eight-launch torch formulation of Keras' Adam, with the gradient scale and the
+    NaN scrub folded in (tf/inference.py:34-37)."""
+    import torch
+    from gigalens_b200.inference import Adam, PolynomialDecay
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x0 = torch.randn(4096, 22, device="cuda", generator=g)
+    a, b = x0.clone(), x0.clone().cpu()
+    oa, ob = Adam(PolynomialDecay(1e-2, 10, 1e-3)), Adam(PolynomialDecay(1e-2, 10, 1e-3))
+    for t in range(12):
+        grad = torch.randn(4096, 22, device="cuda", generator=g) * 10.0 ** float(t % 5 - 2)
+        if t == 3:
+            grad[5, 7] = float("nan"); grad[9, 1] = float("inf")
+        oa.step(a, grad, grad_scale=-0.37, scrub_nan=True)       # CUDA float32 contiguous: the fused kernel
+        ob.step(b, grad.cpu(), grad_scale=-0.37, scrub_nan=True)  # CPU tensors: the torch formulation
+    assert torch.isfinite(a).all()
+
+    def rel(u, w):
+        return float((u.cpu() - w).abs().max() / w.abs().max())
+
+    # twelve updates: a few float32 ulps (FMA contraction on the GPU, separate roundings on the CPU)
+    errs = dict(x=rel(a, b), m=rel(oa.m, ob.m), v=rel(oa.v, ob.v))
+    assert all(e < 2e-6 for e in errs.values()), errs
