@@ -1,5 +1,5 @@
 #!/bin/bash
-# ncu launch list + full capture of the lstsq config
+# ncu launch list + full capture of the lstsq config (C3) on the final tree
 mkdir -p gpurun_out
 python scripts/bench_configs.py c3 2048 > gpurun_out/plain_c3.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/r02_c3_launches.csv \
