@@ -222,6 +222,18 @@ def simulator_cases(psf, demo):
     cases["constants_capped"] = dict(model=model, constants=consts, sim=dict(delta_pix=0.1, num_pix=n, supersample=2, kernel=None, pix_region=None),
                                      params=p, observed=f32(rng.normal(0, 1, size=(n, n)) + 4), noise=dict(background_rms=0.3, exp_time=60.0),
                                      variants=False)
+    # image-position likelihood through a deflector WITHOUT an analytic Hessian: EPL + shear, so magnification comes from the autodiff
+    # default of tf/profile.py:9-30 through the EPL while_loop, and its parameter gradient from second-order autodiff
+    model = dict(lens_mass=[("EPL", dict(niter=50)), ("Shear", {})], lens_light=[], source_light=[("SersicEllipse", dict(use_lstsq=False))])
+    rng = np.random.default_rng(2010)
+    n = 20
+    p = _draw_model(model, 3, rng)
+    p["lens_mass"][0]["theta_E"] = f32([1.1, 1.15, 1.05])
+    cen = dict(x=[f32([1.05, -0.95, 0.2, -0.3])], y=[f32([0.35, -0.5, 1.1, -1.0])], ex=[f32([0.03, 0.04, 0.03, 0.05])],
+               ey=[f32([0.04, 0.03, 0.05, 0.03])])
+    cases["epl_positions"] = dict(model=model, sim=dict(delta_pix=0.15, num_pix=n, supersample=1, kernel=None, pix_region=None), params=p,
+                                  observed=f32(rng.normal(0, 1, size=(n, n)) + 3), noise=dict(background_rms=0.3, exp_time=50.0),
+                                  centroids=cen, variants=False)
     # C4 at BASELINE geometry (configs[3]): 200 x 200, ss = 2, +-10 arcsec, NFW + 30-member dPIE scaling relation + shear;
     # one sample near the prior medians of workloads.c4_prior() (image, likelihood and gradient only: the fixture stays small)
     model = dict(lens_mass=[("NFW", {}), ("DPIESubhalo", dict(lum_star=1.0, galaxy_catalogue=c4_catalogue())), ("Shear", {})],
