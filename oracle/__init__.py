@@ -31,6 +31,6 @@ The oracle is pinned in two ways.
 Still **parity unpinned** (third-party arithmetic that is neither vendored in the reference nor installable): the TFP prior /
 bijector values (``oracle/model.py``), lenstronomy's ``subgrid_kernel`` and ``phi_n`` (restated; the stand-in borrows the
 restatements), and ``tf.linalg.pinv``'s own kernel.  The reference's ``lstsq_simulate`` cannot execute as a whole in either substrate
-(``tf/simulator.py:183-203`` scatters into a zero-sized buffer); (1) pins its inputs (component light, conv / pool) and, by
-executing its source lines ``:231-240`` on the oracle's stack, its normal-equation tail.  DESIGN.md says the same.
+(``tf/simulator.py:183-203`` scatters into a zero-sized buffer); (1) executes everything else of it -- the reference's simulator
+object, ``beta``, ``light`` calls and its source lines ``:204-240`` -- restating only those three scatter lines.  DESIGN.md says the same.
 """

@@ -11,9 +11,8 @@ Each case runs twice: with ``tf.float32`` = float32 (the reference's arithmetic)
 Not covered: ``lstsq_simulate`` (``tf/simulator.py:158-240``) cannot execute as written -- it scatters the component values
 into a buffer whose leading dimension is 0 (``:183-203``; a real TensorFlow raises the same out-of-range error the stand-in
 does) and the JAX variant concatenates 3-D components onto a 4-D buffer -- so the normal-equation / pinv tail stays restated in
-the oracle -- its inputs, the per-component light and the conv / pool, are pinned here, and the tail itself (weights, normal
-equations, ``pinv(rcond=1e-6)``, recombination: ``:231-240``) is executed from the reference file's source lines on the oracle's
-component stack (``run_lstsq_tail``); and the TFP prior / bijector arithmetic.
+the oracle; ``run_lstsq`` below executes everything of it that can run (the reference's own simulator object, ``beta`` and ``light``
+calls, and its source lines :204-240 read from the file), restating only the scatter of :183-203; and the TFP prior / bijector arithmetic.
 
     python tests/golden/make_reference_golden.py [out.npz]       (needs /root/reference; writes tests/golden/reference_golden.npz)
 
@@ -184,9 +183,45 @@ def run_simulators(out, tag, dtype, psf, demo):
             out[f"{pre}/pos_grad"] = np.stack([N(torch.zeros(bs, dtype=dtype) if v is None else v) for v in gp])
 
 
+def run_lstsq(out, tag, dtype, psf):
+    """``lstsq_simulate`` (``tf/simulator.py:158-240``) cannot run as a whole: lines 183-203 scatter the component values into a
+    buffer whose leading dimension is 0.  Everything else can.  The reference's own simulator object (its ``__init__`` builds
+    ``self.kernel`` / ``self.depth``), its own ``beta`` and its own profile ``light`` calls produce the components; three lines
+    here do what :183-203 meant (scatter each component onto the supersampled grid, concatenate); and the source lines from the
+    first NaN scrub (:204) to the end -- transpose / reshape, depthwise conv, pooling, second NaN scrub, weights, normal
+    equations, ``pinv(rcond=1e-6)``, recombination -- are read from the reference file and executed."""
+    import inspect
+    import textwrap
+
+    src = inspect.getsource(ref_sim.LensSimulator.lstsq_simulate)
+    body = textwrap.dedent(src[src.index("        img = tf.where(tf.math.is_nan(img), tf.zeros_like(img), img)"):])
+    ns = {"tf": tf}
+    exec("def lstsq_rest(self, img, observed_image, err_map, return_stacked, return_coeffs):\n" + textwrap.indent(body, "    "), ns)
+    tf.set_float(dtype)
+    c = RC.lstsq_sersic_case(psf)
+    bs = 2
+    phys, sim = build(c, dtype, bs)
+    params = {g: [{k: T(v, dtype) for k, v in d.items()} for d in c["params"][g]] for g in c["params"]}
+    beta_x, beta_y = sim.beta(sim.img_X, sim.img_Y, params["lens_mass"])
+    nss = sim.wcs.n_x * sim.supersample
+    comps = []
+    for lm, p in zip(phys.lens_light, params["lens_light"]):
+        comps.append(lm.light(sim.img_X, sim.img_Y, **p))
+    for lm, p in zip(phys.source_light, params["source_light"]):
+        comps.append(lm.light(beta_x, beta_y, **p))
+    vals = torch.cat(comps, dim=0)                                                   # (D, N, bs)
+    img = torch.zeros((vals.shape[0], nss, nss, bs), dtype=vals.dtype)
+    img[:, sim.region[:, 0], sim.region[:, 1], :] = vals                             # what :183-203 meant
+    obs, err = T(c["observed"], dtype), T(c["err_map"], dtype)
+    out[f"lstsq/{tag}/stack"] = N(ns["lstsq_rest"](sim, img, obs, err, True, False))
+    out[f"lstsq/{tag}/coeffs"] = N(ns["lstsq_rest"](sim, img, obs, err, False, True))
+    out[f"lstsq/{tag}/image"] = N(ns["lstsq_rest"](sim, img, obs, err, False, False))
+
+
 def run_lstsq_tail(out, tag, dtype, psf):
-    """Execute the source lines of the reference's ``lstsq_simulate`` from ``W = (1 / err_map)...`` to its end
-    (``tf/simulator.py:231-240``) -- read from the reference file at run time -- on the oracle's component stack."""
+    """The tail of ``lstsq_simulate`` (``:231-240``: weights, normal equations, ``pinv(rcond=1e-6)``, recombination), read from the
+    reference file and executed on the ORACLE's component stack of a model the reference's own reshape cannot take (a 15-component
+    Shapelets set: ``self.depth`` counts profiles)."""
     import inspect
     import textwrap
     from types import SimpleNamespace
@@ -224,6 +259,7 @@ def generate():
     for tag, dtype in (("f32", torch.float32), ("f64", torch.float64)):
         run_profiles(out, tag, dtype)
         run_simulators(out, tag, dtype, psf, demo)
+        run_lstsq(out, tag, dtype, psf)
         run_lstsq_tail(out, tag, dtype, psf)
     tf.set_float(torch.float32)
     return out

@@ -268,6 +268,23 @@ def lstsq_tail_case(psf):
                 observed=obs, err_map=err)
 
 
+def lstsq_sersic_case(psf):
+    """The part of ``lstsq_simulate`` that executes in the reference when every linear component is a single-component profile
+    (``self.depth`` counts PROFILES, ``tf/simulator.py:57-59``, so a Shapelets set does not fit its reshape): SersicEllipse lens light
+    + two Sersic-type sources, ss = 2, PSF."""
+    model = dict(lens_mass=[("EPL", dict(niter=50)), ("Shear", {})], lens_light=[("SersicEllipse", dict(use_lstsq=True))],
+                 source_light=[("SersicEllipse", dict(use_lstsq=True)), ("Sersic", dict(use_lstsq=True))])
+    rng = np.random.default_rng(2011)
+    n = 30
+    p = _draw_model(model, 2, rng)
+    p["source_light"][1]["center_x"] = f32([0.3, -0.25])
+    p["source_light"][1]["R_sersic"] = f32([0.2, 0.35])
+    obs = f32(np.abs(rng.normal(0, 1, size=(n, n))) * 3 + 1)
+    err = f32(np.sqrt(0.2 ** 2 + np.clip(obs, 0, np.inf) / 100.0))
+    return dict(model=model, sim=dict(delta_pix=0.13, num_pix=n, supersample=2, kernel=f32(psf[4:9, 4:9]), pix_region=None), params=p,
+                observed=obs, err_map=err)
+
+
 def c4_catalogue(G=30, seed=7):
     """``gigalens_b200.workloads.cluster_catalogue`` (SURVEY 8d C4), restated here so that this module stays import-free;
     tests/test_reference_golden.py asserts the two are identical."""

@@ -149,3 +149,30 @@ def test_cuda_simulator_and_likelihood_match_the_executed_reference(key):
                 continue
             pert = np.zeros(bs) if o_g[j] is None else o_g[j].numpy()
             assert_parity(gpos[row[k]], G("pos_grad", "f32")[j], G("pos_grad", "f64")[j], 1e-4, f"{key} positions grad {k}", pert)
+
+
+def test_cuda_lstsq_simulate_matches_the_executed_reference():
+    """lstsq_simulate through the C ABI against the reference's own simulator object, beta, light calls and source lines :204-240
+    (tests/golden/make_reference_golden.py run_lstsq): component stack, amplitudes and recombined image."""
+    c, pm, osim_p, params_p, obs, err = R.lstsq_oracle(torch.float64)
+    s = c["sim"]
+    n, bs = s["num_pix"], 2
+    sim = LensSimulator(pm, SimulatorConfig(delta_pix=s["delta_pix"], num_pix=n, supersample=s["supersample"],
+                                            kernel=s["kernel"].astype(np.float32)), bs=bs)
+    cm = sim.compiled
+    params = cm.unflatten(torch.as_tensor(_matrix(cm, c["params"], bs), device="cuda"))
+    o, e = c["observed"].astype(np.float32), c["err_map"].astype(np.float32)
+    stack = sim.lstsq_simulate(params, o, e, return_stacked=True).cpu().numpy()
+    coef = sim.lstsq_simulate(params, o, e, return_coeffs=True).cpu().numpy()
+    img = sim.lstsq_simulate(params, o, e).cpu().numpy().reshape(bs, n, n)
+    pert = {g: [{k: torch.as_tensor(common.ulp_perturb(v.numpy(), seed=5 + i)) for k, v in d.items()} for i, d in enumerate(params_p[g])]
+            for g in params_p}
+    with torch.no_grad():
+        sp = osim_p.lstsq_simulate(pert, obs, err, return_stacked=True).numpy()
+        cp = osim_p.lstsq_simulate(pert, obs, err, return_coeffs=True).numpy()
+        ip = osim_p.lstsq_simulate(pert, obs, err).numpy().reshape(bs, n, n)
+    G = lambda q, t: GOLD[f"lstsq/{t}/{q}"]   # noqa: E731
+    assert stack.shape == G("stack", "f64").shape
+    assert_parity(stack, G("stack", "f32"), G("stack", "f64"), 1e-5, "lstsq stack", sp, axis=(1, 2, 3))
+    assert_parity(coef, G("coeffs", "f32"), G("coeffs", "f64"), 1e-4, "lstsq coefficients", cp, axis=1)
+    assert_parity(img, G("image", "f32").reshape(bs, n, n), G("image", "f64").reshape(bs, n, n), 1e-5, "lstsq image", ip, axis=(1, 2))

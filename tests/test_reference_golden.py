@@ -145,18 +145,31 @@ def test_oracle_simulator_and_likelihood_match_the_executed_reference(key, tag):
             close(a, r, 1000 * tol, f"positions grad {grp}[{i}].{k}")
 
 
-@pytest.mark.parametrize("tag", ["f32", "f64"])
-def test_oracle_lstsq_tail_matches_the_executed_reference_lines(tag):
-    """tf/simulator.py:231-240 (weights, normal equations, pinv(rcond=1e-6), recombination), executed from the reference
-    file on the oracle's component stack, against the oracle's own tail."""
-    dt = DT[tag]
-    c = RC.lstsq_tail_case(PSF)
+def lstsq_oracle(dt, which="sersic"):
+    c = RC.lstsq_sersic_case(PSF) if which == "sersic" else RC.lstsq_tail_case(PSF)
     pm = common.spec_model(c["model"])
     s = c["sim"]
     osim = OracleSimulator(common.to_oracle_model(pm, dt), s["delta_pix"], s["num_pix"], s["supersample"], kernel=s["kernel"], bs=2, dtype=dt)
     params = {g: [{k: T(v, dt) for k, v in d.items()} for d in c["params"][g]] for g in c["params"]}
-    obs, err = T(c["observed"], dt), T(c["err_map"], dt)
-    # same operations on the same stack and the same SVD: measured bit-identical in both precisions
+    return c, pm, osim, params, T(c["observed"], dt), T(c["err_map"], dt)
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+def test_oracle_lstsq_simulate_matches_the_executed_reference(tag):
+    """lstsq_simulate with the reference's own simulator object, beta, light calls and source lines :204-240 (depthwise conv, pooling,
+    NaN scrubs, weights, normal equations, pinv(rcond=1e-6), recombination); only the broken scatter of :183-203 is restated in the
+    generator.  Supersampled (ss = 2), PSF, three single-component linear profiles (what the reference's reshape can take)."""
+    c, pm, osim, params, obs, err = lstsq_oracle(DT[tag])
+    close(osim.lstsq_simulate(params, obs, err, return_stacked=True).numpy(), GOLD[f"lstsq/{tag}/stack"], TOL[tag], "stack")
+    close(osim.lstsq_simulate(params, obs, err, return_coeffs=True).numpy(), GOLD[f"lstsq/{tag}/coeffs"], {"f32": 1e-4, "f64": 1e-10}[tag], "coeffs")
+    close(osim.lstsq_simulate(params, obs, err).numpy(), GOLD[f"lstsq/{tag}/image"], {"f32": 1e-5, "f64": 1e-11}[tag], "image")
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+def test_oracle_lstsq_tail_matches_the_executed_reference_lines(tag):
+    """tf/simulator.py:231-240 (weights, normal equations, pinv(rcond=1e-6), recombination), executed from the reference file on the
+    oracle's component stack of a model with a 15-component Shapelets set, against the oracle's own tail (measured bit-identical)."""
+    c, pm, osim, params, obs, err = lstsq_oracle(DT[tag], "shapelets")
     close(osim.lstsq_simulate(params, obs, err, return_coeffs=True).numpy(), GOLD[f"lstsq_tail/{tag}/coeffs"], TOL[tag], "coeffs")
     close(osim.lstsq_simulate(params, obs, err).numpy(), GOLD[f"lstsq_tail/{tag}/image"], TOL[tag], "image")
 
