@@ -154,6 +154,10 @@ def linspace(start, stop, num):
 
 
 def _shape_tuple(shape):
+    if isinstance(shape, (builtins.int, _np.integer)):      # tf.zeros(n)
+        return (builtins.int(shape),)
+    if isinstance(shape, _torch.Tensor) and shape.dim() == 0:
+        return (builtins.int(shape),)
     if isinstance(shape, _torch.Tensor):
         return tuple(int(s) for s in shape.tolist())
     return tuple(int(s) for s in shape)

@@ -181,6 +181,20 @@ def run_simulators(out, tag, dtype, psf, demo):
             out[f"{pre}/pos_loglike"], out[f"{pre}/pos_red_chi2"] = N(llp), N(chi2p)
             gp = torch.autograd.grad(llp.sum(), leaves, allow_unused=True)
             out[f"{pre}/pos_grad"] = np.stack([N(torch.zeros(bs, dtype=dtype) if v is None else v) for v in gp])
+            # ForwardProbModel.log_prob / log_like (tf/model.py:126-181): how the two likelihood terms, the reduced chi^2 average over
+            # the included terms and the prior are combined.  The TFP objects are replaced by stand-ins returning fixed vectors (their
+            # arithmetic is not what is pinned here); z only supplies the batch size.
+            from types import SimpleNamespace
+            lp = T(RC.FAKE_LOG_PRIOR[:bs], dtype)
+            fldj = T(RC.FAKE_FLDJ[:bs], dtype)
+            pm.bij = SimpleNamespace(forward=lambda z: params)
+            pm.pack_bij = SimpleNamespace(forward=lambda z: z)
+            pm.unconstraining_bij = SimpleNamespace(forward_log_det_jacobian=lambda x: fldj)
+            pm.prior = SimpleNamespace(log_prob=lambda p: lp)
+            z = torch.zeros((bs, len(leaves)), dtype=dtype)
+            logp, chi = pm.log_prob(sim, z)
+            out[f"{pre}/logprob_total"], out[f"{pre}/red_chi2_total"] = N(logp), N(chi)
+            out[f"{pre}/loglike_total"] = N(pm.log_like(sim, z))
 
 
 def run_lstsq(out, tag, dtype, psf):

@@ -37,6 +37,11 @@ PARAMS = {   # parameter names per class, in the reference's ``_params`` order (
 }
 
 
+# stand-in values of prior.log_prob(params) and the bijector's forward_log_det_jacobian in the executed ForwardProbModel.log_prob
+FAKE_LOG_PRIOR = np.array([0.5, -1.25, 3.0, -0.75])
+FAKE_FLDJ = np.array([0.25, 2.0, -1.5, 0.125])
+
+
 def f32(v):
     return np.asarray(np.asarray(v, dtype=np.float32), dtype=np.float64)
 

@@ -149,6 +149,15 @@ def test_cuda_simulator_and_likelihood_match_the_executed_reference(key):
                 continue
             pert = np.zeros(bs) if o_g[j] is None else o_g[j].numpy()
             assert_parity(gpos[row[k]], G("pos_grad", "f32")[j], G("pos_grad", "f64")[j], 1e-4, f"{key} positions grad {k}", pert)
+        # both terms together: log-likes add, the reduced chi^2 is the mean of the included terms (tf/model.py:150-163)
+        pboth = ForwardProbModel({"lens_mass": []}, c["observed"].astype(np.float32), centroids_x=f(cen["x"]), centroids_y=f(cen["y"]),
+                                 centroids_errors_x=f(cen["ex"]), centroids_errors_y=f(cen["ey"]), include_pixels=True, **kw)
+        llb, chib, _ = (t.cpu().numpy() for t in pboth.loglike_and_grad(sim, dev))
+        o_llb, o_chib = opm_p._stats(osim_p, params_p)
+        assert_parity(llb[:, None], G("loglike_total", "f32")[:, None], G("loglike_total", "f64")[:, None], 1e-5, f"{key} log-like (both terms)",
+                      o_llb.detach().numpy()[:, None], axis=1)
+        assert_parity(chib[:, None], G("red_chi2_total", "f32")[:, None], G("red_chi2_total", "f64")[:, None], 1e-5,
+                      f"{key} red chi2 (mean of both terms)", o_chib.detach().numpy()[:, None], axis=1)
 
 
 def test_cuda_lstsq_simulate_matches_the_executed_reference():

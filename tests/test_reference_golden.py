@@ -143,6 +143,12 @@ def test_oracle_simulator_and_likelihood_match_the_executed_reference(key, tag):
         gp = np.stack([np.zeros(bs) if v is None else v.numpy() for v in gp])
         for (grp, i, k), a, r in zip(RC.grad_keys(c["params"]), gp, GOLD[f"{pre}/pos_grad"]):
             close(a, r, 1000 * tol, f"positions grad {grp}[{i}].{k}")
+        # the combination of the terms (tf/model.py:126-181) with stand-in prior / bijector values
+        ll_all, rc_all = opm._stats(osim, params)
+        prior = T(RC.FAKE_LOG_PRIOR[:bs] + RC.FAKE_FLDJ[:bs], dt)
+        close((ll_all + prior).detach().numpy(), GOLD[f"{pre}/logprob_total"], 100 * tol, "log_prob (pixels + positions + prior)")
+        close(ll_all.detach().numpy(), GOLD[f"{pre}/loglike_total"], 100 * tol, "log_like (pixels + positions)")
+        close(rc_all.detach().numpy(), GOLD[f"{pre}/red_chi2_total"], 100 * tol, "red chi2 averaged over the included terms")
 
 
 def lstsq_oracle(dt, which="sersic"):
