@@ -59,6 +59,9 @@ def test_alias_modules_export_the_cuda_classes():
                        (sis, ("SIS",)), (scaling_relation, ("ScalingRelation",)), (dpie_subhalo, ("DPIESubhalo",)), (shapelets, ("Shapelets",))):
         for n in names:
             assert hasattr(mod, n)
+    import gigalens_b200.profiles.light.sersic as b_sersic
+    assert sersic.CoreSersic is b_sersic.CoreSersic and sersic.CoreSersic._params == [
+        "R_sersic", "n_sersic", "Rb", "alpha", "gamma", "e1", "e2", "center_x", "center_y"]   # tf/profiles/light/sersic.py:83-97
 
 
 def test_reference_fixture_spec_builds_and_bijector_round_trips():
